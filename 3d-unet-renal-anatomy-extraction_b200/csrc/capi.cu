@@ -1,0 +1,207 @@
+// C-ABI of libunet3d_b200.so (declared in include/unet3d_b200.h).  Thin: argument checks,
+// TMA tensor-map encoding, launcher calls.  No device allocation, no synchronisation.
+#include "../../include/unet3d_b200.h"
+#include "conv_gemm.cuh"
+#include "wgrad_gemm.cuh"
+#include "kernels.cuh"
+
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+int check(int rc, const char* what) {
+  if (rc == U3D_OK) return rc;
+  if (rc == U3D_ERR_CUDA) {
+    cudaError_t e = cudaGetLastError();
+    snprintf(g_err, sizeof(g_err), "%s: CUDA error: %s", what, cudaGetErrorString(e));
+  } else {
+    snprintf(g_err, sizeof(g_err), "%s: error code %d (invalid / unsupported arguments)", what, rc);
+  }
+  return rc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 5-D (C, W, H, D, N) bf16 view; box = (8 channels, bw, bh, 1, 1); OOB reads give zeros (conv padding).
+int encode_src(CUtensorMap* m, const unet3d_src& s, int bw, int bh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(U3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found%s");
+  if (s.ptr == nullptr || (reinterpret_cast<uintptr_t>(s.ptr) & 15) || s.C % 8 || (s.sW & 15) || (s.sH & 15) ||
+      (s.sD & 15) || (s.sN & 15))
+    return fail(U3D_ERR_INVALID, "source view must be 16-byte aligned with C %% 8 == 0%s");
+  cuuint64_t dims[5] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.D, (cuuint64_t)s.N};
+  cuuint64_t strides[4] = {(cuuint64_t)s.sW, (cuuint64_t)s.sH, (cuuint64_t)s.sD, (cuuint64_t)s.sN};
+  cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(s.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(U3D_ERR_CUDA, "cuTensorMapEncodeTiled failed%s (CUresult %lld)", "", (long long)r);
+  return U3D_OK;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms > 0) return g_num_sms;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  g_num_sms = n;
+  return n;
+}
+
+}  // namespace
+
+using namespace u3d;
+
+extern "C" {
+
+const char* unet3d_version(void) { return "unet3d_b200 0.1 (sm_100a)"; }
+const char* unet3d_last_error_string(void) { return g_err; }
+int unet3d_num_sms(void) { return num_sms(); }
+
+size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk) { return conv_gemm_smem_bytes(Dt, G, nblk); }
+
+int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
+  if (!a || a->n_src < 1 || a->n_src > CG_MAX_MAPS || !a->tab || !a->w || !a->out || !a->err)
+    return fail(U3D_ERR_INVALID, "conv_gemm: null / out-of-range argument%s");
+  const int sms = num_sms();
+  if (sms <= 0) return fail(U3D_ERR_CUDA, "conv_gemm: no CUDA device%s");
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < CG_MAX_MAPS; ++i) {
+    const unet3d_src& s = a->src[i < a->n_src ? i : 0];
+    int rc = encode_src(&p.amap[i], s, CG_WB, CG_HB);
+    if (rc != U3D_OK) return rc;
+  }
+  p.tab = a->tab;
+  p.w = reinterpret_cast<const bf16*>(a->w);
+  p.out = reinterpret_cast<bf16*>(a->out);
+  p.out2 = reinterpret_cast<bf16*>(a->out2);
+  p.addend2 = reinterpret_cast<const bf16*>(a->addend2);
+  p.bias = a->bias;
+  p.addend = reinterpret_cast<const bf16*>(a->addend);
+  p.stats = a->stats;
+  p.err = a->err;
+  p.N = a->N; p.D = a->D; p.H = a->H; p.W = a->W;
+  p.Dt = a->Dt;
+  p.tiles_h = (a->H + CG_HT - 1) / CG_HT;
+  p.tiles_w = (a->W + CG_WT - 1) / CG_WT;
+  p.segs_d = (a->D + a->Dt - 1) / (a->Dt > 0 ? a->Dt : 1);
+  p.n_nblk = a->n_nblk; p.nblk = a->nblk; p.G = a->G; p.n_cg = a->n_cg; p.n_taps = a->n_taps;
+  p.out_sN = a->out_sN; p.out_sD = a->out_sD; p.out_sH = a->out_sH; p.out_sW = a->out_sW;
+  p.out_C = a->out_C; p.stats_C = a->stats_C; p.omul = a->omul;
+  p.zD = a->zD; p.zH = a->zH; p.zW = a->zW;
+  p.n_work = a->n_nblk * a->N * p.segs_d * p.tiles_h * p.tiles_w;
+  return check(conv_gemm_launch(p, sms, reinterpret_cast<cudaStream_t>(stream)), "conv_gemm");
+}
+
+int unet3d_wgrad_gemm(const unet3d_wgrad_args* a, void* stream) {
+  if (!a || a->n_src < 1 || a->n_src > WG_MAX_MAPS || !a->tab || !a->dw || !a->err || a->n_jobs < 1 || a->split < 1)
+    return fail(U3D_ERR_INVALID, "wgrad_gemm: null / out-of-range argument%s");
+  const int sms = num_sms();
+  if (sms <= 0) return fail(U3D_ERR_CUDA, "wgrad_gemm: no CUDA device%s");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < WG_MAX_MAPS; ++i) {
+    const unet3d_src& s = a->src[i < a->n_src ? i : 0];
+    int rc = encode_src(&p.map[i], s, a->box_w[i < a->n_src ? i : 0], a->box_h[i < a->n_src ? i : 0]);
+    if (rc != U3D_OK) return rc;
+  }
+  p.tab = a->tab;
+  p.dw = a->dw;
+  p.err = a->err;
+  p.N = a->N; p.D = a->D; p.H = a->H; p.W = a->W;
+  p.tiles_h = (a->H + CG_HT - 1) / CG_HT;
+  p.tiles_w = (a->W + CG_WT - 1) / CG_WT;
+  p.n_jobs = a->n_jobs;
+  p.job_stride = a->job_stride;
+  p.split = a->split;
+  return check(wgrad_gemm_launch(p, reinterpret_cast<cudaStream_t>(stream)), "wgrad_gemm");
+}
+
+int unet3d_in_finalize(const double* stats, const float* drop_scale, float* table, int NC, double count, float eps,
+                       void* stream) {
+  return check(in_finalize(stats, drop_scale, table, NC, count, eps, (cudaStream_t)stream), "in_finalize");
+}
+int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, int N, long long V, int Cp,
+                    void* stream) {
+  return check(in_apply((const bf16*)y, (const bf16*)skip, (bf16*)out, table, N, V, Cp, num_sms(), (cudaStream_t)stream),
+               "in_apply");
+}
+int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, void* g,
+                         const float* table, double* sums, int N, long long V, int Cp, void* stream) {
+  return check(in_bwd_reduce((const bf16*)dout, (const bf16*)dout2, (const bf16*)out, (const bf16*)y, (bf16*)g, table,
+                             sums, N, V, Cp, num_sms(), (cudaStream_t)stream),
+               "in_bwd_reduce");
+}
+int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums, double* dsum,
+                        int N, int D, int H, int W, int Cp, int zero_last, void* stream) {
+  return check(in_bwd_apply((const bf16*)g, (const bf16*)y, (bf16*)dy, table, sums, dsum, N, D, H, W, Cp, zero_last,
+                            num_sms(), (cudaStream_t)stream),
+               "in_bwd_apply");
+}
+int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* stream) {
+  return check(channel_sum((const bf16*)x, dsum, NV, Cp, num_sms(), (cudaStream_t)stream), "channel_sum");
+}
+int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, int N, int D, int H, int W, int Cp,
+                    void* stream) {
+  return check(stem_fwd(x, w, b, (bf16*)out, N, D, H, W, Cp, num_sms(), (cudaStream_t)stream), "stem_fwd");
+}
+int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, int Cp, void* stream) {
+  return check(stem_wgrad(x, (const bf16*)dy, dw, N, D, H, W, Cp, num_sms(), (cudaStream_t)stream), "stem_wgrad");
+}
+int unet3d_head_fwd(const void* a, const float* w, const float* b, float* logits, int K, int N, long long V, int Cp,
+                    void* stream) {
+  return check(head_fwd((const bf16*)a, w, b, logits, K, N, V, Cp, num_sms(), (cudaStream_t)stream), "head_fwd");
+}
+int unet3d_head_bwd(const float* dlogits, const void* a, const float* w, void* da, float* dw, int K, int N,
+                    long long V, int Cp, void* stream) {
+  return check(head_bwd(dlogits, (const bf16*)a, w, (bf16*)da, dw, K, N, V, Cp, num_sms(), (cudaStream_t)stream),
+               "head_bwd");
+}
+int unet3d_loss_fwd(const float* logits, const long long* target, double* sums, int K, int N, long long V,
+                    float gamma, void* stream) {
+  return check(loss_fwd(logits, target, sums, K, N, V, gamma, num_sms(), (cudaStream_t)stream), "loss_fwd");
+}
+int unet3d_loss_bwd(const float* logits, const long long* target, const float* coef, const float* grad_scale,
+                    float* dlogits, int K, int N, long long V, float gamma, int use_focal, void* stream) {
+  return check(loss_bwd(logits, target, coef, grad_scale, dlogits, K, N, V, gamma, use_focal, num_sms(),
+                        (cudaStream_t)stream),
+               "loss_bwd");
+}
+int unet3d_sw_accumulate(const float* logits, const float* window, float* result, float* weight, int K, int px,
+                         int py, int pz, int x0, int y0, int z0, int X, int Y, int Z, void* stream) {
+  return check(sw_accumulate(logits, window, result, weight, K, px, py, pz, x0, y0, z0, X, Y, Z, num_sms(),
+                             (cudaStream_t)stream),
+               "sw_accumulate");
+}
+int unet3d_sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K,
+                       long long XYZ, void* stream) {
+  return check(sw_finalize(result, weight, labels, probs, K, XYZ, num_sms(), (cudaStream_t)stream), "sw_finalize");
+}
+
+}  // extern "C"

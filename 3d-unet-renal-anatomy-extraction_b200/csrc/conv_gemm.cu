@@ -1,0 +1,346 @@
+// tcgen05 shifted-GEMM convolution kernel for sm_100a (see conv_gemm.cuh for the formulation).
+//
+// Replaces the cuDNN calls behind nn.Conv3d / nn.ConvTranspose3d forward and their data gradients
+// (reference call sites: network.py:394-395,403,411,415,541,545 and 312-314).
+//
+// Roles (warp-specialised, persistent over work items = (output tile, N block)):
+//   warp 0  : A producer  - TMA 5-D tiled loads of (18 x 10 voxel) x 8-channel boxes, OOB zero fill = padding
+//   warp 1  : W producer  - cp.async.bulk of pre-packed weight tiles, 6-deep ring
+//   warp 2  : MMA issuer  - tcgen05.mma kind::f16, M=128 (16h x 8w voxels), N=nblk, K=16; accumulators in TMEM,
+//             double buffered (2 x 256 columns) so the epilogue of item i overlaps the MMAs of item i+1
+//   warps 3-6: epilogue   - tcgen05.ld, + bias / + addend, zero planes, per-(n,c) sum / sum^2 for
+//             InstanceNorm (warp butterfly, fp64 atomics once per sample change), bf16 NDHWC stores
+#include "conv_gemm.cuh"
+
+namespace u3d {
+
+namespace {
+
+struct SmemCtl {
+  uint64_t a_full[2], a_empty[2];
+  uint64_t w_full[CG_W_STAGES], w_empty[CG_W_STAGES];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  int abort_flag;
+};
+
+// column sums over the 32 lanes of a warp: in v[j] = value of column j for this lane's row;
+// returns the sum of column `lane`.  31 shuffles (recursive halving).
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      float keep = up ? v[j + half] : v[j];
+      float send = up ? v[j] : v[j + half];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* smem = smem_raw + pad;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int planes = p.Dt + 2;
+  const uint32_t plane_pitch = (uint32_t)p.G * CG_CHUNK_PITCH;
+  const uint32_t slab_bytes = (uint32_t)planes * plane_pitch;
+  const uint32_t wtile_bytes = (uint32_t)p.G * p.nblk * 16;
+  const uint32_t slab0 = smem_u32(smem) + 1024;
+  const uint32_t wring0 = slab0 + 2 * slab_bytes;
+
+  const int* tab_map = p.tab;
+  const int* tab_ch = p.tab + p.n_cg;
+  const int* tab_shift = p.tab + 2 * p.n_cg;
+  const int* tab_mask = tab_shift + p.n_taps;
+  const int* tab_wbase = tab_mask + p.n_nblk * p.n_cg;
+  const int* tab_coff = tab_wbase + p.n_nblk;
+  const int* tab_ooff = tab_coff + p.n_nblk;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&ctl->a_full[i]), 1);
+      mbar_init(smem_u32(&ctl->a_empty[i]), 1);
+      mbar_init(smem_u32(&ctl->acc_full[i]), 1);
+      mbar_init(smem_u32(&ctl->acc_empty[i]), 4);
+    }
+    for (int i = 0; i < CG_W_STAGES; ++i) {
+      mbar_init(smem_u32(&ctl->w_full[i]), 1);
+      mbar_init(smem_u32(&ctl->w_empty[i]), 1);
+    }
+    ctl->abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&ctl->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  volatile int* abort_flag = &ctl->abort_flag;
+
+  const int n_tiles = p.N * p.segs_d * p.tiles_h * p.tiles_w;
+
+  if (warp == 0) {
+    // ================= A producer =================
+    if (lane == 0) {
+      for (int i = 0; i < CG_MAX_MAPS; ++i) tma_prefetch_desc(&p.amap[i]);
+      uint32_t a_it = 0;
+      bool ok = true;
+      for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
+        const int nb = item / n_tiles;
+        int t = item - nb * n_tiles;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int seg = t % p.segs_d;
+        const int n = t / p.segs_d;
+        const int w0 = tw * CG_WT - 1, h0 = th * CG_HT - 1, d0 = seg * p.Dt - 1;
+        for (int cg = 0; cg < p.n_cg; ++cg) {
+          if (__ldg(&tab_mask[nb * p.n_cg + cg]) == 0) continue;
+          const uint32_t st = a_it & 1, ph = (a_it >> 1) & 1;
+          if (!mbar_wait(smem_u32(&ctl->a_empty[st]), ph ^ 1, abort_flag, p.err, 101)) { ok = false; break; }
+          const uint32_t full = smem_u32(&ctl->a_full[st]);
+          mbar_expect_tx(full, (uint32_t)planes * p.G * CG_BOX_BYTES);
+          const CUtensorMap* m = &p.amap[__ldg(&tab_map[cg])];
+          const int ch0 = __ldg(&tab_ch[cg]);
+          uint32_t dst = slab0 + st * slab_bytes;
+          for (int pl = 0; pl < planes; ++pl)
+            for (int g = 0; g < p.G; ++g, dst += CG_CHUNK_PITCH)
+              tma_load_5d(dst, m, full, ch0 + g * 8, w0, h0, d0 + pl, n);
+          ++a_it;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= W producer =================
+    if (lane == 0) {
+      uint32_t w_it = 0;
+      bool ok = true;
+      for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
+        const int nb = item / n_tiles;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)__ldg(&tab_wbase[nb]) * wtile_bytes;
+        for (int cg = 0; cg < p.n_cg && ok; ++cg) {
+          uint32_t mask = (uint32_t)__ldg(&tab_mask[nb * p.n_cg + cg]);
+          while (mask) {
+            mask &= mask - 1;
+            const uint32_t st = w_it % CG_W_STAGES, ph = (w_it / CG_W_STAGES) & 1;
+            if (!mbar_wait(smem_u32(&ctl->w_empty[st]), ph ^ 1, abort_flag, p.err, 102)) { ok = false; break; }
+            const uint32_t full = smem_u32(&ctl->w_full[st]);
+            mbar_expect_tx(full, wtile_bytes);
+            bulk_load(wring0 + st * wtile_bytes, src, wtile_bytes, full);
+            src += wtile_bytes;
+            ++w_it;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.nblk, 0, 0);
+      uint32_t a_it = 0, w_it = 0, acc_it = 0;
+      bool ok = true;
+      for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
+        const int nb = item / n_tiles;
+        const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+        if (!mbar_wait(smem_u32(&ctl->acc_empty[buf]), aph ^ 1, abort_flag, p.err, 103)) break;
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + buf * 256;
+        bool fresh = true;
+        for (int cg = 0; cg < p.n_cg && ok; ++cg) {
+          uint32_t mask = (uint32_t)__ldg(&tab_mask[nb * p.n_cg + cg]);
+          if (mask == 0) continue;
+          const uint32_t ast = a_it & 1, aphase = (a_it >> 1) & 1;
+          if (!mbar_wait(smem_u32(&ctl->a_full[ast]), aphase, abort_flag, p.err, 104)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t slab = slab0 + ast * slab_bytes;
+          while (mask) {
+            const int tap = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t wst = w_it % CG_W_STAGES, wph = (w_it / CG_W_STAGES) & 1;
+            if (!mbar_wait(smem_u32(&ctl->w_full[wst]), wph, abort_flag, p.err, 105)) { ok = false; break; }
+            tc_fence_after();
+            const int sh = __ldg(&tab_shift[tap]);
+            const int sd = sh & 0xff, shh = (sh >> 8) & 0xff, sw = (sh >> 16) & 0xff;
+            const uint32_t a_tap = slab + (uint32_t)sd * plane_pitch + (uint32_t)(shh * CG_WB + sw) * 16;
+            const uint32_t b_tap = wring0 + wst * wtile_bytes;
+            for (int d = 0; d < p.Dt; ++d) {
+              for (int kk = 0; kk < p.G / 2; ++kk) {
+                const uint64_t adesc =
+                    umma_desc(a_tap + (uint32_t)d * plane_pitch + (uint32_t)(2 * kk) * CG_CHUNK_PITCH,
+                              CG_CHUNK_PITCH, CG_WB * 16);
+                const uint64_t bdesc = umma_desc(b_tap + (uint32_t)(2 * kk) * p.nblk * 16, (uint32_t)p.nblk * 16, 128);
+                tc_mma_bf16(acc0 + (uint32_t)d * p.nblk, adesc, bdesc, idesc, (fresh && kk == 0) ? 0u : 1u);
+              }
+            }
+            tc_commit(smem_u32(&ctl->w_empty[wst]));
+            ++w_it;
+            fresh = false;
+          }
+          if (!ok) break;
+          tc_commit(smem_u32(&ctl->a_empty[ast]));
+          ++a_it;
+        }
+        if (!ok) break;
+        tc_commit(smem_u32(&ctl->acc_full[buf]));
+        ++acc_it;
+      }
+    }
+  } else {
+    // ================= epilogue (warps 3..6) =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int line = row >> 3, wi = row & 7;
+    const int n_cc = p.nblk / 32;
+    float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+    int cur_n = -1, cur_nb = -1;
+    uint32_t acc_it = 0;
+    auto flush_stats = [&]() {
+      if (p.stats == nullptr || cur_n < 0) return;
+      const int coff = __ldg(&tab_coff[cur_nb]) & 0x3fffffff;
+      for (int cc = 0; cc < n_cc; ++cc) {
+        const int c = coff + cc * 32 + lane;
+        if (c < p.stats_C) {
+          double* s = p.stats + ((size_t)cur_n * p.stats_C + c) * 2;
+          atomicAdd(s, (double)ssum[cc]);
+          atomicAdd(s + 1, (double)ssq[cc]);
+        }
+        ssum[cc] = 0.f;
+        ssq[cc] = 0.f;
+      }
+    };
+    for (int item = blockIdx.x; item < p.n_work; item += gridDim.x) {
+      const int nb = item / n_tiles;
+      int t = item - nb * n_tiles;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int seg = t % p.segs_d;
+      const int n = t / p.segs_d;
+      if (n != cur_n || nb != cur_nb) {
+        flush_stats();
+        cur_n = n;
+        cur_nb = nb;
+      }
+      const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+      if (!mbar_wait(smem_u32(&ctl->acc_full[buf]), aph, abort_flag, p.err, 106)) break;
+      tc_fence_after();
+      const int coff_raw = __ldg(&tab_coff[nb]);
+      const int coff = coff_raw & 0x3fffffff;
+      bf16* const outp = (coff_raw >> 30) ? p.out2 : p.out;
+      const bf16* const addp = (coff_raw >> 30) ? p.addend2 : p.addend;
+      const int ooff = __ldg(&tab_ooff[nb]);
+      const int gh = th * CG_HT + line, gw = tw * CG_WT + wi;
+      const int oh = gh * p.omul + ((ooff >> 8) & 0xff), ow = gw * p.omul + ((ooff >> 16) & 0xff);
+      const bool hw_ok = gh < p.H && gw < p.W;
+      for (int d = 0; d < p.Dt; ++d) {
+        const int gd = seg * p.Dt + d;
+        const int od = gd * p.omul + (ooff & 0xff);
+        const bool valid = hw_ok && gd < p.D;
+        const bool zero = (od == p.zD) || (oh == p.zH) || (ow == p.zW);
+        const long long off = (long long)n * p.out_sN + (long long)od * p.out_sD + (long long)oh * p.out_sH +
+                              (long long)ow * p.out_sW + coff;
+        for (int cc = 0; cc < n_cc; ++cc) {
+          uint32_t raw[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)d * p.nblk + cc * 32, raw);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (p.bias != nullptr) {
+            const float* b = p.bias + nb * p.nblk + cc * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(&b[j]);
+          }
+          const int c0 = coff + cc * 32;
+          if (addp != nullptr && valid) {
+            const uint4* ap = reinterpret_cast<const uint4*>(addp + off + cc * 32);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (c0 + k4 * 8 < p.out_C) {
+                const uint4 u = __ldg(ap + k4);
+                float2 f;
+                f = unpack_bf16x2(u.x); v[k4 * 8 + 0] += f.x; v[k4 * 8 + 1] += f.y;
+                f = unpack_bf16x2(u.y); v[k4 * 8 + 2] += f.x; v[k4 * 8 + 3] += f.y;
+                f = unpack_bf16x2(u.z); v[k4 * 8 + 4] += f.x; v[k4 * 8 + 5] += f.y;
+                f = unpack_bf16x2(u.w); v[k4 * 8 + 6] += f.x; v[k4 * 8 + 7] += f.y;
+              }
+            }
+          }
+          if (!valid || zero) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (valid) {
+            uint4* op = reinterpret_cast<uint4*>(outp + off + cc * 32);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (c0 + k4 * 8 < p.out_C) {
+                uint4 u;
+                u.x = pack_bf16x2(v[k4 * 8 + 0], v[k4 * 8 + 1]);
+                u.y = pack_bf16x2(v[k4 * 8 + 2], v[k4 * 8 + 3]);
+                u.z = pack_bf16x2(v[k4 * 8 + 4], v[k4 * 8 + 5]);
+                u.w = pack_bf16x2(v[k4 * 8 + 6], v[k4 * 8 + 7]);
+                op[k4] = u;
+              }
+            }
+          }
+          if (p.stats != nullptr) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            ssum[cc] += warp_colsum32(v, lane);
+            ssq[cc] += warp_colsum32(sq, lane);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty[buf]));
+      ++acc_it;
+    }
+    flush_stats();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+size_t conv_gemm_smem_bytes(int Dt, int G, int nblk) {
+  return 1024 /*align slack*/ + 1024 /*ctl*/ + 2 * (size_t)(Dt + 2) * G * CG_CHUNK_PITCH +
+         (size_t)CG_W_STAGES * G * nblk * 16;
+}
+
+int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  if (p.G < 2 || (p.G & 1) || p.nblk % 32 != 0 || p.nblk > 128 || p.Dt < 1 || p.Dt * p.nblk > 256 ||
+      p.n_taps < 1 || p.n_taps > 32 || p.n_work < 1)
+    return U3D_ERR_INVALID;
+  const size_t smem = conv_gemm_smem_bytes(p.Dt, p.G, p.nblk);
+  if (smem > 227 * 1024) return U3D_ERR_INVALID;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return U3D_ERR_CUDA;
+    attr_set = true;
+  }
+  const int grid = p.n_work < num_sms ? p.n_work : num_sms;
+  conv_gemm_kernel<<<grid, CG_THREADS, smem, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? U3D_OK : U3D_ERR_CUDA;
+}
+
+}  // namespace u3d

@@ -1,0 +1,62 @@
+// Parameters of the tcgen05 "shifted GEMM" convolution kernel (conv_gemm.cu).
+//
+// One kernel covers every dense contraction of the U-Net forward / data-gradient path
+// (network.py:394-403 Conv3d k3/k1, stride 1/2; network.py:312-314 ConvTranspose3d + pad; and the
+// autograd data gradients of all of them) by expressing each as
+//
+//     out[v, n] = sum_{tap, c} A[v + shift(tap), c] * Wp[tap, c, n]
+//
+// on a "tile grid" (the output grid for ordinary convs, the coarse grid for strided / transposed
+// ones).  The halo brick of A lives in shared memory once and every tap is just a different start
+// address of the UMMA shared-memory descriptor (no-swizzle K-major layout), so an A byte is read
+// from L2 ~1.4-1.9x instead of 27x.
+#pragma once
+#include "common.cuh"
+
+namespace u3d {
+
+constexpr int CG_HT = 16;            // output tile: 16 (h) x 8 (w) voxels = the 128 rows of one UMMA
+constexpr int CG_WT = 8;
+constexpr int CG_HB = CG_HT + 2;     // brick with a 1-voxel halo on both sides
+constexpr int CG_WB = CG_WT + 2;
+constexpr int CG_BOX_BYTES = CG_HB * CG_WB * 16;     // one (plane, 8-channel chunk) TMA box = 2880 B
+constexpr int CG_CHUNK_PITCH = 2944;                 // padded to 128 B (TMA smem destination alignment)
+constexpr int CG_W_STAGES = 6;
+constexpr int CG_THREADS = 224;      // warp0 A-TMA, warp1 W-TMA, warp2 MMA (+TMEM alloc), warps 3-6 epilogue
+constexpr int CG_MAX_MAPS = 8;
+
+struct ConvGemmParams {
+  CUtensorMap amap[CG_MAX_MAPS];   // A sources (NDHWC bf16): concat halves or stride-2 parity views
+  // device tables (int32), laid out by the host plan:
+  //   [0, n_cg)                     map id of cgroup
+  //   [n_cg, 2 n_cg)                first channel (element index within its source) of cgroup
+  //   [2 n_cg, 2 n_cg + n_taps)     tap shift: sd | sh << 8 | sw << 16   (each in 0..2, brick coords)
+  //   then n_nblk * n_cg            bitmask of active taps per (nblock, cgroup)
+  //   then n_nblk                   first packed-weight tile index of nblock
+  //   then n_nblk                   output channel offset of nblock | (output tensor index << 30)
+  //   then n_nblk                   output coordinate offset: od | oh << 8 | ow << 16
+  const int* tab;
+  const bf16* w;          // packed weight tiles [G][nblk][8], in consumption order
+  bf16* out;          // output tensor 0
+  bf16* out2;         // output tensor 1 (data gradient of a channel concat), same strides / out_C
+  const float* bias;      // [n_nblk * nblk] fp32 or null
+  const bf16* addend;     // tensor with out's strides added in the epilogue, or null
+  const bf16* addend2;    // addend for out2
+  double* stats;          // [N][stats_C][2] (sum, sum of squares) accumulated with atomics, or null
+  int* err;               // device error word
+  int N, D, H, W;         // tile-grid extents
+  int tiles_h, tiles_w, segs_d, Dt;
+  int n_nblk, nblk;       // nblk in {32, 64, 96, 128}; Dt * nblk <= 256
+  int G, n_cg, n_taps;    // G chunks (of 8 channels) per cgroup, G even
+  long long out_sN, out_sD, out_sH, out_sW;   // element strides of out / addend
+  int out_C;              // channels physically present in out (store mask)
+  int stats_C;
+  int omul;               // output coordinate = tile-grid coordinate * omul + offset(nblock)
+  int zD, zH, zW;         // output planes forced to zero (ConvTranspose3d + ConstantPad3d), or -1
+  int n_work;
+};
+
+size_t conv_gemm_smem_bytes(int Dt, int G, int nblk);
+int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+
+}  // namespace u3d

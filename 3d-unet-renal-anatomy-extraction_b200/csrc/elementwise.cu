@@ -1,0 +1,776 @@
+// HBM-bound kernels of the U-Net hot path (sm_100a): InstanceNorm(+dropout)+LeakyReLU(+residual)
+// forward / backward, the 1-channel stem conv and the 1x1x1 classifier head (both far below the
+// tensor-core ridge), the fused softmax + Dice / focal loss and its gradient, and the sliding-window
+// blend.  Activations are bf16 NDHWC with the channel count padded to a multiple of 8 (16-byte
+// vectors); one thread owns one 8-channel vector, threads of a block tile (channel chunk, voxel) so
+// every warp access is a run of consecutive 16-byte words.
+#include "kernels.cuh"
+
+namespace u3d {
+
+namespace {
+
+constexpr float LRELU = 0.01f;     // nn.LeakyReLU default slope (network.py:165,390)
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm3d(affine=False, eps=1e-5) statistics -> (mean, scale) per (n, c).
+// network.py:175,401,315.  With Dropout3d in front (network.py:159-160,412-413) the normalised
+// tensor is z = m*y, m in {0, 1/(1-p)} per (n,c):  IN(z) = (y - mean) * m / sqrt(m^2 var + eps).
+// ---------------------------------------------------------------------------------------------
+__global__ void in_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ drop,
+                                   float2* __restrict__ table, int NC, double inv_count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  const double mean = stats[2 * i] * inv_count;
+  double var = stats[2 * i + 1] * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double m = drop ? (double)drop[i] : 1.0;
+  const double scale = m / sqrt(m * m * var + (double)eps);
+  table[i] = make_float2((float)mean, (float)scale);
+}
+
+// out = lrelu((y - mean) * scale [+ skip])
+template <bool HAS_SKIP>
+__global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ skip,
+                                uint4* __restrict__ out, const float2* __restrict__ table, int chunks,
+                                long long V, int Cp) {
+  const int n = blockIdx.y;
+  const int ch = threadIdx.x;                   // 8-channel chunk
+  float mean[8], scale[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 t = table[(size_t)n * Cp + ch * 8 + j];
+    mean[j] = t.x;
+    scale[j] = t.y;
+  }
+  const size_t base = (size_t)n * V * chunks;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
+    const size_t idx = base + (size_t)v * chunks + ch;
+    float f[8];
+    unpack8(ld_stream(y + idx), f);
+    float s[8];
+    if (HAS_SKIP) unpack8(ld_stream(skip + idx), s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = (f[j] - mean[j]) * scale[j];
+      if (HAS_SKIP) z += s[j];
+      f[j] = z > 0.f ? z : LRELU * z;
+    }
+    out[idx] = pack8(f);
+  }
+}
+
+// Backward, pass 1:  g = (dout [+ dout2]) * lrelu'(out)   (sign(out) == sign(pre-activation));
+// accumulates sum(g), sum(g * yhat) per (n, c).  g is also d(skip) of a residual block.
+template <bool HAS_D2>
+__global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2,
+                                     const uint4* __restrict__ out, const uint4* __restrict__ y,
+                                     uint4* __restrict__ g, const float2* __restrict__ table,
+                                     double* __restrict__ sums, int chunks, long long V, int Cp) {
+  extern __shared__ float red[];   // [blockDim.y][chunks*8][2]
+  const int n = blockIdx.y;
+  const int ch = threadIdx.x;
+  float mean[8], scale[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 t = table[(size_t)n * Cp + ch * 8 + j];
+    mean[j] = t.x;
+    scale[j] = t.y;
+    s1[j] = 0.f;
+    s2[j] = 0.f;
+  }
+  const size_t base = (size_t)n * V * chunks;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
+    const size_t idx = base + (size_t)v * chunks + ch;
+    float d[8], o[8], yy[8];
+    unpack8(ld_stream(dout + idx), d);
+    if (HAS_D2) {
+      float d2[8];
+      unpack8(ld_stream(dout2 + idx), d2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] += d2[j];
+    }
+    unpack8(ld_stream(out + idx), o);
+    unpack8(ld_stream(y + idx), yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gg = o[j] > 0.f ? d[j] : LRELU * d[j];
+      d[j] = gg;
+    }
+    const uint4 gp = pack8(d);
+    g[idx] = gp;
+    unpack8(gp, d);          // reduce what pass 2 will read back (bf16-rounded g)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float yh = (yy[j] - mean[j]) * scale[j];
+      s1[j] += d[j];
+      s2[j] += d[j] * yh;
+    }
+  }
+  const int C8 = chunks * 8;
+  float* my = red + ((size_t)threadIdx.y * C8 + ch * 8) * 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    my[2 * j] = s1[j];
+    my[2 * j + 1] = s2[j];
+  }
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < C8 * 2; i += blockDim.x * blockDim.y) {
+    float acc = 0.f;
+    for (int r = 0; r < (int)blockDim.y; ++r) acc += red[(size_t)r * C8 * 2 + i];
+    atomicAdd(&sums[((size_t)n * Cp) * 2 + i], (double)acc);
+  }
+}
+
+// Backward, pass 2:  dy = scale * (g - mean(g) - yhat * mean(g * yhat)); optional zeroing of the
+// ConstantPad3d planes of a ConvTrans3D output (network.py:314) and per-channel sum(dy) (its bias grad).
+__global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+                                    uint4* __restrict__ dy, const float2* __restrict__ table,
+                                    const double* __restrict__ sums, double* __restrict__ dsum, int chunks,
+                                    long long V, int Cp, double inv_count, int zero_last, int D, int H, int W) {
+  extern __shared__ float red[];
+  const int n = blockIdx.y;
+  const int ch = threadIdx.x;
+  float mean[8], scale[8], mg[8], mgy[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const size_t c = (size_t)n * Cp + ch * 8 + j;
+    const float2 t = table[c];
+    mean[j] = t.x;
+    scale[j] = t.y;
+    mg[j] = (float)(sums[2 * c] * inv_count);
+    mgy[j] = (float)(sums[2 * c + 1] * inv_count);
+    acc[j] = 0.f;
+  }
+  const size_t base = (size_t)n * V * chunks;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
+    const size_t idx = base + (size_t)v * chunks + ch;
+    float gg[8], yy[8];
+    unpack8(ld_stream(g + idx), gg);
+    unpack8(ld_stream(y + idx), yy);
+    bool z = false;
+    if (zero_last) {
+      const int w = (int)(v % W), h = (int)((v / W) % H), d = (int)(v / ((long long)W * H));
+      z = (w == W - 1) || (h == H - 1) || (d == D - 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float yh = (yy[j] - mean[j]) * scale[j];
+      float r = scale[j] * (gg[j] - mg[j] - yh * mgy[j]);
+      if (z) r = 0.f;
+      gg[j] = r;
+    }
+    const uint4 o = pack8(gg);
+    dy[idx] = o;
+    if (dsum) {
+      unpack8(o, gg);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += gg[j];
+    }
+  }
+  if (dsum) {
+    const int C8 = chunks * 8;
+    float* my = red + (size_t)threadIdx.y * C8 + ch * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) my[j] = acc[j];
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int i = tid; i < C8; i += blockDim.x * blockDim.y) {
+      float a = 0.f;
+      for (int r = 0; r < (int)blockDim.y; ++r) a += red[(size_t)r * C8 + i];
+      atomicAdd(&dsum[i], (double)a);
+    }
+  }
+}
+
+// per-channel sum over (n, voxels) of a bf16 NDHWC tensor (bias gradients)
+__global__ void channel_sum_kernel(const uint4* __restrict__ x, double* __restrict__ dsum, int chunks, long long NV) {
+  extern __shared__ float red[];
+  const int ch = threadIdx.x;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < NV; v += (long long)gridDim.x * blockDim.y) {
+    float f[8];
+    unpack8(ld_stream(x + (size_t)v * chunks + ch), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+  const int C8 = chunks * 8;
+  float* my = red + (size_t)threadIdx.y * C8 + ch * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) my[j] = acc[j];
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < C8; i += blockDim.x * blockDim.y) {
+    float a = 0.f;
+    for (int r = 0; r < (int)blockDim.y; ++r) a += red[(size_t)r * C8 + i];
+    atomicAdd(&dsum[i], (double)a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem: Conv3d(1 -> C, k3, p1) + bias on an fp32 NCDHW (C=1) input, bf16 NDHWC output
+// (network.py:541,550 -- no norm / activation follows).  K = 27: HBM-bound, CUDA cores.
+// ---------------------------------------------------------------------------------------------
+template <int CP>
+__global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[27][CP]*/,
+                                const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, int N, int D, int H,
+                                int W) {
+  __shared__ float ws[27 * CP + CP];
+  for (int i = threadIdx.x; i < 27 * CP + CP; i += blockDim.x) ws[i] = i < 27 * CP ? w[i] : b[i - 27 * CP];
+  __syncthreads();
+  const long long V = (long long)D * H * W, total = (long long)N * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / V);
+    const long long v = i - (long long)n * V;
+    const int xw = (int)(v % W), xh = (int)((v / W) % H), xd = (int)(v / ((long long)W * H));
+    float acc[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) acc[c] = ws[27 * CP + c];
+    const float* xn = x + (size_t)n * V;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const int dd = xd + kd - 1;
+      if (dd < 0 || dd >= D) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hh = xh + kh - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ww = xw + kw - 1;
+          if (ww < 0 || ww >= W) continue;
+          const float xv = __ldg(xn + ((size_t)dd * H + hh) * W + ww);
+          const float* wt = ws + ((kd * 3 + kh) * 3 + kw) * CP;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) acc[c] = fmaf(xv, wt[c], acc[c]);
+        }
+      }
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + (size_t)i * CP);
+#pragma unroll
+    for (int k = 0; k < CP / 8; ++k) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = acc[k * 8 + j];
+      op[k] = pack8(f);
+    }
+  }
+}
+
+// Stem weight/bias gradient: dW[tap][c] = sum_v x[v + tap] * dy[v][c];  db[c] = sum_v dy[v][c].
+// block = (CP/8 chunks, 28 taps [27 + bias], S voxel streams); fp32 atomics into dw[28][CP].
+template <int CP>
+__global__ void stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
+                                  int N, int D, int H, int W) {
+  const int ch = threadIdx.x, tap = threadIdx.y, s = threadIdx.z;
+  const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+  const long long V = (long long)D * H * W, total = (long long)N * V;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.z + s; i < total; i += (long long)gridDim.x * blockDim.z) {
+    const int n = (int)(i / V);
+    const long long v = i - (long long)n * V;
+    float xv = 1.f;
+    if (tap < 27) {
+      const int xw = (int)(v % W) + kw - 1, xh = (int)((v / W) % H) + kh - 1, xd = (int)(v / ((long long)W * H)) + kd - 1;
+      xv = (xw >= 0 && xw < W && xh >= 0 && xh < H && xd >= 0 && xd < D)
+               ? __ldg(x + (size_t)n * V + ((size_t)xd * H + xh) * W + xw)
+               : 0.f;
+    }
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (size_t)i * CP) + ch), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, f[j], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = acc[j];
+    atomicAdd(&dw[tap * CP + ch * 8 + j], a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head: Conv3d(C -> K, k1) + bias (network.py:545-547,563): bf16 NDHWC in, fp32 NCDHW logits out.
+// ---------------------------------------------------------------------------------------------
+template <int CP, int KMAX>
+__global__ void head_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ w /*[K][CP]*/,
+                                const float* __restrict__ b, float* __restrict__ logits, int K, int N, long long V) {
+  __shared__ float ws[KMAX * CP + KMAX];
+  for (int i = threadIdx.x; i < K * CP + K; i += blockDim.x) ws[i] = i < K * CP ? w[i] : b[i - K * CP];
+  __syncthreads();
+  const long long total = (long long)N * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / V);
+    const long long v = i - (long long)n * V;
+    float acc[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) acc[k] = k < K ? ws[K * CP + k] : 0.f;
+    const uint4* ap = reinterpret_cast<const uint4*>(a + (size_t)i * CP);
+#pragma unroll
+    for (int c8 = 0; c8 < CP / 8; ++c8) {
+      float f[8];
+      unpack8(ld_stream(ap + c8), f);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], ws[k * CP + c8 * 8 + j], acc[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) logits[((size_t)n * K + k) * V + v] = acc[k];
+  }
+}
+
+// da[v][c] = sum_k dl[k][v] w[k][c];  dW[k][c] += sum_v dl[k][v] a[v][c];  db[k] += sum_v dl[k][v]
+template <int CP, int KMAX>
+__global__ void head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ a,
+                                const float* __restrict__ w, bf16* __restrict__ da, float* __restrict__ dw /*[K][CP]+[K]*/,
+                                int K, int N, long long V) {
+  __shared__ float ws[KMAX * CP];
+  __shared__ float red[KMAX * CP + KMAX];
+  for (int i = threadIdx.x; i < K * CP; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < KMAX * CP + KMAX; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const long long total = (long long)N * V;
+  const int lane = threadIdx.x & 31;
+  // each warp walks 32 voxels at a time; lane owns a voxel for da, then the warp reduces dW over voxels
+  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < total;
+       i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + lane;
+    const bool ok = i < total;
+    float g[KMAX];
+    float f[CP];
+    if (ok) {
+      const int n = (int)(i / V);
+      const long long v = i - (long long)n * V;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) g[k] = k < K ? dl[((size_t)n * K + k) * V + v] : 0.f;
+      const uint4* ap = reinterpret_cast<const uint4*>(a + (size_t)i * CP);
+#pragma unroll
+      for (int c8 = 0; c8 < CP / 8; ++c8) {
+        float t[8];
+        unpack8(ld_stream(ap + c8), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[c8 * 8 + j] = t[j];
+      }
+      uint4* op = reinterpret_cast<uint4*>(da + (size_t)i * CP);
+#pragma unroll
+      for (int c8 = 0; c8 < CP / 8; ++c8) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (k < K) s = fmaf(g[k], ws[k * CP + c8 * 8 + j], s);
+          t[j] = s;
+        }
+        op[c8] = pack8(t);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) g[k] = 0.f;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) f[c] = 0.f;
+    }
+    // warp reduction of g[k]*f[c] over the 32 voxels: column sums via xor butterflies
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k >= K) continue;
+      float col[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) col[c] = g[k] * f[c];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        float s = col[c];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        col[c] = s;
+      }
+      float gs = g[k];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) atomicAdd(&red[k * CP + c], col[c]);
+        atomicAdd(&red[KMAX * CP + k], gs);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * CP; i += blockDim.x) atomicAdd(&dw[i], red[i]);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) atomicAdd(&dw[K * CP + i], red[KMAX * CP + i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Loss: softmax over classes fused with the batch Tversky-Dice and focal/CE sums
+// (loss.py:7-11 softmax, :32-48 dice, :70-80 focal; one-hot never materialised).
+//   sums[c] = { TP = sum p_c g_c,  SP = sum p_c,  SG = sum g_c,  F = sum g_c * -(1-p_c)^gamma * log p_c }
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+__device__ __forceinline__ void softmax_k(const float (&z)[KMAX], int K, float (&p)[KMAX], float& lse) {
+  float m = z[0];
+#pragma unroll
+  for (int k = 1; k < KMAX; ++k)
+    if (k < K) m = fmaxf(m, z[k]);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    p[k] = k < K ? expf(z[k] - m) : 0.f;
+    s += p[k];
+  }
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) p[k] *= inv;
+  lse = m + logf(s);
+}
+
+template <int KMAX>
+__global__ void loss_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                double* __restrict__ sums /*[K][4]*/, int K, int N, long long V, float gamma) {
+  __shared__ float red[KMAX * 4];
+  for (int i = threadIdx.x; i < KMAX * 4; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float tp[KMAX], sp[KMAX], sg[KMAX], fo[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) tp[k] = sp[k] = sg[k] = fo[k] = 0.f;
+  const long long total = (long long)N * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / V);
+    const long long v = i - (long long)n * V;
+    float z[KMAX], p[KMAX], lse;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) z[k] = k < K ? __ldg(&logits[((size_t)n * K + k) * V + v]) : 0.f;
+    softmax_k<KMAX>(z, K, p, lse);
+    const int t = (int)target[i];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k >= K) continue;
+      sp[k] += p[k];
+      if (k == t) {
+        tp[k] += p[k];
+        sg[k] += 1.f;
+        const float logpt = z[k] - lse;
+        const float om = 1.f - p[k];
+        const float mod = gamma == 0.f ? 1.f : (gamma == 2.f ? om * om : powf(fmaxf(om, 0.f), gamma));
+        fo[k] += -mod * logpt;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k >= K) continue;
+    float a = tp[k], b = sp[k], c = sg[k], d = fo[k];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&red[k * 4 + 0], a);
+      atomicAdd(&red[k * 4 + 1], b);
+      atomicAdd(&red[k * 4 + 2], c);
+      atomicAdd(&red[k * 4 + 3], d);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * 4; i += blockDim.x) atomicAdd(&sums[i], (double)red[i]);
+}
+
+// coef[k] = { a_k = dL/dTP_k, b_k = dL/dSP_k, f_k = w_k * K / (N V) (focal weight), unused };
+// dL/dz_j = p_j (q_j - sum_c p_c q_c),  q_c = a_c g_c + b_c + [c == t] f_t * fprime(p_t)
+template <int KMAX>
+__global__ void loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                const float* __restrict__ coef /*[K][4]*/, const float* __restrict__ gscale,
+                                float* __restrict__ dlogits, int K, int N, long long V, float gamma, int use_focal) {
+  __shared__ float cf[KMAX * 4];
+  for (int i = threadIdx.x; i < K * 4; i += blockDim.x) cf[i] = coef[i];
+  __syncthreads();
+  const float gs = gscale ? gscale[0] : 1.f;
+  const long long total = (long long)N * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / V);
+    const long long v = i - (long long)n * V;
+    float z[KMAX], p[KMAX], q[KMAX], lse;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) z[k] = k < K ? __ldg(&logits[((size_t)n * K + k) * V + v]) : 0.f;
+    softmax_k<KMAX>(z, K, p, lse);
+    const int t = (int)target[i];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k >= K) { q[k] = 0.f; continue; }
+      float qq = cf[k * 4 + 1];
+      if (k == t) {
+        qq += cf[k * 4 + 0];
+        if (use_focal) {
+          const float pt = fmaxf(p[k], 1e-30f);
+          const float logpt = z[k] - lse;
+          const float om = 1.f - pt;
+          float fp;   // d/dp [ -(1-p)^gamma log p ]
+          if (gamma == 0.f) fp = -1.f / pt;
+          else if (gamma == 2.f) fp = 2.f * om * logpt - om * om / pt;
+          else fp = gamma * powf(fmaxf(om, 0.f), gamma - 1.f) * logpt - powf(fmaxf(om, 0.f), gamma) / pt;
+          qq += cf[k * 4 + 2] * fp;
+        }
+      }
+      q[k] = qq;
+      dot += p[k] * qq;
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) dlogits[((size_t)n * K + k) * V + v] = gs * p[k] * (q[k] - dot);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sliding-window blend (trainer.py:72-96): result[:, tile] += softmax(logits) * w ; weight[tile] += w
+// then result / weight -> argmax (uint8) or probabilities.  w == null is the reference's uniform blend.
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void sw_accumulate_kernel(const float* __restrict__ logits /*[K][px][py][pz]*/,
+                                     const float* __restrict__ window /*[px][py][pz] or null*/,
+                                     float* __restrict__ result /*[K][X][Y][Z]*/, float* __restrict__ weight /*[X][Y][Z]*/,
+                                     int K, int px, int py, int pz, int x0, int y0, int z0, int X, int Y, int Z) {
+  const long long P = (long long)px * py * pz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+    const int iz = (int)(i % pz), iy = (int)((i / pz) % py), ix = (int)(i / ((long long)pz * py));
+    float z[KMAX], p[KMAX], lse;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) z[k] = k < K ? __ldg(&logits[(size_t)k * P + i]) : 0.f;
+    if (K == 1) {
+      p[0] = 1.f / (1.f + expf(-z[0]));      // trainer.py:76 sigmoid branch
+    } else {
+      softmax_k<KMAX>(z, K, p, lse);
+    }
+    const float wv = window ? __ldg(&window[i]) : 1.f;
+    const size_t o = ((size_t)(x0 + ix) * Y + (y0 + iy)) * Z + (z0 + iz);
+    const size_t XYZ = (size_t)X * Y * Z;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) result[(size_t)k * XYZ + o] += p[k] * wv;
+    weight[o] += wv;
+  }
+}
+
+template <int KMAX>
+__global__ void sw_finalize_kernel(const float* __restrict__ result, const float* __restrict__ weight,
+                                   uint8_t* __restrict__ labels, float* __restrict__ probs /*[X][Y][Z][K] or null*/,
+                                   int K, long long XYZ) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < XYZ; i += (long long)gridDim.x * blockDim.x) {
+    const float wv = weight[i];
+    float r[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) r[k] = k < K ? result[(size_t)k * XYZ + i] / wv : 0.f;   // 0/0 = NaN where uncovered
+    if (probs) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) probs[(size_t)i * K + k] = r[k];
+    }
+    if (labels) {
+      // argmax(softmax(r)) == argmax(r); NaN (uncovered) -> torch.argmax picks index 0 (first NaN)
+      int best = 0;
+      if (K == 1) {
+        best = (int)rintf(r[0]);      // trainer.py:91-96: squeeze + np.round
+      } else if (!(r[0] != r[0])) {
+        float bv = r[0];
+#pragma unroll
+        for (int k = 1; k < KMAX; ++k)
+          if (k < K && r[k] > bv) { bv = r[k]; best = k; }
+      }
+      labels[i] = (uint8_t)best;
+    }
+  }
+}
+
+inline int grid_for(long long work_items, int per_block, int num_sms, int waves) {
+  long long need = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)num_sms * waves;
+  return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+}  // namespace
+
+// ----------------------------------- launchers ---------------------------------------------------
+static inline dim3 cv_block(int chunks) {
+  int ty = 256 / chunks;
+  if (ty < 1) ty = 1;
+  return dim3(chunks, ty, 1);
+}
+#define U3D_CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? U3D_OK : U3D_ERR_CUDA)
+
+int in_finalize(const double* stats, const float* drop, float* table, int NC, double count, float eps, cudaStream_t s) {
+  in_finalize_kernel<<<(NC + 127) / 128, 128, 0, s>>>(stats, drop, reinterpret_cast<float2*>(table), NC, 1.0 / count, eps);
+  return U3D_CHECK_LAUNCH();
+}
+
+int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int N, long long V, int Cp, int num_sms,
+             cudaStream_t s) {
+  if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
+  const int chunks = Cp / 8;
+  dim3 blk = cv_block(chunks);
+  int gx = grid_for(V, blk.y * 4, num_sms, 16) / N;
+  if (gx < 1) gx = 1;
+  dim3 grd(gx, N);
+  if (skip)
+    in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (const float2*)table, chunks, V, Cp);
+  else
+    in_apply_kernel<false><<<grd, blk, 0, s>>>((const uint4*)y, nullptr, (uint4*)out, (const float2*)table, chunks, V, Cp);
+  return U3D_CHECK_LAUNCH();
+}
+
+int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf16* y, bf16* g, const float* table,
+                  double* sums, int N, long long V, int Cp, int num_sms, cudaStream_t s) {
+  if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
+  const int chunks = Cp / 8;
+  dim3 blk = cv_block(chunks);
+  int gx = grid_for(V, blk.y * 8, num_sms, 8) / N;
+  if (gx < 1) gx = 1;
+  dim3 grd(gx, N);
+  const size_t sm = (size_t)blk.y * Cp * 2 * sizeof(float);
+  if (dout2)
+    in_bwd_reduce_kernel<true><<<grd, blk, sm, s>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)out,
+                                                    (const uint4*)y, (uint4*)g, (const float2*)table, sums, chunks, V, Cp);
+  else
+    in_bwd_reduce_kernel<false><<<grd, blk, sm, s>>>((const uint4*)dout, nullptr, (const uint4*)out, (const uint4*)y,
+                                                     (uint4*)g, (const float2*)table, sums, chunks, V, Cp);
+  return U3D_CHECK_LAUNCH();
+}
+
+int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, const double* sums, double* dsum, int N,
+                 int D, int H, int W, int Cp, int zero_last, int num_sms, cudaStream_t s) {
+  if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
+  const int chunks = Cp / 8;
+  const long long V = (long long)D * H * W;
+  dim3 blk = cv_block(chunks);
+  int gx = grid_for(V, blk.y * 8, num_sms, 8) / N;
+  if (gx < 1) gx = 1;
+  dim3 grd(gx, N);
+  const size_t sm = dsum ? (size_t)blk.y * Cp * sizeof(float) : 0;
+  in_bwd_apply_kernel<<<grd, blk, sm, s>>>((const uint4*)g, (const uint4*)y, (uint4*)dy, (const float2*)table, sums, dsum,
+                                           chunks, V, Cp, 1.0 / (double)V, zero_last, D, H, W);
+  return U3D_CHECK_LAUNCH();
+}
+
+int channel_sum(const bf16* x, double* dsum, long long NV, int Cp, int num_sms, cudaStream_t s) {
+  if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
+  const int chunks = Cp / 8;
+  dim3 blk = cv_block(chunks);
+  const int gx = grid_for(NV, blk.y * 8, num_sms, 8);
+  channel_sum_kernel<<<gx, blk, (size_t)blk.y * Cp * sizeof(float), s>>>((const uint4*)x, dsum, chunks, NV);
+  return U3D_CHECK_LAUNCH();
+}
+
+int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int D, int H, int W, int Cp, int num_sms,
+             cudaStream_t s) {
+  const long long total = (long long)N * D * H * W;
+  const int g = grid_for(total, 128, num_sms, 16);
+  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W);
+  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W);
+  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W);
+  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W);
+  else return U3D_ERR_UNSUPPORTED;
+  return U3D_CHECK_LAUNCH();
+}
+
+int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, int Cp, int num_sms, cudaStream_t s) {
+  const long long total = (long long)N * D * H * W;
+  const int streams = 1024 / (28 * (Cp / 8));
+  if (streams < 1) return U3D_ERR_UNSUPPORTED;
+  dim3 blk(Cp / 8, 28, streams);
+  const int g = grid_for(total, streams * 64, num_sms, 2);
+  if (Cp == 32) stem_wgrad_kernel<32><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
+  else if (Cp == 16) stem_wgrad_kernel<16><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
+  else if (Cp == 48) stem_wgrad_kernel<48><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
+  else if (Cp == 64) stem_wgrad_kernel<64><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
+  else return U3D_ERR_UNSUPPORTED;
+  return U3D_CHECK_LAUNCH();
+}
+
+int head_fwd(const bf16* a, const float* w, const float* b, float* logits, int K, int N, long long V, int Cp, int num_sms,
+             cudaStream_t s) {
+  if (K < 1 || K > 8) return U3D_ERR_UNSUPPORTED;
+  const int g = grid_for((long long)N * V, 256, num_sms, 16);
+  if (Cp == 32) head_fwd_kernel<32, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V);
+  else if (Cp == 16) head_fwd_kernel<16, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V);
+  else if (Cp == 48) head_fwd_kernel<48, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V);
+  else if (Cp == 64) head_fwd_kernel<64, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V);
+  else return U3D_ERR_UNSUPPORTED;
+  return U3D_CHECK_LAUNCH();
+}
+
+int head_bwd(const float* dl, const bf16* a, const float* w, bf16* da, float* dw, int K, int N, long long V, int Cp,
+             int num_sms, cudaStream_t s) {
+  if (K < 1 || K > 4) return U3D_ERR_UNSUPPORTED;
+  const int g = grid_for((long long)N * V, 128 * 8, num_sms, 4);
+  if (Cp == 32) head_bwd_kernel<32, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, K, N, V);
+  else if (Cp == 16) head_bwd_kernel<16, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, K, N, V);
+  else return U3D_ERR_UNSUPPORTED;
+  return U3D_CHECK_LAUNCH();
+}
+
+int loss_fwd(const float* logits, const long long* target, double* sums, int K, int N, long long V, float gamma,
+             int num_sms, cudaStream_t s) {
+  if (K < 2 || K > 8) return U3D_ERR_UNSUPPORTED;
+  const int g = grid_for((long long)N * V, 256 * 4, num_sms, 8);
+  loss_fwd_kernel<8><<<g, 256, 0, s>>>(logits, target, sums, K, N, V, gamma);
+  return U3D_CHECK_LAUNCH();
+}
+
+int loss_bwd(const float* logits, const long long* target, const float* coef, const float* gscale, float* dlogits, int K,
+             int N, long long V, float gamma, int use_focal, int num_sms, cudaStream_t s) {
+  if (K < 2 || K > 8) return U3D_ERR_UNSUPPORTED;
+  const int g = grid_for((long long)N * V, 256 * 4, num_sms, 8);
+  loss_bwd_kernel<8><<<g, 256, 0, s>>>(logits, target, coef, gscale, dlogits, K, N, V, gamma, use_focal);
+  return U3D_CHECK_LAUNCH();
+}
+
+int sw_accumulate(const float* logits, const float* window, float* result, float* weight, int K, int px, int py, int pz,
+                  int x0, int y0, int z0, int X, int Y, int Z, int num_sms, cudaStream_t s) {
+  if (K < 1 || K > 8) return U3D_ERR_UNSUPPORTED;
+  if (x0 < 0 || y0 < 0 || z0 < 0 || x0 + px > X || y0 + py > Y || z0 + pz > Z) return U3D_ERR_INVALID;
+  const int g = grid_for((long long)px * py * pz, 256 * 2, num_sms, 8);
+  sw_accumulate_kernel<8><<<g, 256, 0, s>>>(logits, window, result, weight, K, px, py, pz, x0, y0, z0, X, Y, Z);
+  return U3D_CHECK_LAUNCH();
+}
+
+int sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K, long long XYZ,
+                int num_sms, cudaStream_t s) {
+  if (K < 1 || K > 8) return U3D_ERR_UNSUPPORTED;
+  const int g = grid_for(XYZ, 256 * 2, num_sms, 8);
+  sw_finalize_kernel<8><<<g, 256, 0, s>>>(result, weight, labels, probs, K, XYZ);
+  return U3D_CHECK_LAUNCH();
+}
+
+}  // namespace u3d

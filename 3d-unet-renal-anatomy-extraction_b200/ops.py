@@ -1,0 +1,237 @@
+"""Torch-tensor level wrappers over the C ABI: device-resident plans and one function per kernel.
+
+Activations are ``torch.bfloat16`` tensors of shape (N, D, H, W, Cp), contiguous, Cp = pad_channels(C).
+Nothing here computes on the host or through PyTorch ops: every function enqueues one of the
+library's kernels on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import plan as P
+
+_err_words: Dict[int, torch.Tensor] = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def err_word(device) -> torch.Tensor:
+    idx = torch.device(device).index or 0
+    if idx not in _err_words:
+        _err_words[idx] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _err_words[idx]
+
+
+def check_device_errors(device=None):
+    """Synchronising check of the device error word the pipelined kernels write on a timeout."""
+    for idx, w in _err_words.items():
+        v = int(w.item())
+        if v != 0:
+            w.zero_()
+            raise _lib.Unet3dError(f"device-side pipeline timeout, role code {v} (see csrc/conv_gemm.cu)")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def make_src(t: torch.Tensor, parity=None) -> _lib.Src:
+    assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.dim() == 5, (t.dtype, t.shape)
+    n, d, h, w, cp = t.shape
+    sW = cp * 2
+    sH, sD, sN = w * sW, h * w * sW, d * h * w * sW
+    s = _lib.Src()
+    if parity is None:
+        s.ptr, s.C, s.W, s.H, s.D, s.N = t.data_ptr(), cp, w, h, d, n
+        s.sW, s.sH, s.sD, s.sN = sW, sH, sD, sN
+    else:
+        pd, ph, pw = parity
+        s.ptr = t.data_ptr() + pd * sD + ph * sH + pw * sW
+        s.C, s.W, s.H, s.D, s.N = cp, (w - pw + 1) // 2, (h - ph + 1) // 2, (d - pd + 1) // 2, n
+        s.sW, s.sH, s.sD, s.sN = 2 * sW, 2 * sH, 2 * sD, sN
+    return s
+
+
+class DeviceConvPlan:
+    """A ConvPlan with its tables resident on one device."""
+
+    def __init__(self, plan: P.ConvPlan, device):
+        self.plan = plan
+        self.device = device
+        self.tab = torch.from_numpy(plan.tab).to(device)
+        self.widx = torch.from_numpy(plan.widx).to(device)
+        self.bidx = torch.from_numpy(P.bias_index(plan)).to(device)
+        self._w_version = None
+        self._w_packed = None
+        self._b_version = None
+        self._b_packed = None
+
+    def packed_weight(self, w: torch.Tensor) -> torch.Tensor:
+        """bf16 tile stream of parameter `w` (re-gathered only when the parameter changed)."""
+        key = (w.data_ptr(), w._version)
+        if self._w_version != key:
+            flat = torch.cat([w.detach().reshape(-1), w.new_zeros(1)])
+            self._w_packed = flat.index_select(0, self.widx).to(torch.bfloat16)
+            self._w_version = key
+        return self._w_packed
+
+    def packed_bias(self, b: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if b is None:
+            return None
+        key = (b.data_ptr(), b._version)
+        if self._b_version != key:
+            flat = torch.cat([b.detach().reshape(-1).float(), b.new_zeros(1, dtype=torch.float32)])
+            self._b_packed = flat.index_select(0, self.bidx).contiguous()
+            self._b_version = key
+        return self._b_packed
+
+
+def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch.Tensor, outs: Sequence[torch.Tensor],
+              grid: Tuple[int, int, int, int], bias: Optional[torch.Tensor] = None,
+              addends: Optional[Sequence[Optional[torch.Tensor]]] = None, stats: Optional[torch.Tensor] = None,
+              zero_last: bool = False):
+    """Launch the shifted-GEMM kernel for `dp` (see plan.make_conv_plan for the meaning of a plan)."""
+    pl = dp.plan
+    a = _lib.ConvArgs()
+    a.n_src = len(pl.maps)
+    for i, (ti, par) in enumerate(pl.maps):
+        a.src[i] = make_src(inputs[ti], par)
+    a.tab, a.w = dp.tab.data_ptr(), wpacked.data_ptr()
+    o0 = outs[0]
+    assert o0.dtype == torch.bfloat16 and o0.is_contiguous()
+    for o in outs:
+        assert o.shape == o0.shape and o.is_contiguous() and o.dtype == torch.bfloat16
+    a.out = o0.data_ptr()
+    a.out2 = outs[1].data_ptr() if len(outs) > 1 else None
+    a.bias = _ptr(bias)
+    if addends is not None:
+        a.addend = _ptr(addends[0])
+        a.addend2 = _ptr(addends[1]) if len(addends) > 1 else None
+    a.stats = _ptr(stats)
+    a.err = err_word(o0.device).data_ptr()
+    a.N, a.D, a.H, a.W = grid
+    a.Dt, a.n_nblk, a.nblk, a.G, a.n_cg, a.n_taps = pl.Dt, pl.n_nblk, pl.nblk, pl.G, pl.n_cg, len(pl.shifts)
+    n, d, h, w, cp = o0.shape
+    a.out_sW, a.out_sH, a.out_sD, a.out_sN = cp, w * cp, h * w * cp, d * h * w * cp
+    a.out_C = cp
+    a.stats_C = stats.shape[1] if stats is not None else 0
+    a.omul = pl.omul
+    a.zD, a.zH, a.zW = (d - 1, h - 1, w - 1) if zero_last else (-1, -1, -1)
+    _lib.check(_lib.lib().unet3d_conv_gemm(C.byref(a), _stream()), "unet3d_conv_gemm")
+
+
+class DeviceWgradPlan:
+    def __init__(self, plan: P.WgradPlan, device):
+        self.plan = plan
+        self.tab = torch.from_numpy(plan.tab).to(device)
+        self.gidx = torch.from_numpy(plan.gidx).to(device)
+
+
+def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor, dw: torch.Tensor,
+               grid: Tuple[int, int, int, int]):
+    pl = dp.plan
+    a = _lib.WgradArgs()
+    srcs = [(xs[ti], par, P.WT + 2, P.HT + 2) for (ti, par) in pl.x_maps] + [(dy, par, P.WT, P.HT) for par in pl.y_maps]
+    a.n_src = len(srcs)
+    for i, (t, par, bw, bh) in enumerate(srcs):
+        a.src[i] = make_src(t, par)
+        a.box_w[i], a.box_h[i] = bw, bh
+    a.tab, a.dw, a.err = dp.tab.data_ptr(), dw.data_ptr(), err_word(dw.device).data_ptr()
+    a.N, a.D, a.H, a.W = grid
+    a.n_jobs, a.job_stride, a.split = pl.n_jobs, pl.job_stride, pl.split
+    assert dw.dtype == torch.float32 and dw.numel() >= pl.dw_numel
+    _lib.check(_lib.lib().unet3d_wgrad_gemm(C.byref(a), _stream()), "unet3d_wgrad_gemm")
+
+
+# ---- memory-bound kernels ---------------------------------------------------------------------------
+def in_finalize(stats: torch.Tensor, drop: Optional[torch.Tensor], table: torch.Tensor, count: int, eps: float = 1e-5):
+    nc = stats.shape[0] * stats.shape[1]
+    _lib.check(_lib.lib().unet3d_in_finalize(stats.data_ptr(), _ptr(drop), table.data_ptr(), nc, float(count), eps,
+                                             _stream()), "unet3d_in_finalize")
+
+
+def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, table: torch.Tensor):
+    n, d, h, w, cp = y.shape
+    _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), n, d * h * w, cp,
+                                          _stream()), "unet3d_in_apply")
+
+
+def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
+    n, d, h, w, cp = y.shape
+    _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), out.data_ptr(), y.data_ptr(), g.data_ptr(),
+                                               table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _stream()),
+               "unet3d_in_bwd_reduce")
+
+
+def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False):
+    n, d, h, w, cp = y.shape
+    _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
+                                              _ptr(dsum), n, d, h, w, cp, int(zero_last), _stream()), "unet3d_in_bwd_apply")
+
+
+def channel_sum(x: torch.Tensor, dsum: torch.Tensor):
+    n, d, h, w, cp = x.shape
+    _lib.check(_lib.lib().unet3d_channel_sum(x.data_ptr(), dsum.data_ptr(), n * d * h * w, cp, _stream()),
+               "unet3d_channel_sum")
+
+
+def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
+    n, d, h, ww, cp = out.shape
+    _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, d, h, ww, cp,
+                                          _stream()), "unet3d_stem_fwd")
+
+
+def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
+    n, d, h, ww, cp = dy.shape
+    _lib.check(_lib.lib().unet3d_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), n, d, h, ww, cp, _stream()),
+               "unet3d_stem_wgrad")
+
+
+def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Tensor):
+    n, d, h, ww, cp = a.shape
+    k = logits.shape[1]
+    _lib.check(_lib.lib().unet3d_head_fwd(a.data_ptr(), w.data_ptr(), b.data_ptr(), logits.data_ptr(), k, n, d * h * ww,
+                                          cp, _stream()), "unet3d_head_fwd")
+
+
+def head_bwd(dl: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tensor, dw: torch.Tensor):
+    n, d, h, ww, cp = a.shape
+    k = dl.shape[1]
+    _lib.check(_lib.lib().unet3d_head_bwd(dl.data_ptr(), a.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(), k, n,
+                                          d * h * ww, cp, _stream()), "unet3d_head_bwd")
+
+
+def loss_fwd(logits, target, sums, gamma):
+    n, k = logits.shape[:2]
+    v = logits[0, 0].numel()
+    _lib.check(_lib.lib().unet3d_loss_fwd(logits.data_ptr(), target.data_ptr(), sums.data_ptr(), k, n, v, float(gamma),
+                                          _stream()), "unet3d_loss_fwd")
+
+
+def loss_bwd(logits, target, coef, gscale, dlogits, gamma, use_focal):
+    n, k = logits.shape[:2]
+    v = logits[0, 0].numel()
+    _lib.check(_lib.lib().unet3d_loss_bwd(logits.data_ptr(), target.data_ptr(), coef.data_ptr(), _ptr(gscale),
+                                          dlogits.data_ptr(), k, n, v, float(gamma), int(use_focal), _stream()),
+               "unet3d_loss_bwd")
+
+
+def sw_accumulate(logits, window, result, weight, origin):
+    k, px, py, pz = logits.shape[-4:]
+    _, X, Y, Z = result.shape
+    _lib.check(_lib.lib().unet3d_sw_accumulate(logits.data_ptr(), _ptr(window), result.data_ptr(), weight.data_ptr(), k,
+                                               px, py, pz, origin[0], origin[1], origin[2], X, Y, Z, _stream()),
+               "unet3d_sw_accumulate")
+
+
+def sw_finalize(result, weight, labels, probs):
+    k = result.shape[0]
+    _lib.check(_lib.lib().unet3d_sw_finalize(result.data_ptr(), weight.data_ptr(), _ptr(labels), _ptr(probs), k,
+                                             weight.numel(), _stream()), "unet3d_sw_finalize")

@@ -1,0 +1,131 @@
+/* unet3d_b200 -- C ABI of the B200 (sm_100a) kernels behind the 3D U-Net train / infer hot path.
+ *
+ * The reference (icrdr/3D-UNet-Renal-Anatomy-Extraction) is pure Python and has no FFI; the calls
+ * it makes on this path are torch.nn layer calls that dispatch to cuDNN/ATen.  Each entry point
+ * below replaces one such dispatch (reference file:line given per function) and is what a ctypes
+ * binding on the reference side would bind.
+ *
+ * Conventions
+ *   - return 0 on success, a U3D_ERR_* code otherwise; unet3d_last_error_string() explains.
+ *   - the caller owns every buffer (device pointers unless stated); the library never allocates
+ *     or frees device memory and keeps no references after the call returns.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
+ *   - activations are bf16 NDHWC with the channel count padded to a multiple of 16
+ *     ("Cp"); logits and the stem input are fp32 NCDHW exactly as PyTorch lays them out.
+ */
+#ifndef UNET3D_B200_H
+#define UNET3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define U3D_OK 0
+#define U3D_ERR_INVALID 1
+#define U3D_ERR_CUDA 2
+#define U3D_ERR_TIMEOUT 3
+#define U3D_ERR_UNSUPPORTED 4
+
+#define U3D_MAX_SRC 8
+
+const char* unet3d_version(void);
+const char* unet3d_last_error_string(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int unet3d_num_sms(void);
+
+/* One bf16 NDHWC view feeding the A operand of a contraction: a whole tensor, one half of a
+ * channel concat (network.py:350 torch.cat -- never materialised), or one stride-2 parity
+ * sub-lattice of a tensor (network.py:126 stride-2 convs).  Strides are in BYTES. */
+typedef struct unet3d_src {
+  const void* ptr;
+  int C, W, H, D, N;
+  long long sW, sH, sD, sN;
+} unet3d_src;
+
+/* Shifted-GEMM convolution on tcgen05 tensor cores (conv_gemm.cu).  Replaces the cuDNN dispatch of
+ *   nn.Conv3d forward            network.py:394-395 (k3, stride 1/2), :403 (k1 skip), :411, :541
+ *   nn.ConvTranspose3d forward   network.py:312-313 followed by ConstantPad3d :314 (zD/zH/zW)
+ *   and the autograd data gradients of all of the above.
+ * `tab` (device int32) and `w` (device bf16, packed tiles) are produced by the host plan
+ * (3d-unet-renal-anatomy-extraction_b200/plan.py); their layout is documented in csrc/conv_gemm.cuh. */
+typedef struct unet3d_conv_args {
+  int n_src;
+  unet3d_src src[U3D_MAX_SRC];
+  const int* tab;
+  const void* w;
+  void* out;
+  void* out2;            /* second output (data gradient of a concat input) or NULL */
+  const float* bias;     /* fp32 [n_nblk*nblk] or NULL */
+  const void* addend;    /* bf16, same strides as out, added in the epilogue, or NULL */
+  const void* addend2;   /* addend for out2 */
+  double* stats;         /* fp64 [N][stats_C][2] running (sum, sum^2) for InstanceNorm, or NULL */
+  int* err;              /* device int32 error word (0 = ok) */
+  int N, D, H, W;        /* tile-grid extents */
+  int Dt, n_nblk, nblk, G, n_cg, n_taps;
+  long long out_sN, out_sD, out_sH, out_sW;   /* ELEMENT strides of out/addend */
+  int out_C, stats_C, omul, zD, zH, zW;
+} unet3d_conv_args;
+int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream);
+size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk);
+
+/* Weight gradient on tcgen05 tensor cores (wgrad_gemm.cu): dW[tap][cin][cout] = sum_v x[v+tap][cin] dy[v][cout].
+ * Replaces the cuDNN backward-filter dispatch of the layers listed above. */
+typedef struct unet3d_wgrad_args {
+  int n_src;                     /* x views (box 10 x 18, halo) and dy views (box 8 x 16) share one array */
+  unet3d_src src[16];
+  int box_w[16], box_h[16];
+  const int* tab;                /* device int32 job table, layout in csrc/wgrad_gemm.cuh */
+  float* dw;                     /* fp32 accumulator the partial sums are atomically added to */
+  int* err;
+  int N, D, H, W;                /* tile-grid extents */
+  int n_jobs, job_stride;
+  int split;                     /* CTAs per job (split over voxel tiles) */
+} unet3d_wgrad_args;
+int unet3d_wgrad_gemm(const unet3d_wgrad_args* a, void* stream);
+
+/* InstanceNorm3d(affine=False) [+ Dropout3d channel mask] + LeakyReLU(0.01) [+ residual add]
+ * network.py:159-160,175-176,401-402,412-416,315-316.  stats come from the conv epilogue. */
+int unet3d_in_finalize(const double* stats, const float* drop_scale, float* table, int NC, double count, float eps,
+                       void* stream);
+int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, int N, long long V, int Cp,
+                    void* stream);
+int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, void* g,
+                         const float* table, double* sums, int N, long long V, int Cp, void* stream);
+int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums, double* dsum,
+                        int N, int D, int H, int W, int Cp, int zero_last, void* stream);
+int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* stream);
+
+/* Stem Conv3d(1->C,k3,p1)+bias, fp32 NCDHW in -> bf16 NDHWC out (network.py:541,550) and its
+ * weight/bias gradient (dw fp32 [28][Cp]: 27 taps then the bias row; accumulated atomically). */
+int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, int N, int D, int H, int W, int Cp,
+                    void* stream);
+int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, int Cp, void* stream);
+
+/* Head Conv3d(C->K,k1)+bias, bf16 NDHWC in -> fp32 NCDHW logits (network.py:545-547,563), and backward
+ * (da bf16 NDHWC; dw fp32 [K][Cp] followed by [K] bias grads, accumulated atomically). */
+int unet3d_head_fwd(const void* a, const float* w, const float* b, float* logits, int K, int N, long long V, int Cp,
+                    void* stream);
+int unet3d_head_bwd(const float* dlogits, const void* a, const float* w, void* da, float* dw, int K, int N,
+                    long long V, int Cp, void* stream);
+
+/* Fused softmax + batch Tversky-Dice / focal sums (loss.py:7-11,32-48,70-80) and the logits gradient.
+ * sums: fp64 [K][4] = {TP, sum p, sum g, focal}; coef: fp32 [K][4] = {dL/dTP, dL/dSP, focal weight, 0}. */
+int unet3d_loss_fwd(const float* logits, const long long* target, double* sums, int K, int N, long long V,
+                    float gamma, void* stream);
+int unet3d_loss_bwd(const float* logits, const long long* target, const float* coef, const float* grad_scale,
+                    float* dlogits, int K, int N, long long V, float gamma, int use_focal, void* stream);
+
+/* Sliding-window blending (trainer.py:72-96): accumulate one window's softmax (uniform when window==NULL,
+ * else weighted), then normalise + argmax / probabilities. */
+int unet3d_sw_accumulate(const float* logits, const float* window, float* result, float* weight, int K, int px,
+                         int py, int pz, int x0, int y0, int z0, int X, int Y, int Z, void* stream);
+int unet3d_sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K,
+                       long long XYZ, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNET3D_B200_H */

@@ -1,0 +1,73 @@
+"""CPU execution of the host plans (plan.py) with torch ops -- TEST INFRASTRUCTURE.
+
+Runs exactly the arithmetic the tcgen05 kernels are told to do by a plan (same tables, same packed
+weight stream, same source views / shifts / masks), ignoring only the tiling.  Lets the CPU suite
+prove the integer bookkeeping (tap tables, parity views, weight packing) against torch.nn.functional
+without a GPU; the GPU suite then only has to prove the kernels execute a plan faithfully.
+"""
+import numpy as np
+import torch
+
+
+def pack_weights(plan, w: torch.Tensor) -> torch.Tensor:
+    flat = torch.cat([w.reshape(-1).float(), torch.zeros(1)])
+    return flat[torch.from_numpy(plan.widx)]
+
+
+def run_conv_plan(plan, inputs, wpacked, grid, out_dims, bias_vec=None, zero_last=False):
+    """inputs: list of (N, D, H, W, Cp) float tensors; grid = (N, D, H, W) tile-grid extents;
+    out_dims = (D, H, W) of the output tensors.  Returns list of (N, *out_dims, Cp_out) tensors."""
+    N, D, H, W = grid
+    outs = [torch.zeros(N, *out_dims, cp) for cp in plan.out_Cp]
+    G, nblk = plan.G, plan.nblk
+    tile_elems = G * nblk * 8
+    for nb in range(plan.n_nblk):
+        acc = torch.zeros(N, D, H, W, nblk)
+        tptr = plan.wbase[nb]
+        for cg in range(plan.n_cg):
+            mask = int(plan.masks[nb, cg])
+            if mask == 0:
+                continue
+            ti, par = plan.maps[plan.cg_map[cg]]
+            v = inputs[ti]
+            if par is not None:
+                v = v[:, par[0]::2, par[1]::2, par[2]::2, :]
+            ch = plan.cg_ch[cg]
+            v = v[..., ch:ch + G * 8]
+            # brick coordinate s <-> view index o + s - 1; pad generously with zeros (TMA OOB fill)
+            vp = torch.zeros(N, D + 2, H + 2, W + 2, G * 8)
+            d1, h1, w1 = min(v.shape[1], D + 1), min(v.shape[2], H + 1), min(v.shape[3], W + 1)
+            vp[:, 1:1 + d1, 1:1 + h1, 1:1 + w1] = v[:, :d1, :h1, :w1]
+            for t, (sd, sh, sw) in enumerate(plan.shifts):
+                if not (mask >> t) & 1:
+                    continue
+                tile = wpacked[tptr * tile_elems:(tptr + 1) * tile_elems].reshape(G, nblk, 8)
+                tptr += 1
+                a = vp[:, sd:sd + D, sh:sh + H, sw:sw + W]
+                acc += torch.einsum("bdhwk,kn->bdhwn", a, tile.permute(0, 2, 1).reshape(G * 8, nblk))
+        if bias_vec is not None:
+            acc += bias_vec[nb * nblk:(nb + 1) * nblk]
+        o = outs[plan.nb_sel[nb]]
+        od, oh, ow = plan.nb_ooff[nb]
+        m = plan.omul
+        c0 = plan.nb_coff[nb]
+        c1 = min(c0 + nblk, o.shape[-1])
+        o[:, od::m, oh::m, ow::m, c0:c1] = acc[..., :c1 - c0]
+    if zero_last:
+        for o in outs:
+            o[:, -1] = 0
+            o[:, :, -1] = 0
+            o[:, :, :, -1] = 0
+    return outs
+
+
+def to_ndhwc(x: torch.Tensor, cp: int) -> torch.Tensor:
+    """(N, C, D, H, W) -> (N, D, H, W, Cp) zero padded."""
+    n, c = x.shape[:2]
+    out = torch.zeros(n, *x.shape[2:], cp)
+    out[..., :c] = x.permute(0, 2, 3, 4, 1)
+    return out
+
+
+def from_ndhwc(x: torch.Tensor, c: int) -> torch.Tensor:
+    return x[..., :c].permute(0, 4, 1, 2, 3).contiguous()

@@ -1,1 +1,10 @@
-"""B200-native 3D U-Net hot path."""
+"""B200-native (sm_100a) implementation of the 3D U-Net training / sliding-window-inference hot path of
+icrdr/3D-UNet-Renal-Anatomy-Extraction, behind the reference's own Python API.
+
+    from unet3d_b200 import ResUnet3D, DiceLoss, HybirdLoss, Trainer, predict_per_patch
+"""
+from .network import ResUnet3D, UNet3D, Unet, ResBlock, ResBlockStack, ConvTrans3D, UpConcat, generate_paired_features
+from .loss import DiceLoss, FocalLoss, HybirdLoss, Dice, dice
+
+__all__ = ["ResUnet3D", "UNet3D", "Unet", "ResBlock", "ResBlockStack", "ConvTrans3D", "UpConcat",
+           "generate_paired_features", "DiceLoss", "FocalLoss", "HybirdLoss", "Dice", "dice"]

@@ -1,0 +1,302 @@
+"""Forward / backward executor of the residual 3D U-Net on the library's sm_100a kernels.
+
+Walks the module tree of :class:`network.ResUnet3D` in the order of the reference's
+``Unet.forward`` (network.py:549-565) and ``ResBlock.forward`` (network.py:405-416) and enqueues
+
+  conv (tcgen05 shifted GEMM, IN statistics in the epilogue) -> in_finalize -> in_apply (+residual)
+
+per layer; the backward pass is the hand-derived reverse (no autograd graph over activations).
+The whole network is ONE ``torch.autograd.Function`` whose outputs are the logits and whose
+backward returns the parameter gradients, so ``loss.backward(); optimizer.step()`` in the
+reference's step loop (trainer.py:490-496) works unchanged.
+
+Layout: activations bf16 NDHWC (channels padded to 16), statistics fp64, master weights fp32.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from . import plan as P
+
+IN_EPS = 1e-5      # nn.InstanceNorm3d default (network.py:163,388: no eps passed)
+
+
+class _ConvOp:
+    """Forward, data-gradient and weight-gradient plans of one conv / transposed-conv layer call."""
+
+    def __init__(self, eng, kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: int, grid, transposed=False):
+        self.kind, self.ks, self.stride = kind, ks, stride
+        self.in_C, self.out_C = list(in_C), out_C
+        self.grid = grid            # (N, D, H, W) tile grid (coarse grid for strided / transposed layers)
+        dev = eng.device
+        depth = grid[1]
+        if kind == "conv":
+            self.fwd = ops.DeviceConvPlan(P.make_conv_plan("conv_fwd", ks, stride, in_C, [out_C], depth), dev)
+            self.dgrad = ops.DeviceConvPlan(P.make_conv_plan("conv_dgrad", ks, stride, [out_C], in_C, depth), dev)
+        else:
+            self.fwd = ops.DeviceConvPlan(P.make_conv_plan("convT_fwd", 3, 2, in_C, [out_C], depth), dev)
+            self.dgrad = ops.DeviceConvPlan(P.make_conv_plan("convT_dgrad", 3, 2, [out_C], in_C, depth), dev)
+        self.wgrad = ops.DeviceWgradPlan(P.make_wgrad_plan(kind, ks, stride, in_C, out_C, grid, eng.num_sms), dev)
+
+
+class ResUNetEngine:
+    def __init__(self, model):
+        self.model = model
+        self.device = None
+        self.num_sms = 148
+        self._plans: Dict[Tuple, dict] = {}
+
+    # ------------------------------------------------------------------ plans
+    def _get_plans(self, shape) -> dict:
+        key = tuple(shape)
+        if key in self._plans:
+            return self._plans[key]
+        from . import _lib
+        self.num_sms = _lib.lib().unet3d_num_sms()
+        net = self.model.net
+        N, _, D, H, W = shape
+        np_ = net.num_pool
+        if D % (1 << np_) or H % (1 << np_) or W % (1 << np_):
+            raise RuntimeError(f"spatial size {(D, H, W)} must be divisible by 2^num_pool = {1 << np_} "
+                               f"(the reference fails in torch.cat, network.py:350)")
+        plans = {}
+
+        def block_ops(blk, in_C, grid_out):
+            o = {"conv1": _ConvOp(self, "conv", 3, blk.stride, in_C, blk.out_channels, grid_out),
+                 "conv2": _ConvOp(self, "conv", 3, 1, [blk.out_channels], blk.out_channels, grid_out)}
+            if blk.uses_skip_conv:
+                o["skip"] = _ConvOp(self, "conv", 1, blk.stride, in_C, blk.out_channels, grid_out)
+            return o
+
+        dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
+        for i in range(np_ + 1):
+            g = (N, *dims[i])
+            for j, blk in enumerate(net.encode_blocks[i].res_blocks):
+                plans[("enc", i, j)] = block_ops(blk, [blk.in_channels], g)
+            if i < np_:
+                plans[("pool", i)] = block_ops(net.pool_blocks[i], [net.pool_blocks[i].in_channels], (N, *dims[i + 1]))
+                ct = net.up_blocks[i].conv_trans.up[0]
+                plans[("up", i)] = _ConvOp(self, "convT", 3, 2, [ct.in_channels], ct.out_channels, (N, *dims[i + 1]))
+                dec = net.decode_blocks[i]
+                plans[("dec", i)] = block_ops(dec, [ct.out_channels, dec.in_channels - ct.out_channels], g)
+        self._plans[key] = plans
+        return plans
+
+    # ------------------------------------------------------------------ public entry
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("unet3d_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
+        if x.dim() != 5 or x.shape[1] != self.model.in_channels:
+            raise RuntimeError(f"expected input (N, {self.model.in_channels}, D, H, W), got {tuple(x.shape)}")
+        if self.model.in_channels != 1:
+            raise RuntimeError("the stem kernel covers in_channels == 1 (every reference script uses 1)")
+        self.device = x.device
+        params = [p for p in self.model.parameters()]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if need_grad:
+            return _UNetFn.apply(x, self, *params)
+        with torch.no_grad():
+            logits, _ = self.forward_impl(x.detach(), save=False)
+        return logits
+
+    # ------------------------------------------------------------------ helpers
+    def _new_act(self, n, dims, c):
+        return torch.empty((n, *dims, P.pad_channels(c)), dtype=torch.bfloat16, device=self.device)
+
+    def _drop_scale(self, n, c, p):
+        """Dropout3d channel mask drawn exactly as F.dropout3d does, padded to Cp."""
+        m = torch.empty(n, c, 1, 1, 1, device=self.device, dtype=torch.float32).bernoulli_(1 - p).div_(1 - p)
+        self.model.last_dropout_masks.append(m)
+        out = torch.zeros(n, P.pad_channels(c), device=self.device, dtype=torch.float32)
+        out[:, :c] = m.view(n, c)
+        return out
+
+    def _conv_in(self, op: _ConvOp, inputs, weight, out_dims, drop=None, bias=None, zero_last=False):
+        """conv (+ stats) -> finalize: returns (y, table)."""
+        n = inputs[0].shape[0]
+        y = self._new_act(n, out_dims, op.out_C)
+        stats = torch.zeros(n, y.shape[-1], 2, dtype=torch.float64, device=self.device)
+        ops.conv_gemm(op.fwd, inputs, op.fwd.packed_weight(weight), [y], op.grid, bias=op.fwd.packed_bias(bias),
+                      stats=stats, zero_last=zero_last)
+        table = torch.empty(n, y.shape[-1], 2, dtype=torch.float32, device=self.device)
+        ops.in_finalize(stats, drop, table, out_dims[0] * out_dims[1] * out_dims[2], IN_EPS)
+        return y, table
+
+    def _res_block_fwd(self, blk, bops, inputs, out_dims, train, save):
+        n = inputs[0].shape[0]
+        drop = self._drop_scale(n, blk.out_channels, blk.dropout_p) if train else None
+        # conv biases directly followed by InstanceNorm(affine=False) cancel exactly: not applied
+        y1, t1 = self._conv_in(bops["conv1"], inputs, blk.conv1.weight, out_dims, drop=drop)
+        a1 = torch.empty_like(y1)
+        ops.in_apply(y1, None, a1, t1)
+        y2, t2 = self._conv_in(bops["conv2"], [a1], blk.conv2.weight, out_dims)
+        if blk.uses_skip_conv:
+            sop = bops["skip"]
+            s = self._new_act(n, out_dims, blk.out_channels)
+            ops.conv_gemm(sop.fwd, inputs, sop.fwd.packed_weight(blk.skip_conv.weight), [s], sop.grid,
+                          bias=sop.fwd.packed_bias(blk.skip_conv.bias))
+        else:
+            s = inputs[0]
+        out = torch.empty_like(y2)
+        ops.in_apply(y2, s, out, t2)
+        rec = (inputs, y1, t1, a1, y2, t2, out) if save else None
+        return out, rec
+
+    # ------------------------------------------------------------------ forward
+    def forward_impl(self, x: torch.Tensor, save: bool):
+        model, net = self.model, self.model.net
+        train = model.training
+        model.last_dropout_masks = []
+        plans = self._get_plans(x.shape)
+        N, _, D, H, W = x.shape
+        np_ = net.num_pool
+        dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
+        x32 = x.contiguous().float()
+        tape = {}
+        c0 = net.conv.out_channels
+        cp0 = P.pad_channels(c0)
+        # stem weights as [27][Cp] fp32 (+ bias [Cp])
+        w0 = torch.zeros(27, cp0, device=self.device)
+        w0[:, :c0] = net.conv.weight.detach().reshape(c0, 27).t()
+        b0 = torch.zeros(cp0, device=self.device)
+        b0[:c0] = net.conv.bias.detach()
+        cur = self._new_act(N, dims[0], c0)
+        ops.stem_fwd(x32, w0, b0, cur)
+        tape["x"] = x32
+        skips = []
+        for i in range(np_):
+            for j, blk in enumerate(net.encode_blocks[i].res_blocks):
+                cur, tape[("enc", i, j)] = self._res_block_fwd(blk, plans[("enc", i, j)], [cur], dims[i], train, save)
+            skips.append(cur)
+            cur, tape[("pool", i)] = self._res_block_fwd(net.pool_blocks[i], plans[("pool", i)], [cur], dims[i + 1], train,
+                                                         save)
+        for j, blk in enumerate(net.encode_blocks[np_].res_blocks):
+            cur, tape[("enc", np_, j)] = self._res_block_fwd(blk, plans[("enc", np_, j)], [cur], dims[np_], train, save)
+        for i in range(np_ - 1, -1, -1):
+            ct = net.up_blocks[i].conv_trans.up[0]
+            uop = plans[("up", i)]
+            yu, tu = self._conv_in(uop, [cur], ct.weight, dims[i], bias=ct.bias, zero_last=True)
+            au = torch.empty_like(yu)
+            ops.in_apply(yu, None, au, tu)
+            if save:
+                tape[("up", i)] = (cur, yu, tu, au)
+            cur, tape[("dec", i)] = self._res_block_fwd(net.decode_blocks[i], plans[("dec", i)], [au, skips[i]], dims[i],
+                                                        train, save)
+        K = net.fc.out_channels
+        cl = net.fc.in_channels
+        wf = torch.zeros(K, P.pad_channels(cl), device=self.device)
+        wf[:, :cl] = net.fc.weight.detach().reshape(K, cl)
+        logits = torch.empty(N, K, D, H, W, device=self.device, dtype=torch.float32)
+        ops.head_fwd(cur, wf, net.fc.bias.detach().float().contiguous(), logits)
+        if save:
+            tape["head"] = (cur, wf)
+        return logits, (tape if save else None)
+
+    # ------------------------------------------------------------------ backward
+    def _wgrad(self, op: _ConvOp, xs, dy, param):
+        pl = op.wgrad.plan
+        dw = torch.zeros(pl.dw_numel + 1, dtype=torch.float32, device=self.device)
+        ops.wgrad_gemm(op.wgrad, xs, dy, dw, op.grid)
+        return dw.index_select(0, op.wgrad.gidx).view_as(param)
+
+    def _in_bwd(self, dout, dout2, out, y, table, zero_last=False, want_dsum=False):
+        n, cp = y.shape[0], y.shape[-1]
+        g = torch.empty_like(y)
+        sums = torch.zeros(n, cp, 2, dtype=torch.float64, device=self.device)
+        ops.in_bwd_reduce(dout, dout2, out, y, g, table, sums)
+        dy = torch.empty_like(y)
+        dsum = torch.zeros(cp, dtype=torch.float64, device=self.device) if want_dsum else None
+        ops.in_bwd_apply(g, y, dy, table, sums, dsum, zero_last)
+        return g, dy, sums, dsum
+
+    def _res_block_bwd(self, blk, bops, rec, dout, dout2, grads):
+        inputs, y1, t1, a1, y2, t2, out = rec
+        g2, dy2, sums2, _ = self._in_bwd(dout, dout2, out, y2, t2)
+        grads[blk.conv2.weight] = self._wgrad(bops["conv2"], [a1], dy2, blk.conv2.weight)
+        grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias)       # cancelled by the norm (S1)
+        da1 = torch.empty_like(a1)
+        c2 = bops["conv2"]
+        ops.conv_gemm(c2.dgrad, [dy2], c2.dgrad.packed_weight(blk.conv2.weight), [da1], c2.grid)
+        _, dy1, _, _ = self._in_bwd(da1, None, a1, y1, t1)
+        c1 = bops["conv1"]
+        grads[blk.conv1.weight] = self._wgrad(c1, inputs, dy1, blk.conv1.weight)
+        grads[blk.conv1.bias] = torch.zeros_like(blk.conv1.bias)
+        if blk.uses_skip_conv:
+            sk = bops["skip"]
+            grads[blk.skip_conv.weight] = self._wgrad(sk, inputs, g2, blk.skip_conv.weight)
+            grads[blk.skip_conv.bias] = sums2[:, :blk.out_channels, 0].sum(0).float()
+            if blk.stride == 2:
+                dskip = [torch.zeros_like(t) for t in inputs]          # k1 s2 gradient only touches even voxels
+            else:
+                dskip = [torch.empty_like(t) for t in inputs]
+            ops.conv_gemm(sk.dgrad, [g2], sk.dgrad.packed_weight(blk.skip_conv.weight), dskip, sk.grid)
+            addends = dskip
+        else:
+            addends = [g2]
+        dins = [torch.empty_like(t) for t in inputs]
+        ops.conv_gemm(c1.dgrad, [dy1], c1.dgrad.packed_weight(blk.conv1.weight), dins, c1.grid, addends=addends)
+        return dins
+
+    def backward_impl(self, tape, x_shape, dlogits: torch.Tensor) -> Dict[torch.nn.Parameter, torch.Tensor]:
+        net = self.model.net
+        plans = self._get_plans(x_shape)
+        np_ = net.num_pool
+        grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        # head
+        a_last, wf = tape["head"]
+        K, cl = net.fc.out_channels, net.fc.in_channels
+        d_cur = torch.empty_like(a_last)
+        dwf = torch.zeros(K * wf.shape[1] + K, device=self.device)
+        ops.head_bwd(dlogits.contiguous(), a_last, wf, d_cur, dwf)
+        grads[net.fc.weight] = dwf[:K * wf.shape[1]].view(K, wf.shape[1])[:, :cl].reshape(net.fc.weight.shape)
+        grads[net.fc.bias] = dwf[K * wf.shape[1]:].clone()
+        pending = {}
+        for i in range(np_):
+            dec = net.decode_blocks[i]
+            d_up, d_skip = self._res_block_bwd(dec, plans[("dec", i)], tape[("dec", i)], d_cur, None, grads)
+            pending[i] = d_skip
+            xin, yu, tu, au = tape[("up", i)]
+            ct = net.up_blocks[i].conv_trans.up[0]
+            uop = plans[("up", i)]
+            _, dyu, _, dsum = self._in_bwd(d_up, None, au, yu, tu, zero_last=True, want_dsum=True)
+            grads[ct.weight] = self._wgrad(uop, [xin], dyu, ct.weight)
+            grads[ct.bias] = dsum[:ct.out_channels].float()
+            d_cur = torch.empty_like(xin)
+            ops.conv_gemm(uop.dgrad, [dyu], uop.dgrad.packed_weight(ct.weight), [d_cur], uop.grid)
+        for j in range(len(net.encode_blocks[np_].res_blocks) - 1, -1, -1):
+            blk = net.encode_blocks[np_].res_blocks[j]
+            d_cur = self._res_block_bwd(blk, plans[("enc", np_, j)], tape[("enc", np_, j)], d_cur, None, grads)[0]
+        for i in range(np_ - 1, -1, -1):
+            d_cur = self._res_block_bwd(net.pool_blocks[i], plans[("pool", i)], tape[("pool", i)], d_cur, None, grads)[0]
+            nblk = len(net.encode_blocks[i].res_blocks)
+            for j in range(nblk - 1, -1, -1):
+                blk = net.encode_blocks[i].res_blocks[j]
+                d2 = pending[i] if j == nblk - 1 else None
+                d_cur = self._res_block_bwd(blk, plans[("enc", i, j)], tape[("enc", i, j)], d_cur, d2, grads)[0]
+        # stem
+        c0 = net.conv.out_channels
+        cp0 = d_cur.shape[-1]
+        dw0 = torch.zeros(28 * cp0, device=self.device)
+        ops.stem_wgrad(tape["x"], d_cur, dw0)
+        dw0 = dw0.view(28, cp0)
+        grads[net.conv.weight] = dw0[:27, :c0].t().reshape(net.conv.weight.shape)
+        grads[net.conv.bias] = dw0[27, :c0].clone()
+        return grads
+
+
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng: ResUNetEngine, *params):
+        logits, tape = eng.forward_impl(x.detach(), save=True)
+        ctx.eng, ctx.tape, ctx.x_shape, ctx.params = eng, tape, tuple(x.shape), params
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        grads = ctx.eng.backward_impl(ctx.tape, ctx.x_shape, dlogits)
+        ctx.tape = None
+        out = [grads.get(p) if p.requires_grad else None for p in ctx.params]
+        return (None, None, *out)

@@ -1,0 +1,130 @@
+"""Drop-in replacements for the reference's ``loss.py`` modules, on the fused CUDA loss kernels.
+
+  DiceLoss(weight_c=None, weight_v=None, alpha=0.5, beta=0.5, smooth=1e-7)      loss.py:123-166
+  FocalLoss(gamma=2, weight_c=None, weight_v=None)                              loss.py:169-193
+  HybirdLoss(gamma=2, weight_c=None, weight_v=None, alpha=0.5, beta=0.5, ...)   loss.py:196-254
+  Dice(weight_v=None, alpha=0.5, beta=0.5, smooth=1e-7)   (metric)              loss.py:85-120
+
+forward(input (N, C, ...) fp32 logits, target (N, ...) int64) -> 0-dim tensor (on the logits' device;
+the reference returns it on the CPU -- ``.backward()``, ``.item()`` and ``torch.isnan`` behave the same).
+
+One kernel pass computes softmax and the per-class sums {TP, sum p, sum g, focal}; the one-hot
+target (24 B/voxel of int64 in the reference, loss.py:27) is never materialised.  As in the reference,
+``weight_c`` is accepted and ignored (it is overwritten before use, loss.py:154-155) and the sums
+run over the whole batch (batch-Dice).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _class_weights(c: int, weight_v, device) -> torch.Tensor:
+    w = torch.ones(c, dtype=torch.float64) if weight_v is None else torch.as_tensor(weight_v, dtype=torch.float64)
+    return (w / w.abs().sum().clamp_min(1e-12)).to(device)          # F.normalize(p=1), loss.py:155
+
+
+class _SegLossFn(torch.autograd.Function):
+    """mode bits: 1 = dice term (1 - d), 2 = focal term, 4 = dice metric (+d instead of 1 - d)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, w, alpha, beta, smooth, gamma, mode):
+        if not logits.is_cuda:
+            raise RuntimeError("unet3d_b200 losses run on CUDA tensors only")
+        n, k = logits.shape[:2]
+        if k < 2:
+            raise RuntimeError("single-channel (sigmoid) losses are not supported: the reference itself "
+                               "fails in one_hot for C == 1 (SURVEY.md 3.4)")
+        lg = logits.detach().contiguous().float()
+        tg = target.detach().contiguous()
+        if tg.dtype != torch.int64:
+            tg = tg.long()
+        v = lg[0, 0].numel()
+        sums = torch.zeros(k, 4, dtype=torch.float64, device=lg.device)
+        ops.loss_fwd(lg, tg, sums, gamma)
+        tp, sp, sg, fo = sums[:, 0], sums[:, 1], sums[:, 2], sums[:, 3]
+        den = (1 - alpha - beta) * tp + alpha * sg + beta * sp + smooth
+        dice = (tp + smooth) / den
+        total = torch.zeros((), dtype=torch.float64, device=lg.device)
+        a = torch.zeros(k, dtype=torch.float64, device=lg.device)
+        b = torch.zeros_like(a)
+        f = torch.zeros_like(a)
+        ddice_dtp = (den - (tp + smooth) * (1 - alpha - beta)) / (den * den)
+        ddice_dsp = -(tp + smooth) * beta / (den * den)
+        if mode & 1:
+            total = total + (w * (1 - dice)).sum()
+            a, b = a - w * ddice_dtp, b - w * ddice_dsp
+        if mode & 4:
+            total = total + (w * dice).sum()
+            a, b = a + w * ddice_dtp, b + w * ddice_dsp
+        if mode & 2:
+            scale = float(k) / float(n * v)                              # C * mean over rows, loss.py:80
+            total = total + (w * fo * scale).sum()
+            f = w * scale
+        coef = torch.stack([a, b, f, torch.zeros_like(a)], dim=1).float().contiguous()
+        ctx.save_for_backward(lg, tg, coef)
+        ctx.gamma, ctx.use_focal = gamma, bool(mode & 2)
+        return total.float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        lg, tg, coef = ctx.saved_tensors
+        dl = torch.empty_like(lg)
+        ops.loss_bwd(lg, tg, coef, gout.detach().float().contiguous().view(1), dl, ctx.gamma, ctx.use_focal)
+        return dl, None, None, None, None, None, None, None
+
+
+class DiceLoss(nn.Module):
+    def __init__(self, weight_c=None, weight_v=None, alpha=0.5, beta=0.5, smooth=1e-7):
+        super().__init__()
+        self.weight_c, self.weight_v, self.alpha, self.beta, self.smooth = weight_c, weight_v, alpha, beta, smooth
+
+    def forward(self, input, target):
+        w = _class_weights(input.size(1), self.weight_v, input.device)
+        return _SegLossFn.apply(input, target, w, self.alpha, self.beta, self.smooth, 0.0, 1)
+
+
+class Dice(nn.Module):
+    def __init__(self, weight_v=None, alpha=0.5, beta=0.5, smooth=1e-7):
+        super().__init__()
+        self.weight_v, self.alpha, self.beta, self.smooth = weight_v, alpha, beta, smooth
+
+    def forward(self, input, target):
+        w = _class_weights(input.size(1), self.weight_v, input.device)
+        return _SegLossFn.apply(input, target, w, self.alpha, self.beta, self.smooth, 0.0, 4)
+
+
+class FocalLoss(nn.Module):
+    def __init__(self, gamma=2, weight_c=None, weight_v=None):
+        super().__init__()
+        self.gamma, self.weight_c, self.weight_v = gamma, weight_c, weight_v
+
+    def forward(self, input, target):
+        w = _class_weights(input.size(1), self.weight_v, input.device)
+        return _SegLossFn.apply(input, target, w, 0.5, 0.5, 1e-7, float(self.gamma), 2)
+
+
+class HybirdLoss(nn.Module):
+    """(sic) the reference's spelling, loss.py:196."""
+
+    def __init__(self, gamma=2, weight_c=None, weight_v=None, alpha=0.5, beta=0.5, smooth=1e-7):
+        super().__init__()
+        self.gamma, self.weight_c, self.weight_v = gamma, weight_c, weight_v
+        self.alpha, self.beta, self.smooth = alpha, beta, smooth
+
+    def forward(self, input, target):
+        w = _class_weights(input.size(1), self.weight_v, input.device)
+        return _SegLossFn.apply(input, target, w, self.alpha, self.beta, self.smooth, float(self.gamma), 3)
+
+
+def dice(input, target, alpha=0.5, beta=0.5, smooth=1e-7):
+    """Free function of loss.py:32-48 (probabilities / one-hot in, scalar out), used by trainer.evaluate_case
+    on CPU arrays: tiny bookkeeping, plain tensor arithmetic on whatever device the inputs live on."""
+    p = input.reshape(-1).float()
+    g = target.reshape(-1).float()
+    tp = (p * g).sum()
+    fn = ((1 - p) * g).sum()
+    fp = (p * (1 - g)).sum()
+    return (tp + smooth) / (tp + alpha * fn + beta * fp + smooth)

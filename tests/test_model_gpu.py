@@ -1,0 +1,114 @@
+"""Whole-network parity on the GPU: ResUnet3D (CUDA, bf16 activations) against the fp32 CPU oracle
+with identical weights and inputs.  Tolerances are the north-star's: logits rel-L2 <= 1e-2 (bf16),
+argmax agreement >= 99.9 %, Dice within 1e-3; per-layer gradients rel-L2 <= 6e-2 (bf16 through ~40 layers),
+absolute tolerance for the IN-cancelled conv biases."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import unet3d_b200  # noqa: E402
+from unet3d_b200 import ops  # noqa: E402
+from oracle import unet3d_oracle as O  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def _run(num_pool, nf, shape, seed=0, train=False, loss_kind="hybrid"):
+    torch.manual_seed(seed)
+    model = unet3d_b200.ResUnet3D(num_pool=num_pool, num_features=nf, out_channels=3)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(*shape, generator=g)
+    y = torch.randint(0, 3, (shape[0], *shape[2:]), generator=torch.Generator().manual_seed(4321))
+    model = model.to(DEV)
+    model.train(train)
+    if train:
+        torch.manual_seed(77)
+    logits = model(x.to(DEV))
+    if loss_kind == "hybrid":
+        loss_mod = unet3d_b200.HybirdLoss(weight_v=[1, 148, 191], alpha=0.9, beta=0.1)
+        ofn = lambda lg: O.hybrid_loss(lg, y, weight_v=[1, 148, 191], alpha=0.9, beta=0.1)
+    else:
+        loss_mod = unet3d_b200.DiceLoss()
+        ofn = lambda lg: O.dice_loss(lg, y)
+    loss = loss_mod(logits, y.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    ops.check_device_errors()
+    # oracle
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    masks = None
+    if train:
+        masks = O.DropoutMasks(train=True, replay=[m.cpu() for m in model.last_dropout_masks])
+    ref_logits = O.resunet3d_forward(sdr, x, num_pool, nf, masks=masks)
+    ref_loss = ofn(ref_logits)
+    ref_loss.backward()
+    return model, logits.detach().cpu(), loss.item(), sdr, ref_logits.detach(), ref_loss.item(), y
+
+
+def _check(model, logits, loss, sdr, ref_logits, ref_loss, y, grad_tol=6e-2):
+    assert rel(logits, ref_logits) < 1e-2, rel(logits, ref_logits)
+    agree = (logits.argmax(1) == ref_logits.argmax(1)).float().mean().item()
+    assert agree >= 0.999, agree
+    d1 = O.dice_per_class(logits, y)
+    d2 = O.dice_per_class(ref_logits, y)
+    assert (d1 - d2).abs().max().item() < 1e-3
+    assert abs(loss - ref_loss) < 5e-3 * max(1.0, abs(ref_loss))
+    worst = []
+    for name, p in model.named_parameters():
+        rg = sdr[name].grad
+        if rg is None:
+            assert p.grad is None, name           # unused skip_conv parameters
+            continue
+        assert p.grad is not None, name
+        gpu = p.grad.detach().cpu()
+        if name.endswith("bias") and ("conv1" in name or "conv2" in name):
+            assert gpu.abs().max().item() < 1e-5 + 10 * rg.abs().max().item(), name     # S1: ~0 in the reference
+            continue
+        r = rel(gpu, rg)
+        worst.append((r, name))
+        assert r < grad_tol, (name, r)
+    return sorted(worst)[-3:]
+
+
+def test_small_net_eval():
+    out = _run(2, 8, (2, 1, 16, 16, 16))
+    print(_check(*out))
+
+
+def test_small_net_odd_sizes_dice():
+    out = _run(2, 8, (1, 1, 24, 20, 12), loss_kind="dice")
+    print(_check(*out))
+
+
+def test_small_net_train_masks():
+    out = _run(2, 8, (2, 1, 16, 16, 16), train=True)
+    print(_check(*out))
+
+
+def test_default_net_32():
+    out = _run(4, 30, (1, 1, 32, 32, 32))
+    print(_check(*out))
+
+
+def test_state_dict_roundtrip_and_nograd():
+    torch.manual_seed(0)
+    m = unet3d_b200.ResUnet3D(num_pool=2, num_features=8, out_channels=3).to(DEV).eval()
+    x = torch.randn(1, 1, 16, 16, 16, device=DEV)
+    with torch.no_grad():
+        a = m(x)
+    m2 = unet3d_b200.ResUnet3D(num_pool=2, num_features=8, out_channels=3).to(DEV).eval()
+    m2.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        b = m2(x)
+    assert torch.equal(a, b)
+    assert a.shape == (1, 3, 16, 16, 16) and a.dtype == torch.float32
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 1, 18, 16, 16, device=DEV))        # not divisible by 2^num_pool
+    with pytest.raises(RuntimeError):
+        m.cpu()(torch.randn(1, 1, 16, 16, 16))                # no CPU path

@@ -87,3 +87,40 @@ def test_convT_fwd_and_dgrad(cin, cout):
     plan2 = P.make_conv_plan("convT_dgrad", 3, 2, [cout], [cin], D)
     outs2 = run_conv_plan(plan2, [to_ndhwc(dyz, P.pad_channels(cout))], pack_weights(plan2, w), (N, D, H, W), (D, H, W))
     assert torch.allclose(from_ndhwc(outs2[0], cin), x.grad, atol=1e-4, rtol=1e-4)
+
+
+from tests.emulate import run_wgrad_plan
+
+
+@pytest.mark.parametrize("kind,ks,stride,cins,cout", [
+    ("conv", 3, 1, [30], 30), ("conv", 3, 1, [30, 30], 30), ("conv", 1, 1, [60, 60], 60), ("conv", 3, 1, [120], 24),
+    ("conv", 3, 1, [136], 8), ("conv", 3, 2, [30], 60), ("conv", 1, 2, [30], 60), ("conv", 3, 1, [8], 8),
+    ("conv", 3, 1, [40], 20), ("convT", 3, 2, [60], 30), ("convT", 3, 2, [24], 8)])
+def test_wgrad_plans(kind, ks, stride, cins, cout):
+    N, D, H, W = 1, 2, 3, 4
+    g = torch.Generator().manual_seed(5)
+    if kind == "conv":
+        fd = (D * stride, H * stride, W * stride)
+        x = torch.randn(N, sum(cins), *fd, generator=g)
+        w = (torch.randn(cout, sum(cins), ks, ks, ks, generator=g) * 0.1).requires_grad_(True)
+        y = F.conv3d(x, w, None, stride=stride, padding=ks // 2)
+        dy = torch.randn(y.shape, generator=g)
+        y.backward(dy)
+        xs, off = [], 0
+        for c in cins:
+            xs.append(to_ndhwc(x[:, off:off + c], P.pad_channels(c))); off += c
+        dyn = to_ndhwc(dy, P.pad_channels(cout))
+    else:
+        x = torch.randn(N, cins[0], D, H, W, generator=g)
+        w = (torch.randn(cins[0], cout, 3, 3, 3, generator=g) * 0.1).requires_grad_(True)
+        y = F.pad(F.conv_transpose3d(x, w, None, stride=2, padding=1), (0, 1, 0, 1, 0, 1))
+        dy = torch.randn(y.shape, generator=g)
+        y.backward(dy)
+        dyz = dy.clone()
+        dyz[:, :, -1] = 0; dyz[:, :, :, -1] = 0; dyz[..., -1] = 0
+        xs = [to_ndhwc(x, P.pad_channels(cins[0]))]
+        dyn = to_ndhwc(dyz, P.pad_channels(cout))
+    plan = P.make_wgrad_plan(kind, ks, stride, cins, cout, (N, D, H, W))
+    dw = run_wgrad_plan(plan, xs, dyn, (N, D, H, W))
+    got = dw[torch.from_numpy(plan.gidx)].reshape(w.shape).float()
+    assert torch.allclose(got, w.grad, atol=1e-3, rtol=1e-3), (got - w.grad).abs().max()

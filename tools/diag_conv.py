@@ -65,7 +65,9 @@ def run(kind, ks, stride, cins, couts, dims, bias=False, stats=False, addend=Fal
             o.zero_()
     adds = None
     if addend:
-        adds = [torch.randn_like(o.float()).to(torch.bfloat16) for o in outs]
+        adds = [torch.zeros_like(o) for o in outs]
+        for a_, r_ in zip(adds, ref):
+            a_[..., :r_.shape[1]] = torch.randn(*a_.shape[:-1], r_.shape[1], device=dev)
     st = torch.zeros(N, outs[0].shape[-1], 2, device=dev, dtype=torch.float64) if stats else None
     ops.conv_gemm(dp, inputs, wp, outs, grid, bias=bp, addends=adds, stats=st, zero_last=(kind == "convT_fwd"))
     torch.cuda.synchronize()

@@ -22,6 +22,7 @@ struct SmemCtl {
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   int abort_flag;
+  uint32_t tap_off[32];     // byte offset of each tap's window inside an A slab
 };
 
 // column sums over the 32 lanes of a warp: in v[j] = value of column j for this lane's row;
@@ -82,118 +83,138 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
     tmem_alloc(smem_u32(&ctl->tmem_base), 512);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 96 && threadIdx.x < 96 + 32 && (int)threadIdx.x - 96 < p.n_taps) {
+    const int sh = tab_shift[threadIdx.x - 96];
+    ctl->tap_off[threadIdx.x - 96] =
+        (uint32_t)(sh & 0xff) * plane_pitch + (uint32_t)(((sh >> 8) & 0xff) * CG_WB + ((sh >> 16) & 0xff)) * 16;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
   volatile int* abort_flag = &ctl->abort_flag;
+  const uint32_t* tap_off = ctl->tap_off;
 
   const int n_tiles = p.N * p.segs_d * p.tiles_h * p.tiles_w;
 
+  // The three single-issuer roles keep their whole warp converged and guard only the issuing
+  // instructions with elect.sync: descriptors / coordinates then stay in uniform registers
+  // (a `lane == 0` region makes ptxas serialise every TMA / MMA operand through a waterfall loop).
+  const int planes_i = planes, G = p.G, nblk = p.nblk, Dt = p.Dt, n_cg = p.n_cg;
   if (warp == 0) {
     // ================= A producer =================
-    if (lane == 0) {
+    if (elect_one())
       for (int i = 0; i < CG_MAX_MAPS; ++i) tma_prefetch_desc(&p.amap[i]);
-      uint32_t a_it = 0;
-      bool ok = true;
-      for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
-        const int nb = item / n_tiles;
-        int t = item - nb * n_tiles;
-        const int tw = t % p.tiles_w; t /= p.tiles_w;
-        const int th = t % p.tiles_h; t /= p.tiles_h;
-        const int seg = t % p.segs_d;
-        const int n = t / p.segs_d;
-        const int w0 = tw * CG_WT - 1, h0 = th * CG_HT - 1, d0 = seg * p.Dt - 1;
-        for (int cg = 0; cg < p.n_cg; ++cg) {
-          if (__ldg(&tab_mask[nb * p.n_cg + cg]) == 0) continue;
-          const uint32_t st = a_it & 1, ph = (a_it >> 1) & 1;
-          if (!mbar_wait(smem_u32(&ctl->a_empty[st]), ph ^ 1, abort_flag, p.err, 101)) { ok = false; break; }
-          const uint32_t full = smem_u32(&ctl->a_full[st]);
-          mbar_expect_tx(full, (uint32_t)planes * p.G * CG_BOX_BYTES);
-          const CUtensorMap* m = &p.amap[__ldg(&tab_map[cg])];
-          const int ch0 = __ldg(&tab_ch[cg]);
+    uint32_t a_it = 0;
+    bool ok = true;
+    for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
+      const int nb = item / n_tiles;
+      int t = item - nb * n_tiles;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int seg = t % p.segs_d;
+      const int n = t / p.segs_d;
+      const int w0 = tw * CG_WT - 1, h0 = th * CG_HT - 1, d0 = seg * Dt - 1;
+      for (int cg = 0; cg < n_cg; ++cg) {
+        if (__ldg(&tab_mask[nb * n_cg + cg]) == 0) continue;
+        const uint32_t st = a_it & 1, ph = (a_it >> 1) & 1;
+        if (!mbar_wait(smem_u32(&ctl->a_empty[st]), ph ^ 1, abort_flag, p.err, 101)) { ok = false; break; }
+        const uint32_t full = smem_u32(&ctl->a_full[st]);
+        const CUtensorMap* m = &p.amap[__ldg(&tab_map[cg])];
+        const int ch0 = __ldg(&tab_ch[cg]);
+        if (elect_one()) {
+          mbar_expect_tx(full, (uint32_t)planes_i * G * CG_BOX_BYTES);
           uint32_t dst = slab0 + st * slab_bytes;
-          for (int pl = 0; pl < planes; ++pl)
-            for (int g = 0; g < p.G; ++g, dst += CG_CHUNK_PITCH)
+          for (int pl = 0; pl < planes_i; ++pl)
+            for (int g = 0; g < G; ++g, dst += CG_CHUNK_PITCH)
               tma_load_5d(dst, m, full, ch0 + g * 8, w0, h0, d0 + pl, n);
-          ++a_it;
         }
+        __syncwarp();
+        ++a_it;
       }
     }
   } else if (warp == 1) {
     // ================= W producer =================
-    if (lane == 0) {
-      uint32_t w_it = 0;
-      bool ok = true;
-      for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
-        const int nb = item / n_tiles;
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)__ldg(&tab_wbase[nb]) * wtile_bytes;
-        for (int cg = 0; cg < p.n_cg && ok; ++cg) {
-          uint32_t mask = (uint32_t)__ldg(&tab_mask[nb * p.n_cg + cg]);
-          while (mask) {
-            mask &= mask - 1;
-            const uint32_t st = w_it % CG_W_STAGES, ph = (w_it / CG_W_STAGES) & 1;
-            if (!mbar_wait(smem_u32(&ctl->w_empty[st]), ph ^ 1, abort_flag, p.err, 102)) { ok = false; break; }
+    uint32_t w_it = 0;
+    bool ok = true;
+    for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
+      const int nb = item / n_tiles;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)__ldg(&tab_wbase[nb]) * wtile_bytes;
+      for (int cg = 0; cg < n_cg && ok; ++cg) {
+        uint32_t mask = (uint32_t)__ldg(&tab_mask[nb * n_cg + cg]);
+        while (mask) {
+          mask &= mask - 1;
+          const uint32_t st = w_it % CG_W_STAGES, ph = (w_it / CG_W_STAGES) & 1;
+          if (!mbar_wait(smem_u32(&ctl->w_empty[st]), ph ^ 1, abort_flag, p.err, 102)) { ok = false; break; }
+          if (elect_one()) {
             const uint32_t full = smem_u32(&ctl->w_full[st]);
             mbar_expect_tx(full, wtile_bytes);
             bulk_load(wring0 + st * wtile_bytes, src, wtile_bytes, full);
-            src += wtile_bytes;
-            ++w_it;
           }
+          __syncwarp();
+          src += wtile_bytes;
+          ++w_it;
         }
       }
     }
   } else if (warp == 2) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.nblk, 0, 0);
-      uint32_t a_it = 0, w_it = 0, acc_it = 0;
-      bool ok = true;
-      for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
-        const int nb = item / n_tiles;
-        const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
-        if (!mbar_wait(smem_u32(&ctl->acc_empty[buf]), aph ^ 1, abort_flag, p.err, 103)) break;
+    const uint32_t idesc = umma_idesc_bf16(128, nblk, 0, 0);
+    const int G2 = G / 2;
+    // descriptor increments (the start-address field counts 16-byte units)
+    const uint64_t a_dinc = (uint64_t)(plane_pitch >> 4), a_kinc = (uint64_t)((2 * CG_CHUNK_PITCH) >> 4);
+    const uint64_t b_kinc = (uint64_t)((2 * nblk * 16) >> 4);
+    uint32_t a_it = 0, w_it = 0, acc_it = 0;
+    bool ok = true;
+    for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
+      const int nb = item / n_tiles;
+      const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+      if (!mbar_wait(smem_u32(&ctl->acc_empty[buf]), aph ^ 1, abort_flag, p.err, 103)) break;
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * 256;
+      uint32_t accum = 0;                       // 0 for the first tap of the item: overwrite the accumulators
+      for (int cg = 0; cg < n_cg && ok; ++cg) {
+        uint32_t mask = (uint32_t)__ldg(&tab_mask[nb * n_cg + cg]);
+        if (mask == 0) continue;
+        const uint32_t ast = a_it & 1, aphase = (a_it >> 1) & 1;
+        if (!mbar_wait(smem_u32(&ctl->a_full[ast]), aphase, abort_flag, p.err, 104)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * 256;
-        bool fresh = true;
-        for (int cg = 0; cg < p.n_cg && ok; ++cg) {
-          uint32_t mask = (uint32_t)__ldg(&tab_mask[nb * p.n_cg + cg]);
-          if (mask == 0) continue;
-          const uint32_t ast = a_it & 1, aphase = (a_it >> 1) & 1;
-          if (!mbar_wait(smem_u32(&ctl->a_full[ast]), aphase, abort_flag, p.err, 104)) { ok = false; break; }
+        const uint32_t slab = slab0 + ast * slab_bytes;
+        while (mask) {
+          const int tap = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const uint32_t wst = w_it % CG_W_STAGES, wph = (w_it / CG_W_STAGES) & 1;
+          if (!mbar_wait(smem_u32(&ctl->w_full[wst]), wph, abort_flag, p.err, 105)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t slab = slab0 + ast * slab_bytes;
-          while (mask) {
-            const int tap = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const uint32_t wst = w_it % CG_W_STAGES, wph = (w_it / CG_W_STAGES) & 1;
-            if (!mbar_wait(smem_u32(&ctl->w_full[wst]), wph, abort_flag, p.err, 105)) { ok = false; break; }
-            tc_fence_after();
-            const int sh = __ldg(&tab_shift[tap]);
-            const int sd = sh & 0xff, shh = (sh >> 8) & 0xff, sw = (sh >> 16) & 0xff;
-            const uint32_t a_tap = slab + (uint32_t)sd * plane_pitch + (uint32_t)(shh * CG_WB + sw) * 16;
-            const uint32_t b_tap = wring0 + wst * wtile_bytes;
-            for (int d = 0; d < p.Dt; ++d) {
-              for (int kk = 0; kk < p.G / 2; ++kk) {
-                const uint64_t adesc =
-                    umma_desc(a_tap + (uint32_t)d * plane_pitch + (uint32_t)(2 * kk) * CG_CHUNK_PITCH,
-                              CG_CHUNK_PITCH, CG_WB * 16);
-                const uint64_t bdesc = umma_desc(b_tap + (uint32_t)(2 * kk) * p.nblk * 16, (uint32_t)p.nblk * 16, 128);
-                tc_mma_bf16(acc0 + (uint32_t)d * p.nblk, adesc, bdesc, idesc, (fresh && kk == 0) ? 0u : 1u);
+          const uint64_t adesc0 = umma_desc(slab + tap_off[tap], CG_CHUNK_PITCH, CG_WB * 16);
+          const uint64_t bdesc0 = umma_desc(wring0 + wst * wtile_bytes, (uint32_t)nblk * 16, 128);
+          if (elect_one()) {
+            uint64_t ad = adesc0;
+            uint32_t acc = acc0;
+            for (int d = 0; d < Dt; ++d, ad += a_dinc, acc += nblk) {
+              uint64_t a = ad, b = bdesc0;
+              tc_mma_bf16(acc, a, b, idesc, accum);
+              for (int kk = 1; kk < G2; ++kk) {
+                a += a_kinc;
+                b += b_kinc;
+                tc_mma_bf16(acc, a, b, idesc, 1u);
               }
             }
             tc_commit(smem_u32(&ctl->w_empty[wst]));
-            ++w_it;
-            fresh = false;
           }
-          if (!ok) break;
-          tc_commit(smem_u32(&ctl->a_empty[ast]));
-          ++a_it;
+          __syncwarp();
+          ++w_it;
+          accum = 1;
         }
         if (!ok) break;
-        tc_commit(smem_u32(&ctl->acc_full[buf]));
-        ++acc_it;
+        if (elect_one()) tc_commit(smem_u32(&ctl->a_empty[ast]));
+        __syncwarp();
+        ++a_it;
       }
+      if (!ok) break;
+      if (elect_one()) tc_commit(smem_u32(&ctl->acc_full[buf]));
+      __syncwarp();
+      ++acc_it;
     }
   } else {
     // ================= epilogue (warps 3..6) =================

@@ -11,6 +11,7 @@ struct WgCtl {
   uint64_t full[2], empty[2], acc_full;
   uint32_t tmem_base;
   int abort_flag;
+  uint32_t ent_aoff[16], ent_col[16];
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -51,24 +52,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
     tmem_alloc(smem_u32(&ctl->tmem_base), 512);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64 && (int)threadIdx.x - 64 < n_ent && threadIdx.x < 64 + 16) {
+    const int* ent = jt + WG_J_ENT + (threadIdx.x - 64) * WG_E_SIZE;
+    ctl->ent_aoff[threadIdx.x - 64] = (uint32_t)ent[WG_E_AOFF];
+    ctl->ent_col[threadIdx.x - 64] = (uint32_t)ent[WG_E_COL];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
   volatile int* abort_flag = &ctl->abort_flag;
+  const uint32_t* ent_aoff = ctl->ent_aoff;
+  const uint32_t* ent_col = ctl->ent_col;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one())
       for (int i = 0; i < WG_MAX_MAPS; ++i) tma_prefetch_desc(&p.map[i]);
-      uint32_t it = 0;
-      for (int t = sid; t < n_tiles; t += p.split, ++it) {
-        const uint32_t st = it & 1, ph = (it >> 1) & 1;
-        if (!mbar_wait(smem_u32(&ctl->empty[st]), ph ^ 1, abort_flag, p.err, 201)) break;
-        int r = t;
-        const int tw = r % p.tiles_w; r /= p.tiles_w;
-        const int th = r % p.tiles_h; r /= p.tiles_h;
-        const int seg = r % segs;
-        const int n = r / segs;
+    uint32_t it = 0;
+    for (int t = sid; t < n_tiles; t += p.split, ++it) {
+      const uint32_t st = it & 1, ph = (it >> 1) & 1;
+      if (!mbar_wait(smem_u32(&ctl->empty[st]), ph ^ 1, abort_flag, p.err, 201)) break;
+      int r = t;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; r /= p.tiles_h;
+      const int seg = r % segs;
+      const int n = r / segs;
+      if (elect_one()) {
         const uint32_t full = smem_u32(&ctl->full[st]);
         mbar_expect_tx(full, (uint32_t)Px * Gx * CG_BOX_BYTES + (uint32_t)Dt * Gy * WG_DY_BOX_BYTES);
         uint32_t dst = stage0 + st * stage_bytes;
@@ -81,34 +90,42 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
             tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_YLIST + 2 * g])], full, __ldg(&jt[WG_J_YLIST + 2 * g + 1]),
                         tw * CG_WT, th * CG_HT, seg * Dt + d, n);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, Gy * 8, 1, 1);
-      uint32_t it = 0;
-      bool ok = true;
-      for (int t = sid; t < n_tiles && ok; t += p.split, ++it) {
-        const uint32_t st = it & 1, ph = (it >> 1) & 1;
-        if (!mbar_wait(smem_u32(&ctl->full[st]), ph, abort_flag, p.err, 202)) { ok = false; break; }
-        tc_fence_after();
-        const uint32_t xs = stage0 + st * stage_bytes, ys = xs + xstage;
-        for (int e = 0; e < n_ent; ++e) {
-          const int* ent = jt + WG_J_ENT + e * WG_E_SIZE;
-          const uint32_t a0 = xs + (uint32_t)__ldg(&ent[WG_E_AOFF]);
-          const uint32_t acc = tmem_base + (uint32_t)__ldg(&ent[WG_E_COL]);
+    const uint32_t idesc = umma_idesc_bf16(128, Gy * 8, 1, 1);
+    const uint64_t a_kinc = (uint64_t)((2 * CG_WB * 16) >> 4), b_kinc = (uint64_t)((2 * 128) >> 4);
+    uint32_t it = 0;
+    bool ok = true;
+    for (int t = sid; t < n_tiles && ok; t += p.split, ++it) {
+      const uint32_t st = it & 1, ph = (it >> 1) & 1;
+      if (!mbar_wait(smem_u32(&ctl->full[st]), ph, abort_flag, p.err, 202)) { ok = false; break; }
+      tc_fence_after();
+      const uint32_t xs = stage0 + st * stage_bytes, ys = xs + xstage;
+      for (int e = 0; e < n_ent; ++e) {
+        const uint32_t a0 = xs + ent_aoff[e];
+        const uint32_t acc = tmem_base + ent_col[e];
+        if (elect_one()) {
           for (int d = 0; d < Dt; ++d) {
+            uint64_t a = umma_desc(a0 + (uint32_t)d * xplane, CG_WB * 16, CG_CHUNK_PITCH);
+            uint64_t b = umma_desc(ys + (uint32_t)d * yplane, 128, WG_DY_BOX_BYTES);
+            tc_mma_bf16(acc, a, b, idesc, (it == 0 && d == 0) ? 0u : 1u);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t adesc = umma_desc(a0 + (uint32_t)d * xplane + (uint32_t)(2 * k) * (CG_WB * 16), CG_WB * 16,
-                                               CG_CHUNK_PITCH);
-              const uint64_t bdesc = umma_desc(ys + (uint32_t)d * yplane + (uint32_t)(2 * k) * 128, 128, WG_DY_BOX_BYTES);
-              tc_mma_bf16(acc, adesc, bdesc, idesc, (it == 0 && d == 0 && k == 0) ? 0u : 1u);
+            for (int k = 1; k < 8; ++k) {
+              a += a_kinc;
+              b += b_kinc;
+              tc_mma_bf16(acc, a, b, idesc, 1u);
             }
           }
         }
-        tc_commit(smem_u32(&ctl->empty[st]));
+        __syncwarp();
       }
-      if (ok) tc_commit(smem_u32(&ctl->acc_full));
+      if (elect_one()) tc_commit(smem_u32(&ctl->empty[st]));
+      __syncwarp();
+    }
+    if (ok) {
+      if (elect_one()) tc_commit(smem_u32(&ctl->acc_full));
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

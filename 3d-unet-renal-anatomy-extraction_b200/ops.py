@@ -17,6 +17,32 @@ from . import plan as P
 
 _err_words: Dict[int, torch.Tensor] = {}
 
+# bench.py instrumentation: when PROFILE is a list, the tensor-core launches append
+# (kernel name, algorithmic FLOPs, start event, end event); LAUNCHES counts every kernel enqueued.
+PROFILE = None
+LAUNCHES = 0
+
+
+def _count(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _Timed:
+    def __init__(self, name, flops):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.flops, self.e0, e1))
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -124,7 +150,10 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.stats_C = stats.shape[1] if stats is not None else 0
     a.omul = pl.omul
     a.zD, a.zH, a.zW = (d - 1, h - 1, w - 1) if zero_last else (-1, -1, -1)
-    _lib.check(_lib.lib().unet3d_conv_gemm(C.byref(a), _stream()), "unet3d_conv_gemm")
+    flops = 2.0 * grid[0] * grid[1] * grid[2] * grid[3] * sum(pl.in_C) * sum(pl.out_C) * pl.ks ** 3
+    _count()
+    with _Timed("conv_gemm_kernel", flops):
+        _lib.check(_lib.lib().unet3d_conv_gemm(C.byref(a), _stream()), "unet3d_conv_gemm")
 
 
 class DeviceWgradPlan:
@@ -147,24 +176,29 @@ def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor
     a.N, a.D, a.H, a.W = grid
     a.n_jobs, a.job_stride, a.split = pl.n_jobs, pl.job_stride, pl.split
     assert dw.dtype == torch.float32 and dw.numel() >= pl.dw_numel
-    _lib.check(_lib.lib().unet3d_wgrad_gemm(C.byref(a), _stream()), "unet3d_wgrad_gemm")
+    _count()
+    with _Timed("wgrad_gemm_kernel", pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3]):
+        _lib.check(_lib.lib().unet3d_wgrad_gemm(C.byref(a), _stream()), "unet3d_wgrad_gemm")
 
 
 # ---- memory-bound kernels ---------------------------------------------------------------------------
 def in_finalize(stats: torch.Tensor, drop: Optional[torch.Tensor], table: torch.Tensor, count: int, eps: float = 1e-5):
     nc = stats.shape[0] * stats.shape[1]
+    _count()
     _lib.check(_lib.lib().unet3d_in_finalize(stats.data_ptr(), _ptr(drop), table.data_ptr(), nc, float(count), eps,
                                              _stream()), "unet3d_in_finalize")
 
 
 def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, table: torch.Tensor):
     n, d, h, w, cp = y.shape
+    _count()
     _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), n, d * h * w, cp,
                                           _stream()), "unet3d_in_apply")
 
 
 def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
     n, d, h, w, cp = y.shape
+    _count()
     _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), out.data_ptr(), y.data_ptr(), g.data_ptr(),
                                                table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _stream()),
                "unet3d_in_bwd_reduce")
@@ -172,24 +206,28 @@ def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
 
 def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False):
     n, d, h, w, cp = y.shape
+    _count()
     _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
                                               _ptr(dsum), n, d, h, w, cp, int(zero_last), _stream()), "unet3d_in_bwd_apply")
 
 
 def channel_sum(x: torch.Tensor, dsum: torch.Tensor):
     n, d, h, w, cp = x.shape
+    _count()
     _lib.check(_lib.lib().unet3d_channel_sum(x.data_ptr(), dsum.data_ptr(), n * d * h * w, cp, _stream()),
                "unet3d_channel_sum")
 
 
 def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
     n, d, h, ww, cp = out.shape
+    _count()
     _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, d, h, ww, cp,
                                           _stream()), "unet3d_stem_fwd")
 
 
 def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
     n, d, h, ww, cp = dy.shape
+    _count()
     _lib.check(_lib.lib().unet3d_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), n, d, h, ww, cp, _stream()),
                "unet3d_stem_wgrad")
 
@@ -197,6 +235,7 @@ def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
 def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Tensor):
     n, d, h, ww, cp = a.shape
     k = logits.shape[1]
+    _count()
     _lib.check(_lib.lib().unet3d_head_fwd(a.data_ptr(), w.data_ptr(), b.data_ptr(), logits.data_ptr(), k, n, d * h * ww,
                                           cp, _stream()), "unet3d_head_fwd")
 
@@ -204,6 +243,7 @@ def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Te
 def head_bwd(dl: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tensor, dw: torch.Tensor):
     n, d, h, ww, cp = a.shape
     k = dl.shape[1]
+    _count()
     _lib.check(_lib.lib().unet3d_head_bwd(dl.data_ptr(), a.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(), k, n,
                                           d * h * ww, cp, _stream()), "unet3d_head_bwd")
 
@@ -211,6 +251,7 @@ def head_bwd(dl: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tenso
 def loss_fwd(logits, target, sums, gamma):
     n, k = logits.shape[:2]
     v = logits[0, 0].numel()
+    _count()
     _lib.check(_lib.lib().unet3d_loss_fwd(logits.data_ptr(), target.data_ptr(), sums.data_ptr(), k, n, v, float(gamma),
                                           _stream()), "unet3d_loss_fwd")
 
@@ -218,6 +259,7 @@ def loss_fwd(logits, target, sums, gamma):
 def loss_bwd(logits, target, coef, gscale, dlogits, gamma, use_focal):
     n, k = logits.shape[:2]
     v = logits[0, 0].numel()
+    _count()
     _lib.check(_lib.lib().unet3d_loss_bwd(logits.data_ptr(), target.data_ptr(), coef.data_ptr(), _ptr(gscale),
                                           dlogits.data_ptr(), k, n, v, float(gamma), int(use_focal), _stream()),
                "unet3d_loss_bwd")
@@ -226,6 +268,7 @@ def loss_bwd(logits, target, coef, gscale, dlogits, gamma, use_focal):
 def sw_accumulate(logits, window, result, weight, origin):
     k, px, py, pz = logits.shape[-4:]
     _, X, Y, Z = result.shape
+    _count()
     _lib.check(_lib.lib().unet3d_sw_accumulate(logits.data_ptr(), _ptr(window), result.data_ptr(), weight.data_ptr(), k,
                                                px, py, pz, origin[0], origin[1], origin[2], X, Y, Z, _stream()),
                "unet3d_sw_accumulate")
@@ -233,5 +276,6 @@ def sw_accumulate(logits, window, result, weight, origin):
 
 def sw_finalize(result, weight, labels, probs):
     k = result.shape[0]
+    _count()
     _lib.check(_lib.lib().unet3d_sw_finalize(result.data_ptr(), weight.data_ptr(), _ptr(labels), _ptr(probs), k,
                                              weight.numel(), _stream()), "unet3d_sw_finalize")

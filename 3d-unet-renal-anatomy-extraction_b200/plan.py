@@ -311,6 +311,7 @@ class WgradPlan:
     dw_numel: int
     ld: int
     gidx: np.ndarray            # gather: param_grad.flatten() = cat(dw, [0])[gidx]
+    flops_per_voxel: float = 0.0
 
 
 WG_ENT_MAX = 16
@@ -477,4 +478,4 @@ def make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: in
     split = max(1, min(n_tiles_max, -(-(2 * num_sms) // len(jobs))))
     return WgradPlan(kind=kind, x_maps=x_maps, y_maps=y_maps, tab=tab.reshape(-1).astype(np.int32), jobs=jobs,
                      n_jobs=len(jobs), job_stride=job_stride, split=split, dw_numel=dw_numel, ld=ld,
-                     gidx=gidx.reshape(-1).astype(np.int64))
+                     gidx=gidx.reshape(-1).astype(np.int64), flops_per_voxel=2.0 * Ktot * Ntot * k3)

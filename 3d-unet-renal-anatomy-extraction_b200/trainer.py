@@ -1,0 +1,297 @@
+"""Drop-in replacements for the hot-path parts of the reference's ``trainer.py``:
+
+  predict_per_patch(input, model, num_classes=3, patch_size=(96,96,96), step_per_patch=4,
+                    verbose=True, one_hot=False)                                   trainer.py:17-98
+  Trainer(model, optimizer, loss, dataset, ...).fit / batch_loop / save_checkpoint / load_checkpoint
+                                                                                   trainer.py:415-634
+
+Same arguments, same return values, same tile grid (including the float-step truncation of
+trainer.py:34-40) and the same checkpoint dictionary.  New, optional capabilities the
+reference does not have: Gaussian-weighted blending (``window="gaussian"``), a ``grid_mode="full_cover"``
+tile grid that reaches the volume border, tiles of one volume sharded over the ranks of a
+``torch.distributed`` job, and data-parallel training with a gradient all-reduce.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from . import parallel
+
+
+# ------------------------------------------------------------------------------------------------
+# integer index math (bit-exact with transform.py:387-437 / trainer.py:29-65)
+# ------------------------------------------------------------------------------------------------
+def center_pad_crop(a: np.ndarray, size: Sequence[int], cval=0) -> np.ndarray:
+    """Centre crop-or-pad of the leading len(size) axes to `size` (transform.py:393-437, centre mode).
+    The low edge of the window is floor((extent - size) / 2); missing voxels are filled with cval."""
+    out_shape = list(a.shape)
+    src, dst = [], []
+    for d, s in enumerate(size):
+        lo = (a.shape[d] - s) // 2                  # may be negative: then -lo voxels of padding in front
+        hi = lo + s
+        s0, s1 = max(lo, 0), min(hi, a.shape[d])
+        src.append(slice(s0, s1))
+        dst.append(slice(s0 - lo, s1 - lo))
+        out_shape[d] = s
+    out = np.full(out_shape, cval, dtype=a.dtype)
+    out[tuple(dst)] = a[tuple(src)]
+    return out
+
+
+def pad_to_patch(a: np.ndarray, patch: Sequence[int]) -> np.ndarray:
+    """transform.py:387-390: grow every axis that is shorter than the patch."""
+    return center_pad_crop(a, [max(a.shape[d], patch[d]) for d in range(len(patch))])
+
+
+def tile_centres(extent: int, patch: int, step_per_patch: int, mode: str = "reference") -> np.ndarray:
+    """Window centres along one axis.
+
+    mode="reference": exactly what ``np.arange(start, end + 1e-8, step, dtype=np.int)`` produced in the
+    reference (trainer.py:29-40): the float step is a hair below the nominal stride, numpy derives the
+    integer stride from the first two elements, so the stride is one voxel short and the last
+    voxels of the axis may stay uncovered (they come out as label 0 / NaN probabilities).
+    mode="full_cover": nominal stride, last window clamped to the border."""
+    start = patch // 2
+    end = extent - patch // 2
+    n_steps = math.ceil((end - start) / (patch / step_per_patch))
+    if mode == "reference":
+        step = (end - start) / (n_steps + 1e-8)
+        if step == 0:
+            step = 9999999
+        count = int(math.ceil((end + 1e-8 - start) / step))
+        delta = int(start + step) - start
+        return start + delta * np.arange(count, dtype=np.int64)
+    if mode == "full_cover":
+        if n_steps == 0:
+            return np.array([start], dtype=np.int64)
+        return np.unique(np.round(start + (end - start) * np.arange(n_steps + 1) / n_steps).astype(np.int64))
+    raise ValueError(mode)
+
+
+def tile_origins(shape: Sequence[int], patch: Sequence[int], step_per_patch: int, mode: str = "reference"):
+    """Window origins in the reference's visiting order (x outermost, z fastest; trainer.py:53-65)."""
+    cs = [tile_centres(shape[d], patch[d], step_per_patch, mode) for d in range(3)]
+    return [(int(x) - patch[0] // 2, int(y) - patch[1] // 2, int(z) - patch[2] // 2)
+            for x in cs[0] for y in cs[1] for z in cs[2]]
+
+
+def gaussian_window(patch: Sequence[int], sigma_scale: float = 0.125) -> np.ndarray:
+    """Separable Gaussian importance map, w(i) = exp(-((i - (p-1)/2) / (sigma_scale p))^2 / 2)."""
+    ax = [np.exp(-0.5 * ((np.arange(p, dtype=np.float64) - (p - 1) / 2.0) / (sigma_scale * p)) ** 2) for p in patch]
+    return (ax[0][:, None, None] * ax[1][None, :, None] * ax[2][None, None, :]).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# sliding-window inference
+# ------------------------------------------------------------------------------------------------
+def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step_per_patch=4, verbose=True,
+                      one_hot=False, window=None, grid_mode="reference"):
+    """input: (X, Y, Z, C_in) float32 numpy.  Returns uint8 labels (X, Y, Z) or, with one_hot=True,
+    float32 probabilities (X, Y, Z, num_classes) -- trainer.py:17-98.
+
+    window: None = uniform blending (the reference), "gaussian" or a (px,py,pz) float array = weighted.
+    Under an initialised torch.distributed job the windows are dealt round-robin to the ranks and the
+    partial sums are all-reduced; every rank returns the full result."""
+    device = next(model.parameters()).device
+    patch = tuple(int(p) for p in patch_size)
+    orig_shape = input.shape[:3]
+    vol = pad_to_patch(np.asarray(input, dtype=np.float32), patch)
+    shape = vol.shape[:3]
+    origins = tile_origins(shape, patch, step_per_patch, grid_mode)
+    rank, world = parallel.rank_world()
+    mine = origins[rank::world]
+
+    x = torch.from_numpy(np.ascontiguousarray(np.moveaxis(vol, -1, 0))[None]).to(device)      # (1, C, X, Y, Z)
+    result = torch.zeros((num_classes, *shape), dtype=torch.float32, device=device)
+    weight = torch.zeros(shape, dtype=torch.float32, device=device)
+    if isinstance(window, str):
+        if window != "gaussian":
+            raise ValueError(window)
+        window = gaussian_window(patch)
+    wdev = None if window is None else torch.as_tensor(window, dtype=torch.float32, device=device).contiguous()
+
+    was_training = model.training
+    model.eval()
+    it = mine
+    if verbose:
+        from tqdm import tqdm
+        it = tqdm(mine)
+    with torch.no_grad():
+        for (ox, oy, oz) in it:
+            tile = x[:, :, ox:ox + patch[0], oy:oy + patch[1], oz:oz + patch[2]].contiguous()
+            logits = model(tile)
+            ops.sw_accumulate(logits[0].contiguous(), wdev, result, weight, (ox, oy, oz))
+    model.train(was_training)
+    if world > 1:
+        parallel.all_reduce_sum([result, weight])
+    if one_hot:
+        probs = torch.empty((*shape, num_classes), dtype=torch.float32, device=device)
+        ops.sw_finalize(result, weight, None, probs)
+        res = probs.cpu().numpy()
+    else:
+        labels = torch.empty(shape, dtype=torch.uint8, device=device)
+        ops.sw_finalize(result, weight, labels, None)
+        res = labels.cpu().numpy()
+    ops.check_device_errors()
+    return center_pad_crop(res, orig_shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# training step loop
+# ------------------------------------------------------------------------------------------------
+class _TransformedSubset(torch.utils.data.Dataset):
+    def __init__(self, dataset, indices, transform):
+        self.dataset, self.indices, self.transform = dataset, list(indices), transform
+
+    def __len__(self):
+        return len(self.indices)
+
+    def __getitem__(self, i):
+        case = self.dataset[self.indices[i]]
+        return self.transform(case) if self.transform else case
+
+
+class Trainer:
+    """Same constructor and methods as the reference's Trainer (trainer.py:415-634).
+
+    ``use_amp=True`` in ``fit`` is accepted for compatibility: the model already computes in 16-bit
+    on the tensor cores with fp32 master weights, so no apex is involved."""
+
+    def __init__(self, model, optimizer, loss, dataset, batch_size=10,
+                 dataloader_kwargs={'num_workers': 2, 'pin_memory': True}, valid_split=0.2, num_samples=None,
+                 metrics=None, scheduler=None, train_transform=None, valid_transform=None):
+        self.model, self.optimizer, self.loss, self.dataset = model, optimizer, loss, dataset
+        self.metrics, self.scheduler = metrics, scheduler
+        self.train_transform, self.valid_transform = train_transform, valid_transform
+        order = list(range(len(dataset)))
+        n_valid = int(np.floor(valid_split * len(dataset)))
+        np.random.shuffle(order)
+        self.train_indices, self.valid_indices = order[n_valid:], order[:n_valid]
+        self.dataloader_kwargs = {'batch_size': batch_size, **dataloader_kwargs}
+        self.num_samples, self.valid_split = num_samples, valid_split
+        self.device = next(model.parameters()).device
+        self.best_result = {'loss': float('inf')}
+        self.current_epoch = 0
+        self.patience_counter = 0
+        self.amp_state_dict = None
+        self.num_epochs, self.use_amp, self.save_dir, self.progress_bar = 1, False, None, None
+
+    def get_lr(self, idx=0):
+        return self.optimizer.param_groups[idx]['lr']
+
+    def set_lr(self, lr, idx=0):
+        self.optimizer.param_groups[idx]['lr'] = lr
+
+    def summary(self, input_shape):
+        n = sum(p.numel() for p in self.model.parameters())
+        return f"{type(self.model).__name__}: {n} parameters, input {tuple(input_shape)}"
+
+    # -- one pass over a loader: the hot loop (trainer.py:465-523)
+    def batch_loop(self, data_loader, is_train=True):
+        results = []
+        bar = self.progress_bar
+        if bar is not None:
+            bar.reset(len(data_loader))
+            bar.set_description("Epoch %d/%d (LR %.2g)" % (self.current_epoch + 1, self.num_epochs, self.get_lr()))
+        for batch in data_loader:
+            x = batch['image'].to(self.device, non_blocking=True)
+            y = batch['label'].to(self.device, non_blocking=True)
+            if is_train:
+                self.model.train()
+                y_pred = self.model(x)
+            else:
+                self.model.eval()
+                with torch.no_grad():
+                    y_pred = self.model(x)
+            loss = self.loss(y_pred, y)
+            if is_train:
+                self.optimizer.zero_grad()
+                loss.backward()
+                parallel.all_reduce_gradients(self.model)
+                self.optimizer.step()
+            result = {'loss': loss.item()}
+            if self.metrics is not None:
+                with torch.no_grad():
+                    for key, fn in self.metrics.items():
+                        result[key] = fn(y_pred.detach(), y).item()
+            if not math.isnan(result['loss']):            # NaN steps are left out of the epoch mean (trainer.py:505)
+                results.append(result)
+            if bar is not None:
+                bar.set_postfix(result)
+                bar.update()
+        ops.check_device_errors()
+        mean_result = {k: float(np.mean([r[k] for r in results])) for k in results[0]}
+        if self.save_dir is not None and parallel.rank_world()[0] == 0:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                w = SummaryWriter(self.save_dir)
+                for k, v in mean_result.items():
+                    w.add_scalar('%s/%s' % (k, 'train' if is_train else 'valid'), v, self.current_epoch)
+                w.close()
+            except Exception:        # tensorboard is optional here
+                pass
+        return mean_result
+
+    def _loader(self, indices, transform, n_samples, shuffle):
+        ds = _TransformedSubset(self.dataset, indices, transform)
+        rank, world = parallel.rank_world()
+        if world > 1:
+            ds = _TransformedSubset(ds, list(range(rank, len(ds), world)), None)     # shard cases over ranks
+        if n_samples is not None:
+            sampler = torch.utils.data.RandomSampler(ds, True, max(1, n_samples // world))
+            return torch.utils.data.DataLoader(ds, sampler=sampler, **self.dataloader_kwargs)
+        return torch.utils.data.DataLoader(ds, shuffle=shuffle, **self.dataloader_kwargs)
+
+    def fit(self, num_epochs=10, save_dir=None, use_amp=False, opt_level='O1'):
+        from tqdm import tqdm
+        self.num_epochs, self.use_amp, self.save_dir = num_epochs, use_amp, save_dir
+        self.progress_bar = tqdm(total=0, disable=parallel.rank_world()[0] != 0)
+        train_loader = self._loader(self.train_indices, self.train_transform, self.num_samples, True)
+        valid_loader = None
+        if len(self.valid_indices) > 0:
+            nv = None if self.num_samples is None else round(self.num_samples * self.valid_split)
+            valid_loader = self._loader(self.valid_indices, self.valid_transform, nv, False)
+        for epoch in range(self.current_epoch, num_epochs):
+            self.current_epoch = epoch
+            result = self.batch_loop(train_loader, is_train=True)
+            if valid_loader is not None:
+                result = self.batch_loop(valid_loader, is_train=False)
+            if self.scheduler is not None:
+                if isinstance(self.scheduler, torch.optim.lr_scheduler.ReduceLROnPlateau):
+                    self.scheduler.step(result['loss'])
+                else:
+                    self.scheduler.step()
+            if result['loss'] < self.best_result['loss'] - 1e-3:
+                self.best_result = result
+                if save_dir is not None:
+                    self.save_checkpoint(save_dir + '-best.pt')
+            if save_dir is not None:
+                self.save_checkpoint(save_dir + '-last.pt')
+        self.progress_bar.close()
+
+    def save_checkpoint(self, file_path):
+        if parallel.rank_world()[0] != 0:
+            return
+        ckpt = {'model_state_dict': self.model.state_dict(), 'optimizer_state_dict': self.optimizer.state_dict(),
+                'current_epoch': self.current_epoch, 'train_indices': self.train_indices,
+                'valid_indices': self.valid_indices, 'best_result': self.best_result}
+        if self.scheduler is not None:
+            ckpt['scheduler_state_dict'] = self.scheduler.state_dict()
+        torch.save(ckpt, file_path)
+
+    def load_checkpoint(self, file_path):
+        ckpt = torch.load(file_path, map_location=self.device, weights_only=False)   # reference files hold numpy scalars
+        self.model.load_state_dict(ckpt['model_state_dict'])
+        self.optimizer.load_state_dict(ckpt['optimizer_state_dict'])
+        self.current_epoch = ckpt['current_epoch'] + 1
+        self.train_indices, self.valid_indices = ckpt['train_indices'], ckpt['valid_indices']
+        self.best_result = ckpt['best_result']
+        if 'amp_state_dict' in ckpt:
+            self.amp_state_dict = ckpt['amp_state_dict']
+        if 'scheduler_state_dict' in ckpt and self.scheduler is not None:
+            self.scheduler.load_state_dict(ckpt['scheduler_state_dict'])

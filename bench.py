@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Benchmark of the 3D U-Net training hot path (BASELINE.json metric: train voxels/s @128^3 patch).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+A "step" is one full training step of ResUnet3D(num_pool=4, num_features=30, out_channels=3) on a batch of
+2 x 1 x 128^3 synthetic patches per GPU (BASELINE.json configs[1]): zero_grad, forward, Dice loss, backward,
+[NCCL gradient all-reduce when N > 1], Adam step.  One JSON line is printed by rank 0 (see the contract in
+the task description): `value` times the step with the batch resident in HBM, `e2e` times the same step
+through the public API from pinned host memory (H2D of image + label, D2H of the loss) each step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PATCH = (128, 128, 128)
+BATCH = 2
+FWD_BWD_FLOP_PER_VOXEL = 1885512          # BASELINE.md section 3 (default net, out=3): conv FLOPs fwd + bwd
+WORKLOAD = "cfg-2: ResUnet3D(4,30,out=3) train step, batch 2 x 1x128^3 per GPU, DiceLoss, Adam"
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_port_step_time(steps, warmup, threads=None):
+    """Reference algorithm (oracle port, fp32) on the host cores: one 1x1x64^3 patch per step
+    (BASELINE.json configs[0]) -- a bounded sample of the 128^3 workload; FLOPs are linear in voxels."""
+    import torch
+    from oracle import unet3d_oracle as O
+    import unet3d_b200
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = unet3d_b200.ResUnet3D(out_channels=3)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    x = torch.randn(1, 1, 64, 64, 64)
+    y = torch.randint(0, 3, (1, 64, 64, 64))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in sd.values():
+            p.grad = None
+        masks = O.DropoutMasks(train=True)
+        loss = O.dice_loss(O.resunet3d_forward(sd, x, masks=masks), y)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), 64 ** 3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 8), min(args.warmup, 2)
+    sec, vox, cores = cpu_port_step_time(steps, max(1, warmup))
+    value = vox / sec
+    line = {"impl": "reference", "metric": "train voxels/s (fwd+bwd)", "value": value, "unit": "voxels/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": max(1, warmup), "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "reference algorithm (oracle port of network.py/loss.py, torch CPU "
+                       "ops, fp32, no optimizer) on the host cores"},
+            "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores, "kind": "port",
+                             "sample": "1 x 1x64^3 patch per step (1/16 of the 2x128^3 step; FLOPs linear in voxels)"},
+            "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--patch", type=int, default=PATCH[0], help="cubic patch edge (default 128 = the metric's config)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import unet3d_b200
+    from unet3d_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = args.steps
+    pe = args.patch
+    torch.manual_seed(0)
+    model = unet3d_b200.ResUnet3D(num_pool=4, num_features=30, in_channels=1, out_channels=3).to(dev).train()
+    loss_fn = unet3d_b200.DiceLoss()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    live = None
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    h_img = torch.randn(BATCH, 1, pe, pe, pe, generator=g).pin_memory()
+    h_lab = torch.randint(0, 3, (BATCH, pe, pe, pe), generator=torch.Generator().manual_seed(4321 + rank)).pin_memory()
+    d_img, d_lab = h_img.to(dev), h_lab.to(dev)
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    def allreduce_grads():
+        nonlocal live
+        if world == 1:
+            return
+        if live is None:
+            live = [p for p in model.parameters() if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for p in live])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        off = 0
+        for p in live:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
+
+    def step(img, lab):
+        opt.zero_grad(set_to_none=True)
+        out = model(img)
+        loss = loss_fn(out, lab)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    def timed(n_steps, e2e):
+        evs = []
+        for _ in range(n_steps):
+            l2_flush.zero_()                                  # flush L2 between timed iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if e2e:
+                img = h_img.to(dev, non_blocking=True)
+                lab = h_lab.to(dev, non_blocking=True)
+                loss = step(img, lab)
+                _ = loss.item()                               # D2H of the step's result
+            else:
+                step(d_img, d_lab)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / n_steps
+
+    for _ in range(W):
+        step(d_img, d_lab)
+    torch.cuda.synchronize()
+    ops.check_device_errors()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.PROFILE = []
+    ops.LAUNCHES = 0
+    ms = timed(K, e2e=False)
+    launches = ops.LAUNCHES
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(max(2, min(K, 5)), e2e=True)
+    ops.check_device_errors()
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    vox = BATCH * pe ** 3 * world
+
+    # dominant kernel: conv_gemm (forward + data-gradient launches) -- algorithmic FLOPs / CUDA-event time
+    roof = None
+    if rank == 0 and prof:
+        by = {}
+        for name, flops, a, b in prof:
+            d = by.setdefault(name, [0.0, 0.0, 0])
+            d[0] += flops
+            d[1] += a.elapsed_time(b)
+            d[2] += 1
+        peak, hbm, src = read_peaks()
+        name = max(by, key=lambda k: by[k][1])
+        fl, tms, cnt = by[name]
+        ach = fl / (tms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "peak_source": f"{src} (bf16_tflops_sustained)",
+                "launches_per_step": cnt // K, "kernel_ms_per_step": tms / K,
+                "per_kernel_ms_per_step": {k: v[1] / K for k, v in by.items()},
+                "per_kernel_tflops": {k: (v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None) for k, v in by.items()}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cvox, cores = cpu_port_step_time(4, 1)
+        cpu = {"value": cvox / sec, "unit": "voxels/s", "cores": cores, "kind": "port",
+               "sample": "4 steps of 1 x 1x64^3 (fwd + Dice + bwd, fp32 oracle port of network.py/loss.py)"}
+
+    if rank == 0:
+        line = {"metric": "train voxels/s (fwd+bwd)", "value": vox / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD if pe == 128 else f"REDUCED patch {pe}^3 (not the metric's config)",
+                           "global_batch": BATCH * world, "patch": [pe, pe, pe], "parallelism": f"dp{world}",
+                           "timed_region": "zero_grad + forward + DiceLoss + backward + grad all-reduce (N>1) + Adam step",
+                           "l2": "256 MB buffer written between timed iterations (L2 flush); activations per step >> L2",
+                           "tensor_frac_of_step": (FWD_BWD_FLOP_PER_VOXEL * BATCH * pe ** 3 / (ms * 1e-3) / 1e12) /
+                                                  read_peaks()[0]},
+                "e2e": {"value": vox / (ms_e2e * 1e-3), "unit": "voxels/s",
+                        "h2d_bytes_per_step": (h_img.numel() * 4 + h_lab.numel() * 8) * world, "d2h_bytes_per_step": 4 * world,
+                        "ms_per_step": ms_e2e},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+"""Host-side logic on CPU: tile grids / pad-crop index math (bit-exact vs the golden vectors made from the
+live reference), the C ABI library exports, state_dict layout, and the world_size-2 gloo paths."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import unet3d_b200
+from oracle import unet3d_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_tile_centres_match_reference_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "tile_centres.npz"))
+    for key in z.files:
+        ext, p, spp = (int(v) for v in key.split("_"))
+        assert np.array_equal(unet3d_b200.tile_centres(ext, p, spp), z[key].astype(np.int64)), key
+    assert unet3d_b200.tile_centres(512, 128, 2).tolist() == [64, 127, 190, 253, 316, 379, 442]
+    assert unet3d_b200.tile_centres(512, 128, 2, "full_cover").tolist() == [64, 128, 192, 256, 320, 384, 448]
+    assert len(unet3d_b200.tile_origins((512, 512, 256), (128, 128, 128), 2)) == 147
+
+
+def test_tile_grid_property():
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        p = int(rng.choice([8, 16, 24, 32, 96, 128]))
+        ext = int(rng.randint(p, 4 * p + 7))
+        spp = int(rng.choice([1, 2, 4]))
+        a = unet3d_b200.tile_centres(ext, p, spp)
+        assert np.array_equal(a, O.tile_centres(ext, p, spp))
+        assert a[0] - p // 2 == 0 and a[-1] + p // 2 <= ext
+        f = unet3d_b200.tile_centres(ext, p, spp, "full_cover")
+        cover = np.zeros(ext, bool)
+        for c in f:
+            cover[c - p // 2:c + p // 2] = True
+        assert cover[:ext - (p % 2)].all()
+
+
+def test_pad_crop_bit_exact():
+    rng = np.random.RandomState(1)
+    for shape, size in [((5, 6, 4), (9, 8, 8)), ((9, 4, 8), (4, 6, 8)), ((6, 6, 6), (6, 6, 6)), ((3, 10, 7), (8, 8, 8))]:
+        a = rng.randn(*shape).astype(np.float32)
+        assert np.array_equal(unet3d_b200.center_pad_crop(a, size), O.crop_pad(a, size))
+        assert np.array_equal(unet3d_b200.pad_to_patch(a, size), O.pad_to(a, size))
+    v = rng.randn(5, 6, 4, 2).astype(np.float32)
+    assert np.array_equal(unet3d_b200.pad_to_patch(v, (8, 8, 8)), O.pad_to(v, (8, 8, 8)))
+
+
+def test_gaussian_window_matches_oracle():
+    assert np.array_equal(unet3d_b200.gaussian_window((8, 12, 6)), O.gaussian_window((8, 12, 6)))
+
+
+def test_library_exports_every_declared_symbol():
+    from unet3d_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "unet3d_b200.h")).read()
+    declared = set(re.findall(r"\b(unet3d_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.exported_symbols())
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.lib().unet3d_version().startswith(b"unet3d_b200")
+
+
+def test_state_dict_layout_and_unused_params():
+    m = unet3d_b200.ResUnet3D(out_channels=3)
+    sd = m.state_dict()
+    assert len(sd) == 126 and sum(v.numel() for v in sd.values()) == 85064343
+    assert sd["net.up_blocks.3.conv_trans.up.0.weight"].shape == (480, 240, 3, 3, 3)
+    assert sd["net.decode_blocks.0.conv1.weight"].shape == (30, 60, 3, 3, 3)
+    assert unet3d_b200.UNet3D is unet3d_b200.ResUnet3D
+    assert (m.num_pool, m.num_features, m.in_channels, m.out_channels) == (4, 30, 1, 3)
+    with pytest.raises(AssertionError):
+        unet3d_b200.Unet(1, 1, [[8, 8], [16, 16]], lambda i: 1)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 16, 16, 16))         # CPU tensors are refused: no fallback path
+
+
+def _gloo_worker(rank, world, port):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unet3d_b200 import parallel
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    unused = torch.nn.Parameter(torch.zeros(5))
+    lin.register_parameter("unused", unused)
+    grads = []
+    for r in range(world):                     # what every rank would compute locally
+        lin.zero_grad()
+        lin(torch.full((2, 4), float(r + 1))).sum().backward()
+        grads.append([p.grad.clone() for p in lin.parameters() if p.grad is not None])
+    lin.zero_grad()
+    unused.grad = None
+    lin(torch.full((2, 4), float(rank + 1))).sum().backward()
+    parallel.all_reduce_gradients(lin)
+    got = [p.grad for p in lin.parameters() if p.grad is not None]
+    for i, g in enumerate(got):
+        assert torch.allclose(g, sum(gr[i] for gr in grads) / world), i
+    assert unused.grad is None                 # parameters without a gradient are left alone
+    buf = torch.zeros(7)
+    for t in parallel.shard(list(range(7)), rank, world):
+        buf[t] += t + 1
+    parallel.all_reduce_sum([buf])
+    assert buf.tolist() == [1, 2, 3, 4, 5, 6, 7]     # every window handled exactly once across ranks
+    assert parallel.rank_world() == (rank, world)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gradient_allreduce_and_tile_sharding():
+    import torch.multiprocessing as mp
+    port = 29000 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port), nprocs=2, join=True)

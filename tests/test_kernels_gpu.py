@@ -11,6 +11,8 @@ import unet3d_b200  # noqa: E402,F401
 from unet3d_b200 import ops, plan as P  # noqa: E402
 
 DEV = "cuda"
+torch.backends.cudnn.allow_tf32 = False          # the fp32 references must be real fp32
+torch.backends.cuda.matmul.allow_tf32 = False
 TOL_BF16 = 5e-3     # rel-L2 of one bf16 conv against the fp32 result on the same bf16-rounded inputs
 
 
@@ -107,8 +109,9 @@ def test_conv_gemm(kind, ks, stride, cins, couts, dims):
         for o in outs:
             o.zero_()
     adds = [torch.zeros_like(o) for o in outs]
-    for a, r in zip(adds, ref):
-        a[..., :r.shape[1]] = torch.randn(*a.shape[:-1], r.shape[1], device=DEV)
+    if not (kind == "conv_dgrad" and stride == 2 and ks == 1):     # that launch only touches even voxels: no addend
+        for a, r in zip(adds, ref):
+            a[..., :r.shape[1]] = torch.randn(*a.shape[:-1], r.shape[1], device=DEV)
     st = torch.zeros(N, outs[0].shape[-1], 2, device=DEV, dtype=torch.float64)
     ops.conv_gemm(dp, inputs, dp.packed_weight(w), outs, grid, bias=dp.packed_bias(b), addends=adds,
                   stats=st if len(outs) == 1 else None, zero_last=zero_last)

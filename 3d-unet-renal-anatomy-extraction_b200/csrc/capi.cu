@@ -83,7 +83,7 @@ const char* unet3d_version(void) { return "unet3d_b200 0.1 (sm_100a)"; }
 const char* unet3d_last_error_string(void) { return g_err; }
 int unet3d_num_sms(void) { return num_sms(); }
 
-size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk) { return conv_gemm_smem_bytes(Dt, G, nblk); }
+size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse) { return conv_gemm_smem_bytes(Dt, G, nblk, fuse); }
 
 int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
   if (!a || a->n_src < 1 || a->n_src > CG_MAX_MAPS || !a->tab || !a->w || !a->out || !a->err)
@@ -112,6 +112,7 @@ int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
   p.tiles_w = (a->W + CG_WT - 1) / CG_WT;
   p.segs_d = (a->D + a->Dt - 1) / (a->Dt > 0 ? a->Dt : 1);
   p.n_nblk = a->n_nblk; p.nblk = a->nblk; p.G = a->G; p.n_cg = a->n_cg; p.n_taps = a->n_taps;
+  p.fuse = a->fuse;
   p.out_sN = a->out_sN; p.out_sD = a->out_sD; p.out_sH = a->out_sH; p.out_sW = a->out_sW;
   p.out_C = a->out_C; p.stats_C = a->stats_C; p.omul = a->omul;
   p.zD = a->zD; p.zH = a->zH; p.zW = a->zW;

@@ -41,6 +41,62 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// All MMAs of one weight tile, fully unrolled for a compile-time (planes per segment, K steps): straight-line
+// UIADD3.64 + UTCHMMA pairs.  (A rolled loop costs ~130 cycles per MMA on the single issuing thread: every
+// uniform-datapath instruction of the loop-carried address chain stalls ~13 cycles; profiles/r01_notes.md.)
+//   FUSE == 1: tap = one (sd,sh,sw) shift, one MMA of N = nblk per (plane, K step)
+//   FUSE == 3: tap = one (sh,sw); the tile holds the d-shifts 2,1,0; input plane pl feeds output planes
+//              pl-2..pl in ONE MMA of N = cnt * nblk (first tap of an item runs unfused so that the first MMA
+//              into every accumulator overwrites it)
+template <int DT, int G2, int FUSE>
+__device__ __forceinline__ void issue_tap(uint32_t acc0, uint64_t adesc0, uint64_t bdesc0, uint32_t idesc1,
+                                          uint32_t idesc2, uint32_t idesc3, uint32_t nblk, uint32_t accum) {
+  constexpr uint64_t A_DINC = (uint64_t)((2 * G2 * CG_CHUNK_PITCH) >> 4);     // one plane
+  constexpr uint64_t A_KINC = (uint64_t)((2 * CG_CHUNK_PITCH) >> 4);          // one K=16 step (two chunks)
+  const uint64_t b_kinc = (uint64_t)(2u * FUSE * nblk);                        // (2 chunks * FUSE*nblk*16 B) / 16
+  if (FUSE == 1) {
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+#pragma unroll
+      for (int kk = 0; kk < G2; ++kk)
+        tc_mma_bf16(acc0 + (uint32_t)d * nblk, adesc0 + d * A_DINC + kk * A_KINC, bdesc0 + kk * b_kinc, idesc1,
+                    kk == 0 ? accum : 1u);
+    }
+  } else if (accum == 0) {
+#pragma unroll 1
+    for (int d = 0; d < DT; ++d) {
+#pragma unroll 1
+      for (int sd = 0; sd < 3; ++sd) {
+        uint64_t a = adesc0 + (uint64_t)(d + sd) * A_DINC, b = bdesc0 + (uint64_t)(2 - sd) * nblk;
+        for (int kk = 0; kk < G2; ++kk, a += A_KINC, b += b_kinc)
+          tc_mma_bf16(acc0 + (uint32_t)d * nblk, a, b, idesc1, (sd | kk) ? 1u : 0u);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int pl = 0; pl < DT + 2; ++pl) {
+      const int hi = pl < 2 ? pl : 2;
+      const int lo = pl - DT + 1 > 0 ? pl - DT + 1 : 0;
+      const int cnt = hi - lo + 1;
+      const uint32_t id = cnt == 3 ? idesc3 : (cnt == 2 ? idesc2 : idesc1);
+#pragma unroll
+      for (int kk = 0; kk < G2; ++kk)
+        tc_mma_bf16(acc0 + (uint32_t)(pl - hi) * nblk, adesc0 + pl * A_DINC + kk * A_KINC,
+                    bdesc0 + (uint64_t)(2 - hi) * nblk + kk * b_kinc, id, 1u);
+    }
+  }
+}
+
+template <int FUSE>
+__device__ __forceinline__ void issue_tap_dispatch(int Dt, int G2, uint32_t acc0, uint64_t a, uint64_t b, uint32_t i1,
+                                                   uint32_t i2, uint32_t i3, uint32_t nblk, uint32_t accum) {
+#define U3D_CASE(DT, GG) \
+  if (Dt == DT && G2 == GG) return issue_tap<DT, GG, FUSE>(acc0, a, b, i1, i2, i3, nblk, accum);
+  U3D_CASE(8, 1) U3D_CASE(8, 2) U3D_CASE(4, 1) U3D_CASE(4, 2) U3D_CASE(4, 3) U3D_CASE(2, 1) U3D_CASE(2, 2) U3D_CASE(2, 3)
+  U3D_CASE(1, 1) U3D_CASE(1, 2) U3D_CASE(1, 3) U3D_CASE(8, 3)
+#undef U3D_CASE
+}
+
 __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -53,7 +109,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   const int planes = p.Dt + 2;
   const uint32_t plane_pitch = (uint32_t)p.G * CG_CHUNK_PITCH;
   const uint32_t slab_bytes = (uint32_t)planes * plane_pitch;
-  const uint32_t wtile_bytes = (uint32_t)p.G * p.nblk * 16;
+  const uint32_t wtile_bytes = (uint32_t)p.G * p.fuse * p.nblk * 16;
   const uint32_t slab0 = smem_u32(smem) + 1024;
   const uint32_t wring0 = slab0 + 2 * slab_bytes;
 
@@ -160,10 +216,14 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   } else if (warp == 2) {
     // ================= MMA issuer =================
     const uint32_t idesc = umma_idesc_bf16(128, nblk, 0, 0);
+    const uint32_t idesc2 = umma_idesc_bf16(128, 2 * nblk, 0, 0), idesc3 = umma_idesc_bf16(128, 3 * nblk, 0, 0);
     const int G2 = G / 2;
+    const int fuse = p.fuse;
     // descriptor increments (the start-address field counts 16-byte units)
     const uint64_t a_dinc = (uint64_t)(plane_pitch >> 4), a_kinc = (uint64_t)((2 * CG_CHUNK_PITCH) >> 4);
-    const uint64_t b_kinc = (uint64_t)((2 * nblk * 16) >> 4);
+    const uint32_t b_lbo = (uint32_t)fuse * nblk * 16;             // stride between the two K chunks of one MMA
+    const uint64_t b_kinc = (uint64_t)((2 * b_lbo) >> 4);
+    const uint64_t b_sdinc = (uint64_t)nblk;                         // one d-tap block of rows (nblk * 16 B)
     uint32_t a_it = 0, w_it = 0, acc_it = 0;
     bool ok = true;
     for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
@@ -187,19 +247,12 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
           if (!mbar_wait(smem_u32(&ctl->w_full[wst]), wph, abort_flag, p.err, 105)) { ok = false; break; }
           tc_fence_after();
           const uint64_t adesc0 = umma_desc(slab + tap_off[tap], CG_CHUNK_PITCH, CG_WB * 16);
-          const uint64_t bdesc0 = umma_desc(wring0 + wst * wtile_bytes, (uint32_t)nblk * 16, 128);
+          const uint64_t bdesc0 = umma_desc(wring0 + wst * wtile_bytes, b_lbo, 128);
           if (elect_one()) {
-            uint64_t ad = adesc0;
-            uint32_t acc = acc0;
-            for (int d = 0; d < Dt; ++d, ad += a_dinc, acc += nblk) {
-              uint64_t a = ad, b = bdesc0;
-              tc_mma_bf16(acc, a, b, idesc, accum);
-              for (int kk = 1; kk < G2; ++kk) {
-                a += a_kinc;
-                b += b_kinc;
-                tc_mma_bf16(acc, a, b, idesc, 1u);
-              }
-            }
+            if (fuse == 1)
+              issue_tap_dispatch<1>(Dt, G2, acc0, adesc0, bdesc0, idesc, idesc2, idesc3, (uint32_t)nblk, accum);
+            else
+              issue_tap_dispatch<3>(Dt, G2, acc0, adesc0, bdesc0, idesc, idesc2, idesc3, (uint32_t)nblk, accum);
             tc_commit(smem_u32(&ctl->w_empty[wst]));
           }
           __syncwarp();
@@ -342,16 +395,16 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
 
 }  // namespace
 
-size_t conv_gemm_smem_bytes(int Dt, int G, int nblk) {
+size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse) {
   return 1024 /*align slack*/ + 1024 /*ctl*/ + 2 * (size_t)(Dt + 2) * G * CG_CHUNK_PITCH +
-         (size_t)CG_W_STAGES * G * nblk * 16;
+         (size_t)CG_W_STAGES * G * fuse * nblk * 16;
 }
 
 int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.G < 2 || (p.G & 1) || p.nblk % 32 != 0 || p.nblk > 128 || p.Dt < 1 || p.Dt * p.nblk > 256 ||
-      p.n_taps < 1 || p.n_taps > 32 || p.n_work < 1)
+      p.n_taps < 1 || p.n_taps > 32 || p.n_work < 1 || (p.Dt != 1 && p.Dt != 2 && p.Dt != 4 && p.Dt != 8) || p.G > 6 || (p.fuse != 1 && p.fuse != 3) || p.fuse * p.nblk > 256)
     return U3D_ERR_INVALID;
-  const size_t smem = conv_gemm_smem_bytes(p.Dt, p.G, p.nblk);
+  const size_t smem = conv_gemm_smem_bytes(p.Dt, p.G, p.nblk, p.fuse);
   if (smem > 227 * 1024) return U3D_ERR_INVALID;
   static bool attr_set = false;
   if (!attr_set) {

@@ -36,7 +36,7 @@ struct ConvGemmParams {
   //   then n_nblk                   output channel offset of nblock | (output tensor index << 30)
   //   then n_nblk                   output coordinate offset: od | oh << 8 | ow << 16
   const int* tab;
-  const bf16* w;          // packed weight tiles [G][nblk][8], in consumption order
+  const bf16* w;          // packed weight tiles [G][fuse * nblk][8], in consumption order
   bf16* out;          // output tensor 0
   bf16* out2;         // output tensor 1 (data gradient of a channel concat), same strides / out_C
   const float* bias;      // [n_nblk * nblk] fp32 or null
@@ -48,6 +48,7 @@ struct ConvGemmParams {
   int tiles_h, tiles_w, segs_d, Dt;
   int n_nblk, nblk;       // nblk in {32, 64, 96, 128}; Dt * nblk <= 256
   int G, n_cg, n_taps;    // G chunks (of 8 channels) per cgroup, G even
+  int fuse;               // 1, or 3: a weight tile holds the d-taps 2,1,0 of one (kh,kw) and taps carry sd = 0
   long long out_sN, out_sD, out_sH, out_sW;   // element strides of out / addend
   int out_C;              // channels physically present in out (store mask)
   int stats_C;
@@ -56,7 +57,7 @@ struct ConvGemmParams {
   int n_work;
 };
 
-size_t conv_gemm_smem_bytes(int Dt, int G, int nblk);
+size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse);
 int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 
 }  // namespace u3d

@@ -284,35 +284,68 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
 }
 
 // Stem weight/bias gradient: dW[tap][c] = sum_v x[v + tap] * dy[v][c];  db[c] = sum_v dy[v][c].
-// block = (CP/8 chunks, 28 taps [27 + bias], S voxel streams); fp32 atomics into dw[28][CP].
+// block = (CP/8 chunks, 28 taps [27 + bias row], S voxel streams); a stream walks groups of 8 consecutive
+// voxels (8 independent x / dy loads in flight per thread); fp32 atomics into dw[28][CP] at the end.
 template <int CP>
 __global__ void stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
                                   int N, int D, int H, int W) {
   const int ch = threadIdx.x, tap = threadIdx.y, s = threadIdx.z;
-  const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+  const int kd = tap / 9 - 1, kh = (tap / 3) % 3 - 1, kw = tap % 3 - 1;
   const long long V = (long long)D * H * W, total = (long long)N * V;
+  const bool row8 = (W % 8) == 0;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.z + s; i < total; i += (long long)gridDim.x * blockDim.z) {
-    const int n = (int)(i / V);
-    const long long v = i - (long long)n * V;
-    float xv = 1.f;
-    if (tap < 27) {
-      const int xw = (int)(v % W) + kw - 1, xh = (int)((v / W) % H) + kh - 1, xd = (int)(v / ((long long)W * H)) + kd - 1;
-      xv = (xw >= 0 && xw < W && xh >= 0 && xh < H && xd >= 0 && xd < D)
-               ? __ldg(x + (size_t)n * V + ((size_t)xd * H + xh) * W + xw)
-               : 0.f;
+  for (long long i0 = ((long long)blockIdx.x * blockDim.z + s) * 8; i0 < total; i0 += (long long)gridDim.x * blockDim.z * 8) {
+    float xv[8];
+    uint4 dv[8];
+    int n0 = 0, d0 = 0, h0 = 0, w0 = 0;
+    if (row8) {
+      n0 = (int)(i0 / V);
+      const long long v = i0 - (long long)n0 * V;
+      w0 = (int)(v % W); h0 = (int)((v / W) % H); d0 = (int)(v / ((long long)W * H));
     }
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (size_t)i * CP) + ch), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, f[j], acc[j]);
+    for (int u = 0; u < 8; ++u) {
+      const long long i = i0 + u;
+      xv[u] = 0.f;
+      dv[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < total) {
+        int n = n0, xd = d0, xh = h0, xw = w0 + u;
+        if (!row8) {
+          n = (int)(i / V);
+          const long long v = i - (long long)n * V;
+          xw = (int)(v % W); xh = (int)((v / W) % H); xd = (int)(v / ((long long)W * H));
+        }
+        if (tap < 27) {
+          xd += kd; xh += kh; xw += kw;
+          if (xw >= 0 && xw < W && xh >= 0 && xh < H && xd >= 0 && xd < D)
+            xv[u] = __ldg(x + (size_t)n * V + ((size_t)xd * H + xh) * W + xw);
+        } else {
+          xv[u] = 1.f;
+        }
+        dv[u] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)i * CP) + ch);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float f[8];
+      unpack8(dv[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[u], f[j], acc[j]);
+    }
   }
+  // reduce the S streams of the block in shared memory, then one atomic per (tap, channel)
+  __shared__ float red[8][28 * CP];
+  const int S = blockDim.z;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float a = acc[j];
-    atomicAdd(&dw[tap * CP + ch * 8 + j], a);
+  for (int j = 0; j < 8; ++j) red[s][tap * CP + ch * 8 + j] = acc[j];
+  __syncthreads();
+  const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+  for (int i = tid; i < 28 * CP; i += blockDim.x * blockDim.y * blockDim.z) {
+    float a = 0.f;
+    for (int r = 0; r < S; ++r) a += red[r][i];
+    atomicAdd(&dw[i], a);
   }
 }
 
@@ -706,10 +739,11 @@ int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, i
 
 int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, int Cp, int num_sms, cudaStream_t s) {
   const long long total = (long long)N * D * H * W;
-  const int streams = 1024 / (28 * (Cp / 8));
+  int streams = 512 / (28 * (Cp / 8));
+  if (streams > 8) streams = 8;
   if (streams < 1) return U3D_ERR_UNSUPPORTED;
   dim3 blk(Cp / 8, 28, streams);
-  const int g = grid_for(total, streams * 64, num_sms, 2);
+  const int g = grid_for(total, streams * 8 * 4, num_sms, 8);
   if (Cp == 32) stem_wgrad_kernel<32><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
   else if (Cp == 16) stem_wgrad_kernel<16><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
   else if (Cp == 48) stem_wgrad_kernel<48><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);

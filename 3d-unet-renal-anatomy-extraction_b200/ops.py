@@ -144,6 +144,7 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.err = err_word(o0.device).data_ptr()
     a.N, a.D, a.H, a.W = grid
     a.Dt, a.n_nblk, a.nblk, a.G, a.n_cg, a.n_taps = pl.Dt, pl.n_nblk, pl.nblk, pl.G, pl.n_cg, len(pl.shifts)
+    a.fuse = 3 if pl.fuse_kd else 1
     n, d, h, w, cp = o0.shape
     a.out_sW, a.out_sH, a.out_sD, a.out_sN = cp, w * cp, h * w * cp, d * h * w * cp
     a.out_C = cp

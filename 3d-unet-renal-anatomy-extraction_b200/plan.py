@@ -23,6 +23,7 @@ import numpy as np
 HT, WT = 16, 8                 # output tile (rows of one UMMA): 16 x 8 voxels
 CHUNK_PITCH = 2944
 W_STAGES = 6
+FUSE_KD = True                 # fuse the three d-taps of a (kh,kw) into one wider UMMA where N <= 64
 SMEM_LIMIT = 227 * 1024
 
 
@@ -31,8 +32,8 @@ def pad_channels(c: int) -> int:
     return (c + 15) // 16 * 16
 
 
-def conv_smem_bytes(dt: int, g: int, nblk: int) -> int:
-    return 2048 + 2 * (dt + 2) * g * CHUNK_PITCH + W_STAGES * g * nblk * 16
+def conv_smem_bytes(dt: int, g: int, nblk: int, fuse: int = 1) -> int:
+    return 2048 + 2 * (dt + 2) * g * CHUNK_PITCH + W_STAGES * g * fuse * nblk * 16
 
 
 def choose_nblk(cp_out: int) -> Tuple[int, int]:
@@ -45,15 +46,17 @@ def choose_nblk(cp_out: int) -> Tuple[int, int]:
     return best[1], best[2]
 
 
-def choose_dt_g(nblk: int, chunk_counts: Sequence[int], depth: int) -> Tuple[int, int]:
+def choose_dt_g(nblk: int, chunk_counts: Sequence[int], depth: int, fuse: int = 1) -> Tuple[int, int]:
     """Planes per segment and chunks per channel group: biggest Dt (halo amortisation), then biggest G."""
     gs = [g for g in (4, 6, 2) if all(c % g == 0 for c in chunk_counts)]
     if not gs:
         raise ValueError(f"channel chunk counts {chunk_counts} need an even common divisor")
     dt_max = max(1, min(256 // nblk, 8, depth))
-    for dt in range(dt_max, 0, -1):
+    for dt in (8, 4, 2, 1):                    # the kernel's MMA issue code is unrolled for these
+        if dt > dt_max:
+            continue
         for g in gs:
-            if conv_smem_bytes(dt, g, nblk) <= SMEM_LIMIT:
+            if conv_smem_bytes(dt, g, nblk, fuse) <= SMEM_LIMIT:
                 return dt, g
     raise ValueError("no (Dt, G) fits shared memory")
 
@@ -93,6 +96,7 @@ class ConvPlan:
     widx: np.ndarray                # int64 gather index into cat(W.flatten(), [0])
     omul: int
     n_tiles_w: int = 0              # number of weight tiles
+    fuse_kd: bool = False           # one weight tile = the 3 d-taps of a (kh,kw), rows ordered sd = 2,1,0
 
     @property
     def n_nblk(self) -> int:
@@ -184,7 +188,8 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
             for j in range(-(-cp // nblk)):
                 nb_sel.append(t); nb_coff.append(j * nblk); nb_ooff.append((0, 0, 0)); nb_real0.append(real0 + j * nblk)
             real0 += out_C[t]
-    Dt, G = choose_dt_g(nblk, chunk_counts, depth)
+    fuse_kd = FUSE_KD and pattern == "direct" and stride == 1 and ks == 3 and nblk <= 64
+    Dt, G = choose_dt_g(nblk, chunk_counts, depth, 3 if fuse_kd else 1)
 
     cg_map, cg_ch = [], []
     for mi, cnt in enumerate(chunk_counts):
@@ -196,6 +201,8 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
         shifts = [(1, 1, 1)]
     elif pattern == "direct" and stride == 1:
         shifts = [(a, b, c) for a in range(3) for b in range(3) for c in range(3)]
+        if fuse_kd:
+            shifts = [(0, b, c) for b in range(3) for c in range(3)]
     elif pattern == "direct":
         shifts = [(a, b, c) for a in (0, 1) for b in (0, 1) for c in (0, 1)]
     else:
@@ -222,26 +229,32 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
             ti, par_in = maps[cg_map[cg]]
             ch = cg_ch[cg] + np.arange(G * 8, dtype=np.int64)                 # channel within the source tensor
             krow = np.where(ch < in_C[ti], in_off[ti] + ch, -1)
-            for t, sh in enumerate(shifts):
-                kk = _kidx_and_valid(kind, ks, stride, pattern, sh, par_in or (0, 0, 0), nb_ooff[nb])
-                if kk is None:
+            for t, sh0 in enumerate(shifts):
+                sub = []
+                for sd in ((2, 1, 0) if fuse_kd else (sh0[0],)):
+                    sh = (sd, sh0[1], sh0[2])
+                    kk = _kidx_and_valid(kind, ks, stride, pattern, sh, par_in or (0, 0, 0), nb_ooff[nb])
+                    if kk is None:
+                        sub = None
+                        break
+                    if kind == "conv_dgrad" and pattern == "direct":
+                        kk = tuple(ks - 1 - v for v in kk)                        # flipped kernel
+                    kflat = (kk[0] * ks + kk[1]) * ks + kk[2]
+                    K = krow.reshape(G, 1, 8)
+                    Nn = ncol.reshape(1, nblk, 1)
+                    if kind == "conv_fwd":            # W[cout=N][cin=K][k]
+                        flat = (Nn * Ktot + K) * k3 + kflat
+                    elif kind == "conv_dgrad":        # W[cout=K][cin=N][k]
+                        flat = (K * Ntot + Nn) * k3 + kflat
+                    elif kind == "convT_fwd":         # Wt[cin=K][cout=N][k]
+                        flat = (K * Ntot + Nn) * k3 + kflat
+                    else:                             # convT_dgrad: Wt[cin=N][cout=K][k]
+                        flat = (Nn * Ktot + K) * k3 + kflat
+                    sub.append(np.where((K >= 0) & (Nn >= 0), flat, -1))
+                if sub is None:
                     continue
-                if kind == "conv_dgrad" and pattern == "direct":
-                    kk = tuple(ks - 1 - v for v in kk)                        # flipped kernel
-                kflat = (kk[0] * ks + kk[1]) * ks + kk[2]
                 masks[nb, cg] |= np.uint32(1 << t)
-                K = krow.reshape(G, 1, 8)
-                Nn = ncol.reshape(1, nblk, 1)
-                if kind == "conv_fwd":            # W[cout=N][cin=K][k]
-                    flat = (Nn * Ktot + K) * k3 + kflat
-                elif kind == "conv_dgrad":        # W[cout=K][cin=N][k]
-                    flat = (K * Ntot + Nn) * k3 + kflat
-                elif kind == "convT_fwd":         # Wt[cin=K][cout=N][k]
-                    flat = (K * Ntot + Nn) * k3 + kflat
-                else:                             # convT_dgrad: Wt[cin=N][cout=K][k]
-                    flat = (Nn * Ktot + K) * k3 + kflat
-                flat = np.where((K >= 0) & (Nn >= 0), flat, -1)
-                pieces.append(flat.reshape(-1))
+                pieces.append(np.concatenate(sub, axis=1).reshape(-1))        # [G][fuse * nblk][8]
                 n_tiles += 1
     widx = np.concatenate(pieces) if pieces else np.zeros(0, np.int64)
     if kind in ("conv_fwd", "convT_dgrad"):
@@ -262,7 +275,7 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
     return ConvPlan(kind=kind, ks=ks, stride=stride, pattern=pattern, in_C=in_C, in_Cp=in_Cp, out_C=out_C, out_Cp=out_Cp,
                     maps=maps, G=G, Dt=Dt, nblk=nblk, cg_map=cg_map, cg_ch=cg_ch, shifts=shifts, nb_sel=nb_sel,
                     nb_coff=nb_coff, nb_ooff=nb_ooff, nb_real0=nb_real0, masks=masks, wbase=wbase, tab=tab, widx=widx,
-                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles)
+                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles, fuse_kd=fuse_kd)
 
 
 def bias_vector(plan: ConvPlan, bias: np.ndarray) -> np.ndarray:

@@ -64,12 +64,12 @@ typedef struct unet3d_conv_args {
   double* stats;         /* fp64 [N][stats_C][2] running (sum, sum^2) for InstanceNorm, or NULL */
   int* err;              /* device int32 error word (0 = ok) */
   int N, D, H, W;        /* tile-grid extents */
-  int Dt, n_nblk, nblk, G, n_cg, n_taps;
+  int Dt, n_nblk, nblk, G, n_cg, n_taps, fuse;
   long long out_sN, out_sD, out_sH, out_sW;   /* ELEMENT strides of out/addend */
   int out_C, stats_C, omul, zD, zH, zW;
 } unet3d_conv_args;
 int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream);
-size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk);
+size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse);
 
 /* Weight gradient on tcgen05 tensor cores (wgrad_gemm.cu): dW[tap][cin][cout] = sum_v x[v+tap][cin] dy[v][cout].
  * Replaces the cuDNN backward-filter dispatch of the layers listed above. */

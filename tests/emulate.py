@@ -20,7 +20,8 @@ def run_conv_plan(plan, inputs, wpacked, grid, out_dims, bias_vec=None, zero_las
     N, D, H, W = grid
     outs = [torch.zeros(N, *out_dims, cp) for cp in plan.out_Cp]
     G, nblk = plan.G, plan.nblk
-    tile_elems = G * nblk * 8
+    fuse = 3 if plan.fuse_kd else 1
+    tile_elems = G * fuse * nblk * 8
     for nb in range(plan.n_nblk):
         acc = torch.zeros(N, D, H, W, nblk)
         tptr = plan.wbase[nb]
@@ -41,10 +42,12 @@ def run_conv_plan(plan, inputs, wpacked, grid, out_dims, bias_vec=None, zero_las
             for t, (sd, sh, sw) in enumerate(plan.shifts):
                 if not (mask >> t) & 1:
                     continue
-                tile = wpacked[tptr * tile_elems:(tptr + 1) * tile_elems].reshape(G, nblk, 8)
+                tile = wpacked[tptr * tile_elems:(tptr + 1) * tile_elems].reshape(G, fuse, nblk, 8)
                 tptr += 1
-                a = vp[:, sd:sd + D, sh:sh + H, sw:sw + W]
-                acc += torch.einsum("bdhwk,kn->bdhwn", a, tile.permute(0, 2, 1).reshape(G * 8, nblk))
+                for f in range(fuse):                      # fused tiles hold the d-shifts 2, 1, 0 in that order
+                    sdd = (2 - f) if plan.fuse_kd else sd
+                    a = vp[:, sdd:sdd + D, sh:sh + H, sw:sw + W]
+                    acc += torch.einsum("bdhwk,kn->bdhwn", a, tile[:, f].permute(0, 2, 1).reshape(G * 8, nblk))
         if bias_vec is not None:
             acc += bias_vec[nb * nblk:(nb + 1) * nblk]
         o = outs[plan.nb_sel[nb]]

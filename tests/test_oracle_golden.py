@@ -132,3 +132,20 @@ def test_oracle_vs_live_reference_default_net():
         ref = net(x)
         got = O.resunet3d_forward(net.state_dict(), x)
     assert torch.allclose(ref, got, rtol=1e-4, atol=1e-5)
+
+
+def test_bf16_storage_model_of_the_oracle(golden_dir):
+    """oracle/bf16_model.py with rounding disabled IS the oracle; with bf16 rounding it shows what 16-bit storage
+    costs on this network (the number the GPU parity tolerances are derived from)."""
+    from oracle import bf16_model as Q
+    z = _load(golden_dir, "small_resunet.npz")
+    sd, x = _sd(z), torch.from_numpy(z["x"])
+    with torch.no_grad():
+        ref = torch.from_numpy(z["logits"])
+        exact = Q.resunet3d_forward(sd, x, 2, 8, dtype=None)
+        bf = Q.resunet3d_forward(sd, x, 2, 8, dtype=torch.bfloat16)
+        fp16 = Q.resunet3d_forward(sd, x, 2, 8, dtype=torch.float16)
+    rel = lambda a: ((a - ref).norm() / ref.norm()).item()
+    assert rel(exact) < 1e-5
+    assert 2e-3 < rel(bf) < 3e-2          # bf16 storage: ~1.7e-2 on this net
+    assert rel(fp16) < 4e-3               # fp16 storage: ~2e-3

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include "../../include/unet3d_b200.h"
@@ -147,11 +148,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
-__device__ __host__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+__device__ __host__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major,
+                                                             int a_f16 = 0, int b_f16 = 0) {
   uint32_t d = 0;
   d |= 1u << 4;                        // D format fp32
-  d |= 1u << 7;                        // A bf16
-  d |= 1u << 10;                       // B bf16
+  d |= (a_f16 ? 0u : 1u) << 7;         // A format: 0 = f16, 1 = bf16
+  d |= (b_f16 ? 0u : 1u) << 10;        // B format
   d |= (uint32_t)(a_mn_major & 1) << 15;
   d |= (uint32_t)(b_mn_major & 1) << 16;
   d |= (uint32_t)(N >> 3) << 17;
@@ -167,6 +169,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+// 16-bit storage format selected at run time (f16 != 0: IEEE half, else bfloat16); the branch is warp-uniform
+__device__ __forceinline__ uint32_t pack_2x16(float lo, float hi, int f16) {
+  if (f16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_2x16(uint32_t u, int f16) {
+  if (f16) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+  }
+  return unpack_bf16x2(u);
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

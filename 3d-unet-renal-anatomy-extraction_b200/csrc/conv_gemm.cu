@@ -215,15 +215,13 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
     }
   } else if (warp == 2) {
     // ================= MMA issuer =================
-    const uint32_t idesc = umma_idesc_bf16(128, nblk, 0, 0);
-    const uint32_t idesc2 = umma_idesc_bf16(128, 2 * nblk, 0, 0), idesc3 = umma_idesc_bf16(128, 3 * nblk, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(128, nblk, 0, 0, p.in_f16, p.in_f16);
+    const uint32_t idesc2 = umma_idesc_bf16(128, 2 * nblk, 0, 0, p.in_f16, p.in_f16),
+                   idesc3 = umma_idesc_bf16(128, 3 * nblk, 0, 0, p.in_f16, p.in_f16);
     const int G2 = G / 2;
     const int fuse = p.fuse;
     // descriptor increments (the start-address field counts 16-byte units)
-    const uint64_t a_dinc = (uint64_t)(plane_pitch >> 4), a_kinc = (uint64_t)((2 * CG_CHUNK_PITCH) >> 4);
     const uint32_t b_lbo = (uint32_t)fuse * nblk * 16;             // stride between the two K chunks of one MMA
-    const uint64_t b_kinc = (uint64_t)((2 * b_lbo) >> 4);
-    const uint64_t b_sdinc = (uint64_t)nblk;                         // one d-tap block of rows (nblk * 16 B)
     uint32_t a_it = 0, w_it = 0, acc_it = 0;
     bool ok = true;
     for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
@@ -275,6 +273,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
     const int row = q * 32 + lane;
     const int line = row >> 3, wi = row & 7;
     const int n_cc = p.nblk / 32;
+    const int of16 = p.out_f16;
     float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
     int cur_n = -1, cur_nb = -1;
     uint32_t acc_it = 0;
@@ -343,10 +342,10 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
               if (c0 + k4 * 8 < p.out_C) {
                 const uint4 u = __ldg(ap + k4);
                 float2 f;
-                f = unpack_bf16x2(u.x); v[k4 * 8 + 0] += f.x; v[k4 * 8 + 1] += f.y;
-                f = unpack_bf16x2(u.y); v[k4 * 8 + 2] += f.x; v[k4 * 8 + 3] += f.y;
-                f = unpack_bf16x2(u.z); v[k4 * 8 + 4] += f.x; v[k4 * 8 + 5] += f.y;
-                f = unpack_bf16x2(u.w); v[k4 * 8 + 6] += f.x; v[k4 * 8 + 7] += f.y;
+                f = unpack_2x16(u.x, of16); v[k4 * 8 + 0] += f.x; v[k4 * 8 + 1] += f.y;
+                f = unpack_2x16(u.y, of16); v[k4 * 8 + 2] += f.x; v[k4 * 8 + 3] += f.y;
+                f = unpack_2x16(u.z, of16); v[k4 * 8 + 4] += f.x; v[k4 * 8 + 5] += f.y;
+                f = unpack_2x16(u.w, of16); v[k4 * 8 + 6] += f.x; v[k4 * 8 + 7] += f.y;
               }
             }
           }
@@ -360,10 +359,10 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
             for (int k4 = 0; k4 < 4; ++k4) {
               if (c0 + k4 * 8 < p.out_C) {
                 uint4 u;
-                u.x = pack_bf16x2(v[k4 * 8 + 0], v[k4 * 8 + 1]);
-                u.y = pack_bf16x2(v[k4 * 8 + 2], v[k4 * 8 + 3]);
-                u.z = pack_bf16x2(v[k4 * 8 + 4], v[k4 * 8 + 5]);
-                u.w = pack_bf16x2(v[k4 * 8 + 6], v[k4 * 8 + 7]);
+                u.x = pack_2x16(v[k4 * 8 + 0], v[k4 * 8 + 1], of16);
+                u.y = pack_2x16(v[k4 * 8 + 2], v[k4 * 8 + 3], of16);
+                u.z = pack_2x16(v[k4 * 8 + 4], v[k4 * 8 + 5], of16);
+                u.w = pack_2x16(v[k4 * 8 + 6], v[k4 * 8 + 7], of16);
                 op[k4] = u;
               }
             }

@@ -12,19 +12,20 @@ namespace {
 
 constexpr float LRELU = 0.01f;     // nn.LeakyReLU default slope (network.py:165,390)
 
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+// f16 = 1: the tensor is stored as IEEE half (forward activations in "fp16" precision mode), else bfloat16
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int f16 = 0) {
   float2 t;
-  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
-  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
-  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
-  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+  t = unpack_2x16(u.x, f16); f[0] = t.x; f[1] = t.y;
+  t = unpack_2x16(u.y, f16); f[2] = t.x; f[3] = t.y;
+  t = unpack_2x16(u.z, f16); f[4] = t.x; f[5] = t.y;
+  t = unpack_2x16(u.w, f16); f[6] = t.x; f[7] = t.y;
 }
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int f16 = 0) {
   uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]);
-  u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]);
-  u.w = pack_bf16x2(f[6], f[7]);
+  u.x = pack_2x16(f[0], f[1], f16);
+  u.y = pack_2x16(f[2], f[3], f16);
+  u.z = pack_2x16(f[4], f[5], f16);
+  u.w = pack_2x16(f[6], f[7], f16);
   return u;
 }
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
@@ -56,7 +57,7 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, const float
 template <bool HAS_SKIP>
 __global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ skip,
                                 uint4* __restrict__ out, const float2* __restrict__ table, int chunks,
-                                long long V, int Cp) {
+                                long long V, int Cp, int af) {
   const int n = blockIdx.y;
   const int ch = threadIdx.x;                   // 8-channel chunk
   float mean[8], scale[8];
@@ -70,16 +71,16 @@ __global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __rest
   for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
     const size_t idx = base + (size_t)v * chunks + ch;
     float f[8];
-    unpack8(ld_stream(y + idx), f);
+    unpack8(ld_stream(y + idx), f, af);
     float s[8];
-    if (HAS_SKIP) unpack8(ld_stream(skip + idx), s);
+    if (HAS_SKIP) unpack8(ld_stream(skip + idx), s, af);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float z = (f[j] - mean[j]) * scale[j];
       if (HAS_SKIP) z += s[j];
       f[j] = z > 0.f ? z : LRELU * z;
     }
-    out[idx] = pack8(f);
+    out[idx] = pack8(f, af);
   }
 }
 
@@ -89,7 +90,7 @@ template <bool HAS_D2>
 __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2,
                                      const uint4* __restrict__ out, const uint4* __restrict__ y,
                                      uint4* __restrict__ g, const float2* __restrict__ table,
-                                     double* __restrict__ sums, int chunks, long long V, int Cp) {
+                                     double* __restrict__ sums, int chunks, long long V, int Cp, int af) {
   extern __shared__ float red[];   // [blockDim.y][chunks*8][2]
   const int n = blockIdx.y;
   const int ch = threadIdx.x;
@@ -113,8 +114,8 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] += d2[j];
     }
-    unpack8(ld_stream(out + idx), o);
-    unpack8(ld_stream(y + idx), yy);
+    unpack8(ld_stream(out + idx), o, af);
+    unpack8(ld_stream(y + idx), yy, af);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float gg = o[j] > 0.f ? d[j] : LRELU * d[j];
@@ -151,7 +152,7 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
 __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
                                     uint4* __restrict__ dy, const float2* __restrict__ table,
                                     const double* __restrict__ sums, double* __restrict__ dsum, int chunks,
-                                    long long V, int Cp, double inv_count, int zero_last, int D, int H, int W) {
+                                    long long V, int Cp, double inv_count, int zero_last, int D, int H, int W, int af) {
   extern __shared__ float red[];
   const int n = blockIdx.y;
   const int ch = threadIdx.x;
@@ -171,7 +172,7 @@ __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
     const size_t idx = base + (size_t)v * chunks + ch;
     float gg[8], yy[8];
     unpack8(ld_stream(g + idx), gg);
-    unpack8(ld_stream(y + idx), yy);
+    unpack8(ld_stream(y + idx), yy, af);
     bool z = false;
     if (zero_last) {
       const int w = (int)(v % W), h = (int)((v / W) % H), d = (int)(v / ((long long)W * H));
@@ -240,7 +241,7 @@ __global__ void channel_sum_kernel(const uint4* __restrict__ x, double* __restri
 template <int CP>
 __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[27][CP]*/,
                                 const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, int N, int D, int H,
-                                int W) {
+                                int W, int af) {
   __shared__ float ws[27 * CP + CP];
   for (int i = threadIdx.x; i < 27 * CP + CP; i += blockDim.x) ws[i] = i < 27 * CP ? w[i] : b[i - 27 * CP];
   __syncthreads();
@@ -278,7 +279,7 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
       float f[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = acc[k * 8 + j];
-      op[k] = pack8(f);
+      op[k] = pack8(f, af);
     }
   }
 }
@@ -336,7 +337,8 @@ __global__ void stem_wgrad_kernel(const float* __restrict__ x, const bf16* __res
     }
   }
   // reduce the S streams of the block in shared memory, then one atomic per (tap, channel)
-  __shared__ float red[8][28 * CP];
+  constexpr int SMAX = (512 / (28 * (CP / 8)) > 8) ? 8 : 512 / (28 * (CP / 8));
+  __shared__ float red[SMAX][28 * CP];
   const int S = blockDim.z;
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[s][tap * CP + ch * 8 + j] = acc[j];
@@ -354,7 +356,8 @@ __global__ void stem_wgrad_kernel(const float* __restrict__ x, const bf16* __res
 // ---------------------------------------------------------------------------------------------
 template <int CP, int KMAX>
 __global__ void head_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ w /*[K][CP]*/,
-                                const float* __restrict__ b, float* __restrict__ logits, int K, int N, long long V) {
+                                const float* __restrict__ b, float* __restrict__ logits, int K, int N, long long V,
+                                int af) {
   __shared__ float ws[KMAX * CP + KMAX];
   for (int i = threadIdx.x; i < K * CP + K; i += blockDim.x) ws[i] = i < K * CP ? w[i] : b[i - K * CP];
   __syncthreads();
@@ -369,7 +372,7 @@ __global__ void head_fwd_kernel(const bf16* __restrict__ a, const float* __restr
 #pragma unroll
     for (int c8 = 0; c8 < CP / 8; ++c8) {
       float f[8];
-      unpack8(ld_stream(ap + c8), f);
+      unpack8(ld_stream(ap + c8), f, af);
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
         if (k < K) {
@@ -387,7 +390,7 @@ __global__ void head_fwd_kernel(const bf16* __restrict__ a, const float* __restr
 template <int CP, int KMAX>
 __global__ void head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ a,
                                 const float* __restrict__ w, bf16* __restrict__ da, float* __restrict__ dw /*[K][CP]+[K]*/,
-                                int K, int N, long long V) {
+                                int K, int N, long long V, int af) {
   __shared__ float ws[KMAX * CP];
   __shared__ float red[KMAX * CP + KMAX];
   for (int i = threadIdx.x; i < K * CP; i += blockDim.x) ws[i] = w[i];
@@ -411,7 +414,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ dl, const bf16* __rest
 #pragma unroll
       for (int c8 = 0; c8 < CP / 8; ++c8) {
         float t[8];
-        unpack8(ld_stream(ap + c8), t);
+        unpack8(ld_stream(ap + c8), t, af);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[c8 * 8 + j] = t[j];
       }
@@ -668,8 +671,8 @@ int in_finalize(const double* stats, const float* drop, float* table, int NC, do
   return U3D_CHECK_LAUNCH();
 }
 
-int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int N, long long V, int Cp, int num_sms,
-             cudaStream_t s) {
+int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int N, long long V, int Cp, int af,
+             int num_sms, cudaStream_t s) {
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
@@ -677,14 +680,14 @@ int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int
   if (gx < 1) gx = 1;
   dim3 grd(gx, N);
   if (skip)
-    in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (const float2*)table, chunks, V, Cp);
+    in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (const float2*)table, chunks, V, Cp, af);
   else
-    in_apply_kernel<false><<<grd, blk, 0, s>>>((const uint4*)y, nullptr, (uint4*)out, (const float2*)table, chunks, V, Cp);
+    in_apply_kernel<false><<<grd, blk, 0, s>>>((const uint4*)y, nullptr, (uint4*)out, (const float2*)table, chunks, V, Cp, af);
   return U3D_CHECK_LAUNCH();
 }
 
 int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf16* y, bf16* g, const float* table,
-                  double* sums, int N, long long V, int Cp, int num_sms, cudaStream_t s) {
+                  double* sums, int N, long long V, int Cp, int af, int num_sms, cudaStream_t s) {
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
@@ -694,15 +697,15 @@ int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf
   const size_t sm = (size_t)blk.y * Cp * 2 * sizeof(float);
   if (dout2)
     in_bwd_reduce_kernel<true><<<grd, blk, sm, s>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)out,
-                                                    (const uint4*)y, (uint4*)g, (const float2*)table, sums, chunks, V, Cp);
+                                                    (const uint4*)y, (uint4*)g, (const float2*)table, sums, chunks, V, Cp, af);
   else
     in_bwd_reduce_kernel<false><<<grd, blk, sm, s>>>((const uint4*)dout, nullptr, (const uint4*)out, (const uint4*)y,
-                                                     (uint4*)g, (const float2*)table, sums, chunks, V, Cp);
+                                                     (uint4*)g, (const float2*)table, sums, chunks, V, Cp, af);
   return U3D_CHECK_LAUNCH();
 }
 
 int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, const double* sums, double* dsum, int N,
-                 int D, int H, int W, int Cp, int zero_last, int num_sms, cudaStream_t s) {
+                 int D, int H, int W, int Cp, int zero_last, int af, int num_sms, cudaStream_t s) {
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   const long long V = (long long)D * H * W;
@@ -712,7 +715,7 @@ int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, con
   dim3 grd(gx, N);
   const size_t sm = dsum ? (size_t)blk.y * Cp * sizeof(float) : 0;
   in_bwd_apply_kernel<<<grd, blk, sm, s>>>((const uint4*)g, (const uint4*)y, (uint4*)dy, (const float2*)table, sums, dsum,
-                                           chunks, V, Cp, 1.0 / (double)V, zero_last, D, H, W);
+                                           chunks, V, Cp, 1.0 / (double)V, zero_last, D, H, W, af);
   return U3D_CHECK_LAUNCH();
 }
 
@@ -725,14 +728,14 @@ int channel_sum(const bf16* x, double* dsum, long long NV, int Cp, int num_sms, 
   return U3D_CHECK_LAUNCH();
 }
 
-int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int D, int H, int W, int Cp, int num_sms,
-             cudaStream_t s) {
+int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int D, int H, int W, int Cp, int af,
+             int num_sms, cudaStream_t s) {
   const long long total = (long long)N * D * H * W;
   const int g = grid_for(total, 128, num_sms, 16);
-  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W);
-  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W);
-  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W);
-  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W);
+  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
+  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
+  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
+  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
   else return U3D_ERR_UNSUPPORTED;
   return U3D_CHECK_LAUNCH();
 }
@@ -752,24 +755,24 @@ int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, i
   return U3D_CHECK_LAUNCH();
 }
 
-int head_fwd(const bf16* a, const float* w, const float* b, float* logits, int K, int N, long long V, int Cp, int num_sms,
-             cudaStream_t s) {
+int head_fwd(const bf16* a, const float* w, const float* b, float* logits, int K, int N, long long V, int Cp, int af,
+             int num_sms, cudaStream_t s) {
   if (K < 1 || K > 8) return U3D_ERR_UNSUPPORTED;
   const int g = grid_for((long long)N * V, 256, num_sms, 16);
-  if (Cp == 32) head_fwd_kernel<32, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V);
-  else if (Cp == 16) head_fwd_kernel<16, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V);
-  else if (Cp == 48) head_fwd_kernel<48, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V);
-  else if (Cp == 64) head_fwd_kernel<64, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V);
+  if (Cp == 32) head_fwd_kernel<32, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V, af);
+  else if (Cp == 16) head_fwd_kernel<16, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V, af);
+  else if (Cp == 48) head_fwd_kernel<48, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V, af);
+  else if (Cp == 64) head_fwd_kernel<64, 8><<<g, 256, 0, s>>>(a, w, b, logits, K, N, V, af);
   else return U3D_ERR_UNSUPPORTED;
   return U3D_CHECK_LAUNCH();
 }
 
 int head_bwd(const float* dl, const bf16* a, const float* w, bf16* da, float* dw, int K, int N, long long V, int Cp,
-             int num_sms, cudaStream_t s) {
+             int af, int num_sms, cudaStream_t s) {
   if (K < 1 || K > 4) return U3D_ERR_UNSUPPORTED;
   const int g = grid_for((long long)N * V, 128 * 8, num_sms, 4);
-  if (Cp == 32) head_bwd_kernel<32, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, K, N, V);
-  else if (Cp == 16) head_bwd_kernel<16, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, K, N, V);
+  if (Cp == 32) head_bwd_kernel<32, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, K, N, V, af);
+  else if (Cp == 16) head_bwd_kernel<16, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, K, N, V, af);
   else return U3D_ERR_UNSUPPORTED;
   return U3D_CHECK_LAUNCH();
 }

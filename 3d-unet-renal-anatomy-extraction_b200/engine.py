@@ -103,8 +103,21 @@ class ResUNetEngine:
         return logits
 
     # ------------------------------------------------------------------ helpers
+    @property
+    def act_dtype(self):
+        """Storage type of the forward activations and forward weights: bf16 (default) or fp16
+        (model.precision = "fp16"; what apex O1 gave the reference).  Gradient tensors are always bf16."""
+        prec = getattr(self.model, "precision", "bf16")
+        if prec not in ("bf16", "fp16"):
+            raise RuntimeError(f"precision must be 'bf16' or 'fp16', got {prec!r}")
+        return torch.float16 if prec == "fp16" else torch.bfloat16
+
     def _new_act(self, n, dims, c):
-        return torch.empty((n, *dims, P.pad_channels(c)), dtype=torch.bfloat16, device=self.device)
+        return torch.empty((n, *dims, P.pad_channels(c)), dtype=self.act_dtype, device=self.device)
+
+    @staticmethod
+    def _grad_like(t):
+        return torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
 
     def _drop_scale(self, n, c, p):
         """Dropout3d channel mask drawn exactly as F.dropout3d does, padded to Cp."""
@@ -119,7 +132,7 @@ class ResUNetEngine:
         n = inputs[0].shape[0]
         y = self._new_act(n, out_dims, op.out_C)
         stats = torch.zeros(n, y.shape[-1], 2, dtype=torch.float64, device=self.device)
-        ops.conv_gemm(op.fwd, inputs, op.fwd.packed_weight(weight), [y], op.grid, bias=op.fwd.packed_bias(bias),
+        ops.conv_gemm(op.fwd, inputs, op.fwd.packed_weight(weight, self.act_dtype), [y], op.grid, bias=op.fwd.packed_bias(bias),
                       stats=stats, zero_last=zero_last)
         table = torch.empty(n, y.shape[-1], 2, dtype=torch.float32, device=self.device)
         ops.in_finalize(stats, drop, table, out_dims[0] * out_dims[1] * out_dims[2], IN_EPS)
@@ -136,7 +149,7 @@ class ResUNetEngine:
         if blk.uses_skip_conv:
             sop = bops["skip"]
             s = self._new_act(n, out_dims, blk.out_channels)
-            ops.conv_gemm(sop.fwd, inputs, sop.fwd.packed_weight(blk.skip_conv.weight), [s], sop.grid,
+            ops.conv_gemm(sop.fwd, inputs, sop.fwd.packed_weight(blk.skip_conv.weight, self.act_dtype), [s], sop.grid,
                           bias=sop.fwd.packed_bias(blk.skip_conv.bias))
         else:
             s = inputs[0]
@@ -204,10 +217,10 @@ class ResUNetEngine:
 
     def _in_bwd(self, dout, dout2, out, y, table, zero_last=False, want_dsum=False):
         n, cp = y.shape[0], y.shape[-1]
-        g = torch.empty_like(y)
+        g = self._grad_like(y)
         sums = torch.zeros(n, cp, 2, dtype=torch.float64, device=self.device)
         ops.in_bwd_reduce(dout, dout2, out, y, g, table, sums)
-        dy = torch.empty_like(y)
+        dy = self._grad_like(y)
         dsum = torch.zeros(cp, dtype=torch.float64, device=self.device) if want_dsum else None
         ops.in_bwd_apply(g, y, dy, table, sums, dsum, zero_last)
         return g, dy, sums, dsum
@@ -217,7 +230,7 @@ class ResUNetEngine:
         g2, dy2, sums2, _ = self._in_bwd(dout, dout2, out, y2, t2)
         grads[blk.conv2.weight] = self._wgrad(bops["conv2"], [a1], dy2, blk.conv2.weight)
         grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias)       # cancelled by the norm (S1)
-        da1 = torch.empty_like(a1)
+        da1 = self._grad_like(a1)
         c2 = bops["conv2"]
         ops.conv_gemm(c2.dgrad, [dy2], c2.dgrad.packed_weight(blk.conv2.weight), [da1], c2.grid)
         _, dy1, _, _ = self._in_bwd(da1, None, a1, y1, t1)
@@ -229,14 +242,14 @@ class ResUNetEngine:
             grads[blk.skip_conv.weight] = self._wgrad(sk, inputs, g2, blk.skip_conv.weight)
             grads[blk.skip_conv.bias] = sums2[:, :blk.out_channels, 0].sum(0).float()
             if blk.stride == 2:
-                dskip = [torch.zeros_like(t) for t in inputs]          # k1 s2 gradient only touches even voxels
+                dskip = [self._grad_like(t).zero_() for t in inputs]   # k1 s2 gradient only touches even voxels
             else:
-                dskip = [torch.empty_like(t) for t in inputs]
+                dskip = [self._grad_like(t) for t in inputs]
             ops.conv_gemm(sk.dgrad, [g2], sk.dgrad.packed_weight(blk.skip_conv.weight), dskip, sk.grid)
             addends = dskip
         else:
             addends = [g2]
-        dins = [torch.empty_like(t) for t in inputs]
+        dins = [self._grad_like(t) for t in inputs]
         ops.conv_gemm(c1.dgrad, [dy1], c1.dgrad.packed_weight(blk.conv1.weight), dins, c1.grid, addends=addends)
         return dins
 
@@ -248,7 +261,7 @@ class ResUNetEngine:
         # head
         a_last, wf = tape["head"]
         K, cl = net.fc.out_channels, net.fc.in_channels
-        d_cur = torch.empty_like(a_last)
+        d_cur = self._grad_like(a_last)
         dwf = torch.zeros(K * wf.shape[1] + K, device=self.device)
         ops.head_bwd(dlogits.contiguous(), a_last, wf, d_cur, dwf)
         grads[net.fc.weight] = dwf[:K * wf.shape[1]].view(K, wf.shape[1])[:, :cl].reshape(net.fc.weight.shape)
@@ -264,7 +277,7 @@ class ResUNetEngine:
             _, dyu, _, dsum = self._in_bwd(d_up, None, au, yu, tu, zero_last=True, want_dsum=True)
             grads[ct.weight] = self._wgrad(uop, [xin], dyu, ct.weight)
             grads[ct.bias] = dsum[:ct.out_channels].float()
-            d_cur = torch.empty_like(xin)
+            d_cur = self._grad_like(xin)
             ops.conv_gemm(uop.dgrad, [dyu], uop.dgrad.packed_weight(ct.weight), [d_cur], uop.grid)
         for j in range(len(net.encode_blocks[np_].res_blocks) - 1, -1, -1):
             blk = net.encode_blocks[np_].res_blocks[j]

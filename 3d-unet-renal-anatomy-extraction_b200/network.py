@@ -111,6 +111,7 @@ class ResUnet3D(nn.Module):
         self.out_channels = out_channels
         self.net = Unet(in_channels, out_channels, generate_paired_features(num_pool, num_features),
                         encode_stacks=lambda level: max(level, 1))                          # network.py:116-118
+        self.precision = "bf16"           # "bf16" | "fp16": 16-bit storage of forward activations / weights
         self._engine = None
         self.last_dropout_masks = None      # masks drawn by the most recent train-mode forward (for tests)
 

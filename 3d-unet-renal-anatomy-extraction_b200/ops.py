@@ -68,8 +68,15 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+ACT_DTYPES = (torch.bfloat16, torch.float16)
+
+
+def _f16(t: torch.Tensor) -> int:
+    return int(t.dtype == torch.float16)
+
+
 def make_src(t: torch.Tensor, parity=None) -> _lib.Src:
-    assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.dim() == 5, (t.dtype, t.shape)
+    assert t.dtype in ACT_DTYPES and t.is_contiguous() and t.dim() == 5, (t.dtype, t.shape)
     n, d, h, w, cp = t.shape
     sW = cp * 2
     sH, sD, sN = w * sW, h * w * sW, d * h * w * sW
@@ -99,12 +106,12 @@ class DeviceConvPlan:
         self._b_version = None
         self._b_packed = None
 
-    def packed_weight(self, w: torch.Tensor) -> torch.Tensor:
-        """bf16 tile stream of parameter `w` (re-gathered only when the parameter changed)."""
-        key = (w.data_ptr(), w._version)
+    def packed_weight(self, w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+        """16-bit tile stream of parameter `w` (re-gathered only when the parameter or the dtype changed)."""
+        key = (w.data_ptr(), w._version, dtype)
         if self._w_version != key:
             flat = torch.cat([w.detach().reshape(-1), w.new_zeros(1)])
-            self._w_packed = flat.index_select(0, self.widx).to(torch.bfloat16)
+            self._w_packed = flat.index_select(0, self.widx).to(dtype)
             self._w_version = key
         return self._w_packed
 
@@ -131,9 +138,12 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
         a.src[i] = make_src(inputs[ti], par)
     a.tab, a.w = dp.tab.data_ptr(), wpacked.data_ptr()
     o0 = outs[0]
-    assert o0.dtype == torch.bfloat16 and o0.is_contiguous()
+    assert o0.dtype in ACT_DTYPES and o0.is_contiguous()
     for o in outs:
-        assert o.shape == o0.shape and o.is_contiguous() and o.dtype == torch.bfloat16
+        assert o.shape == o0.shape and o.is_contiguous() and o.dtype == o0.dtype
+    assert wpacked.dtype == inputs[0].dtype and all(t.dtype == inputs[0].dtype for t in inputs)
+    if addends is not None:
+        assert all(t is None or t.dtype == o0.dtype for t in addends)
     a.out = o0.data_ptr()
     a.out2 = outs[1].data_ptr() if len(outs) > 1 else None
     a.bias = _ptr(bias)
@@ -145,6 +155,7 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.N, a.D, a.H, a.W = grid
     a.Dt, a.n_nblk, a.nblk, a.G, a.n_cg, a.n_taps = pl.Dt, pl.n_nblk, pl.nblk, pl.G, pl.n_cg, len(pl.shifts)
     a.fuse = 3 if pl.fuse_kd else 1
+    a.in_f16, a.out_f16 = _f16(inputs[0]), _f16(o0)
     n, d, h, w, cp = o0.shape
     a.out_sW, a.out_sH, a.out_sD, a.out_sN = cp, w * cp, h * w * cp, d * h * w * cp
     a.out_C = cp
@@ -176,6 +187,8 @@ def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor
     a.tab, a.dw, a.err = dp.tab.data_ptr(), dw.data_ptr(), err_word(dw.device).data_ptr()
     a.N, a.D, a.H, a.W = grid
     a.n_jobs, a.job_stride, a.split = pl.n_jobs, pl.job_stride, pl.split
+    a.x_f16 = _f16(xs[0])
+    assert dy.dtype == torch.bfloat16 and all(x.dtype == xs[0].dtype for x in xs)
     assert dw.dtype == torch.float32 and dw.numel() >= pl.dw_numel
     _count()
     with _Timed("wgrad_gemm_kernel", pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3]):
@@ -193,23 +206,27 @@ def in_finalize(stats: torch.Tensor, drop: Optional[torch.Tensor], table: torch.
 def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, table: torch.Tensor):
     n, d, h, w, cp = y.shape
     _count()
+    assert out.dtype == y.dtype and (skip is None or skip.dtype == y.dtype)
     _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), n, d * h * w, cp,
-                                          _stream()), "unet3d_in_apply")
+                                          _f16(y), _stream()), "unet3d_in_apply")
 
 
 def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
     n, d, h, w, cp = y.shape
     _count()
+    assert dout.dtype == torch.bfloat16 and g.dtype == torch.bfloat16 and out.dtype == y.dtype
     _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), out.data_ptr(), y.data_ptr(), g.data_ptr(),
-                                               table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _stream()),
+                                               table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
                "unet3d_in_bwd_reduce")
 
 
 def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False):
     n, d, h, w, cp = y.shape
     _count()
+    assert g.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
     _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
-                                              _ptr(dsum), n, d, h, w, cp, int(zero_last), _stream()), "unet3d_in_bwd_apply")
+                                              _ptr(dsum), n, d, h, w, cp, int(zero_last), _f16(y), _stream()),
+               "unet3d_in_bwd_apply")
 
 
 def channel_sum(x: torch.Tensor, dsum: torch.Tensor):
@@ -223,7 +240,7 @@ def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tenso
     n, d, h, ww, cp = out.shape
     _count()
     _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, d, h, ww, cp,
-                                          _stream()), "unet3d_stem_fwd")
+                                          _f16(out), _stream()), "unet3d_stem_fwd")
 
 
 def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
@@ -238,15 +255,16 @@ def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Te
     k = logits.shape[1]
     _count()
     _lib.check(_lib.lib().unet3d_head_fwd(a.data_ptr(), w.data_ptr(), b.data_ptr(), logits.data_ptr(), k, n, d * h * ww,
-                                          cp, _stream()), "unet3d_head_fwd")
+                                          cp, _f16(a), _stream()), "unet3d_head_fwd")
 
 
 def head_bwd(dl: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tensor, dw: torch.Tensor):
     n, d, h, ww, cp = a.shape
     k = dl.shape[1]
     _count()
+    assert da.dtype == torch.bfloat16
     _lib.check(_lib.lib().unet3d_head_bwd(dl.data_ptr(), a.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(), k, n,
-                                          d * h * ww, cp, _stream()), "unet3d_head_bwd")
+                                          d * h * ww, cp, _f16(a), _stream()), "unet3d_head_bwd")
 
 
 def loss_fwd(logits, target, sums, gamma):

@@ -250,6 +250,10 @@ class Trainer:
     def fit(self, num_epochs=10, save_dir=None, use_amp=False, opt_level='O1'):
         from tqdm import tqdm
         self.num_epochs, self.use_amp, self.save_dir = num_epochs, use_amp, save_dir
+        if use_amp and hasattr(self.model, "precision"):
+            # apex O1 in the reference = fp16 activations with fp32 master weights (trainer.py:538-542); the
+            # equivalent here is fp16 forward storage (gradients stay bf16, so no loss scaling is needed)
+            self.model.precision = "fp16"
         self.progress_bar = tqdm(total=0, disable=parallel.rank_world()[0] != 0)
         train_loader = self._loader(self.train_indices, self.train_transform, self.num_samples, True)
         valid_loader = None

@@ -174,6 +174,36 @@ def test_wgrad_gemm(kind, ks, stride, cins, cout, dims):
     assert rel(got, w.grad) < TOL_BF16
 
 
+@pytest.mark.parametrize("cins,cout,dims", [([30], 30, (1, 4, 16, 16)), ([60, 60], 60, (1, 4, 16, 16)), ([240], 120, (1, 2, 16, 16))])
+def test_fp16_forward_storage_conv_and_mixed_wgrad(cins, cout, dims):
+    """precision="fp16": fp16 x fp16 forward MMAs, and the weight gradient with an fp16 A operand (saved
+    activations) against a bf16 B operand (gradients) in one tcgen05.mma."""
+    torch.manual_seed(7)
+    N, D, H, W = dims
+    h = lambda t: t.to(torch.float16).float()
+    x = h(torch.randn(N, sum(cins), D, H, W, device=DEV))
+    w = (h(torch.randn(cout, sum(cins), 3, 3, 3, device=DEV) * 0.1)).requires_grad_(True)
+    y = F.conv3d(x, w, None, padding=1)
+    dy = bf(torch.randn_like(y))
+    y.backward(dy)
+    xs, off = [], 0
+    for c in cins:
+        t = torch.zeros(N, D, H, W, P.pad_channels(c), device=DEV, dtype=torch.float16)
+        t[..., :c] = x[:, off:off + c].permute(0, 2, 3, 4, 1).to(torch.float16)
+        xs.append(t); off += c
+    pl = P.make_conv_plan("conv_fwd", 3, 1, cins, [cout], D)
+    dp = ops.DeviceConvPlan(pl, DEV)
+    out = torch.full((N, D, H, W, P.pad_channels(cout)), float("nan"), device=DEV, dtype=torch.float16)
+    ops.conv_gemm(dp, xs, dp.packed_weight(w, torch.float16), [out], dims)
+    assert rel(from_ndhwc(out, cout), y.detach()) < 6e-4          # one fp16 output rounding
+    wp = ops.DeviceWgradPlan(P.make_wgrad_plan("conv", 3, 1, cins, cout, dims, 148), DEV)
+    dw = torch.zeros(wp.plan.dw_numel + 1, device=DEV)
+    ops.wgrad_gemm(wp, xs, to_ndhwc(dy), dw, dims)
+    torch.cuda.synchronize()
+    ops.check_device_errors()
+    assert rel(dw.index_select(0, wp.gidx).view_as(w), w.grad) < 1e-3
+
+
 def test_instance_norm_fwd_bwd():
     torch.manual_seed(3)
     N, C, D, H, W = 2, 30, 6, 10, 12

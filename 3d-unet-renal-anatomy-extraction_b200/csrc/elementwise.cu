@@ -56,8 +56,8 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, const float
 // out = lrelu((y - mean) * scale [+ skip])
 template <bool HAS_SKIP>
 __global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ skip,
-                                uint4* __restrict__ out, const float2* __restrict__ table, int chunks,
-                                long long V, int Cp, int af) {
+                                uint4* __restrict__ out, uint4* __restrict__ out_bf, const float2* __restrict__ table,
+                                int chunks, long long V, int Cp, int af) {
   const int n = blockIdx.y;
   const int ch = threadIdx.x;                   // 8-channel chunk
   float mean[8], scale[8];
@@ -81,6 +81,7 @@ __global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __rest
       f[j] = z > 0.f ? z : LRELU * z;
     }
     out[idx] = pack8(f, af);
+    if (out_bf) out_bf[idx] = pack8(f, 0);      // bf16 twin for the weight-gradient MMAs (fp16 mode, training)
   }
 }
 
@@ -149,6 +150,7 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
 
 // Backward, pass 2:  dy = scale * (g - mean(g) - yhat * mean(g * yhat)); optional zeroing of the
 // ConstantPad3d planes of a ConvTrans3D output (network.py:314) and per-channel sum(dy) (its bias grad).
+template <bool ZERO_LAST, bool HAS_DSUM>
 __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
                                     uint4* __restrict__ dy, const float2* __restrict__ table,
                                     const double* __restrict__ sums, double* __restrict__ dsum, int chunks,
@@ -156,15 +158,16 @@ __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
   extern __shared__ float red[];
   const int n = blockIdx.y;
   const int ch = threadIdx.x;
-  float mean[8], scale[8], mg[8], mgy[8], acc[8];
+  // dy = scale * (g - mg - yhat * mgy) = g * A + y * B + C  with per-channel constants
+  float ca[8], cb[8], cc[8], acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const size_t c = (size_t)n * Cp + ch * 8 + j;
     const float2 t = table[c];
-    mean[j] = t.x;
-    scale[j] = t.y;
-    mg[j] = (float)(sums[2 * c] * inv_count);
-    mgy[j] = (float)(sums[2 * c + 1] * inv_count);
+    const float mg = (float)(sums[2 * c] * inv_count), mgy = (float)(sums[2 * c + 1] * inv_count);
+    ca[j] = t.y;
+    cb[j] = -t.y * t.y * mgy;
+    cc[j] = -t.y * mg + t.y * t.y * mgy * t.x;
     acc[j] = 0.f;
   }
   const size_t base = (size_t)n * V * chunks;
@@ -174,26 +177,25 @@ __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
     unpack8(ld_stream(g + idx), gg);
     unpack8(ld_stream(y + idx), yy, af);
     bool z = false;
-    if (zero_last) {
+    if (ZERO_LAST) {
       const int w = (int)(v % W), h = (int)((v / W) % H), d = (int)(v / ((long long)W * H));
       z = (w == W - 1) || (h == H - 1) || (d == D - 1);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float yh = (yy[j] - mean[j]) * scale[j];
-      float r = scale[j] * (gg[j] - mg[j] - yh * mgy[j]);
-      if (z) r = 0.f;
+      float r = fmaf(gg[j], ca[j], fmaf(yy[j], cb[j], cc[j]));
+      if (ZERO_LAST && z) r = 0.f;
       gg[j] = r;
     }
     const uint4 o = pack8(gg);
     dy[idx] = o;
-    if (dsum) {
+    if (HAS_DSUM) {
       unpack8(o, gg);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += gg[j];
     }
   }
-  if (dsum) {
+  if (HAS_DSUM) {
     const int C8 = chunks * 8;
     float* my = red + (size_t)threadIdx.y * C8 + ch * 8;
 #pragma unroll
@@ -240,8 +242,8 @@ __global__ void channel_sum_kernel(const uint4* __restrict__ x, double* __restri
 // ---------------------------------------------------------------------------------------------
 template <int CP>
 __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[27][CP]*/,
-                                const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, int N, int D, int H,
-                                int W, int af) {
+                                const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, bf16* __restrict__ out_bf,
+                                int N, int D, int H, int W, int af) {
   __shared__ float ws[27 * CP + CP];
   for (int i = threadIdx.x; i < 27 * CP + CP; i += blockDim.x) ws[i] = i < 27 * CP ? w[i] : b[i - 27 * CP];
   __syncthreads();
@@ -280,6 +282,7 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = acc[k * 8 + j];
       op[k] = pack8(f, af);
+      if (out_bf) reinterpret_cast<uint4*>(out_bf + (size_t)i * CP)[k] = pack8(f, 0);
     }
   }
 }
@@ -387,80 +390,68 @@ __global__ void head_fwd_kernel(const bf16* __restrict__ a, const float* __restr
 }
 
 // da[v][c] = sum_k dl[k][v] w[k][c];  dW[k][c] += sum_v dl[k][v] a[v][c];  db[k] += sum_v dl[k][v]
+// Each thread keeps its own K x CP partial of dW in registers over all its voxels; one shuffle + shared
+// reduction per block at the end.
 template <int CP, int KMAX>
-__global__ void head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ a,
-                                const float* __restrict__ w, bf16* __restrict__ da, float* __restrict__ dw /*[K][CP]+[K]*/,
-                                int K, int N, long long V, int af) {
+__global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ a,
+                                                       const float* __restrict__ w, bf16* __restrict__ da,
+                                                       float* __restrict__ dw /*[K][CP]+[K]*/, int K, int N, long long V,
+                                                       int af) {
   __shared__ float ws[KMAX * CP];
   __shared__ float red[KMAX * CP + KMAX];
-  for (int i = threadIdx.x; i < K * CP; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < KMAX * CP; i += blockDim.x) ws[i] = i < K * CP ? w[i] : 0.f;
   for (int i = threadIdx.x; i < KMAX * CP + KMAX; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const long long total = (long long)N * V;
-  const int lane = threadIdx.x & 31;
-  // each warp walks 32 voxels at a time; lane owns a voxel for da, then the warp reduces dW over voxels
-  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < total;
-       i0 += (long long)gridDim.x * blockDim.x) {
-    const long long i = i0 + lane;
-    const bool ok = i < total;
+  float pw[KMAX][CP], pb[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    pb[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) pw[k][c] = 0.f;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / V);
+    const long long v = i - (long long)n * V;
     float g[KMAX];
-    float f[CP];
-    if (ok) {
-      const int n = (int)(i / V);
-      const long long v = i - (long long)n * V;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) g[k] = k < K ? dl[((size_t)n * K + k) * V + v] : 0.f;
-      const uint4* ap = reinterpret_cast<const uint4*>(a + (size_t)i * CP);
+    for (int k = 0; k < KMAX; ++k) g[k] = k < K ? __ldg(&dl[((size_t)n * K + k) * V + v]) : 0.f;
+    const uint4* ap = reinterpret_cast<const uint4*>(a + (size_t)i * CP);
+    uint4* op = reinterpret_cast<uint4*>(da + (size_t)i * CP);
 #pragma unroll
-      for (int c8 = 0; c8 < CP / 8; ++c8) {
-        float t[8];
-        unpack8(ld_stream(ap + c8), t, af);
+    for (int c8 = 0; c8 < CP / 8; ++c8) {
+      float f[8], t[8];
+      unpack8(ld_stream(ap + c8), f, af);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[c8 * 8 + j] = t[j];
-      }
-      uint4* op = reinterpret_cast<uint4*>(da + (size_t)i * CP);
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
 #pragma unroll
-      for (int c8 = 0; c8 < CP / 8; ++c8) {
-        float t[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float s = 0.f;
-#pragma unroll
-          for (int k = 0; k < KMAX; ++k)
-            if (k < K) s = fmaf(g[k], ws[k * CP + c8 * 8 + j], s);
-          t[j] = s;
+        for (int k = 0; k < KMAX; ++k) {
+          s = fmaf(g[k], ws[k * CP + c8 * 8 + j], s);       // rows k >= K of ws are never read with g != 0
+          pw[k][c8 * 8 + j] = fmaf(g[k], f[j], pw[k][c8 * 8 + j]);
         }
-        op[c8] = pack8(t);
+        t[j] = s;
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) g[k] = 0.f;
-#pragma unroll
-      for (int c = 0; c < CP; ++c) f[c] = 0.f;
+      op[c8] = pack8(t);
     }
-    // warp reduction of g[k]*f[c] over the 32 voxels: column sums via xor butterflies
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k >= K) continue;
-      float col[CP];
+    for (int k = 0; k < KMAX; ++k) pb[k] += g[k];
+  }
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-      for (int c = 0; c < CP; ++c) col[c] = g[k] * f[c];
+  for (int k = 0; k < KMAX; ++k) {
+    if (k >= K) continue;
 #pragma unroll
-      for (int c = 0; c < CP; ++c) {
-        float s = col[c];
+    for (int c = 0; c < CP; ++c) {
+      float s = pw[k][c];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        col[c] = s;
-      }
-      float gs = g[k];
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
-      if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < CP; ++c) atomicAdd(&red[k * CP + c], col[c]);
-        atomicAdd(&red[KMAX * CP + k], gs);
-      }
+      for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) atomicAdd(&red[k * CP + c], s);
     }
+    float s = pb[k];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) atomicAdd(&red[KMAX * CP + k], s);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < K * CP; i += blockDim.x) atomicAdd(&dw[i], red[i]);
@@ -671,8 +662,8 @@ int in_finalize(const double* stats, const float* drop, float* table, int NC, do
   return U3D_CHECK_LAUNCH();
 }
 
-int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int N, long long V, int Cp, int af,
-             int num_sms, cudaStream_t s) {
+int in_apply(const bf16* y, const bf16* skip, bf16* out, bf16* out_bf, const float* table, int N, long long V, int Cp,
+             int af, int num_sms, cudaStream_t s) {
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
@@ -680,9 +671,9 @@ int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int
   if (gx < 1) gx = 1;
   dim3 grd(gx, N);
   if (skip)
-    in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (const float2*)table, chunks, V, Cp, af);
+    in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (uint4*)out_bf, (const float2*)table, chunks, V, Cp, af);
   else
-    in_apply_kernel<false><<<grd, blk, 0, s>>>((const uint4*)y, nullptr, (uint4*)out, (const float2*)table, chunks, V, Cp, af);
+    in_apply_kernel<false><<<grd, blk, 0, s>>>((const uint4*)y, nullptr, (uint4*)out, (uint4*)out_bf, (const float2*)table, chunks, V, Cp, af);
   return U3D_CHECK_LAUNCH();
 }
 
@@ -714,8 +705,14 @@ int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, con
   if (gx < 1) gx = 1;
   dim3 grd(gx, N);
   const size_t sm = dsum ? (size_t)blk.y * Cp * sizeof(float) : 0;
-  in_bwd_apply_kernel<<<grd, blk, sm, s>>>((const uint4*)g, (const uint4*)y, (uint4*)dy, (const float2*)table, sums, dsum,
-                                           chunks, V, Cp, 1.0 / (double)V, zero_last, D, H, W, af);
+#define U3D_BWD_APPLY(Z, S)                                                                                         \
+  in_bwd_apply_kernel<Z, S><<<grd, blk, sm, s>>>((const uint4*)g, (const uint4*)y, (uint4*)dy, (const float2*)table, \
+                                                 sums, dsum, chunks, V, Cp, 1.0 / (double)V, zero_last, D, H, W, af)
+  if (zero_last && dsum) U3D_BWD_APPLY(true, true);
+  else if (zero_last) U3D_BWD_APPLY(true, false);
+  else if (dsum) U3D_BWD_APPLY(false, true);
+  else U3D_BWD_APPLY(false, false);
+#undef U3D_BWD_APPLY
   return U3D_CHECK_LAUNCH();
 }
 
@@ -728,14 +725,14 @@ int channel_sum(const bf16* x, double* dsum, long long NV, int Cp, int num_sms, 
   return U3D_CHECK_LAUNCH();
 }
 
-int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int D, int H, int W, int Cp, int af,
-             int num_sms, cudaStream_t s) {
+int stem_fwd(const float* x, const float* w, const float* b, bf16* out, bf16* out_bf, int N, int D, int H, int W, int Cp,
+             int af, int num_sms, cudaStream_t s) {
   const long long total = (long long)N * D * H * W;
   const int g = grid_for(total, 128, num_sms, 16);
-  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
-  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
-  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
-  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
+  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, 0, s>>>(x, w, b, out, out_bf, N, D, H, W, af);
+  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, 0, s>>>(x, w, b, out, out_bf, N, D, H, W, af);
+  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, 0, s>>>(x, w, b, out, out_bf, N, D, H, W, af);
+  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, 0, s>>>(x, w, b, out, out_bf, N, D, H, W, af);
   else return U3D_ERR_UNSUPPORTED;
   return U3D_CHECK_LAUNCH();
 }

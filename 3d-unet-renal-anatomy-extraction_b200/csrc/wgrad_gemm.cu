@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
       __syncwarp();
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_bf16(128, Gy * 8, 1, 1, p.x_f16, 0);
+    const uint32_t idesc = umma_idesc_bf16(128, Gy * 8, 1, 1, p.x_f16, p.x_f16);
     const uint64_t a_kinc = (uint64_t)((2 * CG_WB * 16) >> 4), b_kinc = (uint64_t)((2 * 128) >> 4);
     uint32_t it = 0;
     bool ok = true;

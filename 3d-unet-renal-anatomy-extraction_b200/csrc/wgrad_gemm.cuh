@@ -35,7 +35,7 @@ struct WgradParams {
   int N, D, H, W;
   int tiles_h, tiles_w;
   int n_jobs, job_stride, split;
-  int x_f16;        // storage of the x views: 0 = bf16, 1 = fp16 (dy is always bf16)
+  int x_f16;        // storage of the x and dy views: 0 = bf16, 1 = fp16 (tcgen05.mma rejects mixed A/B formats)
 };
 
 int wgrad_gemm_launch(const WgradParams& p, cudaStream_t stream);

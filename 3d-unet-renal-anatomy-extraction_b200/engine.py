@@ -48,6 +48,7 @@ class ResUNetEngine:
         self.device = None
         self.num_sms = 148
         self._plans: Dict[Tuple, dict] = {}
+        self._twins: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ plans
     def _get_plans(self, shape) -> dict:
@@ -119,6 +120,21 @@ class ResUNetEngine:
     def _grad_like(t):
         return torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
 
+    # In fp16 mode the weight-gradient MMAs need their x operand in bf16 like the gradients (tcgen05.mma rejects
+    # mixed A/B formats, and gradients do not fit fp16's range without loss scaling): while training, the kernels
+    # that produce an activation also write a bf16 twin of it, which only wgrad reads.
+    def _apply(self, y, skip, table, save):
+        out = torch.empty_like(y)
+        twin = None
+        if save and y.dtype == torch.float16:
+            twin = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
+            self._twins[id(out)] = twin
+        ops.in_apply(y, skip, out, table, twin)
+        return out
+
+    def _x_for_wgrad(self, t):
+        return self._twins.get(id(t), t)
+
     def _drop_scale(self, n, c, p):
         """Dropout3d channel mask drawn exactly as F.dropout3d does, padded to Cp."""
         m = torch.empty(n, c, 1, 1, 1, device=self.device, dtype=torch.float32).bernoulli_(1 - p).div_(1 - p)
@@ -143,8 +159,7 @@ class ResUNetEngine:
         drop = self._drop_scale(n, blk.out_channels, blk.dropout_p) if train else None
         # conv biases directly followed by InstanceNorm(affine=False) cancel exactly: not applied
         y1, t1 = self._conv_in(bops["conv1"], inputs, blk.conv1.weight, out_dims, drop=drop)
-        a1 = torch.empty_like(y1)
-        ops.in_apply(y1, None, a1, t1)
+        a1 = self._apply(y1, None, t1, save)
         y2, t2 = self._conv_in(bops["conv2"], [a1], blk.conv2.weight, out_dims)
         if blk.uses_skip_conv:
             sop = bops["skip"]
@@ -153,8 +168,7 @@ class ResUNetEngine:
                           bias=sop.fwd.packed_bias(blk.skip_conv.bias))
         else:
             s = inputs[0]
-        out = torch.empty_like(y2)
-        ops.in_apply(y2, s, out, t2)
+        out = self._apply(y2, s, t2, save)
         rec = (inputs, y1, t1, a1, y2, t2, out) if save else None
         return out, rec
 
@@ -176,8 +190,13 @@ class ResUNetEngine:
         w0[:, :c0] = net.conv.weight.detach().reshape(c0, 27).t()
         b0 = torch.zeros(cp0, device=self.device)
         b0[:c0] = net.conv.bias.detach()
+        self._twins = {}
         cur = self._new_act(N, dims[0], c0)
-        ops.stem_fwd(x32, w0, b0, cur)
+        twin0 = None
+        if save and cur.dtype == torch.float16:
+            twin0 = torch.empty(cur.shape, dtype=torch.bfloat16, device=self.device)
+            self._twins[id(cur)] = twin0
+        ops.stem_fwd(x32, w0, b0, cur, twin0)
         tape["x"] = x32
         skips = []
         for i in range(np_):
@@ -192,8 +211,7 @@ class ResUNetEngine:
             ct = net.up_blocks[i].conv_trans.up[0]
             uop = plans[("up", i)]
             yu, tu = self._conv_in(uop, [cur], ct.weight, dims[i], bias=ct.bias, zero_last=True)
-            au = torch.empty_like(yu)
-            ops.in_apply(yu, None, au, tu)
+            au = self._apply(yu, None, tu, save)
             if save:
                 tape[("up", i)] = (cur, yu, tu, au)
             cur, tape[("dec", i)] = self._res_block_fwd(net.decode_blocks[i], plans[("dec", i)], [au, skips[i]], dims[i],
@@ -206,13 +224,15 @@ class ResUNetEngine:
         ops.head_fwd(cur, wf, net.fc.bias.detach().float().contiguous(), logits)
         if save:
             tape["head"] = (cur, wf)
+            tape["twins"] = self._twins
+        self._twins = {}
         return logits, (tape if save else None)
 
     # ------------------------------------------------------------------ backward
     def _wgrad(self, op: _ConvOp, xs, dy, param):
         pl = op.wgrad.plan
         dw = torch.zeros(pl.dw_numel + 1, dtype=torch.float32, device=self.device)
-        ops.wgrad_gemm(op.wgrad, xs, dy, dw, op.grid)
+        ops.wgrad_gemm(op.wgrad, [self._x_for_wgrad(x) for x in xs], dy, dw, op.grid)
         return dw.index_select(0, op.wgrad.gidx).view_as(param)
 
     def _in_bwd(self, dout, dout2, out, y, table, zero_last=False, want_dsum=False):
@@ -257,6 +277,7 @@ class ResUNetEngine:
         net = self.model.net
         plans = self._get_plans(x_shape)
         np_ = net.num_pool
+        self._twins = tape.get("twins", {})
         grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         # head
         a_last, wf = tape["head"]
@@ -297,6 +318,7 @@ class ResUNetEngine:
         dw0 = dw0.view(28, cp0)
         grads[net.conv.weight] = dw0[:27, :c0].t().reshape(net.conv.weight.shape)
         grads[net.conv.bias] = dw0[27, :c0].clone()
+        self._twins = {}
         return grads
 
 

@@ -188,7 +188,7 @@ def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor
     a.N, a.D, a.H, a.W = grid
     a.n_jobs, a.job_stride, a.split = pl.n_jobs, pl.job_stride, pl.split
     a.x_f16 = _f16(xs[0])
-    assert dy.dtype == torch.bfloat16 and all(x.dtype == xs[0].dtype for x in xs)
+    assert all(x.dtype == dy.dtype for x in xs)        # one MMA cannot mix fp16 and bf16 operands
     assert dw.dtype == torch.float32 and dw.numel() >= pl.dw_numel
     _count()
     with _Timed("wgrad_gemm_kernel", pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3]):
@@ -203,12 +203,13 @@ def in_finalize(stats: torch.Tensor, drop: Optional[torch.Tensor], table: torch.
                                              _stream()), "unet3d_in_finalize")
 
 
-def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, table: torch.Tensor):
+def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, table: torch.Tensor,
+             out_bf16: Optional[torch.Tensor] = None):
     n, d, h, w, cp = y.shape
     _count()
     assert out.dtype == y.dtype and (skip is None or skip.dtype == y.dtype)
-    _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), n, d * h * w, cp,
-                                          _f16(y), _stream()), "unet3d_in_apply")
+    _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), _ptr(out_bf16), table.data_ptr(), n,
+                                          d * h * w, cp, _f16(y), _stream()), "unet3d_in_apply")
 
 
 def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
@@ -236,11 +237,11 @@ def channel_sum(x: torch.Tensor, dsum: torch.Tensor):
                "unet3d_channel_sum")
 
 
-def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
+def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor, out_bf16: Optional[torch.Tensor] = None):
     n, d, h, ww, cp = out.shape
     _count()
-    _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, d, h, ww, cp,
-                                          _f16(out), _stream()), "unet3d_stem_fwd")
+    _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(out_bf16), n, d, h,
+                                          ww, cp, _f16(out), _stream()), "unet3d_stem_fwd")
 
 
 def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):

@@ -86,7 +86,7 @@ typedef struct unet3d_wgrad_args {
   int N, D, H, W;                /* tile-grid extents */
   int n_jobs, job_stride;
   int split;                     /* CTAs per job (split over voxel tiles) */
-  int x_f16;                     /* x views stored as fp16 (dy is always bf16) */
+  int x_f16;                     /* x AND dy views stored as fp16 (operands of one MMA must share the format) */
 } unet3d_wgrad_args;
 int unet3d_wgrad_gemm(const unet3d_wgrad_args* a, void* stream);
 
@@ -94,8 +94,10 @@ int unet3d_wgrad_gemm(const unet3d_wgrad_args* a, void* stream);
  * network.py:159-160,175-176,401-402,412-416,315-316.  stats come from the conv epilogue. */
 int unet3d_in_finalize(const double* stats, const float* drop_scale, float* table, int NC, double count, float eps,
                        void* stream);
-int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, int N, long long V, int Cp,
-                    int act_f16, void* stream);
+/* out_bf16 (optional, may be NULL): a second, bf16 copy of the result -- tcgen05.mma cannot mix an fp16 A with a
+ * bf16 B operand, so in fp16 mode the weight-gradient kernel reads this twin of the saved activation. */
+int unet3d_in_apply(const void* y, const void* skip, void* out, void* out_bf16, const float* table, int N, long long V,
+                    int Cp, int act_f16, void* stream);
 int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, void* g,
                          const float* table, double* sums, int N, long long V, int Cp, int act_f16, void* stream);
 int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums, double* dsum,
@@ -104,8 +106,8 @@ int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* 
 
 /* Stem Conv3d(1->C,k3,p1)+bias, fp32 NCDHW in -> bf16 NDHWC out (network.py:541,550) and its
  * weight/bias gradient (dw fp32 [28][Cp]: 27 taps then the bias row; accumulated atomically). */
-int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, int N, int D, int H, int W, int Cp,
-                    int act_f16, void* stream);
+int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, void* out_bf16, int N, int D, int H, int W,
+                    int Cp, int act_f16, void* stream);
 int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, int Cp, void* stream);
 
 /* Head Conv3d(C->K,k1)+bias, bf16 NDHWC in -> fp32 NCDHW logits (network.py:545-547,563), and backward

@@ -175,9 +175,9 @@ def test_wgrad_gemm(kind, ks, stride, cins, cout, dims):
 
 
 @pytest.mark.parametrize("cins,cout,dims", [([30], 30, (1, 4, 16, 16)), ([60, 60], 60, (1, 4, 16, 16)), ([240], 120, (1, 2, 16, 16))])
-def test_fp16_forward_storage_conv_and_mixed_wgrad(cins, cout, dims):
-    """precision="fp16": fp16 x fp16 forward MMAs, and the weight gradient with an fp16 A operand (saved
-    activations) against a bf16 B operand (gradients) in one tcgen05.mma."""
+def test_fp16_forward_storage_conv(cins, cout, dims):
+    """precision="fp16": fp16 x fp16 forward MMAs; the weight gradient reads the bf16 twin of the saved activation
+    (tcgen05.mma raises an illegal-instruction fault for an fp16 A with a bf16 B operand -- tried in round 1)."""
     torch.manual_seed(7)
     N, D, H, W = dims
     h = lambda t: t.to(torch.float16).float()
@@ -198,10 +198,10 @@ def test_fp16_forward_storage_conv_and_mixed_wgrad(cins, cout, dims):
     assert rel(from_ndhwc(out, cout), y.detach()) < 6e-4          # one fp16 output rounding
     wp = ops.DeviceWgradPlan(P.make_wgrad_plan("conv", 3, 1, cins, cout, dims, 148), DEV)
     dw = torch.zeros(wp.plan.dw_numel + 1, device=DEV)
-    ops.wgrad_gemm(wp, xs, to_ndhwc(dy), dw, dims)
+    ops.wgrad_gemm(wp, [t.to(torch.bfloat16) for t in xs], to_ndhwc(dy), dw, dims)
     torch.cuda.synchronize()
     ops.check_device_errors()
-    assert rel(dw.index_select(0, wp.gidx).view_as(w), w.grad) < 1e-3
+    assert rel(dw.index_select(0, wp.gidx).view_as(w), w.grad) < 5e-3
 
 
 def test_instance_norm_fwd_bwd():

@@ -113,6 +113,7 @@ int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
   p.segs_d = (a->D + a->Dt - 1) / (a->Dt > 0 ? a->Dt : 1);
   p.n_nblk = a->n_nblk; p.nblk = a->nblk; p.G = a->G; p.n_cg = a->n_cg; p.n_taps = a->n_taps;
   p.fuse = a->fuse;
+  p.nbuf = a->nbuf;
   p.in_f16 = a->in_f16;
   p.out_f16 = a->out_f16;
   p.out_sN = a->out_sN; p.out_sD = a->out_sD; p.out_sH = a->out_sH; p.out_sW = a->out_sW;
@@ -151,10 +152,9 @@ int unet3d_in_finalize(const double* stats, const float* drop_scale, float* tabl
                        void* stream) {
   return check(in_finalize(stats, drop_scale, table, NC, count, eps, (cudaStream_t)stream), "in_finalize");
 }
-int unet3d_in_apply(const void* y, const void* skip, void* out, void* out_bf16, const float* table, int N, long long V,
-                    int Cp, int act_f16, void* stream) {
-  return check(in_apply((const bf16*)y, (const bf16*)skip, (bf16*)out, (bf16*)out_bf16, table, N, V, Cp, act_f16, num_sms(),
-                        (cudaStream_t)stream),
+int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, int N, long long V, int Cp,
+                    int act_f16, void* stream) {
+  return check(in_apply((const bf16*)y, (const bf16*)skip, (bf16*)out, table, N, V, Cp, act_f16, num_sms(), (cudaStream_t)stream),
                "in_apply");
 }
 int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, void* g,
@@ -172,21 +172,22 @@ int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* tab
 int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* stream) {
   return check(channel_sum((const bf16*)x, dsum, NV, Cp, num_sms(), (cudaStream_t)stream), "channel_sum");
 }
-int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, void* out_bf16, int N, int D, int H, int W,
-                    int Cp, int act_f16, void* stream) {
-  return check(stem_fwd(x, w, b, (bf16*)out, (bf16*)out_bf16, N, D, H, W, Cp, act_f16, num_sms(), (cudaStream_t)stream),
-               "stem_fwd");
+int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, int N, int D, int H, int W, int Cp,
+                    int act_f16, void* stream) {
+  return check(stem_fwd(x, w, b, (bf16*)out, N, D, H, W, Cp, act_f16, num_sms(), (cudaStream_t)stream), "stem_fwd");
 }
-int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, int Cp, void* stream) {
-  return check(stem_wgrad(x, (const bf16*)dy, dw, N, D, H, W, Cp, num_sms(), (cudaStream_t)stream), "stem_wgrad");
+int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, int Cp, int act_f16,
+                      void* stream) {
+  return check(stem_wgrad(x, (const bf16*)dy, dw, N, D, H, W, Cp, act_f16, num_sms(), (cudaStream_t)stream), "stem_wgrad");
 }
 int unet3d_head_fwd(const void* a, const float* w, const float* b, float* logits, int K, int N, long long V, int Cp,
                     int act_f16, void* stream) {
   return check(head_fwd((const bf16*)a, w, b, logits, K, N, V, Cp, act_f16, num_sms(), (cudaStream_t)stream), "head_fwd");
 }
-int unet3d_head_bwd(const float* dlogits, const void* a, const float* w, void* da, float* dw, int K, int N,
-                    long long V, int Cp, int act_f16, void* stream) {
-  return check(head_bwd(dlogits, (const bf16*)a, w, (bf16*)da, dw, K, N, V, Cp, act_f16, num_sms(), (cudaStream_t)stream),
+int unet3d_head_bwd(const float* dlogits, const void* a, const float* w, void* da, float* dw, const float* grad_scale,
+                    int K, int N, long long V, int Cp, int act_f16, void* stream) {
+  return check(head_bwd(dlogits, (const bf16*)a, w, (bf16*)da, dw, grad_scale, K, N, V, Cp, act_f16, num_sms(),
+                        (cudaStream_t)stream),
                "head_bwd");
 }
 int unet3d_loss_fwd(const float* logits, const long long* target, double* sums, int K, int N, long long V,

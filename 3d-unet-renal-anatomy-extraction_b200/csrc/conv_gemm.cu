@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
     bool ok = true;
     for (int item = blockIdx.x; item < p.n_work && ok; item += gridDim.x) {
       const int nb = item / n_tiles;
-      const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+      const uint32_t buf = p.nbuf == 2 ? (acc_it & 1) : 0u, aph = p.nbuf == 2 ? ((acc_it >> 1) & 1) : (acc_it & 1);
       if (!mbar_wait(smem_u32(&ctl->acc_empty[buf]), aph ^ 1, abort_flag, p.err, 103)) break;
       tc_fence_after();
       const uint32_t acc0 = tmem_base + buf * 256;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
         cur_n = n;
         cur_nb = nb;
       }
-      const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+      const uint32_t buf = p.nbuf == 2 ? (acc_it & 1) : 0u, aph = p.nbuf == 2 ? ((acc_it >> 1) & 1) : (acc_it & 1);
       if (!mbar_wait(smem_u32(&ctl->acc_full[buf]), aph, abort_flag, p.err, 106)) break;
       tc_fence_after();
       const int coff_raw = __ldg(&tab_coff[nb]);
@@ -400,7 +400,8 @@ size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse) {
 }
 
 int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  if (p.G < 2 || (p.G & 1) || p.nblk % 32 != 0 || p.nblk > 128 || p.Dt < 1 || p.Dt * p.nblk > 256 ||
+  if (p.G < 2 || (p.G & 1) || p.nblk % 32 != 0 || p.nblk > 128 || p.Dt < 1 || (p.nbuf != 1 && p.nbuf != 2) ||
+      p.Dt * p.nblk * p.nbuf > 512 ||
       p.n_taps < 1 || p.n_taps > 32 || p.n_work < 1 || (p.Dt != 1 && p.Dt != 2 && p.Dt != 4 && p.Dt != 8) || p.G > 6 || (p.fuse != 1 && p.fuse != 3) || p.fuse * p.nblk > 256)
     return U3D_ERR_INVALID;
   const size_t smem = conv_gemm_smem_bytes(p.Dt, p.G, p.nblk, p.fuse);

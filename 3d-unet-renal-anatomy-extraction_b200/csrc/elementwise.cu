@@ -56,8 +56,8 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, const float
 // out = lrelu((y - mean) * scale [+ skip])
 template <bool HAS_SKIP>
 __global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ skip,
-                                uint4* __restrict__ out, uint4* __restrict__ out_bf, const float2* __restrict__ table,
-                                int chunks, long long V, int Cp, int af) {
+                                uint4* __restrict__ out, const float2* __restrict__ table, int chunks,
+                                long long V, int Cp, int af) {
   const int n = blockIdx.y;
   const int ch = threadIdx.x;                   // 8-channel chunk
   float mean[8], scale[8];
@@ -81,7 +81,6 @@ __global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __rest
       f[j] = z > 0.f ? z : LRELU * z;
     }
     out[idx] = pack8(f, af);
-    if (out_bf) out_bf[idx] = pack8(f, 0);      // bf16 twin for the weight-gradient MMAs (fp16 mode, training)
   }
 }
 
@@ -108,10 +107,10 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
   for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
     const size_t idx = base + (size_t)v * chunks + ch;
     float d[8], o[8], yy[8];
-    unpack8(ld_stream(dout + idx), d);
+    unpack8(ld_stream(dout + idx), d, af);
     if (HAS_D2) {
       float d2[8];
-      unpack8(ld_stream(dout2 + idx), d2);
+      unpack8(ld_stream(dout2 + idx), d2, af);
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] += d2[j];
     }
@@ -122,9 +121,9 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
       const float gg = o[j] > 0.f ? d[j] : LRELU * d[j];
       d[j] = gg;
     }
-    const uint4 gp = pack8(d);
+    const uint4 gp = pack8(d, af);
     g[idx] = gp;
-    unpack8(gp, d);          // reduce what pass 2 will read back (bf16-rounded g)
+    unpack8(gp, d, af);      // reduce what pass 2 will read back (the rounded g)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float yh = (yy[j] - mean[j]) * scale[j];
@@ -174,7 +173,7 @@ __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
   for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
     const size_t idx = base + (size_t)v * chunks + ch;
     float gg[8], yy[8];
-    unpack8(ld_stream(g + idx), gg);
+    unpack8(ld_stream(g + idx), gg, af);
     unpack8(ld_stream(y + idx), yy, af);
     bool z = false;
     if (ZERO_LAST) {
@@ -187,10 +186,10 @@ __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
       if (ZERO_LAST && z) r = 0.f;
       gg[j] = r;
     }
-    const uint4 o = pack8(gg);
+    const uint4 o = pack8(gg, af);
     dy[idx] = o;
     if (HAS_DSUM) {
-      unpack8(o, gg);
+      unpack8(o, gg, af);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += gg[j];
     }
@@ -242,8 +241,8 @@ __global__ void channel_sum_kernel(const uint4* __restrict__ x, double* __restri
 // ---------------------------------------------------------------------------------------------
 template <int CP>
 __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[27][CP]*/,
-                                const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, bf16* __restrict__ out_bf,
-                                int N, int D, int H, int W, int af) {
+                                const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, int N, int D, int H,
+                                int W, int af) {
   __shared__ float ws[27 * CP + CP];
   for (int i = threadIdx.x; i < 27 * CP + CP; i += blockDim.x) ws[i] = i < 27 * CP ? w[i] : b[i - 27 * CP];
   __syncthreads();
@@ -282,7 +281,6 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = acc[k * 8 + j];
       op[k] = pack8(f, af);
-      if (out_bf) reinterpret_cast<uint4*>(out_bf + (size_t)i * CP)[k] = pack8(f, 0);
     }
   }
 }
@@ -292,7 +290,7 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
 // voxels (8 independent x / dy loads in flight per thread); fp32 atomics into dw[28][CP] at the end.
 template <int CP>
 __global__ void stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
-                                  int N, int D, int H, int W) {
+                                  int N, int D, int H, int W, int af) {
   const int ch = threadIdx.x, tap = threadIdx.y, s = threadIdx.z;
   const int kd = tap / 9 - 1, kh = (tap / 3) % 3 - 1, kw = tap % 3 - 1;
   const long long V = (long long)D * H * W, total = (long long)N * V;
@@ -334,7 +332,7 @@ __global__ void stem_wgrad_kernel(const float* __restrict__ x, const bf16* __res
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       float f[8];
-      unpack8(dv[u], f);
+      unpack8(dv[u], f, af);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[u], f[j], acc[j]);
     }
@@ -395,7 +393,8 @@ __global__ void head_fwd_kernel(const bf16* __restrict__ a, const float* __restr
 template <int CP, int KMAX>
 __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ a,
                                                        const float* __restrict__ w, bf16* __restrict__ da,
-                                                       float* __restrict__ dw /*[K][CP]+[K]*/, int K, int N, long long V,
+                                                       float* __restrict__ dw /*[K][CP]+[K]*/,
+                                                       const float* __restrict__ gscale, int K, int N, long long V,
                                                        int af) {
   __shared__ float ws[KMAX * CP];
   __shared__ float red[KMAX * CP + KMAX];
@@ -403,6 +402,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
   for (int i = threadIdx.x; i < KMAX * CP + KMAX; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const long long total = (long long)N * V;
+  const float gs = gscale ? __ldg(gscale) : 1.f;      // internal gradient scale (fp16 mode); dW / db stay unscaled
   float pw[KMAX][CP], pb[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
@@ -430,9 +430,9 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
           s = fmaf(g[k], ws[k * CP + c8 * 8 + j], s);       // rows k >= K of ws are never read with g != 0
           pw[k][c8 * 8 + j] = fmaf(g[k], f[j], pw[k][c8 * 8 + j]);
         }
-        t[j] = s;
+        t[j] = s * gs;
       }
-      op[c8] = pack8(t);
+      op[c8] = pack8(t, af);
     }
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) pb[k] += g[k];
@@ -662,8 +662,8 @@ int in_finalize(const double* stats, const float* drop, float* table, int NC, do
   return U3D_CHECK_LAUNCH();
 }
 
-int in_apply(const bf16* y, const bf16* skip, bf16* out, bf16* out_bf, const float* table, int N, long long V, int Cp,
-             int af, int num_sms, cudaStream_t s) {
+int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int N, long long V, int Cp, int af,
+             int num_sms, cudaStream_t s) {
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
@@ -671,9 +671,9 @@ int in_apply(const bf16* y, const bf16* skip, bf16* out, bf16* out_bf, const flo
   if (gx < 1) gx = 1;
   dim3 grd(gx, N);
   if (skip)
-    in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (uint4*)out_bf, (const float2*)table, chunks, V, Cp, af);
+    in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (const float2*)table, chunks, V, Cp, af);
   else
-    in_apply_kernel<false><<<grd, blk, 0, s>>>((const uint4*)y, nullptr, (uint4*)out, (uint4*)out_bf, (const float2*)table, chunks, V, Cp, af);
+    in_apply_kernel<false><<<grd, blk, 0, s>>>((const uint4*)y, nullptr, (uint4*)out, (const float2*)table, chunks, V, Cp, af);
   return U3D_CHECK_LAUNCH();
 }
 
@@ -725,29 +725,30 @@ int channel_sum(const bf16* x, double* dsum, long long NV, int Cp, int num_sms, 
   return U3D_CHECK_LAUNCH();
 }
 
-int stem_fwd(const float* x, const float* w, const float* b, bf16* out, bf16* out_bf, int N, int D, int H, int W, int Cp,
-             int af, int num_sms, cudaStream_t s) {
+int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int D, int H, int W, int Cp, int af,
+             int num_sms, cudaStream_t s) {
   const long long total = (long long)N * D * H * W;
   const int g = grid_for(total, 128, num_sms, 16);
-  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, 0, s>>>(x, w, b, out, out_bf, N, D, H, W, af);
-  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, 0, s>>>(x, w, b, out, out_bf, N, D, H, W, af);
-  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, 0, s>>>(x, w, b, out, out_bf, N, D, H, W, af);
-  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, 0, s>>>(x, w, b, out, out_bf, N, D, H, W, af);
+  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
+  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
+  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
+  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
   else return U3D_ERR_UNSUPPORTED;
   return U3D_CHECK_LAUNCH();
 }
 
-int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, int Cp, int num_sms, cudaStream_t s) {
+int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, int Cp, int af, int num_sms,
+               cudaStream_t s) {
   const long long total = (long long)N * D * H * W;
   int streams = 512 / (28 * (Cp / 8));
   if (streams > 8) streams = 8;
   if (streams < 1) return U3D_ERR_UNSUPPORTED;
   dim3 blk(Cp / 8, 28, streams);
   const int g = grid_for(total, streams * 8 * 4, num_sms, 8);
-  if (Cp == 32) stem_wgrad_kernel<32><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
-  else if (Cp == 16) stem_wgrad_kernel<16><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
-  else if (Cp == 48) stem_wgrad_kernel<48><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
-  else if (Cp == 64) stem_wgrad_kernel<64><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W);
+  if (Cp == 32) stem_wgrad_kernel<32><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
+  else if (Cp == 16) stem_wgrad_kernel<16><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
+  else if (Cp == 48) stem_wgrad_kernel<48><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
+  else if (Cp == 64) stem_wgrad_kernel<64><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
   else return U3D_ERR_UNSUPPORTED;
   return U3D_CHECK_LAUNCH();
 }
@@ -764,12 +765,12 @@ int head_fwd(const bf16* a, const float* w, const float* b, float* logits, int K
   return U3D_CHECK_LAUNCH();
 }
 
-int head_bwd(const float* dl, const bf16* a, const float* w, bf16* da, float* dw, int K, int N, long long V, int Cp,
-             int af, int num_sms, cudaStream_t s) {
+int head_bwd(const float* dl, const bf16* a, const float* w, bf16* da, float* dw, const float* gscale, int K, int N,
+             long long V, int Cp, int af, int num_sms, cudaStream_t s) {
   if (K < 1 || K > 4) return U3D_ERR_UNSUPPORTED;
   const int g = grid_for((long long)N * V, 128 * 8, num_sms, 4);
-  if (Cp == 32) head_bwd_kernel<32, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, K, N, V, af);
-  else if (Cp == 16) head_bwd_kernel<16, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, K, N, V, af);
+  if (Cp == 32) head_bwd_kernel<32, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, gscale, K, N, V, af);
+  else if (Cp == 16) head_bwd_kernel<16, 4><<<g, 128, 0, s>>>(dl, a, w, da, dw, gscale, K, N, V, af);
   else return U3D_ERR_UNSUPPORTED;
   return U3D_CHECK_LAUNCH();
 }

@@ -34,11 +34,11 @@ class _ConvOp:
         dev = eng.device
         depth = grid[1]
         if kind == "conv":
-            self.fwd = ops.DeviceConvPlan(P.make_conv_plan("conv_fwd", ks, stride, in_C, [out_C], depth), dev)
-            self.dgrad = ops.DeviceConvPlan(P.make_conv_plan("conv_dgrad", ks, stride, [out_C], in_C, depth), dev)
+            self.fwd = ops.DeviceConvPlan(P.make_conv_plan("conv_fwd", ks, stride, in_C, [out_C], depth, grid), dev)
+            self.dgrad = ops.DeviceConvPlan(P.make_conv_plan("conv_dgrad", ks, stride, [out_C], in_C, depth, grid), dev)
         else:
-            self.fwd = ops.DeviceConvPlan(P.make_conv_plan("convT_fwd", 3, 2, in_C, [out_C], depth), dev)
-            self.dgrad = ops.DeviceConvPlan(P.make_conv_plan("convT_dgrad", 3, 2, [out_C], in_C, depth), dev)
+            self.fwd = ops.DeviceConvPlan(P.make_conv_plan("convT_fwd", 3, 2, in_C, [out_C], depth, grid), dev)
+            self.dgrad = ops.DeviceConvPlan(P.make_conv_plan("convT_dgrad", 3, 2, [out_C], in_C, depth, grid), dev)
         self.wgrad = ops.DeviceWgradPlan(P.make_wgrad_plan(kind, ks, stride, in_C, out_C, grid, eng.num_sms), dev)
 
 
@@ -48,7 +48,7 @@ class ResUNetEngine:
         self.device = None
         self.num_sms = 148
         self._plans: Dict[Tuple, dict] = {}
-        self._twins: Dict[int, torch.Tensor] = {}
+        self._inv_scale = None
 
     # ------------------------------------------------------------------ plans
     def _get_plans(self, shape) -> dict:
@@ -118,22 +118,14 @@ class ResUNetEngine:
 
     @staticmethod
     def _grad_like(t):
-        return torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+        """Gradient tensors use the storage format of the activations (one tcgen05.mma cannot mix fp16 and bf16
+        operands -- it faults with an illegal instruction -- and the weight gradient multiplies the two)."""
+        return torch.empty_like(t)
 
-    # In fp16 mode the weight-gradient MMAs need their x operand in bf16 like the gradients (tcgen05.mma rejects
-    # mixed A/B formats, and gradients do not fit fp16's range without loss scaling): while training, the kernels
-    # that produce an activation also write a bf16 twin of it, which only wgrad reads.
     def _apply(self, y, skip, table, save):
         out = torch.empty_like(y)
-        twin = None
-        if save and y.dtype == torch.float16:
-            twin = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
-            self._twins[id(out)] = twin
-        ops.in_apply(y, skip, out, table, twin)
+        ops.in_apply(y, skip, out, table)
         return out
-
-    def _x_for_wgrad(self, t):
-        return self._twins.get(id(t), t)
 
     def _drop_scale(self, n, c, p):
         """Dropout3d channel mask drawn exactly as F.dropout3d does, padded to Cp."""
@@ -190,13 +182,8 @@ class ResUNetEngine:
         w0[:, :c0] = net.conv.weight.detach().reshape(c0, 27).t()
         b0 = torch.zeros(cp0, device=self.device)
         b0[:c0] = net.conv.bias.detach()
-        self._twins = {}
         cur = self._new_act(N, dims[0], c0)
-        twin0 = None
-        if save and cur.dtype == torch.float16:
-            twin0 = torch.empty(cur.shape, dtype=torch.bfloat16, device=self.device)
-            self._twins[id(cur)] = twin0
-        ops.stem_fwd(x32, w0, b0, cur, twin0)
+        ops.stem_fwd(x32, w0, b0, cur)
         tape["x"] = x32
         skips = []
         for i in range(np_):
@@ -224,16 +211,15 @@ class ResUNetEngine:
         ops.head_fwd(cur, wf, net.fc.bias.detach().float().contiguous(), logits)
         if save:
             tape["head"] = (cur, wf)
-            tape["twins"] = self._twins
-        self._twins = {}
         return logits, (tape if save else None)
 
     # ------------------------------------------------------------------ backward
     def _wgrad(self, op: _ConvOp, xs, dy, param):
         pl = op.wgrad.plan
         dw = torch.zeros(pl.dw_numel + 1, dtype=torch.float32, device=self.device)
-        ops.wgrad_gemm(op.wgrad, [self._x_for_wgrad(x) for x in xs], dy, dw, op.grid)
-        return dw.index_select(0, op.wgrad.gidx).view_as(param)
+        ops.wgrad_gemm(op.wgrad, xs, dy, dw, op.grid)
+        g = dw.index_select(0, op.wgrad.gidx).view_as(param)
+        return g if self._inv_scale is None else g.mul_(self._inv_scale)
 
     def _in_bwd(self, dout, dout2, out, y, table, zero_last=False, want_dsum=False):
         n, cp = y.shape[0], y.shape[-1]
@@ -260,7 +246,7 @@ class ResUNetEngine:
         if blk.uses_skip_conv:
             sk = bops["skip"]
             grads[blk.skip_conv.weight] = self._wgrad(sk, inputs, g2, blk.skip_conv.weight)
-            grads[blk.skip_conv.bias] = sums2[:, :blk.out_channels, 0].sum(0).float()
+            grads[blk.skip_conv.bias] = self._unscale(sums2[:, :blk.out_channels, 0].sum(0).float())
             if blk.stride == 2:
                 dskip = [self._grad_like(t).zero_() for t in inputs]   # k1 s2 gradient only touches even voxels
             else:
@@ -277,14 +263,22 @@ class ResUNetEngine:
         net = self.model.net
         plans = self._get_plans(x_shape)
         np_ = net.num_pool
-        self._twins = tape.get("twins", {})
         grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        # fp16 gradients need a scale to stay inside fp16's range (Dice gradients are ~1e-7 per voxel).  It is
+        # internal and dynamic: a power of two that puts max|dlogits| at 64, taken from this step's dlogits on the
+        # device (no host sync), multiplied in by head_bwd and divided out of every parameter gradient.
+        self._inv_scale = None
+        gscale = None
+        if self.act_dtype == torch.float16:
+            amax = dlogits.detach().abs().amax().clamp_min(1e-30)
+            gscale = torch.exp2(torch.floor(torch.log2(64.0 / amax))).clamp(1.0, 2.0 ** 40).float().reshape(1)
+            self._inv_scale = (1.0 / gscale)
         # head
         a_last, wf = tape["head"]
         K, cl = net.fc.out_channels, net.fc.in_channels
         d_cur = self._grad_like(a_last)
         dwf = torch.zeros(K * wf.shape[1] + K, device=self.device)
-        ops.head_bwd(dlogits.contiguous(), a_last, wf, d_cur, dwf)
+        ops.head_bwd(dlogits.contiguous(), a_last, wf, d_cur, dwf, gscale)
         grads[net.fc.weight] = dwf[:K * wf.shape[1]].view(K, wf.shape[1])[:, :cl].reshape(net.fc.weight.shape)
         grads[net.fc.bias] = dwf[K * wf.shape[1]:].clone()
         pending = {}
@@ -297,7 +291,7 @@ class ResUNetEngine:
             uop = plans[("up", i)]
             _, dyu, _, dsum = self._in_bwd(d_up, None, au, yu, tu, zero_last=True, want_dsum=True)
             grads[ct.weight] = self._wgrad(uop, [xin], dyu, ct.weight)
-            grads[ct.bias] = dsum[:ct.out_channels].float()
+            grads[ct.bias] = self._unscale(dsum[:ct.out_channels].float())
             d_cur = self._grad_like(xin)
             ops.conv_gemm(uop.dgrad, [dyu], uop.dgrad.packed_weight(ct.weight), [d_cur], uop.grid)
         for j in range(len(net.encode_blocks[np_].res_blocks) - 1, -1, -1):
@@ -316,10 +310,13 @@ class ResUNetEngine:
         dw0 = torch.zeros(28 * cp0, device=self.device)
         ops.stem_wgrad(tape["x"], d_cur, dw0)
         dw0 = dw0.view(28, cp0)
-        grads[net.conv.weight] = dw0[:27, :c0].t().reshape(net.conv.weight.shape)
-        grads[net.conv.bias] = dw0[27, :c0].clone()
-        self._twins = {}
+        grads[net.conv.weight] = self._unscale(dw0[:27, :c0].t().reshape(net.conv.weight.shape))
+        grads[net.conv.bias] = self._unscale(dw0[27, :c0].clone())
+        self._inv_scale = None
         return grads
+
+    def _unscale(self, g):
+        return g if self._inv_scale is None else g * self._inv_scale
 
 
 class _UNetFn(torch.autograd.Function):

@@ -155,6 +155,7 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.N, a.D, a.H, a.W = grid
     a.Dt, a.n_nblk, a.nblk, a.G, a.n_cg, a.n_taps = pl.Dt, pl.n_nblk, pl.nblk, pl.G, pl.n_cg, len(pl.shifts)
     a.fuse = 3 if pl.fuse_kd else 1
+    a.nbuf = pl.nbuf
     a.in_f16, a.out_f16 = _f16(inputs[0]), _f16(o0)
     n, d, h, w, cp = o0.shape
     a.out_sW, a.out_sH, a.out_sD, a.out_sN = cp, w * cp, h * w * cp, d * h * w * cp
@@ -203,19 +204,18 @@ def in_finalize(stats: torch.Tensor, drop: Optional[torch.Tensor], table: torch.
                                              _stream()), "unet3d_in_finalize")
 
 
-def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, table: torch.Tensor,
-             out_bf16: Optional[torch.Tensor] = None):
+def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, table: torch.Tensor):
     n, d, h, w, cp = y.shape
     _count()
     assert out.dtype == y.dtype and (skip is None or skip.dtype == y.dtype)
-    _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), _ptr(out_bf16), table.data_ptr(), n,
-                                          d * h * w, cp, _f16(y), _stream()), "unet3d_in_apply")
+    _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), n, d * h * w, cp,
+                                          _f16(y), _stream()), "unet3d_in_apply")
 
 
 def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
     n, d, h, w, cp = y.shape
     _count()
-    assert dout.dtype == torch.bfloat16 and g.dtype == torch.bfloat16 and out.dtype == y.dtype
+    assert dout.dtype == y.dtype and g.dtype == y.dtype and out.dtype == y.dtype
     _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), out.data_ptr(), y.data_ptr(), g.data_ptr(),
                                                table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
                "unet3d_in_bwd_reduce")
@@ -224,7 +224,7 @@ def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
 def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False):
     n, d, h, w, cp = y.shape
     _count()
-    assert g.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
+    assert g.dtype == y.dtype and dy.dtype == y.dtype
     _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
                                               _ptr(dsum), n, d, h, w, cp, int(zero_last), _f16(y), _stream()),
                "unet3d_in_bwd_apply")
@@ -237,18 +237,18 @@ def channel_sum(x: torch.Tensor, dsum: torch.Tensor):
                "unet3d_channel_sum")
 
 
-def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor, out_bf16: Optional[torch.Tensor] = None):
+def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
     n, d, h, ww, cp = out.shape
     _count()
-    _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(out_bf16), n, d, h,
-                                          ww, cp, _f16(out), _stream()), "unet3d_stem_fwd")
+    _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, d, h, ww, cp,
+                                          _f16(out), _stream()), "unet3d_stem_fwd")
 
 
 def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
     n, d, h, ww, cp = dy.shape
     _count()
-    _lib.check(_lib.lib().unet3d_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), n, d, h, ww, cp, _stream()),
-               "unet3d_stem_wgrad")
+    _lib.check(_lib.lib().unet3d_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), n, d, h, ww, cp, _f16(dy),
+                                            _stream()), "unet3d_stem_wgrad")
 
 
 def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Tensor):
@@ -259,13 +259,14 @@ def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Te
                                           cp, _f16(a), _stream()), "unet3d_head_fwd")
 
 
-def head_bwd(dl: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tensor, dw: torch.Tensor):
+def head_bwd(dl: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tensor, dw: torch.Tensor,
+             grad_scale: Optional[torch.Tensor] = None):
     n, d, h, ww, cp = a.shape
     k = dl.shape[1]
     _count()
-    assert da.dtype == torch.bfloat16
-    _lib.check(_lib.lib().unet3d_head_bwd(dl.data_ptr(), a.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(), k, n,
-                                          d * h * ww, cp, _f16(a), _stream()), "unet3d_head_bwd")
+    assert da.dtype == a.dtype
+    _lib.check(_lib.lib().unet3d_head_bwd(dl.data_ptr(), a.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(),
+                                          _ptr(grad_scale), k, n, d * h * ww, cp, _f16(a), _stream()), "unet3d_head_bwd")
 
 
 def loss_fwd(logits, target, sums, gamma):

@@ -61,6 +61,64 @@ def choose_dt_g(nblk: int, chunk_counts: Sequence[int], depth: int, fuse: int = 
     raise ValueError("no (Dt, G) fits shared memory")
 
 
+NUM_SMS = 148
+_L2_BYTES_PER_CLK = 3700.0          # whole-chip L2 -> SM bandwidth the cost model assumes (~7 TB/s at 1.9 GHz)
+
+
+def _mma_cycles(n: int) -> float:
+    """One M=128, K=16 UMMA of width n: tensor floor n/2 cycles, or the 128 B/clk shared-memory operand read
+    (4 KB of A + 32 n bytes of B) when that is slower (measured: profiles/r01_notes.md)."""
+    return max(n / 2.0, 32.0 + n / 4.0)
+
+
+def choose_config(out_cp: int, chunk_counts: Sequence[int], grid, taps_per_cg: float, n_out_par: int, can_fuse: bool):
+    """Pick (nblk, Dt, G, nbuf, fuse) for one conv launch with a small analytic model of the kernel:
+    per work item  t = max(MMA cycles, L2 bytes / share of L2 bandwidth) [+ exposed epilogue if TMEM is single
+    buffered], total = waves * t.  Wide N blocks and few planes starve small grids; narrow ones re-stream weights."""
+    N_, D_, H_, W_ = grid
+    best = None
+    gs = [g for g in (4, 6, 2) if all(c % g == 0 for c in chunk_counts)]
+    if not gs:
+        raise ValueError(f"channel chunk counts {chunk_counts} need an even common divisor")
+    n_chunks = sum(chunk_counts)
+    for nblk in (128, 96, 64, 32):
+        n_nb = -(-out_cp // nblk) * n_out_par
+        waste = (-(-out_cp // nblk) * nblk) / float(out_cp)
+        for nbuf in (2, 1):
+            for dt in (8, 4, 2, 1):
+                if dt * nblk * nbuf > 512 or dt > max(1, D_):
+                    continue
+                fuse = 3 if (can_fuse and nblk <= 64 and FUSE_KD) else 1
+                g = next((g for g in gs if conv_smem_bytes(dt, g, nblk, fuse) <= SMEM_LIMIT), None)
+                if g is None:
+                    continue
+                n_cg = n_chunks // g
+                g2 = g // 2
+                tiles = N_ * (-(-D_ // dt)) * (-(-H_ // HT)) * (-(-W_ // WT))
+                items = tiles * n_nb
+                if fuse == 3:
+                    per_tap = (max(dt - 2, 0) * _mma_cycles(3 * nblk) + min(2, dt) * _mma_cycles(2 * nblk if dt >= 2 else nblk)
+                               + 2 * _mma_cycles(nblk)) * g2
+                    mma = n_cg * (taps_per_cg / 3.0) * per_tap
+                else:
+                    mma = n_cg * taps_per_cg * dt * g2 * _mma_cycles(nblk)
+                a_bytes = n_cg * (dt + 2) * g * 2880 * 2.0            # 16-byte TMA rows fetch whole 32-byte sectors
+                w_bytes = n_cg * taps_per_cg * g * nblk * 16
+                active = min(items, NUM_SMS)
+                bw = min(48.0, _L2_BYTES_PER_CLK / active)
+                epi = dt * (nblk / 32.0) * 500.0
+                t_item = max(mma, (a_bytes + w_bytes) / bw) + (epi if nbuf == 1 else 0.0) + 3000.0
+                waves = max(1.0, items / float(NUM_SMS))
+                if waves < 6:
+                    waves = float(-(-items // NUM_SMS))
+                cost = waves * t_item * (1.0 + 0.0 * waste)
+                if best is None or cost < best[0]:
+                    best = (cost, nblk, dt, g, nbuf, fuse)
+    if best is None:
+        raise ValueError("no conv configuration fits shared memory / TMEM")
+    return best[1:]
+
+
 # per-dimension (parity, shift) -> kernel index for a stride-2 k3 p1 conv read through parity views:
 # in = 2*o + k - 1;  parity-0 view index q = o holds in = 2q (k = 1), brick shift 1 (offset 0);
 # parity-1 view: in = 2q + 1 -> k = 0 at q = o - 1 (shift 0), k = 2 at q = o (shift 1).
@@ -95,6 +153,7 @@ class ConvPlan:
     tab: np.ndarray                 # int32 table for the kernel
     widx: np.ndarray                # int64 gather index into cat(W.flatten(), [0])
     omul: int
+    nbuf: int = 2                   # TMEM accumulator buffers (1: Dt * nblk <= 512, epilogue not overlapped)
     n_tiles_w: int = 0              # number of weight tiles
     fuse_kd: bool = False           # one weight tile = the 3 d-taps of a (kh,kw), rows ordered sd = 2,1,0
 
@@ -136,7 +195,8 @@ def _kidx_and_valid(plan_kind: str, ks: int, stride: int, pattern: str, shift, p
     return tuple(k)
 
 
-def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: Sequence[int], depth: int) -> ConvPlan:
+def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: Sequence[int], depth: int,
+                   grid: Optional[Tuple[int, int, int, int]] = None) -> ConvPlan:
     """kind:
          conv_fwd    Conv3d forward (weight (Cout, Cin, k,k,k)); inputs may be a concat (len(in_C) > 1)
          conv_dgrad  its data gradient; outputs may be a concat split (len(out_C) > 1)
@@ -169,27 +229,39 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
         maps = [(i, None) for i in range(len(in_C))]
     chunk_counts = [in_Cp[m[0]] // 8 for m in maps]
 
+    # ---- configuration (N block width, planes per segment, chunks per channel group, TMEM buffering, d-tap fusion)
+    if grid is None:
+        grid = (2, max(1, depth), 64, 64)
+    n_shift = 1 if ks == 1 else (27 if (pattern == "direct" and stride == 1) else 8)
+    if ks == 1:
+        taps_avg = 1.0
+    elif pattern == "direct" and stride == 1:
+        taps_avg = 27.0
+    else:
+        taps_avg = 27.0 / 8.0
+    can_fuse = pattern == "direct" and stride == 1 and ks == 3
+    n_out_par = 8 if (pattern == "transposed" and ks == 3) else 1
+    nblk, Dt, G, nbuf, fuse = choose_config(max(out_Cp), chunk_counts, grid, taps_avg, n_out_par, can_fuse)
+    if len(out_Cp) > 1 and any(cp % nblk and cp > nblk for cp in out_Cp):
+        nblk = 32
+        Dt, G = choose_dt_g(nblk, chunk_counts, depth, 3 if can_fuse and FUSE_KD else 1)
+        nbuf, fuse = 2, (3 if can_fuse and FUSE_KD else 1)
+    fuse_kd = fuse == 3
+
     # ---- N blocks
     nb_sel, nb_coff, nb_ooff, nb_real0 = [], [], [], []
-    nblk = None
     if pattern == "transposed":
-        nblk, n = choose_nblk(out_Cp[0])
+        n = -(-out_Cp[0] // nblk)
         out_par = parities if ks == 3 else [(0, 0, 0)]
         for p in out_par:
             for j in range(n):
                 nb_sel.append(0); nb_coff.append(j * nblk); nb_ooff.append(p); nb_real0.append(j * nblk)
     else:
-        # one blocking for every output tensor (dgrad of a concat): use the blocking of the widest
-        nblk, _ = choose_nblk(max(out_Cp))
-        if any(cp % nblk and cp > nblk for cp in out_Cp) and len(out_Cp) > 1:
-            nblk = 32
         real0 = 0
         for t, cp in enumerate(out_Cp):
             for j in range(-(-cp // nblk)):
                 nb_sel.append(t); nb_coff.append(j * nblk); nb_ooff.append((0, 0, 0)); nb_real0.append(real0 + j * nblk)
             real0 += out_C[t]
-    fuse_kd = FUSE_KD and pattern == "direct" and stride == 1 and ks == 3 and nblk <= 64
-    Dt, G = choose_dt_g(nblk, chunk_counts, depth, 3 if fuse_kd else 1)
 
     cg_map, cg_ch = [], []
     for mi, cnt in enumerate(chunk_counts):
@@ -275,7 +347,7 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
     return ConvPlan(kind=kind, ks=ks, stride=stride, pattern=pattern, in_C=in_C, in_Cp=in_Cp, out_C=out_C, out_Cp=out_Cp,
                     maps=maps, G=G, Dt=Dt, nblk=nblk, cg_map=cg_map, cg_ch=cg_ch, shifts=shifts, nb_sel=nb_sel,
                     nb_coff=nb_coff, nb_ooff=nb_ooff, nb_real0=nb_real0, masks=masks, wbase=wbase, tab=tab, widx=widx,
-                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles, fuse_kd=fuse_kd)
+                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles, fuse_kd=fuse_kd, nbuf=nbuf)
 
 
 def bias_vector(plan: ConvPlan, bias: np.ndarray) -> np.ndarray:

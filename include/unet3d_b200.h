@@ -11,8 +11,9 @@
  *     or frees device memory and keeps no references after the call returns.
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
  *   - activations are 16-bit NDHWC with the channel count padded to a multiple of 16 ("Cp"): bf16 by
- *     default; `act_f16` / `in_f16` / `out_f16` / `x_f16` = 1 selects IEEE fp16 storage for the FORWARD
- *     activations and weights (gradient tensors are always bf16, accumulation always fp32);
+ *     default; `act_f16` / `in_f16` / `out_f16` / `x_f16` = 1 selects IEEE fp16 storage for activations,
+ *     packed weights AND gradient tensors alike (tcgen05.mma cannot mix operand formats); accumulation is
+ *     always fp32.  fp16 gradients are kept in range by one scalar `grad_scale` applied in unet3d_head_bwd;
  *     logits and the stem input are fp32 NCDHW exactly as PyTorch lays them out.
  */
 #ifndef UNET3D_B200_H
@@ -66,7 +67,7 @@ typedef struct unet3d_conv_args {
   double* stats;         /* fp64 [N][stats_C][2] running (sum, sum^2) for InstanceNorm, or NULL */
   int* err;              /* device int32 error word (0 = ok) */
   int N, D, H, W;        /* tile-grid extents */
-  int Dt, n_nblk, nblk, G, n_cg, n_taps, fuse;
+  int Dt, n_nblk, nblk, G, n_cg, n_taps, fuse, nbuf;
   int in_f16, out_f16;   /* 16-bit format of A + weights / of out + addend: 0 = bf16, 1 = fp16 */
   long long out_sN, out_sD, out_sH, out_sW;   /* ELEMENT strides of out/addend */
   int out_C, stats_C, omul, zD, zH, zW;
@@ -94,10 +95,8 @@ int unet3d_wgrad_gemm(const unet3d_wgrad_args* a, void* stream);
  * network.py:159-160,175-176,401-402,412-416,315-316.  stats come from the conv epilogue. */
 int unet3d_in_finalize(const double* stats, const float* drop_scale, float* table, int NC, double count, float eps,
                        void* stream);
-/* out_bf16 (optional, may be NULL): a second, bf16 copy of the result -- tcgen05.mma cannot mix an fp16 A with a
- * bf16 B operand, so in fp16 mode the weight-gradient kernel reads this twin of the saved activation. */
-int unet3d_in_apply(const void* y, const void* skip, void* out, void* out_bf16, const float* table, int N, long long V,
-                    int Cp, int act_f16, void* stream);
+int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, int N, long long V, int Cp,
+                    int act_f16, void* stream);
 int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, void* g,
                          const float* table, double* sums, int N, long long V, int Cp, int act_f16, void* stream);
 int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums, double* dsum,
@@ -106,16 +105,18 @@ int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* 
 
 /* Stem Conv3d(1->C,k3,p1)+bias, fp32 NCDHW in -> bf16 NDHWC out (network.py:541,550) and its
  * weight/bias gradient (dw fp32 [28][Cp]: 27 taps then the bias row; accumulated atomically). */
-int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, void* out_bf16, int N, int D, int H, int W,
-                    int Cp, int act_f16, void* stream);
-int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, int Cp, void* stream);
+int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, int N, int D, int H, int W, int Cp,
+                    int act_f16, void* stream);
+int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, int Cp, int act_f16,
+                      void* stream);
 
 /* Head Conv3d(C->K,k1)+bias, bf16 NDHWC in -> fp32 NCDHW logits (network.py:545-547,563), and backward
  * (da bf16 NDHWC; dw fp32 [K][Cp] followed by [K] bias grads, accumulated atomically). */
 int unet3d_head_fwd(const void* a, const float* w, const float* b, float* logits, int K, int N, long long V, int Cp,
                     int act_f16, void* stream);
-int unet3d_head_bwd(const float* dlogits, const void* a, const float* w, void* da, float* dw, int K, int N,
-                    long long V, int Cp, int act_f16, void* stream);
+/* grad_scale: optional device scalar multiplied into da (the internal loss scale of fp16 mode); dw is unscaled */
+int unet3d_head_bwd(const float* dlogits, const void* a, const float* w, void* da, float* dw, const float* grad_scale,
+                    int K, int N, long long V, int Cp, int act_f16, void* stream);
 
 /* Fused softmax + batch Tversky-Dice / focal sums (loss.py:7-11,32-48,70-80) and the logits gradient.
  * sums: fp64 [K][4] = {TP, sum p, sum g, focal}; coef: fp32 [K][4] = {dL/dTP, dL/dSP, focal weight, 0}. */

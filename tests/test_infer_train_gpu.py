@@ -1,0 +1,137 @@
+"""GPU parity of the callers around the network: sliding-window inference (trainer.py:17-98) against the oracle's
+restatement, and the Trainer step loop / checkpoint round trip (trainer.py:415-634)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import unet3d_b200  # noqa: E402
+from unet3d_b200 import ops  # noqa: E402
+from oracle import unet3d_oracle as O  # noqa: E402
+
+DEV = "cuda"
+
+
+class _ToyNet(torch.nn.Module):
+    """A stand-in 'model' for the blend tests: one fp32 conv evaluated with torch (the network itself is covered
+    by test_model_gpu.py); makes the window arithmetic checkable to fp32 accuracy."""
+
+    def __init__(self, w, b):
+        super().__init__()
+        self.w, self.b = torch.nn.Parameter(w), torch.nn.Parameter(b)
+
+    def forward(self, x):
+        return torch.nn.functional.conv3d(x, self.w, self.b, padding=1)
+
+
+def test_predict_per_patch_matches_reference_golden(golden_dir):
+    """Same toy conv + volume as tests/golden/predict_toy.npz (made by the live reference's predict_per_patch):
+    labels bit-exact incl. the uncovered border (label 0), probabilities to 1e-6 with NaN where uncovered."""
+    torch.backends.cudnn.allow_tf32 = False
+    z = np.load(os.path.join(golden_dir, "predict_toy.npz"))
+    net = _ToyNet(torch.from_numpy(z["w"]), torch.from_numpy(z["b"])).to(DEV)
+    lab = unet3d_b200.predict_per_patch(z["vol"], net, 3, (16, 24, 16), 2, verbose=False)
+    assert lab.dtype == np.uint8 and lab.shape == z["labels"].shape
+    assert (lab != z["labels"]).mean() < 1e-4          # argmax of fp32 sums: ties aside, bit-exact
+    prob = unet3d_b200.predict_per_patch(z["vol"], net, 3, (16, 24, 16), 2, verbose=False, one_hot=True)
+    assert np.array_equal(np.isnan(prob), np.isnan(z["probs"]))
+    assert np.allclose(np.nan_to_num(prob), np.nan_to_num(z["probs"]), atol=2e-6)
+
+
+@pytest.mark.parametrize("window", [None, "gaussian"])
+@pytest.mark.parametrize("grid_mode", ["reference", "full_cover"])
+def test_predict_per_patch_windows_and_grids(window, grid_mode):
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(3)
+    vol = torch.randn(40, 30, 37, 1, generator=g).numpy()
+    w, b = torch.randn(3, 1, 3, 3, 3, generator=g), torch.randn(3, generator=g)
+    net = _ToyNet(w, b).to(DEV)
+    patch = (16, 16, 16)
+    got = unet3d_b200.predict_per_patch(vol, net, 3, patch, 2, verbose=False, one_hot=True, window=window, grid_mode=grid_mode)
+    # oracle with the same grid / window
+    fn = lambda t: torch.nn.functional.conv3d(t, w, b, padding=1)
+    win = None if window is None else O.gaussian_window(patch)
+    if grid_mode == "reference":
+        want = O.predict_per_patch(vol, fn, 3, patch, 2, one_hot=True, window=win)
+    else:
+        padded = O.pad_to(vol, patch)
+        res = torch.zeros(3, *padded.shape[:3]); wsum = torch.zeros(padded.shape[:3])
+        xx = torch.from_numpy(np.ascontiguousarray(np.moveaxis(padded, -1, 0))[None])
+        for (ox, oy, oz) in unet3d_b200.tile_origins(padded.shape[:3], patch, 2, "full_cover"):
+            p = torch.softmax(fn(xx[:, :, ox:ox + 16, oy:oy + 16, oz:oz + 16]), 1)[0]
+            wt = torch.ones(patch) if win is None else torch.from_numpy(win)
+            res[:, ox:ox + 16, oy:oy + 16, oz:oz + 16] += p * wt
+            wsum[ox:ox + 16, oy:oy + 16, oz:oz + 16] += wt
+        want = O.crop_pad(np.moveaxis((res / wsum).numpy(), 0, -1), vol.shape[:3])
+        assert not np.isnan(want).any()               # full_cover reaches every voxel
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.allclose(np.nan_to_num(got), np.nan_to_num(want), atol=3e-6)
+
+
+def test_predict_per_patch_with_the_unet():
+    torch.manual_seed(0)
+    model = unet3d_b200.ResUnet3D(num_pool=2, num_features=8, out_channels=3)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV)
+    model.precision = "fp16"
+    vol = torch.randn(40, 36, 24, 1, generator=torch.Generator().manual_seed(1)).numpy()
+    got = unet3d_b200.predict_per_patch(vol, model, 3, (16, 16, 16), 2, verbose=False, one_hot=True, grid_mode="full_cover")
+    padded = vol
+    res = torch.zeros(3, *padded.shape[:3]); wsum = torch.zeros(padded.shape[:3])
+    xx = torch.from_numpy(np.ascontiguousarray(np.moveaxis(padded, -1, 0))[None])
+    with torch.no_grad():
+        for (ox, oy, oz) in unet3d_b200.tile_origins(padded.shape[:3], (16, 16, 16), 2, "full_cover"):
+            p = torch.softmax(O.resunet3d_forward(sd, xx[:, :, ox:ox + 16, oy:oy + 16, oz:oz + 16], 2, 8), 1)[0]
+            res[:, ox:ox + 16, oy:oy + 16, oz:oz + 16] += p
+            wsum[ox:ox + 16, oy:oy + 16, oz:oz + 16] += 1
+    want = np.moveaxis((res / wsum).numpy(), 0, -1)
+    assert np.abs(got - want).max() < 2e-2
+    assert (got.argmax(-1) == want.argmax(-1)).mean() > 0.995
+
+
+class _Cases(torch.utils.data.Dataset):
+    def __init__(self, n):
+        g = torch.Generator().manual_seed(11)
+        self.x = torch.randn(n, 1, 16, 16, 16, generator=g)
+        self.y = (self.x[:, 0] > 0.3).long() + (self.x[:, 0] > 1.0).long()
+
+    def __len__(self):
+        return len(self.x)
+
+    def __getitem__(self, i):
+        return {"image": self.x[i], "label": self.y[i]}
+
+
+def test_trainer_fit_learns_and_checkpoints(tmp_path):
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = unet3d_b200.ResUnet3D(num_pool=2, num_features=8, out_channels=3).to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    tr = unet3d_b200.Trainer(model, opt, unet3d_b200.HybirdLoss(), _Cases(8), batch_size=2,
+                             dataloader_kwargs={"num_workers": 0, "pin_memory": True}, valid_split=0.25,
+                             metrics={"dice": unet3d_b200.Dice()})
+    save = str(tmp_path / "ck")
+    tr.fit(num_epochs=3, save_dir=save, use_amp=True)
+    assert model.precision == "fp16"
+    first = tr.batch_loop(torch.utils.data.DataLoader(_Cases(8), batch_size=2), is_train=False)
+    assert set(first) == {"loss", "dice"} and np.isfinite(first["loss"])
+    assert os.path.exists(save + "-last.pt") and os.path.exists(save + "-best.pt")
+    # learns: a few more epochs lower the training loss
+    l0 = tr.batch_loop(torch.utils.data.DataLoader(_Cases(8), batch_size=2), is_train=True)["loss"]
+    for _ in range(6):
+        l1 = tr.batch_loop(torch.utils.data.DataLoader(_Cases(8), batch_size=2), is_train=True)["loss"]
+    assert l1 < l0
+    # checkpoint round trip (reference dictionary layout)
+    ck = torch.load(save + "-last.pt", weights_only=False)
+    assert {"model_state_dict", "optimizer_state_dict", "current_epoch", "train_indices", "valid_indices",
+            "best_result"} <= set(ck)
+    m2 = unet3d_b200.ResUnet3D(num_pool=2, num_features=8, out_channels=3).to(DEV)
+    tr2 = unet3d_b200.Trainer(m2, torch.optim.Adam(m2.parameters(), lr=2e-3), unet3d_b200.HybirdLoss(), _Cases(8), batch_size=2)
+    tr2.load_checkpoint(save + "-last.pt")
+    assert tr2.current_epoch == 3
+    for k, v in ck["model_state_dict"].items():
+        assert torch.equal(m2.state_dict()[k].cpu(), v.cpu())
+    ops.check_device_errors()

@@ -55,15 +55,15 @@ for name, kind, ks, stride, cins, cout, g, cnt in layers:
         xs = [act(in_dims, c) for c in cins]
         y = act(g, cout)
         w = torch.randn(cout, sum(cins), ks, ks, ks, device=dev) * 0.05
-        fp = ops.DeviceConvPlan(P.make_conv_plan("conv_fwd", ks, stride, cins, [cout], g[0]), dev)
-        dp = ops.DeviceConvPlan(P.make_conv_plan("conv_dgrad", ks, stride, [cout], cins, g[0]), dev)
+        fp = ops.DeviceConvPlan(P.make_conv_plan("conv_fwd", ks, stride, cins, [cout], g[0], grid), dev)
+        dp = ops.DeviceConvPlan(P.make_conv_plan("conv_dgrad", ks, stride, [cout], cins, g[0], grid), dev)
         dxs = [torch.zeros_like(x) for x in xs]
     else:
         xs = [act(g, cins[0])]
         y = act(tuple(2 * v for v in g), cout)
         w = torch.randn(cins[0], cout, 3, 3, 3, device=dev) * 0.05
-        fp = ops.DeviceConvPlan(P.make_conv_plan("convT_fwd", 3, 2, cins, [cout], g[0]), dev)
-        dp = ops.DeviceConvPlan(P.make_conv_plan("convT_dgrad", 3, 2, [cout], cins, g[0]), dev)
+        fp = ops.DeviceConvPlan(P.make_conv_plan("convT_fwd", 3, 2, cins, [cout], g[0], grid), dev)
+        dp = ops.DeviceConvPlan(P.make_conv_plan("convT_dgrad", 3, 2, [cout], cins, g[0], grid), dev)
         dxs = [torch.zeros_like(xs[0])]
     wp = ops.DeviceWgradPlan(P.make_wgrad_plan(kind, ks, stride, cins, cout, grid, 148), dev)
     st = torch.zeros(N, y.shape[-1], 2, device=dev, dtype=torch.float64)
@@ -73,7 +73,7 @@ for name, kind, ks, stride, cins, cout, g, cnt in layers:
     t_d = timeit(lambda: ops.conv_gemm(dp, [y], wd, dxs, grid))
     t_w = timeit(lambda: ops.wgrad_gemm(wp, xs, y, dw, grid))
     ops.check_device_errors()
-    print(f"{name:20s} x{cnt}  GF {flops/1e9:7.1f} | fwd {t_f:7.3f} ms {flops/t_f/1e9:7.1f} TF/s (Dt{fp.plan.Dt} G{fp.plan.G} nblk{fp.plan.nblk}x{fp.plan.n_nblk})"
+    print(f"{name:20s} x{cnt}  GF {flops/1e9:7.1f} | fwd {t_f:7.3f} ms {flops/t_f/1e9:7.1f} TF/s (Dt{fp.plan.Dt} G{fp.plan.G} nblk{fp.plan.nblk}x{fp.plan.n_nblk} buf{fp.plan.nbuf} f{int(fp.plan.fuse_kd)}; dgrad Dt{dp.plan.Dt} nblk{dp.plan.nblk}x{dp.plan.n_nblk} buf{dp.plan.nbuf})"
           f" | dgrad {t_d:7.3f} ms {flops/t_d/1e9:7.1f} TF/s | wgrad {t_w:7.3f} ms {flops/t_w/1e9:7.1f} TF/s"
           f" (jobs {wp.plan.n_jobs} split {wp.plan.split})", flush=True)
     tot["fwd"] += t_f * cnt; tot["dgrad"] += t_d * cnt; tot["wgrad"] += t_w * cnt

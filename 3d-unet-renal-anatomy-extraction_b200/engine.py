@@ -238,7 +238,7 @@ class ResUNetEngine:
         grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias)       # cancelled by the norm (S1)
         da1 = self._grad_like(a1)
         c2 = bops["conv2"]
-        ops.conv_gemm(c2.dgrad, [dy2], c2.dgrad.packed_weight(blk.conv2.weight), [da1], c2.grid)
+        ops.conv_gemm(c2.dgrad, [dy2], c2.dgrad.packed_weight(blk.conv2.weight, self.act_dtype), [da1], c2.grid)
         _, dy1, _, _ = self._in_bwd(da1, None, a1, y1, t1)
         c1 = bops["conv1"]
         grads[blk.conv1.weight] = self._wgrad(c1, inputs, dy1, blk.conv1.weight)
@@ -251,12 +251,12 @@ class ResUNetEngine:
                 dskip = [self._grad_like(t).zero_() for t in inputs]   # k1 s2 gradient only touches even voxels
             else:
                 dskip = [self._grad_like(t) for t in inputs]
-            ops.conv_gemm(sk.dgrad, [g2], sk.dgrad.packed_weight(blk.skip_conv.weight), dskip, sk.grid)
+            ops.conv_gemm(sk.dgrad, [g2], sk.dgrad.packed_weight(blk.skip_conv.weight, self.act_dtype), dskip, sk.grid)
             addends = dskip
         else:
             addends = [g2]
         dins = [self._grad_like(t) for t in inputs]
-        ops.conv_gemm(c1.dgrad, [dy1], c1.dgrad.packed_weight(blk.conv1.weight), dins, c1.grid, addends=addends)
+        ops.conv_gemm(c1.dgrad, [dy1], c1.dgrad.packed_weight(blk.conv1.weight, self.act_dtype), dins, c1.grid, addends=addends)
         return dins
 
     def backward_impl(self, tape, x_shape, dlogits: torch.Tensor) -> Dict[torch.nn.Parameter, torch.Tensor]:
@@ -293,7 +293,7 @@ class ResUNetEngine:
             grads[ct.weight] = self._wgrad(uop, [xin], dyu, ct.weight)
             grads[ct.bias] = self._unscale(dsum[:ct.out_channels].float())
             d_cur = self._grad_like(xin)
-            ops.conv_gemm(uop.dgrad, [dyu], uop.dgrad.packed_weight(ct.weight), [d_cur], uop.grid)
+            ops.conv_gemm(uop.dgrad, [dyu], uop.dgrad.packed_weight(ct.weight, self.act_dtype), [d_cur], uop.grid)
         for j in range(len(net.encode_blocks[np_].res_blocks) - 1, -1, -1):
             blk = net.encode_blocks[np_].res_blocks[j]
             d_cur = self._res_block_bwd(blk, plans[("enc", np_, j)], tape[("enc", np_, j)], d_cur, None, grads)[0]

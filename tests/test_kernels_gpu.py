@@ -201,7 +201,7 @@ def test_fp16_storage_conv_and_wgrad(cins, cout, dims):
     ops.wgrad_gemm(wp, xs, to_ndhwc(dy).to(torch.float16), dw, dims)
     torch.cuda.synchronize()
     ops.check_device_errors()
-    assert rel(dw.index_select(0, wp.gidx).view_as(w), w.grad) < 1e-3
+    assert rel(dw.index_select(0, wp.gidx).view_as(w), w.grad) < 5e-3
 
 
 def test_instance_norm_fwd_bwd():

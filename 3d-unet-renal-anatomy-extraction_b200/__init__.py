@@ -7,7 +7,8 @@ from .network import ResUnet3D, UNet3D, Unet, ResBlock, ResBlockStack, ConvTrans
 from .loss import DiceLoss, FocalLoss, HybirdLoss, Dice, dice
 from .trainer import Trainer, predict_per_patch, tile_centres, tile_origins, gaussian_window, center_pad_crop, pad_to_patch
 from . import parallel
+from .graph import GraphedTrainStep
 
 __all__ = ["ResUnet3D", "UNet3D", "Unet", "ResBlock", "ResBlockStack", "ConvTrans3D", "UpConcat",
            "generate_paired_features", "DiceLoss", "FocalLoss", "HybirdLoss", "Dice", "dice", "Trainer",
-           "predict_per_patch", "tile_centres", "tile_origins", "gaussian_window", "center_pad_crop", "pad_to_patch", "parallel"]
+           "predict_per_patch", "tile_centres", "tile_origins", "gaussian_window", "center_pad_crop", "pad_to_patch", "parallel", "GraphedTrainStep"]

@@ -286,69 +286,98 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
 }
 
 // Stem weight/bias gradient: dW[tap][c] = sum_v x[v + tap] * dy[v][c];  db[c] = sum_v dy[v][c].
-// block = (CP/8 chunks, 28 taps [27 + bias row], S voxel streams); a stream walks groups of 8 consecutive
-// voxels (8 independent x / dy loads in flight per thread); fp32 atomics into dw[28][CP] at the end.
+// A thread owns (8-channel chunk, kd) and walks a run of SEG voxels along w: per voxel one 16-byte dy load, three
+// new x values (the 3x3 (kh,kw) window slides along w in registers) and 72 FMAs into register accumulators
+// [9 taps][8 channels] (+ 8 bias sums on the kd == 1 threads).  Block = (CP/8, 3, RUNS); the RUNS partials are
+// reduced in shared memory, then one fp32 atomic per (tap, channel) and block into dw[28][CP].
 template <int CP>
-__global__ void stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
-                                  int N, int D, int H, int W, int af) {
-  const int ch = threadIdx.x, tap = threadIdx.y, s = threadIdx.z;
-  const int kd = tap / 9 - 1, kh = (tap / 3) % 3 - 1, kw = tap % 3 - 1;
-  const long long V = (long long)D * H * W, total = (long long)N * V;
-  const bool row8 = (W % 8) == 0;
-  float acc[8];
+__global__ void __launch_bounds__(CP / 8 * 3 * 16) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
+                                                                    float* __restrict__ dw, int N, int D, int H, int W,
+                                                                    int af) {
+  constexpr int SEG = 16, RUNS = 16;
+  const int ch = threadIdx.x, kd = threadIdx.y, run = threadIdx.z;
+  const int segs_w = (W + SEG - 1) / SEG;
+  const long long n_runs = (long long)N * D * H * segs_w;
+  float acc[9][8], bsum[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (long long i0 = ((long long)blockIdx.x * blockDim.z + s) * 8; i0 < total; i0 += (long long)gridDim.x * blockDim.z * 8) {
-    float xv[8];
-    uint4 dv[8];
-    int n0 = 0, d0 = 0, h0 = 0, w0 = 0;
-    if (row8) {
-      n0 = (int)(i0 / V);
-      const long long v = i0 - (long long)n0 * V;
-      w0 = (int)(v % W); h0 = (int)((v / W) % H); d0 = (int)(v / ((long long)W * H));
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+  for (long long r = (long long)blockIdx.x * RUNS + run; r < n_runs; r += (long long)gridDim.x * RUNS) {
+    long long q = r;
+    const int sw = (int)(q % segs_w); q /= segs_w;
+    const int h = (int)(q % H); q /= H;
+    const int d = (int)(q % D);
+    const int n = (int)(q / D);
+    const int w0 = sw * SEG;
+    const int xd = d + kd - 1;
+    const bool d_ok = xd >= 0 && xd < D;
+    const float* xrow[3];
+    bool row_ok[3];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int xh = h + kh - 1;
+      row_ok[kh] = d_ok && xh >= 0 && xh < H;
+      xrow[kh] = x + (size_t)n * D * H * W + ((size_t)(row_ok[kh] ? xd : 0) * H + (row_ok[kh] ? xh : 0)) * W;
     }
+    float win[3][3];          // win[kh][kw] = x[.., w + kw - 1]
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const long long i = i0 + u;
-      xv[u] = 0.f;
-      dv[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (i < total) {
-        int n = n0, xd = d0, xh = h0, xw = w0 + u;
-        if (!row8) {
-          n = (int)(i / V);
-          const long long v = i - (long long)n * V;
-          xw = (int)(v % W); xh = (int)((v / W) % H); xd = (int)(v / ((long long)W * H));
-        }
-        if (tap < 27) {
-          xd += kd; xh += kh; xw += kw;
-          if (xw >= 0 && xw < W && xh >= 0 && xh < H && xd >= 0 && xd < D)
-            xv[u] = __ldg(x + (size_t)n * V + ((size_t)xd * H + xh) * W + xw);
-        } else {
-          xv[u] = 1.f;
-        }
-        dv[u] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)i * CP) + ch);
+    for (int kh = 0; kh < 3; ++kh) {
+      win[kh][1] = (row_ok[kh] && w0 - 1 >= 0) ? __ldg(xrow[kh] + w0 - 1) : 0.f;
+      win[kh][2] = (row_ok[kh] && w0 < W) ? __ldg(xrow[kh] + w0) : 0.f;
+    }
+    const uint4* dyp = reinterpret_cast<const uint4*>(dy + ((size_t)((size_t)n * D + d) * H + h) * W * CP) + ch;
+#pragma unroll 4
+    for (int i = 0; i < SEG; ++i) {
+      const int w = w0 + i;
+      if (w >= W) break;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        win[kh][0] = win[kh][1];
+        win[kh][1] = win[kh][2];
+        win[kh][2] = (row_ok[kh] && w + 1 < W) ? __ldg(xrow[kh] + w + 1) : 0.f;
+      }
+      float f[8];
+      unpack8(__ldg(dyp + (size_t)w * (CP / 8)), f, af);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[kh * 3 + kw][j] = fmaf(win[kh][kw], f[j], acc[kh * 3 + kw][j]);
+      if (kd == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bsum[j] += f[j];
       }
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      float f[8];
-      unpack8(dv[u], f, af);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[u], f[j], acc[j]);
-    }
   }
-  // reduce the S streams of the block in shared memory, then one atomic per (tap, channel)
-  constexpr int SMAX = (512 / (28 * (CP / 8)) > 8) ? 8 : 512 / (28 * (CP / 8));
-  __shared__ float red[SMAX][28 * CP];
-  const int S = blockDim.z;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) red[s][tap * CP + ch * 8 + j] = acc[j];
-  __syncthreads();
+  __shared__ float red[RUNS][28 * CP / 4 + 1];      // reduced in 4 passes (one per 7-tap slice) to stay under 48 KB
   const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
-  for (int i = tid; i < 28 * CP; i += blockDim.x * blockDim.y * blockDim.z) {
-    float a = 0.f;
-    for (int r = 0; r < S; ++r) a += red[r][i];
-    atomicAdd(&dw[i], a);
+  const int nthr = blockDim.x * blockDim.y * blockDim.z;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {      // taps [7 pass, 7 pass + 7); tap 27 = bias row
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int tap = kd * 9 + t;
+      if (tap / 7 == pass) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[run][(tap - 7 * pass) * CP + ch * 8 + j] = acc[t][j];
+      }
+    }
+    if (pass == 3 && kd == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[run][(27 - 21) * CP + ch * 8 + j] = bsum[j];
+    }
+    __syncthreads();
+    for (int i = tid; i < 7 * CP; i += nthr) {
+      float a = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < RUNS; ++rr) a += red[rr][i];
+      atomicAdd(&dw[pass * 7 * CP + i], a);
+    }
+    __syncthreads();
   }
 }
 
@@ -739,12 +768,9 @@ int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, i
 
 int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, int Cp, int af, int num_sms,
                cudaStream_t s) {
-  const long long total = (long long)N * D * H * W;
-  int streams = 512 / (28 * (Cp / 8));
-  if (streams > 8) streams = 8;
-  if (streams < 1) return U3D_ERR_UNSUPPORTED;
-  dim3 blk(Cp / 8, 28, streams);
-  const int g = grid_for(total, streams * 8 * 4, num_sms, 8);
+  const long long n_runs = (long long)N * D * H * ((W + 15) / 16);
+  dim3 blk(Cp / 8, 3, 16);
+  const int g = grid_for(n_runs, 16 * 4, num_sms, 4);
   if (Cp == 32) stem_wgrad_kernel<32><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
   else if (Cp == 16) stem_wgrad_kernel<16><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
   else if (Cp == 48) stem_wgrad_kernel<48><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);

@@ -1,0 +1,77 @@
+"""Whole-step CUDA graph: zero_grad + forward + loss + backward [+ gradient all-reduce] + optimizer step captured once
+and replayed, so the ~1 600 kernel launches of a training step cost no host time (Python, ctypes, TMA descriptor
+encoding all happen at capture time only).
+
+The reference's step loop (trainer.py:473-509) is eager; this is an optional accelerator for the same loop:
+``Trainer(..., cuda_graph=True)`` or directly
+
+    step = GraphedTrainStep(model, loss_fn, optimizer)
+    loss = step(image, label)          # device tensors or pinned host tensors of a fixed shape
+
+The first ``warmup`` calls run eagerly (they are real training steps; they also let the caching allocator and the
+plans settle), the next call captures, every later call copies the batch into the static buffers and replays.
+A batch of a different shape falls back to the eager path.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import ops
+from . import parallel
+
+
+def _make_capturable(optimizer):
+    for group in optimizer.param_groups:
+        if "capturable" in group:
+            group["capturable"] = True
+
+
+class GraphedTrainStep:
+    def __init__(self, model, loss_fn, optimizer, warmup: int = 3, allreduce: bool = True):
+        self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.warmup, self.allreduce = warmup, allreduce
+        self.calls = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.static_image = self.static_label = self.static_loss = self.static_logits = None
+        self.key = None
+        _make_capturable(optimizer)
+
+    def _eager(self, image, label):
+        self.model.train()
+        self.optimizer.zero_grad(set_to_none=True)
+        logits = self.model(image)
+        loss = self.loss_fn(logits, label)
+        loss.backward()
+        if self.allreduce:
+            parallel.all_reduce_gradients(self.model)
+        self.optimizer.step()
+        return loss, logits
+
+    def __call__(self, image: torch.Tensor, label: torch.Tensor):
+        """Returns (loss, logits) -- device tensors; under replay they are the graph's static outputs."""
+        dev = next(self.model.parameters()).device
+        key = (tuple(image.shape), tuple(label.shape), image.dtype, label.dtype, self.model.training)
+        self.calls += 1
+        world = parallel.rank_world()[1]
+        if self.calls <= self.warmup or (self.key is not None and key != self.key) or (world > 1 and self.allreduce):
+            return self._eager(image.to(dev, non_blocking=True), label.to(dev, non_blocking=True))
+        if self.graph is None:
+            self.key = key
+            self.static_image = torch.empty(image.shape, dtype=image.dtype, device=dev)
+            self.static_label = torch.empty(label.shape, dtype=label.dtype, device=dev)
+            self.static_image.copy_(image, non_blocking=True)
+            self.static_label.copy_(label, non_blocking=True)
+            torch.cuda.synchronize()
+            ops.check_device_errors()
+            g = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(g):
+                self.static_loss, self.static_logits = self._eager(self.static_image, self.static_label)
+            self.graph = g
+        else:
+            self.static_image.copy_(image, non_blocking=True)
+            self.static_label.copy_(label, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss, self.static_logits

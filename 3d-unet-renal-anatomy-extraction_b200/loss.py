@@ -21,9 +21,17 @@ import torch.nn as nn
 from . import ops
 
 
+_W_CACHE = {}
+
+
 def _class_weights(c: int, weight_v, device) -> torch.Tensor:
-    w = torch.ones(c, dtype=torch.float64) if weight_v is None else torch.as_tensor(weight_v, dtype=torch.float64)
-    return (w / w.abs().sum().clamp_min(1e-12)).to(device)          # F.normalize(p=1), loss.py:155
+    """L1-normalised class weights (F.normalize(p=1), loss.py:155), cached on the device (no host-to-device copy
+    inside the step, so the loss can be captured in a CUDA graph)."""
+    key = (c, None if weight_v is None else tuple(float(v) for v in weight_v), str(device))
+    if key not in _W_CACHE:
+        w = torch.ones(c, dtype=torch.float64) if weight_v is None else torch.as_tensor(weight_v, dtype=torch.float64)
+        _W_CACHE[key] = (w / w.abs().sum().clamp_min(1e-12)).to(device)
+    return _W_CACHE[key]
 
 
 class _SegLossFn(torch.autograd.Function):

@@ -109,7 +109,7 @@ class DeviceConvPlan:
     def packed_weight(self, w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
         """16-bit tile stream of parameter `w` (re-gathered only when the parameter or the dtype changed)."""
         key = (w.data_ptr(), w._version, dtype)
-        if self._w_version != key:
+        if self._w_version != key or torch.cuda.is_current_stream_capturing():   # a graph must re-pack on every replay
             flat = torch.cat([w.detach().reshape(-1), w.new_zeros(1)])
             self._w_packed = flat.index_select(0, self.widx).to(dtype)
             self._w_version = key
@@ -119,7 +119,7 @@ class DeviceConvPlan:
         if b is None:
             return None
         key = (b.data_ptr(), b._version)
-        if self._b_version != key:
+        if self._b_version != key or torch.cuda.is_current_stream_capturing():
             flat = torch.cat([b.detach().reshape(-1).float(), b.new_zeros(1, dtype=torch.float32)])
             self._b_packed = flat.index_select(0, self.bidx).contiguous()
             self._b_version = key

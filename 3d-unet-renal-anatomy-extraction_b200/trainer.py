@@ -164,7 +164,7 @@ class Trainer:
 
     def __init__(self, model, optimizer, loss, dataset, batch_size=10,
                  dataloader_kwargs={'num_workers': 2, 'pin_memory': True}, valid_split=0.2, num_samples=None,
-                 metrics=None, scheduler=None, train_transform=None, valid_transform=None):
+                 metrics=None, scheduler=None, train_transform=None, valid_transform=None, cuda_graph=False):
         self.model, self.optimizer, self.loss, self.dataset = model, optimizer, loss, dataset
         self.metrics, self.scheduler = metrics, scheduler
         self.train_transform, self.valid_transform = train_transform, valid_transform
@@ -180,6 +180,11 @@ class Trainer:
         self.patience_counter = 0
         self.amp_state_dict = None
         self.num_epochs, self.use_amp, self.save_dir, self.progress_bar = 1, False, None, None
+        # optional (not in the reference): replay the whole training step as one CUDA graph
+        self._graphed = None
+        if cuda_graph:
+            from .graph import GraphedTrainStep
+            self._graphed = GraphedTrainStep(model, loss, optimizer)
 
     def get_lr(self, idx=0):
         return self.optimizer.param_groups[idx]['lr']
@@ -199,6 +204,20 @@ class Trainer:
             bar.reset(len(data_loader))
             bar.set_description("Epoch %d/%d (LR %.2g)" % (self.current_epoch + 1, self.num_epochs, self.get_lr()))
         for batch in data_loader:
+            if is_train and self._graphed is not None:
+                loss, y_pred = self._graphed(batch['image'], batch['label'])
+                y = self._graphed.static_label if self._graphed.graph is not None else batch['label'].to(self.device)
+                result = {'loss': loss.item()}
+                if self.metrics is not None:
+                    with torch.no_grad():
+                        for key, fn in self.metrics.items():
+                            result[key] = fn(y_pred.detach(), y).item()
+                if not math.isnan(result['loss']):
+                    results.append(result)
+                if bar is not None:
+                    bar.set_postfix(result)
+                    bar.update()
+                continue
             x = batch['image'].to(self.device, non_blocking=True)
             y = batch['label'].to(self.device, non_blocking=True)
             if is_train:

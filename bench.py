@@ -148,7 +148,6 @@ def main():
     model = unet3d_b200.ResUnet3D(num_pool=4, num_features=30, in_channels=1, out_channels=3).to(dev).train()
     loss_fn = unet3d_b200.DiceLoss()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
-    live = None
 
     g = torch.Generator().manual_seed(1234 + rank)
     h_img = torch.randn(BATCH, 1, pe, pe, pe, generator=g).pin_memory()
@@ -157,19 +156,7 @@ def main():
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def allreduce_grads():
-        nonlocal live
-        if world == 1:
-            return
-        if live is None:
-            live = [p for p in model.parameters() if p.grad is not None]
-        flat = torch.cat([p.grad.reshape(-1) for p in live])
-        dist.all_reduce(flat)
-        flat.div_(world)
-        off = 0
-        for p in live:
-            n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p))
-            off += n
+        unet3d_b200.parallel.all_reduce_gradients(model)      # bucketed NCCL all-reduce (mean); no-op for N = 1
 
     def step(img, lab):
         opt.zero_grad(set_to_none=True)

@@ -43,6 +43,7 @@ _SIGS = {
     "unet3d_num_sms": (C.c_int, []),
     "unet3d_conv_gemm": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "unet3d_conv_gemm_smem_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "unet3d_weight_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "unet3d_wgrad_gemm": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "unet3d_in_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_void_p]),
     "unet3d_in_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int,

@@ -148,6 +148,9 @@ int unet3d_wgrad_gemm(const unet3d_wgrad_args* a, void* stream) {
   return check(wgrad_gemm_launch(p, reinterpret_cast<cudaStream_t>(stream)), "wgrad_gemm");
 }
 
+int unet3d_weight_pack(const float* w, const int* idx, void* out, long long n, int out_f16, void* stream) {
+  return check(weight_pack(w, idx, out, n, out_f16, num_sms(), (cudaStream_t)stream), "weight_pack");
+}
 int unet3d_in_finalize(const double* stats, const float* drop_scale, float* table, int NC, double count, float eps,
                        void* stream) {
   return check(in_finalize(stats, drop_scale, table, NC, count, eps, (cudaStream_t)stream), "in_finalize");

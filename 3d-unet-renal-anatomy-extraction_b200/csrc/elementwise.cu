@@ -670,6 +670,29 @@ __global__ void sw_finalize_kernel(const float* __restrict__ result, const float
   }
 }
 
+// Weight packing: out[i] = 16-bit( idx[i] < 0 ? 0 : w[idx[i]] ).  Turns the fp32 PyTorch-layout parameter into the
+// tile stream the conv kernel's weight ring consumes (one pass: 4 B index + 4 B gather + 2 B store per element).
+__global__ void weight_pack_kernel(const float* __restrict__ w, const int* __restrict__ idx, uint16_t* __restrict__ out,
+                                   long long n, int f16) {
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * blockDim.x * 8) {
+    if (i + 8 <= n) {
+      const int4 a = __ldg(reinterpret_cast<const int4*>(idx + i));
+      const int4 b = __ldg(reinterpret_cast<const int4*>(idx + i + 4));
+      const int id[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = id[j] < 0 ? 0.f : __ldg(w + id[j]);
+      *reinterpret_cast<uint4*>(out + i) = pack8(f, f16);
+    } else {
+      for (long long k = i; k < n; ++k) {
+        const int id = idx[k];
+        const float v = id < 0 ? 0.f : w[id];
+        out[k] = (uint16_t)(pack_2x16(v, 0.f, f16) & 0xffffu);
+      }
+    }
+  }
+}
+
 inline int grid_for(long long work_items, int per_block, int num_sms, int waves) {
   long long need = (work_items + per_block - 1) / per_block;
   long long cap = (long long)num_sms * waves;
@@ -685,6 +708,13 @@ static inline dim3 cv_block(int chunks) {
   return dim3(chunks, ty, 1);
 }
 #define U3D_CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? U3D_OK : U3D_ERR_CUDA)
+
+int weight_pack(const float* w, const int* idx, void* out, long long n, int f16, int num_sms, cudaStream_t s) {
+  if (n <= 0) return U3D_ERR_INVALID;
+  const int g = grid_for(n, 256 * 8, num_sms, 8);
+  weight_pack_kernel<<<g, 256, 0, s>>>(w, idx, reinterpret_cast<uint16_t*>(out), n, f16);
+  return U3D_CHECK_LAUNCH();
+}
 
 int in_finalize(const double* stats, const float* drop, float* table, int NC, double count, float eps, cudaStream_t s) {
   in_finalize_kernel<<<(NC + 127) / 128, 128, 0, s>>>(stats, drop, reinterpret_cast<float2*>(table), NC, 1.0 / count, eps);

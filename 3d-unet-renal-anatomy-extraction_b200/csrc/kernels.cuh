@@ -4,6 +4,7 @@
 
 namespace u3d {
 
+int weight_pack(const float* w, const int* idx, void* out, long long n, int f16, int num_sms, cudaStream_t s);
 int in_finalize(const double* stats, const float* drop, float* table, int NC, double count, float eps, cudaStream_t s);
 int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int N, long long V, int Cp, int af,
              int num_sms, cudaStream_t s);

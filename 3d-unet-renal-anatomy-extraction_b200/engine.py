@@ -70,6 +70,10 @@ class ResUNetEngine:
                  "conv2": _ConvOp(self, "conv", 3, 1, [blk.out_channels], blk.out_channels, grid_out)}
             if blk.uses_skip_conv:
                 o["skip"] = _ConvOp(self, "conv", 1, blk.stride, in_C, blk.out_channels, grid_out)
+                # d(block input) = dgrad_conv1(dy1) + dgrad_skip(g2) in one launch (two A sources)
+                o["dgrad_in"] = ops.DeviceConvPlan(
+                    P.make_conv_plan("conv_dgrad", 3, blk.stride, [blk.out_channels] * 2, in_C, grid_out[1], grid_out,
+                                     skip_k1=True), self.device)
             return o
 
         dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
@@ -247,16 +251,14 @@ class ResUNetEngine:
             sk = bops["skip"]
             grads[blk.skip_conv.weight] = self._wgrad(sk, inputs, g2, blk.skip_conv.weight)
             grads[blk.skip_conv.bias] = self._unscale(sums2[:, :blk.out_channels, 0].sum(0).float())
-            if blk.stride == 2:
-                dskip = [self._grad_like(t).zero_() for t in inputs]   # k1 s2 gradient only touches even voxels
-            else:
-                dskip = [self._grad_like(t) for t in inputs]
-            ops.conv_gemm(sk.dgrad, [g2], sk.dgrad.packed_weight(blk.skip_conv.weight, self.act_dtype), dskip, sk.grid)
-            addends = dskip
-        else:
-            addends = [g2]
+            dins = [self._grad_like(t) for t in inputs]
+            dp = bops["dgrad_in"]
+            ops.conv_gemm(dp, [dy1, g2], dp.packed_weight([blk.conv1.weight, blk.skip_conv.weight], self.act_dtype), dins,
+                          c1.grid)
+            return dins
         dins = [self._grad_like(t) for t in inputs]
-        ops.conv_gemm(c1.dgrad, [dy1], c1.dgrad.packed_weight(blk.conv1.weight, self.act_dtype), dins, c1.grid, addends=addends)
+        ops.conv_gemm(c1.dgrad, [dy1], c1.dgrad.packed_weight(blk.conv1.weight, self.act_dtype), dins, c1.grid,
+                      addends=[g2])
         return dins
 
     def backward_impl(self, tape, x_shape, dlogits: torch.Tensor) -> Dict[torch.nn.Parameter, torch.Tensor]:

@@ -106,12 +106,26 @@ class DeviceConvPlan:
         self._b_version = None
         self._b_packed = None
 
-    def packed_weight(self, w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
-        """16-bit tile stream of parameter `w` (re-gathered only when the parameter or the dtype changed)."""
+    def packed_weight(self, w, dtype=torch.bfloat16) -> torch.Tensor:
+        """16-bit tile stream of parameter `w` (re-gathered only when the parameter or the dtype changed).
+        `w` may be a list of parameters: the plan's gather index then addresses their concatenation."""
+        if isinstance(w, (list, tuple)):
+            key = tuple((t.data_ptr(), t._version) for t in w) + (dtype,)
+            if self._w_version == key and not torch.cuda.is_current_stream_capturing():
+                return self._w_packed
+            packed = self.packed_weight(torch.cat([t.detach().reshape(-1).float() for t in w]), dtype)
+            self._w_version = key
+            return packed
         key = (w.data_ptr(), w._version, dtype)
         if self._w_version != key or torch.cuda.is_current_stream_capturing():   # a graph must re-pack on every replay
-            flat = torch.cat([w.detach().reshape(-1), w.new_zeros(1)])
-            self._w_packed = flat.index_select(0, self.widx).to(dtype)
+            src = w.detach()
+            if src.dtype != torch.float32 or not src.is_contiguous():
+                src = src.float().contiguous()
+            out = torch.empty(self.widx.numel(), dtype=dtype, device=src.device)
+            _count()
+            _lib.check(_lib.lib().unet3d_weight_pack(src.data_ptr(), self.widx.data_ptr(), out.data_ptr(), out.numel(),
+                                                     int(dtype == torch.float16), _stream()), "unet3d_weight_pack")
+            self._w_packed = out
             self._w_version = key
         return self._w_packed
 
@@ -163,7 +177,7 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.stats_C = stats.shape[1] if stats is not None else 0
     a.omul = pl.omul
     a.zD, a.zH, a.zW = (d - 1, h - 1, w - 1) if zero_last else (-1, -1, -1)
-    flops = 2.0 * grid[0] * grid[1] * grid[2] * grid[3] * sum(pl.in_C) * sum(pl.out_C) * pl.ks ** 3
+    flops = pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3]
     _count()
     with _Timed("conv_gemm_kernel", flops):
         _lib.check(_lib.lib().unet3d_conv_gemm(C.byref(a), _stream()), "unet3d_conv_gemm")

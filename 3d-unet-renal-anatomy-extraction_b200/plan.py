@@ -153,6 +153,7 @@ class ConvPlan:
     tab: np.ndarray                 # int32 table for the kernel
     widx: np.ndarray                # int64 gather index into cat(W.flatten(), [0])
     omul: int
+    flops_per_voxel: float = 0.0    # algorithmic FLOPs per tile-grid voxel (unpadded channels)
     nbuf: int = 2                   # TMEM accumulator buffers (1: Dt * nblk <= 512, epilogue not overlapped)
     n_tiles_w: int = 0              # number of weight tiles
     fuse_kd: bool = False           # one weight tile = the 3 d-taps of a (kh,kw), rows ordered sd = 2,1,0
@@ -196,15 +197,22 @@ def _kidx_and_valid(plan_kind: str, ks: int, stride: int, pattern: str, shift, p
 
 
 def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: Sequence[int], depth: int,
-                   grid: Optional[Tuple[int, int, int, int]] = None) -> ConvPlan:
+                   grid: Optional[Tuple[int, int, int, int]] = None, skip_k1: bool = False) -> ConvPlan:
     """kind:
          conv_fwd    Conv3d forward (weight (Cout, Cin, k,k,k)); inputs may be a concat (len(in_C) > 1)
          conv_dgrad  its data gradient; outputs may be a concat split (len(out_C) > 1)
          convT_fwd   ConvTranspose3d(k3,s2,p1) forward + zero pad plane (weight (Cin, Cout, k,k,k))
          convT_dgrad its data gradient
        in_C / out_C are the REAL channel counts of the A-side / output-side tensors of this call
-       (for a gradient, in_C is the channel count of dy).  `depth` = D extent of the tile grid."""
+       (for a gradient, in_C is the channel count of dy).  `depth` = D extent of the tile grid.
+
+       skip_k1 (conv_dgrad only): the data gradient of a whole residual block input in ONE launch,
+         dx = dgrad_conv1(dy1) + dgrad_skip_conv(g2)        (network.py:405-416: both convs read the block input)
+       A sources = [dy1, g2] (same channel count); the first uses the k3 weight with every tap, the second the k1
+       skip weight with the centre tap only.  The packed stream is gathered from cat(W_conv1.flatten(), W_skip.flatten())."""
     in_C, out_C = list(in_C), list(out_C)
+    if skip_k1:
+        assert kind == "conv_dgrad" and ks == 3 and len(in_C) == 2 and in_C[0] == in_C[1]
     in_Cp = [pad_channels(c) for c in in_C]
     out_Cp = [pad_channels(c) for c in out_C]
     if kind == "conv_fwd":
@@ -217,7 +225,7 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
         pattern, stride, ks = "direct", 2, 3
     else:
         raise ValueError(kind)
-    if (pattern == "transposed" or stride == 2) and (len(in_C) != 1 or len(out_C) != 1):
+    if (pattern == "transposed" or stride == 2) and ((len(in_C) != 1 and not skip_k1) or len(out_C) != 1):
         raise ValueError("strided / transposed convs take one input and one output")
 
     # ---- A maps and channel groups
@@ -283,6 +291,10 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
     # real channel index of every K slot: concat offset of the source tensor + channel, -1 for padding
     in_off = np.concatenate([[0], np.cumsum(in_C)]).astype(np.int64)
     Ktot, Ntot = int(sum(in_C)), int(sum(out_C))
+    skip_woff = 0
+    if skip_k1:
+        Ktot = in_C[0]
+        skip_woff = Ktot * Ntot * ks ** 3          # W_skip starts right after W_conv1 in the concatenated source
     out_real_end = np.cumsum(out_C)
 
     n_nb, n_cg = len(nb_sel), len(cg_map)
@@ -301,10 +313,27 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
             ti, par_in = maps[cg_map[cg]]
             ch = cg_ch[cg] + np.arange(G * 8, dtype=np.int64)                 # channel within the source tensor
             krow = np.where(ch < in_C[ti], in_off[ti] + ch, -1)
+            is_skip_src = skip_k1 and ti == 1
+            if skip_k1:
+                krow = np.where(ch < in_C[ti], ch, -1)                        # each source has its own weight tensor
             for t, sh0 in enumerate(shifts):
                 sub = []
                 for sd in ((2, 1, 0) if fuse_kd else (sh0[0],)):
                     sh = (sd, sh0[1], sh0[2])
+                    if is_skip_src:
+                        # k1 skip conv: centre tap only; in a fused tile the other two d-taps are structural zeros
+                        kk1 = _kidx_and_valid(kind, 1, stride, pattern, sh, par_in or (0, 0, 0), nb_ooff[nb])
+                        if kk1 is None:
+                            if fuse_kd and (sh0[1], sh0[2]) == (1, 1):
+                                sub.append(np.full((G, nblk, 8), -1, np.int64))
+                                continue
+                            sub = None
+                            break
+                        K = krow.reshape(G, 1, 8)
+                        Nn = ncol.reshape(1, nblk, 1)
+                        flat = skip_woff + (K * Ntot + Nn)                      # W_skip[cout=K][cin=N][0]
+                        sub.append(np.where((K >= 0) & (Nn >= 0), flat, -1))
+                        continue
                     kk = _kidx_and_valid(kind, ks, stride, pattern, sh, par_in or (0, 0, 0), nb_ooff[nb])
                     if kk is None:
                         sub = None
@@ -333,7 +362,10 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
         numel = Ntot * Ktot * k3
     else:
         numel = Ktot * Ntot * k3
-    widx = np.where(widx < 0, numel, widx)          # slot `numel` of cat(W.flatten(), [0]) is the zero
+    if skip_k1:
+        numel += Ktot * Ntot
+    assert numel < 2 ** 31
+    widx = widx.astype(np.int32)                    # -1 = structural zero (channel padding)
 
     tab = np.concatenate([
         np.asarray(cg_map, np.int32), np.asarray(cg_ch, np.int32),
@@ -347,7 +379,8 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
     return ConvPlan(kind=kind, ks=ks, stride=stride, pattern=pattern, in_C=in_C, in_Cp=in_Cp, out_C=out_C, out_Cp=out_Cp,
                     maps=maps, G=G, Dt=Dt, nblk=nblk, cg_map=cg_map, cg_ch=cg_ch, shifts=shifts, nb_sel=nb_sel,
                     nb_coff=nb_coff, nb_ooff=nb_ooff, nb_real0=nb_real0, masks=masks, wbase=wbase, tab=tab, widx=widx,
-                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles, fuse_kd=fuse_kd, nbuf=nbuf)
+                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles, fuse_kd=fuse_kd, nbuf=nbuf,
+                    flops_per_voxel=(2.0 * in_C[0] * sum(out_C) * (k3 + 1)) if skip_k1 else 2.0 * sum(in_C) * sum(out_C) * k3)
 
 
 def bias_vector(plan: ConvPlan, bias: np.ndarray) -> np.ndarray:

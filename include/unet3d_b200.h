@@ -75,6 +75,10 @@ typedef struct unet3d_conv_args {
 int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream);
 size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse);
 
+/* Pack an fp32 parameter (PyTorch layout) into the 16-bit tile stream unet3d_conv_gemm consumes:
+ * out[i] = idx[i] < 0 ? 0 : w[idx[i]]; idx (device int32, n elements, n % 8 == 0 preferred) comes from the host plan. */
+int unet3d_weight_pack(const float* w, const int* idx, void* out, long long n, int out_f16, void* stream);
+
 /* Weight gradient on tcgen05 tensor cores (wgrad_gemm.cu): dW[tap][cin][cout] = sum_v x[v+tap][cin] dy[v][cout].
  * Replaces the cuDNN backward-filter dispatch of the layers listed above. */
 typedef struct unet3d_wgrad_args {

@@ -10,8 +10,8 @@ import torch
 
 
 def pack_weights(plan, w: torch.Tensor) -> torch.Tensor:
-    flat = torch.cat([w.reshape(-1).float(), torch.zeros(1)])
-    return flat[torch.from_numpy(plan.widx)]
+    flat = torch.cat([w.reshape(-1).float(), torch.zeros(1)])          # index -1 (structural zero) -> the last slot
+    return flat[torch.from_numpy(plan.widx.astype(np.int64))]
 
 
 def run_conv_plan(plan, inputs, wpacked, grid, out_dims, bias_vec=None, zero_last=False):

@@ -124,3 +124,27 @@ def test_wgrad_plans(kind, ks, stride, cins, cout):
     dw = run_wgrad_plan(plan, xs, dyn, (N, D, H, W))
     got = dw[torch.from_numpy(plan.gidx)].reshape(w.shape).float()
     assert torch.allclose(got, w.grad, atol=1e-3, rtol=1e-3), (got - w.grad).abs().max()
+
+
+@pytest.mark.parametrize("cins,cout,stride", [([30], 60, 1), ([30, 30], 30, 1), ([30], 60, 2), ([120, 120], 120, 1)])
+def test_block_input_gradient_in_one_launch(cins, cout, stride):
+    """dx = dgrad_conv1(dy1) + dgrad_skip_conv(g2) as one plan with two A sources (skip_k1)."""
+    N, D, H, W = 1, 4, 6, 8
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, sum(cins), D, H, W, generator=g).requires_grad_(True)
+    w1 = torch.randn(cout, sum(cins), 3, 3, 3, generator=g) * 0.1
+    ws = torch.randn(cout, sum(cins), 1, 1, 1, generator=g) * 0.1
+    y1 = F.conv3d(x, w1, None, stride=stride, padding=1)
+    s = F.conv3d(x, ws, None, stride=stride)
+    dy1, g2 = torch.randn(y1.shape, generator=g), torch.randn(s.shape, generator=g)
+    (y1 * dy1).sum().backward(retain_graph=True)
+    (s * g2).sum().backward()
+    grid = (N, D // stride, H // stride, W // stride)
+    plan = P.make_conv_plan("conv_dgrad", 3, stride, [cout, cout], cins, grid[1], grid, skip_k1=True)
+    wp = pack_weights(plan, torch.cat([w1.reshape(-1), ws.reshape(-1)]))
+    cp = P.pad_channels(cout)
+    outs = run_conv_plan(plan, [to_ndhwc(dy1, cp), to_ndhwc(g2, cp)], wp, grid, (D, H, W))
+    off = 0
+    for o, c in zip(outs, cins):
+        assert torch.allclose(from_ndhwc(o, c), x.grad[:, off:off + c], atol=1e-4, rtol=1e-4)
+        off += c

@@ -83,7 +83,9 @@ const char* unet3d_version(void) { return "unet3d_b200 0.1 (sm_100a)"; }
 const char* unet3d_last_error_string(void) { return g_err; }
 int unet3d_num_sms(void) { return num_sms(); }
 
-size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse) { return conv_gemm_smem_bytes(Dt, G, nblk, fuse); }
+size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages) {
+  return conv_gemm_smem_bytes(Dt, G, nblk, fuse, wT, w_stages);
+}
 
 int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
   if (!a || a->n_src < 1 || a->n_src > CG_MAX_MAPS || !a->tab || !a->w || !a->out || !a->err)
@@ -114,6 +116,8 @@ int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
   p.n_nblk = a->n_nblk; p.nblk = a->nblk; p.G = a->G; p.n_cg = a->n_cg; p.n_taps = a->n_taps;
   p.fuse = a->fuse;
   p.nbuf = a->nbuf;
+  p.wT = a->wT;
+  p.w_stages = a->w_stages;
   p.in_f16 = a->in_f16;
   p.out_f16 = a->out_f16;
   p.out_sN = a->out_sN; p.out_sD = a->out_sD; p.out_sH = a->out_sH; p.out_sW = a->out_sW;

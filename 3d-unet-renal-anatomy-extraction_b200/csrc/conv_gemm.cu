@@ -87,11 +87,30 @@ __device__ __forceinline__ void issue_tap(uint32_t acc0, uint64_t adesc0, uint64
   }
 }
 
+// One weight-ring stage = a batch of taps (their tiles are contiguous in the packed stream): one barrier wait, one
+// dispatch on (planes, K steps) and one commit per batch instead of per tap.  `mask` holds the taps of the batch.
+template <int DT, int G2, int FUSE>
+__device__ __forceinline__ void issue_batch(uint32_t mask, int cnt, const uint32_t* tap_off, uint32_t slab, uint32_t wst_addr,
+                                         uint32_t wtile_bytes, uint32_t b_lbo, uint32_t acc0, uint32_t idesc1,
+                                         uint32_t idesc2, uint32_t idesc3, uint32_t nblk, uint32_t accum) {
+  for (int i = 0; i < cnt; ++i) {
+    const int tap = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const uint64_t adesc0 = umma_desc(slab + tap_off[tap], CG_CHUNK_PITCH, CG_WB * 16);
+    const uint64_t bdesc0 = umma_desc(wst_addr + (uint32_t)i * wtile_bytes, b_lbo, 128);
+    issue_tap<DT, G2, FUSE>(acc0, adesc0, bdesc0, idesc1, idesc2, idesc3, nblk, accum);
+    accum = 1;
+  }
+}
+
 template <int FUSE>
-__device__ __forceinline__ void issue_tap_dispatch(int Dt, int G2, uint32_t acc0, uint64_t a, uint64_t b, uint32_t i1,
-                                                   uint32_t i2, uint32_t i3, uint32_t nblk, uint32_t accum) {
-#define U3D_CASE(DT, GG) \
-  if (Dt == DT && G2 == GG) return issue_tap<DT, GG, FUSE>(acc0, a, b, i1, i2, i3, nblk, accum);
+__device__ __forceinline__ void issue_batch_dispatch(int Dt, int G2, uint32_t mask, int cnt, const uint32_t* tap_off,
+                                                     uint32_t slab, uint32_t wst_addr, uint32_t wtile_bytes, uint32_t b_lbo,
+                                                     uint32_t acc0, uint32_t i1, uint32_t i2, uint32_t i3, uint32_t nblk,
+                                                     uint32_t accum) {
+#define U3D_CASE(DT, GG)          \
+  if (Dt == DT && G2 == GG)       \
+    return issue_batch<DT, GG, FUSE>(mask, cnt, tap_off, slab, wst_addr, wtile_bytes, b_lbo, acc0, i1, i2, i3, nblk, accum);
   U3D_CASE(8, 1) U3D_CASE(8, 2) U3D_CASE(4, 1) U3D_CASE(4, 2) U3D_CASE(4, 3) U3D_CASE(2, 1) U3D_CASE(2, 2) U3D_CASE(2, 3)
   U3D_CASE(1, 1) U3D_CASE(1, 2) U3D_CASE(1, 3) U3D_CASE(8, 3)
 #undef U3D_CASE
@@ -110,6 +129,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   const uint32_t plane_pitch = (uint32_t)p.G * CG_CHUNK_PITCH;
   const uint32_t slab_bytes = (uint32_t)planes * plane_pitch;
   const uint32_t wtile_bytes = (uint32_t)p.G * p.fuse * p.nblk * 16;
+  const int wT = p.wT;                                   // taps per weight-ring stage
+  const uint32_t w_stages = (uint32_t)p.w_stages;
+  const uint32_t wstage_bytes = (uint32_t)wT * wtile_bytes;
   const uint32_t slab0 = smem_u32(smem) + 1024;
   const uint32_t wring0 = slab0 + 2 * slab_bytes;
 
@@ -197,18 +219,19 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
       const int nb = item / n_tiles;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)__ldg(&tab_wbase[nb]) * wtile_bytes;
       for (int cg = 0; cg < n_cg && ok; ++cg) {
-        uint32_t mask = (uint32_t)__ldg(&tab_mask[nb * n_cg + cg]);
-        while (mask) {
-          mask &= mask - 1;
-          const uint32_t st = w_it % CG_W_STAGES, ph = (w_it / CG_W_STAGES) & 1;
+        int left = __popc((uint32_t)__ldg(&tab_mask[nb * n_cg + cg]));
+        while (left > 0) {
+          const int cnt = left < wT ? left : wT;
+          left -= cnt;
+          const uint32_t st = w_it % w_stages, ph = (w_it / w_stages) & 1;
           if (!mbar_wait(smem_u32(&ctl->w_empty[st]), ph ^ 1, abort_flag, p.err, 102)) { ok = false; break; }
           if (elect_one()) {
             const uint32_t full = smem_u32(&ctl->w_full[st]);
-            mbar_expect_tx(full, wtile_bytes);
-            bulk_load(wring0 + st * wtile_bytes, src, wtile_bytes, full);
+            mbar_expect_tx(full, (uint32_t)cnt * wtile_bytes);
+            bulk_load(wring0 + st * wstage_bytes, src, (uint32_t)cnt * wtile_bytes, full);
           }
           __syncwarp();
-          src += wtile_bytes;
+          src += (size_t)cnt * wtile_bytes;
           ++w_it;
         }
       }
@@ -239,18 +262,21 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
         tc_fence_after();
         const uint32_t slab = slab0 + ast * slab_bytes;
         while (mask) {
-          const int tap = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const uint32_t wst = w_it % CG_W_STAGES, wph = (w_it / CG_W_STAGES) & 1;
+          const int left = __popc(mask);
+          const int cnt = left < wT ? left : wT;
+          uint32_t batch = mask;                       // the `cnt` lowest set bits
+          for (int i = 0; i < cnt; ++i) mask &= mask - 1;
+          batch &= ~mask;
+          const uint32_t wst = w_it % w_stages, wph = (w_it / w_stages) & 1;
           if (!mbar_wait(smem_u32(&ctl->w_full[wst]), wph, abort_flag, p.err, 105)) { ok = false; break; }
           tc_fence_after();
-          const uint64_t adesc0 = umma_desc(slab + tap_off[tap], CG_CHUNK_PITCH, CG_WB * 16);
-          const uint64_t bdesc0 = umma_desc(wring0 + wst * wtile_bytes, b_lbo, 128);
           if (elect_one()) {
             if (fuse == 1)
-              issue_tap_dispatch<1>(Dt, G2, acc0, adesc0, bdesc0, idesc, idesc2, idesc3, (uint32_t)nblk, accum);
+              issue_batch_dispatch<1>(Dt, G2, batch, cnt, tap_off, slab, wring0 + wst * wstage_bytes, wtile_bytes, b_lbo, acc0,
+                                      idesc, idesc2, idesc3, (uint32_t)nblk, accum);
             else
-              issue_tap_dispatch<3>(Dt, G2, acc0, adesc0, bdesc0, idesc, idesc2, idesc3, (uint32_t)nblk, accum);
+              issue_batch_dispatch<3>(Dt, G2, batch, cnt, tap_off, slab, wring0 + wst * wstage_bytes, wtile_bytes, b_lbo, acc0,
+                                      idesc, idesc2, idesc3, (uint32_t)nblk, accum);
             tc_commit(smem_u32(&ctl->w_empty[wst]));
           }
           __syncwarp();
@@ -394,9 +420,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
 
 }  // namespace
 
-size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse) {
+size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages) {
   return 1024 /*align slack*/ + 1024 /*ctl*/ + 2 * (size_t)(Dt + 2) * G * CG_CHUNK_PITCH +
-         (size_t)CG_W_STAGES * G * fuse * nblk * 16;
+         (size_t)w_stages * wT * G * fuse * nblk * 16;
 }
 
 int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
@@ -404,7 +430,8 @@ int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
       p.Dt * p.nblk * p.nbuf > 512 ||
       p.n_taps < 1 || p.n_taps > 32 || p.n_work < 1 || (p.Dt != 1 && p.Dt != 2 && p.Dt != 4 && p.Dt != 8) || p.G > 6 || (p.fuse != 1 && p.fuse != 3) || p.fuse * p.nblk > 256)
     return U3D_ERR_INVALID;
-  const size_t smem = conv_gemm_smem_bytes(p.Dt, p.G, p.nblk, p.fuse);
+  if (p.wT < 1 || p.wT > 32 || p.w_stages < 2 || p.w_stages > CG_W_STAGES) return U3D_ERR_INVALID;
+  const size_t smem = conv_gemm_smem_bytes(p.Dt, p.G, p.nblk, p.fuse, p.wT, p.w_stages);
   if (smem > 227 * 1024) return U3D_ERR_INVALID;
   static bool attr_set = false;
   if (!attr_set) {

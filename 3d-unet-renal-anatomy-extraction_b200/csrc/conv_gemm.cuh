@@ -49,6 +49,7 @@ struct ConvGemmParams {
   int n_nblk, nblk;       // nblk in {32, 64, 96, 128}; Dt * nblk <= 256
   int G, n_cg, n_taps;    // G chunks (of 8 channels) per cgroup, G even
   int in_f16, out_f16;    // 16-bit storage of A / weights and of out / addend: 0 = bf16, 1 = fp16
+  int wT, w_stages;       // weight ring: taps per stage (their tiles are contiguous) and ring depth (2..6)
   int nbuf;               // TMEM accumulator buffers: 2 (Dt*nblk <= 256, epilogue overlaps next item) or 1 (<= 512)
   int fuse;               // 1, or 3: a weight tile holds the d-taps 2,1,0 of one (kh,kw) and taps carry sd = 0
   long long out_sN, out_sD, out_sH, out_sW;   // element strides of out / addend
@@ -59,7 +60,7 @@ struct ConvGemmParams {
   int n_work;
 };
 
-size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse);
+size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages);
 int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 
 }  // namespace u3d

@@ -170,6 +170,7 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.Dt, a.n_nblk, a.nblk, a.G, a.n_cg, a.n_taps = pl.Dt, pl.n_nblk, pl.nblk, pl.G, pl.n_cg, len(pl.shifts)
     a.fuse = 3 if pl.fuse_kd else 1
     a.nbuf = pl.nbuf
+    a.wT, a.w_stages = pl.wT, pl.w_stages
     a.in_f16, a.out_f16 = _f16(inputs[0]), _f16(o0)
     n, d, h, w, cp = o0.shape
     a.out_sW, a.out_sH, a.out_sD, a.out_sN = cp, w * cp, h * w * cp, d * h * w * cp

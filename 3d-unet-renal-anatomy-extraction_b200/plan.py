@@ -32,8 +32,19 @@ def pad_channels(c: int) -> int:
     return (c + 15) // 16 * 16
 
 
-def conv_smem_bytes(dt: int, g: int, nblk: int, fuse: int = 1) -> int:
-    return 2048 + 2 * (dt + 2) * g * CHUNK_PITCH + W_STAGES * g * fuse * nblk * 16
+def weight_ring(g: int, nblk: int, fuse: int, n_taps: int = 27) -> Tuple[int, int]:
+    """(taps per stage, stages) of the weight ring: batch small tiles up to ~28 KB per stage (one barrier round trip
+    and one issue dispatch per batch), keep the ring within ~56 KB."""
+    tile = g * fuse * nblk * 16
+    taps = max(1, -(-n_taps // fuse))
+    wt = max(1, min(taps, 16, 28672 // tile))
+    stages = max(2, min(W_STAGES, 57344 // (wt * tile)))
+    return wt, stages
+
+
+def conv_smem_bytes(dt: int, g: int, nblk: int, fuse: int = 1, n_taps: int = 27) -> int:
+    wt, stages = weight_ring(g, nblk, fuse, n_taps)
+    return 2048 + 2 * (dt + 2) * g * CHUNK_PITCH + stages * wt * g * fuse * nblk * 16
 
 
 def choose_nblk(cp_out: int) -> Tuple[int, int]:
@@ -154,6 +165,8 @@ class ConvPlan:
     widx: np.ndarray                # int64 gather index into cat(W.flatten(), [0])
     omul: int
     flops_per_voxel: float = 0.0    # algorithmic FLOPs per tile-grid voxel (unpadded channels)
+    wT: int = 1                     # taps per weight-ring stage
+    w_stages: int = 6               # weight-ring depth
     nbuf: int = 2                   # TMEM accumulator buffers (1: Dt * nblk <= 512, epilogue not overlapped)
     n_tiles_w: int = 0              # number of weight tiles
     fuse_kd: bool = False           # one weight tile = the 3 d-taps of a (kh,kw), rows ordered sd = 2,1,0
@@ -367,6 +380,8 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
     assert numel < 2 ** 31
     widx = widx.astype(np.int32)                    # -1 = structural zero (channel padding)
 
+    ring = weight_ring(G, nblk, 3 if fuse_kd else 1, 27 if ks == 3 else 1)
+    assert conv_smem_bytes(Dt, G, nblk, 3 if fuse_kd else 1, 27 if ks == 3 else 1) <= SMEM_LIMIT
     tab = np.concatenate([
         np.asarray(cg_map, np.int32), np.asarray(cg_ch, np.int32),
         np.asarray([s[0] | (s[1] << 8) | (s[2] << 16) for s in shifts], np.int32),
@@ -379,7 +394,7 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
     return ConvPlan(kind=kind, ks=ks, stride=stride, pattern=pattern, in_C=in_C, in_Cp=in_Cp, out_C=out_C, out_Cp=out_Cp,
                     maps=maps, G=G, Dt=Dt, nblk=nblk, cg_map=cg_map, cg_ch=cg_ch, shifts=shifts, nb_sel=nb_sel,
                     nb_coff=nb_coff, nb_ooff=nb_ooff, nb_real0=nb_real0, masks=masks, wbase=wbase, tab=tab, widx=widx,
-                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles, fuse_kd=fuse_kd, nbuf=nbuf,
+                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles, fuse_kd=fuse_kd, nbuf=nbuf, wT=ring[0], w_stages=ring[1],
                     flops_per_voxel=(2.0 * in_C[0] * sum(out_C) * (k3 + 1)) if skip_k1 else 2.0 * sum(in_C) * sum(out_C) * k3)
 
 

@@ -67,13 +67,13 @@ typedef struct unet3d_conv_args {
   double* stats;         /* fp64 [N][stats_C][2] running (sum, sum^2) for InstanceNorm, or NULL */
   int* err;              /* device int32 error word (0 = ok) */
   int N, D, H, W;        /* tile-grid extents */
-  int Dt, n_nblk, nblk, G, n_cg, n_taps, fuse, nbuf;
+  int Dt, n_nblk, nblk, G, n_cg, n_taps, fuse, nbuf, wT, w_stages;
   int in_f16, out_f16;   /* 16-bit format of A + weights / of out + addend: 0 = bf16, 1 = fp16 */
   long long out_sN, out_sD, out_sH, out_sW;   /* ELEMENT strides of out/addend */
   int out_C, stats_C, omul, zD, zH, zW;
 } unet3d_conv_args;
 int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream);
-size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse);
+size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages);
 
 /* Pack an fp32 parameter (PyTorch layout) into the 16-bit tile stream unet3d_conv_gemm consumes:
  * out[i] = idx[i] < 0 ? 0 : w[idx[i]]; idx (device int32, n elements, n % 8 == 0 preferred) comes from the host plan. */

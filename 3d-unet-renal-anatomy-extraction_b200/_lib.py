@@ -27,7 +27,7 @@ class ConvArgs(C.Structure):
                 ("n_taps", C.c_int), ("fuse", C.c_int), ("nbuf", C.c_int), ("wT", C.c_int), ("w_stages", C.c_int), ("in_f16", C.c_int), ("out_f16", C.c_int),
                 ("out_sN", C.c_longlong), ("out_sD", C.c_longlong), ("out_sH", C.c_longlong), ("out_sW", C.c_longlong),
                 ("out_C", C.c_int), ("stats_C", C.c_int), ("omul", C.c_int), ("zD", C.c_int), ("zH", C.c_int),
-                ("zW", C.c_int)]
+                ("zW", C.c_int), ("act", C.c_int)]
 
 
 class WgradArgs(C.Structure):
@@ -59,6 +59,11 @@ _SIGS = {
     "unet3d_loss_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_int, C.c_void_p]),
     "unet3d_sw_accumulate": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 10 + [C.c_void_p]),
     "unet3d_sw_finalize": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_longlong, C.c_void_p]),
+    "unet3d_att_gate_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "unet3d_att_gate_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "unet3d_att_mid_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "unet3d_maxpool3d_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
+    "unet3d_maxpool3d_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
 }
 
 _lib = None

@@ -123,6 +123,7 @@ int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
   p.out_sN = a->out_sN; p.out_sD = a->out_sD; p.out_sH = a->out_sH; p.out_sW = a->out_sW;
   p.out_C = a->out_C; p.stats_C = a->stats_C; p.omul = a->omul;
   p.zD = a->zD; p.zH = a->zH; p.zW = a->zW;
+  p.act = a->act;
   p.n_work = a->n_nblk * a->N * p.segs_d * p.tiles_h * p.tiles_w;
   return check(conv_gemm_launch(p, sms, reinterpret_cast<cudaStream_t>(stream)), "conv_gemm");
 }
@@ -216,6 +217,32 @@ int unet3d_sw_accumulate(const float* logits, const float* window, float* result
 int unet3d_sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K,
                        long long XYZ, void* stream) {
   return check(sw_finalize(result, weight, labels, probs, K, XYZ, num_sms(), (cudaStream_t)stream), "sw_finalize");
+}
+int unet3d_maxpool3d_fwd(const void* x, void* out, uint8_t* code, int N, int D, int H, int W, int Cp, int act_f16,
+                         void* stream) {
+  return check(maxpool_fwd((const bf16*)x, (bf16*)out, code, N, D, H, W, Cp, act_f16, num_sms(), (cudaStream_t)stream),
+               "maxpool3d_fwd");
+}
+int unet3d_maxpool3d_bwd(const void* dout, const uint8_t* code, void* dx, int N, int D, int H, int W, int Cp,
+                         void* stream) {
+  return check(maxpool_bwd((const bf16*)dout, code, (bf16*)dx, N, D, H, W, Cp, num_sms(), (cudaStream_t)stream),
+               "maxpool3d_bwd");
+}
+int unet3d_att_gate_fwd(const void* xs, const void* z, void* out, long long n_elem, int act_f16, void* stream) {
+  return check(att_gate_fwd((const bf16*)xs, (const bf16*)z, (bf16*)out, n_elem, act_f16, num_sms(), (cudaStream_t)stream),
+               "att_gate_fwd");
+}
+int unet3d_att_gate_bwd(const void* dout, const void* xs, const void* z, void* dxs, void* dz, double* sums, long long NV,
+                        int Cp, int act_f16, void* stream) {
+  return check(att_gate_bwd((const bf16*)dout, (const bf16*)xs, (const bf16*)z, (bf16*)dxs, (bf16*)dz, sums, NV, Cp, act_f16,
+                            num_sms(), (cudaStream_t)stream),
+               "att_gate_bwd");
+}
+int unet3d_att_mid_bwd(const void* df, const void* f, const void* dxs, void* dpre, void* t, double* sum, long long NV,
+                       int Cp, int act_f16, void* stream) {
+  return check(att_mid_bwd((const bf16*)df, (const bf16*)f, (const bf16*)dxs, (bf16*)dpre, (bf16*)t, sum, NV, Cp, act_f16,
+                           num_sms(), (cudaStream_t)stream),
+               "att_mid_bwd");
 }
 
 }  // extern "C"

@@ -375,6 +375,10 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
               }
             }
           }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
+          }
           if (!valid || zero) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;

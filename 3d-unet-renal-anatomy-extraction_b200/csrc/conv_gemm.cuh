@@ -57,6 +57,7 @@ struct ConvGemmParams {
   int stats_C;
   int omul;               // output coordinate = tile-grid coordinate * omul + offset(nblock)
   int zD, zH, zW;         // output planes forced to zero (ConvTranspose3d + ConstantPad3d), or -1
+  int act;                // 0 none, 1 LeakyReLU(0.01) applied after bias / addend
   int n_work;
 };
 

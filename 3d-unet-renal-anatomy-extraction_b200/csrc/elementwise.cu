@@ -699,6 +699,190 @@ inline int grid_for(long long work_items, int per_block, int num_sms, int waves)
   return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// MaxPoolBlock: nn.MaxPool3d(kernel_size=2, stride=2) (network.py:452-463) on 16-bit NDHWC.
+// One thread = one output voxel x 8 channels.  The window is scanned in PyTorch's order (kd, kh, kw)
+// with `v > best || isnan(v)`, so the first maximum wins and a NaN propagates; the winner is kept as
+// a 3-bit code kd*4 + kh*2 + kw (PyTorch's flat index = ((2d+kd)*H + 2h+kh)*W + 2w+kw).
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, uint2* __restrict__ code,
+                                   int chunks, int Do, int Ho, int Wo, long long total /* N*Do*Ho*Wo */, int af) {
+  const int ch = threadIdx.x;
+  const int H = 2 * Ho, W = 2 * Wo;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < total; v += (long long)gridDim.x * blockDim.y) {
+    const int w = (int)(v % Wo);
+    long long t = v / Wo;
+    const int h = (int)(t % Ho);
+    t /= Ho;
+    const int d = (int)(t % Do);
+    const long long n = t / Do;
+    const size_t in0 = ((((size_t)n * 2 * Do + 2 * d) * H + 2 * h) * W + 2 * w) * chunks + ch;
+    float best[8];
+    unsigned arg[8];
+    uint4 raw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      raw[k] = ld_stream(x + in0 + ((size_t)(k >> 2) * H * W + (size_t)((k >> 1) & 1) * W + (k & 1)) * chunks);
+    unpack8(raw[0], best, af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) arg[j] = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      float f[8];
+      unpack8(raw[k], f, af);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (f[j] > best[j] || f[j] != f[j]) {
+          best[j] = f[j];
+          arg[j] = k;
+        }
+    }
+    out[(size_t)v * chunks + ch] = pack8(best, af);
+    uint2 c;
+    c.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+    c.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+    code[(size_t)v * chunks + ch] = c;
+  }
+}
+
+// dx[window position == code] = dout, 0 elsewhere (windows do not overlap: every input voxel is written once).
+__global__ void maxpool_bwd_kernel(const uint4* __restrict__ dout, const uint2* __restrict__ code, uint4* __restrict__ dx,
+                                   int chunks, int Do, int Ho, int Wo, long long total) {
+  const int ch = threadIdx.x;
+  const int H = 2 * Ho, W = 2 * Wo;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < total; v += (long long)gridDim.x * blockDim.y) {
+    const int w = (int)(v % Wo);
+    long long t = v / Wo;
+    const int h = (int)(t % Ho);
+    t /= Ho;
+    const int d = (int)(t % Do);
+    const long long n = t / Do;
+    const size_t in0 = ((((size_t)n * 2 * Do + 2 * d) * H + 2 * h) * W + 2 * w) * chunks + ch;
+    const uint4 g = ld_stream(dout + (size_t)v * chunks + ch);
+    const uint2 c = code[(size_t)v * chunks + ch];
+    const unsigned gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      unsigned o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned cw = q < 2 ? c.x : c.y;
+        const unsigned a0 = (cw >> ((q & 1) * 16)) & 0xffu, a1 = (cw >> ((q & 1) * 16 + 8)) & 0xffu;
+        o[q] = (a0 == (unsigned)k ? (gw[q] & 0xffffu) : 0u) | (a1 == (unsigned)k ? (gw[q] & 0xffff0000u) : 0u);
+      }
+      dx[in0 + ((size_t)(k >> 2) * H * W + (size_t)((k >> 1) & 1) * W + (k & 1)) * chunks] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// AttBlock (network.py:353-371): out = xs * sigmoid(z) with xs = conv(skip), z = conv(lrelu(conv(skip)+conv(gate)))
+// (the three 1x1x1 convs run on the tensor-core kernel; these are the gate's pointwise parts).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void att_gate_fwd_kernel(const uint4* __restrict__ xs, const uint4* __restrict__ z, uint4* __restrict__ out,
+                                    long long n16, int af) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    unpack8(ld_stream(xs + i), a, af);
+    unpack8(ld_stream(z + i), b, af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= sigmoidf_(b[j]);
+    out[i] = pack8(a, af);
+  }
+}
+
+// dxs = dout * r, dz = dout * xs * r (1 - r), r = sigmoid(z); sums[c] = {sum dxs, sum dz} over (n, voxels)
+__global__ void att_gate_bwd_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ xs, const uint4* __restrict__ z,
+                                    uint4* __restrict__ dxs, uint4* __restrict__ dz, double* __restrict__ sums,
+                                    int chunks, long long NV, int af) {
+  extern __shared__ float red[];   // [blockDim.y][chunks*8][2]
+  const int ch = threadIdx.x;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < NV; v += (long long)gridDim.x * blockDim.y) {
+    const size_t idx = (size_t)v * chunks + ch;
+    float d[8], a[8], b[8], e[8];
+    unpack8(ld_stream(dout + idx), d, af);
+    unpack8(ld_stream(xs + idx), a, af);
+    unpack8(ld_stream(z + idx), b, af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float r = sigmoidf_(b[j]);
+      e[j] = d[j] * a[j] * r * (1.f - r);
+      d[j] = d[j] * r;
+    }
+    const uint4 o1 = pack8(d, af), o2 = pack8(e, af);
+    dxs[idx] = o1;
+    dz[idx] = o2;
+    unpack8(o1, d, af);
+    unpack8(o2, e, af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += d[j];
+      s2[j] += e[j];
+    }
+  }
+  const int C8 = chunks * 8;
+  float* my = red + ((size_t)threadIdx.y * C8 + ch * 8) * 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    my[2 * j] = s1[j];
+    my[2 * j + 1] = s2[j];
+  }
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < C8 * 2; i += blockDim.x * blockDim.y) {
+    float acc = 0.f;
+    for (int r = 0; r < (int)blockDim.y; ++r) acc += red[(size_t)r * C8 * 2 + i];
+    atomicAdd(&sums[i], (double)acc);
+  }
+}
+
+// dpre = df * lrelu'(f); t = dxs + dpre; sum[c] = sum dpre over (n, voxels)
+__global__ void att_mid_bwd_kernel(const uint4* __restrict__ df, const uint4* __restrict__ f, const uint4* __restrict__ dxs,
+                                   uint4* __restrict__ dpre, uint4* __restrict__ t, double* __restrict__ sum,
+                                   int chunks, long long NV, int af) {
+  extern __shared__ float red[];   // [blockDim.y][chunks*8]
+  const int ch = threadIdx.x;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < NV; v += (long long)gridDim.x * blockDim.y) {
+    const size_t idx = (size_t)v * chunks + ch;
+    float d[8], a[8], x[8];
+    unpack8(ld_stream(df + idx), d, af);
+    unpack8(ld_stream(f + idx), a, af);
+    unpack8(ld_stream(dxs + idx), x, af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = a[j] > 0.f ? d[j] : LRELU * d[j];
+    const uint4 o = pack8(d, af);
+    dpre[idx] = o;
+    unpack8(o, d, af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] += d[j];
+      x[j] += d[j];
+    }
+    t[idx] = pack8(x, af);
+  }
+  const int C8 = chunks * 8;
+  float* my = red + (size_t)threadIdx.y * C8 + ch * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) my[j] = acc[j];
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < C8; i += blockDim.x * blockDim.y) {
+    float a = 0.f;
+    for (int r = 0; r < (int)blockDim.y; ++r) a += red[(size_t)r * C8 + i];
+    atomicAdd(&sum[i], (double)a);
+  }
+}
+
 }  // namespace
 
 // ----------------------------------- launchers ---------------------------------------------------
@@ -861,6 +1045,58 @@ int sw_finalize(const float* result, const float* weight, uint8_t* labels, float
   if (K < 1 || K > 8) return U3D_ERR_UNSUPPORTED;
   const int g = grid_for(XYZ, 256 * 2, num_sms, 8);
   sw_finalize_kernel<8><<<g, 256, 0, s>>>(result, weight, labels, probs, K, XYZ);
+  return U3D_CHECK_LAUNCH();
+}
+
+int maxpool_fwd(const bf16* x, bf16* out, uint8_t* code, int N, int D, int H, int W, int Cp, int af, int num_sms,
+                cudaStream_t s) {
+  if (Cp % 8 || Cp / 8 > 256 || (D | H | W) & 1 || N < 1) return U3D_ERR_INVALID;
+  const int chunks = Cp / 8;
+  const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2);
+  dim3 blk = cv_block(chunks);
+  const int g = grid_for(total, blk.y * 2, num_sms, 8);
+  maxpool_fwd_kernel<<<g, blk, 0, s>>>((const uint4*)x, (uint4*)out, (uint2*)code, chunks, D / 2, H / 2, W / 2, total, af);
+  return U3D_CHECK_LAUNCH();
+}
+
+int maxpool_bwd(const bf16* dout, const uint8_t* code, bf16* dx, int N, int D, int H, int W, int Cp, int num_sms,
+                cudaStream_t s) {
+  if (Cp % 8 || Cp / 8 > 256 || (D | H | W) & 1 || N < 1) return U3D_ERR_INVALID;
+  const int chunks = Cp / 8;
+  const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2);
+  dim3 blk = cv_block(chunks);
+  const int g = grid_for(total, blk.y * 2, num_sms, 8);
+  maxpool_bwd_kernel<<<g, blk, 0, s>>>((const uint4*)dout, (const uint2*)code, (uint4*)dx, chunks, D / 2, H / 2, W / 2, total);
+  return U3D_CHECK_LAUNCH();
+}
+
+int att_gate_fwd(const bf16* xs, const bf16* z, bf16* out, long long n_elem, int af, int num_sms, cudaStream_t s) {
+  if (n_elem <= 0 || n_elem % 8) return U3D_ERR_INVALID;
+  const long long n16 = n_elem / 8;
+  const int g = grid_for(n16, 256 * 2, num_sms, 16);
+  att_gate_fwd_kernel<<<g, 256, 0, s>>>((const uint4*)xs, (const uint4*)z, (uint4*)out, n16, af);
+  return U3D_CHECK_LAUNCH();
+}
+
+int att_gate_bwd(const bf16* dout, const bf16* xs, const bf16* z, bf16* dxs, bf16* dz, double* sums, long long NV, int Cp,
+                 int af, int num_sms, cudaStream_t s) {
+  if (Cp % 8 || Cp / 8 > 256 || NV <= 0) return U3D_ERR_INVALID;
+  const int chunks = Cp / 8;
+  dim3 blk = cv_block(chunks);
+  const int g = grid_for(NV, blk.y * 8, num_sms, 8);
+  att_gate_bwd_kernel<<<g, blk, (size_t)blk.y * Cp * 2 * sizeof(float), s>>>(
+      (const uint4*)dout, (const uint4*)xs, (const uint4*)z, (uint4*)dxs, (uint4*)dz, sums, chunks, NV, af);
+  return U3D_CHECK_LAUNCH();
+}
+
+int att_mid_bwd(const bf16* df, const bf16* f, const bf16* dxs, bf16* dpre, bf16* t, double* sum, long long NV, int Cp,
+                int af, int num_sms, cudaStream_t s) {
+  if (Cp % 8 || Cp / 8 > 256 || NV <= 0) return U3D_ERR_INVALID;
+  const int chunks = Cp / 8;
+  dim3 blk = cv_block(chunks);
+  const int g = grid_for(NV, blk.y * 8, num_sms, 8);
+  att_mid_bwd_kernel<<<g, blk, (size_t)blk.y * Cp * sizeof(float), s>>>(
+      (const uint4*)df, (const uint4*)f, (const uint4*)dxs, (uint4*)dpre, (uint4*)t, sum, chunks, NV, af);
   return U3D_CHECK_LAUNCH();
 }
 

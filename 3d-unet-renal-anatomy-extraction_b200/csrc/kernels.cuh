@@ -29,5 +29,14 @@ int sw_accumulate(const float* logits, const float* window, float* result, float
                   int x0, int y0, int z0, int X, int Y, int Z, int num_sms, cudaStream_t s);
 int sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K, long long XYZ,
                 int num_sms, cudaStream_t s);
+int maxpool_fwd(const bf16* x, bf16* out, uint8_t* code, int N, int D, int H, int W, int Cp, int af, int num_sms,
+                cudaStream_t s);
+int maxpool_bwd(const bf16* dout, const uint8_t* code, bf16* dx, int N, int D, int H, int W, int Cp, int num_sms,
+                cudaStream_t s);
+int att_gate_fwd(const bf16* xs, const bf16* z, bf16* out, long long n_elem, int af, int num_sms, cudaStream_t s);
+int att_gate_bwd(const bf16* dout, const bf16* xs, const bf16* z, bf16* dxs, bf16* dz, double* sums, long long NV, int Cp,
+                 int af, int num_sms, cudaStream_t s);
+int att_mid_bwd(const bf16* df, const bf16* f, const bf16* dxs, bf16* dpre, bf16* t, double* sum, long long NV, int Cp,
+                int af, int num_sms, cudaStream_t s);
 
 }  // namespace u3d

@@ -1,16 +1,20 @@
-"""Forward / backward executor of the residual 3D U-Net on the library's sm_100a kernels.
+"""Forward / backward executor of the 3D U-Net family on the library's sm_100a kernels.
 
-Walks the module tree of :class:`network.ResUnet3D` in the order of the reference's
-``Unet.forward`` (network.py:549-565) and ``ResBlock.forward`` (network.py:405-416) and enqueues
+Walks the module tree of :class:`network.Unet` in the order of the reference's ``Unet.forward``
+(network.py:549-565) and dispatches on the block type
 
-  conv (tcgen05 shifted GEMM, IN statistics in the epilogue) -> in_finalize -> in_apply (+residual)
+  ResBlock / ResBlockStack   (network.py:374-449)   conv -> dropout -> IN -> LReLU -> conv -> IN -> (+skip) -> LReLU
+  ConvBlock / ConvBlockStack (network.py:153-214)   conv -> dropout -> IN -> LReLU
+  MaxPoolBlock               (network.py:452-463)   max-pool k2 s2
+  UpConcat                   (network.py:298-350)   convT k3 s2 + zero pad -> IN -> LReLU, concat by addressing
 
+enqueueing  conv (tcgen05 shifted GEMM, IN statistics in the epilogue) -> in_finalize -> in_apply (+residual)
 per layer; the backward pass is the hand-derived reverse (no autograd graph over activations).
 The whole network is ONE ``torch.autograd.Function`` whose outputs are the logits and whose
 backward returns the parameter gradients, so ``loss.backward(); optimizer.step()`` in the
 reference's step loop (trainer.py:490-496) works unchanged.
 
-Layout: activations bf16 NDHWC (channels padded to 16), statistics fp64, master weights fp32.
+Layout: activations 16-bit NDHWC (channels padded to 16), statistics fp64, master weights fp32.
 """
 from __future__ import annotations
 
@@ -27,79 +31,60 @@ IN_EPS = 1e-5      # nn.InstanceNorm3d default (network.py:163,388: no eps passe
 class _ConvOp:
     """Forward, data-gradient and weight-gradient plans of one conv / transposed-conv layer call."""
 
-    def __init__(self, eng, kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: int, grid, transposed=False):
+    def __init__(self, eng, kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: int, grid, skip_k1: bool = False,
+                 fwd_only: bool = False):
         self.kind, self.ks, self.stride = kind, ks, stride
         self.in_C, self.out_C = list(in_C), out_C
         self.grid = grid            # (N, D, H, W) tile grid (coarse grid for strided / transposed layers)
         dev = eng.device
         depth = grid[1]
+        self.dgrad_in = None
+        if fwd_only:
+            self.fwd = ops.DeviceConvPlan(P.make_conv_plan("conv_fwd", ks, stride, in_C, [out_C], depth, grid), dev)
+            return
         if kind == "conv":
             self.fwd = ops.DeviceConvPlan(P.make_conv_plan("conv_fwd", ks, stride, in_C, [out_C], depth, grid), dev)
             self.dgrad = ops.DeviceConvPlan(P.make_conv_plan("conv_dgrad", ks, stride, [out_C], in_C, depth, grid), dev)
+            if skip_k1:     # d(block input) = dgrad_conv1(dy1) + dgrad_skip(g2) in one launch (two A sources)
+                self.dgrad_in = ops.DeviceConvPlan(
+                    P.make_conv_plan("conv_dgrad", 3, stride, [out_C] * 2, in_C, depth, grid, skip_k1=True), dev)
         else:
             self.fwd = ops.DeviceConvPlan(P.make_conv_plan("convT_fwd", 3, 2, in_C, [out_C], depth, grid), dev)
             self.dgrad = ops.DeviceConvPlan(P.make_conv_plan("convT_dgrad", 3, 2, [out_C], in_C, depth, grid), dev)
         self.wgrad = ops.DeviceWgradPlan(P.make_wgrad_plan(kind, ks, stride, in_C, out_C, grid, eng.num_sms), dev)
 
 
-class ResUNetEngine:
-    def __init__(self, model):
-        self.model = model
+class UNetEngine:
+    """Bound to one :class:`network.Unet` (the module that owns conv / blocks / fc)."""
+
+    def __init__(self, net, owner=None):
+        self.net = net
+        self.owner = owner if owner is not None else net      # carries .precision / .training / .last_dropout_masks
         self.device = None
         self.num_sms = 148
-        self._plans: Dict[Tuple, dict] = {}
+        self._ops: Dict[Tuple, _ConvOp] = {}
         self._inv_scale = None
-
-    # ------------------------------------------------------------------ plans
-    def _get_plans(self, shape) -> dict:
-        key = tuple(shape)
-        if key in self._plans:
-            return self._plans[key]
-        from . import _lib
-        self.num_sms = _lib.lib().unet3d_num_sms()
-        net = self.model.net
-        N, _, D, H, W = shape
-        np_ = net.num_pool
-        if D % (1 << np_) or H % (1 << np_) or W % (1 << np_):
-            raise RuntimeError(f"spatial size {(D, H, W)} must be divisible by 2^num_pool = {1 << np_} "
-                               f"(the reference fails in torch.cat, network.py:350)")
-        plans = {}
-
-        def block_ops(blk, in_C, grid_out):
-            o = {"conv1": _ConvOp(self, "conv", 3, blk.stride, in_C, blk.out_channels, grid_out),
-                 "conv2": _ConvOp(self, "conv", 3, 1, [blk.out_channels], blk.out_channels, grid_out)}
-            if blk.uses_skip_conv:
-                o["skip"] = _ConvOp(self, "conv", 1, blk.stride, in_C, blk.out_channels, grid_out)
-                # d(block input) = dgrad_conv1(dy1) + dgrad_skip(g2) in one launch (two A sources)
-                o["dgrad_in"] = ops.DeviceConvPlan(
-                    P.make_conv_plan("conv_dgrad", 3, blk.stride, [blk.out_channels] * 2, in_C, grid_out[1], grid_out,
-                                     skip_k1=True), self.device)
-            return o
-
-        dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
-        for i in range(np_ + 1):
-            g = (N, *dims[i])
-            for j, blk in enumerate(net.encode_blocks[i].res_blocks):
-                plans[("enc", i, j)] = block_ops(blk, [blk.in_channels], g)
-            if i < np_:
-                plans[("pool", i)] = block_ops(net.pool_blocks[i], [net.pool_blocks[i].in_channels], (N, *dims[i + 1]))
-                ct = net.up_blocks[i].conv_trans.up[0]
-                plans[("up", i)] = _ConvOp(self, "convT", 3, 2, [ct.in_channels], ct.out_channels, (N, *dims[i + 1]))
-                dec = net.decode_blocks[i]
-                plans[("dec", i)] = block_ops(dec, [ct.out_channels, dec.in_channels - ct.out_channels], g)
-        self._plans[key] = plans
-        return plans
 
     # ------------------------------------------------------------------ public entry
     def run(self, x: torch.Tensor) -> torch.Tensor:
+        net = self.net
         if not x.is_cuda:
             raise RuntimeError("unet3d_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
-        if x.dim() != 5 or x.shape[1] != self.model.in_channels:
-            raise RuntimeError(f"expected input (N, {self.model.in_channels}, D, H, W), got {tuple(x.shape)}")
-        if self.model.in_channels != 1:
+        if x.dim() != 5 or x.shape[1] != net.conv.in_channels:
+            raise RuntimeError(f"expected input (N, {net.conv.in_channels}, D, H, W), got {tuple(x.shape)}")
+        if net.conv.in_channels != 1:
             raise RuntimeError("the stem kernel covers in_channels == 1 (every reference script uses 1)")
-        self.device = x.device
-        params = [p for p in self.model.parameters()]
+        np_ = net.num_pool
+        D, H, W = x.shape[2:]
+        if D % (1 << np_) or H % (1 << np_) or W % (1 << np_):
+            raise RuntimeError(f"spatial size {(D, H, W)} must be divisible by 2^num_pool = {1 << np_} "
+                               f"(the reference fails in torch.cat, network.py:350)")
+        if self.device != x.device:
+            from . import _lib
+            self.device = x.device
+            self.num_sms = _lib.lib().unet3d_num_sms()
+            self._ops = {}
+        params = list(net.parameters())
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if need_grad:
             return _UNetFn.apply(x, self, *params)
@@ -110,12 +95,18 @@ class ResUNetEngine:
     # ------------------------------------------------------------------ helpers
     @property
     def act_dtype(self):
-        """Storage type of the forward activations and forward weights: bf16 (default) or fp16
-        (model.precision = "fp16"; what apex O1 gave the reference).  Gradient tensors are always bf16."""
-        prec = getattr(self.model, "precision", "bf16")
+        """16-bit storage type of activations, packed weights and gradients: bf16 (default) or fp16
+        (``model.precision = "fp16"``; what apex O1 gave the reference)."""
+        prec = getattr(self.owner, "precision", "bf16")
         if prec not in ("bf16", "fp16"):
             raise RuntimeError(f"precision must be 'bf16' or 'fp16', got {prec!r}")
         return torch.float16 if prec == "fp16" else torch.bfloat16
+
+    def _op(self, key, kind, ks, stride, in_C, out_C, grid, skip_k1=False, fwd_only=False) -> _ConvOp:
+        k = (key, tuple(grid))
+        if k not in self._ops:
+            self._ops[k] = _ConvOp(self, kind, ks, stride, in_C, out_C, grid, skip_k1, fwd_only)
+        return self._ops[k]
 
     def _new_act(self, n, dims, c):
         return torch.empty((n, *dims, P.pad_channels(c)), dtype=self.act_dtype, device=self.device)
@@ -126,7 +117,7 @@ class ResUNetEngine:
         operands -- it faults with an illegal instruction -- and the weight gradient multiplies the two)."""
         return torch.empty_like(t)
 
-    def _apply(self, y, skip, table, save):
+    def _apply(self, y, skip, table):
         out = torch.empty_like(y)
         ops.in_apply(y, skip, out, table)
         return out
@@ -134,96 +125,21 @@ class ResUNetEngine:
     def _drop_scale(self, n, c, p):
         """Dropout3d channel mask drawn exactly as F.dropout3d does, padded to Cp."""
         m = torch.empty(n, c, 1, 1, 1, device=self.device, dtype=torch.float32).bernoulli_(1 - p).div_(1 - p)
-        self.model.last_dropout_masks.append(m)
+        self.owner.last_dropout_masks.append(m)
         out = torch.zeros(n, P.pad_channels(c), device=self.device, dtype=torch.float32)
         out[:, :c] = m.view(n, c)
         return out
 
     def _conv_in(self, op: _ConvOp, inputs, weight, out_dims, drop=None, bias=None, zero_last=False):
-        """conv (+ stats) -> finalize: returns (y, table)."""
+        """conv (+ statistics) -> finalize: returns (y, table)."""
         n = inputs[0].shape[0]
         y = self._new_act(n, out_dims, op.out_C)
         stats = torch.zeros(n, y.shape[-1], 2, dtype=torch.float64, device=self.device)
-        ops.conv_gemm(op.fwd, inputs, op.fwd.packed_weight(weight, self.act_dtype), [y], op.grid, bias=op.fwd.packed_bias(bias),
-                      stats=stats, zero_last=zero_last)
+        ops.conv_gemm(op.fwd, inputs, op.fwd.packed_weight(weight, self.act_dtype), [y], op.grid,
+                      bias=op.fwd.packed_bias(bias), stats=stats, zero_last=zero_last)
         table = torch.empty(n, y.shape[-1], 2, dtype=torch.float32, device=self.device)
         ops.in_finalize(stats, drop, table, out_dims[0] * out_dims[1] * out_dims[2], IN_EPS)
         return y, table
-
-    def _res_block_fwd(self, blk, bops, inputs, out_dims, train, save):
-        n = inputs[0].shape[0]
-        drop = self._drop_scale(n, blk.out_channels, blk.dropout_p) if train else None
-        # conv biases directly followed by InstanceNorm(affine=False) cancel exactly (SURVEY.md S1): not applied
-        y1, t1 = self._conv_in(bops["conv1"], inputs, blk.conv1.weight, out_dims, drop=drop)
-        a1 = self._apply(y1, None, t1, save)
-        y2, t2 = self._conv_in(bops["conv2"], [a1], blk.conv2.weight, out_dims)
-        if blk.uses_skip_conv:
-            sop = bops["skip"]
-            s = self._new_act(n, out_dims, blk.out_channels)
-            ops.conv_gemm(sop.fwd, inputs, sop.fwd.packed_weight(blk.skip_conv.weight, self.act_dtype), [s], sop.grid,
-                          bias=sop.fwd.packed_bias(blk.skip_conv.bias))
-        else:
-            s = inputs[0]
-        out = self._apply(y2, s, t2, save)
-        rec = (inputs, y1, t1, a1, y2, t2, out) if save else None
-        return out, rec
-
-    # ------------------------------------------------------------------ forward
-    def forward_impl(self, x: torch.Tensor, save: bool):
-        model, net = self.model, self.model.net
-        train = model.training
-        model.last_dropout_masks = []
-        plans = self._get_plans(x.shape)
-        N, _, D, H, W = x.shape
-        np_ = net.num_pool
-        dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
-        x32 = x.contiguous().float()
-        tape = {}
-        c0 = net.conv.out_channels
-        cp0 = P.pad_channels(c0)
-        # stem weights as [27][Cp] fp32 (+ bias [Cp])
-        w0 = torch.zeros(27, cp0, device=self.device)
-        w0[:, :c0] = net.conv.weight.detach().reshape(c0, 27).t()
-        b0 = torch.zeros(cp0, device=self.device)
-        b0[:c0] = net.conv.bias.detach()
-        cur = self._new_act(N, dims[0], c0)
-        ops.stem_fwd(x32, w0, b0, cur)
-        tape["x"] = x32
-        skips = []
-        for i in range(np_):
-            for j, blk in enumerate(net.encode_blocks[i].res_blocks):
-                cur, tape[("enc", i, j)] = self._res_block_fwd(blk, plans[("enc", i, j)], [cur], dims[i], train, save)
-            skips.append(cur)
-            cur, tape[("pool", i)] = self._res_block_fwd(net.pool_blocks[i], plans[("pool", i)], [cur], dims[i + 1], train,
-                                                         save)
-        for j, blk in enumerate(net.encode_blocks[np_].res_blocks):
-            cur, tape[("enc", np_, j)] = self._res_block_fwd(blk, plans[("enc", np_, j)], [cur], dims[np_], train, save)
-        for i in range(np_ - 1, -1, -1):
-            ct = net.up_blocks[i].conv_trans.up[0]
-            uop = plans[("up", i)]
-            yu, tu = self._conv_in(uop, [cur], ct.weight, dims[i], bias=ct.bias, zero_last=True)
-            au = self._apply(yu, None, tu, save)
-            if save:
-                tape[("up", i)] = (cur, yu, tu, au)
-            cur, tape[("dec", i)] = self._res_block_fwd(net.decode_blocks[i], plans[("dec", i)], [au, skips[i]], dims[i],
-                                                        train, save)
-        K = net.fc.out_channels
-        cl = net.fc.in_channels
-        wf = torch.zeros(K, P.pad_channels(cl), device=self.device)
-        wf[:, :cl] = net.fc.weight.detach().reshape(K, cl)
-        logits = torch.empty(N, K, D, H, W, device=self.device, dtype=torch.float32)
-        ops.head_fwd(cur, wf, net.fc.bias.detach().float().contiguous(), logits)
-        if save:
-            tape["head"] = (cur, wf)
-        return logits, (tape if save else None)
-
-    # ------------------------------------------------------------------ backward
-    def _wgrad(self, op: _ConvOp, xs, dy, param):
-        pl = op.wgrad.plan
-        dw = torch.zeros(pl.dw_numel + 1, dtype=torch.float32, device=self.device)
-        ops.wgrad_gemm(op.wgrad, xs, dy, dw, op.grid)
-        g = dw.index_select(0, op.wgrad.gidx).view_as(param)
-        return g if self._inv_scale is None else g.mul_(self._inv_scale)
 
     def _in_bwd(self, dout, dout2, out, y, table, zero_last=False, want_dsum=False):
         n, cp = y.shape[0], y.shape[-1]
@@ -235,36 +151,255 @@ class ResUNetEngine:
         ops.in_bwd_apply(g, y, dy, table, sums, dsum, zero_last)
         return g, dy, sums, dsum
 
-    def _res_block_bwd(self, blk, bops, rec, dout, dout2, grads):
+    def _wgrad(self, op: _ConvOp, xs, dy, param, more=()):
+        """Weight gradient of `param`; `more` = further (xs, dy) pairs of the same layer shape whose products are
+        accumulated into the same buffer (a weight applied several times: the attention gate's shared conv)."""
+        pl = op.wgrad.plan
+        dw = torch.zeros(pl.dw_numel + 1, dtype=torch.float32, device=self.device)
+        ops.wgrad_gemm(op.wgrad, xs, dy, dw, op.grid)
+        for xs2, dy2 in more:
+            ops.wgrad_gemm(op.wgrad, xs2, dy2, dw, op.grid)
+        g = dw.index_select(0, op.wgrad.gidx).view_as(param)
+        return g if self._inv_scale is None else g.mul_(self._inv_scale)
+
+    def _unscale(self, g):
+        return g if self._inv_scale is None else g * self._inv_scale
+
+    # ------------------------------------------------------------------ blocks: forward
+    def _block_fwd(self, blk, key, inputs, out_dims, train, save):
+        """Returns (output, record).  `inputs` is a list (a channel concat is a list of two tensors)."""
+        from . import network as NW
+        if isinstance(blk, NW.ResBlock):
+            return self._res_block_fwd(blk, key, inputs, out_dims, train, save)
+        if isinstance(blk, NW.ResBlockStack):
+            recs, cur = [], inputs
+            for j, b in enumerate(blk.res_blocks):
+                out, r = self._res_block_fwd(b, key + (j,), cur, out_dims, train, save)
+                recs.append(r)
+                cur = [out]
+            return cur[0], recs
+        if isinstance(blk, NW.ConvBlock):
+            return self._conv_block_fwd(blk, key, inputs, out_dims, train, save)
+        if isinstance(blk, NW.ConvBlockStack):
+            recs, cur = [], inputs
+            for j, b in enumerate(blk.conv_blocks):
+                out, r = self._conv_block_fwd(b, key + (j,), cur, out_dims, train, save)
+                recs.append(r)
+                cur = [out]
+            return cur[0], recs
+        if isinstance(blk, NW.MaxPoolBlock):
+            x = inputs[0]
+            n = x.shape[0]
+            out = torch.empty((n, *out_dims, x.shape[-1]), dtype=x.dtype, device=x.device)
+            idx = torch.empty((n, *out_dims, x.shape[-1]), dtype=torch.uint8, device=x.device)
+            ops.maxpool_fwd(x, out, idx)
+            return out, ((x.shape, idx) if save else None)
+        raise RuntimeError(f"unsupported block type {type(blk).__name__}")
+
+    def _res_block_fwd(self, blk, key, inputs, out_dims, train, save):
+        n = inputs[0].shape[0]
+        grid = (n, *out_dims)
+        in_C = self._split_channels(blk.in_channels, inputs)
+        c1 = self._op(key + ("conv1",), "conv", 3, blk.stride, in_C, blk.out_channels, grid, skip_k1=blk.uses_skip_conv)
+        c2 = self._op(key + ("conv2",), "conv", 3, 1, [blk.out_channels], blk.out_channels, grid)
+        drop = self._drop_scale(n, blk.out_channels, blk.dropout_p) if (train and blk.dropout_p > 0) else None
+        # conv biases directly followed by InstanceNorm(affine=False) cancel exactly (SURVEY.md S1): not applied
+        y1, t1 = self._conv_in(c1, inputs, blk.conv1.weight, out_dims, drop=drop)
+        a1 = self._apply(y1, None, t1)
+        y2, t2 = self._conv_in(c2, [a1], blk.conv2.weight, out_dims)
+        if blk.uses_skip_conv:
+            sk = self._op(key + ("skip",), "conv", 1, blk.stride, in_C, blk.out_channels, grid)
+            s = self._new_act(n, out_dims, blk.out_channels)
+            ops.conv_gemm(sk.fwd, inputs, sk.fwd.packed_weight(blk.skip_conv.weight, self.act_dtype), [s], sk.grid,
+                          bias=sk.fwd.packed_bias(blk.skip_conv.bias))
+        else:
+            s = inputs[0]
+        out = self._apply(y2, s, t2)
+        return out, ((inputs, y1, t1, a1, y2, t2, out) if save else None)
+
+    def _conv_block_fwd(self, blk, key, inputs, out_dims, train, save):
+        n = inputs[0].shape[0]
+        in_C = self._split_channels(blk.in_channels, inputs)
+        op = self._op(key + ("conv",), "conv", 3, 1, in_C, blk.out_channels, (n, *out_dims))
+        drop = self._drop_scale(n, blk.out_channels, blk.dropout_p) if (train and blk.dropout_p > 0) else None
+        y, t = self._conv_in(op, inputs, blk.conv.weight, out_dims, drop=drop)
+        a = self._apply(y, None, t)
+        return a, ((inputs, y, t, a) if save else None)
+
+    # ------------------------------------------------------------------ attention gate (network.py:353-371)
+    def _att_ops(self, gate, level, grid):
+        c = gate.conv.in_channels
+        if gate.conv.out_channels != c:
+            raise RuntimeError("AttBlock conv must keep the width")
+        k1 = self._op(("att", level), "conv", 1, 1, [c], c, grid)
+        k2 = self._op(("att2", level), "conv", 1, 1, [c, c], c, grid, fwd_only=True)
+        return c, k1, k2
+
+    def _att_fwd(self, gate, level, skip, au, dims):
+        """xs = conv(skip); f = lrelu(conv(skip) + conv(gate)) as ONE two-source GEMM with the weight repeated
+        along K and twice the bias; z = conv(f); result = xs * sigmoid(z).  All three use gate.conv."""
+        n = skip.shape[0]
+        c, k1, k2 = self._att_ops(gate, level, (n, *dims))
+        w, b = gate.conv.weight, gate.conv.bias
+        wp = k1.fwd.packed_weight(w, self.act_dtype)
+        bp = k1.fwd.packed_bias(b)
+        xs, f, z, out = (self._new_act(n, dims, c) for _ in range(4))
+        ops.conv_gemm(k1.fwd, [skip], wp, [xs], k1.grid, bias=bp)
+        ops.conv_gemm(k2.fwd, [skip, au], k2.fwd.packed_weight(torch.cat([w.detach(), w.detach()], 1), self.act_dtype,
+                                                           key=(w.data_ptr(), w._version, self.act_dtype, "x2")), [f],
+                      k2.grid, bias=bp * 2.0, act=1)
+        ops.conv_gemm(k1.fwd, [f], wp, [z], k1.grid, bias=bp)
+        ops.att_gate_fwd(xs, z, out)
+        return out, (skip, au, xs, f, z)
+
+    def _att_bwd(self, gate, level, rec, d_up, d_out, grads):
+        """Returns (d(upsampled), d(skip)) with the gate's contributions folded in."""
+        skip, au, xs, f, z = rec
+        n, dims = skip.shape[0], tuple(skip.shape[1:4])
+        c, k1, _ = self._att_ops(gate, level, (n, *dims))
+        w = gate.conv.weight
+        cp = xs.shape[-1]
+        dxs, dz, df, dpre, t, dskip, dup = (self._grad_like(xs) for _ in range(7))
+        sums = torch.zeros(cp, 2, dtype=torch.float64, device=self.device)
+        psum = torch.zeros(cp, dtype=torch.float64, device=self.device)
+        ops.att_gate_bwd(d_out, xs, z, dxs, dz, sums)
+        wp = k1.dgrad.packed_weight(w, self.act_dtype)
+        ops.conv_gemm(k1.dgrad, [dz], wp, [df], k1.grid)
+        ops.att_mid_bwd(df, f, dxs, dpre, t, psum)
+        ops.conv_gemm(k1.dgrad, [t], wp, [dskip], k1.grid)                       # W^T (dxs + dpre)
+        ops.conv_gemm(k1.dgrad, [dpre], wp, [dup], k1.grid, addends=[d_up])      # d_up + W^T dpre
+        grads[w] = self._wgrad(k1, [f], dz, w, more=[([skip], t), ([au], dpre)])
+        grads[gate.conv.bias] = self._unscale((sums[:c, 0] + sums[:c, 1] + 2.0 * psum[:c]).float())
+        return dup, dskip
+
+    @staticmethod
+    def _split_channels(total: int, inputs) -> List[int]:
+        """Real channel counts of the tensors of a concat: [total] or [c_up, total - c_up]; the real count of the
+        upsampled tensor is recorded on it by its producer (attribute _c)."""
+        if len(inputs) == 1:
+            return [total]
+        c0 = getattr(inputs[0], "_c")
+        return [c0, total - c0]
+
+    # ------------------------------------------------------------------ forward
+    def forward_impl(self, x: torch.Tensor, save: bool):
+        net, owner = self.net, self.owner
+        train = owner.training
+        owner.last_dropout_masks = []
+        N, _, D, H, W = x.shape
+        np_ = net.num_pool
+        dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
+        x32 = x.contiguous().float()
+        tape = {}
+        c0 = net.conv.out_channels
+        cp0 = P.pad_channels(c0)
+        w0 = torch.zeros(27, cp0, device=self.device)                  # stem weights as [27][Cp] fp32 (+ bias [Cp])
+        w0[:, :c0] = net.conv.weight.detach().reshape(c0, 27).t()
+        b0 = torch.zeros(cp0, device=self.device)
+        b0[:c0] = net.conv.bias.detach()
+        cur = self._new_act(N, dims[0], c0)
+        ops.stem_fwd(x32, w0, b0, cur)
+        tape["x"] = x32
+        skips = []
+        for i in range(np_):
+            cur, tape[("enc", i)] = self._block_fwd(net.encode_blocks[i], ("enc", i), [cur], dims[i], train, save)
+            skips.append(cur)
+            cur, tape[("pool", i)] = self._block_fwd(net.pool_blocks[i], ("pool", i), [cur], dims[i + 1], train, save)
+        cur, tape[("enc", np_)] = self._block_fwd(net.encode_blocks[np_], ("enc", np_), [cur], dims[np_], train, save)
+        for i in range(np_ - 1, -1, -1):
+            up = net.up_blocks[i]
+            ct = up.conv_trans.up[0]
+            uop = self._op(("up", i), "convT", 3, 2, [ct.in_channels], ct.out_channels, (N, *dims[i + 1]))
+            yu, tu = self._conv_in(uop, [cur], ct.weight, dims[i], bias=ct.bias, zero_last=True)
+            au = self._apply(yu, None, tu)
+            au._c = ct.out_channels
+            if save:
+                tape[("up", i)] = (cur, yu, tu, au)
+            skip = skips[i]
+            if getattr(up, "attention", False):
+                skip, rec = self._att_fwd(up.att_gate, i, skip, au, dims[i])
+                if save:
+                    tape[("att", i)] = rec
+            cur, tape[("dec", i)] = self._block_fwd(net.decode_blocks[i], ("dec", i), [au, skip], dims[i], train, save)
+        K = net.fc.out_channels
+        cl = net.fc.in_channels
+        wf = torch.zeros(K, P.pad_channels(cl), device=self.device)
+        wf[:, :cl] = net.fc.weight.detach().reshape(K, cl)
+        logits = torch.empty(N, K, D, H, W, device=self.device, dtype=torch.float32)
+        ops.head_fwd(cur, wf, net.fc.bias.detach().float().contiguous(), logits)
+        if save:
+            tape["head"] = (cur, wf)
+        return logits, (tape if save else None)
+
+    # ------------------------------------------------------------------ blocks: backward
+    def _block_bwd(self, blk, key, rec, dout, dout2, grads):
+        """Returns the list of gradients w.r.t. the block's inputs."""
+        from . import network as NW
+        if isinstance(blk, NW.ResBlock):
+            return self._res_block_bwd(blk, key, rec, dout, dout2, grads)
+        if isinstance(blk, (NW.ResBlockStack, NW.ConvBlockStack)):
+            blocks = blk.res_blocks if isinstance(blk, NW.ResBlockStack) else blk.conv_blocks
+            fn = self._res_block_bwd if isinstance(blk, NW.ResBlockStack) else self._conv_block_bwd
+            d, d2 = dout, dout2
+            for j in range(len(blocks) - 1, -1, -1):
+                dins = fn(blocks[j], key + (j,), rec[j], d, d2, grads)
+                d, d2 = dins[0], None
+            return dins
+        if isinstance(blk, NW.ConvBlock):
+            return self._conv_block_bwd(blk, key, rec, dout, dout2, grads)
+        if isinstance(blk, NW.MaxPoolBlock):
+            shape, idx = rec
+            if dout2 is not None:
+                dout = dout + dout2
+            dx = torch.empty(shape, dtype=dout.dtype, device=dout.device)
+            ops.maxpool_bwd(dout, idx, dx)
+            return [dx]
+        raise RuntimeError(f"unsupported block type {type(blk).__name__}")
+
+    def _res_block_bwd(self, blk, key, rec, dout, dout2, grads):
         inputs, y1, t1, a1, y2, t2, out = rec
+        grid = (inputs[0].shape[0], *y1.shape[1:4])
+        in_C = self._split_channels(blk.in_channels, inputs)
+        c1 = self._op(key + ("conv1",), "conv", 3, blk.stride, in_C, blk.out_channels, grid, skip_k1=blk.uses_skip_conv)
+        c2 = self._op(key + ("conv2",), "conv", 3, 1, [blk.out_channels], blk.out_channels, grid)
         g2, dy2, sums2, _ = self._in_bwd(dout, dout2, out, y2, t2)
-        grads[blk.conv2.weight] = self._wgrad(bops["conv2"], [a1], dy2, blk.conv2.weight)
+        grads[blk.conv2.weight] = self._wgrad(c2, [a1], dy2, blk.conv2.weight)
         grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias)       # cancelled by the norm (S1)
         da1 = self._grad_like(a1)
-        c2 = bops["conv2"]
         ops.conv_gemm(c2.dgrad, [dy2], c2.dgrad.packed_weight(blk.conv2.weight, self.act_dtype), [da1], c2.grid)
         _, dy1, _, _ = self._in_bwd(da1, None, a1, y1, t1)
-        c1 = bops["conv1"]
         grads[blk.conv1.weight] = self._wgrad(c1, inputs, dy1, blk.conv1.weight)
         grads[blk.conv1.bias] = torch.zeros_like(blk.conv1.bias)
+        dins = [self._grad_like(t) for t in inputs]
         if blk.uses_skip_conv:
-            sk = bops["skip"]
+            sk = self._op(key + ("skip",), "conv", 1, blk.stride, in_C, blk.out_channels, grid)
             grads[blk.skip_conv.weight] = self._wgrad(sk, inputs, g2, blk.skip_conv.weight)
             grads[blk.skip_conv.bias] = self._unscale(sums2[:, :blk.out_channels, 0].sum(0).float())
-            dins = [self._grad_like(t) for t in inputs]
-            dp = bops["dgrad_in"]
+            dp = c1.dgrad_in
             ops.conv_gemm(dp, [dy1, g2], dp.packed_weight([blk.conv1.weight, blk.skip_conv.weight], self.act_dtype), dins,
                           c1.grid)
-            return dins
-        dins = [self._grad_like(t) for t in inputs]
-        ops.conv_gemm(c1.dgrad, [dy1], c1.dgrad.packed_weight(blk.conv1.weight, self.act_dtype), dins, c1.grid,
-                      addends=[g2])
+        else:
+            ops.conv_gemm(c1.dgrad, [dy1], c1.dgrad.packed_weight(blk.conv1.weight, self.act_dtype), dins, c1.grid,
+                          addends=[g2])
         return dins
 
+    def _conv_block_bwd(self, blk, key, rec, dout, dout2, grads):
+        inputs, y, t, a = rec
+        in_C = self._split_channels(blk.in_channels, inputs)
+        op = self._op(key + ("conv",), "conv", 3, 1, in_C, blk.out_channels, (inputs[0].shape[0], *y.shape[1:4]))
+        _, dy, _, _ = self._in_bwd(dout, dout2, a, y, t)
+        grads[blk.conv.weight] = self._wgrad(op, inputs, dy, blk.conv.weight)
+        grads[blk.conv.bias] = torch.zeros_like(blk.conv.bias)          # cancelled by the norm (S1)
+        dins = [self._grad_like(x) for x in inputs]
+        ops.conv_gemm(op.dgrad, [dy], op.dgrad.packed_weight(blk.conv.weight, self.act_dtype), dins, op.grid)
+        return dins
+
+    # ------------------------------------------------------------------ backward
     def backward_impl(self, tape, x_shape, dlogits: torch.Tensor) -> Dict[torch.nn.Parameter, torch.Tensor]:
-        net = self.model.net
-        plans = self._get_plans(x_shape)
+        net = self.net
         np_ = net.num_pool
+        N, _, D, H, W = x_shape
+        dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
         grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         # fp16 gradients need a scale to stay inside fp16's range (Dice gradients are ~1e-7 per voxel).  It is
         # internal and dynamic: a power of two that puts max|dlogits| at 64, taken from this step's dlogits on the
@@ -275,7 +410,6 @@ class ResUNetEngine:
             amax = dlogits.detach().abs().amax().clamp_min(1e-30)
             gscale = torch.exp2(torch.floor(torch.log2(64.0 / amax))).clamp(1.0, 2.0 ** 40).float().reshape(1)
             self._inv_scale = (1.0 / gscale)
-        # head
         a_last, wf = tape["head"]
         K, cl = net.fc.out_channels, net.fc.in_channels
         d_cur = self._grad_like(a_last)
@@ -285,28 +419,23 @@ class ResUNetEngine:
         grads[net.fc.bias] = dwf[K * wf.shape[1]:].clone()
         pending = {}
         for i in range(np_):
-            dec = net.decode_blocks[i]
-            d_up, d_skip = self._res_block_bwd(dec, plans[("dec", i)], tape[("dec", i)], d_cur, None, grads)
+            d_up, d_skip = self._block_bwd(net.decode_blocks[i], ("dec", i), tape[("dec", i)], d_cur, None, grads)
+            if ("att", i) in tape:
+                d_up, d_skip = self._att_bwd(net.up_blocks[i].att_gate, i, tape[("att", i)], d_up, d_skip, grads)
             pending[i] = d_skip
             xin, yu, tu, au = tape[("up", i)]
             ct = net.up_blocks[i].conv_trans.up[0]
-            uop = plans[("up", i)]
+            uop = self._op(("up", i), "convT", 3, 2, [ct.in_channels], ct.out_channels, (N, *dims[i + 1]))
             _, dyu, _, dsum = self._in_bwd(d_up, None, au, yu, tu, zero_last=True, want_dsum=True)
             grads[ct.weight] = self._wgrad(uop, [xin], dyu, ct.weight)
             grads[ct.bias] = self._unscale(dsum[:ct.out_channels].float())
             d_cur = self._grad_like(xin)
             ops.conv_gemm(uop.dgrad, [dyu], uop.dgrad.packed_weight(ct.weight, self.act_dtype), [d_cur], uop.grid)
-        for j in range(len(net.encode_blocks[np_].res_blocks) - 1, -1, -1):
-            blk = net.encode_blocks[np_].res_blocks[j]
-            d_cur = self._res_block_bwd(blk, plans[("enc", np_, j)], tape[("enc", np_, j)], d_cur, None, grads)[0]
+        d_cur = self._block_bwd(net.encode_blocks[np_], ("enc", np_), tape[("enc", np_)], d_cur, None, grads)[0]
         for i in range(np_ - 1, -1, -1):
-            d_cur = self._res_block_bwd(net.pool_blocks[i], plans[("pool", i)], tape[("pool", i)], d_cur, None, grads)[0]
-            nblk = len(net.encode_blocks[i].res_blocks)
-            for j in range(nblk - 1, -1, -1):
-                blk = net.encode_blocks[i].res_blocks[j]
-                d2 = pending[i] if j == nblk - 1 else None
-                d_cur = self._res_block_bwd(blk, plans[("enc", i, j)], tape[("enc", i, j)], d_cur, d2, grads)[0]
-        # stem
+            d_cur = self._block_bwd(net.pool_blocks[i], ("pool", i), tape[("pool", i)], d_cur, None, grads)[0]
+            # the level's encoder output fed both the pooling block and the skip connection
+            d_cur = self._block_bwd(net.encode_blocks[i], ("enc", i), tape[("enc", i)], d_cur, pending[i], grads)[0]
         c0 = net.conv.out_channels
         cp0 = d_cur.shape[-1]
         dw0 = torch.zeros(28 * cp0, device=self.device)
@@ -317,13 +446,10 @@ class ResUNetEngine:
         self._inv_scale = None
         return grads
 
-    def _unscale(self, g):
-        return g if self._inv_scale is None else g * self._inv_scale
-
 
 class _UNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, eng: ResUNetEngine, *params):
+    def forward(ctx, x, eng: UNetEngine, *params):
         logits, tape = eng.forward_impl(x.detach(), save=True)
         ctx.eng, ctx.tape, ctx.x_shape, ctx.params = eng, tape, tuple(x.shape), params
         return logits

@@ -106,9 +106,10 @@ class DeviceConvPlan:
         self._b_version = None
         self._b_packed = None
 
-    def packed_weight(self, w, dtype=torch.bfloat16) -> torch.Tensor:
+    def packed_weight(self, w, dtype=torch.bfloat16, key=None) -> torch.Tensor:
         """16-bit tile stream of parameter `w` (re-gathered only when the parameter or the dtype changed).
-        `w` may be a list of parameters: the plan's gather index then addresses their concatenation."""
+        `w` may be a list of parameters: the plan's gather index then addresses their concatenation.
+        `key`: cache key to use when `w` is a temporary derived from parameters (its own address means nothing)."""
         if isinstance(w, (list, tuple)):
             key = tuple((t.data_ptr(), t._version) for t in w) + (dtype,)
             if self._w_version == key and not torch.cuda.is_current_stream_capturing():
@@ -116,7 +117,7 @@ class DeviceConvPlan:
             packed = self.packed_weight(torch.cat([t.detach().reshape(-1).float() for t in w]), dtype)
             self._w_version = key
             return packed
-        key = (w.data_ptr(), w._version, dtype)
+        key = (w.data_ptr(), w._version, dtype) if key is None else key
         if self._w_version != key or torch.cuda.is_current_stream_capturing():   # a graph must re-pack on every replay
             src = w.detach()
             if src.dtype != torch.float32 or not src.is_contiguous():
@@ -143,7 +144,7 @@ class DeviceConvPlan:
 def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch.Tensor, outs: Sequence[torch.Tensor],
               grid: Tuple[int, int, int, int], bias: Optional[torch.Tensor] = None,
               addends: Optional[Sequence[Optional[torch.Tensor]]] = None, stats: Optional[torch.Tensor] = None,
-              zero_last: bool = False):
+              zero_last: bool = False, act: int = 0):
     """Launch the shifted-GEMM kernel for `dp` (see plan.make_conv_plan for the meaning of a plan)."""
     pl = dp.plan
     a = _lib.ConvArgs()
@@ -178,6 +179,7 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.stats_C = stats.shape[1] if stats is not None else 0
     a.omul = pl.omul
     a.zD, a.zH, a.zW = (d - 1, h - 1, w - 1) if zero_last else (-1, -1, -1)
+    a.act = act
     flops = pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3]
     _count()
     with _Timed("conv_gemm_kernel", flops):
@@ -250,6 +252,60 @@ def channel_sum(x: torch.Tensor, dsum: torch.Tensor):
     _count()
     _lib.check(_lib.lib().unet3d_channel_sum(x.data_ptr(), dsum.data_ptr(), n * d * h * w, cp, _stream()),
                "unet3d_channel_sum")
+
+
+def att_gate_fwd(xs: torch.Tensor, z: torch.Tensor, out: torch.Tensor):
+    assert xs.dtype in ACT_DTYPES and z.dtype == xs.dtype and out.dtype == xs.dtype and xs.shape == z.shape == out.shape
+    _count()
+    _lib.check(_lib.lib().unet3d_att_gate_fwd(xs.data_ptr(), z.data_ptr(), out.data_ptr(), xs.numel(), _f16(xs), _stream()),
+               "unet3d_att_gate_fwd")
+
+
+def att_gate_bwd(dout, xs, z, dxs, dz, sums):
+    n, d, h, w, cp = xs.shape
+    assert all(t.dtype == xs.dtype and t.shape == xs.shape for t in (dout, z, dxs, dz))
+    assert sums.dtype == torch.float64 and sums.numel() == 2 * cp
+    _count()
+    _lib.check(_lib.lib().unet3d_att_gate_bwd(dout.data_ptr(), xs.data_ptr(), z.data_ptr(), dxs.data_ptr(), dz.data_ptr(),
+                                              sums.data_ptr(), n * d * h * w, cp, _f16(xs), _stream()), "unet3d_att_gate_bwd")
+
+
+def att_mid_bwd(df, f, dxs, dpre, t, ssum):
+    n, d, h, w, cp = f.shape
+    assert all(x.dtype == f.dtype and x.shape == f.shape for x in (df, dxs, dpre, t))
+    assert ssum.dtype == torch.float64 and ssum.numel() == cp
+    _count()
+    _lib.check(_lib.lib().unet3d_att_mid_bwd(df.data_ptr(), f.data_ptr(), dxs.data_ptr(), dpre.data_ptr(), t.data_ptr(),
+                                             ssum.data_ptr(), n * d * h * w, cp, _f16(f), _stream()), "unet3d_att_mid_bwd")
+
+
+def maxpool_fwd(x: torch.Tensor, out: torch.Tensor, code: torch.Tensor):
+    """nn.MaxPool3d(2, 2) on (N, D, H, W, Cp); code (uint8, shape of out) = kd*4 + kh*2 + kw of the winner."""
+    n, d, h, w, cp = x.shape
+    assert x.dtype in ACT_DTYPES and out.dtype == x.dtype and code.dtype == torch.uint8
+    assert tuple(out.shape) == (n, d // 2, h // 2, w // 2, cp) and code.shape == out.shape
+    _count()
+    _lib.check(_lib.lib().unet3d_maxpool3d_fwd(x.data_ptr(), out.data_ptr(), code.data_ptr(), n, d, h, w, cp, _f16(x),
+                                               _stream()), "unet3d_maxpool3d_fwd")
+
+
+def maxpool_bwd(dout: torch.Tensor, code: torch.Tensor, dx: torch.Tensor):
+    n, d, h, w, cp = dx.shape
+    assert dout.dtype == dx.dtype and code.dtype == torch.uint8 and code.shape == dout.shape
+    _count()
+    _lib.check(_lib.lib().unet3d_maxpool3d_bwd(dout.data_ptr(), code.data_ptr(), dx.data_ptr(), n, d, h, w, cp, _stream()),
+               "unet3d_maxpool3d_bwd")
+
+
+def maxpool_flat_index(code: torch.Tensor, c: int) -> torch.Tensor:
+    """The int64 indices ``F.max_pool3d(..., return_indices=True)`` returns, (N, C, D/2, H/2, W/2), from the codes."""
+    n, do, ho, wo, _ = code.shape
+    k = code[..., :c].long()
+    d = torch.arange(do, device=code.device).view(1, do, 1, 1, 1)
+    h = torch.arange(ho, device=code.device).view(1, 1, ho, 1, 1)
+    w = torch.arange(wo, device=code.device).view(1, 1, 1, wo, 1)
+    flat = ((2 * d + (k >> 2)) * (2 * ho) + 2 * h + ((k >> 1) & 1)) * (2 * wo) + 2 * w + (k & 1)
+    return flat.permute(0, 4, 1, 2, 3).contiguous()
 
 
 def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor):

@@ -125,6 +125,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--patch", type=int, default=PATCH[0], help="cubic patch edge (default 128 = the metric's config)")
+    ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement (cfg-4)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -146,6 +148,7 @@ def main():
     pe = args.patch
     torch.manual_seed(0)
     model = unet3d_b200.ResUnet3D(num_pool=4, num_features=30, in_channels=1, out_channels=3).to(dev).train()
+    model.precision = args.precision
     loss_fn = unet3d_b200.DiceLoss()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
 
@@ -234,6 +237,36 @@ def main():
                 "per_kernel_ms_per_step": {k: v[1] / K for k, v in by.items()},
                 "per_kernel_tflops": {k: (v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None) for k, v in by.items()}}
 
+    # ---- second half of BASELINE.json's metric: sliding-window inference, CT volumes/s (cfg-4: 512x512x256 volume,
+    # 128^3 windows at 50 % overlap = 147 windows on the reference's grid; windows are dealt to the ranks)
+    infer = None
+    if not args.no_infer and pe == 128:
+        import numpy as np
+        del d_img, d_lab
+        opt.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        vol = np.random.RandomState(7).standard_normal((512, 512, 256, 1)).astype(np.float32)
+        unet3d_b200.predict_per_patch(vol[:128, :128, :128], model, 3, (128, 128, 128), 2, verbose=False)   # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        labels = unet3d_b200.predict_per_patch(vol, model, 3, (128, 128, 128), 2, verbose=False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        n_win = len(unet3d_b200.tile_origins((512, 512, 256), (128, 128, 128), 2))
+        infer = {"metric": "infer CT volumes/s", "value": 1.0 / dt, "unit": "volumes/s", "seconds_per_volume": dt,
+                 "volume": [512, 512, 256], "window": [128, 128, 128], "windows": n_win, "grid": "reference (trainer.py:29-40)",
+                 "blend": "uniform", "includes": "H2D of the fp32 volume, all window forwards, blend, normalise + argmax, "
+                 "D2H of the uint8 label map" + (", all-reduce of the blend buffers" if world > 1 else ""),
+                 "label_hist": [int(v) for v in np.bincount(labels.reshape(-1), minlength=3)[:3]]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cvox, cores = cpu_port_step_time(4, 1)
@@ -243,7 +276,7 @@ def main():
     if rank == 0:
         line = {"metric": "train voxels/s (fwd+bwd)", "value": vox / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": WORKLOAD if pe == 128 else f"REDUCED patch {pe}^3 (not the metric's config)",
                            "global_batch": BATCH * world, "patch": [pe, pe, pe], "parallelism": f"dp{world}",
                            "timed_region": "zero_grad + forward + DiceLoss + backward + grad all-reduce (N>1) + Adam step",
@@ -253,7 +286,7 @@ def main():
                 "e2e": {"value": vox / (ms_e2e * 1e-3), "unit": "voxels/s",
                         "h2d_bytes_per_step": (h_img.numel() * 4 + h_lab.numel() * 8) * world, "d2h_bytes_per_step": 4 * world,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "infer": infer}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

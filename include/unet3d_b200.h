@@ -71,6 +71,7 @@ typedef struct unet3d_conv_args {
   int in_f16, out_f16;   /* 16-bit format of A + weights / of out + addend: 0 = bf16, 1 = fp16 */
   long long out_sN, out_sD, out_sH, out_sW;   /* ELEMENT strides of out/addend */
   int out_C, stats_C, omul, zD, zH, zW;
+  int act;                /* epilogue activation after bias/addend: 0 none, 1 LeakyReLU(0.01) */
 } unet3d_conv_args;
 int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream);
 size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages);
@@ -135,6 +136,23 @@ int unet3d_sw_accumulate(const float* logits, const float* window, float* result
                          int py, int pz, int x0, int y0, int z0, int X, int Y, int Z, void* stream);
 int unet3d_sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K,
                        long long XYZ, void* stream);
+
+/* MaxPoolBlock = nn.MaxPool3d(kernel_size=2, stride=2) (network.py:452-463) on 16-bit NDHWC (N, D, H, W, Cp), D/H/W even.
+ * code: uint8 (N, D/2, H/2, W/2, Cp) = kd*4 + kh*2 + kw of the winner, PyTorch's scan order and tie/NaN rule, i.e.
+ * torch's return_indices value is ((2d+kd)*H + 2h+kh)*W + 2w+kw.  bwd writes every element of dx (no pre-zeroing). */
+int unet3d_maxpool3d_fwd(const void* x, void* out, uint8_t* code, int N, int D, int H, int W, int Cp, int act_f16,
+                         void* stream);
+int unet3d_maxpool3d_bwd(const void* dout, const uint8_t* code, void* dx, int N, int D, int H, int W, int Cp,
+                         void* stream);
+
+/* Pointwise parts of the attention gate AttBlock (network.py:353-371); its three 1x1x1 convs are unet3d_conv_gemm calls
+ * (the middle one with act = 1).  fwd: out = xs * sigmoid(z).  bwd: dxs = dout * r, dz = dout * xs * r * (1 - r),
+ * sums fp64 [Cp][2] += {sum dxs, sum dz}.  mid_bwd: dpre = df * lrelu'(f), t = dxs + dpre, sum fp64 [Cp] += sum dpre. */
+int unet3d_att_gate_fwd(const void* xs, const void* z, void* out, long long n_elem, int act_f16, void* stream);
+int unet3d_att_gate_bwd(const void* dout, const void* xs, const void* z, void* dxs, void* dz, double* sums, long long NV,
+                        int Cp, int act_f16, void* stream);
+int unet3d_att_mid_bwd(const void* df, const void* f, const void* dxs, void* dpre, void* t, double* sum, long long NV,
+                       int Cp, int act_f16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,9 +74,43 @@ def test_state_dict_layout_and_unused_params():
     assert unet3d_b200.UNet3D is unet3d_b200.ResUnet3D
     assert (m.num_pool, m.num_features, m.in_channels, m.out_channels) == (4, 30, 1, 3)
     with pytest.raises(AssertionError):
-        unet3d_b200.Unet(1, 1, [[8, 8], [16, 16]], lambda i: 1)
+        unet3d_b200.Unet(1, 1, [[8, 8], [16, 16]])          # even number of pairs (network.py:491)
+    with pytest.raises(AssertionError):
+        unet3d_b200.Unet(1, 1, [[8, 8]])                    # no pooling level (network.py:493)
+    with pytest.raises(NotImplementedError):
+        unet3d_b200.ResBlock(8, 8, norm_op=torch.nn.BatchNorm3d)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 16, 16, 16))         # CPU tensors are refused: no fallback path
+
+
+@pytest.mark.parametrize("fixture,build", [
+    ("small_resunet.npz", lambda: unet3d_b200.ResUnet3D(num_pool=2, num_features=8, out_channels=3)),
+    ("attr_resunet.npz", lambda: unet3d_b200.ResAttrUnet3D(num_pool=2, num_features=8, out_channels=3)),
+    ("plain_unet_train.npz", lambda: unet3d_b200.Unet(1, 3, unet3d_b200.generate_paired_features2(2, 4))),
+])
+def test_variants_load_reference_state_dicts(golden_dir, fixture, build):
+    """Keys, shapes and -- where recorded -- the parameter ORDER (what optimizer state_dicts index by) equal the
+    reference's (network.py:536-547 registers pool, up, encode, decode, conv, fc)."""
+    z = np.load(os.path.join(golden_dir, fixture))
+    ref = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    m = build()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys()) or set(sd.keys()) == set(ref.keys())
+    assert all(sd[k].shape == ref[k].shape for k in ref)
+    m.load_state_dict(ref, strict=True)
+    if "param_order" in z.files:
+        assert [k for k, _ in m.named_parameters()] == z["param_order"].tolist()
+
+
+def test_default_net_parameter_order_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "default_resunet_32.npz"))
+    m = unet3d_b200.ResUnet3D(out_channels=3)
+    assert [k for k, _ in m.named_parameters()] == z["names"].tolist()
+    assert list(m.state_dict().keys()) == z["state_keys"].tolist()
+    assert unet3d_b200.generate_paired_features2(2, 4) == O.paired_features2(2, 4)
+    a = unet3d_b200.ResAttrUnet3D2(out_channels=3)
+    assert a.net.num_pool == 5 and a.net.up_blocks[0].att_gate.conv.weight.shape == (30, 30, 1, 1, 1)
+    assert a.net.encode_blocks[5].res_blocks[0].conv1.weight.shape == (320, 320, 3, 3, 3)
 
 
 def _gloo_worker(rank, world, port):

@@ -98,6 +98,38 @@ def test_plain_unet_maxpool(golden_dir):
     assert torch.allclose(logits, torch.from_numpy(z["logits"]), rtol=1e-4, atol=1e-5)
 
 
+def _check_grads(sd, z, rtol=2e-3, atol=2e-6):
+    unused = set(z["unused"].tolist())
+    for k, p in sd.items():
+        if k in unused:
+            assert p.grad is None, k
+            continue
+        assert torch.allclose(p.grad, torch.from_numpy(z["grad/" + k]), rtol=rtol, atol=atol), k
+
+
+def test_attention_resunet_forward_loss_grads(golden_dir):
+    """ResAttrUnet3D (AttBlock gates, network.py:72-101,353-371) from the live reference."""
+    z = _load(golden_dir, "attr_resunet.npz")
+    sd = {k: v.clone().requires_grad_(True) for k, v in _sd(z).items()}
+    logits = O.resunet3d_forward(sd, torch.from_numpy(z["x"]), num_pool=2, num_features=8, attention=True)
+    assert torch.allclose(logits, torch.from_numpy(z["logits"]), rtol=1e-4, atol=1e-5)
+    loss = O.hybrid_loss(logits, torch.from_numpy(z["y"]), weight_v=[1, 148, 191], alpha=0.9, beta=0.1)
+    assert abs(loss.item() - float(z["loss"])) < 1e-5
+    loss.backward()
+    _check_grads(sd, z)
+
+
+def test_plain_unet_maxpool_grads(golden_dir):
+    z = _load(golden_dir, "plain_unet_train.npz")
+    sd = {k: v.clone().requires_grad_(True) for k, v in _sd(z).items()}
+    logits = O.plain_unet_forward(sd, torch.from_numpy(z["x"]), z["pf"].tolist())
+    assert torch.allclose(logits, torch.from_numpy(z["logits"]), rtol=1e-4, atol=1e-5)
+    loss = O.dice_loss(logits, torch.from_numpy(z["y"]))
+    assert abs(loss.item() - float(z["loss"])) < 1e-5
+    loss.backward()
+    _check_grads(sd, z)
+
+
 def test_pad_crop_roundtrip():
     """Even size differences round-trip; odd ones come back shifted by one voxel because the pad
     puts ceil(diff/2) in front (floor division of a negative lower bound, transform.py:414) while

@@ -27,7 +27,7 @@ class ConvArgs(C.Structure):
                 ("n_taps", C.c_int), ("fuse", C.c_int), ("nbuf", C.c_int), ("wT", C.c_int), ("w_stages", C.c_int), ("in_f16", C.c_int), ("out_f16", C.c_int),
                 ("out_sN", C.c_longlong), ("out_sD", C.c_longlong), ("out_sH", C.c_longlong), ("out_sW", C.c_longlong),
                 ("out_C", C.c_int), ("stats_C", C.c_int), ("omul", C.c_int), ("zD", C.c_int), ("zH", C.c_int),
-                ("zW", C.c_int), ("act", C.c_int)]
+                ("zW", C.c_int), ("act", C.c_int), ("a_stages", C.c_int), ("dense", C.c_int)]
 
 
 class WgradArgs(C.Structure):
@@ -42,7 +42,7 @@ _SIGS = {
     "unet3d_last_error_string": (C.c_char_p, []),
     "unet3d_num_sms": (C.c_int, []),
     "unet3d_conv_gemm": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
-    "unet3d_conv_gemm_smem_bytes": (C.c_size_t, [C.c_int] * 6),
+    "unet3d_conv_gemm_smem_bytes": (C.c_size_t, [C.c_int] * 7),
     "unet3d_weight_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "unet3d_wgrad_gemm": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "unet3d_in_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_void_p]),

@@ -7,6 +7,7 @@
 
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -83,8 +84,8 @@ const char* unet3d_version(void) { return "unet3d_b200 0.1 (sm_100a)"; }
 const char* unet3d_last_error_string(void) { return g_err; }
 int unet3d_num_sms(void) { return num_sms(); }
 
-size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages) {
-  return conv_gemm_smem_bytes(Dt, G, nblk, fuse, wT, w_stages);
+size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages, int a_stages) {
+  return conv_gemm_smem_bytes(Dt, G, nblk, fuse, wT, w_stages, a_stages);
 }
 
 int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
@@ -118,12 +119,15 @@ int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
   p.nbuf = a->nbuf;
   p.wT = a->wT;
   p.w_stages = a->w_stages;
+  p.a_stages = a->a_stages;
+  p.dense = a->dense && !(getenv("U3D_NO_DENSE") != nullptr);
   p.in_f16 = a->in_f16;
   p.out_f16 = a->out_f16;
   p.out_sN = a->out_sN; p.out_sD = a->out_sD; p.out_sH = a->out_sH; p.out_sW = a->out_sW;
   p.out_C = a->out_C; p.stats_C = a->stats_C; p.omul = a->omul;
   p.zD = a->zD; p.zH = a->zH; p.zW = a->zW;
   p.act = a->act;
+  { const char* e = getenv("U3D_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.n_work = a->n_nblk * a->N * p.segs_d * p.tiles_h * p.tiles_w;
   return check(conv_gemm_launch(p, sms, reinterpret_cast<cudaStream_t>(stream)), "conv_gemm");
 }

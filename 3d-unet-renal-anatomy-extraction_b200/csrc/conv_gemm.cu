@@ -5,7 +5,7 @@
 //
 // Roles (warp-specialised, persistent over work items = (output tile, N block)):
 //   warp 0  : A producer  - TMA 5-D tiled loads of (18 x 10 voxel) x 8-channel boxes, OOB zero fill = padding
-//   warp 1  : W producer  - cp.async.bulk of pre-packed weight tiles, 6-deep ring
+//   warp 1  : W producer  - cp.async.bulk of pre-packed weight tiles, ring of up to 16 stages sized by the host plan
 //   warp 2  : MMA issuer  - tcgen05.mma kind::f16, M=128 (16h x 8w voxels), N=nblk, K=16; accumulators in TMEM,
 //             double buffered (2 x 256 columns) so the epilogue of item i overlaps the MMAs of item i+1
 //   warps 3-6: epilogue   - tcgen05.ld, + bias / + addend, zero planes, per-(n,c) sum / sum^2 for
@@ -17,7 +17,7 @@ namespace u3d {
 namespace {
 
 struct SmemCtl {
-  uint64_t a_full[2], a_empty[2];
+  uint64_t a_full[CG_A_STAGES], a_empty[CG_A_STAGES];
   uint64_t w_full[CG_W_STAGES], w_empty[CG_W_STAGES];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
@@ -116,6 +116,124 @@ __device__ __forceinline__ void issue_batch_dispatch(int Dt, int G2, uint32_t ma
 #undef U3D_CASE
 }
 
+
+// ---- dense fast path --------------------------------------------------------------------------------------------
+// Ordinary 3x3x3 stride-1 convolutions with d-tap fusion and every tap active (the layers that hold >90 % of the
+// FLOPs): the nine (kh,kw) taps, the planes and the K steps are unrolled at compile time with N block width NBLK a
+// template parameter, so every descriptor / TMEM address is `base + immediate` (2-3 uniform instructions per MMA).
+// The generic path pays ~45 instructions of mask / table / descriptor bookkeeping per tap on the single issuing
+// thread, which bounded the level-0/1 layers (ncu: MMA warp 62 % of its samples in issue code, tensor pipe 42 %).
+template <int DT, int G2, int NBLK>
+__device__ __forceinline__ void issue_tap_dense(uint32_t acc0, uint64_t aslab, uint64_t bdesc0, uint32_t idesc1,
+                                                uint32_t idesc2, uint32_t idesc3, const int t, const bool first) {
+  constexpr uint64_t A_DINC = (uint64_t)((2 * G2 * CG_CHUNK_PITCH) >> 4);
+  constexpr uint64_t A_KINC = (uint64_t)((2 * CG_CHUNK_PITCH) >> 4);
+  constexpr uint64_t B_KINC = (uint64_t)(2 * 3 * NBLK);
+  const uint64_t adesc0 = aslab + (uint64_t)((t / 3) * CG_WB + (t % 3));       // (kh * 10 + kw) * 16 B, in 16-B units
+  if (t == 0 && first) {
+    // first tap of an item: unfused, so that the first MMA into every accumulator overwrites it
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+#pragma unroll
+      for (int sd = 0; sd < 3; ++sd) {
+#pragma unroll
+        for (int kk = 0; kk < G2; ++kk)
+          tc_mma_bf16(acc0 + (uint32_t)(d * NBLK), adesc0 + (uint64_t)(d + sd) * A_DINC + kk * A_KINC,
+                      bdesc0 + (uint64_t)((2 - sd) * NBLK) + kk * B_KINC, idesc1, (sd | kk) ? 1u : 0u);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int pl = 0; pl < DT + 2; ++pl) {
+      const int hi = pl < 2 ? pl : 2;
+      const int lo = pl - DT + 1 > 0 ? pl - DT + 1 : 0;
+      const int cnt = hi - lo + 1;
+      const uint32_t id = cnt == 3 ? idesc3 : (cnt == 2 ? idesc2 : idesc1);
+#pragma unroll
+      for (int kk = 0; kk < G2; ++kk)
+        tc_mma_bf16(acc0 + (uint32_t)((pl - hi) * NBLK), adesc0 + (uint64_t)pl * A_DINC + kk * A_KINC,
+                    bdesc0 + (uint64_t)((2 - hi) * NBLK) + kk * B_KINC, id, 1u);
+    }
+  }
+}
+
+struct MmaRoleArgs {
+  SmemCtl* ctl;
+  uint32_t slab0, slab_bytes, wring0, wstage_bytes, wtile_bytes, tmem_base;
+  int n_tiles;
+};
+
+template <int DT, int G2, int NBLK>
+__device__ __noinline__ void mma_role_dense(const ConvGemmParams& p, const MmaRoleArgs r) {
+  SmemCtl* ctl = r.ctl;
+  volatile int* abort_flag = &ctl->abort_flag;
+  const uint32_t idesc1 = umma_idesc_bf16(128, NBLK, 0, 0, p.in_f16, p.in_f16);
+  const uint32_t idesc2 = umma_idesc_bf16(128, 2 * NBLK, 0, 0, p.in_f16, p.in_f16);
+  const uint32_t idesc3 = umma_idesc_bf16(128, 3 * NBLK, 0, 0, p.in_f16, p.in_f16);
+  const uint32_t a_stages = (uint32_t)p.a_stages, w_stages = (uint32_t)p.w_stages;
+  const int wT = p.wT, n_cg = p.n_cg;
+  const uint64_t wtile16 = (uint64_t)(r.wtile_bytes >> 4);
+  uint32_t a_it = 0, w_it = 0, acc_it = 0;
+  for (int item = blockIdx.x; item < p.n_work; item += gridDim.x) {
+    const uint32_t buf = p.nbuf == 2 ? (acc_it & 1) : 0u, aph = p.nbuf == 2 ? ((acc_it >> 1) & 1) : (acc_it & 1);
+    if (!mbar_wait(smem_u32(&ctl->acc_empty[buf]), aph ^ 1, abort_flag, p.err, 103)) return;
+    tc_fence_after();
+    const uint32_t acc0 = r.tmem_base + buf * 256;
+    for (int cg = 0; cg < n_cg; ++cg) {
+      const uint32_t ast = a_it % a_stages, aphase = (a_it / a_stages) & 1;
+      if (!mbar_wait(smem_u32(&ctl->a_full[ast]), aphase, abort_flag, p.err, 104)) return;
+      tc_fence_after();
+      const uint64_t aslab = umma_desc(r.slab0 + ast * r.slab_bytes, CG_CHUNK_PITCH, CG_WB * 16);
+      uint64_t bdesc = 0;
+      uint32_t wst = 0;
+      int in_batch = 0;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (in_batch == 0) {
+          wst = w_it % w_stages;
+          if (!mbar_wait(smem_u32(&ctl->w_full[wst]), (w_it / w_stages) & 1, abort_flag, p.err, 105)) return;
+          tc_fence_after();
+          bdesc = umma_desc(r.wring0 + wst * r.wstage_bytes, 3 * NBLK * 16, 128);
+        }
+        ++in_batch;
+        const bool last = in_batch == wT || t == 8;
+        if (elect_one()) {
+          issue_tap_dense<DT, G2, NBLK>(acc0, aslab, bdesc, idesc1, idesc2, idesc3, t, cg == 0);
+          if (last) tc_commit(smem_u32(&ctl->w_empty[wst]));
+        }
+        __syncwarp();
+        bdesc += wtile16;
+        if (last) {
+          ++w_it;
+          in_batch = 0;
+        }
+      }
+      if (elect_one()) tc_commit(smem_u32(&ctl->a_empty[ast]));
+      __syncwarp();
+      ++a_it;
+    }
+    if (elect_one()) tc_commit(smem_u32(&ctl->acc_full[buf]));
+    __syncwarp();
+    ++acc_it;
+  }
+}
+
+__device__ __forceinline__ bool mma_role_dense_dispatch(const ConvGemmParams& p, const MmaRoleArgs& r) {
+  const int G2 = p.G / 2;
+#define U3D_DENSE(DT, GG, NB)                              \
+  if (p.Dt == DT && G2 == GG && p.nblk == NB) {            \
+    mma_role_dense<DT, GG, NB>(p, r);                      \
+    return true;                                           \
+  }
+#define U3D_DENSE_G(DT, NB) U3D_DENSE(DT, 1, NB) U3D_DENSE(DT, 2, NB) U3D_DENSE(DT, 3, NB)
+  U3D_DENSE_G(8, 32) U3D_DENSE_G(4, 32) U3D_DENSE_G(2, 32) U3D_DENSE_G(1, 32)
+  U3D_DENSE_G(4, 64) U3D_DENSE_G(2, 64) U3D_DENSE_G(1, 64)
+  U3D_DENSE(8, 1, 64) U3D_DENSE(8, 2, 64) U3D_DENSE(8, 3, 64)
+#undef U3D_DENSE_G
+#undef U3D_DENSE
+  return false;
+}
+
 __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -133,7 +251,8 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   const uint32_t w_stages = (uint32_t)p.w_stages;
   const uint32_t wstage_bytes = (uint32_t)wT * wtile_bytes;
   const uint32_t slab0 = smem_u32(smem) + 1024;
-  const uint32_t wring0 = slab0 + 2 * slab_bytes;
+  const uint32_t a_stages = (uint32_t)p.a_stages;
+  const uint32_t wring0 = slab0 + a_stages * slab_bytes;
 
   const int* tab_map = p.tab;
   const int* tab_ch = p.tab + p.n_cg;
@@ -144,11 +263,13 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   const int* tab_ooff = tab_coff + p.n_nblk;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < CG_A_STAGES; ++i) {
       mbar_init(smem_u32(&ctl->a_full[i]), 1);
       mbar_init(smem_u32(&ctl->a_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ctl->acc_full[i]), 1);
-      mbar_init(smem_u32(&ctl->acc_empty[i]), 4);
+      mbar_init(smem_u32(&ctl->acc_empty[i]), CG_EPI_WARPS);
     }
     for (int i = 0; i < CG_W_STAGES; ++i) {
       mbar_init(smem_u32(&ctl->w_full[i]), 1);
@@ -195,16 +316,17 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
       const int w0 = tw * CG_WT - 1, h0 = th * CG_HT - 1, d0 = seg * Dt - 1;
       for (int cg = 0; cg < n_cg; ++cg) {
         if (__ldg(&tab_mask[nb * n_cg + cg]) == 0) continue;
-        const uint32_t st = a_it & 1, ph = (a_it >> 1) & 1;
+        const uint32_t st = a_it % a_stages, ph = (a_it / a_stages) & 1;
         if (!mbar_wait(smem_u32(&ctl->a_empty[st]), ph ^ 1, abort_flag, p.err, 101)) { ok = false; break; }
         const uint32_t full = smem_u32(&ctl->a_full[st]);
         const CUtensorMap* m = &p.amap[__ldg(&tab_map[cg])];
         const int ch0 = __ldg(&tab_ch[cg]);
         if (elect_one()) {
-          mbar_expect_tx(full, (uint32_t)planes_i * G * CG_BOX_BYTES);
+          const int gl = (p.dbg & 1) ? 1 : G;
+          mbar_expect_tx(full, (uint32_t)planes_i * gl * CG_BOX_BYTES);
           uint32_t dst = slab0 + st * slab_bytes;
-          for (int pl = 0; pl < planes_i; ++pl)
-            for (int g = 0; g < G; ++g, dst += CG_CHUNK_PITCH)
+          for (int pl = 0; pl < planes_i; ++pl, dst += (G - gl) * CG_CHUNK_PITCH)
+            for (int g = 0; g < gl; ++g, dst += CG_CHUNK_PITCH)
               tma_load_5d(dst, m, full, ch0 + g * 8, w0, h0, d0 + pl, n);
         }
         __syncwarp();
@@ -238,6 +360,15 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
     }
   } else if (warp == 2) {
     // ================= MMA issuer =================
+    if (p.dense) {
+      MmaRoleArgs r;
+      r.ctl = ctl; r.slab0 = slab0; r.slab_bytes = slab_bytes; r.wring0 = wring0; r.wstage_bytes = wstage_bytes;
+      r.wtile_bytes = wtile_bytes; r.tmem_base = tmem_base; r.n_tiles = n_tiles;
+      if (!mma_role_dense_dispatch(p, r) && lane == 0) {       // the host never sets `dense` for other shapes
+        ctl->abort_flag = 1;
+        atomicCAS(p.err, 0, 107);
+      }
+    } else {
     const uint32_t idesc = umma_idesc_bf16(128, nblk, 0, 0, p.in_f16, p.in_f16);
     const uint32_t idesc2 = umma_idesc_bf16(128, 2 * nblk, 0, 0, p.in_f16, p.in_f16),
                    idesc3 = umma_idesc_bf16(128, 3 * nblk, 0, 0, p.in_f16, p.in_f16);
@@ -257,7 +388,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
       for (int cg = 0; cg < n_cg && ok; ++cg) {
         uint32_t mask = (uint32_t)__ldg(&tab_mask[nb * n_cg + cg]);
         if (mask == 0) continue;
-        const uint32_t ast = a_it & 1, aphase = (a_it >> 1) & 1;
+        const uint32_t ast = a_it % a_stages, aphase = (a_it / a_stages) & 1;
         if (!mbar_wait(smem_u32(&ctl->a_full[ast]), aphase, abort_flag, p.err, 104)) { ok = false; break; }
         tc_fence_after();
         const uint32_t slab = slab0 + ast * slab_bytes;
@@ -293,18 +424,23 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
       __syncwarp();
       ++acc_it;
     }
+    }
   } else {
     // ================= epilogue (warps 3..6) =================
+    // CG_EPI_WARPS / 4 warps per TMEM lane quarter; the (channel block, plane) units of an item alternate between them.
+    // (Measured: 8 epilogue warps are slower than 4 -- they take issue slots from the MMA warp, the critical role.)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 3) >> 2;       // which of the quarter's warps (always 0 with 4 epilogue warps)
     const int row = q * 32 + lane;
     const int line = row >> 3, wi = row & 7;
     const int n_cc = p.nblk / 32;
     const int of16 = p.out_f16;
+    const bool do_stats = p.stats != nullptr && !(p.dbg & 2);
     float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
     int cur_n = -1, cur_nb = -1;
     uint32_t acc_it = 0;
     auto flush_stats = [&]() {
-      if (p.stats == nullptr || cur_n < 0) return;
+      if (!do_stats || cur_n < 0) return;
       const int coff = __ldg(&tab_coff[cur_nb]) & 0x3fffffff;
       for (int cc = 0; cc < n_cc; ++cc) {
         const int c = coff + cc * 32 + lane;
@@ -340,14 +476,26 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
       const int gh = th * CG_HT + line, gw = tw * CG_WT + wi;
       const int oh = gh * p.omul + ((ooff >> 8) & 0xff), ow = gw * p.omul + ((ooff >> 16) & 0xff);
       const bool hw_ok = gh < p.H && gw < p.W;
-      for (int d = 0; d < p.Dt; ++d) {
-        const int gd = seg * p.Dt + d;
-        const int od = gd * p.omul + (ooff & 0xff);
-        const bool valid = hw_ok && gd < p.D;
-        const bool zero = (od == p.zD) || (oh == p.zH) || (ow == p.zW);
-        const long long off = (long long)n * p.out_sN + (long long)od * p.out_sD + (long long)oh * p.out_sH +
-                              (long long)ow * p.out_sW + coff;
-        for (int cc = 0; cc < n_cc; ++cc) {
+      for (int cc = 0; cc < n_cc; ++cc) {
+        // per-thread partial sums of this warp's planes; ONE cross-lane reduction per (item, cc) instead of per plane
+        float a1[32], a2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a1[j] = a2[j] = 0.f;
+        bool any = false;
+        const int c0 = coff + cc * 32;
+        float bias_v[32];
+        if (p.bias != nullptr) {
+          const float* b = p.bias + nb * p.nblk + cc * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bias_v[j] = __ldg(&b[j]);
+        }
+        for (int d = (CG_EPI_WARPS == 8 ? ((cc * p.Dt + half) & 1) : 0); d < p.Dt; d += CG_EPI_WARPS / 4) {
+          const int gd = seg * p.Dt + d;
+          const int od = gd * p.omul + (ooff & 0xff);
+          const bool valid = hw_ok && gd < p.D;
+          const bool zero = (od == p.zD) || (oh == p.zH) || (ow == p.zW);
+          const long long off = (long long)n * p.out_sN + (long long)od * p.out_sD + (long long)oh * p.out_sH +
+                                (long long)ow * p.out_sW + coff;
           uint32_t raw[32];
           __syncwarp();
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)d * p.nblk + cc * 32, raw);
@@ -356,11 +504,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           if (p.bias != nullptr) {
-            const float* b = p.bias + nb * p.nblk + cc * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(&b[j]);
+            for (int j = 0; j < 32; ++j) v[j] += bias_v[j];
           }
-          const int c0 = coff + cc * 32;
           if (addp != nullptr && valid) {
             const uint4* ap = reinterpret_cast<const uint4*>(addp + off + cc * 32);
 #pragma unroll
@@ -383,7 +529,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (valid) {
+          if (valid && !(p.dbg & 4)) {
             uint4* op = reinterpret_cast<uint4*>(outp + off + cc * 32);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
@@ -397,13 +543,18 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
               }
             }
           }
-          if (p.stats != nullptr) {
-            float sq[32];
+          if (do_stats) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-            ssum[cc] += warp_colsum32(v, lane);
-            ssq[cc] += warp_colsum32(sq, lane);
+            for (int j = 0; j < 32; ++j) {
+              a1[j] += v[j];
+              a2[j] = fmaf(v[j], v[j], a2[j]);
+            }
+            any = true;
           }
+        }
+        if (do_stats && any) {              // `any` is warp-uniform
+          ssum[cc] += warp_colsum32(a1, lane);
+          ssq[cc] += warp_colsum32(a2, lane);
         }
       }
       tc_fence_before();
@@ -424,8 +575,8 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
 
 }  // namespace
 
-size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages) {
-  return 1024 /*align slack*/ + 1024 /*ctl*/ + 2 * (size_t)(Dt + 2) * G * CG_CHUNK_PITCH +
+size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages, int a_stages) {
+  return 1024 /*align slack*/ + 1024 /*ctl*/ + (size_t)a_stages * (Dt + 2) * G * CG_CHUNK_PITCH +
          (size_t)w_stages * wT * G * fuse * nblk * 16;
 }
 
@@ -434,8 +585,9 @@ int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
       p.Dt * p.nblk * p.nbuf > 512 ||
       p.n_taps < 1 || p.n_taps > 32 || p.n_work < 1 || (p.Dt != 1 && p.Dt != 2 && p.Dt != 4 && p.Dt != 8) || p.G > 6 || (p.fuse != 1 && p.fuse != 3) || p.fuse * p.nblk > 256)
     return U3D_ERR_INVALID;
-  if (p.wT < 1 || p.wT > 32 || p.w_stages < 2 || p.w_stages > CG_W_STAGES) return U3D_ERR_INVALID;
-  const size_t smem = conv_gemm_smem_bytes(p.Dt, p.G, p.nblk, p.fuse, p.wT, p.w_stages);
+  if (p.wT < 1 || p.wT > 32 || p.w_stages < 2 || p.w_stages > CG_W_STAGES || p.a_stages < 2 || p.a_stages > CG_A_STAGES)
+    return U3D_ERR_INVALID;
+  const size_t smem = conv_gemm_smem_bytes(p.Dt, p.G, p.nblk, p.fuse, p.wT, p.w_stages, p.a_stages);
   if (smem > 227 * 1024) return U3D_ERR_INVALID;
   static bool attr_set = false;
   if (!attr_set) {

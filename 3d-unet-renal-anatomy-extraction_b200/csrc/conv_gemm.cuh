@@ -21,8 +21,10 @@ constexpr int CG_HB = CG_HT + 2;     // brick with a 1-voxel halo on both sides
 constexpr int CG_WB = CG_WT + 2;
 constexpr int CG_BOX_BYTES = CG_HB * CG_WB * 16;     // one (plane, 8-channel chunk) TMA box = 2880 B
 constexpr int CG_CHUNK_PITCH = 2944;                 // padded to 128 B (TMA smem destination alignment)
-constexpr int CG_W_STAGES = 6;
-constexpr int CG_THREADS = 224;      // warp0 A-TMA, warp1 W-TMA, warp2 MMA (+TMEM alloc), warps 3-6 epilogue
+constexpr int CG_W_STAGES = 16;
+constexpr int CG_A_STAGES = 4;       // at most this many A slabs in flight
+constexpr int CG_EPI_WARPS = 4;      // 4 or 8
+constexpr int CG_THREADS = 96 + 32 * CG_EPI_WARPS;      // warp0 A-TMA, warp1 W-TMA, warp2 MMA (+TMEM alloc), then the epilogue warps
 constexpr int CG_MAX_MAPS = 8;
 
 struct ConvGemmParams {
@@ -49,7 +51,8 @@ struct ConvGemmParams {
   int n_nblk, nblk;       // nblk in {32, 64, 96, 128}; Dt * nblk <= 256
   int G, n_cg, n_taps;    // G chunks (of 8 channels) per cgroup, G even
   int in_f16, out_f16;    // 16-bit storage of A / weights and of out / addend: 0 = bf16, 1 = fp16
-  int wT, w_stages;       // weight ring: taps per stage (their tiles are contiguous) and ring depth (2..6)
+  int wT, w_stages;       // weight ring: taps per stage (their tiles are contiguous) and ring depth (2..16)
+  int a_stages;           // A slabs (channel groups) in flight: 2..4
   int nbuf;               // TMEM accumulator buffers: 2 (Dt*nblk <= 256, epilogue overlaps next item) or 1 (<= 512)
   int fuse;               // 1, or 3: a weight tile holds the d-taps 2,1,0 of one (kh,kw) and taps carry sd = 0
   long long out_sN, out_sD, out_sH, out_sW;   // element strides of out / addend
@@ -58,10 +61,12 @@ struct ConvGemmParams {
   int omul;               // output coordinate = tile-grid coordinate * omul + offset(nblock)
   int zD, zH, zW;         // output planes forced to zero (ConvTranspose3d + ConstantPad3d), or -1
   int act;                // 0 none, 1 LeakyReLU(0.01) applied after bias / addend
+  int dense;              // 1: fuse == 3, n_taps == 9 in (kh,kw) order, every tap of every (N block, group) active
   int n_work;
+  int dbg;                // timing experiments only (env U3D_DBG): 1 = load only chunk 0 of every A group, 2 = no statistics, 4 = no stores
 };
 
-size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages);
+size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages, int a_stages);
 int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 
 }  // namespace u3d

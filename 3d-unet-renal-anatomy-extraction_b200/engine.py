@@ -64,6 +64,7 @@ class UNetEngine:
         self.num_sms = 148
         self._ops: Dict[Tuple, _ConvOp] = {}
         self._inv_scale = None
+        self._last_was_train = True      # the first forward always packs
 
     # ------------------------------------------------------------------ public entry
     def run(self, x: torch.Tensor) -> torch.Tensor:
@@ -86,6 +87,9 @@ class UNetEngine:
             self._ops = {}
         params = list(net.parameters())
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if need_grad or self._last_was_train:
+            ops.PACK_EPOCH += 1          # an optimizer step may lie behind us: re-pack the weights (see ops.PACK_EPOCH)
+        self._last_was_train = need_grad
         if need_grad:
             return _UNetFn.apply(x, self, *params)
         with torch.no_grad():

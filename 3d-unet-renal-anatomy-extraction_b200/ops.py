@@ -17,10 +17,16 @@ from . import plan as P
 
 _err_words: Dict[int, torch.Tensor] = {}
 
-# bench.py instrumentation: when PROFILE is a list, the tensor-core launches append
-# (kernel name, algorithmic FLOPs, start event, end event); LAUNCHES counts every kernel enqueued.
+# bench.py instrumentation: when PROFILE is a list, every launch of the library appends
+# (kernel name, algorithmic FLOPs, start event, end event, algorithmic HBM bytes); LAUNCHES counts every kernel enqueued.
 PROFILE = None
 LAUNCHES = 0
+
+# Packed-weight caches are keyed by (address, tensor version, dtype, PACK_EPOCH).  The version counter alone is NOT
+# enough: fused optimizers (torch.optim.Adam(fused=True)) update parameters without bumping it.  The engine bumps
+# PACK_EPOCH at every training-mode forward and at the first no-grad forward after one, so a pack is reused only
+# across forwards between which no optimizer step can have happened (e.g. the windows of one inference volume).
+PACK_EPOCH = 0
 
 
 def _count(n: int = 1):
@@ -29,8 +35,8 @@ def _count(n: int = 1):
 
 
 class _Timed:
-    def __init__(self, name, flops):
-        self.name, self.flops = name, flops
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
 
     def __enter__(self):
         if PROFILE is not None:
@@ -41,7 +47,7 @@ class _Timed:
         if PROFILE is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.name, self.flops, self.e0, e1))
+            PROFILE.append((self.name, self.flops, self.e0, e1, self.nbytes))
 
 
 def _stream() -> int:
@@ -111,13 +117,13 @@ class DeviceConvPlan:
         `w` may be a list of parameters: the plan's gather index then addresses their concatenation.
         `key`: cache key to use when `w` is a temporary derived from parameters (its own address means nothing)."""
         if isinstance(w, (list, tuple)):
-            key = tuple((t.data_ptr(), t._version) for t in w) + (dtype,)
+            key = tuple((t.data_ptr(), t._version) for t in w) + (dtype, PACK_EPOCH)
             if self._w_version == key and not torch.cuda.is_current_stream_capturing():
                 return self._w_packed
             packed = self.packed_weight(torch.cat([t.detach().reshape(-1).float() for t in w]), dtype)
             self._w_version = key
             return packed
-        key = (w.data_ptr(), w._version, dtype) if key is None else key
+        key = (w.data_ptr(), w._version, dtype, PACK_EPOCH) if key is None else tuple(key) + (PACK_EPOCH,)
         if self._w_version != key or torch.cuda.is_current_stream_capturing():   # a graph must re-pack on every replay
             src = w.detach()
             if src.dtype != torch.float32 or not src.is_contiguous():
@@ -133,7 +139,7 @@ class DeviceConvPlan:
     def packed_bias(self, b: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         if b is None:
             return None
-        key = (b.data_ptr(), b._version)
+        key = (b.data_ptr(), b._version, PACK_EPOCH)
         if self._b_version != key or torch.cuda.is_current_stream_capturing():
             flat = torch.cat([b.detach().reshape(-1).float(), b.new_zeros(1, dtype=torch.float32)])
             self._b_packed = flat.index_select(0, self.bidx).contiguous()
@@ -171,7 +177,7 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.Dt, a.n_nblk, a.nblk, a.G, a.n_cg, a.n_taps = pl.Dt, pl.n_nblk, pl.nblk, pl.G, pl.n_cg, len(pl.shifts)
     a.fuse = 3 if pl.fuse_kd else 1
     a.nbuf = pl.nbuf
-    a.wT, a.w_stages = pl.wT, pl.w_stages
+    a.wT, a.w_stages, a.a_stages = pl.wT, pl.w_stages, pl.a_stages
     a.in_f16, a.out_f16 = _f16(inputs[0]), _f16(o0)
     n, d, h, w, cp = o0.shape
     a.out_sW, a.out_sH, a.out_sD, a.out_sN = cp, w * cp, h * w * cp, d * h * w * cp
@@ -180,6 +186,7 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.omul = pl.omul
     a.zD, a.zH, a.zW = (d - 1, h - 1, w - 1) if zero_last else (-1, -1, -1)
     a.act = act
+    a.dense = int(pl.dense)
     flops = pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3]
     _count()
     with _Timed("conv_gemm_kernel", flops):
@@ -225,40 +232,45 @@ def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, t
     n, d, h, w, cp = y.shape
     _count()
     assert out.dtype == y.dtype and (skip is None or skip.dtype == y.dtype)
-    _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), n, d * h * w, cp,
-                                          _f16(y), _stream()), "unet3d_in_apply")
+    with _Timed("in_apply", 0.0, y.numel() * 2.0 * (3 if skip is not None else 2)):
+        _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), n, d * h * w, cp,
+                                              _f16(y), _stream()), "unet3d_in_apply")
 
 
 def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
     n, d, h, w, cp = y.shape
     _count()
     assert dout.dtype == y.dtype and g.dtype == y.dtype and out.dtype == y.dtype
-    _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), out.data_ptr(), y.data_ptr(), g.data_ptr(),
-                                               table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
-               "unet3d_in_bwd_reduce")
+    with _Timed("in_bwd_reduce", 0.0, y.numel() * 2.0 * (5 if dout2 is not None else 4)):
+        _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), out.data_ptr(), y.data_ptr(), g.data_ptr(),
+                                                   table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
+                   "unet3d_in_bwd_reduce")
 
 
 def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False):
     n, d, h, w, cp = y.shape
     _count()
     assert g.dtype == y.dtype and dy.dtype == y.dtype
-    _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
-                                              _ptr(dsum), n, d, h, w, cp, int(zero_last), _f16(y), _stream()),
-               "unet3d_in_bwd_apply")
+    with _Timed("in_bwd_apply", 0.0, y.numel() * 2.0 * 3):
+        _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
+                                                  _ptr(dsum), n, d, h, w, cp, int(zero_last), _f16(y), _stream()),
+                   "unet3d_in_bwd_apply")
 
 
 def channel_sum(x: torch.Tensor, dsum: torch.Tensor):
     n, d, h, w, cp = x.shape
     _count()
-    _lib.check(_lib.lib().unet3d_channel_sum(x.data_ptr(), dsum.data_ptr(), n * d * h * w, cp, _stream()),
-               "unet3d_channel_sum")
+    with _Timed("channel_sum", 0.0, x.numel() * 2.0):
+        _lib.check(_lib.lib().unet3d_channel_sum(x.data_ptr(), dsum.data_ptr(), n * d * h * w, cp, _stream()),
+                   "unet3d_channel_sum")
 
 
 def att_gate_fwd(xs: torch.Tensor, z: torch.Tensor, out: torch.Tensor):
     assert xs.dtype in ACT_DTYPES and z.dtype == xs.dtype and out.dtype == xs.dtype and xs.shape == z.shape == out.shape
     _count()
-    _lib.check(_lib.lib().unet3d_att_gate_fwd(xs.data_ptr(), z.data_ptr(), out.data_ptr(), xs.numel(), _f16(xs), _stream()),
-               "unet3d_att_gate_fwd")
+    with _Timed("att_gate_fwd", 0.0, xs.numel() * 6.0):
+        _lib.check(_lib.lib().unet3d_att_gate_fwd(xs.data_ptr(), z.data_ptr(), out.data_ptr(), xs.numel(), _f16(xs), _stream()),
+                   "unet3d_att_gate_fwd")
 
 
 def att_gate_bwd(dout, xs, z, dxs, dz, sums):
@@ -266,8 +278,9 @@ def att_gate_bwd(dout, xs, z, dxs, dz, sums):
     assert all(t.dtype == xs.dtype and t.shape == xs.shape for t in (dout, z, dxs, dz))
     assert sums.dtype == torch.float64 and sums.numel() == 2 * cp
     _count()
-    _lib.check(_lib.lib().unet3d_att_gate_bwd(dout.data_ptr(), xs.data_ptr(), z.data_ptr(), dxs.data_ptr(), dz.data_ptr(),
-                                              sums.data_ptr(), n * d * h * w, cp, _f16(xs), _stream()), "unet3d_att_gate_bwd")
+    with _Timed("att_gate_bwd", 0.0, xs.numel() * 10.0):
+        _lib.check(_lib.lib().unet3d_att_gate_bwd(dout.data_ptr(), xs.data_ptr(), z.data_ptr(), dxs.data_ptr(), dz.data_ptr(),
+                                                  sums.data_ptr(), n * d * h * w, cp, _f16(xs), _stream()), "unet3d_att_gate_bwd")
 
 
 def att_mid_bwd(df, f, dxs, dpre, t, ssum):
@@ -275,8 +288,9 @@ def att_mid_bwd(df, f, dxs, dpre, t, ssum):
     assert all(x.dtype == f.dtype and x.shape == f.shape for x in (df, dxs, dpre, t))
     assert ssum.dtype == torch.float64 and ssum.numel() == cp
     _count()
-    _lib.check(_lib.lib().unet3d_att_mid_bwd(df.data_ptr(), f.data_ptr(), dxs.data_ptr(), dpre.data_ptr(), t.data_ptr(),
-                                             ssum.data_ptr(), n * d * h * w, cp, _f16(f), _stream()), "unet3d_att_mid_bwd")
+    with _Timed("att_mid_bwd", 0.0, f.numel() * 10.0):
+        _lib.check(_lib.lib().unet3d_att_mid_bwd(df.data_ptr(), f.data_ptr(), dxs.data_ptr(), dpre.data_ptr(), t.data_ptr(),
+                                                 ssum.data_ptr(), n * d * h * w, cp, _f16(f), _stream()), "unet3d_att_mid_bwd")
 
 
 def maxpool_fwd(x: torch.Tensor, out: torch.Tensor, code: torch.Tensor):
@@ -285,16 +299,18 @@ def maxpool_fwd(x: torch.Tensor, out: torch.Tensor, code: torch.Tensor):
     assert x.dtype in ACT_DTYPES and out.dtype == x.dtype and code.dtype == torch.uint8
     assert tuple(out.shape) == (n, d // 2, h // 2, w // 2, cp) and code.shape == out.shape
     _count()
-    _lib.check(_lib.lib().unet3d_maxpool3d_fwd(x.data_ptr(), out.data_ptr(), code.data_ptr(), n, d, h, w, cp, _f16(x),
-                                               _stream()), "unet3d_maxpool3d_fwd")
+    with _Timed("maxpool_fwd", 0.0, x.numel() * 2.0 + out.numel() * 3.0):
+        _lib.check(_lib.lib().unet3d_maxpool3d_fwd(x.data_ptr(), out.data_ptr(), code.data_ptr(), n, d, h, w, cp, _f16(x),
+                                                   _stream()), "unet3d_maxpool3d_fwd")
 
 
 def maxpool_bwd(dout: torch.Tensor, code: torch.Tensor, dx: torch.Tensor):
     n, d, h, w, cp = dx.shape
     assert dout.dtype == dx.dtype and code.dtype == torch.uint8 and code.shape == dout.shape
     _count()
-    _lib.check(_lib.lib().unet3d_maxpool3d_bwd(dout.data_ptr(), code.data_ptr(), dx.data_ptr(), n, d, h, w, cp, _stream()),
-               "unet3d_maxpool3d_bwd")
+    with _Timed("maxpool_bwd", 0.0, dx.numel() * 2.0 + dout.numel() * 3.0):
+        _lib.check(_lib.lib().unet3d_maxpool3d_bwd(dout.data_ptr(), code.data_ptr(), dx.data_ptr(), n, d, h, w, cp, _stream()),
+                   "unet3d_maxpool3d_bwd")
 
 
 def maxpool_flat_index(code: torch.Tensor, c: int) -> torch.Tensor:
@@ -311,23 +327,26 @@ def maxpool_flat_index(code: torch.Tensor, c: int) -> torch.Tensor:
 def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
     n, d, h, ww, cp = out.shape
     _count()
-    _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, d, h, ww, cp,
-                                          _f16(out), _stream()), "unet3d_stem_fwd")
+    with _Timed("stem_fwd", 0.0, x.numel() * 4.0 + out.numel() * 2.0):
+        _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, d, h, ww, cp,
+                                              _f16(out), _stream()), "unet3d_stem_fwd")
 
 
 def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
     n, d, h, ww, cp = dy.shape
     _count()
-    _lib.check(_lib.lib().unet3d_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), n, d, h, ww, cp, _f16(dy),
-                                            _stream()), "unet3d_stem_wgrad")
+    with _Timed("stem_wgrad", 0.0, x.numel() * 4.0 + dy.numel() * 2.0):
+        _lib.check(_lib.lib().unet3d_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), n, d, h, ww, cp, _f16(dy),
+                                                _stream()), "unet3d_stem_wgrad")
 
 
 def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Tensor):
     n, d, h, ww, cp = a.shape
     k = logits.shape[1]
     _count()
-    _lib.check(_lib.lib().unet3d_head_fwd(a.data_ptr(), w.data_ptr(), b.data_ptr(), logits.data_ptr(), k, n, d * h * ww,
-                                          cp, _f16(a), _stream()), "unet3d_head_fwd")
+    with _Timed("head_fwd", 0.0, a.numel() * 2.0 + logits.numel() * 4.0):
+        _lib.check(_lib.lib().unet3d_head_fwd(a.data_ptr(), w.data_ptr(), b.data_ptr(), logits.data_ptr(), k, n, d * h * ww,
+                                              cp, _f16(a), _stream()), "unet3d_head_fwd")
 
 
 def head_bwd(dl: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tensor, dw: torch.Tensor,
@@ -336,38 +355,43 @@ def head_bwd(dl: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tenso
     k = dl.shape[1]
     _count()
     assert da.dtype == a.dtype
-    _lib.check(_lib.lib().unet3d_head_bwd(dl.data_ptr(), a.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(),
-                                          _ptr(grad_scale), k, n, d * h * ww, cp, _f16(a), _stream()), "unet3d_head_bwd")
+    with _Timed("head_bwd", 0.0, dl.numel() * 4.0 + a.numel() * 4.0):
+        _lib.check(_lib.lib().unet3d_head_bwd(dl.data_ptr(), a.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(),
+                                              _ptr(grad_scale), k, n, d * h * ww, cp, _f16(a), _stream()), "unet3d_head_bwd")
 
 
 def loss_fwd(logits, target, sums, gamma):
     n, k = logits.shape[:2]
     v = logits[0, 0].numel()
     _count()
-    _lib.check(_lib.lib().unet3d_loss_fwd(logits.data_ptr(), target.data_ptr(), sums.data_ptr(), k, n, v, float(gamma),
-                                          _stream()), "unet3d_loss_fwd")
+    with _Timed("loss_fwd", 0.0, logits.numel() * 4.0 + target.numel() * 8.0):
+        _lib.check(_lib.lib().unet3d_loss_fwd(logits.data_ptr(), target.data_ptr(), sums.data_ptr(), k, n, v, float(gamma),
+                                              _stream()), "unet3d_loss_fwd")
 
 
 def loss_bwd(logits, target, coef, gscale, dlogits, gamma, use_focal):
     n, k = logits.shape[:2]
     v = logits[0, 0].numel()
     _count()
-    _lib.check(_lib.lib().unet3d_loss_bwd(logits.data_ptr(), target.data_ptr(), coef.data_ptr(), _ptr(gscale),
-                                          dlogits.data_ptr(), k, n, v, float(gamma), int(use_focal), _stream()),
-               "unet3d_loss_bwd")
+    with _Timed("loss_bwd", 0.0, logits.numel() * 8.0 + target.numel() * 8.0):
+        _lib.check(_lib.lib().unet3d_loss_bwd(logits.data_ptr(), target.data_ptr(), coef.data_ptr(), _ptr(gscale),
+                                              dlogits.data_ptr(), k, n, v, float(gamma), int(use_focal), _stream()),
+                   "unet3d_loss_bwd")
 
 
 def sw_accumulate(logits, window, result, weight, origin):
     k, px, py, pz = logits.shape[-4:]
     _, X, Y, Z = result.shape
     _count()
-    _lib.check(_lib.lib().unet3d_sw_accumulate(logits.data_ptr(), _ptr(window), result.data_ptr(), weight.data_ptr(), k,
-                                               px, py, pz, origin[0], origin[1], origin[2], X, Y, Z, _stream()),
-               "unet3d_sw_accumulate")
+    with _Timed("sw_accumulate", 0.0, px * py * pz * (12.0 * k + 8.0 + (4.0 if window is not None else 0.0))):
+        _lib.check(_lib.lib().unet3d_sw_accumulate(logits.data_ptr(), _ptr(window), result.data_ptr(), weight.data_ptr(), k,
+                                                   px, py, pz, origin[0], origin[1], origin[2], X, Y, Z, _stream()),
+                   "unet3d_sw_accumulate")
 
 
 def sw_finalize(result, weight, labels, probs):
     k = result.shape[0]
     _count()
-    _lib.check(_lib.lib().unet3d_sw_finalize(result.data_ptr(), weight.data_ptr(), _ptr(labels), _ptr(probs), k,
-                                             weight.numel(), _stream()), "unet3d_sw_finalize")
+    with _Timed("sw_finalize", 0.0, weight.numel() * (4.0 * k + 4.0 + (1.0 if labels is not None else 0.0) + (4.0 * k if probs is not None else 0.0))):
+        _lib.check(_lib.lib().unet3d_sw_finalize(result.data_ptr(), weight.data_ptr(), _ptr(labels), _ptr(probs), k,
+                                                 weight.numel(), _stream()), "unet3d_sw_finalize")

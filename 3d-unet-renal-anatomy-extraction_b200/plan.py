@@ -15,6 +15,7 @@ plan with torch CPU ops).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -22,7 +23,7 @@ import numpy as np
 
 HT, WT = 16, 8                 # output tile (rows of one UMMA): 16 x 8 voxels
 CHUNK_PITCH = 2944
-W_STAGES = 6
+W_STAGES = 16
 FUSE_KD = True                 # fuse the three d-taps of a (kh,kw) into one wider UMMA where N <= 64
 SMEM_LIMIT = 227 * 1024
 
@@ -32,19 +33,37 @@ def pad_channels(c: int) -> int:
     return (c + 15) // 16 * 16
 
 
-def weight_ring(g: int, nblk: int, fuse: int, n_taps: int = 27) -> Tuple[int, int]:
+def a_slabs(dt: int, g: int) -> int:
+    """A slabs (channel groups) in flight: 2.  The kernel supports up to 4 (env U3D_A_STAGES, for sweeps); measured at
+    cfg-2 (gpurun_out, sweep with 2/3/4 slabs) a third slab never helps and costs weight-ring space: the A loads are
+    not what the MMA warp waits for."""
+    forced = os.environ.get("U3D_A_STAGES")
+    slab = (dt + 2) * g * CHUNK_PITCH
+    n = int(forced) if forced else 2
+    return max(2, min(4, n, (SMEM_LIMIT - 2048 - 16384) // slab))
+
+
+def weight_ring(dt: int, g: int, nblk: int, fuse: int, n_taps: int = 27) -> Tuple[int, int]:
     """(taps per stage, stages) of the weight ring: batch small tiles up to ~28 KB per stage (one barrier round trip
-    and one issue dispatch per batch), keep the ring within ~56 KB."""
+    and one issue dispatch per batch), ring of ~56 KB when the A slabs leave that much.  Measured (gpurun_out/
+    layers6.log): smaller batches in a deeper ring (16 KB x 7..11 stages) are SLOWER on every layer (L0 +6 %, L4 +30 %):
+    the per-batch cost on the single MMA-issuing thread outweighs the extra latency cover."""
     tile = g * fuse * nblk * 16
     taps = max(1, -(-n_taps // fuse))
+    avail = SMEM_LIMIT - 2048 - a_slabs(dt, g) * (dt + 2) * g * CHUNK_PITCH
     wt = max(1, min(taps, 16, 28672 // tile))
-    stages = max(2, min(W_STAGES, 57344 // (wt * tile)))
+    while wt > 1 and avail // (wt * tile) < 2:
+        wt -= 1
+    stages = min(W_STAGES, max(2, 57344 // (wt * tile)), avail // (wt * tile))
     return wt, stages
 
 
 def conv_smem_bytes(dt: int, g: int, nblk: int, fuse: int = 1, n_taps: int = 27) -> int:
-    wt, stages = weight_ring(g, nblk, fuse, n_taps)
-    return 2048 + 2 * (dt + 2) * g * CHUNK_PITCH + stages * wt * g * fuse * nblk * 16
+    """Shared memory of one conv_gemm CTA; > SMEM_LIMIT when not even a 2-stage weight ring fits."""
+    wt, stages = weight_ring(dt, g, nblk, fuse, n_taps)
+    if stages < 2:
+        return SMEM_LIMIT + 1
+    return 2048 + a_slabs(dt, g) * (dt + 2) * g * CHUNK_PITCH + stages * wt * g * fuse * nblk * 16
 
 
 def choose_nblk(cp_out: int) -> Tuple[int, int]:
@@ -73,6 +92,7 @@ def choose_dt_g(nblk: int, chunk_counts: Sequence[int], depth: int, fuse: int = 
 
 
 NUM_SMS = 148
+_L2_LATENCY_CLK = 1.0               # loaded L2 -> SM round trip the weight ring has to cover (~2 us)
 _L2_BYTES_PER_CLK = 3700.0          # whole-chip L2 -> SM bandwidth the cost model assumes (~7 TB/s at 1.9 GHz)
 
 
@@ -88,6 +108,12 @@ def choose_config(out_cp: int, chunk_counts: Sequence[int], grid, taps_per_cg: f
     buffered], total = waves * t.  Wide N blocks and few planes starve small grids; narrow ones re-stream weights."""
     N_, D_, H_, W_ = grid
     best = None
+    forced = os.environ.get("U3D_CONV_CFG")         # tuning sweeps only: "nblk,dt,g,nbuf,fuse"
+    if forced:
+        nblk, dt, g, nbuf, fuse = (int(v) for v in forced.split(","))
+        if not can_fuse:
+            fuse = 1
+        return nblk, dt, g, nbuf, fuse
     gs = [g for g in (4, 6, 2) if all(c % g == 0 for c in chunk_counts)]
     if not gs:
         raise ValueError(f"channel chunk counts {chunk_counts} need an even common divisor")
@@ -100,31 +126,34 @@ def choose_config(out_cp: int, chunk_counts: Sequence[int], grid, taps_per_cg: f
                 if dt * nblk * nbuf > 512 or dt > max(1, D_):
                     continue
                 fuse = 3 if (can_fuse and nblk <= 64 and FUSE_KD) else 1
-                g = next((g for g in gs if conv_smem_bytes(dt, g, nblk, fuse) <= SMEM_LIMIT), None)
-                if g is None:
-                    continue
-                n_cg = n_chunks // g
-                g2 = g // 2
-                tiles = N_ * (-(-D_ // dt)) * (-(-H_ // HT)) * (-(-W_ // WT))
-                items = tiles * n_nb
-                if fuse == 3:
-                    per_tap = (max(dt - 2, 0) * _mma_cycles(3 * nblk) + min(2, dt) * _mma_cycles(2 * nblk if dt >= 2 else nblk)
-                               + 2 * _mma_cycles(nblk)) * g2
-                    mma = n_cg * (taps_per_cg / 3.0) * per_tap
-                else:
-                    mma = n_cg * taps_per_cg * dt * g2 * _mma_cycles(nblk)
-                a_bytes = n_cg * (dt + 2) * g * 2880 * 2.0            # 16-byte TMA rows fetch whole 32-byte sectors
-                w_bytes = n_cg * taps_per_cg * g * nblk * 16
-                active = min(items, NUM_SMS)
-                bw = min(48.0, _L2_BYTES_PER_CLK / active)
-                epi = dt * (nblk / 32.0) * 500.0
-                t_item = max(mma, (a_bytes + w_bytes) / bw) + (epi if nbuf == 1 else 0.0) + 3000.0
-                waves = max(1.0, items / float(NUM_SMS))
-                if waves < 6:
-                    waves = float(-(-items // NUM_SMS))
-                cost = waves * t_item * (1.0 + 0.0 * waste)
-                if best is None or cost < best[0]:
-                    best = (cost, nblk, dt, g, nbuf, fuse)
+                for g in gs:
+                    if conv_smem_bytes(dt, g, nblk, fuse) > SMEM_LIMIT:
+                        continue
+                    n_cg = n_chunks // g
+                    g2 = g // 2
+                    tiles = N_ * (-(-D_ // dt)) * (-(-H_ // HT)) * (-(-W_ // WT))
+                    items = tiles * n_nb
+                    if fuse == 3:
+                        per_tap = (max(dt - 2, 0) * _mma_cycles(3 * nblk) + min(2, dt) * _mma_cycles(2 * nblk if dt >= 2 else nblk)
+                                   + 2 * _mma_cycles(nblk)) * g2
+                        mma = n_cg * (taps_per_cg / 3.0) * per_tap
+                    else:
+                        mma = n_cg * taps_per_cg * dt * g2 * _mma_cycles(nblk)
+                    a_bytes = n_cg * (dt + 2) * g * 2880 * 2.0            # 16-byte TMA rows fetch whole 32-byte sectors
+                    w_bytes = n_cg * taps_per_cg * g * nblk * 16
+                    active = min(items, NUM_SMS)
+                    bw = min(48.0, _L2_BYTES_PER_CLK / active)
+                    epi = dt * (nblk / 32.0) * 500.0
+                    wt, stages = weight_ring(dt, g, nblk, fuse)
+                    ring_rate = stages * wt * g * fuse * nblk * 16 / _L2_LATENCY_CLK     # bytes in flight per L2 round trip
+                    t_item = (max(mma, (a_bytes + w_bytes) / bw, w_bytes / min(bw, ring_rate))
+                              + (epi if nbuf == 1 else 0.0) + 3000.0)
+                    waves = max(1.0, items / float(NUM_SMS))
+                    if waves < 6:
+                        waves = float(-(-items // NUM_SMS))
+                    cost = waves * t_item * (1.0 + 0.0 * waste)
+                    if best is None or cost < best[0]:
+                        best = (cost, nblk, dt, g, nbuf, fuse)
     if best is None:
         raise ValueError("no conv configuration fits shared memory / TMEM")
     return best[1:]
@@ -167,6 +196,8 @@ class ConvPlan:
     flops_per_voxel: float = 0.0    # algorithmic FLOPs per tile-grid voxel (unpadded channels)
     wT: int = 1                     # taps per weight-ring stage
     w_stages: int = 6               # weight-ring depth
+    a_stages: int = 2               # A slabs in flight
+    dense: bool = False             # fused, 9 taps in (kh,kw) order, all active everywhere: the kernel's unrolled path
     nbuf: int = 2                   # TMEM accumulator buffers (1: Dt * nblk <= 512, epilogue not overlapped)
     n_tiles_w: int = 0              # number of weight tiles
     fuse_kd: bool = False           # one weight tile = the 3 d-taps of a (kh,kw), rows ordered sd = 2,1,0
@@ -380,7 +411,7 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
     assert numel < 2 ** 31
     widx = widx.astype(np.int32)                    # -1 = structural zero (channel padding)
 
-    ring = weight_ring(G, nblk, 3 if fuse_kd else 1, 27 if ks == 3 else 1)
+    ring = weight_ring(Dt, G, nblk, 3 if fuse_kd else 1, 27 if ks == 3 else 1)
     assert conv_smem_bytes(Dt, G, nblk, 3 if fuse_kd else 1, 27 if ks == 3 else 1) <= SMEM_LIMIT
     tab = np.concatenate([
         np.asarray(cg_map, np.int32), np.asarray(cg_ch, np.int32),
@@ -394,7 +425,8 @@ def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: 
     return ConvPlan(kind=kind, ks=ks, stride=stride, pattern=pattern, in_C=in_C, in_Cp=in_Cp, out_C=out_C, out_Cp=out_Cp,
                     maps=maps, G=G, Dt=Dt, nblk=nblk, cg_map=cg_map, cg_ch=cg_ch, shifts=shifts, nb_sel=nb_sel,
                     nb_coff=nb_coff, nb_ooff=nb_ooff, nb_real0=nb_real0, masks=masks, wbase=wbase, tab=tab, widx=widx,
-                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles, fuse_kd=fuse_kd, nbuf=nbuf, wT=ring[0], w_stages=ring[1],
+                    omul=2 if pattern == "transposed" else 1, n_tiles_w=n_tiles, fuse_kd=fuse_kd, nbuf=nbuf, wT=ring[0], w_stages=ring[1], a_stages=a_slabs(Dt, G),
+                    dense=bool(fuse_kd and len(shifts) == 9 and nblk in (32, 64) and (masks == 0x1ff).all()),
                     flops_per_voxel=(2.0 * in_C[0] * sum(out_C) * (k3 + 1)) if skip_k1 else 2.0 * sum(in_C) * sum(out_C) * k3)
 
 

@@ -221,10 +221,10 @@ def main():
     # dominant kernel: conv_gemm (forward + data-gradient launches) -- algorithmic FLOPs / CUDA-event time
     roof = None
     if rank == 0 and prof:
-        by = {}
-        for name, flops, a, b in prof:
-            d = by.setdefault(name, [0.0, 0.0, 0])
-            d[0] += flops
+        by, mem = {}, {}
+        for name, flops, a, b, nbytes in prof:
+            d = (by if flops > 0 else mem).setdefault(name, [0.0, 0.0, 0])
+            d[0] += flops if flops > 0 else nbytes
             d[1] += a.elapsed_time(b)
             d[2] += 1
         peak, hbm, src = read_peaks()
@@ -235,7 +235,13 @@ def main():
                 "frac": ach / peak, "traffic": None, "peak_source": f"{src} (bf16_tflops_sustained)",
                 "launches_per_step": cnt // K, "kernel_ms_per_step": tms / K,
                 "per_kernel_ms_per_step": {k: v[1] / K for k, v in by.items()},
-                "per_kernel_tflops": {k: (v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None) for k, v in by.items()}}
+                "per_kernel_tflops": {k: (v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None) for k, v in by.items()},
+                # the HBM-bound kernels of the step: algorithmic bytes / CUDA-event time against the measured copy bandwidth
+                "hbm_peak_gbs": hbm,
+                "hbm_kernels": {k: {"launches_per_step": v[2] // K, "ms_per_step": round(v[1] / K, 4),
+                                    "gbs": round(v[0] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None,
+                                    "frac": round(v[0] / (v[1] * 1e-3) / 1e9 / hbm, 3) if v[1] > 0 else None}
+                                for k, v in sorted(mem.items(), key=lambda kv: -kv[1][1])}}
 
     # ---- second half of BASELINE.json's metric: sliding-window inference, CT volumes/s (cfg-4: 512x512x256 volume,
     # 128^3 windows at 50 % overlap = 147 windows on the reference's grid; windows are dealt to the ranks)

@@ -72,9 +72,11 @@ typedef struct unet3d_conv_args {
   long long out_sN, out_sD, out_sH, out_sW;   /* ELEMENT strides of out/addend */
   int out_C, stats_C, omul, zD, zH, zW;
   int act;                /* epilogue activation after bias/addend: 0 none, 1 LeakyReLU(0.01) */
+  int a_stages;           /* A slabs in flight (2..4) */
+  int dense;              /* 1 = every one of the 9 fused (kh,kw) taps is active for every (N block, channel group) */
 } unet3d_conv_args;
 int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream);
-size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages);
+size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages, int a_stages);
 
 /* Pack an fp32 parameter (PyTorch layout) into the 16-bit tile stream unet3d_conv_gemm consumes:
  * out[i] = idx[i] < 0 ? 0 : w[idx[i]]; idx (device int32, n elements, n % 8 == 0 preferred) comes from the host plan. */

@@ -135,3 +135,29 @@ def test_trainer_fit_learns_and_checkpoints(tmp_path):
     for k, v in ck["model_state_dict"].items():
         assert torch.equal(m2.state_dict()[k].cpu(), v.cpu())
     ops.check_device_errors()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_forward_sees_optimizer_updates(fused):
+    """Packed 16-bit weight tiles are cached between forwards; the cache must not survive an optimizer step.
+    torch.optim.Adam(fused=True) updates parameters WITHOUT bumping their version counters, so the version alone
+    cannot be the cache key (ops.PACK_EPOCH).  Checked against the oracle run on the updated state_dict."""
+    torch.manual_seed(0)
+    m = unet3d_b200.ResUnet3D(num_pool=2, num_features=8, out_channels=3).to(DEV).eval()     # eval: no dropout
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2, fused=fused)
+    x = torch.randn(1, 1, 16, 16, 16, device=DEV)
+    y = torch.randint(0, 3, (1, 16, 16, 16), device=DEV)
+    sd0 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    for _ in range(2):
+        opt.zero_grad()
+        unet3d_b200.DiceLoss()(m(x), y).backward()
+        opt.step()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    ref = O.resunet3d_forward(sd, x.cpu(), 2, 8)
+    stale = O.resunet3d_forward(sd0, x.cpu(), 2, 8)
+    assert ((stale - ref).norm() / ref.norm()).item() > 0.2          # the update is large enough to be seen
+    with torch.no_grad():
+        out = m(x).cpu()
+    assert ((out - ref).norm() / ref.norm()).item() < 3e-2
+    out2 = m(x).detach().cpu()                                       # grad-enabled forward after the step
+    assert ((out2 - ref).norm() / ref.norm()).item() < 3e-2

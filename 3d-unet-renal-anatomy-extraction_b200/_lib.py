@@ -27,7 +27,7 @@ class ConvArgs(C.Structure):
                 ("n_taps", C.c_int), ("fuse", C.c_int), ("nbuf", C.c_int), ("wT", C.c_int), ("w_stages", C.c_int), ("in_f16", C.c_int), ("out_f16", C.c_int),
                 ("out_sN", C.c_longlong), ("out_sD", C.c_longlong), ("out_sH", C.c_longlong), ("out_sW", C.c_longlong),
                 ("out_C", C.c_int), ("stats_C", C.c_int), ("omul", C.c_int), ("zD", C.c_int), ("zH", C.c_int),
-                ("zW", C.c_int), ("act", C.c_int), ("a_stages", C.c_int), ("dense", C.c_int)]
+                ("zW", C.c_int), ("act", C.c_int), ("a_stages", C.c_int), ("dense", C.c_int), ("dbg_out", C.c_void_p)]
 
 
 class WgradArgs(C.Structure):

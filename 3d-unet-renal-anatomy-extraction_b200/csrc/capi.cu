@@ -46,19 +46,25 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 5-D (C, W, H, D, N) bf16 view; box = (8 channels, bw, bh, 1, 1); OOB reads give zeros (conv padding).
-int encode_src(CUtensorMap* m, const unet3d_src& s, int bw, int bh) {
+// 5-D (C, W, H, D, N) 16-bit view; box = (chans channels, bw, bh, 1, 1); OOB reads give zeros (conv padding).
+// chans = 8: 16-byte rows, no swizzle (weight-gradient bricks); 16 / 32 / 64: SWIZZLE_32B / 64B / 128B (conv_gemm slabs).
+int encode_src(CUtensorMap* m, const unet3d_src& s, int bw, int bh, int chans = 8) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(U3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found%s");
   if (s.ptr == nullptr || (reinterpret_cast<uintptr_t>(s.ptr) & 15) || s.C % 8 || (s.sW & 15) || (s.sH & 15) ||
       (s.sD & 15) || (s.sN & 15))
     return fail(U3D_ERR_INVALID, "source view must be 16-byte aligned with C %% 8 == 0%s");
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (chans == 16) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (chans == 32) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (chans == 64) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else if (chans != 8) return fail(U3D_ERR_INVALID, "box channel count must be 8, 16, 32 or 64%s");
   cuuint64_t dims[5] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.D, (cuuint64_t)s.N};
   cuuint64_t strides[4] = {(cuuint64_t)s.sW, (cuuint64_t)s.sH, (cuuint64_t)s.sD, (cuuint64_t)s.sN};
-  cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)chans, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(s.ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(U3D_ERR_CUDA, "cuTensorMapEncodeTiled failed%s (CUresult %lld)", "", (long long)r);
   return U3D_OK;
@@ -97,7 +103,7 @@ int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
   memset(&p, 0, sizeof(p));
   for (int i = 0; i < CG_MAX_MAPS; ++i) {
     const unet3d_src& s = a->src[i < a->n_src ? i : 0];
-    int rc = encode_src(&p.amap[i], s, CG_WB, CG_HB);
+    int rc = encode_src(&p.amap[i], s, CG_WB, CG_HB, 8 * a->G);
     if (rc != U3D_OK) return rc;
   }
   p.tab = a->tab;
@@ -120,6 +126,7 @@ int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream) {
   p.wT = a->wT;
   p.w_stages = a->w_stages;
   p.a_stages = a->a_stages;
+  p.dbg_out = a->dbg_out;
   p.dense = a->dense && !(getenv("U3D_NO_DENSE") != nullptr);
   p.in_f16 = a->in_f16;
   p.out_f16 = a->out_f16;

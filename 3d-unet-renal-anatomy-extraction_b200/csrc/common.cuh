@@ -44,6 +44,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or `ns` elapse, instead
+// of returning to a polling loop.  For the roles that are NOT on the critical path (producers, epilogue): their polls
+// go through the same MIO queue as the MMA warp's tcgen05.mma issue and measurably slow it down.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -62,6 +76,25 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0) {
+      if (*abort_flag) return false;
+      if (globaltimer_ns() - t0 > U3D_WAIT_TIMEOUT_NS) {
+        *abort_flag = 1;
+        if (err_word) atomicCAS(err_word, 0, code);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+// Same contract, for waiters off the critical path: parked waits + a sleep between polls.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, volatile int* abort_flag,
+                                                  int* err_word, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+    __nanosleep(200);
+    if ((++spins & 0x3f) == 0) {
       if (*abort_flag) return false;
       if (globaltimer_ns() - t0 > U3D_WAIT_TIMEOUT_NS) {
         *abort_flag = 1;
@@ -145,6 +178,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
+  return d;
+}
+// Swizzled K-major operand (row pitch = swizzle span): LBO unused, SBO = pitch of the 8-row groups, base offset 0
+// (address-based swizzle: any 16-byte-aligned start inside a TMA-written box reads the right rows, tools/probe).
+// row_bytes: 32 / 64 / 128.
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t row_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;
   return d;
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.

@@ -51,8 +51,8 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 template <int DT, int G2, int FUSE>
 __device__ __forceinline__ void issue_tap(uint32_t acc0, uint64_t adesc0, uint64_t bdesc0, uint32_t idesc1,
                                           uint32_t idesc2, uint32_t idesc3, uint32_t nblk, uint32_t accum) {
-  constexpr uint64_t A_DINC = (uint64_t)((2 * G2 * CG_CHUNK_PITCH) >> 4);     // one plane
-  constexpr uint64_t A_KINC = (uint64_t)((2 * CG_CHUNK_PITCH) >> 4);          // one K=16 step (two chunks)
+  constexpr uint64_t A_DINC = (uint64_t)(cg_plane_pitch(2 * G2) >> 4);        // one plane
+  constexpr uint64_t A_KINC = 2;                                              // one K=16 step = 32 B inside the swizzled row
   const uint64_t b_kinc = (uint64_t)(2u * FUSE * nblk);                        // (2 chunks * FUSE*nblk*16 B) / 16
   if (FUSE == 1) {
 #pragma unroll
@@ -96,7 +96,7 @@ __device__ __forceinline__ void issue_batch(uint32_t mask, int cnt, const uint32
   for (int i = 0; i < cnt; ++i) {
     const int tap = __ffs(mask) - 1;
     mask &= mask - 1;
-    const uint64_t adesc0 = umma_desc(slab + tap_off[tap], CG_CHUNK_PITCH, CG_WB * 16);
+    const uint64_t adesc0 = umma_desc_sw(slab + tap_off[tap], CG_WB * 32 * G2, 32 * G2);
     const uint64_t bdesc0 = umma_desc(wst_addr + (uint32_t)i * wtile_bytes, b_lbo, 128);
     issue_tap<DT, G2, FUSE>(acc0, adesc0, bdesc0, idesc1, idesc2, idesc3, nblk, accum);
     accum = 1;
@@ -111,8 +111,8 @@ __device__ __forceinline__ void issue_batch_dispatch(int Dt, int G2, uint32_t ma
 #define U3D_CASE(DT, GG)          \
   if (Dt == DT && G2 == GG)       \
     return issue_batch<DT, GG, FUSE>(mask, cnt, tap_off, slab, wst_addr, wtile_bytes, b_lbo, acc0, i1, i2, i3, nblk, accum);
-  U3D_CASE(8, 1) U3D_CASE(8, 2) U3D_CASE(4, 1) U3D_CASE(4, 2) U3D_CASE(4, 3) U3D_CASE(2, 1) U3D_CASE(2, 2) U3D_CASE(2, 3)
-  U3D_CASE(1, 1) U3D_CASE(1, 2) U3D_CASE(1, 3) U3D_CASE(8, 3)
+  U3D_CASE(8, 1) U3D_CASE(8, 2) U3D_CASE(4, 1) U3D_CASE(4, 2) U3D_CASE(4, 4) U3D_CASE(2, 1) U3D_CASE(2, 2) U3D_CASE(2, 4)
+  U3D_CASE(1, 1) U3D_CASE(1, 2) U3D_CASE(1, 4) U3D_CASE(8, 4)
 #undef U3D_CASE
 }
 
@@ -126,10 +126,10 @@ __device__ __forceinline__ void issue_batch_dispatch(int Dt, int G2, uint32_t ma
 template <int DT, int G2, int NBLK>
 __device__ __forceinline__ void issue_tap_dense(uint32_t acc0, uint64_t aslab, uint64_t bdesc0, uint32_t idesc1,
                                                 uint32_t idesc2, uint32_t idesc3, const int t, const bool first) {
-  constexpr uint64_t A_DINC = (uint64_t)((2 * G2 * CG_CHUNK_PITCH) >> 4);
-  constexpr uint64_t A_KINC = (uint64_t)((2 * CG_CHUNK_PITCH) >> 4);
+  constexpr uint64_t A_DINC = (uint64_t)(cg_plane_pitch(2 * G2) >> 4);
+  constexpr uint64_t A_KINC = 2;
   constexpr uint64_t B_KINC = (uint64_t)(2 * 3 * NBLK);
-  const uint64_t adesc0 = aslab + (uint64_t)((t / 3) * CG_WB + (t % 3));       // (kh * 10 + kw) * 16 B, in 16-B units
+  const uint64_t adesc0 = aslab + (uint64_t)(((t / 3) * CG_WB + (t % 3)) * 2 * G2);   // (kh * 10 + kw) rows of 32 * G2 bytes, in 16-B units
   if (t == 0 && first) {
     // first tap of an item: unfused, so that the first MMA into every accumulator overwrites it
 #pragma unroll
@@ -165,6 +165,10 @@ struct MmaRoleArgs {
 
 template <int DT, int G2, int NBLK>
 __device__ __noinline__ void mma_role_dense(const ConvGemmParams& p, const MmaRoleArgs r) {
+  // The WHOLE role runs in one elected thread, barrier waits included: any per-tap warp-level step (elect.sync,
+  // __syncwarp, a warp-wide barrier poll) between two taps lets the shallow tcgen05 queue drain -- measured +36 % on
+  // the level-0 layers against the back-to-back rate of tools/probe/mma_rate.cu.
+  if (!elect_one()) return;
   SmemCtl* ctl = r.ctl;
   volatile int* abort_flag = &ctl->abort_flag;
   const uint32_t idesc1 = umma_idesc_bf16(128, NBLK, 0, 0, p.in_f16, p.in_f16);
@@ -174,16 +178,22 @@ __device__ __noinline__ void mma_role_dense(const ConvGemmParams& p, const MmaRo
   const int wT = p.wT, n_cg = p.n_cg;
   const uint64_t wtile16 = (uint64_t)(r.wtile_bytes >> 4);
   uint32_t a_it = 0, w_it = 0, acc_it = 0;
+  const bool timing = p.dbg_out != nullptr && blockIdx.x == 0;
+  long long t_acc = 0, t_a = 0, t_w = 0, n_items = 0, t_begin = timing ? clock64() : 0;
   for (int item = blockIdx.x; item < p.n_work; item += gridDim.x) {
     const uint32_t buf = p.nbuf == 2 ? (acc_it & 1) : 0u, aph = p.nbuf == 2 ? ((acc_it >> 1) & 1) : (acc_it & 1);
+    long long tq = timing ? clock64() : 0;
     if (!mbar_wait(smem_u32(&ctl->acc_empty[buf]), aph ^ 1, abort_flag, p.err, 103)) return;
+    if (timing) t_acc += clock64() - tq, ++n_items;
     tc_fence_after();
     const uint32_t acc0 = r.tmem_base + buf * 256;
     for (int cg = 0; cg < n_cg; ++cg) {
       const uint32_t ast = a_it % a_stages, aphase = (a_it / a_stages) & 1;
+      tq = timing ? clock64() : 0;
       if (!mbar_wait(smem_u32(&ctl->a_full[ast]), aphase, abort_flag, p.err, 104)) return;
+      if (timing) t_a += clock64() - tq;
       tc_fence_after();
-      const uint64_t aslab = umma_desc(r.slab0 + ast * r.slab_bytes, CG_CHUNK_PITCH, CG_WB * 16);
+      const uint64_t aslab = umma_desc_sw(r.slab0 + ast * r.slab_bytes, CG_WB * 32 * G2, 32 * G2);
       uint64_t bdesc = 0;
       uint32_t wst = 0;
       int in_batch = 0;
@@ -191,30 +201,33 @@ __device__ __noinline__ void mma_role_dense(const ConvGemmParams& p, const MmaRo
       for (int t = 0; t < 9; ++t) {
         if (in_batch == 0) {
           wst = w_it % w_stages;
+          tq = timing ? clock64() : 0;
           if (!mbar_wait(smem_u32(&ctl->w_full[wst]), (w_it / w_stages) & 1, abort_flag, p.err, 105)) return;
+          if (timing) t_w += clock64() - tq;
           tc_fence_after();
           bdesc = umma_desc(r.wring0 + wst * r.wstage_bytes, 3 * NBLK * 16, 128);
         }
         ++in_batch;
-        const bool last = in_batch == wT || t == 8;
-        if (elect_one()) {
-          issue_tap_dense<DT, G2, NBLK>(acc0, aslab, bdesc, idesc1, idesc2, idesc3, t, cg == 0);
-          if (last) tc_commit(smem_u32(&ctl->w_empty[wst]));
-        }
-        __syncwarp();
+        if (!(p.dbg & 8)) issue_tap_dense<DT, G2, NBLK>(acc0, aslab, bdesc, idesc1, idesc2, idesc3, t, cg == 0);
         bdesc += wtile16;
-        if (last) {
+        if (in_batch == wT || t == 8) {
+          tc_commit(smem_u32(&ctl->w_empty[wst]));
           ++w_it;
           in_batch = 0;
         }
       }
-      if (elect_one()) tc_commit(smem_u32(&ctl->a_empty[ast]));
-      __syncwarp();
+      tc_commit(smem_u32(&ctl->a_empty[ast]));
       ++a_it;
     }
-    if (elect_one()) tc_commit(smem_u32(&ctl->acc_full[buf]));
-    __syncwarp();
+    tc_commit(smem_u32(&ctl->acc_full[buf]));
     ++acc_it;
+  }
+  if (timing) {
+    p.dbg_out[0] = clock64() - t_begin;
+    p.dbg_out[1] = t_acc;
+    p.dbg_out[2] = t_a;
+    p.dbg_out[3] = t_w;
+    p.dbg_out[4] = n_items;
   }
 }
 
@@ -225,10 +238,10 @@ __device__ __forceinline__ bool mma_role_dense_dispatch(const ConvGemmParams& p,
     mma_role_dense<DT, GG, NB>(p, r);                      \
     return true;                                           \
   }
-#define U3D_DENSE_G(DT, NB) U3D_DENSE(DT, 1, NB) U3D_DENSE(DT, 2, NB) U3D_DENSE(DT, 3, NB)
+#define U3D_DENSE_G(DT, NB) U3D_DENSE(DT, 1, NB) U3D_DENSE(DT, 2, NB) U3D_DENSE(DT, 4, NB)
   U3D_DENSE_G(8, 32) U3D_DENSE_G(4, 32) U3D_DENSE_G(2, 32) U3D_DENSE_G(1, 32)
   U3D_DENSE_G(4, 64) U3D_DENSE_G(2, 64) U3D_DENSE_G(1, 64)
-  U3D_DENSE(8, 1, 64) U3D_DENSE(8, 2, 64) U3D_DENSE(8, 3, 64)
+  U3D_DENSE(8, 1, 64) U3D_DENSE(8, 2, 64)
 #undef U3D_DENSE_G
 #undef U3D_DENSE
   return false;
@@ -244,7 +257,8 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
 
   const int planes = p.Dt + 2;
-  const uint32_t plane_pitch = (uint32_t)p.G * CG_CHUNK_PITCH;
+  const uint32_t plane_pitch = (uint32_t)cg_plane_pitch(p.G);
+  const uint32_t row_bytes = (uint32_t)cg_row_bytes(p.G);
   const uint32_t slab_bytes = (uint32_t)planes * plane_pitch;
   const uint32_t wtile_bytes = (uint32_t)p.G * p.fuse * p.nblk * 16;
   const int wT = p.wT;                                   // taps per weight-ring stage
@@ -285,7 +299,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   if (threadIdx.x >= 96 && threadIdx.x < 96 + 32 && (int)threadIdx.x - 96 < p.n_taps) {
     const int sh = tab_shift[threadIdx.x - 96];
     ctl->tap_off[threadIdx.x - 96] =
-        (uint32_t)(sh & 0xff) * plane_pitch + (uint32_t)(((sh >> 8) & 0xff) * CG_WB + ((sh >> 16) & 0xff)) * 16;
+        (uint32_t)(sh & 0xff) * plane_pitch + (uint32_t)(((sh >> 8) & 0xff) * CG_WB + ((sh >> 16) & 0xff)) * row_bytes;
   }
   tc_fence_before();
   __syncthreads();
@@ -317,17 +331,19 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
       for (int cg = 0; cg < n_cg; ++cg) {
         if (__ldg(&tab_mask[nb * n_cg + cg]) == 0) continue;
         const uint32_t st = a_it % a_stages, ph = (a_it / a_stages) & 1;
-        if (!mbar_wait(smem_u32(&ctl->a_empty[st]), ph ^ 1, abort_flag, p.err, 101)) { ok = false; break; }
+        if (!mbar_wait_relaxed(smem_u32(&ctl->a_empty[st]), ph ^ 1, abort_flag, p.err, 101)) { ok = false; break; }
         const uint32_t full = smem_u32(&ctl->a_full[st]);
         const CUtensorMap* m = &p.amap[__ldg(&tab_map[cg])];
         const int ch0 = __ldg(&tab_ch[cg]);
         if (elect_one()) {
-          const int gl = (p.dbg & 1) ? 1 : G;
-          mbar_expect_tx(full, (uint32_t)planes_i * gl * CG_BOX_BYTES);
-          uint32_t dst = slab0 + st * slab_bytes;
-          for (int pl = 0; pl < planes_i; ++pl, dst += (G - gl) * CG_CHUNK_PITCH)
-            for (int g = 0; g < gl; ++g, dst += CG_CHUNK_PITCH)
-              tma_load_5d(dst, m, full, ch0 + g * 8, w0, h0, d0 + pl, n);
+          if (p.dbg & 32) {
+            mbar_arrive(full);                      // timing experiment: no A loads
+          } else {
+            mbar_expect_tx(full, (uint32_t)planes_i * (uint32_t)cg_plane_bytes(G));
+            uint32_t dst = slab0 + st * slab_bytes;
+            for (int pl = 0; pl < planes_i; ++pl, dst += plane_pitch)
+              tma_load_5d(dst, m, full, ch0, w0, h0, d0 + pl, n);
+          }
         }
         __syncwarp();
         ++a_it;
@@ -346,11 +362,15 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
           const int cnt = left < wT ? left : wT;
           left -= cnt;
           const uint32_t st = w_it % w_stages, ph = (w_it / w_stages) & 1;
-          if (!mbar_wait(smem_u32(&ctl->w_empty[st]), ph ^ 1, abort_flag, p.err, 102)) { ok = false; break; }
+          if (!mbar_wait_relaxed(smem_u32(&ctl->w_empty[st]), ph ^ 1, abort_flag, p.err, 102)) { ok = false; break; }
           if (elect_one()) {
             const uint32_t full = smem_u32(&ctl->w_full[st]);
-            mbar_expect_tx(full, (uint32_t)cnt * wtile_bytes);
-            bulk_load(wring0 + st * wstage_bytes, src, (uint32_t)cnt * wtile_bytes, full);
+            if (p.dbg & 64) {
+              mbar_arrive(full);                    // timing experiment: no weight loads
+            } else {
+              mbar_expect_tx(full, (uint32_t)cnt * wtile_bytes);
+              bulk_load(wring0 + st * wstage_bytes, src, (uint32_t)cnt * wtile_bytes, full);
+            }
           }
           __syncwarp();
           src += (size_t)cnt * wtile_bytes;
@@ -466,7 +486,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
         cur_nb = nb;
       }
       const uint32_t buf = p.nbuf == 2 ? (acc_it & 1) : 0u, aph = p.nbuf == 2 ? ((acc_it >> 1) & 1) : (acc_it & 1);
-      if (!mbar_wait(smem_u32(&ctl->acc_full[buf]), aph, abort_flag, p.err, 106)) break;
+      if (!mbar_wait_relaxed(smem_u32(&ctl->acc_full[buf]), aph, abort_flag, p.err, 106)) break;
       tc_fence_after();
       const int coff_raw = __ldg(&tab_coff[nb]);
       const int coff = coff_raw & 0x3fffffff;
@@ -476,7 +496,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
       const int gh = th * CG_HT + line, gw = tw * CG_WT + wi;
       const int oh = gh * p.omul + ((ooff >> 8) & 0xff), ow = gw * p.omul + ((ooff >> 16) & 0xff);
       const bool hw_ok = gh < p.H && gw < p.W;
-      for (int cc = 0; cc < n_cc; ++cc) {
+      for (int cc = 0; cc < ((p.dbg & 16) ? 0 : n_cc); ++cc) {
         // per-thread partial sums of this warp's planes; ONE cross-lane reduction per (item, cc) instead of per plane
         float a1[32], a2[32];
 #pragma unroll
@@ -576,14 +596,14 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
 }  // namespace
 
 size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages, int a_stages) {
-  return 1024 /*align slack*/ + 1024 /*ctl*/ + (size_t)a_stages * (Dt + 2) * G * CG_CHUNK_PITCH +
+  return 1024 /*align slack*/ + 1024 /*ctl*/ + (size_t)a_stages * (Dt + 2) * cg_plane_pitch(G) +
          (size_t)w_stages * wT * G * fuse * nblk * 16;
 }
 
 int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.G < 2 || (p.G & 1) || p.nblk % 32 != 0 || p.nblk > 128 || p.Dt < 1 || (p.nbuf != 1 && p.nbuf != 2) ||
       p.Dt * p.nblk * p.nbuf > 512 ||
-      p.n_taps < 1 || p.n_taps > 32 || p.n_work < 1 || (p.Dt != 1 && p.Dt != 2 && p.Dt != 4 && p.Dt != 8) || p.G > 6 || (p.fuse != 1 && p.fuse != 3) || p.fuse * p.nblk > 256)
+      p.n_taps < 1 || p.n_taps > 32 || p.n_work < 1 || (p.Dt != 1 && p.Dt != 2 && p.Dt != 4 && p.Dt != 8) || (p.G != 2 && p.G != 4 && p.G != 8) || (p.fuse != 1 && p.fuse != 3) || p.fuse * p.nblk > 256)
     return U3D_ERR_INVALID;
   if (p.wT < 1 || p.wT > 32 || p.w_stages < 2 || p.w_stages > CG_W_STAGES || p.a_stages < 2 || p.a_stages > CG_A_STAGES)
     return U3D_ERR_INVALID;

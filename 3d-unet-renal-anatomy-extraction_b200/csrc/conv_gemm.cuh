@@ -19,8 +19,16 @@ constexpr int CG_HT = 16;            // output tile: 16 (h) x 8 (w) voxels = the
 constexpr int CG_WT = 8;
 constexpr int CG_HB = CG_HT + 2;     // brick with a 1-voxel halo on both sides
 constexpr int CG_WB = CG_WT + 2;
-constexpr int CG_BOX_BYTES = CG_HB * CG_WB * 16;     // one (plane, 8-channel chunk) TMA box = 2880 B
-constexpr int CG_CHUNK_PITCH = 2944;                 // padded to 128 B (TMA smem destination alignment)
+constexpr int CG_BOX_BYTES = CG_HB * CG_WB * 16;     // one (plane, 8-channel chunk) TMA box = 2880 B   (weight-gradient kernel)
+constexpr int CG_CHUNK_PITCH = 2944;                 // padded to 128 B (TMA smem destination alignment) (weight-gradient kernel)
+// conv_gemm A slabs: one TMA box per plane holds the whole channel group, (18 x 10 voxels) rows of 16 * G bytes
+// (G = 2 / 4 / 8 chunks = 32 / 64 / 128 B), written with SWIZZLE_32B / 64B / 128B = the swizzled K-major UMMA layouts
+// (row pitch = swizzle span, 8-row group pitch SBO = one brick line).  A 16-byte-row box costs one shared-memory write
+// wavefront and one 32-byte L2 sector PER ROW: at level 0 the TMA writes then took as many shared-memory cycles as all
+// tensor-core operand reads together (profiles/r01_notes.md); whole-group rows cut that 2-8x.
+__host__ __device__ constexpr int cg_row_bytes(int G) { return 16 * G; }
+__host__ __device__ constexpr int cg_plane_bytes(int G) { return CG_HB * CG_WB * 16 * G; }
+__host__ __device__ constexpr int cg_plane_pitch(int G) { return (cg_plane_bytes(G) + 1023) / 1024 * 1024; }
 constexpr int CG_W_STAGES = 16;
 constexpr int CG_A_STAGES = 4;       // at most this many A slabs in flight
 constexpr int CG_EPI_WARPS = 4;      // 4 or 8
@@ -63,7 +71,8 @@ struct ConvGemmParams {
   int act;                // 0 none, 1 LeakyReLU(0.01) applied after bias / addend
   int dense;              // 1: fuse == 3, n_taps == 9 in (kh,kw) order, every tap of every (N block, group) active
   int n_work;
-  int dbg;                // timing experiments only (env U3D_DBG): 1 = load only chunk 0 of every A group, 2 = no statistics, 4 = no stores
+  long long* dbg_out;     // timing experiments only: CTA 0's MMA warp writes {total, acc_empty wait, a_full wait, w_full wait, items} cycles
+  int dbg;                // timing experiments only (env U3D_DBG): 1 = load only chunk 0 of every A group, 2 = no statistics, 4 = no stores, 8 = no MMAs (dense path), 16 = no epilogue work
 };
 
 size_t conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages, int a_stages);

@@ -27,6 +27,7 @@ LAUNCHES = 0
 # PACK_EPOCH at every training-mode forward and at the first no-grad forward after one, so a pack is reused only
 # across forwards between which no optimizer step can have happened (e.g. the windows of one inference volume).
 PACK_EPOCH = 0
+DBG_OUT = None          # tuning experiments: int64[8] device tensor receiving the conv MMA warp's cycle counters
 
 
 def _count(n: int = 1):
@@ -187,6 +188,7 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.zD, a.zH, a.zW = (d - 1, h - 1, w - 1) if zero_last else (-1, -1, -1)
     a.act = act
     a.dense = int(pl.dense)
+    a.dbg_out = DBG_OUT.data_ptr() if DBG_OUT is not None else None
     flops = pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3]
     _count()
     with _Timed("conv_gemm_kernel", flops):

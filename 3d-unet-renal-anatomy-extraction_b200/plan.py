@@ -22,7 +22,13 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 HT, WT = 16, 8                 # output tile (rows of one UMMA): 16 x 8 voxels
-CHUNK_PITCH = 2944
+CHUNK_PITCH = 2944             # weight-gradient x bricks: one (plane, 8-channel chunk) box, padded to 128 B
+
+
+def plane_pitch(g: int) -> int:
+    """conv_gemm A slab: bytes of one plane of a channel group of g chunks (18 x 10 rows of 16 g bytes, swizzled),
+    padded to the 1 KiB swizzle-atom alignment (csrc/conv_gemm.cuh: cg_plane_pitch)."""
+    return -(-(18 * 10 * 16 * g) // 1024) * 1024
 W_STAGES = 16
 FUSE_KD = True                 # fuse the three d-taps of a (kh,kw) into one wider UMMA where N <= 64
 SMEM_LIMIT = 227 * 1024
@@ -38,7 +44,7 @@ def a_slabs(dt: int, g: int) -> int:
     cfg-2 (gpurun_out, sweep with 2/3/4 slabs) a third slab never helps and costs weight-ring space: the A loads are
     not what the MMA warp waits for."""
     forced = os.environ.get("U3D_A_STAGES")
-    slab = (dt + 2) * g * CHUNK_PITCH
+    slab = (dt + 2) * plane_pitch(g)
     n = int(forced) if forced else 2
     return max(2, min(4, n, (SMEM_LIMIT - 2048 - 16384) // slab))
 
@@ -50,7 +56,7 @@ def weight_ring(dt: int, g: int, nblk: int, fuse: int, n_taps: int = 27) -> Tupl
     the per-batch cost on the single MMA-issuing thread outweighs the extra latency cover."""
     tile = g * fuse * nblk * 16
     taps = max(1, -(-n_taps // fuse))
-    avail = SMEM_LIMIT - 2048 - a_slabs(dt, g) * (dt + 2) * g * CHUNK_PITCH
+    avail = SMEM_LIMIT - 2048 - a_slabs(dt, g) * (dt + 2) * plane_pitch(g)
     wt = max(1, min(taps, 16, 28672 // tile))
     while wt > 1 and avail // (wt * tile) < 2:
         wt -= 1
@@ -63,7 +69,7 @@ def conv_smem_bytes(dt: int, g: int, nblk: int, fuse: int = 1, n_taps: int = 27)
     wt, stages = weight_ring(dt, g, nblk, fuse, n_taps)
     if stages < 2:
         return SMEM_LIMIT + 1
-    return 2048 + a_slabs(dt, g) * (dt + 2) * g * CHUNK_PITCH + stages * wt * g * fuse * nblk * 16
+    return 2048 + a_slabs(dt, g) * (dt + 2) * plane_pitch(g) + stages * wt * g * fuse * nblk * 16
 
 
 def choose_nblk(cp_out: int) -> Tuple[int, int]:
@@ -78,7 +84,7 @@ def choose_nblk(cp_out: int) -> Tuple[int, int]:
 
 def choose_dt_g(nblk: int, chunk_counts: Sequence[int], depth: int, fuse: int = 1) -> Tuple[int, int]:
     """Planes per segment and chunks per channel group: biggest Dt (halo amortisation), then biggest G."""
-    gs = [g for g in (4, 6, 2) if all(c % g == 0 for c in chunk_counts)]
+    gs = [g for g in (4, 8, 2) if all(c % g == 0 for c in chunk_counts)]
     if not gs:
         raise ValueError(f"channel chunk counts {chunk_counts} need an even common divisor")
     dt_max = max(1, min(256 // nblk, 8, depth))
@@ -114,7 +120,7 @@ def choose_config(out_cp: int, chunk_counts: Sequence[int], grid, taps_per_cg: f
         if not can_fuse:
             fuse = 1
         return nblk, dt, g, nbuf, fuse
-    gs = [g for g in (4, 6, 2) if all(c % g == 0 for c in chunk_counts)]
+    gs = [g for g in (4, 8, 2) if all(c % g == 0 for c in chunk_counts)]
     if not gs:
         raise ValueError(f"channel chunk counts {chunk_counts} need an even common divisor")
     n_chunks = sum(chunk_counts)
@@ -139,7 +145,7 @@ def choose_config(out_cp: int, chunk_counts: Sequence[int], grid, taps_per_cg: f
                         mma = n_cg * (taps_per_cg / 3.0) * per_tap
                     else:
                         mma = n_cg * taps_per_cg * dt * g2 * _mma_cycles(nblk)
-                    a_bytes = n_cg * (dt + 2) * g * 2880 * 2.0            # 16-byte TMA rows fetch whole 32-byte sectors
+                    a_bytes = n_cg * (dt + 2) * g * 2880 * (2.0 if g == 1 else 1.0)     # rows of 16 g >= 32 bytes: whole sectors
                     w_bytes = n_cg * taps_per_cg * g * nblk * 16
                     active = min(items, NUM_SMS)
                     bw = min(48.0, _L2_BYTES_PER_CLK / active)

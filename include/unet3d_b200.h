@@ -74,6 +74,7 @@ typedef struct unet3d_conv_args {
   int act;                /* epilogue activation after bias/addend: 0 none, 1 LeakyReLU(0.01) */
   int a_stages;           /* A slabs in flight (2..4) */
   int dense;              /* 1 = every one of the 9 fused (kh,kw) taps is active for every (N block, channel group) */
+  long long* dbg_out;     /* NULL, or 8 int64 slots for the MMA warp's cycle counters (tuning experiments only) */
 } unet3d_conv_args;
 int unet3d_conv_gemm(const unet3d_conv_args* a, void* stream);
 size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages, int a_stages);

@@ -60,7 +60,7 @@ else:
 dxs = [torch.zeros_like(x) for x in xs]
 st = torch.zeros(N, y.shape[-1], 2, device=dev, dtype=torch.float64)
 res = []
-for nblk, dt, gg, nbuf, fuse in [(None,) * 5] + list(itertools.product((32, 64, 96, 128), (8, 4, 2, 1), (2, 4, 6), (2, 1), (3, 1))):
+for nblk, dt, gg, nbuf, fuse in [(None,) * 5] + list(itertools.product((32, 64, 96, 128), (8, 4, 2, 1), (2, 4, 8), (2, 1), (3, 1))):
     if nblk is None:
         os.environ.pop("U3D_CONV_CFG", None)
     else:

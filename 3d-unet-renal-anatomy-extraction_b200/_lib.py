@@ -30,6 +30,11 @@ class ConvArgs(C.Structure):
                 ("zW", C.c_int), ("act", C.c_int), ("a_stages", C.c_int), ("dense", C.c_int), ("dbg_out", C.c_void_p)]
 
 
+class GatherJob(C.Structure):
+    _fields_ = [("src0", C.c_void_p), ("src1", C.c_void_p), ("idx", C.c_void_p), ("out", C.c_void_p), ("n", C.c_longlong),
+                ("n0", C.c_int), ("mode", C.c_int)]
+
+
 class WgradArgs(C.Structure):
     _fields_ = [("n_src", C.c_int), ("src", Src * 16), ("box_w", C.c_int * 16), ("box_h", C.c_int * 16),
                 ("tab", C.c_void_p), ("dw", C.c_void_p), ("err", C.c_void_p),
@@ -44,6 +49,7 @@ _SIGS = {
     "unet3d_conv_gemm": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "unet3d_conv_gemm_smem_bytes": (C.c_size_t, [C.c_int] * 7),
     "unet3d_weight_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "unet3d_gather_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "unet3d_wgrad_gemm": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "unet3d_in_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_void_p]),
     "unet3d_in_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int,

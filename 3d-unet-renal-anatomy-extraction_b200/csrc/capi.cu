@@ -255,5 +255,9 @@ int unet3d_att_mid_bwd(const void* df, const void* f, const void* dxs, void* dpr
                            num_sms(), (cudaStream_t)stream),
                "att_mid_bwd");
 }
+int unet3d_gather_multi(const unet3d_gather_job* jobs_dev, const int* first_block_dev, int n_jobs, int n_blocks,
+                        const float* scale, void* out_base, void* stream) {
+  return check(gather_multi(jobs_dev, first_block_dev, n_jobs, n_blocks, scale, out_base, (cudaStream_t)stream), "gather_multi");
+}
 
 }  // extern "C"

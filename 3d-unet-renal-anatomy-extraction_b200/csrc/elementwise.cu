@@ -883,6 +883,61 @@ __global__ void att_mid_bwd_kernel(const uint4* __restrict__ df, const uint4* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Batched gather: every job is  out[i] = idx[i] < 0 ? 0 : src[idx[i]]  (src = src0 ++ src1 when src1 != NULL),
+// written as 16-bit (weight packing: all conv layers' forward + data-gradient tile streams of a step in ONE launch
+// instead of 92) or as fp32 times an optional device scalar (weight-gradient unpacking: all layers' dW accumulators
+// back to the PyTorch parameter layout in ONE launch instead of ~50 index_selects).  One CTA = 2048 consecutive
+// elements of one job; the job of a CTA is found by bisection in the prefix table `first_block`.
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_multi_kernel(const unet3d_gather_job* __restrict__ jobs, const int* __restrict__ first_block,
+                                    int n_jobs, const float* __restrict__ scale, char* out_base) {
+  int lo = 0, hi = n_jobs;                    // first_block[lo] <= blockIdx.x < first_block[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((int)blockIdx.x >= __ldg(&first_block[mid])) lo = mid; else hi = mid;
+  }
+  const unet3d_gather_job j = jobs[lo];
+  const long long base = ((long long)(blockIdx.x - __ldg(&first_block[lo])) * 256 + threadIdx.x) * 8;
+  if (base >= j.n) return;
+  const float* __restrict__ s0 = j.src0;
+  const float* __restrict__ s1 = j.src1;
+  const int n0 = j.n0;
+  int id[8];
+  const int cnt = (j.n - base >= 8) ? 8 : (int)(j.n - base);
+  if (cnt == 8) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(j.idx + base));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(j.idx + base + 4));
+    id[0] = a.x; id[1] = a.y; id[2] = a.z; id[3] = a.w; id[4] = b.x; id[5] = b.y; id[6] = b.z; id[7] = b.w;
+  } else {
+    for (int k = 0; k < 8; ++k) id[k] = k < cnt ? j.idx[base + k] : -1;
+  }
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = id[k];
+    f[k] = i < 0 ? 0.f : ((s1 != nullptr && i >= n0) ? __ldg(s1 + (i - n0)) : __ldg(s0 + i));
+  }
+  if (j.mode == 2) {
+    const float sc = scale ? __ldg(scale) : 1.f;
+    float* o = reinterpret_cast<float*>(out_base + reinterpret_cast<uintptr_t>(j.out)) + base;
+    if (cnt == 8 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+      reinterpret_cast<float4*>(o)[0] = make_float4(f[0] * sc, f[1] * sc, f[2] * sc, f[3] * sc);
+      reinterpret_cast<float4*>(o)[1] = make_float4(f[4] * sc, f[5] * sc, f[6] * sc, f[7] * sc);
+    } else {
+      for (int k = 0; k < cnt; ++k) o[k] = f[k] * sc;
+    }
+  } else {
+    uint16_t* o = reinterpret_cast<uint16_t*>(out_base + reinterpret_cast<uintptr_t>(j.out)) + base;
+    if (cnt == 8 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+      *reinterpret_cast<uint4*>(o) = pack8(f, j.mode);
+    } else {
+      for (int k = 0; k < cnt; ++k) o[k] = (uint16_t)(pack_2x16(f[k], 0.f, j.mode) & 0xffffu);
+    }
+  }
+}
+
 }  // namespace
 
 // ----------------------------------- launchers ---------------------------------------------------
@@ -1097,6 +1152,13 @@ int att_mid_bwd(const bf16* df, const bf16* f, const bf16* dxs, bf16* dpre, bf16
   const int g = grid_for(NV, blk.y * 8, num_sms, 8);
   att_mid_bwd_kernel<<<g, blk, (size_t)blk.y * Cp * sizeof(float), s>>>(
       (const uint4*)df, (const uint4*)f, (const uint4*)dxs, (uint4*)dpre, (uint4*)t, sum, chunks, NV, af);
+  return U3D_CHECK_LAUNCH();
+}
+
+int gather_multi(const unet3d_gather_job* jobs, const int* first_block, int n_jobs, int n_blocks, const float* scale,
+                 void* out_base, cudaStream_t s) {
+  if (n_jobs < 1 || n_blocks < 1) return U3D_ERR_INVALID;
+  gather_multi_kernel<<<n_blocks, 256, 0, s>>>(jobs, first_block, n_jobs, scale, reinterpret_cast<char*>(out_base));
   return U3D_CHECK_LAUNCH();
 }
 

@@ -38,5 +38,7 @@ int att_gate_bwd(const bf16* dout, const bf16* xs, const bf16* z, bf16* dxs, bf1
                  int af, int num_sms, cudaStream_t s);
 int att_mid_bwd(const bf16* df, const bf16* f, const bf16* dxs, bf16* dpre, bf16* t, double* sum, long long NV, int Cp,
                 int af, int num_sms, cudaStream_t s);
+int gather_multi(const unet3d_gather_job* jobs, const int* first_block, int n_jobs, int n_blocks, const float* scale,
+                 void* out_base, cudaStream_t s);
 
 }  // namespace u3d

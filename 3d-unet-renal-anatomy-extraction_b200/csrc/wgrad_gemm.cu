@@ -93,40 +93,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
       __syncwarp();
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_bf16(128, Gy * 8, 1, 1, p.x_f16, p.x_f16);
-    const uint64_t a_kinc = (uint64_t)((2 * CG_WB * 16) >> 4), b_kinc = (uint64_t)((2 * 128) >> 4);
-    uint32_t it = 0;
-    bool ok = true;
-    for (int t = sid; t < n_tiles && ok; t += p.split, ++it) {
-      const uint32_t st = it & 1, ph = (it >> 1) & 1;
-      if (!mbar_wait(smem_u32(&ctl->full[st]), ph, abort_flag, p.err, 202)) { ok = false; break; }
-      tc_fence_after();
-      const uint32_t xs = stage0 + st * stage_bytes, ys = xs + xstage;
-      for (int e = 0; e < n_ent; ++e) {
-        const uint32_t a0 = xs + ent_aoff[e];
-        const uint32_t acc = tmem_base + ent_col[e];
-        if (elect_one()) {
-          for (int d = 0; d < Dt; ++d) {
-            uint64_t a = umma_desc(a0 + (uint32_t)d * xplane, CG_WB * 16, CG_CHUNK_PITCH);
-            uint64_t b = umma_desc(ys + (uint32_t)d * yplane, 128, WG_DY_BOX_BYTES);
+    // The whole issuing role runs in ONE elected thread, barrier waits included (no elect.sync / __syncwarp between
+    // entries): a warp-level step between MMAs lets the shallow tcgen05 queue drain (measured on the conv kernel).
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, Gy * 8, 1, 1, p.x_f16, p.x_f16);
+      const uint64_t a_kinc = (uint64_t)((2 * CG_WB * 16) >> 4), b_kinc = (uint64_t)((2 * 128) >> 4);
+      const uint64_t a_dinc = (uint64_t)(xplane >> 4), b_dinc = (uint64_t)(yplane >> 4);
+      uint32_t it = 0;
+      bool ok = true;
+      for (int t = sid; t < n_tiles && ok; t += p.split, ++it) {
+        const uint32_t st = it & 1, ph = (it >> 1) & 1;
+        if (!mbar_wait(smem_u32(&ctl->full[st]), ph, abort_flag, p.err, 202)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t xs = stage0 + st * stage_bytes, ys = xs + xstage;
+        const uint64_t b0 = umma_desc(ys, 128, WG_DY_BOX_BYTES);
+        for (int e = 0; e < n_ent; ++e) {
+          uint64_t a = umma_desc(xs + ent_aoff[e], CG_WB * 16, CG_CHUNK_PITCH);
+          uint64_t b = b0;
+          const uint32_t acc = tmem_base + ent_col[e];
+          for (int d = 0; d < Dt; ++d, a += a_dinc, b += b_dinc) {
             tc_mma_bf16(acc, a, b, idesc, (it == 0 && d == 0) ? 0u : 1u);
 #pragma unroll
-            for (int k = 1; k < 8; ++k) {
-              a += a_kinc;
-              b += b_kinc;
-              tc_mma_bf16(acc, a, b, idesc, 1u);
-            }
+            for (int k = 1; k < 8; ++k) tc_mma_bf16(acc, a + k * a_kinc, b + k * b_kinc, idesc, 1u);
           }
         }
-        __syncwarp();
+        tc_commit(smem_u32(&ctl->empty[st]));
       }
-      if (elect_one()) tc_commit(smem_u32(&ctl->empty[st]));
-      __syncwarp();
+      if (ok) tc_commit(smem_u32(&ctl->acc_full));
     }
-    if (ok) {
-      if (elect_one()) tc_commit(smem_u32(&ctl->acc_full));
-      __syncwarp();
-    }
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;

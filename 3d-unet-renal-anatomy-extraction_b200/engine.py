@@ -65,6 +65,14 @@ class UNetEngine:
         self._ops: Dict[Tuple, _ConvOp] = {}
         self._inv_scale = None
         self._last_was_train = True      # the first forward always packs
+        self._reset_caches()
+
+    def _reset_caches(self):
+        self._ops = {}
+        self._pack_bind, self._pack_table, self._pack_table_key, self._pack_ptrs = {}, None, None, None
+        self._dw_slots, self._dw_order, self._dw_table, self._dw_table_n = {}, [], None, 0
+        self._dw_arena, self._gflat, self._g_total, self._dw_ready = None, None, 0, False
+        self._z_arena, self._z_used, self._z_demand, self._z_size = None, 0, 0, 0
 
     # ------------------------------------------------------------------ public entry
     def run(self, x: torch.Tensor) -> torch.Tensor:
@@ -84,7 +92,7 @@ class UNetEngine:
             from . import _lib
             self.device = x.device
             self.num_sms = _lib.lib().unet3d_num_sms()
-            self._ops = {}
+            self._reset_caches()
         params = list(net.parameters())
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if need_grad or self._last_was_train:
@@ -138,8 +146,8 @@ class UNetEngine:
         """conv (+ statistics) -> finalize: returns (y, table)."""
         n = inputs[0].shape[0]
         y = self._new_act(n, out_dims, op.out_C)
-        stats = torch.zeros(n, y.shape[-1], 2, dtype=torch.float64, device=self.device)
-        ops.conv_gemm(op.fwd, inputs, op.fwd.packed_weight(weight, self.act_dtype), [y], op.grid,
+        stats = self._z64(n, y.shape[-1], 2)
+        ops.conv_gemm(op.fwd, inputs, self._pw(op.fwd, weight), [y], op.grid,
                       bias=op.fwd.packed_bias(bias), stats=stats, zero_last=zero_last)
         table = torch.empty(n, y.shape[-1], 2, dtype=torch.float32, device=self.device)
         ops.in_finalize(stats, drop, table, out_dims[0] * out_dims[1] * out_dims[2], IN_EPS)
@@ -148,23 +156,122 @@ class UNetEngine:
     def _in_bwd(self, dout, dout2, out, y, table, zero_last=False, want_dsum=False):
         n, cp = y.shape[0], y.shape[-1]
         g = self._grad_like(y)
-        sums = torch.zeros(n, cp, 2, dtype=torch.float64, device=self.device)
+        sums = self._z64(n, cp, 2)
         ops.in_bwd_reduce(dout, dout2, out, y, g, table, sums)
         dy = self._grad_like(y)
-        dsum = torch.zeros(cp, dtype=torch.float64, device=self.device) if want_dsum else None
+        dsum = self._z64(cp) if want_dsum else None
         ops.in_bwd_apply(g, y, dy, table, sums, dsum, zero_last)
         return g, dy, sums, dsum
 
     def _wgrad(self, op: _ConvOp, xs, dy, param, more=()):
         """Weight gradient of `param`; `more` = further (xs, dy) pairs of the same layer shape whose products are
-        accumulated into the same buffer (a weight applied several times: the attention gate's shared conv)."""
+        accumulated into the same buffer (a weight applied several times: the attention gate's shared conv).
+        Steady state: the fp32 accumulator is a slice of one arena zeroed once per backward, and the gradient
+        tensor is a view of one flat buffer that ONE batched gather fills at the end of the backward pass
+        (_finish_wgrads); the first backward of a shape runs layer by layer and records the layout."""
         pl = op.wgrad.plan
-        dw = torch.zeros(pl.dw_numel + 1, dtype=torch.float32, device=self.device)
+        slot = self._dw_slots.get(id(op.wgrad)) if self._dw_ready else None
+        if slot is not None:
+            dw = self._dw_arena[slot[0]:slot[0] + pl.dw_numel + 1]
+        else:
+            dw = torch.zeros(pl.dw_numel + 1, dtype=torch.float32, device=self.device)
         ops.wgrad_gemm(op.wgrad, xs, dy, dw, op.grid)
         for xs2, dy2 in more:
             ops.wgrad_gemm(op.wgrad, xs2, dy2, dw, op.grid)
+        if slot is not None:
+            return self._gflat[slot[1]:slot[1] + param.numel()].view_as(param)
+        if id(op.wgrad) not in self._dw_slots:
+            self._dw_slots[id(op.wgrad)] = None
+            self._dw_order.append((op.wgrad, param.numel()))
         g = dw.index_select(0, op.wgrad.gidx).view_as(param)
         return g if self._inv_scale is None else g.mul_(self._inv_scale)
+
+    def _begin_wgrads(self):
+        """Called at the start of a backward pass: zero the accumulator arena, allocate this step's flat gradient buffer."""
+        self._dw_ready = False
+        if self._dw_table is not None and self._dw_table_n == len(self._dw_order):
+            self._dw_arena.zero_()
+            self._gflat = torch.empty(self._g_total, dtype=torch.float32, device=self.device)
+            self._dw_ready = True
+
+    def _finish_wgrads(self):
+        if self._dw_ready:
+            self._dw_table.launch(scale=self._inv_scale, out_base=self._gflat)
+            self._dw_ready = False
+        elif self._dw_order and (self._dw_table is None or self._dw_table_n != len(self._dw_order)):
+            off = goff = 0
+            jobs = []
+            for wp, n_param in self._dw_order:                 # 16-byte aligned slices
+                self._dw_slots[id(wp)] = (off, goff)
+                off += (wp.plan.dw_numel + 1 + 3) // 4 * 4
+                goff += (n_param + 3) // 4 * 4
+            self._dw_arena = torch.empty(off, dtype=torch.float32, device=self.device)
+            self._g_total = goff
+            for wp, n_param in self._dw_order:
+                o, g = self._dw_slots[id(wp)]
+                jobs.append(dict(src0=self._dw_arena[o:o + wp.plan.dw_numel + 1], idx=wp.gidx32, out=4 * g, mode=2))
+            self._dw_table = ops.GatherTable(jobs, self.device)
+            self._dw_table_n = len(self._dw_order)
+
+    # ------------------------------------------------------------------ packed weights: one batched launch per step
+    def _pw(self, dp, w):
+        """16-bit tile stream of `w` for plan `dp` (cached per ops.PACK_EPOCH); remembers the pairing so that the next
+        steps can pack every layer in one launch (_prepack)."""
+        if id(dp) not in self._pack_bind:
+            self._pack_bind[id(dp)] = (dp, w)
+        return dp.packed_weight(w, self.act_dtype)
+
+    def _prepack(self):
+        """Pack all known (plan, parameter) pairs whose cached tile stream is stale with one gather_multi launch."""
+        if not self._pack_bind or torch.cuda.is_current_stream_capturing():
+            return
+        dt = self.act_dtype
+        binds = list(self._pack_bind.values())
+        if all(dp._w_version == dp.weight_key(w, dt) for dp, w in binds):
+            return
+        if self._pack_table is None or self._pack_table_key != (len(binds), dt):
+            jobs = []
+            for dp, w in binds:
+                if isinstance(w, (list, tuple)):
+                    if len(w) != 2:
+                        return
+                    src0, src1, n0 = w[0].detach(), w[1].detach(), w[0].numel()
+                else:
+                    src0, src1, n0 = w.detach(), None, 0
+                if src0.dtype != torch.float32 or not src0.is_contiguous() or (src1 is not None and not src1.is_contiguous()):
+                    return
+                jobs.append(dict(src0=src0.view(-1), src1=None if src1 is None else src1.view(-1), idx=dp.widx,
+                                 out=dp.pack_buffer(dt, self.device), n0=n0, mode=int(dt == torch.float16)))
+            self._pack_table = ops.GatherTable(jobs, self.device)
+            self._pack_table_key = (len(binds), dt)
+            self._pack_ptrs = [tuple(t.data_ptr() for t in (w if isinstance(w, (list, tuple)) else [w])) for _, w in binds]
+        if self._pack_ptrs != [tuple(t.data_ptr() for t in (w if isinstance(w, (list, tuple)) else [w])) for _, w in binds]:
+            self._pack_table = None              # a parameter was re-allocated (e.g. .to()): rebuild next time
+            return
+        self._pack_table.launch()
+        for dp, w in binds:
+            dp._w_version = dp.weight_key(w, dt)
+
+    # ------------------------------------------------------------------ zero-initialised fp64 scratch (statistics)
+    def _z64(self, *shape):
+        """fp64 zeros for statistic accumulators, carved out of one arena zeroed once per pass instead of one fill
+        kernel per layer; the arena is sized from the previous pass's demand."""
+        n = 1
+        for v in shape:
+            n *= v
+        self._z_demand += (n + 1) // 2 * 2
+        if self._z_arena is not None and self._z_used + n <= self._z_arena.numel():
+            out = self._z_arena[self._z_used:self._z_used + n].view(*shape)
+            self._z_used += (n + 1) // 2 * 2
+            return out
+        return torch.zeros(*shape, dtype=torch.float64, device=self.device)
+
+    def _z_begin(self):
+        size = max(self._z_demand, self._z_size)
+        self._z_size = size
+        self._z_demand = 0
+        self._z_used = 0
+        self._z_arena = torch.zeros(size, dtype=torch.float64, device=self.device) if size else None
 
     def _unscale(self, g):
         return g if self._inv_scale is None else g * self._inv_scale
@@ -214,7 +321,7 @@ class UNetEngine:
         if blk.uses_skip_conv:
             sk = self._op(key + ("skip",), "conv", 1, blk.stride, in_C, blk.out_channels, grid)
             s = self._new_act(n, out_dims, blk.out_channels)
-            ops.conv_gemm(sk.fwd, inputs, sk.fwd.packed_weight(blk.skip_conv.weight, self.act_dtype), [s], sk.grid,
+            ops.conv_gemm(sk.fwd, inputs, self._pw(sk.fwd, blk.skip_conv.weight), [s], sk.grid,
                           bias=sk.fwd.packed_bias(blk.skip_conv.bias))
         else:
             s = inputs[0]
@@ -245,7 +352,7 @@ class UNetEngine:
         n = skip.shape[0]
         c, k1, k2 = self._att_ops(gate, level, (n, *dims))
         w, b = gate.conv.weight, gate.conv.bias
-        wp = k1.fwd.packed_weight(w, self.act_dtype)
+        wp = self._pw(k1.fwd, w)
         bp = k1.fwd.packed_bias(b)
         xs, f, z, out = (self._new_act(n, dims, c) for _ in range(4))
         ops.conv_gemm(k1.fwd, [skip], wp, [xs], k1.grid, bias=bp)
@@ -264,10 +371,10 @@ class UNetEngine:
         w = gate.conv.weight
         cp = xs.shape[-1]
         dxs, dz, df, dpre, t, dskip, dup = (self._grad_like(xs) for _ in range(7))
-        sums = torch.zeros(cp, 2, dtype=torch.float64, device=self.device)
-        psum = torch.zeros(cp, dtype=torch.float64, device=self.device)
+        sums = self._z64(cp, 2)
+        psum = self._z64(cp)
         ops.att_gate_bwd(d_out, xs, z, dxs, dz, sums)
-        wp = k1.dgrad.packed_weight(w, self.act_dtype)
+        wp = self._pw(k1.dgrad, w)
         ops.conv_gemm(k1.dgrad, [dz], wp, [df], k1.grid)
         ops.att_mid_bwd(df, f, dxs, dpre, t, psum)
         ops.conv_gemm(k1.dgrad, [t], wp, [dskip], k1.grid)                       # W^T (dxs + dpre)
@@ -290,6 +397,8 @@ class UNetEngine:
         net, owner = self.net, self.owner
         train = owner.training
         owner.last_dropout_masks = []
+        self._prepack()
+        self._z_begin()
         N, _, D, H, W = x.shape
         np_ = net.num_pool
         dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
@@ -370,7 +479,7 @@ class UNetEngine:
         grads[blk.conv2.weight] = self._wgrad(c2, [a1], dy2, blk.conv2.weight)
         grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias)       # cancelled by the norm (S1)
         da1 = self._grad_like(a1)
-        ops.conv_gemm(c2.dgrad, [dy2], c2.dgrad.packed_weight(blk.conv2.weight, self.act_dtype), [da1], c2.grid)
+        ops.conv_gemm(c2.dgrad, [dy2], self._pw(c2.dgrad, blk.conv2.weight), [da1], c2.grid)
         _, dy1, _, _ = self._in_bwd(da1, None, a1, y1, t1)
         grads[blk.conv1.weight] = self._wgrad(c1, inputs, dy1, blk.conv1.weight)
         grads[blk.conv1.bias] = torch.zeros_like(blk.conv1.bias)
@@ -380,10 +489,10 @@ class UNetEngine:
             grads[blk.skip_conv.weight] = self._wgrad(sk, inputs, g2, blk.skip_conv.weight)
             grads[blk.skip_conv.bias] = self._unscale(sums2[:, :blk.out_channels, 0].sum(0).float())
             dp = c1.dgrad_in
-            ops.conv_gemm(dp, [dy1, g2], dp.packed_weight([blk.conv1.weight, blk.skip_conv.weight], self.act_dtype), dins,
+            ops.conv_gemm(dp, [dy1, g2], self._pw(dp, [blk.conv1.weight, blk.skip_conv.weight]), dins,
                           c1.grid)
         else:
-            ops.conv_gemm(c1.dgrad, [dy1], c1.dgrad.packed_weight(blk.conv1.weight, self.act_dtype), dins, c1.grid,
+            ops.conv_gemm(c1.dgrad, [dy1], self._pw(c1.dgrad, blk.conv1.weight), dins, c1.grid,
                           addends=[g2])
         return dins
 
@@ -395,7 +504,7 @@ class UNetEngine:
         grads[blk.conv.weight] = self._wgrad(op, inputs, dy, blk.conv.weight)
         grads[blk.conv.bias] = torch.zeros_like(blk.conv.bias)          # cancelled by the norm (S1)
         dins = [self._grad_like(x) for x in inputs]
-        ops.conv_gemm(op.dgrad, [dy], op.dgrad.packed_weight(blk.conv.weight, self.act_dtype), dins, op.grid)
+        ops.conv_gemm(op.dgrad, [dy], self._pw(op.dgrad, blk.conv.weight), dins, op.grid)
         return dins
 
     # ------------------------------------------------------------------ backward
@@ -405,6 +514,8 @@ class UNetEngine:
         N, _, D, H, W = x_shape
         dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
         grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self._z_begin()
+        self._begin_wgrads()
         # fp16 gradients need a scale to stay inside fp16's range (Dice gradients are ~1e-7 per voxel).  It is
         # internal and dynamic: a power of two that puts max|dlogits| at 64, taken from this step's dlogits on the
         # device (no host sync), multiplied in by head_bwd and divided out of every parameter gradient.
@@ -434,7 +545,7 @@ class UNetEngine:
             grads[ct.weight] = self._wgrad(uop, [xin], dyu, ct.weight)
             grads[ct.bias] = self._unscale(dsum[:ct.out_channels].float())
             d_cur = self._grad_like(xin)
-            ops.conv_gemm(uop.dgrad, [dyu], uop.dgrad.packed_weight(ct.weight, self.act_dtype), [d_cur], uop.grid)
+            ops.conv_gemm(uop.dgrad, [dyu], self._pw(uop.dgrad, ct.weight), [d_cur], uop.grid)
         d_cur = self._block_bwd(net.encode_blocks[np_], ("enc", np_), tape[("enc", np_)], d_cur, None, grads)[0]
         for i in range(np_ - 1, -1, -1):
             d_cur = self._block_bwd(net.pool_blocks[i], ("pool", i), tape[("pool", i)], d_cur, None, grads)[0]
@@ -447,6 +558,7 @@ class UNetEngine:
         dw0 = dw0.view(28, cp0)
         grads[net.conv.weight] = self._unscale(dw0[:27, :c0].t().reshape(net.conv.weight.shape))
         grads[net.conv.bias] = self._unscale(dw0[27, :c0].clone())
+        self._finish_wgrads()
         self._inv_scale = None
         return grads
 

@@ -113,28 +113,37 @@ class DeviceConvPlan:
         self._b_version = None
         self._b_packed = None
 
+    @staticmethod
+    def weight_key(w, dtype, key=None):
+        if isinstance(w, (list, tuple)):
+            return tuple((t.data_ptr(), t._version) for t in w) + (dtype, PACK_EPOCH)
+        return (w.data_ptr(), w._version, dtype, PACK_EPOCH) if key is None else tuple(key) + (PACK_EPOCH,)
+
+    def pack_buffer(self, dtype, device) -> torch.Tensor:
+        """The persistent 16-bit tile-stream buffer of this plan (its address is what batched pack tables hold)."""
+        if self._w_packed is None or self._w_packed.dtype != dtype:
+            self._w_packed = torch.empty(self.widx.numel(), dtype=dtype, device=device)
+            self._w_version = None
+        return self._w_packed
+
     def packed_weight(self, w, dtype=torch.bfloat16, key=None) -> torch.Tensor:
-        """16-bit tile stream of parameter `w` (re-gathered only when the parameter or the dtype changed).
+        """16-bit tile stream of parameter `w` (re-gathered only when the parameter, the dtype or ops.PACK_EPOCH changed).
         `w` may be a list of parameters: the plan's gather index then addresses their concatenation.
         `key`: cache key to use when `w` is a temporary derived from parameters (its own address means nothing)."""
+        k = self.weight_key(w, dtype, key)
+        if self._w_version == k and not torch.cuda.is_current_stream_capturing():   # a graph must re-pack on every replay
+            return self._w_packed
         if isinstance(w, (list, tuple)):
-            key = tuple((t.data_ptr(), t._version) for t in w) + (dtype, PACK_EPOCH)
-            if self._w_version == key and not torch.cuda.is_current_stream_capturing():
-                return self._w_packed
-            packed = self.packed_weight(torch.cat([t.detach().reshape(-1).float() for t in w]), dtype)
-            self._w_version = key
-            return packed
-        key = (w.data_ptr(), w._version, dtype, PACK_EPOCH) if key is None else tuple(key) + (PACK_EPOCH,)
-        if self._w_version != key or torch.cuda.is_current_stream_capturing():   # a graph must re-pack on every replay
+            src = torch.cat([t.detach().reshape(-1).float() for t in w])
+        else:
             src = w.detach()
             if src.dtype != torch.float32 or not src.is_contiguous():
                 src = src.float().contiguous()
-            out = torch.empty(self.widx.numel(), dtype=dtype, device=src.device)
-            _count()
-            _lib.check(_lib.lib().unet3d_weight_pack(src.data_ptr(), self.widx.data_ptr(), out.data_ptr(), out.numel(),
-                                                     int(dtype == torch.float16), _stream()), "unet3d_weight_pack")
-            self._w_packed = out
-            self._w_version = key
+        out = self.pack_buffer(dtype, src.device)
+        _count()
+        _lib.check(_lib.lib().unet3d_weight_pack(src.data_ptr(), self.widx.data_ptr(), out.data_ptr(), out.numel(),
+                                                 int(dtype == torch.float16), _stream()), "unet3d_weight_pack")
+        self._w_version = k
         return self._w_packed
 
     def packed_bias(self, b: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -195,11 +204,41 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
         _lib.check(_lib.lib().unet3d_conv_gemm(C.byref(a), _stream()), "unet3d_conv_gemm")
 
 
+class GatherTable:
+    """Device-resident job table of unet3d_gather_multi: many `out = src[idx]` gathers in one launch."""
+
+    def __init__(self, jobs: Sequence[dict], device):
+        """jobs: dicts with src0, idx (tensors), optional src1 (tensor), out (tensor, or an int byte offset that is
+        added to the `out_base` given at launch), n0, mode (0 bf16, 1 fp16, 2 fp32 * scale)."""
+        arr = (_lib.GatherJob * len(jobs))()
+        first = [0]
+        self._keep = []
+        for i, j in enumerate(jobs):
+            n = j["idx"].numel()
+            assert j["idx"].dtype == torch.int32 and j["src0"].dtype == torch.float32 and j["src0"].is_contiguous()
+            arr[i].src0 = j["src0"].data_ptr()
+            arr[i].src1 = j["src1"].data_ptr() if j.get("src1") is not None else None
+            arr[i].idx = j["idx"].data_ptr()
+            arr[i].out = j["out"].data_ptr() if isinstance(j["out"], torch.Tensor) else int(j["out"])
+            arr[i].n, arr[i].n0, arr[i].mode = n, int(j.get("n0", 0)), int(j["mode"])
+            first.append(first[-1] + -(-n // 2048))
+            self._keep.append((j["src0"], j.get("src1"), j["idx"], j["out"]))
+        self.jobs_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        self.first = torch.tensor(first, dtype=torch.int32, device=device)
+        self.n_jobs, self.n_blocks = len(jobs), first[-1]
+
+    def launch(self, scale: Optional[torch.Tensor] = None, out_base: Optional[torch.Tensor] = None):
+        _count()
+        _lib.check(_lib.lib().unet3d_gather_multi(self.jobs_dev.data_ptr(), self.first.data_ptr(), self.n_jobs, self.n_blocks,
+                                                  _ptr(scale), _ptr(out_base), _stream()), "unet3d_gather_multi")
+
+
 class DeviceWgradPlan:
     def __init__(self, plan: P.WgradPlan, device):
         self.plan = plan
         self.tab = torch.from_numpy(plan.tab).to(device)
         self.gidx = torch.from_numpy(plan.gidx).to(device)
+        self.gidx32 = self.gidx.to(torch.int32)
 
 
 def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor, dw: torch.Tensor,

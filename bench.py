@@ -199,15 +199,19 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ops.PROFILE = []
     ops.LAUNCHES = 0
     ms = timed(K, e2e=False)
     launches = ops.LAUNCHES
-    prof = ops.PROFILE
-    ops.PROFILE = None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    # per-kernel CUDA events for the roofline: a REPEAT of the timed region (same steps, same inputs, same clocks window)
+    # with an event pair around every launch -- kept out of `value` because ~700 event records per step cost ~1.5 ms
+    ops.PROFILE = []
+    timed(K, e2e=False)
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(max(2, min(K, 5)), e2e=True)
     ops.check_device_errors()

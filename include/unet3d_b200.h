@@ -83,6 +83,23 @@ size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, in
  * out[i] = idx[i] < 0 ? 0 : w[idx[i]]; idx (device int32, n elements, n % 8 == 0 preferred) comes from the host plan. */
 int unet3d_weight_pack(const float* w, const int* idx, void* out, long long n, int out_f16, void* stream);
 
+/* Batched form of the gather above, for all layers of a step in one launch.  Job i covers the blocks
+ * [first_block[i], first_block[i+1]) of 2048 elements:  out[k] = idx[k] < 0 ? 0 : src[idx[k]],  src = src0 (n0 elements)
+ * followed by src1 when src1 != NULL.  mode 0 / 1: out is bf16 / fp16 (weight packing); mode 2: out is fp32 and is
+ * multiplied by *scale when scale != NULL (weight-gradient accumulators -> PyTorch parameter layout).
+ * Every job's `out` is taken relative to out_base (pass NULL for absolute pointers). */
+typedef struct unet3d_gather_job {
+  const float* src0;
+  const float* src1;
+  const int* idx;
+  void* out;
+  long long n;
+  int n0;
+  int mode;
+} unet3d_gather_job;
+int unet3d_gather_multi(const unet3d_gather_job* jobs_dev, const int* first_block_dev, int n_jobs, int n_blocks,
+                        const float* scale, void* out_base, void* stream);
+
 /* Weight gradient on tcgen05 tensor cores (wgrad_gemm.cu): dW[tap][cin][cout] = sum_v x[v+tap][cin] dy[v][cout].
  * Replaces the cuDNN backward-filter dispatch of the layers listed above. */
 typedef struct unet3d_wgrad_args {

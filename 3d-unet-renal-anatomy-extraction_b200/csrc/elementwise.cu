@@ -693,6 +693,15 @@ __global__ void weight_pack_kernel(const float* __restrict__ w, const int* __res
   }
 }
 
+// grid.x for the (voxel-row, sample) kernels: ~2 voxel rows per thread for small tensors (a thread that loops over
+// 16-32 rows of a 1 MB tensor is DRAM-latency bound: ~20 us launches at levels 3-4), capped at `waves` CTA waves over
+// the whole (gx, N) grid for large ones.
+inline int grid_rows(long long V, int rows_per_block, int N, int num_sms, int waves) {
+  long long need = (V + 2LL * rows_per_block - 1) / (2LL * rows_per_block);
+  long long cap = ((long long)num_sms * waves + N - 1) / N;
+  long long g = need < cap ? need : cap;
+  return (int)(g < 1 ? 1 : g);
+}
 inline int grid_for(long long work_items, int per_block, int num_sms, int waves) {
   long long need = (work_items + per_block - 1) / per_block;
   long long cap = (long long)num_sms * waves;
@@ -965,8 +974,7 @@ int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
-  int gx = grid_for(V, blk.y * 4, num_sms, 16) / N;
-  if (gx < 1) gx = 1;
+  const int gx = grid_rows(V, blk.y, N, num_sms, 16);
   dim3 grd(gx, N);
   if (skip)
     in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (const float2*)table, chunks, V, Cp, af);
@@ -980,8 +988,7 @@ int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
-  int gx = grid_for(V, blk.y * 8, num_sms, 8) / N;
-  if (gx < 1) gx = 1;
+  const int gx = grid_rows(V, blk.y, N, num_sms, 8);
   dim3 grd(gx, N);
   const size_t sm = (size_t)blk.y * Cp * 2 * sizeof(float);
   if (dout2)
@@ -999,8 +1006,7 @@ int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, con
   const int chunks = Cp / 8;
   const long long V = (long long)D * H * W;
   dim3 blk = cv_block(chunks);
-  int gx = grid_for(V, blk.y * 8, num_sms, 8) / N;
-  if (gx < 1) gx = 1;
+  const int gx = grid_rows(V, blk.y, N, num_sms, 8);
   dim3 grd(gx, N);
   const size_t sm = dsum ? (size_t)blk.y * Cp * sizeof(float) : 0;
 #define U3D_BWD_APPLY(Z, S)                                                                                         \

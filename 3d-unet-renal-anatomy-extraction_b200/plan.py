@@ -103,9 +103,10 @@ _L2_BYTES_PER_CLK = 3700.0          # whole-chip L2 -> SM bandwidth the cost mod
 
 
 def _mma_cycles(n: int) -> float:
-    """One M=128, K=16 UMMA of width n: tensor floor n/2 cycles, or the 128 B/clk shared-memory operand read
-    (4 KB of A + 32 n bytes of B) when that is slower (measured: profiles/r01_notes.md)."""
-    return max(n / 2.0, 32.0 + n / 4.0)
+    """Sustained cycles of one M=128, K=16 tcgen05.mma of width n with both operands in shared memory, measured back
+    to back on a B200 (tools/probe/mma_rate.cu): 47 / 51 / 56 / 64 / 96 / 128 for n = 32 / 64 / 96 / 128 / 192 / 256 --
+    the tensor floor n/2 above n = 128, a ~45-cycle operand-read floor below it, independent of layout and swizzle."""
+    return max(n / 2.0, 42.0 + n / 7.0)
 
 
 def choose_config(out_cp: int, chunk_counts: Sequence[int], grid, taps_per_cg: float, n_out_par: int, can_fuse: bool):
@@ -145,6 +146,8 @@ def choose_config(out_cp: int, chunk_counts: Sequence[int], grid, taps_per_cg: f
                         mma = n_cg * (taps_per_cg / 3.0) * per_tap
                     else:
                         mma = n_cg * taps_per_cg * dt * g2 * _mma_cycles(nblk)
+                    if not (fuse == 3 and nblk in (32, 64)):
+                        mma *= 1.3          # generic issue path: per-tap table / mask bookkeeping on the issuing thread
                     a_bytes = n_cg * (dt + 2) * g * 2880 * (2.0 if g == 1 else 1.0)     # rows of 16 g >= 32 bytes: whole sectors
                     w_bytes = n_cg * taps_per_cg * g * nblk * 16
                     active = min(items, NUM_SMS)
@@ -646,7 +649,14 @@ def make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: in
     gidx = (kf * Kp + kreal[ci]) * Np + co
     n_tiles_min = N_ * (-(-max(1, D_) // 8)) * (-(-H_ // HT)) * (-(-W_ // WT))
     n_tiles_max = N_ * max(1, D_) * (-(-H_ // HT)) * (-(-W_ // WT))
-    split = max(1, min(n_tiles_max, -(-(2 * num_sms) // len(jobs))))
+    # CTAs = jobs x split, one CTA per SM at a time (227 KB of shared memory): never spill a few CTAs into an extra
+    # wave (6 jobs x 50 = 300 CTAs ran 40 % slower than 6 x 74 = 444 = exactly three waves), so round DOWN to whole
+    # waves.  One wave unless there are more jobs than SMs (measured: fewer, longer CTAs win -- less split-K
+    # reduction traffic and pipeline fill).  Env U3D_WG_WAVES overrides (sweeps).
+    waves = int(os.environ.get("U3D_WG_WAVES", "1"))
+    if len(jobs) > waves * num_sms:
+        waves = -(-len(jobs) // num_sms)
+    split = max(1, min(n_tiles_max, (waves * num_sms) // len(jobs)))
     return WgradPlan(kind=kind, x_maps=x_maps, y_maps=y_maps, tab=tab.reshape(-1).astype(np.int32), jobs=jobs,
                      n_jobs=len(jobs), job_stride=job_stride, split=split, dw_numel=dw_numel, ld=ld,
                      gidx=gidx.reshape(-1).astype(np.int64), flops_per_voxel=2.0 * Ktot * Ntot * k3)

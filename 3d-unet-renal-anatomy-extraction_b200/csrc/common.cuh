@@ -167,6 +167,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "memory");
 }
 
+// zero 32 lanes (this warp's TMEM lane quarter) x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_st_zero_32x32(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory matrix descriptor, no swizzle (layout type 0), sm_100 version field = 1.
 //   K-major operand:  8 rows x 16 B core matrices; LBO = byte stride between the two K chunks of
 //                     one MMA (K=16 bf16 = 2 x 16 B), SBO = byte stride between 8-row groups.

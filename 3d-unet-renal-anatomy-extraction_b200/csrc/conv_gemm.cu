@@ -130,30 +130,17 @@ __device__ __forceinline__ void issue_tap_dense(uint32_t acc0, uint64_t aslab, u
   constexpr uint64_t A_KINC = 2;
   constexpr uint64_t B_KINC = (uint64_t)(2 * 3 * NBLK);
   const uint64_t adesc0 = aslab + (uint64_t)(((t / 3) * CG_WB + (t % 3)) * 2 * G2);   // (kh * 10 + kw) rows of 32 * G2 bytes, in 16-B units
-  if (t == 0 && first) {
-    // first tap of an item: unfused, so that the first MMA into every accumulator overwrites it
+  (void)first;      // the epilogue hands every accumulator buffer back ZEROED (tcgen05.st), so every tap accumulates
 #pragma unroll
-    for (int d = 0; d < DT; ++d) {
+  for (int pl = 0; pl < DT + 2; ++pl) {
+    const int hi = pl < 2 ? pl : 2;
+    const int lo = pl - DT + 1 > 0 ? pl - DT + 1 : 0;
+    const int cnt = hi - lo + 1;
+    const uint32_t id = cnt == 3 ? idesc3 : (cnt == 2 ? idesc2 : idesc1);
 #pragma unroll
-      for (int sd = 0; sd < 3; ++sd) {
-#pragma unroll
-        for (int kk = 0; kk < G2; ++kk)
-          tc_mma_bf16(acc0 + (uint32_t)(d * NBLK), adesc0 + (uint64_t)(d + sd) * A_DINC + kk * A_KINC,
-                      bdesc0 + (uint64_t)((2 - sd) * NBLK) + kk * B_KINC, idesc1, (sd | kk) ? 1u : 0u);
-      }
-    }
-  } else {
-#pragma unroll
-    for (int pl = 0; pl < DT + 2; ++pl) {
-      const int hi = pl < 2 ? pl : 2;
-      const int lo = pl - DT + 1 > 0 ? pl - DT + 1 : 0;
-      const int cnt = hi - lo + 1;
-      const uint32_t id = cnt == 3 ? idesc3 : (cnt == 2 ? idesc2 : idesc1);
-#pragma unroll
-      for (int kk = 0; kk < G2; ++kk)
-        tc_mma_bf16(acc0 + (uint32_t)((pl - hi) * NBLK), adesc0 + (uint64_t)pl * A_DINC + kk * A_KINC,
-                    bdesc0 + (uint64_t)((2 - hi) * NBLK) + kk * B_KINC, id, 1u);
-    }
+    for (int kk = 0; kk < G2; ++kk)
+      tc_mma_bf16(acc0 + (uint32_t)((pl - hi) * NBLK), adesc0 + (uint64_t)pl * A_DINC + kk * A_KINC,
+                  bdesc0 + (uint64_t)((2 - hi) * NBLK) + kk * B_KINC, id, 1u);
   }
 }
 
@@ -305,6 +292,17 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  if (p.dense) {
+    // dense path: accumulators start (and are handed back by the epilogue) zeroed, so that no tap needs the
+    // overwrite form -- the first tap of an item then runs d-fused like all others (10 wide MMAs instead of 24 narrow)
+    if (warp >= 3 && warp < 7) {
+      for (int c = 0; c < 512; c += 32) tmem_st_zero_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + c);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   volatile int* abort_flag = &ctl->abort_flag;
   const uint32_t* tap_off = ctl->tap_off;
 
@@ -518,8 +516,10 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
                                 (long long)ow * p.out_sW + coff;
           uint32_t raw[32];
           __syncwarp();
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)d * p.nblk + cc * 32, raw);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)d * p.nblk + cc * 32;
+          tmem_ld_32x32(taddr, raw);
           tmem_ld_wait();
+          if (p.dense) tmem_st_zero_32x32(taddr);
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -577,6 +577,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
           ssq[cc] += warp_colsum32(a2, lane);
         }
       }
+      if (p.dense) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty[buf]));

@@ -73,6 +73,7 @@ class UNetEngine:
         self._dw_slots, self._dw_order, self._dw_table, self._dw_table_n = {}, [], None, 0
         self._dw_arena, self._gflat, self._g_total, self._dw_ready = None, None, 0, False
         self._z_arena, self._z_used, self._z_demand, self._z_size = None, 0, 0, 0
+        self._last_gflat = None
 
     # ------------------------------------------------------------------ public entry
     def run(self, x: torch.Tensor) -> torch.Tensor:
@@ -195,8 +196,10 @@ class UNetEngine:
             self._dw_ready = True
 
     def _finish_wgrads(self):
+        self._last_gflat = None
         if self._dw_ready:
             self._dw_table.launch(scale=self._inv_scale, out_base=self._gflat)
+            self._last_gflat = self._gflat
             self._dw_ready = False
         elif self._dw_order and (self._dw_table is None or self._dw_table_n != len(self._dw_order)):
             off = goff = 0
@@ -212,6 +215,12 @@ class UNetEngine:
                 jobs.append(dict(src0=self._dw_arena[o:o + wp.plan.dw_numel + 1], idx=wp.gidx32, out=4 * g, mode=2))
             self._dw_table = ops.GatherTable(jobs, self.device)
             self._dw_table_n = len(self._dw_order)
+
+    def flat_weight_gradients(self) -> Optional[torch.Tensor]:
+        """The flat fp32 buffer the conv weight gradients of the most recent backward are views of (None while the
+        first, layer-by-layer backward of a shape has not recorded the layout): ONE all-reduce covers 99.9 % of the
+        gradient bytes without flattening copies (parallel.all_reduce_gradients)."""
+        return self._last_gflat
 
     # ------------------------------------------------------------------ packed weights: one batched launch per step
     def _pw(self, dp, w):

@@ -48,19 +48,40 @@ def gradient_buckets(params: List[torch.nn.Parameter], bucket_bytes: int = BUCKE
     return buckets
 
 
+def _flat_gradient_buffers(model: torch.nn.Module) -> List[torch.Tensor]:
+    """Flat buffers that already hold (as views) the conv weight gradients of the engine(s) inside `model`."""
+    out = []
+    for m in model.modules():
+        eng = getattr(m, "_engine", None)
+        flat = eng.flat_weight_gradients() if eng is not None and hasattr(eng, "flat_weight_gradients") else None
+        if flat is not None:
+            out.append(flat)
+    return out
+
+
 def all_reduce_gradients(model: torch.nn.Module, average: bool = True):
-    """Bucketed gradient all-reduce (mean over ranks).  No-op in a single-process run."""
+    """Gradient all-reduce (mean over ranks).  No-op in a single-process run.  The engine's flat weight-gradient
+    buffer (335 MB of the 336 MB at the default net) is reduced in place with one collective; the remaining small
+    tensors (biases, stem, head) go through flattened buckets."""
     rank, world = rank_world()
     if world == 1:
         return
     works = []
-    for bucket in gradient_buckets(list(model.parameters())):
+    flats = _flat_gradient_buffers(model)
+    spans = [(f.data_ptr(), f.data_ptr() + f.numel() * f.element_size()) for f in flats]
+    for f in flats:
+        works.append((dist.all_reduce(f, op=dist.ReduceOp.SUM, async_op=True), f, None))
+    rest = [p for p in model.parameters()
+            if p.grad is not None and not any(a <= p.grad.data_ptr() < b for a, b in spans)]
+    for bucket in gradient_buckets(rest):
         flat = torch.cat([p.grad.reshape(-1) for p in bucket])
         works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, bucket))
     for work, flat, bucket in works:
         work.wait()
         if average:
             flat.div_(world)
+        if bucket is None:
+            continue
         off = 0
         for p in bucket:
             n = p.grad.numel()

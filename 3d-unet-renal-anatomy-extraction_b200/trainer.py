@@ -97,6 +97,17 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
     window: None = uniform blending (the reference), "gaussian" or a (px,py,pz) float array = weighted.
     Under an initialised torch.distributed job the windows are dealt round-robin to the ranks and the
     partial sums are all-reduced; every rank returns the full result."""
+    import os
+    import time
+    dbg = os.environ.get("U3D_PREDICT_TIMES")
+    t_dbg = [time.perf_counter()]
+
+    def mark(what):
+        if dbg:
+            torch.cuda.synchronize()
+            t_dbg.append(time.perf_counter())
+            print(f"[predict_per_patch rank {parallel.rank_world()[0]}] {what}: {t_dbg[-1] - t_dbg[-2]:.3f} s", flush=True)
+
     device = next(model.parameters()).device
     patch = tuple(int(p) for p in patch_size)
     orig_shape = input.shape[:3]
@@ -115,6 +126,7 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
         window = gaussian_window(patch)
     wdev = None if window is None else torch.as_tensor(window, dtype=torch.float32, device=device).contiguous()
 
+    mark("pad + H2D + buffers")
     was_training = model.training
     model.eval()
     it = mine
@@ -127,8 +139,10 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
             logits = model(tile)
             ops.sw_accumulate(logits[0].contiguous(), wdev, result, weight, (ox, oy, oz))
     model.train(was_training)
+    mark(f"{len(mine)} windows")
     if world > 1:
         parallel.all_reduce_sum([result, weight])
+        mark("all-reduce of the blend buffers")
     if one_hot:
         probs = torch.empty((*shape, num_classes), dtype=torch.float32, device=device)
         ops.sw_finalize(result, weight, None, probs)
@@ -138,6 +152,7 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
         ops.sw_finalize(result, weight, labels, None)
         res = labels.cpu().numpy()
     ops.check_device_errors()
+    mark("finalize + D2H")
     return center_pad_crop(res, orig_shape)
 
 

@@ -105,9 +105,13 @@ class DeviceConvPlan:
     def __init__(self, plan: P.ConvPlan, device):
         self.plan = plan
         self.device = device
-        self.tab = torch.from_numpy(plan.tab).to(device)
-        self.widx = torch.from_numpy(plan.widx).to(device)
-        self.bidx = torch.from_numpy(P.bias_index(plan)).to(device)
+        # the device copies of a (memoised, immutable) plan's tables are shared by all layers that use the plan
+        dev_key = str(torch.device(device))
+        cache = plan.__dict__.setdefault("_dev", {})
+        if dev_key not in cache:
+            cache[dev_key] = (torch.from_numpy(plan.tab).to(device), torch.from_numpy(plan.widx).to(device),
+                              torch.from_numpy(P.bias_index(plan)).to(device))
+        self.tab, self.widx, self.bidx = cache[dev_key]
         self._w_version = None
         self._w_packed = None
         self._b_version = None
@@ -236,9 +240,12 @@ class GatherTable:
 class DeviceWgradPlan:
     def __init__(self, plan: P.WgradPlan, device):
         self.plan = plan
-        self.tab = torch.from_numpy(plan.tab).to(device)
-        self.gidx = torch.from_numpy(plan.gidx).to(device)
-        self.gidx32 = self.gidx.to(torch.int32)
+        dev_key = str(torch.device(device))
+        cache = plan.__dict__.setdefault("_dev", {})
+        if dev_key not in cache:
+            gidx = torch.from_numpy(plan.gidx).to(device)
+            cache[dev_key] = (torch.from_numpy(plan.tab).to(device), gidx, gidx.to(torch.int32))
+        self.tab, self.gidx, self.gidx32 = cache[dev_key]
 
 
 def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor, dw: torch.Tensor,

@@ -249,8 +249,24 @@ def _kidx_and_valid(plan_kind: str, ks: int, stride: int, pattern: str, shift, p
     return tuple(k)
 
 
+_PLAN_CACHE: Dict[tuple, object] = {}
+_TUNING_ENV = ("U3D_CONV_CFG", "U3D_A_STAGES", "U3D_WG_WAVES")
+
+
 def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: Sequence[int], depth: int,
                    grid: Optional[Tuple[int, int, int, int]] = None, skip_k1: bool = False) -> ConvPlan:
+    """Memoised front end of _make_conv_plan: a network repeats the same layer shape many times (the nine level-4
+    blocks of the default net share two plans), and building the gather index of a 480x480x27 weight costs ~0.1 s of
+    numpy work.  Plans are immutable after construction."""
+    key = ("conv", kind, ks, stride, tuple(in_C), tuple(out_C), depth, None if grid is None else tuple(grid), skip_k1,
+           tuple(os.environ.get(k) for k in _TUNING_ENV))
+    if key not in _PLAN_CACHE:
+        _PLAN_CACHE[key] = _make_conv_plan(kind, ks, stride, in_C, out_C, depth, grid, skip_k1)
+    return _PLAN_CACHE[key]
+
+
+def _make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: Sequence[int], depth: int,
+                    grid: Optional[Tuple[int, int, int, int]] = None, skip_k1: bool = False) -> ConvPlan:
     """kind:
          conv_fwd    Conv3d forward (weight (Cout, Cin, k,k,k)); inputs may be a concat (len(in_C) > 1)
          conv_dgrad  its data gradient; outputs may be a concat split (len(out_C) > 1)
@@ -494,6 +510,15 @@ _WG_DT_CANDIDATES = (8, 6, 5, 4, 3, 2, 1)
 
 def make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: int, dims: Tuple[int, int, int, int],
                     num_sms: int = 148) -> WgradPlan:
+    """Memoised front end of _make_wgrad_plan (see make_conv_plan)."""
+    key = ("wgrad", kind, ks, stride, tuple(x_C), y_C, tuple(dims), num_sms, tuple(os.environ.get(k) for k in _TUNING_ENV))
+    if key not in _PLAN_CACHE:
+        _PLAN_CACHE[key] = _make_wgrad_plan(kind, ks, stride, x_C, y_C, dims, num_sms)
+    return _PLAN_CACHE[key]
+
+
+def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: int, dims: Tuple[int, int, int, int],
+                     num_sms: int = 148) -> WgradPlan:
     """Weight gradient of
          kind='conv' : Conv3d weight (Cout=y_C, Cin=sum(x_C), k,k,k), stride 1 or 2 (x may be a concat)
          kind='convT': ConvTranspose3d(k3,s2,p1) weight (Cin=x_C[0], Cout=y_C, 3,3,3); dy lives on the fine grid

@@ -489,7 +489,7 @@ class UNetEngine:
         grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias)       # cancelled by the norm (S1)
         da1 = self._grad_like(a1)
         ops.conv_gemm(c2.dgrad, [dy2], self._pw(c2.dgrad, blk.conv2.weight), [da1], c2.grid)
-        _, dy1, _, _ = self._in_bwd(da1, None, a1, y1, t1)
+        _, dy1, _, _ = self._in_bwd(da1, None, None, y1, t1)          # no residual: sign from the normalised value
         grads[blk.conv1.weight] = self._wgrad(c1, inputs, dy1, blk.conv1.weight)
         grads[blk.conv1.bias] = torch.zeros_like(blk.conv1.bias)
         dins = [self._grad_like(t) for t in inputs]
@@ -509,7 +509,7 @@ class UNetEngine:
         inputs, y, t, a = rec
         in_C = self._split_channels(blk.in_channels, inputs)
         op = self._op(key + ("conv",), "conv", 3, 1, in_C, blk.out_channels, (inputs[0].shape[0], *y.shape[1:4]))
-        _, dy, _, _ = self._in_bwd(dout, dout2, a, y, t)
+        _, dy, _, _ = self._in_bwd(dout, dout2, None, y, t)
         grads[blk.conv.weight] = self._wgrad(op, inputs, dy, blk.conv.weight)
         grads[blk.conv.bias] = torch.zeros_like(blk.conv.bias)          # cancelled by the norm (S1)
         dins = [self._grad_like(x) for x in inputs]
@@ -550,7 +550,7 @@ class UNetEngine:
             xin, yu, tu, au = tape[("up", i)]
             ct = net.up_blocks[i].conv_trans.up[0]
             uop = self._op(("up", i), "convT", 3, 2, [ct.in_channels], ct.out_channels, (N, *dims[i + 1]))
-            _, dyu, _, dsum = self._in_bwd(d_up, None, au, yu, tu, zero_last=True, want_dsum=True)
+            _, dyu, _, dsum = self._in_bwd(d_up, None, None, yu, tu, zero_last=True, want_dsum=True)
             grads[ct.weight] = self._wgrad(uop, [xin], dyu, ct.weight)
             grads[ct.bias] = self._unscale(dsum[:ct.out_channels].float())
             d_cur = self._grad_like(xin)

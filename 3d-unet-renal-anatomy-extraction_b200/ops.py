@@ -288,9 +288,9 @@ def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, t
 def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
     n, d, h, w, cp = y.shape
     _count()
-    assert dout.dtype == y.dtype and g.dtype == y.dtype and out.dtype == y.dtype
-    with _Timed("in_bwd_reduce", 0.0, y.numel() * 2.0 * (5 if dout2 is not None else 4)):
-        _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), out.data_ptr(), y.data_ptr(), g.data_ptr(),
+    assert dout.dtype == y.dtype and g.dtype == y.dtype and (out is None or out.dtype == y.dtype)
+    with _Timed("in_bwd_reduce", 0.0, y.numel() * 2.0 * (3 + (dout2 is not None) + (out is not None))):
+        _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), _ptr(out), y.data_ptr(), g.data_ptr(),
                                                    table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
                    "unet3d_in_bwd_reduce")
 

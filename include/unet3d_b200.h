@@ -122,6 +122,8 @@ int unet3d_in_finalize(const double* stats, const float* drop_scale, float* tabl
                        void* stream);
 int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, int N, long long V, int Cp,
                     int act_f16, void* stream);
+/* in_bwd_reduce: `out` may be NULL when the norm had no residual input (the activation's sign is then taken from the
+ * normalised value and the activation output is not read); dout2 may be NULL. */
 int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, void* g,
                          const float* table, double* sums, int N, long long V, int Cp, int act_f16, void* stream);
 int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums, double* dsum,

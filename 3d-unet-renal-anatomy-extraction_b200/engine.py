@@ -74,6 +74,7 @@ class UNetEngine:
         self._dw_arena, self._gflat, self._g_total, self._dw_ready = None, None, 0, False
         self._z_arena, self._z_used, self._z_demand, self._z_size = None, 0, 0, 0
         self._last_gflat = None
+        self._infer_graphs = {}          # predict_per_patch's captured window forwards, by (batch, channels, patch, precision)
 
     # ------------------------------------------------------------------ public entry
     def run(self, x: torch.Tensor) -> torch.Tensor:

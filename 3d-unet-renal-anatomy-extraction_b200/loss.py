@@ -38,7 +38,7 @@ class _SegLossFn(torch.autograd.Function):
     """mode bits: 1 = dice term (1 - d), 2 = focal term, 4 = dice metric (+d instead of 1 - d)."""
 
     @staticmethod
-    def forward(ctx, logits, target, w, alpha, beta, smooth, gamma, mode):
+    def forward(ctx, logits, target, w, alpha, beta, smooth, gamma, mode, global_batch=False):
         if not logits.is_cuda:
             raise RuntimeError("unet3d_b200 losses run on CUDA tensors only")
         n, k = logits.shape[:2]
@@ -52,6 +52,14 @@ class _SegLossFn(torch.autograd.Function):
         v = lg[0, 0].numel()
         sums = torch.zeros(k, 4, dtype=torch.float64, device=lg.device)
         ops.loss_fwd(lg, tg, sums, gamma)
+        if global_batch:
+            # exact large-batch equivalence under data parallelism: the per-class sums of ALL ranks
+            # enter the (nonlinear) Dice ratio, so every rank's logits gradient is the gradient of the one global loss
+            # and the parameter gradients must then be SUMMED over ranks (parallel.all_reduce_gradients(average=False))
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+                n = n * dist.get_world_size()
         tp, sp, sg, fo = sums[:, 0], sums[:, 1], sums[:, 2], sums[:, 3]
         den = (1 - alpha - beta) * tp + alpha * sg + beta * sp + smooth
         dice = (tp + smooth) / den
@@ -81,17 +89,18 @@ class _SegLossFn(torch.autograd.Function):
         lg, tg, coef = ctx.saved_tensors
         dl = torch.empty_like(lg)
         ops.loss_bwd(lg, tg, coef, gout.detach().float().contiguous().view(1), dl, ctx.gamma, ctx.use_focal)
-        return dl, None, None, None, None, None, None, None
+        return dl, None, None, None, None, None, None, None, None
 
 
 class DiceLoss(nn.Module):
-    def __init__(self, weight_c=None, weight_v=None, alpha=0.5, beta=0.5, smooth=1e-7):
+    def __init__(self, weight_c=None, weight_v=None, alpha=0.5, beta=0.5, smooth=1e-7, *, global_batch=False):
         super().__init__()
         self.weight_c, self.weight_v, self.alpha, self.beta, self.smooth = weight_c, weight_v, alpha, beta, smooth
+        self.global_batch = global_batch        # not in the reference: Dice over the batch of ALL data-parallel ranks
 
     def forward(self, input, target):
         w = _class_weights(input.size(1), self.weight_v, input.device)
-        return _SegLossFn.apply(input, target, w, self.alpha, self.beta, self.smooth, 0.0, 1)
+        return _SegLossFn.apply(input, target, w, self.alpha, self.beta, self.smooth, 0.0, 1, self.global_batch)
 
 
 class Dice(nn.Module):
@@ -105,26 +114,28 @@ class Dice(nn.Module):
 
 
 class FocalLoss(nn.Module):
-    def __init__(self, gamma=2, weight_c=None, weight_v=None):
+    def __init__(self, gamma=2, weight_c=None, weight_v=None, *, global_batch=False):
         super().__init__()
         self.gamma, self.weight_c, self.weight_v = gamma, weight_c, weight_v
+        self.global_batch = global_batch
 
     def forward(self, input, target):
         w = _class_weights(input.size(1), self.weight_v, input.device)
-        return _SegLossFn.apply(input, target, w, 0.5, 0.5, 1e-7, float(self.gamma), 2)
+        return _SegLossFn.apply(input, target, w, 0.5, 0.5, 1e-7, float(self.gamma), 2, self.global_batch)
 
 
 class HybirdLoss(nn.Module):
     """(sic) the reference's spelling, loss.py:196."""
 
-    def __init__(self, gamma=2, weight_c=None, weight_v=None, alpha=0.5, beta=0.5, smooth=1e-7):
+    def __init__(self, gamma=2, weight_c=None, weight_v=None, alpha=0.5, beta=0.5, smooth=1e-7, *, global_batch=False):
         super().__init__()
         self.gamma, self.weight_c, self.weight_v = gamma, weight_c, weight_v
         self.alpha, self.beta, self.smooth = alpha, beta, smooth
+        self.global_batch = global_batch
 
     def forward(self, input, target):
         w = _class_weights(input.size(1), self.weight_v, input.device)
-        return _SegLossFn.apply(input, target, w, self.alpha, self.beta, self.smooth, float(self.gamma), 3)
+        return _SegLossFn.apply(input, target, w, self.alpha, self.beta, self.smooth, float(self.gamma), 3, self.global_batch)
 
 
 def dice(input, target, alpha=0.5, beta=0.5, smooth=1e-7):

@@ -135,7 +135,9 @@ class DeviceConvPlan:
         `w` may be a list of parameters: the plan's gather index then addresses their concatenation.
         `key`: cache key to use when `w` is a temporary derived from parameters (its own address means nothing)."""
         k = self.weight_key(w, dtype, key)
-        if self._w_version == k and not torch.cuda.is_current_stream_capturing():   # a graph must re-pack on every replay
+        # a TRAINING graph must re-pack on every replay (the optimizer step is part of it); an inference graph
+        # (no_grad) replays against the weights it was captured with
+        if self._w_version == k and not (torch.cuda.is_current_stream_capturing() and torch.is_grad_enabled()):
             return self._w_packed
         if isinstance(w, (list, tuple)):
             src = torch.cat([t.detach().reshape(-1).float() for t in w])
@@ -154,7 +156,7 @@ class DeviceConvPlan:
         if b is None:
             return None
         key = (b.data_ptr(), b._version, PACK_EPOCH)
-        if self._b_version != key or torch.cuda.is_current_stream_capturing():
+        if self._b_version != key or (torch.cuda.is_current_stream_capturing() and torch.is_grad_enabled()):
             flat = torch.cat([b.detach().reshape(-1).float(), b.new_zeros(1, dtype=torch.float32)])
             self._b_packed = flat.index_select(0, self.bidx).contiguous()
             self._b_version = key

@@ -90,11 +90,15 @@ def gaussian_window(patch: Sequence[int], sigma_scale: float = 0.125) -> np.ndar
 # sliding-window inference
 # ------------------------------------------------------------------------------------------------
 def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step_per_patch=4, verbose=True,
-                      one_hot=False, window=None, grid_mode="reference"):
+                      one_hot=False, window=None, grid_mode="reference", window_batch=2, cuda_graph=True):
     """input: (X, Y, Z, C_in) float32 numpy.  Returns uint8 labels (X, Y, Z) or, with one_hot=True,
     float32 probabilities (X, Y, Z, num_classes) -- trainer.py:17-98.
 
     window: None = uniform blending (the reference), "gaussian" or a (px,py,pz) float array = weighted.
+    window_batch: windows per forward pass (the reference runs one; InstanceNorm and the blend are per window, so
+    the result does not depend on it -- it only amortises the ~300 kernel launches of a forward pass).
+    cuda_graph: capture the forward pass of one window batch once and replay it for the others (this library's
+    models only; a window forward is ~300 kernel launches and is host-bound when launched eagerly).
     Under an initialised torch.distributed job the windows are dealt round-robin to the ranks and the
     partial sums are all-reduced; every rank returns the full result."""
     import os
@@ -129,15 +133,52 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
     mark("pad + H2D + buffers")
     was_training = model.training
     model.eval()
-    it = mine
+    it = None
     if verbose:
         from tqdm import tqdm
-        it = tqdm(mine)
+        it = tqdm(total=len(mine))
+    wb = max(1, int(window_batch))
+    from . import network as _nw
+    graphable = cuda_graph and isinstance(model, (_nw.Unet, _nw._ResNetBase)) and len(mine) > 2 * wb
+    gkey = (wb, x.shape[1], patch, getattr(model, "precision", "bf16"))
+    static_in = torch.empty((wb, x.shape[1], *patch), dtype=torch.float32, device=device)
+    graph, static_out = None, None
+    first = True
     with torch.no_grad():
-        for (ox, oy, oz) in it:
-            tile = x[:, :, ox:ox + patch[0], oy:oy + patch[1], oz:oz + patch[2]].contiguous()
-            logits = model(tile)
-            ops.sw_accumulate(logits[0].contiguous(), wdev, result, weight, (ox, oy, oz))
+        for b0 in range(0, len(mine), wb):
+            group = mine[b0:b0 + wb]
+            # a short last group is padded with its first window so that only ONE batch shape is ever planned
+            padded = group + [group[0]] * (wb - len(group))
+            for i, (ox, oy, oz) in enumerate(padded):
+                static_in[i].copy_(x[0, :, ox:ox + patch[0], oy:oy + patch[1], oz:oz + patch[2]])
+            if graph is not None:
+                graph.replay()
+                logits = static_out
+            else:
+                logits = model(static_in)                    # eager: builds the plans, (re)packs the weights
+                if graphable and first:
+                    # the captured forward is kept on the engine and reused by later calls (other volumes): capture
+                    # + instantiation of ~200 launches costs more than one volume's worth of host launch overhead
+                    eng = (model.net if hasattr(model, "net") else model)._engine
+                    cached = eng._infer_graphs.get(gkey)
+                    if cached is None:
+                        torch.cuda.synchronize()
+                        ops.check_device_errors()
+                        g_in = torch.empty_like(static_in)
+                        g_in.copy_(static_in)
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            g_out = model(g_in)
+                        cached = eng._infer_graphs[gkey] = (g, g_in, g_out)
+                    graph, static_in_new, static_out = cached
+                    static_in = static_in_new
+            first = False
+            for i, origin in enumerate(group):
+                ops.sw_accumulate(logits[i].contiguous(), wdev, result, weight, origin)
+            if verbose:
+                it.update(len(group))
+    if it is not None:
+        it.close()
     model.train(was_training)
     mark(f"{len(mine)} windows")
     if world > 1:

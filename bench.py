@@ -262,10 +262,9 @@ def main():
         opt.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()
         vol = np.random.RandomState(7).standard_normal((512, 512, 256, 1)).astype(np.float32)
-        # warm-up on EVERY rank (plans for the batch-1 window shape are built on first use, ~seconds of host work):
-        # a slab with at least one window per rank
-        unet3d_b200.predict_per_patch(vol[:128, :128 * min(world, 4), :128 * max(1, world // 4)], model, 3, (128, 128, 128), 1,
-                                      verbose=False)
+        # warm-up on EVERY rank: a sub-volume with >= 5 windows per rank at 8 ranks, so that the window-batch plans are
+        # built (~seconds of host work on first use of a shape) and the window forward is captured before the timed call
+        unet3d_b200.predict_per_patch(vol[:384, :256, :256], model, 3, (128, 128, 128), 2, verbose=False)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -282,7 +281,7 @@ def main():
         n_win = len(unet3d_b200.tile_origins((512, 512, 256), (128, 128, 128), 2))
         infer = {"metric": "infer CT volumes/s", "value": 1.0 / dt, "unit": "volumes/s", "seconds_per_volume": dt,
                  "volume": [512, 512, 256], "window": [128, 128, 128], "windows": n_win, "grid": "reference (trainer.py:29-40)",
-                 "blend": "uniform", "includes": "H2D of the fp32 volume, all window forwards, blend, normalise + argmax, "
+                 "blend": "uniform", "windows_per_forward": 2, "includes": "H2D of the fp32 volume, all window forwards, blend, normalise + argmax, "
                  "D2H of the uint8 label map" + (", all-reduce of the blend buffers" if world > 1 else ""),
                  "label_hist": [int(v) for v in np.bincount(labels.reshape(-1), minlength=3)[:3]]}
 

@@ -1,0 +1,58 @@
+"""2-GPU check of the two data-parallel loss modes, run under torchrun on one box:
+
+  (i)  local Dice (default): every rank's loss on its own shard, gradients averaged == mean of the shard gradients;
+  (ii) global_batch=True   : per-class sums all-reduced inside the loss, gradients SUMMED == the gradient of ONE process
+                             on the concatenated batch (exact large-batch equivalence).
+
+Both references are computed by rank 0 alone on the same weights.  python -m torch.distributed.run --nproc-per-node 2 tools/check_global_dice.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+import unet3d_b200
+from unet3d_b200 import parallel
+
+dist.init_process_group("nccl")
+rank, world = dist.get_rank(), dist.get_world_size()
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
+torch.cuda.set_device(dev)
+torch.manual_seed(0)
+model = unet3d_b200.ResUnet3D(num_pool=2, num_features=8, out_channels=3).to(dev).eval()      # eval: no dropout
+g = torch.Generator().manual_seed(5)
+x_all = torch.randn(2 * world, 1, 16, 16, 16, generator=g).to(dev)
+y_all = torch.randint(0, 3, (2 * world, 16, 16, 16), generator=g).to(dev)
+xs, ys = x_all[2 * rank:2 * rank + 2], y_all[2 * rank:2 * rank + 2]
+
+
+def grads_of(loss_fn, x, y):
+    model.zero_grad(set_to_none=True)
+    loss_fn(model(x), y).backward()
+    return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+ok = True
+for name, glob in (("local-dice / averaged", False), ("global-dice / summed", True)):
+    loss_fn = unet3d_b200.HybirdLoss(weight_v=[1, 148, 191], alpha=0.9, beta=0.1, global_batch=glob)
+    model.zero_grad(set_to_none=True)
+    loss_fn(model(xs), ys).backward()
+    parallel.all_reduce_gradients(model, average=not glob)
+    got = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    ref_fn = unet3d_b200.HybirdLoss(weight_v=[1, 148, 191], alpha=0.9, beta=0.1)
+    if glob:
+        ref = grads_of(ref_fn, x_all, y_all)
+    else:
+        parts = [grads_of(ref_fn, x_all[2 * r:2 * r + 2], y_all[2 * r:2 * r + 2]) for r in range(world)]
+        ref = {n: sum(p[n] for p in parts) / world for n in parts[0]}
+    worst = max(rel(got[n], ref[n]) for n in ref if not (n.endswith("bias") and ("conv1" in n or "conv2" in n)))
+    if rank == 0:
+        print(f"{name}: worst per-tensor rel-L2 vs the single-process reference {worst:.2e}")
+    ok = ok and worst < 2e-2
+dist.barrier()
+if rank == 0:
+    print("OK" if ok else "MISMATCH")
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

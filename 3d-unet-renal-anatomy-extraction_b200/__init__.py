@@ -3,7 +3,7 @@ icrdr/3D-UNet-Renal-Anatomy-Extraction, behind the reference's own Python API (s
 
     from unet3d_b200 import ResUnet3D, DiceLoss, HybirdLoss, Trainer, predict_per_patch
 """
-from .network import (ResUnet3D, ResAttrUnet3D, ResAttrUnet3D2, UNet3D, Unet, ResBlock, ResBlockStack, ConvBlock,
+from .network import (ResUnet3D, ResAttrUnet3D, ResAttrUnet3D2, ResAttrBNUnet3D, UNet3D, Unet, ResBlock, ResBlockStack, ConvBlock,
                       ConvBlockStack, MaxPoolBlock, AttBlock, ConvTrans3D, UpConcat, generate_paired_features,
                       generate_paired_features2)
 from .loss import DiceLoss, FocalLoss, HybirdLoss, Dice, dice
@@ -11,7 +11,7 @@ from .trainer import Trainer, predict_per_patch, tile_centres, tile_origins, gau
 from . import parallel
 from .graph import GraphedTrainStep
 
-__all__ = ["ResUnet3D", "ResAttrUnet3D", "ResAttrUnet3D2", "UNet3D", "Unet", "ResBlock", "ResBlockStack", "ConvBlock",
+__all__ = ["ResUnet3D", "ResAttrUnet3D", "ResAttrUnet3D2", "ResAttrBNUnet3D", "UNet3D", "Unet", "ResBlock", "ResBlockStack", "ConvBlock",
            "ConvBlockStack", "MaxPoolBlock", "AttBlock", "ConvTrans3D", "UpConcat", "generate_paired_features",
            "generate_paired_features2", "DiceLoss", "FocalLoss", "HybirdLoss", "Dice", "dice", "Trainer",
            "predict_per_patch", "tile_centres", "tile_origins", "gaussian_window", "center_pad_crop", "pad_to_patch", "parallel", "GraphedTrainStep"]

@@ -171,20 +171,22 @@ int unet3d_in_finalize(const double* stats, const float* drop_scale, float* tabl
                        void* stream) {
   return check(in_finalize(stats, drop_scale, table, NC, count, eps, (cudaStream_t)stream), "in_finalize");
 }
-int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, int N, long long V, int Cp,
-                    int act_f16, void* stream) {
-  return check(in_apply((const bf16*)y, (const bf16*)skip, (bf16*)out, table, N, V, Cp, act_f16, num_sms(), (cudaStream_t)stream),
+int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, const float* shift, int N,
+                    long long V, int Cp, int act_f16, void* stream) {
+  return check(in_apply((const bf16*)y, (const bf16*)skip, (bf16*)out, table, shift, N, V, Cp, act_f16, num_sms(), (cudaStream_t)stream),
                "in_apply");
 }
 int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, void* g,
-                         const float* table, double* sums, int N, long long V, int Cp, int act_f16, void* stream) {
+                         const float* table, const float* shift, double* sums, int N, long long V, int Cp, int act_f16,
+                         void* stream) {
   return check(in_bwd_reduce((const bf16*)dout, (const bf16*)dout2, (const bf16*)out, (const bf16*)y, (bf16*)g, table,
-                             sums, N, V, Cp, act_f16, num_sms(), (cudaStream_t)stream),
+                             shift, sums, N, V, Cp, act_f16, num_sms(), (cudaStream_t)stream),
                "in_bwd_reduce");
 }
-int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums, double* dsum,
-                        int N, int D, int H, int W, int Cp, int zero_last, int act_f16, void* stream) {
-  return check(in_bwd_apply((const bf16*)g, (const bf16*)y, (bf16*)dy, table, sums, dsum, N, D, H, W, Cp, zero_last,
+int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums,
+                        const float* coef, double* dsum, int N, int D, int H, int W, int Cp, int zero_last, int act_f16,
+                        void* stream) {
+  return check(in_bwd_apply((const bf16*)g, (const bf16*)y, (bf16*)dy, table, sums, coef, dsum, N, D, H, W, Cp, zero_last,
                             act_f16, num_sms(), (cudaStream_t)stream),
                "in_bwd_apply");
 }

@@ -53,19 +53,20 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, const float
   table[i] = make_float2((float)mean, (float)scale);
 }
 
-// out = lrelu((y - mean) * scale [+ skip])
+// out = lrelu((y - mean) * scale [+ shift] [+ skip]);  shift (per (n, c), optional) carries BatchNorm's affine offset
 template <bool HAS_SKIP>
 __global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ skip,
-                                uint4* __restrict__ out, const float2* __restrict__ table, int chunks,
-                                long long V, int Cp, int af) {
+                                uint4* __restrict__ out, const float2* __restrict__ table,
+                                const float* __restrict__ shift, int chunks, long long V, int Cp, int af) {
   const int n = blockIdx.y;
   const int ch = threadIdx.x;                   // 8-channel chunk
-  float mean[8], scale[8];
+  float mean[8], scale[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float2 t = table[(size_t)n * Cp + ch * 8 + j];
     mean[j] = t.x;
     scale[j] = t.y;
+    sh[j] = shift ? shift[(size_t)n * Cp + ch * 8 + j] : 0.f;
   }
   const size_t base = (size_t)n * V * chunks;
   for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
@@ -76,7 +77,7 @@ __global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __rest
     if (HAS_SKIP) unpack8(ld_stream(skip + idx), s, af);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float z = (f[j] - mean[j]) * scale[j];
+      float z = fmaf(f[j] - mean[j], scale[j], sh[j]);
       if (HAS_SKIP) z += s[j];
       f[j] = z > 0.f ? z : LRELU * z;
     }
@@ -90,16 +91,18 @@ template <bool HAS_D2>
 __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2,
                                      const uint4* __restrict__ out, const uint4* __restrict__ y,
                                      uint4* __restrict__ g, const float2* __restrict__ table,
-                                     double* __restrict__ sums, int chunks, long long V, int Cp, int af) {
+                                     const float* __restrict__ shift, double* __restrict__ sums, int chunks,
+                                     long long V, int Cp, int af) {
   extern __shared__ float red[];   // [blockDim.y][chunks*8][2]
   const int n = blockIdx.y;
   const int ch = threadIdx.x;
-  float mean[8], scale[8], s1[8], s2[8];
+  float mean[8], scale[8], sh[8], s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float2 t = table[(size_t)n * Cp + ch * 8 + j];
     mean[j] = t.x;
     scale[j] = t.y;
+    sh[j] = shift ? shift[(size_t)n * Cp + ch * 8 + j] : 0.f;     // yhat = (y - mean) * scale + shift
     s1[j] = 0.f;
     s2[j] = 0.f;
   }
@@ -120,7 +123,7 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
     } else {
       // no residual input: the activation's sign is the sign of the normalised value, `out` need not be read
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (yy[j] - mean[j]) * scale[j];
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(yy[j] - mean[j], scale[j], sh[j]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -132,7 +135,7 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
     unpack8(gp, d, af);      // reduce what pass 2 will read back (the rounded g)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float yh = (yy[j] - mean[j]) * scale[j];
+      const float yh = fmaf(yy[j] - mean[j], scale[j], sh[j]);
       s1[j] += d[j];
       s2[j] += d[j] * yh;
     }
@@ -158,7 +161,8 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
 template <bool ZERO_LAST, bool HAS_DSUM>
 __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
                                     uint4* __restrict__ dy, const float2* __restrict__ table,
-                                    const double* __restrict__ sums, double* __restrict__ dsum, int chunks,
+                                    const double* __restrict__ sums, const float* __restrict__ coef,
+                                    double* __restrict__ dsum, int chunks,
                                     long long V, int Cp, double inv_count, int zero_last, int D, int H, int W, int af) {
   extern __shared__ float red[];
   const int n = blockIdx.y;
@@ -169,10 +173,16 @@ __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
   for (int j = 0; j < 8; ++j) {
     const size_t c = (size_t)n * Cp + ch * 8 + j;
     const float2 t = table[c];
-    const float mg = (float)(sums[2 * c] * inv_count), mgy = (float)(sums[2 * c + 1] * inv_count);
-    ca[j] = t.y;
-    cb[j] = -t.y * t.y * mgy;
-    cc[j] = -t.y * mg + t.y * t.y * mgy * t.x;
+    if (coef != nullptr) {          // BatchNorm: the host supplies dy = g * A + y * B + C per (n, c)
+      ca[j] = coef[3 * c];
+      cb[j] = coef[3 * c + 1];
+      cc[j] = coef[3 * c + 2];
+    } else {
+      const float mg = (float)(sums[2 * c] * inv_count), mgy = (float)(sums[2 * c + 1] * inv_count);
+      ca[j] = t.y;
+      cb[j] = -t.y * t.y * mgy;
+      cc[j] = -t.y * mg + t.y * t.y * mgy * t.x;
+    }
     acc[j] = 0.f;
   }
   const size_t base = (size_t)n * V * chunks;
@@ -981,22 +991,22 @@ int in_finalize(const double* stats, const float* drop, float* table, int NC, do
   return U3D_CHECK_LAUNCH();
 }
 
-int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int N, long long V, int Cp, int af,
-             int num_sms, cudaStream_t s) {
+int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, const float* shift, int N, long long V,
+             int Cp, int af, int num_sms, cudaStream_t s) {
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
   const int gx = grid_rows(V, blk.y, N, num_sms, 16);
   dim3 grd(gx, N);
   if (skip)
-    in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (const float2*)table, chunks, V, Cp, af);
+    in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (const float2*)table, shift, chunks, V, Cp, af);
   else
-    in_apply_kernel<false><<<grd, blk, 0, s>>>((const uint4*)y, nullptr, (uint4*)out, (const float2*)table, chunks, V, Cp, af);
+    in_apply_kernel<false><<<grd, blk, 0, s>>>((const uint4*)y, nullptr, (uint4*)out, (const float2*)table, shift, chunks, V, Cp, af);
   return U3D_CHECK_LAUNCH();
 }
 
 int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf16* y, bf16* g, const float* table,
-                  double* sums, int N, long long V, int Cp, int af, int num_sms, cudaStream_t s) {
+                  const float* shift, double* sums, int N, long long V, int Cp, int af, int num_sms, cudaStream_t s) {
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
@@ -1005,15 +1015,15 @@ int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf
   const size_t sm = (size_t)blk.y * Cp * 2 * sizeof(float);
   if (dout2)
     in_bwd_reduce_kernel<true><<<grd, blk, sm, s>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)out,
-                                                    (const uint4*)y, (uint4*)g, (const float2*)table, sums, chunks, V, Cp, af);
+                                                    (const uint4*)y, (uint4*)g, (const float2*)table, shift, sums, chunks, V, Cp, af);
   else
     in_bwd_reduce_kernel<false><<<grd, blk, sm, s>>>((const uint4*)dout, nullptr, (const uint4*)out, (const uint4*)y,
-                                                     (uint4*)g, (const float2*)table, sums, chunks, V, Cp, af);
+                                                     (uint4*)g, (const float2*)table, shift, sums, chunks, V, Cp, af);
   return U3D_CHECK_LAUNCH();
 }
 
-int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, const double* sums, double* dsum, int N,
-                 int D, int H, int W, int Cp, int zero_last, int af, int num_sms, cudaStream_t s) {
+int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, const double* sums, const float* coef,
+                 double* dsum, int N, int D, int H, int W, int Cp, int zero_last, int af, int num_sms, cudaStream_t s) {
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   const long long V = (long long)D * H * W;
@@ -1023,7 +1033,7 @@ int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, con
   const size_t sm = dsum ? (size_t)blk.y * Cp * sizeof(float) : 0;
 #define U3D_BWD_APPLY(Z, S)                                                                                         \
   in_bwd_apply_kernel<Z, S><<<grd, blk, sm, s>>>((const uint4*)g, (const uint4*)y, (uint4*)dy, (const float2*)table, \
-                                                 sums, dsum, chunks, V, Cp, 1.0 / (double)V, zero_last, D, H, W, af)
+                                                 sums, coef, dsum, chunks, V, Cp, 1.0 / (double)V, zero_last, D, H, W, af)
   if (zero_last && dsum) U3D_BWD_APPLY(true, true);
   else if (zero_last) U3D_BWD_APPLY(true, false);
   else if (dsum) U3D_BWD_APPLY(false, true);

@@ -6,12 +6,12 @@ namespace u3d {
 
 int weight_pack(const float* w, const int* idx, void* out, long long n, int f16, int num_sms, cudaStream_t s);
 int in_finalize(const double* stats, const float* drop, float* table, int NC, double count, float eps, cudaStream_t s);
-int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, int N, long long V, int Cp, int af,
-             int num_sms, cudaStream_t s);
+int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, const float* shift, int N, long long V,
+             int Cp, int af, int num_sms, cudaStream_t s);
 int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf16* y, bf16* g, const float* table,
-                  double* sums, int N, long long V, int Cp, int af, int num_sms, cudaStream_t s);
-int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, const double* sums, double* dsum, int N,
-                 int D, int H, int W, int Cp, int zero_last, int af, int num_sms, cudaStream_t s);
+                  const float* shift, double* sums, int N, long long V, int Cp, int af, int num_sms, cudaStream_t s);
+int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, const double* sums, const float* coef,
+                 double* dsum, int N, int D, int H, int W, int Cp, int zero_last, int af, int num_sms, cudaStream_t s);
 int channel_sum(const bf16* x, double* dsum, long long NV, int Cp, int num_sms, cudaStream_t s);
 int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int D, int H, int W, int Cp, int af,
              int num_sms, cudaStream_t s);

@@ -131,9 +131,9 @@ class UNetEngine:
         operands -- it faults with an illegal instruction -- and the weight gradient multiplies the two)."""
         return torch.empty_like(t)
 
-    def _apply(self, y, skip, table):
+    def _apply(self, y, skip, table, shift=None):
         out = torch.empty_like(y)
-        ops.in_apply(y, skip, out, table)
+        ops.in_apply(y, skip, out, table, shift)
         return out
 
     def _drop_scale(self, n, c, p):
@@ -144,16 +144,97 @@ class UNetEngine:
         out[:, :c] = m.view(n, c)
         return out
 
-    def _conv_in(self, op: _ConvOp, inputs, weight, out_dims, drop=None, bias=None, zero_last=False):
-        """conv (+ statistics) -> finalize: returns (y, table)."""
+    def _conv_in(self, op: _ConvOp, inputs, weight, out_dims, drop=None, bias=None, zero_last=False, norm=None):
+        """conv (+ statistics) -> norm tables: returns (y, table, bn) with bn = None for InstanceNorm or the
+        BatchNorm record (shift table + what the backward pass needs)."""
         n = inputs[0].shape[0]
         y = self._new_act(n, out_dims, op.out_C)
         stats = self._z64(n, y.shape[-1], 2)
         ops.conv_gemm(op.fwd, inputs, self._pw(op.fwd, weight), [y], op.grid,
                       bias=op.fwd.packed_bias(bias), stats=stats, zero_last=zero_last)
+        count = out_dims[0] * out_dims[1] * out_dims[2]
+        if isinstance(norm, torch.nn.BatchNorm3d):
+            table, bn = self._bn_tables(norm, stats, drop, count)
+            return y, table, bn
         table = torch.empty(n, y.shape[-1], 2, dtype=torch.float32, device=self.device)
-        ops.in_finalize(stats, drop, table, out_dims[0] * out_dims[1] * out_dims[2], IN_EPS)
-        return y, table
+        ops.in_finalize(stats, drop, table, count, IN_EPS)
+        return y, table, None
+
+    # ------------------------------------------------------------------ BatchNorm3d (network.py:38-69 variant)
+    def _bn_tables(self, norm, stats, drop, count):
+        """BatchNorm3d(affine, running statistics) on top of the InstanceNorm kernels: the conv epilogue's per-(n, c)
+        sums are combined over the batch with O(C) tensor arithmetic, and the normalisation is handed to in_apply as
+        out = y * scale[n,c] + shift[n,c] (scale carries the Dropout3d mask m, gamma and 1/sigma; shift carries beta and
+        the mean -- a dropped channel becomes the constant beta - mean * gamma / sigma, exactly what BatchNorm makes
+        of an all-zero channel)."""
+        n, cp = stats.shape[0], stats.shape[1]
+        c = norm.num_features
+        dev = self.device
+        m = drop.double() if drop is not None else torch.ones(n, cp, dtype=torch.float64, device=dev)
+        gamma = torch.zeros(cp, dtype=torch.float64, device=dev)
+        beta = torch.zeros(cp, dtype=torch.float64, device=dev)
+        gamma[:c] = norm.weight.detach().double()
+        beta[:c] = norm.bias.detach().double()
+        train = self.owner.training or not norm.track_running_stats
+        cnt = float(n * count)
+        if train:
+            mean = (m * stats[..., 0]).sum(0) / cnt
+            var = ((m * m * stats[..., 1]).sum(0) / cnt - mean * mean).clamp_min(0.0)
+            if norm.track_running_stats and self.owner.training:
+                with torch.no_grad():
+                    norm.num_batches_tracked += 1
+                    mom = norm.momentum if norm.momentum is not None else 1.0 / float(norm.num_batches_tracked)
+                    norm.running_mean.mul_(1 - mom).add_(mean[:c].to(norm.running_mean.dtype), alpha=mom)
+                    norm.running_var.mul_(1 - mom).add_((var[:c] * (cnt / max(cnt - 1.0, 1.0))).to(norm.running_var.dtype),
+                                                        alpha=mom)
+        else:
+            mean = torch.zeros(cp, dtype=torch.float64, device=dev)
+            var = torch.ones(cp, dtype=torch.float64, device=dev)
+            mean[:c] = norm.running_mean.double()
+            var[:c] = norm.running_var.double()
+        r = torch.rsqrt(var + norm.eps)
+        table = torch.zeros(n, cp, 2, dtype=torch.float32, device=dev)
+        table[..., 1] = (m * (r * gamma)).float()
+        shift = (beta - mean * r * gamma).float().expand(n, cp).contiguous()
+        return table, dict(norm=norm, shift=shift, m=m, r=r, mean=mean, gamma=gamma, train=train, cnt=cnt, c=c)
+
+    def _bn_bwd(self, bn, dout, dout2, out, y, grads, zero_last=False):
+        """Backward of the above: x_hat = y * (m r) - mean r;  d gamma = sum g x_hat, d beta = sum g;
+        dz = gamma r (g - mean(g) - x_hat mean(g x_hat)) (training) or gamma r g (running statistics); dy = m dz is
+        given to in_bwd_apply as per-(n, c) coefficients dy = g A + y B + C."""
+        n, cp = y.shape[0], y.shape[-1]
+        m, r, mean, gamma, c = bn["m"], bn["r"], bn["mean"], bn["gamma"], bn["c"]
+        hat = torch.zeros(n, cp, 2, dtype=torch.float32, device=self.device)
+        hat[..., 1] = (m * r).float()
+        hat_shift = (-mean * r).float().expand(n, cp).contiguous()
+        g = self._grad_like(y)
+        sums = self._z64(n, cp, 2)
+        ops.in_bwd_reduce(dout, dout2, out, y, g, hat, sums, shift=hat_shift)
+        s1, s2 = sums[..., 0].sum(0), sums[..., 1].sum(0)
+        a = m * (gamma * r)
+        if bn["train"]:
+            g1, g2 = s1 / bn["cnt"], s2 / bn["cnt"]
+            b = -a * g2 * (m * r)
+            cc = a * (-g1 + mean * r * g2)
+        else:
+            b = torch.zeros_like(a)
+            cc = torch.zeros_like(a)
+        coef = torch.stack([a, b, cc], dim=-1).float().contiguous()
+        dy = self._grad_like(y)
+        dsum = self._z64(cp)
+        ops.in_bwd_apply(g, y, dy, hat, sums, dsum, zero_last, coef=coef)
+        norm = bn["norm"]
+        dg, db = self._unscale(s2[:c].float()), self._unscale(s1[:c].float())
+        grads[norm.weight] = dg if norm.weight not in grads else grads[norm.weight] + dg
+        grads[norm.bias] = db if norm.bias not in grads else grads[norm.bias] + db
+        return g, dy, sums, dsum
+
+    def _norm_bwd(self, bn, dout, dout2, act, residual, y, table, grads, zero_last=False, want_dsum=False):
+        """(g, dy, sums, dsum) of one norm + LeakyReLU application; `act` is its output, `residual` says whether a skip
+        tensor was added before the activation (only then InstanceNorm has to read `act` for the sign)."""
+        if bn is None:
+            return self._in_bwd(dout, dout2, act if residual else None, y, table, zero_last, want_dsum)
+        return self._bn_bwd(bn, dout, dout2, act, y, grads, zero_last)
 
     def _in_bwd(self, dout, dout2, out, y, table, zero_last=False, want_dsum=False):
         n, cp = y.shape[0], y.shape[-1]
@@ -324,10 +405,14 @@ class UNetEngine:
         c1 = self._op(key + ("conv1",), "conv", 3, blk.stride, in_C, blk.out_channels, grid, skip_k1=blk.uses_skip_conv)
         c2 = self._op(key + ("conv2",), "conv", 3, 1, [blk.out_channels], blk.out_channels, grid)
         drop = self._drop_scale(n, blk.out_channels, blk.dropout_p) if (train and blk.dropout_p > 0) else None
-        # conv biases directly followed by InstanceNorm(affine=False) cancel exactly: not applied
-        y1, t1 = self._conv_in(c1, inputs, blk.conv1.weight, out_dims, drop=drop)
-        a1 = self._apply(y1, None, t1)
-        y2, t2 = self._conv_in(c2, [a1], blk.conv2.weight, out_dims)
+        # conv biases directly followed by InstanceNorm(affine=False) cancel exactly: not applied.
+        # In front of BatchNorm they shift the running mean (and count in eval mode): applied.
+        bn = isinstance(blk.norm, torch.nn.BatchNorm3d)
+        y1, t1, b1 = self._conv_in(c1, inputs, blk.conv1.weight, out_dims, drop=drop,
+                                   bias=blk.conv1.bias if bn else None, norm=blk.norm)
+        a1 = self._apply(y1, None, t1, None if b1 is None else b1["shift"])
+        y2, t2, b2 = self._conv_in(c2, [a1], blk.conv2.weight, out_dims, bias=blk.conv2.bias if bn else None,
+                                   norm=blk.norm)      # the block's ONE norm module is applied twice (network.py:401-416)
         if blk.uses_skip_conv:
             sk = self._op(key + ("skip",), "conv", 1, blk.stride, in_C, blk.out_channels, grid)
             s = self._new_act(n, out_dims, blk.out_channels)
@@ -335,17 +420,19 @@ class UNetEngine:
                           bias=sk.fwd.packed_bias(blk.skip_conv.bias))
         else:
             s = inputs[0]
-        out = self._apply(y2, s, t2)
-        return out, ((inputs, y1, t1, a1, y2, t2, out) if save else None)
+        out = self._apply(y2, s, t2, None if b2 is None else b2["shift"])
+        return out, ((inputs, y1, t1, a1, y2, t2, out, b1, b2) if save else None)
 
     def _conv_block_fwd(self, blk, key, inputs, out_dims, train, save):
         n = inputs[0].shape[0]
         in_C = self._split_channels(blk.in_channels, inputs)
         op = self._op(key + ("conv",), "conv", 3, 1, in_C, blk.out_channels, (n, *out_dims))
         drop = self._drop_scale(n, blk.out_channels, blk.dropout_p) if (train and blk.dropout_p > 0) else None
-        y, t = self._conv_in(op, inputs, blk.conv.weight, out_dims, drop=drop)
-        a = self._apply(y, None, t)
-        return a, ((inputs, y, t, a) if save else None)
+        bn = isinstance(blk.norm, torch.nn.BatchNorm3d)
+        y, t, b = self._conv_in(op, inputs, blk.conv.weight, out_dims, drop=drop, bias=blk.conv.bias if bn else None,
+                                norm=blk.norm)
+        a = self._apply(y, None, t, None if b is None else b["shift"])
+        return a, ((inputs, y, t, a, b) if save else None)
 
     # ------------------------------------------------------------------ attention gate (network.py:353-371)
     def _att_ops(self, gate, level, grid):
@@ -433,11 +520,12 @@ class UNetEngine:
             up = net.up_blocks[i]
             ct = up.conv_trans.up[0]
             uop = self._op(("up", i), "convT", 3, 2, [ct.in_channels], ct.out_channels, (N, *dims[i + 1]))
-            yu, tu = self._conv_in(uop, [cur], ct.weight, dims[i], bias=ct.bias, zero_last=True)
-            au = self._apply(yu, None, tu)
+            yu, tu, bu = self._conv_in(uop, [cur], ct.weight, dims[i], bias=ct.bias, zero_last=True,
+                                       norm=up.conv_trans.up[2])
+            au = self._apply(yu, None, tu, None if bu is None else bu["shift"])
             au._c = ct.out_channels
             if save:
-                tape[("up", i)] = (cur, yu, tu, au)
+                tape[("up", i)] = (cur, yu, tu, au, bu)
             skip = skips[i]
             if getattr(up, "attention", False):
                 skip, rec = self._att_fwd(up.att_gate, i, skip, au, dims[i])
@@ -480,19 +568,22 @@ class UNetEngine:
         raise RuntimeError(f"unsupported block type {type(blk).__name__}")
 
     def _res_block_bwd(self, blk, key, rec, dout, dout2, grads):
-        inputs, y1, t1, a1, y2, t2, out = rec
+        inputs, y1, t1, a1, y2, t2, out, b1, b2 = rec
         grid = (inputs[0].shape[0], *y1.shape[1:4])
         in_C = self._split_channels(blk.in_channels, inputs)
         c1 = self._op(key + ("conv1",), "conv", 3, blk.stride, in_C, blk.out_channels, grid, skip_k1=blk.uses_skip_conv)
         c2 = self._op(key + ("conv2",), "conv", 3, 1, [blk.out_channels], blk.out_channels, grid)
-        g2, dy2, sums2, _ = self._in_bwd(dout, dout2, out, y2, t2)
+        co = blk.out_channels
+        g2, dy2, sums2, ds2 = self._norm_bwd(b2, dout, dout2, out, True, y2, t2, grads)
         grads[blk.conv2.weight] = self._wgrad(c2, [a1], dy2, blk.conv2.weight)
-        grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias)       # cancelled by the norm (S1)
+        # InstanceNorm cancels the bias exactly (S1); under BatchNorm its gradient is sum(dy) (zero up to rounding in
+        # training mode, real in eval mode)
+        grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias) if b2 is None else self._unscale(ds2[:co].float())
         da1 = self._grad_like(a1)
         ops.conv_gemm(c2.dgrad, [dy2], self._pw(c2.dgrad, blk.conv2.weight), [da1], c2.grid)
-        _, dy1, _, _ = self._in_bwd(da1, None, None, y1, t1)          # no residual: sign from the normalised value
+        _, dy1, _, ds1 = self._norm_bwd(b1, da1, None, a1, False, y1, t1, grads)
         grads[blk.conv1.weight] = self._wgrad(c1, inputs, dy1, blk.conv1.weight)
-        grads[blk.conv1.bias] = torch.zeros_like(blk.conv1.bias)
+        grads[blk.conv1.bias] = torch.zeros_like(blk.conv1.bias) if b1 is None else self._unscale(ds1[:co].float())
         dins = [self._grad_like(t) for t in inputs]
         if blk.uses_skip_conv:
             sk = self._op(key + ("skip",), "conv", 1, blk.stride, in_C, blk.out_channels, grid)
@@ -507,12 +598,13 @@ class UNetEngine:
         return dins
 
     def _conv_block_bwd(self, blk, key, rec, dout, dout2, grads):
-        inputs, y, t, a = rec
+        inputs, y, t, a, b = rec
         in_C = self._split_channels(blk.in_channels, inputs)
         op = self._op(key + ("conv",), "conv", 3, 1, in_C, blk.out_channels, (inputs[0].shape[0], *y.shape[1:4]))
-        _, dy, _, _ = self._in_bwd(dout, dout2, None, y, t)
+        _, dy, _, ds = self._norm_bwd(b, dout, dout2, a, False, y, t, grads)
         grads[blk.conv.weight] = self._wgrad(op, inputs, dy, blk.conv.weight)
-        grads[blk.conv.bias] = torch.zeros_like(blk.conv.bias)          # cancelled by the norm (S1)
+        grads[blk.conv.bias] = (torch.zeros_like(blk.conv.bias) if b is None          # cancelled by InstanceNorm (S1)
+                                else self._unscale(ds[:blk.out_channels].float()))
         dins = [self._grad_like(x) for x in inputs]
         ops.conv_gemm(op.dgrad, [dy], self._pw(op.dgrad, blk.conv.weight), dins, op.grid)
         return dins
@@ -548,10 +640,10 @@ class UNetEngine:
             if ("att", i) in tape:
                 d_up, d_skip = self._att_bwd(net.up_blocks[i].att_gate, i, tape[("att", i)], d_up, d_skip, grads)
             pending[i] = d_skip
-            xin, yu, tu, au = tape[("up", i)]
+            xin, yu, tu, au, bu = tape[("up", i)]
             ct = net.up_blocks[i].conv_trans.up[0]
             uop = self._op(("up", i), "convT", 3, 2, [ct.in_channels], ct.out_channels, (N, *dims[i + 1]))
-            _, dyu, _, dsum = self._in_bwd(d_up, None, None, yu, tu, zero_last=True, want_dsum=True)
+            _, dyu, _, dsum = self._norm_bwd(bu, d_up, None, au, False, yu, tu, grads, zero_last=True, want_dsum=True)
             grads[ct.weight] = self._wgrad(uop, [xin], dyu, ct.weight)
             grads[ct.bias] = self._unscale(dsum[:ct.out_channels].float())
             d_cur = self._grad_like(xin)

@@ -56,9 +56,8 @@ def _check_ops(conv_op, conv_kwargs, dropout_op, dropout_kwargs, norm_op, norm_k
         raise NotImplementedError(f"conv_kwargs {conv_kwargs}: only kernel_size=3, padding=1 is built")
     if dropout_op not in (nn.Dropout3d, None):
         raise NotImplementedError("dropout_op must be nn.Dropout3d or None")
-    if norm_op is not nn.InstanceNorm3d or norm_kwargs:
-        raise NotImplementedError("norm_op must be nn.InstanceNorm3d with default arguments "
-                                  "(BatchNorm3d variant: SURVEY.md 8f rank 4)")
+    if norm_op not in (nn.InstanceNorm3d, nn.BatchNorm3d) or norm_kwargs:
+        raise NotImplementedError("norm_op must be nn.InstanceNorm3d or nn.BatchNorm3d with default arguments")
     if nonlin_op is not nn.LeakyReLU or nonlin_kwargs.get('negative_slope', 0.01) != 0.01:
         raise NotImplementedError("nonlin_op must be nn.LeakyReLU(negative_slope=0.01)")
 
@@ -246,13 +245,15 @@ def _encode_kwargs_fn(level):           # network.py:116-118
 class _ResNetBase(nn.Module):
     """Shared shape of the concrete residual nets: attributes, ``.net``, forward."""
 
-    def _build(self, in_channels, out_channels, paired_features, attention):
+    def _build(self, in_channels, out_channels, paired_features, attention, norm_op=None):
         self.in_channels = in_channels
         self.out_channels = out_channels
+        nk = {} if norm_op is None else {'norm_op': norm_op}
         self.net = Unet(in_channels=in_channels, out_channels=out_channels, paired_features=paired_features,
-                        pool_block=ResBlock, pool_kwargs={'stride': 2},
-                        up_kwargs={'attention': True} if attention else {},
-                        encode_block=ResBlockStack, encode_kwargs_fn=_encode_kwargs_fn, decode_block=ResBlock)
+                        pool_block=ResBlock, pool_kwargs={'stride': 2, **nk},
+                        up_kwargs={**({'attention': True} if attention else {}), **nk},
+                        encode_block=ResBlockStack, encode_kwargs=dict(nk), encode_kwargs_fn=_encode_kwargs_fn,
+                        decode_block=ResBlock, decode_kwargs=dict(nk))
         self.precision = "bf16"           # "bf16" | "fp16": 16-bit storage of activations / packed weights / gradients
         self.last_dropout_masks = None
 
@@ -278,6 +279,18 @@ class ResAttrUnet3D(_ResNetBase):
         self.num_pool = num_pool
         self.num_features = num_features
         self._build(in_channels, out_channels, generate_paired_features(num_pool, num_features), attention=True)
+
+
+class ResAttrBNUnet3D(_ResNetBase):
+    """``ResAttrUnet3D`` with BatchNorm3d (affine, running statistics) in place of InstanceNorm3d -- network.py:38-69.
+    As in the reference, each ResBlock owns ONE BatchNorm3d module that normalises both of its convolutions."""
+
+    def __init__(self, num_pool: int = 4, num_features: int = 30, in_channels: int = 1, out_channels: int = 1):
+        super().__init__()
+        self.num_pool = num_pool
+        self.num_features = num_features
+        self._build(in_channels, out_channels, generate_paired_features(num_pool, num_features), attention=True,
+                    norm_op=nn.BatchNorm3d)
 
 
 class ResAttrUnet3D2(_ResNetBase):

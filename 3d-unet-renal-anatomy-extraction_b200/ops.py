@@ -278,32 +278,33 @@ def in_finalize(stats: torch.Tensor, drop: Optional[torch.Tensor], table: torch.
                                              _stream()), "unet3d_in_finalize")
 
 
-def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, table: torch.Tensor):
+def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, table: torch.Tensor,
+             shift: Optional[torch.Tensor] = None):
     n, d, h, w, cp = y.shape
     _count()
     assert out.dtype == y.dtype and (skip is None or skip.dtype == y.dtype)
     with _Timed("in_apply", 0.0, y.numel() * 2.0 * (3 if skip is not None else 2)):
-        _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), n, d * h * w, cp,
+        _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), _ptr(shift), n, d * h * w, cp,
                                               _f16(y), _stream()), "unet3d_in_apply")
 
 
-def in_bwd_reduce(dout, dout2, out, y, g, table, sums):
+def in_bwd_reduce(dout, dout2, out, y, g, table, sums, shift=None):
     n, d, h, w, cp = y.shape
     _count()
     assert dout.dtype == y.dtype and g.dtype == y.dtype and (out is None or out.dtype == y.dtype)
     with _Timed("in_bwd_reduce", 0.0, y.numel() * 2.0 * (3 + (dout2 is not None) + (out is not None))):
         _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), _ptr(out), y.data_ptr(), g.data_ptr(),
-                                                   table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
+                                                   table.data_ptr(), _ptr(shift), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
                    "unet3d_in_bwd_reduce")
 
 
-def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False):
+def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False, coef=None):
     n, d, h, w, cp = y.shape
     _count()
     assert g.dtype == y.dtype and dy.dtype == y.dtype
     with _Timed("in_bwd_apply", 0.0, y.numel() * 2.0 * 3):
         _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
-                                                  _ptr(dsum), n, d, h, w, cp, int(zero_last), _f16(y), _stream()),
+                                                  _ptr(coef), _ptr(dsum), n, d, h, w, cp, int(zero_last), _f16(y), _stream()),
                    "unet3d_in_bwd_apply")
 
 

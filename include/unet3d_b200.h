@@ -120,14 +120,19 @@ int unet3d_wgrad_gemm(const unet3d_wgrad_args* a, void* stream);
  * network.py:159-160,175-176,401-402,412-416,315-316.  stats come from the conv epilogue. */
 int unet3d_in_finalize(const double* stats, const float* drop_scale, float* table, int NC, double count, float eps,
                        void* stream);
-int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, int N, long long V, int Cp,
-                    int act_f16, void* stream);
+/* out = lrelu((y - mean) * scale [+ shift] [+ skip]); table = (mean, scale) per (n, c); shift: NULL, or fp32 per (n, c)
+ * (BatchNorm3d's affine offset / dropped-channel constant, network.py:38-69). */
+int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, const float* shift, int N,
+                    long long V, int Cp, int act_f16, void* stream);
 /* in_bwd_reduce: `out` may be NULL when the norm had no residual input (the activation's sign is then taken from the
  * normalised value and the activation output is not read); dout2 may be NULL. */
 int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, void* g,
-                         const float* table, double* sums, int N, long long V, int Cp, int act_f16, void* stream);
-int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums, double* dsum,
-                        int N, int D, int H, int W, int Cp, int zero_last, int act_f16, void* stream);
+                         const float* table, const float* shift, double* sums, int N, long long V, int Cp, int act_f16,
+                         void* stream);
+/* dy = g * A + y * B + C per (n, c): from (table, sums) for InstanceNorm, or from coef (fp32 [N][Cp][3], BatchNorm). */
+int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums,
+                        const float* coef, double* dsum, int N, int D, int H, int W, int Cp, int zero_last, int act_f16,
+                        void* stream);
 int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* stream);
 
 /* Stem Conv3d(1->C,k3,p1)+bias, fp32 NCDHW in -> bf16 NDHWC out (network.py:541,550) and its

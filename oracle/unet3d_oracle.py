@@ -83,6 +83,21 @@ def _inorm(x: Tensor) -> Tensor:
     return F.instance_norm(x, eps=IN_EPS)
 
 
+BN_TRAIN = False        # set by resunet3d_forward(bn_train=...) for the duration of one forward
+
+
+def _norm(sd: Dict[str, Tensor], pre: str, x: Tensor) -> Tensor:
+    """The block's norm module: InstanceNorm3d (no state) unless the state dict holds BatchNorm3d tensors under
+    `pre` (network.py:38-69 variant: affine, running statistics, momentum 0.1, eps 1e-5).  In training mode the
+    running buffers IN `sd` are updated in place, once per application, exactly like nn.BatchNorm3d."""
+    if pre + "weight" not in sd:
+        return _inorm(x)
+    if BN_TRAIN:
+        sd[pre + "num_batches_tracked"] += 1
+    return F.batch_norm(x, sd[pre + "running_mean"], sd[pre + "running_var"], sd[pre + "weight"], sd[pre + "bias"],
+                        training=BN_TRAIN, momentum=0.1, eps=1e-5)
+
+
 def _lrelu(x: Tensor) -> Tensor:
     return F.leaky_relu(x, LRELU_SLOPE)
 
@@ -98,9 +113,9 @@ def res_block(sd: Dict[str, Tensor], pre: str, x: Tensor, cin: int, cout: int, s
     m = masks.next(y.shape[0], y.shape[1])
     if m is not None:
         y = y * m
-    y = _lrelu(_inorm(y))
+    y = _lrelu(_norm(sd, pre + "norm.", y))
     y = F.conv3d(y, sd[pre + "conv2.weight"], sd[pre + "conv2.bias"], padding=1)
-    return _lrelu(_inorm(y) + skip)
+    return _lrelu(_norm(sd, pre + "norm.", y) + skip)        # the SAME norm module twice (network.py:401-416)
 
 
 def res_block_stack(sd, pre, x, cin, cout, num_stacks, masks) -> Tensor:
@@ -116,7 +131,7 @@ def conv_block(sd, pre, x, masks) -> Tensor:
     m = masks.next(y.shape[0], y.shape[1])
     if m is not None:
         y = y * m
-    return _lrelu(_inorm(y))
+    return _lrelu(_norm(sd, pre + "norm.", y))
 
 
 def conv_block_stack(sd, pre, x, num_stacks, masks) -> Tensor:
@@ -131,7 +146,7 @@ def conv_trans3d(sd, pre, x) -> Tensor:
     The pad plane is zero *before* the norm."""
     y = F.conv_transpose3d(x, sd[pre + "up.0.weight"], sd[pre + "up.0.bias"], stride=2, padding=1)
     y = F.pad(y, (0, 1, 0, 1, 0, 1), value=0.0)
-    return _lrelu(_inorm(y))
+    return _lrelu(_norm(sd, pre + "up.2.", y))
 
 
 def att_block(sd, pre, x, gate) -> Tensor:
@@ -153,13 +168,19 @@ def up_concat(sd, pre, x, skip, attention: bool = False) -> Tensor:
 
 
 def resunet3d_forward(sd: Dict[str, Tensor], x: Tensor, num_pool: int = 4, num_features: int = 30,
-                      masks: Optional[DropoutMasks] = None, attention: bool = False) -> Tensor:
+                      masks: Optional[DropoutMasks] = None, attention: bool = False, bn_train: bool = False) -> Tensor:
     """network.py:104-132 (ResUnet3D) over network.py:549-565 (Unet.forward).
+
+    A state dict with ``...norm.weight`` / ``...up.2.weight`` tensors selects the BatchNorm3d variant
+    (ResAttrBNUnet3D, network.py:38-69); ``bn_train`` = the module's training flag for those norms (batch statistics,
+    running buffers in ``sd`` updated in place).
 
     encode level L = ResBlockStack with max(L,1) blocks (network.py:116-118); pooling is a
     stride-2 ResBlock (network.py:125-126); decode = ResBlock(2f -> f) (network.py:523-527).
     ``attention=True`` gives ResAttrUnet3D (network.py:72-101).
     """
+    global BN_TRAIN
+    BN_TRAIN = bool(bn_train)
     masks = masks or DropoutMasks(train=False)
     pf = paired_features(num_pool, num_features)
     npairs = len(pf)

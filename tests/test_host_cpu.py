@@ -78,7 +78,7 @@ def test_state_dict_layout_and_unused_params():
     with pytest.raises(AssertionError):
         unet3d_b200.Unet(1, 1, [[8, 8]])                    # no pooling level (network.py:493)
     with pytest.raises(NotImplementedError):
-        unet3d_b200.ResBlock(8, 8, norm_op=torch.nn.BatchNorm3d)
+        unet3d_b200.ResBlock(8, 8, norm_op=torch.nn.GroupNorm)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 16, 16, 16))         # CPU tensors are refused: no fallback path
 
@@ -100,6 +100,30 @@ def test_variants_load_reference_state_dicts(golden_dir, fixture, build):
     m.load_state_dict(ref, strict=True)
     if "param_order" in z.files:
         assert [k for k, _ in m.named_parameters()] == z["param_order"].tolist()
+
+
+def _bn_net():
+    bn = {'norm_op': torch.nn.BatchNorm3d}
+    nd = {'norm_op': torch.nn.BatchNorm3d, 'dropout_op': None}
+    return unet3d_b200.Unet(1, 3, unet3d_b200.generate_paired_features(2, 4), pool_block=unet3d_b200.ResBlock,
+                            pool_kwargs={'stride': 2, **nd}, up_kwargs={'attention': True, **bn},
+                            encode_block=unet3d_b200.ResBlockStack, encode_kwargs=nd,
+                            encode_kwargs_fn=lambda level: {'num_stacks': max(level, 1)},
+                            decode_block=unet3d_b200.ResBlock, decode_kwargs=nd)
+
+
+def test_batchnorm_variant_state_dict(golden_dir):
+    """BatchNorm3d variant: the reference's kwargs hooks build the same module tree (keys incl. running buffers, shapes,
+    parameter order); ResAttrBNUnet3D is that wiring with the default dropout (network.py:38-69)."""
+    z = np.load(os.path.join(golden_dir, "bn_attr_resunet.npz"))
+    ref = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    m = _bn_net()
+    assert list(m.state_dict().keys()) == list(ref.keys())
+    m.load_state_dict(ref, strict=True)
+    assert [k for k, _ in m.named_parameters()] == z["param_order"].tolist()
+    full = unet3d_b200.ResAttrBNUnet3D(num_pool=2, num_features=4, out_channels=3)
+    assert ["net." + k for k in ref] == list(full.state_dict().keys())
+    assert full.net.pool_blocks[0].dropout_p == 0.5 and isinstance(full.net.pool_blocks[0].norm, torch.nn.BatchNorm3d)
 
 
 def test_default_net_parameter_order_matches_reference(golden_dir):

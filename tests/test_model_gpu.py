@@ -107,7 +107,7 @@ def _check(model, logits, loss, sdr, ref_logits, ref_loss, y, q_logits, precisio
     elif n_layers <= 8:
         grad_tol = 0.15 if precision == "fp16" else 0.5
     else:
-        grad_tol = 0.3 if precision == "fp16" else 0.9
+        grad_tol = 0.4 if precision == "fp16" else 0.9        # run-to-run spread (atomic order) seen: 0.27-0.30 fp16
     bad = [(n, r) for r, n in worst if not r < grad_tol]
     assert not bad, bad
     return sorted(worst)[-3:]

@@ -130,6 +130,38 @@ def test_plain_unet_maxpool_grads(golden_dir):
     _check_grads(sd, z)
 
 
+def test_batchnorm_attention_net_train_and_eval(golden_dir):
+    """BatchNorm3d variant (network.py:38-69 wiring, dropout hooks off) from the live reference: training mode (batch
+    statistics, running-buffer updates, gamma / beta / conv-bias gradients) and, with the updated buffers, eval mode."""
+    z = _load(golden_dir, "bn_attr_resunet.npz")
+    sd = {"net." + k: v.clone() for k, v in _sd(z).items()}
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    loss_fn = lambda lg: O.hybrid_loss(lg, y, weight_v=[1, 148, 191], alpha=0.9, beta=0.1)
+    logits = O.resunet3d_forward(sd, x, 2, 4, attention=True, bn_train=True)
+    assert torch.allclose(logits, torch.from_numpy(z["train_logits"]), rtol=1e-4, atol=1e-5)
+    loss = loss_fn(logits)
+    assert abs(loss.item() - float(z["train_loss"])) < 1e-5
+    loss.backward()
+    for k in z.files:
+        if k.startswith("train_grad/"):
+            assert torch.allclose(sd["net." + k[11:]].grad, torch.from_numpy(z[k]), rtol=2e-3, atol=2e-6), k
+        if k.startswith("after/"):
+            assert torch.allclose(sd["net." + k[6:]].detach().float(), torch.from_numpy(z[k]).float(), rtol=1e-4, atol=1e-6), k
+    for v in sd.values():
+        v.grad = None
+    logits = O.resunet3d_forward(sd, x, 2, 4, attention=True, bn_train=False)
+    assert torch.allclose(logits, torch.from_numpy(z["eval_logits"]), rtol=1e-4, atol=1e-5)
+    loss = loss_fn(logits)
+    assert abs(loss.item() - float(z["eval_loss"])) < 1e-5
+    loss.backward()
+    for k in z.files:
+        if k.startswith("eval_grad/"):
+            assert torch.allclose(sd["net." + k[10:]].grad, torch.from_numpy(z[k]), rtol=2e-3, atol=2e-6), k
+
+
 def test_pad_crop_roundtrip():
     """Even size differences round-trip; odd ones come back shifted by one voxel because the pad
     puts ceil(diff/2) in front (floor division of a negative lower bound, transform.py:414) while

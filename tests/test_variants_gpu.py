@@ -128,3 +128,56 @@ def test_attention_default_net_runs_train_mode():
         if p.grad is not None:
             assert torch.isfinite(p.grad).all(), name
     assert m.net.up_blocks[0].att_gate.conv.weight.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_batchnorm_variant_vs_reference(golden_dir, precision):
+    """BatchNorm3d + attention net (network.py:38-69 wiring, dropout hooks off) against the live reference's vectors:
+    training mode -- logits, loss, gradients (incl. gamma, beta and the conv biases BatchNorm does not cancel in eval
+    mode), running-buffer updates -- then eval mode on the updated buffers."""
+    from tests.test_host_cpu import _bn_net
+    z = np.load(os.path.join(golden_dir, "bn_attr_resunet.npz"))
+    model = _bn_net()
+    model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")})
+    model = model.to(DEV)
+    model.precision = precision
+    x, y = torch.from_numpy(z["x"]).to(DEV), torch.from_numpy(z["y"]).to(DEV)
+    loss_mod = unet3d_b200.HybirdLoss(weight_v=[1, 148, 191], alpha=0.9, beta=0.1)
+    # gradient buckets: this 4-channel fixture is noisier than the 8-channel ones -- the InstanceNorm version of the
+    # very same net shows the same errors (tools/bn_vs_in_check.py on a B200: median / max per-tensor rel-L2
+    # 0.093 / 0.147 fp16 and 0.30 / 0.49 bf16 with InstanceNorm, 0.101 / 0.223 and 0.28 / 0.53 with BatchNorm)
+    tol, gtol = (1e-2, 0.3) if precision == "fp16" else (3e-2, 0.7)
+    for mode in ("train", "eval"):
+        model.train(mode == "train")
+        model.zero_grad(set_to_none=True)
+        logits = model(x)
+        loss = loss_mod(logits, y)
+        loss.backward()
+        torch.cuda.synchronize()
+        ops.check_device_errors()
+        r = rel(logits.detach().cpu(), torch.from_numpy(z[mode + "_logits"]))
+        print(f"[BN {precision} {mode}] logits rel-L2 {r:.3e} loss {loss.item():.6f} vs {float(z[mode + '_loss']):.6f}")
+        assert r < tol
+        assert abs(loss.item() - float(z[mode + "_loss"])) < 5e-3
+        for name, p in model.named_parameters():
+            key = f"{mode}_grad/{name}"
+            if key not in z.files:
+                assert p.grad is None, name
+                continue
+            ref = torch.from_numpy(z[key])
+            got = p.grad.detach().cpu()
+            if mode == "train" and name.endswith("bias") and ("conv1." in name or "conv2." in name or "up.0." in name):
+                # cancelled by the batch statistics: sum(dy) = 0 up to the 16-bit rounding of dy (8k-64k summands)
+                wname = name[:-4] + "weight"
+                wmax = dict(model.named_parameters())[wname].grad.abs().max().item()
+                assert got.abs().max().item() < 1e-4 + 10 * ref.abs().max().item() + 0.05 * wmax, name
+                continue
+            rr = rel(got, ref)
+            print(f"   {mode} grad rel-L2 {rr:.3e}  {name}")
+            assert rr < gtol, (mode, name, rr)
+        if mode == "train":
+            for k in z.files:
+                if k.startswith("after/"):
+                    got = model.state_dict()[k[6:]].float().cpu()
+                    ref = torch.from_numpy(z[k]).float()
+                    assert torch.allclose(got, ref, rtol=2e-2, atol=2e-3), k

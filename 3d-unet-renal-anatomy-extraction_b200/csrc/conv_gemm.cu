@@ -386,7 +386,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
         ctl->abort_flag = 1;
         atomicCAS(p.err, 0, 107);
       }
-    } else {
+    } else if (elect_one()) {
+    // generic path (strided / transposed / 1x1x1 / wide-N layers, partial tap masks): like the dense path the WHOLE
+    // role runs in one elected thread, barrier waits included
     const uint32_t idesc = umma_idesc_bf16(128, nblk, 0, 0, p.in_f16, p.in_f16);
     const uint32_t idesc2 = umma_idesc_bf16(128, 2 * nblk, 0, 0, p.in_f16, p.in_f16),
                    idesc3 = umma_idesc_bf16(128, 3 * nblk, 0, 0, p.in_f16, p.in_f16);
@@ -419,27 +421,22 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
           const uint32_t wst = w_it % w_stages, wph = (w_it / w_stages) & 1;
           if (!mbar_wait(smem_u32(&ctl->w_full[wst]), wph, abort_flag, p.err, 105)) { ok = false; break; }
           tc_fence_after();
-          if (elect_one()) {
-            if (fuse == 1)
-              issue_batch_dispatch<1>(Dt, G2, batch, cnt, tap_off, slab, wring0 + wst * wstage_bytes, wtile_bytes, b_lbo, acc0,
-                                      idesc, idesc2, idesc3, (uint32_t)nblk, accum);
-            else
-              issue_batch_dispatch<3>(Dt, G2, batch, cnt, tap_off, slab, wring0 + wst * wstage_bytes, wtile_bytes, b_lbo, acc0,
-                                      idesc, idesc2, idesc3, (uint32_t)nblk, accum);
-            tc_commit(smem_u32(&ctl->w_empty[wst]));
-          }
-          __syncwarp();
+          if (fuse == 1)
+            issue_batch_dispatch<1>(Dt, G2, batch, cnt, tap_off, slab, wring0 + wst * wstage_bytes, wtile_bytes, b_lbo, acc0,
+                                    idesc, idesc2, idesc3, (uint32_t)nblk, accum);
+          else
+            issue_batch_dispatch<3>(Dt, G2, batch, cnt, tap_off, slab, wring0 + wst * wstage_bytes, wtile_bytes, b_lbo, acc0,
+                                    idesc, idesc2, idesc3, (uint32_t)nblk, accum);
+          tc_commit(smem_u32(&ctl->w_empty[wst]));
           ++w_it;
           accum = 1;
         }
         if (!ok) break;
-        if (elect_one()) tc_commit(smem_u32(&ctl->a_empty[ast]));
-        __syncwarp();
+        tc_commit(smem_u32(&ctl->a_empty[ast]));
         ++a_it;
       }
       if (!ok) break;
-      if (elect_one()) tc_commit(smem_u32(&ctl->acc_full[buf]));
-      __syncwarp();
+      tc_commit(smem_u32(&ctl->acc_full[buf]));
       ++acc_it;
     }
     }

@@ -27,6 +27,15 @@ def shard(items: list, rank: int, world: int) -> list:
     return items[rank::world]
 
 
+def shard_contiguous(items: list, rank: int, world: int) -> list:
+    """Contiguous share of an ordered work list, sizes differing by at most one.  The windows of a volume are listed
+    z-fastest / x-slowest (trainer.py:54-65), so a contiguous share is an x-slab: a rank uploads only its slab."""
+    n = len(items)
+    lo = rank * n // world
+    hi = (rank + 1) * n // world
+    return items[lo:hi]
+
+
 def all_reduce_sum(tensors: Iterable[torch.Tensor]):
     for t in tensors:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

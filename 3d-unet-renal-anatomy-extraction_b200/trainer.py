@@ -90,7 +90,8 @@ def gaussian_window(patch: Sequence[int], sigma_scale: float = 0.125) -> np.ndar
 # sliding-window inference
 # ------------------------------------------------------------------------------------------------
 def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step_per_patch=4, verbose=True,
-                      one_hot=False, window=None, grid_mode="reference", window_batch=2, cuda_graph=True):
+                      one_hot=False, window=None, grid_mode="reference", window_batch=2, cuda_graph=True,
+                      distributed=True):
     """input: (X, Y, Z, C_in) float32 numpy.  Returns uint8 labels (X, Y, Z) or, with one_hot=True,
     float32 probabilities (X, Y, Z, num_classes) -- trainer.py:17-98.
 
@@ -99,8 +100,8 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
     the result does not depend on it -- it only amortises the ~300 kernel launches of a forward pass).
     cuda_graph: capture the forward pass of one window batch once and replay it for the others (this library's
     models only; a window forward is ~300 kernel launches and is host-bound when launched eagerly).
-    Under an initialised torch.distributed job the windows are dealt round-robin to the ranks and the
-    partial sums are all-reduced; every rank returns the full result."""
+    Under an initialised torch.distributed job the window list is cut into contiguous shares (x-slabs), each rank
+    uploads only its slab, and the partial sums are all-reduced; every rank returns the full result."""
     import os
     import time
     dbg = os.environ.get("U3D_PREDICT_TIMES")
@@ -118,10 +119,18 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
     vol = pad_to_patch(np.asarray(input, dtype=np.float32), patch)
     shape = vol.shape[:3]
     origins = tile_origins(shape, patch, step_per_patch, grid_mode)
-    rank, world = parallel.rank_world()
-    mine = origins[rank::world]
+    rank, world = parallel.rank_world() if distributed else (0, 1)      # distributed=False: this process alone
+    mine = parallel.shard_contiguous(origins, rank, world)          # an x-slab of the volume per rank
 
-    x = torch.from_numpy(np.ascontiguousarray(np.moveaxis(vol, -1, 0))[None]).to(device)      # (1, C, X, Y, Z)
+    host = np.ascontiguousarray(np.moveaxis(vol, -1, 0))[None]                                   # (1, C, X, Y, Z)
+    if world > 1:
+        # only the x-range this rank's windows read is uploaded; the rest of the device copy is never touched
+        x = torch.empty(host.shape, dtype=torch.float32, device=device)
+        if mine:
+            xlo, xhi = min(o[0] for o in mine), max(o[0] for o in mine) + patch[0]
+            x[:, :, xlo:xhi].copy_(torch.from_numpy(host[:, :, xlo:xhi]))
+    else:
+        x = torch.from_numpy(host).to(device)
     result = torch.zeros((num_classes, *shape), dtype=torch.float32, device=device)
     weight = torch.zeros(shape, dtype=torch.float32, device=device)
     if isinstance(window, str):

@@ -164,6 +164,13 @@ def _gloo_worker(rank, world, port):
         buf[t] += t + 1
     parallel.all_reduce_sum([buf])
     assert buf.tolist() == [1, 2, 3, 4, 5, 6, 7]     # every window handled exactly once across ranks
+    buf2 = torch.zeros(7)
+    mine = parallel.shard_contiguous(list(range(7)), rank, world)
+    assert mine == list(range(mine[0], mine[-1] + 1))              # a contiguous share
+    for t in mine:
+        buf2[t] += t + 1
+    parallel.all_reduce_sum([buf2])
+    assert buf2.tolist() == [1, 2, 3, 4, 5, 6, 7]
     assert parallel.rank_world() == (rank, world)
     dist.destroy_process_group()
 

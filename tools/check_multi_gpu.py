@@ -1,10 +1,12 @@
-"""2-GPU check of the two data-parallel loss modes, run under torchrun on one box:
+"""Multi-GPU checks, run under torchrun on one box: sliding-window inference sharded over the ranks must
+return the labels of a single process bit for bit (up to the fp32 summation order of overlapping windows: compared as
+label agreement), and the two data-parallel loss modes:
 
   (i)  local Dice (default): every rank's loss on its own shard, gradients averaged == mean of the shard gradients;
   (ii) global_batch=True   : per-class sums all-reduced inside the loss, gradients SUMMED == the gradient of ONE process
                              on the concatenated batch (exact large-batch equivalence).
 
-Both references are computed by rank 0 alone on the same weights.  python -m torch.distributed.run --nproc-per-node 2 tools/check_global_dice.py"""
+Both references are computed by rank 0 alone on the same weights.  python -m torch.distributed.run --nproc-per-node 2 tools/check_multi_gpu.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -51,6 +53,17 @@ for name, glob in (("local-dice / averaged", False), ("global-dice / summed", Tr
     if rank == 0:
         print(f"{name}: worst per-tensor rel-L2 vs the single-process reference {worst:.2e}")
     ok = ok and worst < 2e-2
+import numpy as np
+vol = np.random.RandomState(3).standard_normal((96, 72, 40, 1)).astype(np.float32)
+sharded = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False)
+single = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, distributed=False)
+agree = float((sharded == single).mean())
+probs_s = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, one_hot=True)
+probs_1 = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, one_hot=True, distributed=False)
+dmax = float(np.nanmax(np.abs(probs_s - probs_1)))
+if rank == 0:
+    print(f"sliding-window inference over {world} ranks vs one process: label agreement {agree:.6f}, max |dp| {dmax:.2e}")
+ok = ok and agree > 0.9999 and dmax < 1e-5
 dist.barrier()
 if rank == 0:
     print("OK" if ok else "MISMATCH")

@@ -65,6 +65,7 @@ class UNetEngine:
         self._ops: Dict[Tuple, _ConvOp] = {}
         self._inv_scale = None
         self._last_was_train = True      # the first forward always packs
+        self.grad_chunk_hook = None      # callable(flat prefix tensor) -> handle; set by parallel.overlap_gradient_all_reduce
         self._reset_caches()
 
     def _reset_caches(self):
@@ -74,6 +75,8 @@ class UNetEngine:
         self._dw_arena, self._gflat, self._g_total, self._dw_ready = None, None, 0, False
         self._z_arena, self._z_used, self._z_demand, self._z_size = None, 0, 0, 0
         self._last_gflat = None
+        self._dw_done, self._dw_split, self._g_split, self._chunk_handle = 0, -1, 0, None
+        self._dw_table_a = self._dw_table_b = None
         self._infer_graphs = {}          # predict_per_patch's captured window forwards, by (batch, channels, patch, precision)
 
     # ------------------------------------------------------------------ public entry
@@ -262,6 +265,7 @@ class UNetEngine:
         for xs2, dy2 in more:
             ops.wgrad_gemm(op.wgrad, xs2, dy2, dw, op.grid)
         if slot is not None:
+            self._wgrad_done()
             return self._gflat[slot[1]:slot[1] + param.numel()].view_as(param)
         if id(op.wgrad) not in self._dw_slots:
             self._dw_slots[id(op.wgrad)] = None
@@ -272,16 +276,32 @@ class UNetEngine:
     def _begin_wgrads(self):
         """Called at the start of a backward pass: zero the accumulator arena, allocate this step's flat gradient buffer."""
         self._dw_ready = False
+        self._dw_done = 0
+        self._chunk_handle = None
         if self._dw_table is not None and self._dw_table_n == len(self._dw_order):
             self._dw_arena.zero_()
             self._gflat = torch.empty(self._g_total, dtype=torch.float32, device=self.device)
             self._dw_ready = True
 
+    def _wgrad_done(self):
+        """Bookkeeping after every weight-gradient launch in steady state: when the layers of the FIRST chunk (backward
+        order: head, decoder, bottom level = ~2/3 of the gradient bytes) are complete and somebody asked for it
+        (parallel.overlap_gradient_all_reduce), unpack that chunk now and hand its slice of the flat buffer to the hook
+        -- the NCCL all-reduce of the prefix then overlaps the encoder half of the backward pass."""
+        self._dw_done += 1
+        if self._dw_ready and self.grad_chunk_hook is not None and self._dw_done == self._dw_split:
+            self._dw_table_a.launch(scale=self._inv_scale, out_base=self._gflat)
+            self._chunk_handle = self.grad_chunk_hook(self._gflat[:self._g_split])
+
     def _finish_wgrads(self):
         self._last_gflat = None
         if self._dw_ready:
-            self._dw_table.launch(scale=self._inv_scale, out_base=self._gflat)
-            self._last_gflat = self._gflat
+            if self._chunk_handle is not None or (self.grad_chunk_hook is not None and self._dw_done >= self._dw_split):
+                self._dw_table_b.launch(scale=self._inv_scale, out_base=self._gflat)
+                self._last_gflat = [(self._gflat[:self._g_split], self._chunk_handle), (self._gflat[self._g_split:], None)]
+            else:
+                self._dw_table.launch(scale=self._inv_scale, out_base=self._gflat)
+                self._last_gflat = [(self._gflat, None)]
             self._dw_ready = False
         elif self._dw_order and (self._dw_table is None or self._dw_table_n != len(self._dw_order)):
             off = goff = 0
@@ -297,11 +317,26 @@ class UNetEngine:
                 jobs.append(dict(src0=self._dw_arena[o:o + wp.plan.dw_numel + 1], idx=wp.gidx32, out=4 * g, mode=2))
             self._dw_table = ops.GatherTable(jobs, self.device)
             self._dw_table_n = len(self._dw_order)
+            # two-chunk variant for the overlapped all-reduce: split where the cumulative gradient bytes pass 60 %
+            # (never inside a layer that accumulates several launches: the split counts wgrad CALLS, see _wgrad)
+            acc, split = 0, len(jobs)
+            for i, (wp, n_param) in enumerate(self._dw_order):
+                acc += n_param
+                if acc >= 0.6 * sum(n for _, n in self._dw_order) and i + 1 < len(jobs):
+                    split = i + 1
+                    break
+            self._dw_split = split
+            self._g_split = self._dw_slots[id(self._dw_order[split][0])][1] if split < len(jobs) else goff
+            self._dw_table_a = ops.GatherTable(jobs[:split], self.device) if split < len(jobs) else None
+            self._dw_table_b = ops.GatherTable(jobs[split:], self.device) if split < len(jobs) else None
+            if self._dw_table_a is None:
+                self._dw_split = -1
 
-    def flat_weight_gradients(self) -> Optional[torch.Tensor]:
-        """The flat fp32 buffer the conv weight gradients of the most recent backward are views of (None while the
-        first, layer-by-layer backward of a shape has not recorded the layout): ONE all-reduce covers 99.9 % of the
-        gradient bytes without flattening copies (parallel.all_reduce_gradients)."""
+    def flat_weight_gradients(self):
+        """[(flat fp32 tensor, pending all-reduce handle or None), ...]: the buffer(s) the conv weight gradients of the
+        most recent backward are views of (None while the first, layer-by-layer backward of a shape has not recorded
+        the layout).  One or two all-reduces cover 99.9 % of the gradient bytes without flattening copies; a piece
+        with a handle was already sent by grad_chunk_hook during the backward pass."""
         return self._last_gflat
 
     # ------------------------------------------------------------------ packed weights: one batched launch per step

@@ -57,29 +57,52 @@ def gradient_buckets(params: List[torch.nn.Parameter], bucket_bytes: int = BUCKE
     return buckets
 
 
-def _flat_gradient_buffers(model: torch.nn.Module) -> List[torch.Tensor]:
-    """Flat buffers that already hold (as views) the conv weight gradients of the engine(s) inside `model`."""
-    out = []
+def _engines(model: torch.nn.Module):
     for m in model.modules():
         eng = getattr(m, "_engine", None)
-        flat = eng.flat_weight_gradients() if eng is not None and hasattr(eng, "flat_weight_gradients") else None
-        if flat is not None:
-            out.append(flat)
+        if eng is not None and hasattr(eng, "flat_weight_gradients"):
+            yield eng
+
+
+def overlap_gradient_all_reduce(model: torch.nn.Module, enable: bool = True):
+    """Ask the engine(s) inside `model` to hand the first ~2/3 of the weight gradients (head, decoder, bottom level) to an
+    asynchronous NCCL all-reduce as soon as they are complete, so that the collective overlaps the encoder half of the
+    backward pass; all_reduce_gradients() then waits for it and sends the rest.  Call once after the model is built
+    (forward must have run at least once, or call it again later: engines are created lazily)."""
+    def hook(t):
+        if rank_world()[1] == 1:
+            return None
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+    n = 0
+    for eng in _engines(model):
+        eng.grad_chunk_hook = hook if enable else None
+        n += 1
+    return n
+
+
+def _flat_gradient_buffers(model: torch.nn.Module):
+    """(flat buffer, pending handle or None) pieces that already hold (as views) the conv weight gradients."""
+    out = []
+    for eng in _engines(model):
+        out.extend(eng.flat_weight_gradients() or [])
     return out
 
 
 def all_reduce_gradients(model: torch.nn.Module, average: bool = True):
     """Gradient all-reduce (mean over ranks).  No-op in a single-process run.  The engine's flat weight-gradient
-    buffer (335 MB of the 336 MB at the default net) is reduced in place with one collective; the remaining small
-    tensors (biases, stem, head) go through flattened buckets."""
+    buffer (335 MB of the 336 MB at the default net) is reduced in place with one collective (two when the first
+    chunk was already sent during the backward pass, see overlap_gradient_all_reduce); the remaining small tensors
+    (biases, stem, head) go through flattened buckets."""
     rank, world = rank_world()
     if world == 1:
         return
     works = []
     flats = _flat_gradient_buffers(model)
-    spans = [(f.data_ptr(), f.data_ptr() + f.numel() * f.element_size()) for f in flats]
-    for f in flats:
-        works.append((dist.all_reduce(f, op=dist.ReduceOp.SUM, async_op=True), f, None))
+    spans = [(f.data_ptr(), f.data_ptr() + f.numel() * f.element_size()) for f, _ in flats]
+    for f, handle in flats:
+        if f.numel() == 0:
+            continue
+        works.append((handle if handle is not None else dist.all_reduce(f, op=dist.ReduceOp.SUM, async_op=True), f, None))
     rest = [p for p in model.parameters()
             if p.grad is not None and not any(a <= p.grad.data_ptr() < b for a, b in spans)]
     for bucket in gradient_buckets(rest):

@@ -127,6 +127,8 @@ def main():
     ap.add_argument("--patch", type=int, default=PATCH[0], help="cubic patch edge (default 128 = the metric's config)")
     ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement (cfg-4)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1: all-reduce the first 2/3 of the weight gradients during the encoder half of the backward pass")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -190,8 +192,12 @@ def main():
             print(f"[bench rank {rank}] e2e={e2e} per-step ms: {[round(a.elapsed_time(b), 2) for a, b in evs]}", file=sys.stderr, flush=True)
         return sum(a.elapsed_time(b) for a, b in evs) / n_steps
 
-    for _ in range(W):
+    for i in range(W):
         step(d_img, d_lab)
+        if i == 0 and world > 1 and args.overlap:
+            # engines exist after the first forward: from now on the first ~2/3 of the weight gradients are all-reduced
+            # while the encoder half of the backward pass is still running
+            unet3d_b200.parallel.overlap_gradient_all_reduce(model)
     torch.cuda.synchronize()
     ops.check_device_errors()
     if world > 1:
@@ -241,8 +247,13 @@ def main():
         name = max(by, key=lambda k: by[k][1])
         fl, tms, cnt = by[name]
         ach = fl / (tms * 1e-3) / 1e12
+        # traffic: dram__bytes_read + dram__bytes_write of ONE launch from the committed ncu --set full capture
+        # (profiles/r01_ncu_kernels.txt: the level-0 30->30 forward launch, 203.8 algorithmic GFLOP, 537 MB algorithmic
+        # bytes = 16-bit input + output); the per-step `achieved` above is the FLOP-weighted mean over all 92 launches
         roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "peak_source": f"{src} (bf16_tflops_sustained)",
+                "frac": ach / peak, "traffic": 489.1e6,
+                "traffic_note": "level-0 conv 30->30 k3 forward launch (203.8 GFLOP, 537e6 algorithmic bytes), ncu capture "
+                                "profiles/r01_ncu_kernels.txt", "peak_source": f"{src} (bf16_tflops_sustained)",
                 "launches_per_step": cnt // K, "kernel_ms_per_step": tms / K,
                 "per_kernel_ms_per_step": {k: v[1] / K for k, v in by.items()},
                 "per_kernel_tflops": {k: (v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None) for k, v in by.items()},

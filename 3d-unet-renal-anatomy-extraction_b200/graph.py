@@ -36,6 +36,7 @@ class GraphedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_image = self.static_label = self.static_loss = self.static_logits = None
         self.key = None
+        self._side = None
         _make_capturable(optimizer)
 
     def _eager(self, image, label):
@@ -55,8 +56,18 @@ class GraphedTrainStep:
         key = (tuple(image.shape), tuple(label.shape), image.dtype, label.dtype, self.model.training)
         self.calls += 1
         world = parallel.rank_world()[1]
-        if self.calls <= self.warmup or (self.key is not None and key != self.key) or (world > 1 and self.allreduce):
+        if (self.key is not None and key != self.key) or (world > 1 and self.allreduce):
             return self._eager(image.to(dev, non_blocking=True), label.to(dev, non_blocking=True))
+        if self.calls <= self.warmup:
+            # warm-up steps run on a side stream: autograd's AccumulateGrad nodes are then not tied to the legacy
+            # default stream, which a capturing stream may not synchronise with (cudaErrorStreamCaptureImplicit)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            self._side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self._side):
+                out = self._eager(image.to(dev, non_blocking=True), label.to(dev, non_blocking=True))
+            torch.cuda.current_stream(dev).wait_stream(self._side)
+            return out
         if self.graph is None:
             self.key = key
             self.static_image = torch.empty(image.shape, dtype=image.dtype, device=dev)

@@ -161,3 +161,48 @@ def test_forward_sees_optimizer_updates(fused):
     assert ((out - ref).norm() / ref.norm()).item() < 3e-2
     out2 = m(x).detach().cpu()                                       # grad-enabled forward after the step
     assert ((out2 - ref).norm() / ref.norm()).item() < 3e-2
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (zero_grad + forward + loss + backward + optimizer step captured once, then replayed) follows
+    the eager step loop: same losses on a dropout-free net (the reference's dropout_op=None hook) over 7 steps, of which
+    3 run eagerly as warm-up, one captures and 3 replay.  Covers capture of the batched weight pack / gradient unpack,
+    the statistic and accumulator arenas and the fused optimizer inside the graph."""
+    def build():
+        torch.manual_seed(11)
+        nd = {'dropout_op': None}
+        return unet3d_b200.Unet(1, 3, unet3d_b200.generate_paired_features(2, 8), pool_block=unet3d_b200.ResBlock,
+                                pool_kwargs={'stride': 2, **nd}, encode_block=unet3d_b200.ResBlockStack, encode_kwargs=nd,
+                                encode_kwargs_fn=lambda level: {'num_stacks': max(level, 1)},
+                                decode_block=unet3d_b200.ResBlock, decode_kwargs=nd).to(DEV).train()
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(2, 1, 16, 16, 16, generator=g).to(DEV) for _ in range(7)]
+    ys = [torch.randint(0, 3, (2, 16, 16, 16), generator=g).to(DEV) for _ in range(7)]
+    loss_fn = unet3d_b200.DiceLoss()
+    m1 = build()
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-3)
+    eager = []
+    for x, y in zip(xs, ys):
+        o1.zero_grad(set_to_none=True)
+        l = loss_fn(m1(x), y)
+        l.backward()
+        o1.step()
+        eager.append(l.item())
+    m2 = build()
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    step = unet3d_b200.GraphedTrainStep(m2, loss_fn, o2, warmup=3)
+    graphed = []
+    for x, y in zip(xs, ys):
+        l, _ = step(x, y)
+        graphed.append(l.item())
+    torch.cuda.synchronize()
+    ops.check_device_errors()
+    assert step.graph is not None
+    print("eager  ", [round(v, 5) for v in eager])
+    print("graphed", [round(v, 5) for v in graphed])
+    assert all(abs(a - b) < 2e-3 for a, b in zip(eager, graphed))
+    assert eager[-1] < eager[0]
+    for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        # Adam normalises the update: an element whose tiny gradient changes sign with the atomic summation order moves
+        # by +-lr per step in either run, so the parameters agree to a few lr x steps, not to rounding
+        assert ((p1 - p2).norm() / p1.norm().clamp_min(1e-12)).item() < 0.1, n1

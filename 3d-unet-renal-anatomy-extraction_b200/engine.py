@@ -349,11 +349,17 @@ class UNetEngine:
 
     def _prepack(self):
         """Pack all known (plan, parameter) pairs whose cached tile stream is stale with one gather_multi launch."""
-        if not self._pack_bind or torch.cuda.is_current_stream_capturing():
+        if not self._pack_bind:
             return
+        capturing = torch.cuda.is_current_stream_capturing()
         dt = self.act_dtype
         binds = list(self._pack_bind.values())
-        if all(dp._w_version == dp.weight_key(w, dt) for dp, w in binds):
+        if capturing:
+            # inside a training graph the pack must be part of every replay; only an already built table can be
+            # launched there (building one copies job tables to the device)
+            if self._pack_table is None or self._pack_table_key != (len(binds), dt) or not torch.is_grad_enabled():
+                return
+        elif all(dp._w_version == dp.weight_key(w, dt) for dp, w in binds):
             return
         if self._pack_table is None or self._pack_table_key != (len(binds), dt):
             jobs = []
@@ -377,6 +383,7 @@ class UNetEngine:
         self._pack_table.launch()
         for dp, w in binds:
             dp._w_version = dp.weight_key(w, dt)
+            dp._packed_in_capture = capturing
 
     # ------------------------------------------------------------------ zero-initialised fp64 scratch (statistics)
     def _z64(self, *shape):

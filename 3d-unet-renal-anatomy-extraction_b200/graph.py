@@ -37,26 +37,38 @@ class GraphedTrainStep:
         self.static_image = self.static_label = self.static_loss = self.static_logits = None
         self.key = None
         self._side = None
+        self.graph_opt = None
+        self.launches_per_replay = 0
+        self._static_grads, self._static_flats = [], []
         _make_capturable(optimizer)
 
-    def _eager(self, image, label):
+    def _fwd_bwd(self, image, label):
         self.model.train()
         self.optimizer.zero_grad(set_to_none=True)
         logits = self.model(image)
         loss = self.loss_fn(logits, label)
         loss.backward()
+        return loss, logits
+
+    def _eager(self, image, label):
+        loss, logits = self._fwd_bwd(image, label)
         if self.allreduce:
             parallel.all_reduce_gradients(self.model)
         self.optimizer.step()
         return loss, logits
 
     def __call__(self, image: torch.Tensor, label: torch.Tensor):
-        """Returns (loss, logits) -- device tensors; under replay they are the graph's static outputs."""
+        """Returns (loss, logits) -- device tensors; under replay they are the graph's static outputs.
+
+        Single process: ONE graph holds the whole step.  Data parallel (world > 1 and allreduce): TWO graphs --
+        zero_grad + forward + loss + backward, then the optimizer step -- with the NCCL gradient all-reduce issued
+        eagerly between them on the static gradient buffers (no collective is captured)."""
         dev = next(self.model.parameters()).device
         key = (tuple(image.shape), tuple(label.shape), image.dtype, label.dtype, self.model.training)
         self.calls += 1
         world = parallel.rank_world()[1]
-        if (self.key is not None and key != self.key) or (world > 1 and self.allreduce):
+        split = world > 1 and self.allreduce
+        if self.key is not None and key != self.key:
             return self._eager(image.to(dev, non_blocking=True), label.to(dev, non_blocking=True))
         if self.calls <= self.warmup:
             # warm-up steps run on a side stream: autograd's AccumulateGrad nodes are then not tied to the legacy
@@ -76,13 +88,34 @@ class GraphedTrainStep:
             self.static_label.copy_(label, non_blocking=True)
             torch.cuda.synchronize()
             ops.check_device_errors()
+            launches0 = ops.LAUNCHES
             g = torch.cuda.CUDAGraph()
             self.optimizer.zero_grad(set_to_none=True)
             with torch.cuda.graph(g):
-                self.static_loss, self.static_logits = self._eager(self.static_image, self.static_label)
+                if split:
+                    self.static_loss, self.static_logits = self._fwd_bwd(self.static_image, self.static_label)
+                else:
+                    self.static_loss, self.static_logits = self._eager(self.static_image, self.static_label)
             self.graph = g
+            if split:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=g.pool()):
+                    self.optimizer.step()
+                self.graph_opt = g2
+            self.launches_per_replay = ops.LAUNCHES - launches0      # this library's kernels inside the graph(s)
+            # the gradient tensors the graph writes (and the engine's flat buffers behind them): re-attached before
+            # every replay, so that an eager step in between cannot leave .grad / the all-reduce pointing elsewhere
+            self._static_grads = [(p, p.grad) for p in self.model.parameters()]
+            self._static_flats = [(eng, eng._last_gflat) for eng in parallel._engines(self.model)]
         else:
             self.static_image.copy_(image, non_blocking=True)
             self.static_label.copy_(label, non_blocking=True)
+        for p, g in self._static_grads:
+            p.grad = g
+        for eng, flats in self._static_flats:
+            eng._last_gflat = flats
         self.graph.replay()
+        if split:
+            parallel.all_reduce_gradients(self.model)
+            self.graph_opt.replay()
         return self.static_loss, self.static_logits

@@ -114,6 +114,7 @@ class DeviceConvPlan:
         self.tab, self.widx, self.bidx = cache[dev_key]
         self._w_version = None
         self._w_packed = None
+        self._packed_in_capture = False      # the engine's batched pack ran inside the current graph capture
         self._b_version = None
         self._b_packed = None
 
@@ -137,7 +138,8 @@ class DeviceConvPlan:
         k = self.weight_key(w, dtype, key)
         # a TRAINING graph must re-pack on every replay (the optimizer step is part of it); an inference graph
         # (no_grad) replays against the weights it was captured with
-        if self._w_version == k and not (torch.cuda.is_current_stream_capturing() and torch.is_grad_enabled()):
+        capturing_train = torch.cuda.is_current_stream_capturing() and torch.is_grad_enabled()
+        if self._w_version == k and (not capturing_train or self._packed_in_capture):
             return self._w_packed
         if isinstance(w, (list, tuple)):
             src = torch.cat([t.detach().reshape(-1).float() for t in w])

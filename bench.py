@@ -127,6 +127,9 @@ def main():
     ap.add_argument("--patch", type=int, default=PATCH[0], help="cubic patch edge (default 128 = the metric's config)")
     ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement (cfg-4)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--eager", action="store_true",
+                    help="launch every kernel of the step from Python instead of replaying the captured step "
+                         "(GraphedTrainStep, the library's Trainer(cuda_graph=True) path)")
     ap.add_argument("--overlap", action="store_true",
                     help="N > 1: all-reduce the first 2/3 of the weight gradients during the encoder half of the backward pass")
     args = ap.parse_args()
@@ -163,7 +166,7 @@ def main():
     def allreduce_grads():
         unet3d_b200.parallel.all_reduce_gradients(model)      # bucketed NCCL all-reduce (mean); no-op for N = 1
 
-    def step(img, lab):
+    def eager_step(img, lab):
         opt.zero_grad(set_to_none=True)
         out = model(img)
         loss = loss_fn(out, lab)
@@ -171,6 +174,15 @@ def main():
         allreduce_grads()
         opt.step()
         return loss
+
+    # default: the whole step replayed as a CUDA graph (one graph at N = 1; at N > 1 two graphs with the NCCL all-reduce
+    # issued eagerly between them) -- the same kernels, without ~530 Python-side launches per step
+    stepper = None if args.eager else unet3d_b200.GraphedTrainStep(model, loss_fn, opt, warmup=3)
+
+    def step(img, lab):
+        if stepper is None:
+            return eager_step(img, lab)
+        return stepper(img, lab)[0]
 
     def timed(n_steps, e2e):
         evs = []
@@ -192,7 +204,7 @@ def main():
             print(f"[bench rank {rank}] e2e={e2e} per-step ms: {[round(a.elapsed_time(b), 2) for a, b in evs]}", file=sys.stderr, flush=True)
         return sum(a.elapsed_time(b) for a, b in evs) / n_steps
 
-    for i in range(W):
+    for i in range(max(W, 3) + (0 if stepper is None else 2)):      # 3 eager steps, then capture + one replay
         step(d_img, d_lab)
         if i == 0 and world > 1 and args.overlap:
             # engines exist after the first forward: from now on the first ~2/3 of the weight gradients are all-reduced
@@ -209,14 +221,16 @@ def main():
         sampler.start()
     ops.LAUNCHES = 0
     ms = timed(K, e2e=False)
-    launches = ops.LAUNCHES
+    launches = ops.LAUNCHES if stepper is None else stepper.launches_per_replay * K
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     # per-kernel CUDA events for the roofline: a REPEAT of the timed region (same steps, same inputs, same clocks window)
     # with an event pair around every launch -- kept out of `value` because ~700 event records per step cost ~1.5 ms
     ops.PROFILE = []
+    graphed, stepper = stepper, None          # the event pairs need eager launches
     timed(K, e2e=False)
+    stepper = graphed
     prof = ops.PROFILE
     ops.PROFILE = None
     torch.cuda.synchronize()
@@ -307,7 +321,7 @@ def main():
                 "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": WORKLOAD if pe == 128 else f"REDUCED patch {pe}^3 (not the metric's config)",
-                           "global_batch": BATCH * world, "patch": [pe, pe, pe], "parallelism": f"dp{world}",
+                           "global_batch": BATCH * world, "patch": [pe, pe, pe], "parallelism": f"dp{world}", "cuda_graph": stepper is not None,
                            "timed_region": "zero_grad + forward + DiceLoss + backward + grad all-reduce (N>1) + Adam step",
                            "l2": "256 MB buffer written between timed iterations (L2 flush); activations per step >> L2",
                            "tensor_frac_of_step": (FWD_BWD_FLOP_PER_VOXEL * BATCH * pe ** 3 / (ms * 1e-3) / 1e12) /

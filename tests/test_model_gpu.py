@@ -102,7 +102,7 @@ def _check(model, logits, loss, sdr, ref_logits, ref_loss, y, q_logits, precisio
         print(f"   grad rel-L2 {r:.3e}  {name}")
     # Deep nets: 16-bit forward rounding flips the LeakyReLU mask of near-zero units, and every flipped unit changes
     # the gradient that flows through it; ~40 layers of that decorrelate the encoder gradients from the fp32 run
-    # (PyTorch's own autocast shows the same: tools/amp_reference.py, DESIGN.md 'Numerics').  Shallow nets are tight.
+    # (PyTorch's own autocast shows the same: tests/tools/amp_reference.py, DESIGN.md 'Numerics').  Shallow nets are tight.
     n_layers = sum(1 for n, _ in model.named_parameters() if n.endswith("conv1.weight"))
     if n_layers <= 3:
         grad_tol = 0.06 if precision == "fp16" else 0.35

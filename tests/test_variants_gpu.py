@@ -144,7 +144,7 @@ def test_batchnorm_variant_vs_reference(golden_dir, precision):
     x, y = torch.from_numpy(z["x"]).to(DEV), torch.from_numpy(z["y"]).to(DEV)
     loss_mod = unet3d_b200.HybirdLoss(weight_v=[1, 148, 191], alpha=0.9, beta=0.1)
     # gradient buckets: this 4-channel fixture is noisier than the 8-channel ones -- the InstanceNorm version of the
-    # very same net shows the same errors (tools/bn_vs_in_check.py on a B200: median / max per-tensor rel-L2
+    # very same net shows the same errors (tests/tools/bn_vs_in_check.py on a B200: median / max per-tensor rel-L2
     # 0.093 / 0.147 fp16 and 0.30 / 0.49 bf16 with InstanceNorm, 0.101 / 0.223 and 0.28 / 0.53 with BatchNorm)
     tol, gtol = (1e-2, 0.3) if precision == "fp16" else (3e-2, 0.7)
     for mode in ("train", "eval"):

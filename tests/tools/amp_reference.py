@@ -3,7 +3,7 @@
 same numbers tests/test_model_gpu.py checks for this repo: logits rel-L2 / argmax agreement vs fp32 and per-layer
 gradient rel-L2.  Context for the tolerances in DESIGN.md (not a test)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import unet3d_b200
 from oracle import unet3d_oracle as O

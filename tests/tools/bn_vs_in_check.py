@@ -1,4 +1,6 @@
-import sys; sys.path.insert(0,'/root/repo')
+"""InstanceNorm vs BatchNorm versions of the same 4-channel attention net against the fp32 oracle (test infrastructure:
+the error levels quoted in tests/test_variants_gpu.py).  python tests/tools/bn_vs_in_check.py  (one B200)"""
+import sys; import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, numpy as np
 import unet3d_b200
 from oracle import unet3d_oracle as O

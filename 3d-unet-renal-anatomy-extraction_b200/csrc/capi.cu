@@ -161,6 +161,7 @@ int unet3d_wgrad_gemm(const unet3d_wgrad_args* a, void* stream) {
   p.job_stride = a->job_stride;
   p.split = a->split;
   p.x_f16 = a->x_f16;
+  { const char* e = getenv("U3D_DBG"); p.dbg = e ? atoi(e) : 0; }
   return check(wgrad_gemm_launch(p, reinterpret_cast<cudaStream_t>(stream)), "wgrad_gemm");
 }
 

@@ -79,16 +79,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
       const int n = r / segs;
       if (elect_one()) {
         const uint32_t full = smem_u32(&ctl->full[st]);
-        mbar_expect_tx(full, (uint32_t)Px * Gx * CG_BOX_BYTES + (uint32_t)Dt * Gy * WG_DY_BOX_BYTES);
-        uint32_t dst = stage0 + st * stage_bytes;
-        for (int pl = 0; pl < Px; ++pl)
-          for (int g = 0; g < Gx; ++g, dst += CG_CHUNK_PITCH)
-            tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_XLIST + 2 * g])], full, __ldg(&jt[WG_J_XLIST + 2 * g + 1]),
-                        tw * CG_WT - 1, th * CG_HT - 1, seg * Dt + xd0 + pl, n);
-        for (int d = 0; d < Dt; ++d)
-          for (int g = 0; g < Gy; ++g, dst += WG_DY_BOX_BYTES)
-            tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_YLIST + 2 * g])], full, __ldg(&jt[WG_J_YLIST + 2 * g + 1]),
-                        tw * CG_WT, th * CG_HT, seg * Dt + d, n);
+        if (p.dbg & 32) {
+          mbar_arrive(full);                            // timing experiment: no loads
+        } else {
+          mbar_expect_tx(full, (uint32_t)Px * Gx * CG_BOX_BYTES + (uint32_t)Dt * Gy * WG_DY_BOX_BYTES);
+          uint32_t dst = stage0 + st * stage_bytes;
+          for (int pl = 0; pl < Px; ++pl)
+            for (int g = 0; g < Gx; ++g, dst += CG_CHUNK_PITCH)
+              tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_XLIST + 2 * g])], full, __ldg(&jt[WG_J_XLIST + 2 * g + 1]),
+                          tw * CG_WT - 1, th * CG_HT - 1, seg * Dt + xd0 + pl, n);
+          for (int d = 0; d < Dt; ++d)
+            for (int g = 0; g < Gy; ++g, dst += WG_DY_BOX_BYTES)
+              tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_YLIST + 2 * g])], full, __ldg(&jt[WG_J_YLIST + 2 * g + 1]),
+                          tw * CG_WT, th * CG_HT, seg * Dt + d, n);
+        }
       }
       __syncwarp();
     }

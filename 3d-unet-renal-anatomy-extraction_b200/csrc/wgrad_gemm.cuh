@@ -36,6 +36,7 @@ struct WgradParams {
   int tiles_h, tiles_w;
   int n_jobs, job_stride, split;
   int x_f16;        // storage of the x and dy views: 0 = bf16, 1 = fp16 (tcgen05.mma rejects mixed A/B formats)
+  int dbg;                // timing experiments only (env U3D_DBG): 32 = no loads
 };
 
 int wgrad_gemm_launch(const WgradParams& p, cudaStream_t stream);

@@ -36,7 +36,7 @@ class GatherJob(C.Structure):
 
 
 class WgradArgs(C.Structure):
-    _fields_ = [("n_src", C.c_int), ("src", Src * 16), ("box_w", C.c_int * 16), ("box_h", C.c_int * 16),
+    _fields_ = [("n_src", C.c_int), ("src", Src * 16), ("box_w", C.c_int * 16), ("box_h", C.c_int * 16), ("box_c", C.c_int * 16),
                 ("tab", C.c_void_p), ("dw", C.c_void_p), ("err", C.c_void_p),
                 ("N", C.c_int), ("D", C.c_int), ("H", C.c_int), ("W", C.c_int),
                 ("n_jobs", C.c_int), ("job_stride", C.c_int), ("split", C.c_int), ("x_f16", C.c_int)]

@@ -148,7 +148,8 @@ int unet3d_wgrad_gemm(const unet3d_wgrad_args* a, void* stream) {
   memset(&p, 0, sizeof(p));
   for (int i = 0; i < WG_MAX_MAPS; ++i) {
     const unet3d_src& s = a->src[i < a->n_src ? i : 0];
-    int rc = encode_src(&p.map[i], s, a->box_w[i < a->n_src ? i : 0], a->box_h[i < a->n_src ? i : 0]);
+    const int j = i < a->n_src ? i : 0;
+    int rc = encode_src(&p.map[i], s, a->box_w[j], a->box_h[j], a->box_c[j] > 0 ? a->box_c[j] : 8);
     if (rc != U3D_OK) return rc;
   }
   p.tab = a->tab;

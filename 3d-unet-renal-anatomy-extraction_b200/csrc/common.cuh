@@ -203,6 +203,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw(uint32_t smem_addr, uint32_t sb
   d |= (uint64_t)(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;
   return d;
 }
+// Swizzled MN-major operand (both weight-gradient operands): the MN index runs over 8 w contiguous channels (one row of
+// 16 w bytes, w = 2 / 4 / 8 -> SWIZZLE_32B / 64B / 128B), further MN atoms follow at `lbo_bytes`; the K index runs over 8
+// rows (voxels) at the row pitch, further 8-row groups at `sbo_bytes`.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                    uint32_t row_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 __device__ __host__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major,
                                                              int a_f16 = 0, int b_f16 = 0) {

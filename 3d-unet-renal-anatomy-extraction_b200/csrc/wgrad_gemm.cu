@@ -34,7 +34,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
   const int n_tiles = p.N * segs * p.tiles_h * p.tiles_w;
   if (sid >= n_tiles) return;                       // nothing to contribute (uniform for the CTA)
 
-  const uint32_t xplane = (uint32_t)Gx * CG_CHUNK_PITCH, yplane = (uint32_t)Gy * WG_DY_BOX_BYTES;
+  // swizzled whole-row boxes (plan.py: wx / wy chunks per TMA box) or the 16-byte-row layout (wx == 0)
+  const int sw_word = jt[7];
+  const int wx = sw_word & 0xff, wy = (sw_word >> 8) & 0xff, nbx = (sw_word >> 16) & 0xff, nby = (sw_word >> 24) & 0xff;
+  const bool sw = wx != 0;
+  const uint32_t rbx = 16u * wx, rby = 16u * wy;                                   // row bytes
+  const uint32_t x_box_bytes = (uint32_t)CG_HB * CG_WB * rbx, y_box_bytes = (uint32_t)CG_HT * CG_WT * rby;
+  const uint32_t x_pitch = sw ? (x_box_bytes + 8 * rbx - 1) / (8 * rbx) * (8 * rbx) : 0u, y_pitch = y_box_bytes;
+  const uint32_t xplane = sw ? (uint32_t)nbx * x_pitch : (uint32_t)Gx * CG_CHUNK_PITCH,
+                 yplane = sw ? (uint32_t)nby * y_pitch : (uint32_t)Gy * WG_DY_BOX_BYTES;
   const uint32_t xstage = (uint32_t)Px * xplane, ystage = (uint32_t)Dt * yplane;
   const uint32_t stage_bytes = xstage + ystage;
   const uint32_t stage0 = smem_u32(smem) + 1024;
@@ -54,7 +62,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
   }
   if (threadIdx.x >= 64 && (int)threadIdx.x - 64 < n_ent && threadIdx.x < 64 + 16) {
     const int* ent = jt + WG_J_ENT + (threadIdx.x - 64) * WG_E_SIZE;
-    ctl->ent_aoff[threadIdx.x - 64] = (uint32_t)ent[WG_E_AOFF];
+    ctl->ent_aoff[threadIdx.x - 64] = sw ? ((uint32_t)ent[WG_E_AOFF] >> 4) * rbx : (uint32_t)ent[WG_E_AOFF];   // row shift
     ctl->ent_col[threadIdx.x - 64] = (uint32_t)ent[WG_E_COL];
   }
   tc_fence_before();
@@ -81,6 +89,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
         const uint32_t full = smem_u32(&ctl->full[st]);
         if (p.dbg & 32) {
           mbar_arrive(full);                            // timing experiment: no loads
+        } else if (sw) {
+          mbar_expect_tx(full, (uint32_t)Px * nbx * x_box_bytes + (uint32_t)Dt * nby * y_box_bytes);
+          uint32_t dst = stage0 + st * stage_bytes;
+          for (int pl = 0; pl < Px; ++pl)
+            for (int b = 0; b < nbx; ++b, dst += x_pitch)
+              tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_XLIST + 2 * b])], full, __ldg(&jt[WG_J_XLIST + 2 * b + 1]),
+                          tw * CG_WT - 1, th * CG_HT - 1, seg * Dt + xd0 + pl, n);
+          for (int d = 0; d < Dt; ++d)
+            for (int b = 0; b < nby; ++b, dst += y_pitch)
+              tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_YLIST + 2 * b])], full, __ldg(&jt[WG_J_YLIST + 2 * b + 1]),
+                          tw * CG_WT, th * CG_HT, seg * Dt + d, n);
         } else {
           mbar_expect_tx(full, (uint32_t)Px * Gx * CG_BOX_BYTES + (uint32_t)Dt * Gy * WG_DY_BOX_BYTES);
           uint32_t dst = stage0 + st * stage_bytes;
@@ -101,7 +120,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
     // entries): a warp-level step between MMAs lets the shallow tcgen05 queue drain (measured on the conv kernel).
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, Gy * 8, 1, 1, p.x_f16, p.x_f16);
-      const uint64_t a_kinc = (uint64_t)((2 * CG_WB * 16) >> 4), b_kinc = (uint64_t)((2 * 128) >> 4);
+      // one K step = 16 voxels = two 8-voxel lines of the brick / of the dy tile.  The two layouts get separate loops so
+      // that the 16-byte-row one keeps compile-time descriptor increments (its layers are bound by the MMA issue rate).
+      const uint64_t a_kinc_sw = (uint64_t)((2 * CG_WB * rbx) >> 4), b_kinc_sw = (uint64_t)((2 * CG_WT * rby) >> 4);
       const uint64_t a_dinc = (uint64_t)(xplane >> 4), b_dinc = (uint64_t)(yplane >> 4);
       uint32_t it = 0;
       bool ok = true;
@@ -110,15 +131,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
         if (!mbar_wait(smem_u32(&ctl->full[st]), ph, abort_flag, p.err, 202)) { ok = false; break; }
         tc_fence_after();
         const uint32_t xs = stage0 + st * stage_bytes, ys = xs + xstage;
-        const uint64_t b0 = umma_desc(ys, 128, WG_DY_BOX_BYTES);
-        for (int e = 0; e < n_ent; ++e) {
-          uint64_t a = umma_desc(xs + ent_aoff[e], CG_WB * 16, CG_CHUNK_PITCH);
-          uint64_t b = b0;
-          const uint32_t acc = tmem_base + ent_col[e];
-          for (int d = 0; d < Dt; ++d, a += a_dinc, b += b_dinc) {
-            tc_mma_bf16(acc, a, b, idesc, (it == 0 && d == 0) ? 0u : 1u);
+        if (sw) {
+          const uint64_t b0 = umma_desc_mn_sw(ys, y_pitch, CG_WT * rby, rby);
+          for (int e = 0; e < n_ent; ++e) {
+            uint64_t a = umma_desc_mn_sw(xs + ent_aoff[e], x_pitch, CG_WB * rbx, rbx);
+            uint64_t b = b0;
+            const uint32_t acc = tmem_base + ent_col[e];
+            for (int d = 0; d < Dt; ++d, a += a_dinc, b += b_dinc) {
+              uint64_t ak = a, bk = b;
+              tc_mma_bf16(acc, ak, bk, idesc, (it == 0 && d == 0) ? 0u : 1u);
 #pragma unroll
-            for (int k = 1; k < 8; ++k) tc_mma_bf16(acc, a + k * a_kinc, b + k * b_kinc, idesc, 1u);
+              for (int k = 1; k < 8; ++k) {
+                ak += a_kinc_sw;
+                bk += b_kinc_sw;
+                tc_mma_bf16(acc, ak, bk, idesc, 1u);
+              }
+            }
+          }
+        } else {
+          constexpr uint64_t a_kinc = (uint64_t)((2 * CG_WB * 16) >> 4), b_kinc = (uint64_t)((2 * 128) >> 4);
+          const uint64_t b0 = umma_desc(ys, 128, WG_DY_BOX_BYTES);
+          for (int e = 0; e < n_ent; ++e) {
+            uint64_t a = umma_desc(xs + ent_aoff[e], CG_WB * 16, CG_CHUNK_PITCH);
+            uint64_t b = b0;
+            const uint32_t acc = tmem_base + ent_col[e];
+            for (int d = 0; d < Dt; ++d, a += a_dinc, b += b_dinc) {
+              tc_mma_bf16(acc, a, b, idesc, (it == 0 && d == 0) ? 0u : 1u);
+#pragma unroll
+              for (int k = 1; k < 8; ++k) tc_mma_bf16(acc, a + k * a_kinc, b + k * b_kinc, idesc, 1u);
+            }
           }
         }
         tc_commit(smem_u32(&ctl->empty[st]));

@@ -256,11 +256,12 @@ def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor
                grid: Tuple[int, int, int, int]):
     pl = dp.plan
     a = _lib.WgradArgs()
-    srcs = [(xs[ti], par, P.WT + 2, P.HT + 2) for (ti, par) in pl.x_maps] + [(dy, par, P.WT, P.HT) for par in pl.y_maps]
+    srcs = ([(xs[ti], par, P.WT + 2, P.HT + 2, 8 * pl.wx) for (ti, par) in pl.x_maps] +
+            [(dy, par, P.WT, P.HT, 8 * pl.wy) for par in pl.y_maps])
     a.n_src = len(srcs)
-    for i, (t, par, bw, bh) in enumerate(srcs):
+    for i, (t, par, bw, bh, bc) in enumerate(srcs):
         a.src[i] = make_src(t, par)
-        a.box_w[i], a.box_h[i] = bw, bh
+        a.box_w[i], a.box_h[i], a.box_c[i] = bw, bh, bc
     a.tab, a.dw, a.err = dp.tab.data_ptr(), dw.data_ptr(), err_word(dw.device).data_ptr()
     a.N, a.D, a.H, a.W = grid
     a.n_jobs, a.job_stride, a.split = pl.n_jobs, pl.job_stride, pl.split

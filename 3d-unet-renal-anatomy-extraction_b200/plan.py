@@ -501,6 +501,8 @@ class WgradPlan:
     dw_numel: int
     ld: int
     gidx: np.ndarray            # gather: param_grad.flatten() = cat(dw, [0])[gidx]
+    wx: int = 1                 # chunks per x TMA box (1 = 16-byte rows, no swizzle; 2/4/8 = SWIZZLE_32B/64B/128B rows)
+    wy: int = 1                 # chunks per dy TMA box
     flops_per_voxel: float = 0.0
 
 
@@ -604,17 +606,61 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
                     jobs.append(dict(y0=y0, ycnt=ycnt, gy=gy, m0=m0, gx=gx, p0=p0, units=us[u0:u0 + per]))
     planes_extra = ppm
 
+    # ---- swizzled whole-row boxes: w consecutive 8-channel chunks of one source are loaded as ONE TMA box with rows of
+    # 16 w bytes (SWIZZLE_32B/64B/128B = the swizzled MN-major UMMA layouts; MN atoms of 8 w channels at the box pitch,
+    # which also continues across planes).  16-byte-row boxes cost a 32-byte L2 sector and a shared-memory write
+    # wavefront per row: every layer but the 30-channel ones was load-bound by 1.4-2x (profiles/r01_notes.md).
+    def box_width(lists, exact):
+        longest = max(len(lst) for lst in lists)
+        for w in (8, 4, 2):
+            if w > longest:                 # never pad a short channel list up to a wider box
+                continue
+            ok = True
+            for lst in lists:
+                if exact and len(lst) % w:
+                    ok = False
+                for i in range(0, len(lst), w):
+                    grp = lst[i:i + w]
+                    if any(c["map"] != grp[0]["map"] or c["ch"] != grp[0]["ch"] + 8 * k for k, c in enumerate(grp)):
+                        ok = False
+                if not ok:
+                    break
+            if ok:
+                return w
+        return 1
+
+    xls = [[XL[j["m0"] + i] for i in range(j["gx"])] for j in jobs]
+    yls = [[YL[j["y0"] + i] for i in range(j["ycnt"])] for j in jobs]
+    wx = box_width(xls, case_a)
+    wy = box_width(yls, False)
+    if os.environ.get("U3D_WG_NOSW"):
+        wx = wy = 1
+    use_sw = wx > 1 and wy > 1
+    if case_a and wx < 8:
+        # 16/32-channel 3x3x3 layers are bound by the tensor core's shared-memory operand reads, not by the loads, and a
+        # 32/64-byte MN-major row fills only part of a 128-byte read wavefront: measured 0.436 vs 0.412 ms (30->30) and
+        # 0.951 vs 0.853 ms (60->30 concat) at 2x128^3 -- they keep the 16-byte-row layout (8 rows x 16 B = one wavefront)
+        use_sw = False
+    x_pitch = -(-((HT + 2) * (WT + 2) * 16 * wx) // (128 * wx)) * (128 * wx)       # whole swizzle atoms (8 rows)
+    y_pitch = WG_DY_BOX * wy
+
     job_stride = WG_J_ENT + WG_E_SIZE * WG_ENT_MAX
     tab = np.zeros((len(jobs), job_stride), np.int64)
     for ji, j in enumerate(jobs):
         gx, gy = j["gx"], j["gy"]
-        margin = 0 if (case_a or gx == 16) else (16 - gx) * CHUNK_PITCH
+        if use_sw:
+            nbx, nby = -(-gx // wx), -(-gy // wy)
+            margin = 0 if case_a else (16 // wx - nbx) * x_pitch
+            x_plane, y_plane = nbx * x_pitch, nby * y_pitch
+        else:
+            margin = 0 if (case_a or gx == 16) else (16 - gx) * CHUNK_PITCH
+            x_plane, y_plane = gx * CHUNK_PITCH, gy * WG_DY_BOX
         dt = None
         for cand in _WG_DT_CANDIDATES:
             if cand > max(1, D_):
                 continue
             px = cand - 1 + planes_extra
-            if 2048 + 2 * (px * gx * CHUNK_PITCH + cand * gy * WG_DY_BOX) + margin <= SMEM_LIMIT:
+            if 2048 + 2 * (px * x_plane + cand * y_plane) + margin <= SMEM_LIMIT:
                 dt = cand
                 break
         if dt is None:
@@ -626,10 +672,18 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
         xl = [XL[j["m0"] + i] for i in range(gx)]
         yl = [YL[j["y0"] + i] if i < j["ycnt"] else YL[j["y0"]] for i in range(gy)]
         j["xl"], j["yl"] = xl, yl
-        for i, c in enumerate(xl):
-            row[WG_J_XLIST + 2 * i], row[WG_J_XLIST + 2 * i + 1] = c["map"], c["ch"]
-        for i, c in enumerate(yl):
-            row[WG_J_YLIST + 2 * i], row[WG_J_YLIST + 2 * i + 1] = c["map"], c["ch"]
+        if use_sw:
+            row[7] = wx | (wy << 8) | (nbx << 16) | (nby << 24)
+            for b in range(nbx):
+                row[WG_J_XLIST + 2 * b], row[WG_J_XLIST + 2 * b + 1] = xl[b * wx]["map"], xl[b * wx]["ch"]
+            for b in range(nby):
+                c = YL[j["y0"] + b * wy] if b * wy < j["ycnt"] else YL[j["y0"]]
+                row[WG_J_YLIST + 2 * b], row[WG_J_YLIST + 2 * b + 1] = c["map"], c["ch"]
+        else:
+            for i, c in enumerate(xl):
+                row[WG_J_XLIST + 2 * i], row[WG_J_XLIST + 2 * i + 1] = c["map"], c["ch"]
+            for i, c in enumerate(yl):
+                row[WG_J_YLIST + 2 * i], row[WG_J_YLIST + 2 * i + 1] = c["map"], c["ch"]
         col = 0
         for e, (p0, sh, sw) in enumerate(j["units"]):
             ent = row[WG_J_ENT + e * WG_E_SIZE: WG_J_ENT + (e + 1) * WG_E_SIZE]
@@ -684,4 +738,5 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
     split = max(1, min(n_tiles_max, (waves * num_sms) // len(jobs)))
     return WgradPlan(kind=kind, x_maps=x_maps, y_maps=y_maps, tab=tab.reshape(-1).astype(np.int32), jobs=jobs,
                      n_jobs=len(jobs), job_stride=job_stride, split=split, dw_numel=dw_numel, ld=ld,
-                     gidx=gidx.reshape(-1).astype(np.int64), flops_per_voxel=2.0 * Ktot * Ntot * k3)
+                     gidx=gidx.reshape(-1).astype(np.int64), flops_per_voxel=2.0 * Ktot * Ntot * k3,
+                     wx=wx if use_sw else 1, wy=wy if use_sw else 1)

@@ -106,6 +106,8 @@ typedef struct unet3d_wgrad_args {
   int n_src;                     /* x views (box 10 x 18, halo) and dy views (box 8 x 16) share one array */
   unet3d_src src[16];
   int box_w[16], box_h[16];
+  int box_c[16];                 /* channels per TMA box of each view: 0 / 8 = 16-byte rows without swizzle; 16 / 32 / 64 =
+                                    whole rows with SWIZZLE_32B / 64B / 128B (swizzled MN-major operands) */
   const int* tab;                /* device int32 job table, layout in csrc/wgrad_gemm.cuh */
   float* dw;                     /* fp32 accumulator the partial sums are atomically added to */
   int* err;

@@ -92,15 +92,26 @@ def run_wgrad_plan(plan, xs, dy, grid):
         # brick shift s <-> view index o + s - 1, zero outside (TMA OOB fill); result on the tile grid
         vp = torch.zeros(N, D + 2, H + 2, W + 2, 8, dtype=torch.float64)
         d1, h1, w1 = min(v.shape[1], D + 1), min(v.shape[2], H + 1), min(v.shape[3], W + 1)
-        vp[:, 1:1 + d1, 1:1 + h1, 1:1 + w1] = v[:, :d1, :h1, :w1, ch:ch + 8]
+        if ch < v.shape[-1]:           # channels past the tensor are TMA out-of-bounds zeros (partial boxes)
+            vp[:, 1:1 + d1, 1:1 + h1, 1:1 + w1] = v[:, :d1, :h1, :w1, ch:ch + 8]
         return vp[:, sd:sd + D, sh:sh + H, sw:sw + W]
 
     maps = [(xs[ti], par) for (ti, par) in plan.x_maps] + [(dy, par) for par in plan.y_maps]
     for ji in range(plan.n_jobs):
         row = tab[ji]
         dt, px, xd0, gx, gy, n_ent, ld = (int(v) for v in row[0:7])
-        xl = [(int(row[P.WG_J_XLIST + 2 * i]), int(row[P.WG_J_XLIST + 2 * i + 1])) for i in range(gx)]
-        yl = [(int(row[P.WG_J_YLIST + 2 * i]), int(row[P.WG_J_YLIST + 2 * i + 1])) for i in range(gy)]
+        sw_word = int(row[7])
+        wx, wy, nbx, nby = sw_word & 0xff, (sw_word >> 8) & 0xff, (sw_word >> 16) & 0xff, (sw_word >> 24) & 0xff
+        if wx:      # swizzled whole-row boxes: the lists hold one (map, first channel) per box of wx / wy chunks
+            bx = [(int(row[P.WG_J_XLIST + 2 * b]), int(row[P.WG_J_XLIST + 2 * b + 1])) for b in range(nbx)]
+            by = [(int(row[P.WG_J_YLIST + 2 * b]), int(row[P.WG_J_YLIST + 2 * b + 1])) for b in range(nby)]
+            xl = [(bx[i // wx][0], bx[i // wx][1] + 8 * (i % wx)) for i in range(nbx * wx)]
+            yl = [(by[i // wy][0], by[i // wy][1] + 8 * (i % wy)) for i in range(nby * wy)]
+            gx_mem = nbx * wx          # chunks per plane as laid out in shared memory (the MMA's M index runs over them)
+        else:
+            xl = [(int(row[P.WG_J_XLIST + 2 * i]), int(row[P.WG_J_XLIST + 2 * i + 1])) for i in range(gx)]
+            yl = [(int(row[P.WG_J_YLIST + 2 * i]), int(row[P.WG_J_YLIST + 2 * i + 1])) for i in range(gy)]
+            gx_mem = gx
         for e in range(n_ent):
             ent = row[P.WG_J_ENT + e * P.WG_E_SIZE: P.WG_J_ENT + (e + 1) * P.WG_E_SIZE]
             a_off = int(ent[0])
@@ -111,7 +122,7 @@ def run_wgrad_plan(plan, xs, dy, grid):
                 if ro < 0:
                     continue
                 slot = slot0 + s
-                plane_rel, ci = divmod(slot, gx)
+                plane_rel, ci = divmod(slot, gx_mem)
                 assert plane_rel < px - dt + 1 + 0 or True
                 sd = xd0 + 1 + plane_rel
                 mx, chx = xl[ci]
@@ -124,7 +135,8 @@ def run_wgrad_plan(plan, xs, dy, grid):
                     vy = view(*maps[my])
                     b = torch.zeros(N, D, H, W, 8, dtype=torch.float64)
                     d1, h1, w1 = min(vy.shape[1], D), min(vy.shape[2], H), min(vy.shape[3], W)
-                    b[:, :d1, :h1, :w1] = vy[:, :d1, :h1, :w1, chy:chy + 8]
+                    if chy < vy.shape[-1]:
+                        b[:, :d1, :h1, :w1] = vy[:, :d1, :h1, :w1, chy:chy + 8]
                     blk = torch.einsum("bdhwr,bdhwc->rc", a, b)
                     for r in range(8):
                         dw[ro + r * ld + co: ro + r * ld + co + 8] += blk[r]

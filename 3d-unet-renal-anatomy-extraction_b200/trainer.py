@@ -186,6 +186,8 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
                 ops.sw_accumulate(logits[i].contiguous(), wdev, result, weight, origin)
             if verbose:
                 it.update(len(group))
+            if dbg and b0 < 6 * wb:
+                mark(f"  group {b0 // wb} ({'replay' if graph is not None and b0 else 'eager'})")
     if it is not None:
         it.close()
     model.train(was_training)

@@ -250,7 +250,7 @@ def _kidx_and_valid(plan_kind: str, ks: int, stride: int, pattern: str, shift, p
 
 
 _PLAN_CACHE: Dict[tuple, object] = {}
-_TUNING_ENV = ("U3D_CONV_CFG", "U3D_A_STAGES", "U3D_WG_WAVES")
+_TUNING_ENV = ("U3D_CONV_CFG", "U3D_A_STAGES", "U3D_WG_WAVES", "U3D_WG_NOSW", "U3D_WG_FORCESW")
 
 
 def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: Sequence[int], depth: int,
@@ -636,7 +636,7 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
     if os.environ.get("U3D_WG_NOSW"):
         wx = wy = 1
     use_sw = wx > 1 and wy > 1
-    if case_a and wx < 8:
+    if case_a and wx < 8 and not os.environ.get("U3D_WG_FORCESW"):
         # 16/32-channel 3x3x3 layers are bound by the tensor core's shared-memory operand reads, not by the loads, and a
         # 32/64-byte MN-major row fills only part of a 128-byte read wavefront: measured 0.436 vs 0.412 ms (30->30) and
         # 0.951 vs 0.853 ms (60->30 concat) at 2x128^3 -- they keep the 16-byte-row layout (8 rows x 16 B = one wavefront)

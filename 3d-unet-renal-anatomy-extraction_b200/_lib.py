@@ -35,6 +35,11 @@ class GatherJob(C.Structure):
                 ("n0", C.c_int), ("mode", C.c_int)]
 
 
+class UnpackJob(C.Structure):
+    _fields_ = [("dw", C.c_void_p), ("rowmap", C.c_void_p), ("out", C.c_void_p), ("k3", C.c_int), ("Kp", C.c_int),
+                ("Np", C.c_int), ("Ncols", C.c_int), ("col_stride", C.c_longlong)]
+
+
 class WgradArgs(C.Structure):
     _fields_ = [("n_src", C.c_int), ("src", Src * 16), ("box_w", C.c_int * 16), ("box_h", C.c_int * 16), ("box_c", C.c_int * 16),
                 ("tab", C.c_void_p), ("dw", C.c_void_p), ("err", C.c_void_p),
@@ -50,6 +55,7 @@ _SIGS = {
     "unet3d_conv_gemm_smem_bytes": (C.c_size_t, [C.c_int] * 7),
     "unet3d_weight_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "unet3d_gather_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "unet3d_dw_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "unet3d_wgrad_gemm": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "unet3d_in_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_void_p]),
     "unet3d_in_apply": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
@@ -69,6 +75,12 @@ _SIGS = {
     "unet3d_att_mid_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "unet3d_maxpool3d_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
     "unet3d_maxpool3d_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
+    "unet3d_zoom_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "unet3d_zoom_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                     C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_longlong),
+                                     C.POINTER(C.c_float), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "unet3d_zoom_label": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 _lib = None

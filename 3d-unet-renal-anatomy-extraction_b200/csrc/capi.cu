@@ -263,5 +263,26 @@ int unet3d_gather_multi(const unet3d_gather_job* jobs_dev, const int* first_bloc
                         const float* scale, void* out_base, void* stream) {
   return check(gather_multi(jobs_dev, first_block_dev, n_jobs, n_blocks, scale, out_base, (cudaStream_t)stream), "gather_multi");
 }
+int unet3d_dw_unpack(const unet3d_unpack_job* jobs_dev, const int* first_block_dev, int n_jobs, int n_blocks,
+                     const float* scale, void* out_base, void* stream) {
+  return check(dw_unpack(jobs_dev, first_block_dev, n_jobs, n_blocks, scale, out_base, (cudaStream_t)stream), "dw_unpack");
+}
+size_t unet3d_zoom_workspace_bytes(int out_x, int out_y, int out_z) { return zoom_workspace_bytes(out_x, out_y, out_z); }
+int unet3d_zoom_linear(const void* in, int in_u8, void* out, int out_u8, int C, const int in_shape[3],
+                       const long long in_stride[4], const int out_shape[3], const long long out_stride[4],
+                       const float* norm_host, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!in || !out || !in_shape || !in_stride || !out_shape || !out_stride) return check(U3D_ERR_INVALID, "zoom_linear");
+  return check(zoom_linear(in, in_u8, out, out_u8, C, in_shape, in_stride, out_shape, out_stride, norm_host, workspace,
+                           workspace_bytes, num_sms(), (cudaStream_t)stream),
+               "zoom_linear");
+}
+int unet3d_zoom_label(const uint8_t* in, uint8_t* out, const int in_shape[3], const long long in_stride[3],
+                      const int out_shape[3], const long long out_stride[3], void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (!in || !out || !in_shape || !in_stride || !out_shape || !out_stride) return check(U3D_ERR_INVALID, "zoom_label");
+  return check(zoom_label(in, out, in_shape, in_stride, out_shape, out_stride, workspace, workspace_bytes, num_sms(),
+                          (cudaStream_t)stream),
+               "zoom_label");
+}
 
 }  // extern "C"

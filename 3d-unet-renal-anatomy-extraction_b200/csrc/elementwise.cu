@@ -969,6 +969,42 @@ __global__ void gather_multi_kernel(const unet3d_gather_job* __restrict__ jobs, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight-gradient accumulators dw[k3][Kp][Np] (fp32) -> PyTorch parameter layout, all layers of a step in one launch.
+// The generic gather above reads one 4-byte word per 32-byte sector (the parameter layout runs tap-fastest, the
+// accumulator channel-fastest).  Here one thread owns one whole sector = 8 consecutive dy channels of one (tap, row):
+// two 16-byte loads, eight stores; consecutive threads are consecutive taps, then rows, i.e. consecutive destination
+// addresses, so every one of the eight store instructions of a warp writes one contiguous run.
+// destination element = rowmap[row] + tap + col * col_stride.
+// ---------------------------------------------------------------------------------------------
+__global__ void dw_unpack_kernel(const unet3d_unpack_job* __restrict__ jobs, const int* __restrict__ first_block,
+                                 int n_jobs, const float* __restrict__ scale, char* out_base) {
+  int lo = 0, hi = n_jobs;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((int)blockIdx.x >= __ldg(&first_block[mid])) lo = mid; else hi = mid;
+  }
+  const unet3d_unpack_job j = jobs[lo];
+  const long long item = (long long)(blockIdx.x - __ldg(&first_block[lo])) * 256 + threadIdx.x;
+  const long long items = (long long)j.k3 * j.Kp * (j.Np >> 3);
+  if (item >= items) return;
+  const int tap = (int)(item % j.k3);
+  const long long r = item / j.k3;
+  const int row = (int)(r % j.Kp), cg = (int)(r / j.Kp);
+  const int ro = __ldg(&j.rowmap[row]);
+  if (ro < 0) return;
+  const float4* src = reinterpret_cast<const float4*>(j.dw + ((size_t)tap * j.Kp + row) * j.Np + 8 * cg);
+  const float4 a = __ldg(src), b = __ldg(src + 1);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const float sc = scale ? __ldg(scale) : 1.f;
+  float* o = reinterpret_cast<float*>(out_base + reinterpret_cast<uintptr_t>(j.out)) + ro + tap;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int col = 8 * cg + k;
+    if (col < j.Ncols) o[(long long)col * j.col_stride] = v[k] * sc;
+  }
+}
+
 }  // namespace
 
 // ----------------------------------- launchers ---------------------------------------------------
@@ -1187,6 +1223,13 @@ int gather_multi(const unet3d_gather_job* jobs, const int* first_block, int n_jo
                  void* out_base, cudaStream_t s) {
   if (n_jobs < 1 || n_blocks < 1) return U3D_ERR_INVALID;
   gather_multi_kernel<<<n_blocks, 256, 0, s>>>(jobs, first_block, n_jobs, scale, reinterpret_cast<char*>(out_base));
+  return U3D_CHECK_LAUNCH();
+}
+
+int dw_unpack(const unet3d_unpack_job* jobs, const int* first_block, int n_jobs, int n_blocks, const float* scale,
+              void* out_base, cudaStream_t s) {
+  if (n_jobs < 1 || n_blocks < 1) return U3D_ERR_INVALID;
+  dw_unpack_kernel<<<n_blocks, 256, 0, s>>>(jobs, first_block, n_jobs, scale, reinterpret_cast<char*>(out_base));
   return U3D_CHECK_LAUNCH();
 }
 

@@ -40,5 +40,13 @@ int att_mid_bwd(const bf16* df, const bf16* f, const bf16* dxs, bf16* dpre, bf16
                 int af, int num_sms, cudaStream_t s);
 int gather_multi(const unet3d_gather_job* jobs, const int* first_block, int n_jobs, int n_blocks, const float* scale,
                  void* out_base, cudaStream_t s);
+int dw_unpack(const unet3d_unpack_job* jobs, const int* first_block, int n_jobs, int n_blocks, const float* scale,
+              void* out_base, cudaStream_t s);
+size_t zoom_workspace_bytes(int ox, int oy, int oz);
+int zoom_linear(const void* in, int in_u8, void* out, int out_u8, int C, const int* ishape, const long long* istride,
+                const int* oshape, const long long* ostride, const float* norm_host, void* ws, size_t ws_bytes,
+                int num_sms, cudaStream_t s);
+int zoom_label(const uint8_t* in, uint8_t* out, const int* ishape, const long long* istride, const int* oshape,
+               const long long* ostride, void* ws, size_t ws_bytes, int num_sms, cudaStream_t s);
 
 }  // namespace u3d

@@ -314,8 +314,9 @@ class UNetEngine:
             self._g_total = goff
             for wp, n_param in self._dw_order:
                 o, g = self._dw_slots[id(wp)]
-                jobs.append(dict(src0=self._dw_arena[o:o + wp.plan.dw_numel + 1], idx=wp.gidx32, out=4 * g, mode=2))
-            self._dw_table = ops.GatherTable(jobs, self.device)
+                jobs.append(dict(dw=self._dw_arena[o:o + wp.plan.dw_numel], rowmap=wp.rowmap, out=4 * g,
+                                 **{k: v for k, v in wp.plan.unpack.items() if k != "rowmap"}))
+            self._dw_table = ops.UnpackTable(jobs, self.device)
             self._dw_table_n = len(self._dw_order)
             # two-chunk variant for the overlapped all-reduce: split where the cumulative gradient bytes pass 60 %
             # (never inside a layer that accumulates several launches: the split counts wgrad CALLS, see _wgrad)
@@ -327,8 +328,8 @@ class UNetEngine:
                     break
             self._dw_split = split
             self._g_split = self._dw_slots[id(self._dw_order[split][0])][1] if split < len(jobs) else goff
-            self._dw_table_a = ops.GatherTable(jobs[:split], self.device) if split < len(jobs) else None
-            self._dw_table_b = ops.GatherTable(jobs[split:], self.device) if split < len(jobs) else None
+            self._dw_table_a = ops.UnpackTable(jobs[:split], self.device) if split < len(jobs) else None
+            self._dw_table_b = ops.UnpackTable(jobs[split:], self.device) if split < len(jobs) else None
             if self._dw_table_a is None:
                 self._dw_split = -1
 

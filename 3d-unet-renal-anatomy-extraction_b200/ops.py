@@ -241,6 +241,33 @@ class GatherTable:
                                                   _ptr(scale), _ptr(out_base), _stream()), "unet3d_gather_multi")
 
 
+class UnpackTable:
+    """Device-resident job table of unet3d_dw_unpack: every layer's dw[k3][Kp][Np] accumulator -> parameter layout."""
+
+    def __init__(self, jobs: Sequence[dict], device):
+        """jobs: dicts with dw (fp32 tensor), rowmap (int32 tensor [Kp]), out (int byte offset added to `out_base` at
+        launch), k3, Kp, Np, ncols, col_stride."""
+        arr = (_lib.UnpackJob * len(jobs))()
+        first = [0]
+        self._keep = []
+        for i, j in enumerate(jobs):
+            assert j["dw"].dtype == torch.float32 and j["rowmap"].dtype == torch.int32 and j["Np"] % 8 == 0
+            assert j["dw"].data_ptr() % 16 == 0 and j["rowmap"].numel() == j["Kp"]
+            arr[i].dw, arr[i].rowmap, arr[i].out = j["dw"].data_ptr(), j["rowmap"].data_ptr(), int(j["out"])
+            arr[i].k3, arr[i].Kp, arr[i].Np, arr[i].Ncols = j["k3"], j["Kp"], j["Np"], j["ncols"]
+            arr[i].col_stride = j["col_stride"]
+            first.append(first[-1] + -(-(j["k3"] * j["Kp"] * (j["Np"] // 8)) // 256))
+            self._keep.append((j["dw"], j["rowmap"]))
+        self.jobs_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        self.first = torch.tensor(first, dtype=torch.int32, device=device)
+        self.n_jobs, self.n_blocks = len(jobs), first[-1]
+
+    def launch(self, scale: Optional[torch.Tensor] = None, out_base: Optional[torch.Tensor] = None):
+        _count()
+        _lib.check(_lib.lib().unet3d_dw_unpack(self.jobs_dev.data_ptr(), self.first.data_ptr(), self.n_jobs, self.n_blocks,
+                                               _ptr(scale), _ptr(out_base), _stream()), "unet3d_dw_unpack")
+
+
 class DeviceWgradPlan:
     def __init__(self, plan: P.WgradPlan, device):
         self.plan = plan
@@ -248,8 +275,9 @@ class DeviceWgradPlan:
         cache = plan.__dict__.setdefault("_dev", {})
         if dev_key not in cache:
             gidx = torch.from_numpy(plan.gidx).to(device)
-            cache[dev_key] = (torch.from_numpy(plan.tab).to(device), gidx, gidx.to(torch.int32))
-        self.tab, self.gidx, self.gidx32 = cache[dev_key]
+            cache[dev_key] = (torch.from_numpy(plan.tab).to(device), gidx, gidx.to(torch.int32),
+                              torch.from_numpy(plan.unpack["rowmap"]).to(device))
+        self.tab, self.gidx, self.gidx32, self.rowmap = cache[dev_key]
 
 
 def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor, dw: torch.Tensor,
@@ -449,3 +477,47 @@ def sw_finalize(result, weight, labels, probs):
     with _Timed("sw_finalize", 0.0, weight.numel() * (4.0 * k + 4.0 + (1.0 if labels is not None else 0.0) + (4.0 * k if probs is not None else 0.0))):
         _lib.check(_lib.lib().unet3d_sw_finalize(result.data_ptr(), weight.data_ptr(), _ptr(labels), _ptr(probs), k,
                                                  weight.numel(), _stream()), "unet3d_sw_finalize")
+
+
+# ------------------------------------------------------------------------------------------------
+# case-level resampling (transform.py:32-100 = scipy.ndimage.zoom order 1) -- csrc/resample.cu
+# ------------------------------------------------------------------------------------------------
+def _zoom_ws(out_shape, device):
+    n = _lib.lib().unet3d_zoom_workspace_bytes(*[int(v) for v in out_shape])
+    return torch.empty((n + 15) // 16 * 2, dtype=torch.float64, device=device), n
+
+
+def _c_arr(ctype, values):
+    return (ctype * len(values))(*[int(v) for v in values])
+
+
+def zoom_linear(src: torch.Tensor, dst: torch.Tensor, norm: Optional[Sequence[Sequence[float]]] = None):
+    """dst[x', y', z', c] = zoom(src[..., c]); src / dst are 4-D (x, y, z, channel) VIEWS (any strides) of float32 or
+    uint8 CUDA tensors; the output shape is dst's.  norm: per channel (pct_00_5, pct_99_5, mean, std + 1e-8)."""
+    assert src.is_cuda and dst.is_cuda and src.dim() == 4 and dst.dim() == 4 and src.shape[3] == dst.shape[3]
+    assert src.dtype in (torch.float32, torch.uint8) and dst.dtype in (torch.float32, torch.uint8)
+    ws, nbytes = _zoom_ws(dst.shape[:3], src.device)
+    nm = None
+    if norm is not None:
+        nm = (C.c_float * (4 * len(norm)))(*[float(np.float32(v)) for row in norm for v in row])
+    vox = float(np.prod(dst.shape[:3])) * dst.shape[3]
+    _count(2)
+    with _Timed("zoom_linear", 0.0, vox * (src.element_size() * float(np.prod(src.shape[:3])) / float(np.prod(dst.shape[:3]))
+                                           + dst.element_size())):
+        _lib.check(_lib.lib().unet3d_zoom_linear(
+            src.data_ptr(), int(src.dtype == torch.uint8), dst.data_ptr(), int(dst.dtype == torch.uint8), int(src.shape[3]),
+            _c_arr(C.c_int, src.shape[:3]), _c_arr(C.c_longlong, src.stride()), _c_arr(C.c_int, dst.shape[:3]),
+            _c_arr(C.c_longlong, dst.stride()), nm, ws.data_ptr(), nbytes, _stream()), "unet3d_zoom_linear")
+
+
+def zoom_label(src: torch.Tensor, dst: torch.Tensor):
+    """Labels with >= 3 classes: per-class one-hot zoom + argmax (transform.py:72-78); 3-D uint8 views."""
+    assert src.is_cuda and dst.is_cuda and src.dim() == 3 and dst.dim() == 3
+    assert src.dtype == torch.uint8 and dst.dtype == torch.uint8
+    ws, nbytes = _zoom_ws(dst.shape, src.device)
+    _count(2)
+    with _Timed("zoom_label", 0.0, float(src.numel() + dst.numel())):
+        _lib.check(_lib.lib().unet3d_zoom_label(
+            src.data_ptr(), dst.data_ptr(), _c_arr(C.c_int, src.shape), _c_arr(C.c_longlong, src.stride()),
+            _c_arr(C.c_int, dst.shape), _c_arr(C.c_longlong, dst.stride()), ws.data_ptr(), nbytes, _stream()),
+            "unet3d_zoom_label")

@@ -504,6 +504,8 @@ class WgradPlan:
     wx: int = 1                 # chunks per x TMA box (1 = 16-byte rows, no swizzle; 2/4/8 = SWIZZLE_32B/64B/128B rows)
     wy: int = 1                 # chunks per dy TMA box
     flops_per_voxel: float = 0.0
+    # analytic form of gidx for unet3d_dw_unpack: parameter element = rowmap[row] + tap + col * col_stride
+    unpack: Optional[dict] = None
 
 
 WG_ENT_MAX = 16
@@ -726,6 +728,9 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
     else:                   # Wt[cin][cout][k]
         ci, co, kf = np.meshgrid(np.arange(Ktot), np.arange(Ntot), np.arange(k3), indexing="ij")
     gidx = (kf * Kp + kreal[ci]) * Np + co
+    rowmap = np.full(Kp, -1, np.int32)
+    rowmap[kreal] = np.arange(Ktot) * (k3 if kind == "conv" else Ntot * k3)
+    unpack = dict(k3=k3, Kp=Kp, Np=Np, ncols=Ntot, col_stride=Ktot * k3 if kind == "conv" else k3, rowmap=rowmap)
     n_tiles_min = N_ * (-(-max(1, D_) // 8)) * (-(-H_ // HT)) * (-(-W_ // WT))
     n_tiles_max = N_ * max(1, D_) * (-(-H_ // HT)) * (-(-W_ // WT))
     # CTAs = jobs x split, one CTA per SM at a time (227 KB of shared memory): never spill a few CTAs into an extra
@@ -739,4 +744,4 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
     return WgradPlan(kind=kind, x_maps=x_maps, y_maps=y_maps, tab=tab.reshape(-1).astype(np.int32), jobs=jobs,
                      n_jobs=len(jobs), job_stride=job_stride, split=split, dw_numel=dw_numel, ld=ld,
                      gidx=gidx.reshape(-1).astype(np.int64), flops_per_voxel=2.0 * Ktot * Ntot * k3,
-                     wx=wx if use_sw else 1, wy=wy if use_sw else 1)
+                     wx=wx if use_sw else 1, wy=wy if use_sw else 1, unpack=unpack)

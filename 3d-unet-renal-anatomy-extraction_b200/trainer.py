@@ -2,6 +2,8 @@
 
   predict_per_patch(input, model, num_classes=3, patch_size=(96,96,96), step_per_patch=4,
                     verbose=True, one_hot=False)                                   trainer.py:17-98
+  predict_case(case, model, target_spacing, normalize_stats, num_classes=3, patch_size=(96,96,96),
+               step_per_patch=4, verbose=True, one_hot=False)                      trainer.py:101-133
   Trainer(model, optimizer, loss, dataset, ...).fit / batch_loop / save_checkpoint / load_checkpoint
                                                                                    trainer.py:415-634
 
@@ -113,24 +115,40 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
             t_dbg.append(time.perf_counter())
             print(f"[predict_per_patch rank {parallel.rank_world()[0]}] {what}: {t_dbg[-1] - t_dbg[-2]:.3f} s", flush=True)
 
-    device = next(model.parameters()).device
     patch = tuple(int(p) for p in patch_size)
     orig_shape = input.shape[:3]
     vol = pad_to_patch(np.asarray(input, dtype=np.float32), patch)
-    shape = vol.shape[:3]
+    host = np.ascontiguousarray(np.moveaxis(vol, -1, 0))[None]                                   # (1, C, X, Y, Z)
+
+    def upload(mine, device):
+        if parallel.rank_world()[1] > 1 and distributed:
+            # only the x-range this rank's windows read is uploaded; the rest of the device copy is never touched
+            x = torch.empty(host.shape, dtype=torch.float32, device=device)
+            if mine:
+                xlo, xhi = min(o[0] for o in mine), max(o[0] for o in mine) + patch[0]
+                x[:, :, xlo:xhi].copy_(torch.from_numpy(host[:, :, xlo:xhi]))
+            return x
+        return torch.from_numpy(host).to(device)
+
+    res = _predict_padded(upload, vol.shape[:3], model, num_classes, patch, step_per_patch, verbose, one_hot, window,
+                          grid_mode, window_batch, cuda_graph, distributed, mark)
+    res = res.cpu().numpy()
+    ops.check_device_errors()
+    mark("D2H")
+    return center_pad_crop(res, orig_shape)
+
+
+def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, verbose, one_hot, window, grid_mode,
+                    window_batch, cuda_graph, distributed, mark=lambda what: None):
+    """The window loop on a volume that is already padded to at least one patch (trainer.py:43-96).
+    upload(windows of this rank, device) -> (1, C, X, Y, Z) float32 device tensor.  Returns a DEVICE tensor on the padded
+    grid: uint8 labels (X, Y, Z) or float32 probabilities (X, Y, Z, num_classes)."""
+    device = next(model.parameters()).device
+    shape = tuple(int(v) for v in shape)
     origins = tile_origins(shape, patch, step_per_patch, grid_mode)
     rank, world = parallel.rank_world() if distributed else (0, 1)      # distributed=False: this process alone
     mine = parallel.shard_contiguous(origins, rank, world)          # an x-slab of the volume per rank
-
-    host = np.ascontiguousarray(np.moveaxis(vol, -1, 0))[None]                                   # (1, C, X, Y, Z)
-    if world > 1:
-        # only the x-range this rank's windows read is uploaded; the rest of the device copy is never touched
-        x = torch.empty(host.shape, dtype=torch.float32, device=device)
-        if mine:
-            xlo, xhi = min(o[0] for o in mine), max(o[0] for o in mine) + patch[0]
-            x[:, :, xlo:xhi].copy_(torch.from_numpy(host[:, :, xlo:xhi]))
-    else:
-        x = torch.from_numpy(host).to(device)
+    x = upload(mine, device)
     result = torch.zeros((num_classes, *shape), dtype=torch.float32, device=device)
     weight = torch.zeros(shape, dtype=torch.float32, device=device)
     if isinstance(window, str):
@@ -186,7 +204,7 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
                 ops.sw_accumulate(logits[i].contiguous(), wdev, result, weight, origin)
             if verbose:
                 it.update(len(group))
-            if dbg and b0 < 6 * wb:
+            if b0 < 6 * wb:
                 mark(f"  group {b0 // wb} ({'replay' if graph is not None and b0 else 'eager'})")
     if it is not None:
         it.close()
@@ -196,16 +214,64 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
         parallel.all_reduce_sum([result, weight])
         mark("all-reduce of the blend buffers")
     if one_hot:
-        probs = torch.empty((*shape, num_classes), dtype=torch.float32, device=device)
-        ops.sw_finalize(result, weight, None, probs)
-        res = probs.cpu().numpy()
+        res = torch.empty((*shape, num_classes), dtype=torch.float32, device=device)
+        ops.sw_finalize(result, weight, None, res)
     else:
-        labels = torch.empty(shape, dtype=torch.uint8, device=device)
-        ops.sw_finalize(result, weight, labels, None)
-        res = labels.cpu().numpy()
+        res = torch.empty(shape, dtype=torch.uint8, device=device)
+        ops.sw_finalize(result, weight, res, None)
+    mark("finalize")
+    return res
+
+
+def predict_case(case, model, target_spacing, normalize_stats, num_classes=3, patch_size=(96, 96, 96),
+                 step_per_patch=4, verbose=True, one_hot=False, window=None, grid_mode="reference", window_batch=2,
+                 cuda_graph=True, distributed=True):
+    """trainer.py:101-133: resample + normalise the case, predict it window by window, resize the prediction back to the
+    original grid.  Same arguments and result (``case['pred']``: uint8 labels, or float32 probabilities with one_hot).
+
+    The whole chain stays in HBM: the raw image is uploaded once, ``zoom + clip + z-score`` writes straight into the
+    interior of the zero-padded NCDHW model input (transform.py:387-390 pad), the label map is centre-cropped as a view
+    and zoomed back by the label kernel, and only the final prediction comes back over PCIe."""
+    from . import transform as T
+    device = next(model.parameters()).device
+    patch = tuple(int(p) for p in patch_size)
+    image = np.ascontiguousarray(case['image'], dtype=np.float32)
+    orig_shape = image.shape[:-1]
+    affine = case['affine']
+    scale = np.array(T.get_spacing(affine)) / np.array(target_spacing)
+    table = T.normalize_table(normalize_stats)
+    if len(table) != image.shape[-1]:
+        raise ValueError("one normalize_stats entry per image channel")
+    if verbose:
+        print('Resampling the case for prediction...')
+    raw = torch.from_numpy(image).to(device)
+    rshape = T.zoomed_shape(orig_shape, scale)                               # the resampled grid
+    pshape = tuple(max(rshape[d], patch[d]) for d in range(3))               # ... padded to at least one patch
+    lo = [-((rshape[d] - pshape[d]) // 2) for d in range(3)]                 # centre pad: floor((n - size) / 2) in front
+    x = torch.zeros((1, image.shape[-1], *pshape), dtype=torch.float32, device=device)
+    interior = x[0, :, lo[0]:lo[0] + rshape[0], lo[1]:lo[1] + rshape[1], lo[2]:lo[2] + rshape[2]].permute(1, 2, 3, 0)
+    T.rescale_device(raw, scale, multi_class=True, out=interior, norm=table)
+    if verbose:
+        print('Predicting the case...')
+    pred = _predict_padded(lambda mine, dev: x, pshape, model, num_classes, patch, step_per_patch, verbose, one_hot,
+                           window, grid_mode, window_batch, cuda_graph, distributed)
+    # crop_pad back (trainer.py:98): a view.  The reference pads with ceil((p - n) / 2) voxels in front but crops
+    # floor((p - n) / 2) away, so for an odd difference the result is one voxel off -- kept, it is the reference's output.
+    cl = [(pshape[d] - rshape[d]) // 2 for d in range(3)]
+    pred = pred[cl[0]:cl[0] + rshape[0], cl[1]:cl[1] + rshape[1], cl[2]:cl[2] + rshape[2]]
+    if verbose:
+        print('Resizing the case to origial shape...')
+    back = np.array(orig_shape) / np.array(rshape)
+    if one_hot:
+        out = T.rescale_device(pred, back, multi_class=True)
+    else:
+        out = T.rescale_device(pred, back, is_label=True)
+    case['pred'] = out.cpu().numpy()
+    case['affine'] = affine
     ops.check_device_errors()
-    mark("finalize + D2H")
-    return center_pad_crop(res, orig_shape)
+    if verbose:
+        print('All done!')
+    return case
 
 
 # ------------------------------------------------------------------------------------------------

@@ -312,6 +312,41 @@ def main():
                  "D2H of the uint8 label map" + (", all-reduce of the blend buffers" if world > 1 else ""),
                  "label_hist": [int(v) for v in np.bincount(labels.reshape(-1), minlength=3)[:3]]}
 
+        if rank == 0:
+            # the steps either side of the window loop (trainer.predict_case): zoom + clip + z-score of a raw
+            # 512x512x128 case onto the 512x512x256 grid, and the label map zoomed back -- HBM-bound kernels
+            from unet3d_b200 import transform as T
+            _, hbm, _ = read_peaks()
+            raw = torch.randn(512, 512, 128, 1, device=dev)
+            lab_dev = torch.from_numpy(labels).to(dev)
+            table = T.normalize_table({"mean": 0.1, "std": 0.9, "pct_00_5": -2.0, "pct_99_5": 2.0})
+
+            def kernel_ms(fn, reps=5):
+                fn()
+                ts = []
+                for _ in range(reps):
+                    l2_flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fn()
+                    e1.record()
+                    e1.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                return sorted(ts)[len(ts) // 2]
+            up = torch.empty(512, 512, 256, 1, device=dev)
+            down = torch.empty(512, 512, 128, dtype=torch.uint8, device=dev)
+            ms_up = kernel_ms(lambda: T.rescale_device(raw, (1.0, 1.0, 2.0), multi_class=True, out=up, norm=table))
+            ms_dn = kernel_ms(lambda: T.rescale_device(lab_dev, (1.0, 1.0, 0.5), is_label=True, num_classes=3, out=down))
+            b_up, b_dn = raw.numel() * 4 + up.numel() * 4, lab_dev.numel() + down.numel()
+            infer["prepost"] = {
+                "zoom_linear_norm": {"in": [512, 512, 128], "out": [512, 512, 256], "ms": round(ms_up, 4),
+                                     "gbs": round(b_up / ms_up / 1e6, 1), "frac_hbm": round(b_up / ms_up / 1e6 / hbm, 3)},
+                "zoom_label": {"in": [512, 512, 256], "out": [512, 512, 128], "ms": round(ms_dn, 4),
+                               "gbs": round(b_dn / ms_dn / 1e6, 1), "frac_hbm": round(b_dn / ms_dn / 1e6 / hbm, 3)},
+                "note": "algorithmic bytes (volume in + volume out) / CUDA-event time incl. the per-axis table kernel; "
+                        "bit-exact with scipy.ndimage.zoom(order=1): float64 corner sums"}
+            del raw, lab_dev, up, down
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cvox, cores = cpu_port_step_time(4, 1)

@@ -100,6 +100,21 @@ typedef struct unet3d_gather_job {
 int unet3d_gather_multi(const unet3d_gather_job* jobs_dev, const int* first_block_dev, int n_jobs, int n_blocks,
                         const float* scale, void* out_base, void* stream);
 
+/* Weight-gradient accumulators (unet3d_wgrad_gemm's dw[k3][Kp][Np], fp32) -> PyTorch parameter layout, all layers in one
+ * launch: out[rowmap[row] + tap + col * col_stride] = dw[tap][row][col] * (*scale), rows with rowmap < 0 (channel padding)
+ * and cols >= Ncols skipped.  nn.Conv3d weight (Cout, Cin, k, k, k): rowmap[row] = cin * k3, col_stride = Cin * k3;
+ * nn.ConvTranspose3d weight (Cin, Cout, k, k, k): rowmap[row] = cin * Cout * k3, col_stride = k3.
+ * Job i covers the blocks [first_block[i], first_block[i+1]) of 256 (tap, row, 8-column group) items. */
+typedef struct unet3d_unpack_job {
+  const float* dw;
+  const int* rowmap;     /* device int32 [Kp] */
+  void* out;             /* relative to out_base (pass NULL for absolute pointers) */
+  int k3, Kp, Np, Ncols;
+  long long col_stride;
+} unet3d_unpack_job;
+int unet3d_dw_unpack(const unet3d_unpack_job* jobs_dev, const int* first_block_dev, int n_jobs, int n_blocks,
+                     const float* scale, void* out_base, void* stream);
+
 /* Weight gradient on tcgen05 tensor cores (wgrad_gemm.cu): dW[tap][cin][cout] = sum_v x[v+tap][cin] dy[v][cout].
  * Replaces the cuDNN backward-filter dispatch of the layers listed above. */
 typedef struct unet3d_wgrad_args {
@@ -182,6 +197,25 @@ int unet3d_att_gate_bwd(const void* dout, const void* xs, const void* z, void* d
                         int Cp, int act_f16, void* stream);
 int unet3d_att_mid_bwd(const void* df, const void* f, const void* dxs, void* dpre, void* t, double* sum, long long NV,
                        int Cp, int act_f16, void* stream);
+
+/* Case-level resampling either side of the window loop: transform.rescale / transform.resize (transform.py:32-100), i.e.
+ * scipy.ndimage.zoom(order=1, mode='reflect') per channel, bit-exact (float64 corner sum in SciPy's order, one rounding
+ * to float32).  Shapes are (x, y, z); strides are in ELEMENTS: (x, y, z, channel) -- any layout (the reference's
+ * channel-last numpy volumes, the model's NCDHW input, a padded destination) is a choice of strides and base pointer.
+ * norm_host: NULL, or a HOST array [C][4] = {pct_00_5, pct_99_5, mean, std + 1e-8} as float32: the clip + z-score of
+ * data.resample_normalize_case (data.py:266-272) applied to the zoomed value (float -> float only, C <= 4).
+ * in_u8 / out_u8: uint8 volumes; uint8 -> uint8 is the reference's route for labels with < 3 classes (zoom as float32,
+ * truncate back, transform.py:54-71).  unet3d_zoom_label is the >= 3 classes route (transform.py:72-78): one float
+ * one-hot volume per class, zoomed, argmax with the first maximum winning.
+ * workspace: device memory, 16-byte aligned, >= unet3d_zoom_workspace_bytes(out shape) (per-axis index / weight tables,
+ * rebuilt by every call on `stream`). */
+size_t unet3d_zoom_workspace_bytes(int out_x, int out_y, int out_z);
+int unet3d_zoom_linear(const void* in, int in_u8, void* out, int out_u8, int C, const int in_shape[3],
+                       const long long in_stride[4], const int out_shape[3], const long long out_stride[4],
+                       const float* norm_host, void* workspace, size_t workspace_bytes, void* stream);
+int unet3d_zoom_label(const uint8_t* in, uint8_t* out, const int in_shape[3], const long long in_stride[3],
+                      const int out_shape[3], const long long out_stride[3], void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 #ifdef __cplusplus
 }

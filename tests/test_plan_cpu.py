@@ -1,5 +1,6 @@
 """Host plans (weight packing, tap tables, parity views) executed on CPU vs torch.nn.functional."""
 import importlib
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -124,6 +125,14 @@ def test_wgrad_plans(kind, ks, stride, cins, cout):
     dw = run_wgrad_plan(plan, xs, dyn, (N, D, H, W))
     got = dw[torch.from_numpy(plan.gidx)].reshape(w.shape).float()
     assert torch.allclose(got, w.grad, atol=1e-3, rtol=1e-3), (got - w.grad).abs().max()
+    # the analytic unpack description (unet3d_dw_unpack) addresses exactly the elements gidx does
+    u = plan.unpack
+    tap, row, col = np.meshgrid(np.arange(u["k3"]), np.arange(u["Kp"]), np.arange(u["Np"]), indexing="ij")
+    ok = (u["rowmap"][row] >= 0) & (col < u["ncols"])
+    dest = u["rowmap"][row].astype(np.int64) + tap + col * u["col_stride"]
+    out = np.full(w.numel(), np.nan, dw.numpy().dtype)
+    out[dest[ok]] = dw[:plan.dw_numel].numpy().reshape(tap.shape)[ok]
+    assert ok.sum() == w.numel() and np.array_equal(out, dw[torch.from_numpy(plan.gidx)].numpy())
 
 
 @pytest.mark.parametrize("cins,cout,stride", [([30], 60, 1), ([30, 30], 30, 1), ([30], 60, 2), ([120, 120], 120, 1)])

@@ -75,6 +75,11 @@ _SIGS = {
     "unet3d_att_mid_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "unet3d_maxpool3d_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
     "unet3d_maxpool3d_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
+    "unet3d_ccl_label": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p]),
+    "unet3d_ccl_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "unet3d_region_accumulate": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong),
+                                           C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p]),
+    "unet3d_merge_finalize": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_longlong, C.c_void_p]),
     "unet3d_zoom_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "unet3d_zoom_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int),
                                      C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_longlong),

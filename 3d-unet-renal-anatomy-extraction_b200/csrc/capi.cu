@@ -284,5 +284,23 @@ int unet3d_zoom_label(const uint8_t* in, uint8_t* out, const int in_shape[3], co
                           (cudaStream_t)stream),
                "zoom_label");
 }
+int unet3d_ccl_label(const uint8_t* mask, int* labels, uint8_t* is_root, int X, int Y, int Z, void* stream) {
+  if (!mask || !labels) return check(U3D_ERR_INVALID, "ccl_label");
+  return check(ccl_label(mask, labels, is_root, X, Y, Z, num_sms(), (cudaStream_t)stream), "ccl_label");
+}
+int unet3d_ccl_stats(const int* labels, const int* roots, int n_roots, int* stats, int X, int Y, int Z, void* stream) {
+  if (!labels || !roots || !stats) return check(U3D_ERR_INVALID, "ccl_stats");
+  return check(ccl_stats(labels, roots, n_roots, stats, X, Y, Z, num_sms(), (cudaStream_t)stream), "ccl_stats");
+}
+int unet3d_region_accumulate(const float* pred, double* result, int* count, int K, const int box_n[3],
+                             const long long pstride[3], const int dst0[3], int Y, int Z, void* stream) {
+  if (!pred || !result || !count || !box_n || !pstride || !dst0) return check(U3D_ERR_INVALID, "region_accumulate");
+  return check(region_accumulate(pred, result, count, K, box_n, pstride, dst0, Y, Z, num_sms(), (cudaStream_t)stream),
+               "region_accumulate");
+}
+int unet3d_merge_finalize(const double* result, const int* count, uint8_t* labels, int K, long long n_voxels, void* stream) {
+  if (!result || !count || !labels) return check(U3D_ERR_INVALID, "merge_finalize");
+  return check(merge_finalize(result, count, labels, K, n_voxels, num_sms(), (cudaStream_t)stream), "merge_finalize");
+}
 
 }  // extern "C"

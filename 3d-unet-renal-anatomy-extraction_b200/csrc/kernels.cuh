@@ -48,5 +48,11 @@ int zoom_linear(const void* in, int in_u8, void* out, int out_u8, int C, const i
                 int num_sms, cudaStream_t s);
 int zoom_label(const uint8_t* in, uint8_t* out, const int* ishape, const long long* istride, const int* oshape,
                const long long* ostride, void* ws, size_t ws_bytes, int num_sms, cudaStream_t s);
+int ccl_label(const uint8_t* mask, int* labels, uint8_t* is_root, int X, int Y, int Z, int num_sms, cudaStream_t s);
+int ccl_stats(const int* labels, const int* roots, int n_roots, int* stats, int X, int Y, int Z, int num_sms,
+              cudaStream_t s);
+int region_accumulate(const float* pred, double* result, int* count, int K, const int* box_n, const long long* pstride,
+                      const int* dst0, int Y, int Z, int num_sms, cudaStream_t s);
+int merge_finalize(const double* result, const int* count, uint8_t* labels, int K, long long n, int num_sms, cudaStream_t s);
 
 }  // namespace u3d

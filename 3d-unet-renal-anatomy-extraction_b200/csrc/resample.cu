@@ -44,44 +44,69 @@ struct ZoomNorm {
 
 template <typename T> __device__ __forceinline__ double load_as_double(const T* p) { return (double)__ldg(p); }
 
-// one thread = one output voxel (z fastest -> coalesced stores), all channels
+// Keep a loop-invariant kernel parameter in a register: without this the compiler re-reads the parameters from the constant
+// bank inside the voxel loop, and those loads (ADU pipe) -- not float64 arithmetic or HBM -- bounded the kernels (ncu: 91 %).
+__device__ __forceinline__ long long pin(long long v) { asm volatile("" : "+l"(v)); return v; }
+__device__ __forceinline__ int pin(int v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); return v; }
+template <typename T> __device__ __forceinline__ T* pin(T* p) { asm volatile("" : "+l"(p)); return p; }
+
+// one CTA = one or more (x, y) output rows, threads run along z (coalesced stores, contiguous corner loads); the x / y
+// table entries are uniform per row, so a voxel costs its 8 loads, 24 + 8 float64 operations and a handful of integer ones
 template <typename TIn, typename TOut>
 __global__ void zoom_linear_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const int* __restrict__ idx,
                                    const double* __restrict__ wts, int C, int OX, int OY, int OZ, long long isx,
                                    long long isy, long long isz, long long isc, long long osx, long long osy,
                                    long long osz, long long osc, ZoomNorm nm) {
-  const long long total = (long long)OX * OY * OZ;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int oz = (int)(i % OZ), oy = (int)((i / OZ) % OY), ox = (int)(i / ((long long)OZ * OY));
+  const int rows = OX * OY;
+  in = pin(in); out = pin(out); idx = pin(idx); wts = pin(wts);
+  C = pin(C); OZ = pin(OZ); isz = pin(isz); isc = pin(isc); osz = pin(osz); osc = pin(osc);
+  const int on = pin(nm.on);
+  // channel 0's constants live in registers; further channels (rare) read the parameter block
+  const float lo0 = pin(nm.lo[0]), hi0 = pin(nm.hi[0]), mean0 = pin(nm.mean[0]), den0 = pin(nm.den[0]);
+  const int2* idz = reinterpret_cast<const int2*>(idx) + OX + OY;
+  const double2* wtz = reinterpret_cast<const double2*>(wts) + OX + OY;
+  for (int row = blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += gridDim.x * blockDim.y) {
+    const int ox = row / OY, oy = row - ox * OY;
     const int2 ix = __ldg(reinterpret_cast<const int2*>(idx) + ox);
     const int2 iy = __ldg(reinterpret_cast<const int2*>(idx) + OX + oy);
-    const int2 iz = __ldg(reinterpret_cast<const int2*>(idx) + OX + OY + oz);
     const double2 wx = __ldg(reinterpret_cast<const double2*>(wts) + ox);
     const double2 wy = __ldg(reinterpret_cast<const double2*>(wts) + OX + oy);
-    const double2 wz = __ldg(reinterpret_cast<const double2*>(wts) + OX + OY + oz);
-    const long long bx[2] = {ix.x * isx, ix.y * isx}, by[2] = {iy.x * isy, iy.y * isy}, bz[2] = {iz.x * isz, iz.y * isz};
-    const double ax[2] = {wx.x, wx.y}, ay[2] = {wy.x, wy.y}, az[2] = {wz.x, wz.y};
-    for (int c = 0; c < C; ++c) {
-      const TIn* src = in + c * isc;
-      double t = 0.0;
+    const long long bxy[4] = {ix.x * isx + iy.x * isy, ix.x * isx + iy.y * isy, ix.y * isx + iy.x * isy,
+                              ix.y * isx + iy.y * isy};
+    const double ax[2] = {wx.x, wx.y}, ay[2] = {wy.x, wy.y};
+    TOut* orow = out + ox * osx + oy * osy;
+    for (int oz = threadIdx.x; oz < OZ; oz += blockDim.x) {
+      const int2 iz = __ldg(idz + oz);
+      const double2 wz = __ldg(wtz + oz);
+      const long long bz[2] = {iz.x * isz, iz.y * isz};
+      const double az[2] = {wz.x, wz.y};
+      for (int c = 0; c < C; ++c) {
+        const TIn* src = in + c * isc;
+        double t = 0.0;
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
+          for (int b = 0; b < 2; ++b)
 #pragma unroll
-          for (int d = 0; d < 2; ++d) {
-            const double v = load_as_double(src + bx[a] + by[b] + bz[d]);
-            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v, ax[a]), ay[b]), az[d]));
+            for (int d = 0; d < 2; ++d) {
+              const double v = load_as_double(src + bxy[a * 2 + b] + bz[d]);
+              t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v, ax[a]), ay[b]), az[d]));
+            }
+        float r = __double2float_rn(t);
+        if (on) {
+          float lo = lo0, hi = hi0, mean = mean0, den = den0;
+          if (c > 0) {
+            const int cn = c < 4 ? c : 3;
+            lo = nm.lo[cn], hi = nm.hi[cn], mean = nm.mean[cn], den = nm.den[cn];
           }
-      float r = __double2float_rn(t);
-      if (nm.on) {
-        const int cn = c < 4 ? c : 3;
-        r = fminf(fmaxf(r, nm.lo[cn]), nm.hi[cn]);                       // np.clip
-        r = __fdiv_rn(__fsub_rn(r, nm.mean[cn]), nm.den[cn]);            // (x - mean) / (std + 1e-8), float32
+          r = fminf(fmaxf(r, lo), hi);                                     // np.clip
+          r = __fdiv_rn(__fsub_rn(r, mean), den);                          // (x - mean) / (std + 1e-8), float32
+        }
+        TOut* dst = orow + oz * osz + c * osc;
+        if constexpr (sizeof(TOut) == 1) *dst = (TOut)r;                   // .astype(uint8): truncation
+        else *dst = r;
       }
-      TOut* dst = out + ox * osx + oy * osy + oz * osz + c * osc;
-      if constexpr (sizeof(TOut) == 1) *dst = (TOut)r;                   // .astype(uint8): truncation
-      else *dst = r;
     }
   }
 }
@@ -92,43 +117,52 @@ __global__ void zoom_linear_kernel(const TIn* __restrict__ in, TOut* __restrict_
 __global__ void zoom_label_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int* __restrict__ idx,
                                   const double* __restrict__ wts, int OX, int OY, int OZ, long long isx, long long isy,
                                   long long isz, long long osx, long long osy, long long osz) {
-  const long long total = (long long)OX * OY * OZ;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int oz = (int)(i % OZ), oy = (int)((i / OZ) % OY), ox = (int)(i / ((long long)OZ * OY));
+  const int rows = OX * OY;
+  in = pin(in); out = pin(out); idx = pin(idx); wts = pin(wts);
+  OZ = pin(OZ); isz = pin(isz); osz = pin(osz);
+  const int2* idz = reinterpret_cast<const int2*>(idx) + OX + OY;
+  const double2* wtz = reinterpret_cast<const double2*>(wts) + OX + OY;
+  for (int row = blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += gridDim.x * blockDim.y) {
+    const int ox = row / OY, oy = row - ox * OY;
     const int2 ix = __ldg(reinterpret_cast<const int2*>(idx) + ox);
     const int2 iy = __ldg(reinterpret_cast<const int2*>(idx) + OX + oy);
-    const int2 iz = __ldg(reinterpret_cast<const int2*>(idx) + OX + OY + oz);
-    const long long bx[2] = {ix.x * isx, ix.y * isx}, by[2] = {iy.x * isy, iy.y * isy}, bz[2] = {iz.x * isz, iz.y * isz};
-    int lab[8];
-    bool same = true;
-#pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      lab[h] = __ldg(in + bx[h >> 2] + by[(h >> 1) & 1] + bz[h & 1]);
-      same = same && lab[h] == lab[0];
-    }
-    int best = lab[0];
-    if (!same) {
-      const double2 wx = __ldg(reinterpret_cast<const double2*>(wts) + ox);
-      const double2 wy = __ldg(reinterpret_cast<const double2*>(wts) + OX + oy);
-      const double2 wz = __ldg(reinterpret_cast<const double2*>(wts) + OX + OY + oz);
-      const double ax[2] = {wx.x, wx.y}, ay[2] = {wy.x, wy.y}, az[2] = {wz.x, wz.y};
-      double p[8];
-#pragma unroll
-      for (int h = 0; h < 8; ++h) p[h] = __dmul_rn(__dmul_rn(ax[h >> 2], ay[(h >> 1) & 1]), az[h & 1]);
-      float bestv = -1.f;
-      best = 256;
+    const long long bxy[4] = {ix.x * isx + iy.x * isy, ix.x * isx + iy.y * isy, ix.y * isx + iy.x * isy,
+                              ix.y * isx + iy.y * isy};
+    uint8_t* orow = out + ox * osx + oy * osy;
+    for (int oz = threadIdx.x; oz < OZ; oz += blockDim.x) {
+      const int2 iz = __ldg(idz + oz);
+      const long long bz[2] = {iz.x * isz, iz.y * isz};
+      int lab[8];
+      bool same = true;
 #pragma unroll
       for (int h = 0; h < 8; ++h) {
-        const int c = lab[h];
-        double t = 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (lab[j] == c) t = __dadd_rn(t, p[j]);
-        const float tv = __double2float_rn(t);
-        if (tv > bestv || (tv == bestv && c < best)) { bestv = tv; best = c; }
+        lab[h] = __ldg(in + bxy[h >> 1] + bz[h & 1]);
+        same = same && lab[h] == lab[0];
       }
+      int best = lab[0];
+      if (!same) {
+        const double2 wx = __ldg(reinterpret_cast<const double2*>(wts) + ox);
+        const double2 wy = __ldg(reinterpret_cast<const double2*>(wts) + OX + oy);
+        const double2 wz = __ldg(wtz + oz);
+        const double ax[2] = {wx.x, wx.y}, ay[2] = {wy.x, wy.y}, az[2] = {wz.x, wz.y};
+        double p[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) p[h] = __dmul_rn(__dmul_rn(ax[h >> 2], ay[(h >> 1) & 1]), az[h & 1]);
+        float bestv = -1.f;
+        best = 256;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const int c = lab[h];
+          double t = 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (lab[j] == c) t = __dadd_rn(t, p[j]);
+          const float tv = __double2float_rn(t);
+          if (tv > bestv || (tv == bestv && c < best)) { bestv = tv; best = c; }
+        }
+      }
+      orow[oz * osz] = (uint8_t)best;
     }
-    out[ox * osx + oy * osy + oz * osz] = (uint8_t)best;
   }
 }
 
@@ -148,10 +182,14 @@ int build_tables(const int* ishape, const int* oshape, void* ws, size_t ws_bytes
   return cudaGetLastError() == cudaSuccess ? U3D_OK : U3D_ERR_CUDA;
 }
 
-inline int grid_1d(long long total, int per_block, int num_sms) {
-  const long long want = (total + per_block - 1) / per_block;
-  const long long cap = (long long)num_sms * 16;
-  return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+// threads along z: 32..128; short rows share a CTA (blockDim.y rows) so that a CTA always has 128 threads
+inline void row_geometry(const int* oshape, int num_sms, dim3* grid, dim3* block) {
+  const int tz = oshape[2] > 64 ? 128 : (oshape[2] > 32 ? 64 : 32);
+  const int ty = 128 / tz;
+  const long long rows = (long long)oshape[0] * oshape[1];
+  const long long want = (rows + ty - 1) / ty, cap = (long long)num_sms * 64;
+  *block = dim3(tz, ty, 1);
+  *grid = dim3((unsigned)(want < 1 ? 1 : (want < cap ? want : cap)), 1, 1);
 }
 
 }  // namespace
@@ -176,10 +214,11 @@ int zoom_linear(const void* in, int in_u8, void* out, int out_u8, int C, const i
       nm.mean[c] = norm_host[4 * c + 2], nm.den[c] = norm_host[4 * c + 3];
     }
   }
-  const long long total = (long long)oshape[0] * oshape[1] * oshape[2];
-  const int g = grid_1d(total, 256, num_sms);
+  if ((long long)oshape[0] * oshape[1] > 0x7fffffffLL) return U3D_ERR_UNSUPPORTED;
+  dim3 g, b;
+  row_geometry(oshape, num_sms, &g, &b);
 #define U3D_ZOOM(TI, TO)                                                                                              \
-  zoom_linear_kernel<TI, TO><<<g, 256, 0, s>>>((const TI*)in, (TO*)out, idx, wts, C, oshape[0], oshape[1], oshape[2], \
+  zoom_linear_kernel<TI, TO><<<g, b, 0, s>>>((const TI*)in, (TO*)out, idx, wts, C, oshape[0], oshape[1], oshape[2], \
                                                istride[0], istride[1], istride[2], istride[3], ostride[0], ostride[1], \
                                                ostride[2], ostride[3], nm)
   if (!in_u8 && !out_u8) U3D_ZOOM(float, float);
@@ -195,8 +234,10 @@ int zoom_label(const uint8_t* in, uint8_t* out, const int* ishape, const long lo
   int* idx;
   double* wts;
   if (int rc = build_tables(ishape, oshape, ws, ws_bytes, &idx, &wts, s)) return rc;
-  const long long total = (long long)oshape[0] * oshape[1] * oshape[2];
-  zoom_label_kernel<<<grid_1d(total, 256, num_sms), 256, 0, s>>>(in, out, idx, wts, oshape[0], oshape[1], oshape[2],
+  if ((long long)oshape[0] * oshape[1] > 0x7fffffffLL) return U3D_ERR_UNSUPPORTED;
+  dim3 g, b;
+  row_geometry(oshape, num_sms, &g, &b);
+  zoom_label_kernel<<<g, b, 0, s>>>(in, out, idx, wts, oshape[0], oshape[1], oshape[2],
                                                                  istride[0], istride[1], istride[2], ostride[0],
                                                                  ostride[1], ostride[2]);
   return cudaGetLastError() == cudaSuccess ? U3D_OK : U3D_ERR_CUDA;

@@ -521,3 +521,55 @@ def zoom_label(src: torch.Tensor, dst: torch.Tensor):
             src.data_ptr(), dst.data_ptr(), _c_arr(C.c_int, src.shape), _c_arr(C.c_longlong, src.stride()),
             _c_arr(C.c_int, dst.shape), _c_arr(C.c_longlong, dst.stride()), ws.data_ptr(), nbytes, _stream()),
             "unet3d_zoom_label")
+
+
+# ------------------------------------------------------------------------------------------------
+# cascade glue (data.regions_crop_case, trainer.cascade_predict_case merge) -- csrc/regions.cu
+# ------------------------------------------------------------------------------------------------
+def connected_components(mask: torch.Tensor):
+    """6-connected components of a uint8 CUDA volume (X, Y, Z): scipy.ndimage.label's numbering.
+    Returns (labels int32 (X, Y, Z): root index or -1, roots int32 [n] sorted, stats int32 [n][8] =
+    {voxels, xmin, xmax, ymin, ymax, zmin, zmax, 0})."""
+    assert mask.is_cuda and mask.dtype == torch.uint8 and mask.dim() == 3 and mask.is_contiguous()
+    X, Y, Z = (int(v) for v in mask.shape)
+    labels = torch.empty((X, Y, Z), dtype=torch.int32, device=mask.device)
+    is_root = torch.empty((X, Y, Z), dtype=torch.uint8, device=mask.device)
+    _count(3)
+    with _Timed("ccl_label", 0.0, mask.numel() * (1.0 + 4.0 + 1.0)):
+        _lib.check(_lib.lib().unet3d_ccl_label(mask.data_ptr(), labels.data_ptr(), is_root.data_ptr(), X, Y, Z, _stream()),
+                   "unet3d_ccl_label")
+    roots = torch.nonzero(is_root.view(-1)).view(-1).to(torch.int32)          # sorted = raster order of the first voxels
+    n = int(roots.numel())
+    init = torch.tensor([0, 2 ** 31 - 1, -1, 2 ** 31 - 1, -1, 2 ** 31 - 1, -1, 0], dtype=torch.int32, device=mask.device)
+    stats = init.repeat(max(n, 1), 1).contiguous()
+    if n:
+        _count()
+        with _Timed("ccl_stats", 0.0, mask.numel() * 4.0):
+            _lib.check(_lib.lib().unet3d_ccl_stats(labels.data_ptr(), roots.data_ptr(), n, stats.data_ptr(), X, Y, Z,
+                                                   _stream()), "unet3d_ccl_stats")
+    return labels, roots, stats[:n]
+
+
+def region_accumulate(pred: torch.Tensor, result: torch.Tensor, count: torch.Tensor, src0, dst0, box):
+    """result[dst0 + i] += pred[src0 + i] over `box` voxels; pred float32 (rx, ry, rz, K) view, result float64
+    (X, Y, Z, K) contiguous, count int32 (X, Y, Z) contiguous."""
+    assert pred.dtype == torch.float32 and result.dtype == torch.float64 and count.dtype == torch.int32
+    assert result.is_contiguous() and count.is_contiguous() and pred.stride(3) == 1 and pred.shape[3] == result.shape[3]
+    if min(box) < 1:
+        return
+    view = pred[src0[0]:src0[0] + box[0], src0[1]:src0[1] + box[1], src0[2]:src0[2] + box[2]]
+    _count()
+    with _Timed("region_accumulate", 0.0, float(np.prod(box)) * (pred.shape[3] * 20.0 + 8.0)):
+        _lib.check(_lib.lib().unet3d_region_accumulate(
+            view.data_ptr(), result.data_ptr(), count.data_ptr(), int(pred.shape[3]), _c_arr(C.c_int, box),
+            _c_arr(C.c_longlong, view.stride()[:3]), _c_arr(C.c_int, dst0), int(result.shape[1]), int(result.shape[2]),
+            _stream()), "unet3d_region_accumulate")
+
+
+def merge_finalize(result: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
+    labels = torch.empty(count.shape, dtype=torch.uint8, device=count.device)
+    _count()
+    with _Timed("merge_finalize", 0.0, count.numel() * (8.0 * result.shape[3] + 5.0)):
+        _lib.check(_lib.lib().unet3d_merge_finalize(result.data_ptr(), count.data_ptr(), labels.data_ptr(),
+                                                    int(result.shape[3]), count.numel(), _stream()), "unet3d_merge_finalize")
+    return labels

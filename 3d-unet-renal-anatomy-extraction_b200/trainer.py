@@ -4,6 +4,8 @@
                     verbose=True, one_hot=False)                                   trainer.py:17-98
   predict_case(case, model, target_spacing, normalize_stats, num_classes=3, patch_size=(96,96,96),
                step_per_patch=4, verbose=True, one_hot=False)                      trainer.py:101-133
+  cascade_predict_case(case, coarse_model, ..., detail_model, ..., num_classes=3, step_per_patch=4,
+                       region_threshold=10000, crop_padding=20, verbose=True)      trainer.py:164-245
   Trainer(model, optimizer, loss, dataset, ...).fit / batch_loop / save_checkpoint / load_checkpoint
                                                                                    trainer.py:415-634
 
@@ -225,7 +227,7 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
 
 def predict_case(case, model, target_spacing, normalize_stats, num_classes=3, patch_size=(96, 96, 96),
                  step_per_patch=4, verbose=True, one_hot=False, window=None, grid_mode="reference", window_batch=2,
-                 cuda_graph=True, distributed=True):
+                 cuda_graph=True, distributed=True, keep_on_device=False):
     """trainer.py:101-133: resample + normalise the case, predict it window by window, resize the prediction back to the
     original grid.  Same arguments and result (``case['pred']``: uint8 labels, or float32 probabilities with one_hot).
 
@@ -235,8 +237,10 @@ def predict_case(case, model, target_spacing, normalize_stats, num_classes=3, pa
     from . import transform as T
     device = next(model.parameters()).device
     patch = tuple(int(p) for p in patch_size)
-    image = np.ascontiguousarray(case['image'], dtype=np.float32)
-    orig_shape = image.shape[:-1]
+    image = case['image']                                  # numpy (X, Y, Z, C) like the reference, or already in HBM
+    if not isinstance(image, torch.Tensor):
+        image = np.ascontiguousarray(image, dtype=np.float32)
+    orig_shape = tuple(image.shape[:-1])
     affine = case['affine']
     scale = np.array(T.get_spacing(affine)) / np.array(target_spacing)
     table = T.normalize_table(normalize_stats)
@@ -244,7 +248,7 @@ def predict_case(case, model, target_spacing, normalize_stats, num_classes=3, pa
         raise ValueError("one normalize_stats entry per image channel")
     if verbose:
         print('Resampling the case for prediction...')
-    raw = torch.from_numpy(image).to(device)
+    raw = image.to(device, torch.float32) if isinstance(image, torch.Tensor) else torch.from_numpy(image).to(device)
     rshape = T.zoomed_shape(orig_shape, scale)                               # the resampled grid
     pshape = tuple(max(rshape[d], patch[d]) for d in range(3))               # ... padded to at least one patch
     lo = [-((rshape[d] - pshape[d]) // 2) for d in range(3)]                 # centre pad: floor((n - size) / 2) in front
@@ -266,8 +270,57 @@ def predict_case(case, model, target_spacing, normalize_stats, num_classes=3, pa
         out = T.rescale_device(pred, back, multi_class=True)
     else:
         out = T.rescale_device(pred, back, is_label=True)
-    case['pred'] = out.cpu().numpy()
+    case['pred'] = out if keep_on_device else out.cpu().numpy()
     case['affine'] = affine
+    ops.check_device_errors()
+    if verbose:
+        print('All done!')
+    return case
+
+
+def cascade_predict_case(case, coarse_model, coarse_target_spacing, coarse_normalize_stats, coarse_patch_size,
+                         detail_model, detail_target_spacing, detail_normalize_stats, detail_patch_size, num_classes=3,
+                         step_per_patch=4, region_threshold=10000, crop_padding=20, verbose=True, **predict_kwargs):
+    """trainer.py:164-245: coarse one-class prediction -> connected regions of at least ``region_threshold`` voxels, each
+    grown by ``crop_padding`` mm -> detail prediction per region -> mean of the overlapping probabilities -> labels.
+
+    Same arguments and result (``case['pred']`` uint8 on the original grid).  The image is uploaded once; the coarse
+    mask, the component labelling (csrc/regions.cu), the region crops, their predictions and the merge buffers all stay
+    in HBM, and only the final label map is copied back."""
+    from . import transform as T
+    device = next(detail_model.parameters()).device
+    if verbose:
+        print('Predicting the rough shape for further prediction...')
+    image = case['image']
+    dev_image = image if isinstance(image, torch.Tensor) else \
+        torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(device)
+    work = dict(case)
+    work['image'] = dev_image
+    work = predict_case(work, coarse_model, coarse_target_spacing, coarse_normalize_stats, 1, coarse_patch_size,
+                        step_per_patch, verbose=verbose, keep_on_device=True, **predict_kwargs)
+    work.setdefault('case_id', 'case')
+    regions = T.regions_crop_case(work, region_threshold, crop_padding, 'pred')
+    num_classes = detail_model.out_channels
+    orig_shape = tuple(dev_image.shape[:-1])
+    result = torch.zeros((*orig_shape, num_classes), dtype=torch.float64, device=device)
+    result_n = torch.zeros(orig_shape, dtype=torch.int32, device=device)
+    if verbose:
+        print('Cropping regions (%d)...' % len(regions))
+    for idx, region in enumerate(regions):
+        bbox = region['bbox']
+        shape = tuple(region['image'].shape[:-1])
+        if verbose:
+            print('Region {} {} predicting...'.format(idx, shape))
+        region = predict_case(region, detail_model, detail_target_spacing, detail_normalize_stats, num_classes,
+                              detail_patch_size, step_per_patch, verbose=verbose, one_hot=True, keep_on_device=True,
+                              **predict_kwargs)
+        src0 = [max(0 - int(bbox[i][0]), 0) for i in range(3)]
+        dst0 = [max(int(bbox[i][0]), 0) for i in range(3)]
+        box = [min(int(bbox[i][1]), orig_shape[i]) - dst0[i] for i in range(3)]
+        ops.region_accumulate(region['pred'], result, result_n, src0, dst0, box)
+    if verbose:
+        print('Merging all regions...')
+    case['pred'] = ops.merge_finalize(result, result_n).cpu().numpy()
     ops.check_device_errors()
     if verbose:
         print('All done!')

@@ -163,3 +163,66 @@ def resample_normalize_case(case: Dict, target_spacing, normalize_stats) -> Dict
     case['affine'] = apply_scale(case['affine'], 1 / scale)
     ops.check_device_errors()
     return case
+
+
+# ------------------------------------------------------------------------------------------------
+# cascade: regions of a coarse prediction (data.py:464-492, transform.py:5-11, 422-437)
+# ------------------------------------------------------------------------------------------------
+def apply_translate(affine, offset):
+    """data.py:68-71 (translation + offset; rotation, zooms and shears unchanged)."""
+    out = np.array(affine, dtype=np.float64, copy=True)
+    out[:3, 3] = out[:3, 3] + np.array(offset)
+    return out
+
+
+def crop_pad_to_bbox(input, bbox, pad_mode='constant', pad_cval=0):
+    """transform.py:422-437 for numpy arrays and CUDA tensors alike: crop to the box, zero-fill what lies outside."""
+    if pad_mode != 'constant':
+        raise NotImplementedError("only constant padding is built")
+    shape = tuple(input.shape)
+    src = tuple(slice(max(0, int(b[0])), min(int(b[1]), shape[d])) for d, b in enumerate(bbox))
+    dst = tuple(slice(max(0, -int(b[0])), max(0, -int(b[0])) + (s.stop - s.start)) for b, s in zip(bbox, src))
+    size = [int(b[1]) - int(b[0]) for b in bbox]
+    if isinstance(input, torch.Tensor):
+        out = torch.full(size, pad_cval, dtype=input.dtype, device=input.device)
+    else:
+        out = np.full(size, pad_cval, dtype=input.dtype)
+    if all(s.stop > s.start for s in src):
+        out[dst] = input[src]
+    return out
+
+
+def component_regions(mask: torch.Tensor, threshold=0):
+    """Connected components (6-connectivity) of a boolean / uint8 CUDA volume with at least ``threshold`` voxels, in
+    scipy.ndimage.label's order: [(voxels, ((x0, x1), (y0, y1), (z0, z1)))] with half-open boxes (find_objects).
+    = remove_small_region + ndi.label + ndi.find_objects (transform.py:5-11, data.py:470-472) in one labelling."""
+    m = (mask > 0).to(torch.uint8).contiguous()
+    _, _, stats = ops.connected_components(m)
+    rows = stats.cpu().numpy()
+    ops.check_device_errors()
+    return [(int(r[0]), ((int(r[1]), int(r[2]) + 1), (int(r[3]), int(r[4]) + 1), (int(r[5]), int(r[6]) + 1)))
+            for r in rows if not r[0] < threshold]
+
+
+def regions_crop_case(case: Dict, threshold=0, padding=20, based_on='label'):
+    """data.py:464-492.  ``case[based_on]`` and ``case['image']`` may be numpy arrays or CUDA tensors; the crops keep the
+    type of what they are cut from."""
+    dev = _device()
+    based = case[based_on]
+    if not isinstance(based, torch.Tensor):
+        based = torch.from_numpy(np.ascontiguousarray(based)).to(dev)
+    comps = component_regions(based, threshold)
+    spacing = np.array(get_spacing(case['affine']))
+    pad = np.round(padding / spacing).astype(int)
+    regions = []
+    for i, (_, box) in enumerate(comps):
+        bbox = np.array([[box[d][0] - pad[d], box[d][1] + pad[d]] for d in range(3)])
+        bbox_c = np.concatenate([bbox, [[0, case['image'].shape[-1]]]])
+        region = {'case_id': '%s_%03d' % (case.get('case_id', 'case'), i),
+                  'affine': apply_translate(case['affine'], bbox[:, 0] * spacing),
+                  'bbox': bbox,
+                  'image': crop_pad_to_bbox(case['image'], bbox_c)}
+        if 'label' in case:
+            region['label'] = crop_pad_to_bbox(case['label'], bbox)
+        regions.append(region)
+    return regions

@@ -322,16 +322,16 @@ def main():
             table = T.normalize_table({"mean": 0.1, "std": 0.9, "pct_00_5": -2.0, "pct_99_5": 2.0})
 
             def kernel_ms(fn, reps=5):
+                # CUDA events recorded immediately around the C-ABI call (ops._Timed), not around the Python wrapper
                 fn()
                 ts = []
                 for _ in range(reps):
                     l2_flush.zero_()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
+                    ops.PROFILE = []
                     fn()
-                    e1.record()
-                    e1.synchronize()
-                    ts.append(e0.elapsed_time(e1))
+                    torch.cuda.synchronize()
+                    ts.append(sum(a.elapsed_time(b) for _, _, a, b, _ in ops.PROFILE))
+                    ops.PROFILE = None
                 return sorted(ts)[len(ts) // 2]
             up = torch.empty(512, 512, 256, 1, device=dev)
             down = torch.empty(512, 512, 128, dtype=torch.uint8, device=dev)

@@ -217,6 +217,24 @@ int unet3d_zoom_label(const uint8_t* in, uint8_t* out, const int in_shape[3], co
                       const int out_shape[3], const long long out_stride[3], void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* Cascade glue (trainer.cascade_predict_case, trainer.py:164-245; data.regions_crop_case, data.py:464-492;
+ * transform.remove_small_region, transform.py:5-11).
+ * unet3d_ccl_label: connected components of a binary uint8 volume (X, Y, Z), 6-connectivity = scipy.ndimage.label's default
+ *   structure.  labels (int32, X*Y*Z): linear index of the component's raster-first voxel, -1 for background; is_root
+ *   (uint8, X*Y*Z, may be NULL): 1 at those first voxels -- their sorted positions number the components like SciPy does.
+ * unet3d_ccl_stats: roots = the sorted root indices (device int32 [n_roots]); stats (device int32 [n_roots][8]) must be
+ *   pre-set to {0, INT_MAX, -1, INT_MAX, -1, INT_MAX, -1, 0} and receives {voxels, xmin, xmax, ymin, ymax, zmin, zmax, 0}
+ *   (np.bincount / scipy.ndimage.find_objects).
+ * unet3d_region_accumulate: result[(dst0 + i)][:] += pred[i][:], count[dst0 + i] += 1 over a box of box_n voxels; result is
+ *   float64 (X, Y, Z, K) channel-last, pred float32 channel-last with ELEMENT strides pstride (x, y, z) (trainer.py:221-222).
+ * unet3d_merge_finalize: mean where count > 0, then argmax (K > 1; NaN counts as the maximum like np.argmax) or round half
+ *   to even (K == 1) -> uint8 (trainer.py:227-239). */
+int unet3d_ccl_label(const uint8_t* mask, int* labels, uint8_t* is_root, int X, int Y, int Z, void* stream);
+int unet3d_ccl_stats(const int* labels, const int* roots, int n_roots, int* stats, int X, int Y, int Z, void* stream);
+int unet3d_region_accumulate(const float* pred, double* result, int* count, int K, const int box_n[3],
+                             const long long pstride[3], const int dst0[3], int Y, int Z, void* stream);
+int unet3d_merge_finalize(const double* result, const int* count, uint8_t* labels, int K, long long n_voxels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

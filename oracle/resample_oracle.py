@@ -149,3 +149,107 @@ def resample_normalize_case(case: Dict, target_spacing, normalize_stats) -> Dict
         case["label"] = rescale(case["label"], scale, is_label=True)
     case["affine"] = apply_scale(case["affine"], 1 / scale)
     return case
+
+
+# --------------------------------------------------------------------------------------
+# cascade: regions of the coarse prediction, per-region detail prediction, merge
+# --------------------------------------------------------------------------------------
+def label_components(mask: np.ndarray):
+    """``scipy.ndimage.label`` with the default structure (6-connectivity in 3-D), restated as a union-find over the
+    raster: components are numbered 1.. in raster order of their first voxel.  Pure numpy/Python: small volumes only."""
+    m = np.asarray(mask).astype(bool)
+    X, Y, Z = m.shape
+    parent = np.arange(m.size, dtype=np.int64)
+
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+
+    flat = m.reshape(-1)
+    for v in np.flatnonzero(flat):
+        x, r = divmod(int(v), Y * Z)
+        y, z = divmod(r, Z)
+        for ok, n in ((x > 0, v - Y * Z), (y > 0, v - Z), (z > 0, v - 1)):
+            if ok and flat[n]:
+                a, b = find(int(v)), find(int(n))
+                if a != b:
+                    parent[max(a, b)] = min(a, b)
+    out = np.zeros(m.size, dtype=np.int32)
+    ids = {}
+    for v in np.flatnonzero(flat):
+        r = find(int(v))
+        if r not in ids:
+            ids[r] = len(ids) + 1          # roots are the raster-first voxels, visited in raster order
+        out[v] = ids[r]
+    return out.reshape(m.shape), len(ids)
+
+
+def remove_small_region(mask: np.ndarray, threshold) -> np.ndarray:
+    """transform.py:5-11."""
+    labels, _ = label_components(mask)
+    areas = np.bincount(labels.ravel())
+    out = np.array(mask, copy=True)
+    out[(areas < threshold)[labels]] = 0
+    return out
+
+
+def crop_pad_to_bbox(a: np.ndarray, bbox) -> np.ndarray:
+    """transform.py:422-437 (constant zero padding)."""
+    shape = a.shape
+    sl = tuple(slice(max(0, int(bbox[d][0])), min(int(bbox[d][1]), shape[d])) for d in range(len(shape)))
+    cropped = a[sl]
+    pad = [[abs(min(0, int(bbox[d][0]))), abs(min(0, shape[d] - int(bbox[d][1])))] for d in range(len(shape))]
+    if any(v > 0 for p in pad for v in p):
+        cropped = np.pad(cropped, pad, "constant", constant_values=0)
+    return cropped.astype(a.dtype)
+
+
+def apply_translate(affine, offset):
+    """data.py:68-71."""
+    T, R, Z, S = decompose(affine)
+    return compose(T + np.array(offset), R, Z, S)
+
+
+def regions_crop_case(case: Dict, threshold=0, padding=20, based_on="label") -> List[Dict]:
+    """data.py:464-492."""
+    based = remove_small_region(case[based_on] > 0, threshold)
+    labels, n = label_components(based)
+    spacing = np.array(get_spacing(case["affine"]))
+    pad = np.round(padding / spacing).astype(int)
+    regions = []
+    for i in range(1, n + 1):
+        idx = np.nonzero(labels == i)
+        bbox = np.array([[idx[d].min() - pad[d], idx[d].max() + 1 + pad[d]] for d in range(3)])
+        bbox_c = np.concatenate([bbox, [[0, case["image"].shape[-1]]]])
+        region = {"case_id": "%s_%03d" % (case.get("case_id", "case"), i - 1),
+                  "affine": apply_translate(case["affine"], bbox[:, 0] * spacing), "bbox": bbox,
+                  "image": crop_pad_to_bbox(case["image"], bbox_c)}
+        if "label" in case:
+            region["label"] = crop_pad_to_bbox(case["label"], bbox)
+        regions.append(region)
+    return regions
+
+
+def merge_regions(orig_shape, num_classes: int, preds) -> np.ndarray:
+    """trainer.py:189-241: ``preds`` = [(bbox, probabilities (rx, ry, rz, C))]; float64 running sums, mean where covered,
+    softmax + argmax (or rounding for one class)."""
+    result = np.zeros(list(orig_shape) + [num_classes])
+    result_n = np.zeros_like(result)
+    for bbox, pred in preds:
+        shape = pred.shape[:3]
+        rs, os_ = [], []
+        for i in range(3):
+            rs.append(slice(max(0 - int(bbox[i][0]), 0), shape[i] - max(int(bbox[i][1]) - orig_shape[i], 0)))
+            os_.append(slice(max(int(bbox[i][0]), 0), min(int(bbox[i][1]), orig_shape[i])))
+        result[tuple(os_)] += pred[tuple(rs)]
+        result_n[tuple(os_)] += 1
+    mask = result_n > 0
+    result[mask] = result[mask] / result_n[mask]
+    if num_classes == 1:
+        result = np.around(np.squeeze(result, axis=-1))
+    else:
+        e = np.exp(result - result.max(axis=-1, keepdims=True))
+        result = np.argmax(e / e.sum(axis=-1, keepdims=True), axis=-1)
+    return result.astype(np.uint8)

@@ -108,6 +108,56 @@ def main():
     out["case_image"], out["case_affine"], out["case_target"] = img, affine, np.array(target)
     out["case_w"], out["case_b"] = toy.weight.detach().numpy(), toy.bias.detach().numpy()
     out["case_labels"], out["case_probs"] = lab, prob
+    # ---- cascade (trainer.py:164-245), live: two bright blobs + a speck; the coarse "model" is a smoothing conv with one
+    # output channel (sigmoid), the detail model the 3-class toy conv above.  Also the regions the reference cuts out of
+    # the coarse prediction (data.regions_crop_case: ndi.label / find_objects / remove_small_region) -- integer work.
+    ref_data.apply_translate.__globals__["compose"], ref_data.apply_translate.__globals__["decompose"] = O.compose, O.decompose
+    rs = np.random.RandomState(21)
+    shape = (40, 36, 20)
+    ax = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+    img = rs.randn(*shape).astype(np.float32) * 20
+    for ctr, rad in (((11, 12, 8), (7, 6, 4)), ((29, 24, 12), (6, 8, 5)), ((35, 5, 3), (1.2, 1.2, 1.2))):
+        d = sum(((a - c) / r) ** 2 for a, c, r in zip(ax, ctr, rad))
+        img[d < 1] += 300
+    img = img[..., None]
+    coarse = torch.nn.Conv3d(1, 1, 3, padding=1)
+    with torch.no_grad():
+        coarse.weight.fill_(1.0 / 27)
+        coarse.bias.fill_(-1.0)
+    detail = toy
+    detail.out_channels = 3
+    c_stats = {"mean": 50.0, "std": 100.0, "pct_00_5": -100.0, "pct_99_5": 400.0}
+    caff = np.diag([1.0, 1.0, 2.0, 1.0])
+    c_target, d_target = (1.6, 1.6, 2.5), (1.0, 1.0, 1.6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ccase = trainer.predict_case({"image": img.copy(), "affine": caff.copy(), "case_id": "c"}, coarse, c_target, c_stats, 1,
+                                     (16, 16, 8), 2, verbose=False)
+        regions = ref_data.regions_crop_case(ccase, 60, 3, "pred")
+        # trainer.cascade_predict_case itself cannot run under numpy >= 1.23 (trainer.py:225-226 index with a LIST of
+        # slices), so its body is followed by hand: live regions, live per-region predict_case, and the merge lines
+        # (trainer.py:189-241) through the oracle's restatement, which differs only in tuple(...) around the slices
+        preds = []
+        for region in regions:
+            r = trainer.predict_case(dict(region), detail, d_target, stats, 3, (16, 24, 16), 2, verbose=False, one_hot=True)
+            preds.append((region["bbox"], r["pred"]))
+        full = {"pred": O.merge_regions(img.shape[:3], 3, preds)}
+    print("cascade: coarse voxels", int(ccase["pred"].sum()), "regions", [r["bbox"].tolist() for r in regions],
+          "labels", np.bincount(full["pred"].ravel()))
+    assert len(regions) == 2
+    out["casc_image"], out["casc_affine"] = img, caff
+    out["casc_coarse_pred"] = ccase["pred"]
+    out["casc_bboxes"] = np.array([r["bbox"] for r in regions])
+    out["casc_region0_image"] = regions[0]["image"]
+    out["casc_region_affines"] = np.array([r["affine"] for r in regions])
+    out["casc_coarse_w"], out["casc_coarse_b"] = coarse.weight.detach().numpy(), coarse.bias.detach().numpy()
+    out["casc_c_stats"] = np.array([c_stats["mean"], c_stats["std"], c_stats["pct_00_5"], c_stats["pct_99_5"]])
+    out["casc_c_target"], out["casc_d_target"] = np.array(c_target), np.array(d_target)
+    out["casc_pred"] = full["pred"]
+    # oracle restatement of the glue, on the reference's own coarse prediction
+    mine = O.regions_crop_case({"image": img, "affine": caff, "pred": ccase["pred"], "case_id": "c"}, 60, 3, "pred")
+    assert len(mine) == 2 and all(np.array_equal(a["bbox"], b["bbox"]) and np.array_equal(a["image"], b["image"])
+                                  and np.allclose(a["affine"], b["affine"]) for a, b in zip(mine, regions))
     np.savez_compressed(os.path.join(HERE, "resample.npz"), **out)
     print("wrote resample.npz:", len(out), "arrays,", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
 

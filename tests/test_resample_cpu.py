@@ -89,3 +89,32 @@ def test_transform_has_no_cpu_path():
         unet3d_b200.rescale(np.zeros((4, 4, 4), np.float32), 2.0)
     with pytest.raises(NotImplementedError):
         unet3d_b200.rescale(np.zeros((4, 4, 4), np.float32), 2.0, order=3)
+
+
+def test_oracle_cascade_glue_against_reference_golden(gold):
+    """data.regions_crop_case restated (label / remove_small_region / find_objects / crop_pad_to_bbox / apply_translate)
+    on the live reference's coarse prediction: boxes, crops and affines as committed by make_golden_resample.py."""
+    case = {"image": gold["casc_image"], "affine": gold["casc_affine"], "pred": gold["casc_coarse_pred"], "case_id": "c"}
+    regions = R.regions_crop_case(case, 60, 3, "pred")
+    assert len(regions) == len(gold["casc_bboxes"]) == 2
+    for r, bbox, aff in zip(regions, gold["casc_bboxes"], gold["casc_region_affines"]):
+        assert np.array_equal(r["bbox"], bbox) and np.allclose(r["affine"], aff)
+    assert np.array_equal(regions[0]["image"], gold["casc_region0_image"])
+    # the speck below the threshold is a component of its own before filtering
+    import scipy.ndimage as ndi
+    lab, n = R.label_components(gold["casc_coarse_pred"] > 0)
+    lab2, n2 = ndi.label(gold["casc_coarse_pred"] > 0)
+    assert n == n2 and np.array_equal(lab, lab2)
+
+
+def test_oracle_merge_regions_semantics():
+    rng = np.random.RandomState(4)
+    preds = [(np.array([[-2, 6], [1, 7], [0, 5]]), rng.rand(8, 6, 5, 3).astype(np.float32)),
+             (np.array([[3, 12], [2, 9], [2, 8]]), rng.rand(9, 7, 6, 3).astype(np.float32))]
+    preds[1][1][0, 0, 0] = np.nan
+    out = R.merge_regions((10, 8, 6), 3, preds)
+    assert out.shape == (10, 8, 6) and out.dtype == np.uint8
+    assert out[9, 0, 0] == 0 and out[3, 2, 2] == 0                     # uncovered -> 0; NaN -> first class
+    assert out[0, 1, 0] == preds[0][1][2, 0, 0].argmax()               # box starts at -2: region voxel 2 lands on voxel 0
+    one = R.merge_regions((10, 8, 6), 1, [(b, p[..., :1]) for b, p in preds])
+    assert set(np.unique(one)) <= {0, 1}

@@ -195,13 +195,14 @@ int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* tab
 int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* stream) {
   return check(channel_sum((const bf16*)x, dsum, NV, Cp, num_sms(), (cudaStream_t)stream), "channel_sum");
 }
-int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, int N, int D, int H, int W, int Cp,
-                    int act_f16, void* stream) {
-  return check(stem_fwd(x, w, b, (bf16*)out, N, D, H, W, Cp, act_f16, num_sms(), (cudaStream_t)stream), "stem_fwd");
+int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, int N, int Cin, int D, int H, int W,
+                    int Cp, int act_f16, void* stream) {
+  return check(stem_fwd(x, w, b, (bf16*)out, N, Cin, D, H, W, Cp, act_f16, num_sms(), (cudaStream_t)stream), "stem_fwd");
 }
-int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, int Cp, int act_f16,
-                      void* stream) {
-  return check(stem_wgrad(x, (const bf16*)dy, dw, N, D, H, W, Cp, act_f16, num_sms(), (cudaStream_t)stream), "stem_wgrad");
+int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, long long x_sample_stride,
+                      int Cp, int act_f16, void* stream) {
+  return check(stem_wgrad(x, (const bf16*)dy, dw, N, D, H, W, x_sample_stride, Cp, act_f16, num_sms(),
+                          (cudaStream_t)stream), "stem_wgrad");
 }
 int unet3d_head_fwd(const void* a, const float* w, const float* b, float* logits, int K, int N, long long V, int Cp,
                     int act_f16, void* stream) {

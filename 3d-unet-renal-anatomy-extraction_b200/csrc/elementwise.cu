@@ -252,15 +252,16 @@ __global__ void channel_sum_kernel(const uint4* __restrict__ x, double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stem: Conv3d(1 -> C, k3, p1) + bias on an fp32 NCDHW (C=1) input, bf16 NDHWC output
-// (network.py:541,550 -- no norm / activation follows).  K = 27: HBM-bound, CUDA cores.
+// Stem: Conv3d(Cin -> C, k3, p1) + bias on an fp32 NCDHW input (Cin = 1 in every reference script), bf16 NDHWC output
+// (network.py:541,550 -- no norm / activation follows).  K = 27 Cin: HBM-bound, CUDA cores.
 // ---------------------------------------------------------------------------------------------
 template <int CP>
-__global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[27][CP]*/,
-                                const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, int N, int D, int H,
-                                int W, int af) {
-  __shared__ float ws[27 * CP + CP];
-  for (int i = threadIdx.x; i < 27 * CP + CP; i += blockDim.x) ws[i] = i < 27 * CP ? w[i] : b[i - 27 * CP];
+__global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cin][27][CP]*/,
+                                const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, int N, int Cin, int D,
+                                int H, int W, int af) {
+  extern __shared__ float ws[];                  // Cin * 27 * CP weights, then CP biases
+  const int nw = Cin * 27 * CP;
+  for (int i = threadIdx.x; i < nw + CP; i += blockDim.x) ws[i] = i < nw ? w[i] : b[i - nw];
   __syncthreads();
   const long long V = (long long)D * H * W, total = (long long)N * V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -269,24 +270,28 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
     const int xw = (int)(v % W), xh = (int)((v / W) % H), xd = (int)(v / ((long long)W * H));
     float acc[CP];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) acc[c] = ws[27 * CP + c];
-    const float* xn = x + (size_t)n * V;
+    for (int c = 0; c < CP; ++c) acc[c] = ws[nw + c];
+#pragma unroll 1
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* xn = x + ((size_t)n * Cin + ci) * V;
+      const float* wc = ws + ci * 27 * CP;
 #pragma unroll
-    for (int kd = 0; kd < 3; ++kd) {
-      const int dd = xd + kd - 1;
-      if (dd < 0 || dd >= D) continue;
+      for (int kd = 0; kd < 3; ++kd) {
+        const int dd = xd + kd - 1;
+        if (dd < 0 || dd >= D) continue;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int hh = xh + kh - 1;
-        if (hh < 0 || hh >= H) continue;
+        for (int kh = 0; kh < 3; ++kh) {
+          const int hh = xh + kh - 1;
+          if (hh < 0 || hh >= H) continue;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int ww = xw + kw - 1;
-          if (ww < 0 || ww >= W) continue;
-          const float xv = __ldg(xn + ((size_t)dd * H + hh) * W + ww);
-          const float* wt = ws + ((kd * 3 + kh) * 3 + kw) * CP;
+          for (int kw = 0; kw < 3; ++kw) {
+            const int ww = xw + kw - 1;
+            if (ww < 0 || ww >= W) continue;
+            const float xv = __ldg(xn + ((size_t)dd * H + hh) * W + ww);
+            const float* wt = wc + ((kd * 3 + kh) * 3 + kw) * CP;
 #pragma unroll
-          for (int c = 0; c < CP; ++c) acc[c] = fmaf(xv, wt[c], acc[c]);
+            for (int c = 0; c < CP; ++c) acc[c] = fmaf(xv, wt[c], acc[c]);
+          }
         }
       }
     }
@@ -306,10 +311,11 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
 // new x values (the 3x3 (kh,kw) window slides along w in registers) and 72 FMAs into register accumulators
 // [9 taps][8 channels] (+ 8 bias sums on the kd == 1 threads).  Block = (CP/8, 3, RUNS); the RUNS partials are
 // reduced in shared memory, then one fp32 atomic per (tap, channel) and block into dw[28][CP].
+// One input channel per launch: x points at that channel of sample 0, x_sN is the sample stride (Cin * D * H * W).
 template <int CP>
 __global__ void __launch_bounds__(CP / 8 * 3 * 16) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
                                                                     float* __restrict__ dw, int N, int D, int H, int W,
-                                                                    int af) {
+                                                                    long long x_sN, int af) {
   constexpr int SEG = 16, RUNS = 16;
   const int ch = threadIdx.x, kd = threadIdx.y, run = threadIdx.z;
   const int segs_w = (W + SEG - 1) / SEG;
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(CP / 8 * 3 * 16) stem_wgrad_kernel(const float
     for (int kh = 0; kh < 3; ++kh) {
       const int xh = h + kh - 1;
       row_ok[kh] = d_ok && xh >= 0 && xh < H;
-      xrow[kh] = x + (size_t)n * D * H * W + ((size_t)(row_ok[kh] ? xd : 0) * H + (row_ok[kh] ? xh : 0)) * W;
+      xrow[kh] = x + (size_t)n * x_sN + ((size_t)(row_ok[kh] ? xd : 0) * H + (row_ok[kh] ? xh : 0)) * W;
     }
     float win[3][3];          // win[kh][kw] = x[.., w + kw - 1]
 #pragma unroll
@@ -1087,27 +1093,29 @@ int channel_sum(const bf16* x, double* dsum, long long NV, int Cp, int num_sms, 
   return U3D_CHECK_LAUNCH();
 }
 
-int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int D, int H, int W, int Cp, int af,
-             int num_sms, cudaStream_t s) {
+int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int Cin, int D, int H, int W, int Cp,
+             int af, int num_sms, cudaStream_t s) {
   const long long total = (long long)N * D * H * W;
   const int g = grid_for(total, 128, num_sms, 16);
-  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
-  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
-  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
-  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, 0, s>>>(x, w, b, out, N, D, H, W, af);
+  const size_t smem = ((size_t)Cin * 27 * Cp + Cp) * sizeof(float);
+  if (Cin < 1 || smem > 48 * 1024) return U3D_ERR_UNSUPPORTED;
+  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af);
+  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af);
+  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af);
+  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af);
   else return U3D_ERR_UNSUPPORTED;
   return U3D_CHECK_LAUNCH();
 }
 
-int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, int Cp, int af, int num_sms,
-               cudaStream_t s) {
+int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, long long x_sN, int Cp, int af,
+               int num_sms, cudaStream_t s) {
   const long long n_runs = (long long)N * D * H * ((W + 15) / 16);
   dim3 blk(Cp / 8, 3, 16);
   const int g = grid_for(n_runs, 16 * 4, num_sms, 4);
-  if (Cp == 32) stem_wgrad_kernel<32><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
-  else if (Cp == 16) stem_wgrad_kernel<16><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
-  else if (Cp == 48) stem_wgrad_kernel<48><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
-  else if (Cp == 64) stem_wgrad_kernel<64><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, af);
+  if (Cp == 32) stem_wgrad_kernel<32><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, x_sN, af);
+  else if (Cp == 16) stem_wgrad_kernel<16><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, x_sN, af);
+  else if (Cp == 48) stem_wgrad_kernel<48><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, x_sN, af);
+  else if (Cp == 64) stem_wgrad_kernel<64><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, x_sN, af);
   else return U3D_ERR_UNSUPPORTED;
   return U3D_CHECK_LAUNCH();
 }

@@ -13,10 +13,10 @@ int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf
 int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, const double* sums, const float* coef,
                  double* dsum, int N, int D, int H, int W, int Cp, int zero_last, int af, int num_sms, cudaStream_t s);
 int channel_sum(const bf16* x, double* dsum, long long NV, int Cp, int num_sms, cudaStream_t s);
-int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int D, int H, int W, int Cp, int af,
-             int num_sms, cudaStream_t s);
-int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, int Cp, int af, int num_sms,
-               cudaStream_t s);
+int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int Cin, int D, int H, int W, int Cp,
+             int af, int num_sms, cudaStream_t s);
+int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, long long x_sN, int Cp, int af,
+               int num_sms, cudaStream_t s);
 int head_fwd(const bf16* a, const float* w, const float* b, float* logits, int K, int N, long long V, int Cp, int af,
              int num_sms, cudaStream_t s);
 int head_bwd(const float* dl, const bf16* a, const float* w, bf16* da, float* dw, const float* gscale, int K, int N,

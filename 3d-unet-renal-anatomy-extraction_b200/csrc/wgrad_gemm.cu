@@ -38,6 +38,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
   const int sw_word = jt[7];
   const int wx = sw_word & 0xff, wy = (sw_word >> 8) & 0xff, nbx = (sw_word >> 16) & 0xff, nby = (sw_word >> 24) & 0xff;
   const bool sw = wx != 0;
+  // pair mode (16-byte-row layout only): two consecutive dy planes side by side in N (plan.py), so an MMA is N = 2*Gy*8
+  // wide and the plane loop advances by two; taps kd = row plane - column plane are sorted out by the epilogue offsets
+  const int npl = (sw_word >> 30) & 1 ? 2 : 1;
   const uint32_t rbx = 16u * wx, rby = 16u * wy;                                   // row bytes
   const uint32_t x_box_bytes = (uint32_t)CG_HB * CG_WB * rbx, y_box_bytes = (uint32_t)CG_HT * CG_WT * rby;
   const uint32_t x_pitch = sw ? (x_box_bytes + 8 * rbx - 1) / (8 * rbx) * (8 * rbx) : 0u, y_pitch = y_box_bytes;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
     // The whole issuing role runs in ONE elected thread, barrier waits included (no elect.sync / __syncwarp between
     // entries): a warp-level step between MMAs lets the shallow tcgen05 queue drain (measured on the conv kernel).
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, Gy * 8, 1, 1, p.x_f16, p.x_f16);
+      const uint32_t idesc = umma_idesc_bf16(128, Gy * 8 * npl, 1, 1, p.x_f16, p.x_f16);
       // one K step = 16 voxels = two 8-voxel lines of the brick / of the dy tile.  The two layouts get separate loops so
       // that the 16-byte-row one keeps compile-time descriptor increments (its layers are bound by the MMA issue rate).
       const uint64_t a_kinc_sw = (uint64_t)((2 * CG_WB * rbx) >> 4), b_kinc_sw = (uint64_t)((2 * CG_WT * rby) >> 4);
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
             uint64_t a = umma_desc(xs + ent_aoff[e], CG_WB * 16, CG_CHUNK_PITCH);
             uint64_t b = b0;
             const uint32_t acc = tmem_base + ent_col[e];
-            for (int d = 0; d < Dt; ++d, a += a_dinc, b += b_dinc) {
+            for (int d = 0; d < Dt; d += npl, a += npl * a_dinc, b += npl * b_dinc) {
               tc_mma_bf16(acc, a, b, idesc, (it == 0 && d == 0) ? 0u : 1u);
 #pragma unroll
               for (int k = 1; k < 8; ++k) tc_mma_bf16(acc, a + k * a_kinc, b + k * b_kinc, idesc, 1u);
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
     const int row = q * 32 + lane;
     if (mbar_wait(smem_u32(&ctl->acc_full), 0, abort_flag, p.err, 203)) {
       tc_fence_after();
-      const int n_cc = Gy / 4;
+      const int n_cc = Gy * npl / 4;
       for (int e = 0; e < n_ent; ++e) {
         const int* ent = jt + WG_J_ENT + e * WG_E_SIZE;
         const int col = __ldg(&ent[WG_E_COL]);

@@ -86,8 +86,8 @@ class UNetEngine:
             raise RuntimeError("unet3d_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
         if x.dim() != 5 or x.shape[1] != net.conv.in_channels:
             raise RuntimeError(f"expected input (N, {net.conv.in_channels}, D, H, W), got {tuple(x.shape)}")
-        if net.conv.in_channels != 1:
-            raise RuntimeError("the stem kernel covers in_channels == 1 (every reference script uses 1)")
+        if net.conv.in_channels * 27 * P.pad_channels(net.conv.out_channels) * 4 > 44 * 1024:
+            raise RuntimeError("the stem kernel keeps all Cin x 27 x C weights in shared memory: in_channels too large")
         np_ = net.num_pool
         D, H, W = x.shape[2:]
         if D % (1 << np_) or H % (1 << np_) or W % (1 << np_):
@@ -181,8 +181,19 @@ class UNetEngine:
         train = self.owner.training or not norm.track_running_stats
         cnt = float(n * count)
         if train:
-            mean = (m * stats[..., 0]).sum(0) / cnt
-            var = ((m * m * stats[..., 1]).sum(0) / cnt - mean * mean).clamp_min(0.0)
+            s0, s1 = (m * stats[..., 0]).sum(0), (m * m * stats[..., 1]).sum(0)
+            if getattr(self.net, "sync_bn", False):      # parallel.enable_sync_batchnorm
+                # SyncBN: the 2 Cp per-channel sums of every rank are added (one small all-reduce per norm application);
+                # every rank contributes the same number of samples, so the count is just multiplied
+                from . import parallel
+                world = parallel.rank_world()[1]
+                if world > 1:
+                    both = torch.stack([s0, s1])
+                    parallel.all_reduce_sum([both])
+                    s0, s1 = both[0], both[1]
+                    cnt *= world
+            mean = s0 / cnt
+            var = (s1 / cnt - mean * mean).clamp_min(0.0)
             if norm.track_running_stats and self.owner.training:
                 with torch.no_grad():
                     norm.num_batches_tracked += 1
@@ -216,7 +227,16 @@ class UNetEngine:
         s1, s2 = sums[..., 0].sum(0), sums[..., 1].sum(0)
         a = m * (gamma * r)
         if bn["train"]:
-            g1, g2 = s1 / bn["cnt"], s2 / bn["cnt"]
+            t1, t2 = s1, s2
+            if getattr(self.net, "sync_bn", False):
+                # the batch statistics couple the ranks: mean(g), mean(g x_hat) run over all ranks' samples (bn["cnt"] is
+                # already the global count); d gamma / d beta below stay local -- the gradient all-reduce adds them
+                from . import parallel
+                if parallel.rank_world()[1] > 1:
+                    both = torch.stack([s1, s2])
+                    parallel.all_reduce_sum([both])
+                    t1, t2 = both[0], both[1]
+            g1, g2 = t1 / bn["cnt"], t2 / bn["cnt"]
             b = -a * g2 * (m * r)
             cc = a * (-g1 + mean * r * g2)
         else:
@@ -314,8 +334,8 @@ class UNetEngine:
             self._g_total = goff
             for wp, n_param in self._dw_order:
                 o, g = self._dw_slots[id(wp)]
-                jobs.append(dict(dw=self._dw_arena[o:o + wp.plan.dw_numel], rowmap=wp.rowmap, out=4 * g,
-                                 **{k: v for k, v in wp.plan.unpack.items() if k != "rowmap"}))
+                jobs.append(dict(dw=self._dw_arena[o + wp.plan.unpack["origin"]:o + wp.plan.dw_numel], rowmap=wp.rowmap,
+                                 out=4 * g, **{k: v for k, v in wp.plan.unpack.items() if k not in ("rowmap", "origin")}))
             self._dw_table = ops.UnpackTable(jobs, self.device)
             self._dw_table_n = len(self._dw_order)
             # two-chunk variant for the overlapped all-reduce: split where the cumulative gradient bytes pass 60 %
@@ -546,8 +566,9 @@ class UNetEngine:
         tape = {}
         c0 = net.conv.out_channels
         cp0 = P.pad_channels(c0)
-        w0 = torch.zeros(27, cp0, device=self.device)                  # stem weights as [27][Cp] fp32 (+ bias [Cp])
-        w0[:, :c0] = net.conv.weight.detach().reshape(c0, 27).t()
+        cin = net.conv.in_channels
+        w0 = torch.zeros(cin, 27, cp0, device=self.device)             # stem weights as [Cin][27][Cp] fp32 (+ bias [Cp])
+        w0[:, :, :c0] = net.conv.weight.detach().reshape(c0, cin, 27).permute(1, 2, 0)
         b0 = torch.zeros(cp0, device=self.device)
         b0[:c0] = net.conv.bias.detach()
         cur = self._new_act(N, dims[0], c0)
@@ -698,11 +719,11 @@ class UNetEngine:
             d_cur = self._block_bwd(net.encode_blocks[i], ("enc", i), tape[("enc", i)], d_cur, pending[i], grads)[0]
         c0 = net.conv.out_channels
         cp0 = d_cur.shape[-1]
-        dw0 = torch.zeros(28 * cp0, device=self.device)
+        cin = net.conv.in_channels
+        dw0 = torch.zeros(cin, 28, cp0, device=self.device)
         ops.stem_wgrad(tape["x"], d_cur, dw0)
-        dw0 = dw0.view(28, cp0)
-        grads[net.conv.weight] = self._unscale(dw0[:27, :c0].t().reshape(net.conv.weight.shape))
-        grads[net.conv.bias] = self._unscale(dw0[27, :c0].clone())
+        grads[net.conv.weight] = self._unscale(dw0[:, :27, :c0].permute(2, 0, 1).reshape(net.conv.weight.shape))
+        grads[net.conv.bias] = self._unscale(dw0[0, 27, :c0].clone())
         self._finish_wgrads()
         self._inv_scale = None
         return grads

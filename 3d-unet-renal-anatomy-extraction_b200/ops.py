@@ -407,19 +407,27 @@ def maxpool_flat_index(code: torch.Tensor, c: int) -> torch.Tensor:
 
 
 def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
+    """x fp32 (N, Cin, D, H, W) contiguous; w fp32 [Cin][27][Cp]; b fp32 [Cp]; out 16-bit (N, D, H, W, Cp)."""
     n, d, h, ww, cp = out.shape
+    cin = x.shape[1]
+    assert x.is_contiguous() and w.numel() == cin * 27 * cp
     _count()
     with _Timed("stem_fwd", 0.0, x.numel() * 4.0 + out.numel() * 2.0):
-        _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, d, h, ww, cp,
+        _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, cin, d, h, ww, cp,
                                               _f16(out), _stream()), "unet3d_stem_fwd")
 
 
 def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
+    """dw fp32 [Cin][28][Cp] (zeroed by the caller): per input channel its 27 taps and the bias row."""
     n, d, h, ww, cp = dy.shape
-    _count()
-    with _Timed("stem_wgrad", 0.0, x.numel() * 4.0 + dy.numel() * 2.0):
-        _lib.check(_lib.lib().unet3d_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), n, d, h, ww, cp, _f16(dy),
-                                                _stream()), "unet3d_stem_wgrad")
+    cin = x.shape[1]
+    assert x.is_contiguous() and dw.numel() == cin * 28 * cp
+    vol = d * h * ww
+    for ci in range(cin):
+        _count()
+        with _Timed("stem_wgrad", 0.0, x.numel() / cin * 4.0 + dy.numel() * 2.0):
+            _lib.check(_lib.lib().unet3d_stem_wgrad(x.data_ptr() + 4 * ci * vol, dy.data_ptr(), dw.data_ptr() + 4 * ci * 28 * cp,
+                                                    n, d, h, ww, cin * vol, cp, _f16(dy), _stream()), "unet3d_stem_wgrad")
 
 
 def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Tensor):

@@ -119,3 +119,15 @@ def all_reduce_gradients(model: torch.nn.Module, average: bool = True):
             n = p.grad.numel()
             p.grad.copy_(flat[off:off + n].view_as(p.grad))
             off += n
+
+
+def enable_sync_batchnorm(model: torch.nn.Module, enabled: bool = True):
+    """BatchNorm3d variant (ResAttrBNUnet3D, network.py:38-69) under data parallelism: normalise with the statistics of
+    the GLOBAL batch (what torch.nn.SyncBatchNorm does around the reference) instead of every rank's own shard.  Each
+    norm application then adds one all-reduce of 2 x C float64 sums in the forward pass and one in the backward pass;
+    with ``DiceLoss(global_batch=True)`` and summed gradients the result is exactly the single-process gradient on
+    the concatenated batch (tools/check_multi_gpu.py).  Every rank must hold the same number of samples.  The
+    all-reduces are issued from Python between kernel launches, so this mode does not combine with GraphedTrainStep."""
+    net = model.net if hasattr(model, "net") else model
+    net.sync_bn = bool(enabled)            # read by the engine at every BatchNorm application
+    return model

@@ -250,7 +250,7 @@ def _kidx_and_valid(plan_kind: str, ks: int, stride: int, pattern: str, shift, p
 
 
 _PLAN_CACHE: Dict[tuple, object] = {}
-_TUNING_ENV = ("U3D_CONV_CFG", "U3D_A_STAGES", "U3D_WG_WAVES", "U3D_WG_NOSW", "U3D_WG_FORCESW")
+_TUNING_ENV = ("U3D_CONV_CFG", "U3D_A_STAGES", "U3D_WG_WAVES", "U3D_WG_NOSW", "U3D_WG_FORCESW", "U3D_WG_PAIR")
 
 
 def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: Sequence[int], depth: int,
@@ -548,6 +548,7 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
     Kp, Np = int(sum(x_Cp)), y_Cp
     ld = Np
     dw_numel = k3 * Kp * Np
+    dw_origin = 0
 
     if ks == 1:
         d_shifts, hw_shifts = [1], [(1, 1)]
@@ -594,11 +595,35 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
         planes_extra = span
     y_blocks = [(y0, min(16, len(YL) - y0)) for y0 in range(0, len(YL), 16)]
 
+    # ---- pair mode (16/32-channel 3x3x3 layers on the 16-byte-row layout): an M = 128, K = 16 MMA costs max(N/2, ~50)
+    # cycles, so N = 32 runs at a third of the tensor peak.  Two consecutive dy planes side by side make N = 64 at the
+    # same cost per MMA: row block i (x plane d-1+i) against column block j (dy plane d+j) is tap kd = i - j.  The four
+    # row blocks x two column blocks hold kd = -1..3; -1 and 3 land in two scratch slots in front of / behind the 27 real
+    # taps (dw_origin), everything else accumulates where the single-plane layout puts it.  Twice the TMEM columns per
+    # (kh,kw) entry, so the nine entries split over two jobs (5 + 4) that read the same tiles at the same time.
+    pair = False       # decided below, once box_width exists
+
+    def group_ok(lst, w, exact):
+        if exact and len(lst) % w:
+            return False
+        for i in range(0, len(lst), w):
+            grp = lst[i:i + w]
+            if any(c["map"] != grp[0]["map"] or c["ch"] != grp[0]["ch"] + 8 * k for k, c in enumerate(grp)):
+                return False
+        return True
+
+    pair = (case_a and D_ >= 2 and len(YL) <= 4 and len(XL) <= 8 and not (len(XL) == 8 and group_ok(XL, 8, True))
+            and not os.environ.get("U3D_WG_FORCESW") and os.environ.get("U3D_WG_PAIR", "0") == "1")
+
+    if pair:
+        dw_origin = 9 * Kp * Np                  # scratch slot for kd = -1 in front, one for kd = 3 behind
+        dw_numel = 45 * Kp * Np
+
     jobs = []
     p0_values = sorted(set(u[0] for u in units))
     for (y0, ycnt) in y_blocks:
         gy = -(-ycnt // 4) * 4
-        max_ent = min(512 // (gy * 8), WG_ENT_MAX)
+        max_ent = min(512 // (gy * 8 * (2 if pair else 1)), WG_ENT_MAX)
         for (m0, gx) in m_blocks:
             for p0 in p0_values:          # one job never spans plane groups: keeps the x stage small
                 us = [u for u in units if u[0] == p0]
@@ -637,7 +662,7 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
     wy = box_width(yls, False)
     if os.environ.get("U3D_WG_NOSW"):
         wx = wy = 1
-    use_sw = wx > 1 and wy > 1
+    use_sw = wx > 1 and wy > 1 and not pair
     if case_a and wx < 8 and not os.environ.get("U3D_WG_FORCESW"):
         # 16/32-channel 3x3x3 layers are bound by the tensor core's shared-memory operand reads, not by the loads, and a
         # 32/64-byte MN-major row fills only part of a 128-byte read wavefront: measured 0.436 vs 0.412 ms (30->30) and
@@ -659,15 +684,15 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
             x_plane, y_plane = gx * CHUNK_PITCH, gy * WG_DY_BOX
         dt = None
         for cand in _WG_DT_CANDIDATES:
-            if cand > max(1, D_):
+            if cand > max(1, D_) + (D_ % 2 if pair else 0) or (pair and cand % 2):
                 continue
-            px = cand - 1 + planes_extra
+            px = cand - (2 if pair else 1) + planes_extra
             if 2048 + 2 * (px * x_plane + cand * y_plane) + margin <= SMEM_LIMIT:
                 dt = cand
                 break
         if dt is None:
             raise ValueError("wgrad stage does not fit shared memory")
-        px = dt - 1 + planes_extra
+        px = dt - (2 if pair else 1) + planes_extra
         j["dt"], j["px"] = dt, px
         row = tab[ji]
         row[0:7] = [dt, px, min_sd - 1 + j["p0"], gx, gy, len(j["units"]), ld]
@@ -682,6 +707,8 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
                 c = YL[j["y0"] + b * wy] if b * wy < j["ycnt"] else YL[j["y0"]]
                 row[WG_J_YLIST + 2 * b], row[WG_J_YLIST + 2 * b + 1] = c["map"], c["ch"]
         else:
+            if pair:
+                row[7] = 1 << 30          # wx = 0 (16-byte rows) + pair flag
             for i, c in enumerate(xl):
                 row[WG_J_XLIST + 2 * i], row[WG_J_XLIST + 2 * i + 1] = c["map"], c["ch"]
             for i, c in enumerate(yl):
@@ -691,8 +718,18 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
             ent = row[WG_J_ENT + e * WG_E_SIZE: WG_J_ENT + (e + 1) * WG_E_SIZE]
             ent[0] = (sh * (WT + 2) + sw) * 16
             ent[1] = col
-            col += gy * 8
+            col += gy * 8 * (2 if pair else 1)
             ent[2:] = -1
+            if pair:
+                # rows: x plane shift sd = 0..3 (3 pairs only with the second dy plane); columns: (dy plane j, chunk h)
+                for s in range(16):
+                    sd = p0 + s // gx
+                    if 0 <= sd <= 3:
+                        ent[2 + s] = (((sd * 3 + sh) * 3 + sw) * Kp + xl[s % gx]["k0"]) * ld
+                for jp in (0, 1):
+                    for h in range(j["ycnt"]):
+                        ent[18 + jp * gy + h] = dw_origin + yl[h]["n0"] - jp * 9 * Kp * ld
+                continue
             for s in range(16):
                 plane_rel = p0 + s // gx if case_a else p0
                 if not case_a and s >= gx:
@@ -727,10 +764,11 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
         co, ci, kf = np.meshgrid(np.arange(Ntot), np.arange(Ktot), np.arange(k3), indexing="ij")
     else:                   # Wt[cin][cout][k]
         ci, co, kf = np.meshgrid(np.arange(Ktot), np.arange(Ntot), np.arange(k3), indexing="ij")
-    gidx = (kf * Kp + kreal[ci]) * Np + co
+    gidx = dw_origin + (kf * Kp + kreal[ci]) * Np + co
     rowmap = np.full(Kp, -1, np.int32)
     rowmap[kreal] = np.arange(Ktot) * (k3 if kind == "conv" else Ntot * k3)
-    unpack = dict(k3=k3, Kp=Kp, Np=Np, ncols=Ntot, col_stride=Ktot * k3 if kind == "conv" else k3, rowmap=rowmap)
+    unpack = dict(k3=k3, Kp=Kp, Np=Np, ncols=Ntot, col_stride=Ktot * k3 if kind == "conv" else k3, rowmap=rowmap,
+                  origin=dw_origin)
     n_tiles_min = N_ * (-(-max(1, D_) // 8)) * (-(-H_ // HT)) * (-(-W_ // WT))
     n_tiles_max = N_ * max(1, D_) * (-(-H_ // HT)) * (-(-W_ // WT))
     # CTAs = jobs x split, one CTA per SM at a time (227 KB of shared memory): never spill a few CTAs into an extra

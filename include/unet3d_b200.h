@@ -152,12 +152,14 @@ int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* tab
                         void* stream);
 int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* stream);
 
-/* Stem Conv3d(1->C,k3,p1)+bias, fp32 NCDHW in -> bf16 NDHWC out (network.py:541,550) and its
- * weight/bias gradient (dw fp32 [28][Cp]: 27 taps then the bias row; accumulated atomically). */
-int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, int N, int D, int H, int W, int Cp,
-                    int act_f16, void* stream);
-int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, int Cp, int act_f16,
-                      void* stream);
+/* Stem Conv3d(Cin->C,k3,p1)+bias, fp32 NCDHW in -> bf16 NDHWC out (network.py:541,550); w fp32 [Cin][27][Cp].
+ * Weight/bias gradient ONE INPUT CHANNEL per call: x points at that channel of sample 0, x_sample_stride = Cin*D*H*W
+ * elements; dw fp32 [28][Cp]: that channel's 27 taps, then the bias row (the same for every channel); accumulated
+ * atomically. */
+int unet3d_stem_fwd(const float* x, const float* w, const float* b, void* out, int N, int Cin, int D, int H, int W,
+                    int Cp, int act_f16, void* stream);
+int unet3d_stem_wgrad(const float* x, const void* dy, float* dw, int N, int D, int H, int W, long long x_sample_stride,
+                      int Cp, int act_f16, void* stream);
 
 /* Head Conv3d(C->K,k1)+bias, bf16 NDHWC in -> fp32 NCDHW logits (network.py:545-547,563), and backward
  * (da bf16 NDHWC; dw fp32 [K][Cp] followed by [K] bias grads, accumulated atomically). */

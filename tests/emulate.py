@@ -90,7 +90,7 @@ def run_wgrad_plan(plan, xs, dy, grid):
 
     def shifted(v, ch, sd, sh, sw):
         # brick shift s <-> view index o + s - 1, zero outside (TMA OOB fill); result on the tile grid
-        vp = torch.zeros(N, D + 2, H + 2, W + 2, 8, dtype=torch.float64)
+        vp = torch.zeros(N, D + 3, H + 2, W + 2, 8, dtype=torch.float64)      # pair mode shifts by up to 3 planes
         d1, h1, w1 = min(v.shape[1], D + 1), min(v.shape[2], H + 1), min(v.shape[3], W + 1)
         if ch < v.shape[-1]:           # channels past the tensor are TMA out-of-bounds zeros (partial boxes)
             vp[:, 1:1 + d1, 1:1 + h1, 1:1 + w1] = v[:, :d1, :h1, :w1, ch:ch + 8]
@@ -102,6 +102,7 @@ def run_wgrad_plan(plan, xs, dy, grid):
         dt, px, xd0, gx, gy, n_ent, ld = (int(v) for v in row[0:7])
         sw_word = int(row[7])
         wx, wy, nbx, nby = sw_word & 0xff, (sw_word >> 8) & 0xff, (sw_word >> 16) & 0xff, (sw_word >> 24) & 0xff
+        pair = (sw_word >> 30) & 1       # two dy planes side by side in N: column group = (plane j, chunk h)
         if wx:      # swizzled whole-row boxes: the lists hold one (map, first channel) per box of wx / wy chunks
             bx = [(int(row[P.WG_J_XLIST + 2 * b]), int(row[P.WG_J_XLIST + 2 * b + 1])) for b in range(nbx)]
             by = [(int(row[P.WG_J_YLIST + 2 * b]), int(row[P.WG_J_YLIST + 2 * b + 1])) for b in range(nby)]
@@ -127,17 +128,25 @@ def run_wgrad_plan(plan, xs, dy, grid):
                 sd = xd0 + 1 + plane_rel
                 mx, chx = xl[ci]
                 a = shifted(view(*maps[mx]), chx, sd, sh, sw)              # (N, D, H, W, 8)
-                for h in range(gy):
-                    co = int(ent[18 + h])
+                for hh in range(gy * (2 if pair else 1)):
+                    co = int(ent[18 + hh])
                     if co < 0:
                         continue
+                    jp, h = divmod(hh, gy)
                     my, chy = yl[h]
                     vy = view(*maps[my])
-                    b = torch.zeros(N, D, H, W, 8, dtype=torch.float64)
+                    b = torch.zeros(N, D + 2, H, W, 8, dtype=torch.float64)
                     d1, h1, w1 = min(vy.shape[1], D), min(vy.shape[2], H), min(vy.shape[3], W)
                     if chy < vy.shape[-1]:
                         b[:, :d1, :h1, :w1] = vy[:, :d1, :h1, :w1, chy:chy + 8]
-                    blk = torch.einsum("bdhwr,bdhwc->rc", a, b)
+                    if pair:       # the MMA of dy planes (d, d+1), d even: x plane d + shift against dy plane d + jp
+                        assert dt % 2 == 0
+                        n_pairs = (D + 1) // 2
+                        a_use = torch.zeros(N, 2 * n_pairs, H, W, 8, dtype=torch.float64)
+                        a_use[:, :D] = a
+                        blk = torch.einsum("bdhwr,bdhwc->rc", a_use[:, 0::2], b[:, jp:jp + 2 * n_pairs:2])
+                    else:
+                        blk = torch.einsum("bdhwr,bdhwc->rc", a, b[:, :D])
                     for r in range(8):
                         dw[ro + r * ld + co: ro + r * ld + co + 8] += blk[r]
     return dw

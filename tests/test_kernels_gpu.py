@@ -234,26 +234,26 @@ def test_instance_norm_fwd_bwd():
     assert rel(from_ndhwc(dy, C), y.grad) < 2e-2
 
 
-def test_stem_and_head():
+@pytest.mark.parametrize("cin", [1, 2, 3])
+def test_stem_and_head(cin):
     torch.manual_seed(4)
     N, D, H, W, C, K = 2, 6, 10, 12, 30, 3
-    x = torch.randn(N, 1, D, H, W, device=DEV)
-    w = (torch.randn(C, 1, 3, 3, 3, device=DEV) * 0.3).requires_grad_(True)
+    x = torch.randn(N, cin, D, H, W, device=DEV)
+    w = (torch.randn(C, cin, 3, 3, 3, device=DEV) * 0.3).requires_grad_(True)
     b = torch.randn(C, device=DEV).requires_grad_(True)
     y = F.conv3d(x, w, b, padding=1)
     cp = P.pad_channels(C)
-    w0 = torch.zeros(27, cp, device=DEV); w0[:, :C] = w.detach().reshape(C, 27).t()
+    w0 = torch.zeros(cin, 27, cp, device=DEV); w0[:, :, :C] = w.detach().reshape(C, cin, 27).permute(1, 2, 0)
     b0 = torch.zeros(cp, device=DEV); b0[:C] = b.detach()
     out = torch.empty(N, D, H, W, cp, device=DEV, dtype=torch.bfloat16)
     ops.stem_fwd(x.contiguous(), w0, b0, out)
     assert rel(from_ndhwc(out, C), y.detach()) < 4e-3
     dy = bf(torch.randn_like(y))
     y.backward(dy)
-    dw0 = torch.zeros(28 * cp, device=DEV)
+    dw0 = torch.zeros(cin, 28, cp, device=DEV)
     ops.stem_wgrad(x.contiguous(), to_ndhwc(dy), dw0)
-    dw0 = dw0.view(28, cp)
-    assert rel(dw0[:27, :C].t().reshape(w.shape), w.grad) < 1e-3
-    assert rel(dw0[27, :C], b.grad) < 1e-3
+    assert rel(dw0[:, :27, :C].permute(2, 0, 1).reshape(w.shape), w.grad) < 1e-3
+    assert rel(dw0[0, 27, :C], b.grad) < 1e-3
     # head
     a = bf(torch.randn(N, C, D, H, W, device=DEV)).requires_grad_(True)
     wf = (torch.randn(K, C, 1, 1, 1, device=DEV) * 0.3).requires_grad_(True)

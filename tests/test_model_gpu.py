@@ -29,7 +29,7 @@ def rel(a, b):
 
 def _run(num_pool, nf, shape, seed=0, train=False, loss_kind="hybrid", precision="bf16"):
     torch.manual_seed(seed)
-    model = unet3d_b200.ResUnet3D(num_pool=num_pool, num_features=nf, out_channels=3)
+    model = unet3d_b200.ResUnet3D(num_pool=num_pool, num_features=nf, in_channels=shape[1], out_channels=3)
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(*shape, generator=g)
@@ -123,6 +123,12 @@ def test_shallow_net_grads_tight(precision):
     """One pooling level (3 residual blocks + transposed conv): every backward kernel is on the path, few enough
     layers that mask flips do not pile up."""
     print(_check(*_run(1, 16, (2, 1, 16, 16, 16), precision=precision)))
+
+
+def test_multi_channel_input():
+    """in_channels = 2 (network.py:105-109 constructor argument; every reference script passes 1): stem forward and the
+    per-channel stem weight gradient."""
+    print(_check(*_run(1, 16, (2, 2, 16, 16, 16), precision="fp16")))
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)

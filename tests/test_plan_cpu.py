@@ -93,12 +93,13 @@ def test_convT_fwd_and_dgrad(cin, cout):
 from tests.emulate import run_wgrad_plan
 
 
-@pytest.mark.parametrize("kind,ks,stride,cins,cout", [
+@pytest.mark.parametrize("kind,ks,stride,cins,cout,D", [p if len(p) == 6 else p + (2,) for p in [
     ("conv", 3, 1, [30], 30), ("conv", 3, 1, [30, 30], 30), ("conv", 1, 1, [60, 60], 60), ("conv", 3, 1, [120], 24),
     ("conv", 3, 1, [136], 8), ("conv", 3, 2, [30], 60), ("conv", 1, 2, [30], 60), ("conv", 3, 1, [8], 8),
-    ("conv", 3, 1, [40], 20), ("convT", 3, 2, [60], 30), ("convT", 3, 2, [24], 8)])
-def test_wgrad_plans(kind, ks, stride, cins, cout):
-    N, D, H, W = 1, 2, 3, 4
+    ("conv", 3, 1, [40], 20), ("convT", 3, 2, [60], 30), ("convT", 3, 2, [24], 8),
+    ("conv", 3, 1, [30], 30, 5), ("conv", 3, 1, [30, 30], 30, 3), ("conv", 3, 1, [12], 30, 4), ("conv", 3, 1, [30], 16, 1)]])
+def test_wgrad_plans(kind, ks, stride, cins, cout, D):
+    N, H, W = 1, 3, 4
     g = torch.Generator().manual_seed(5)
     if kind == "conv":
         fd = (D * stride, H * stride, W * stride)
@@ -131,7 +132,8 @@ def test_wgrad_plans(kind, ks, stride, cins, cout):
     ok = (u["rowmap"][row] >= 0) & (col < u["ncols"])
     dest = u["rowmap"][row].astype(np.int64) + tap + col * u["col_stride"]
     out = np.full(w.numel(), np.nan, dw.numpy().dtype)
-    out[dest[ok]] = dw[:plan.dw_numel].numpy().reshape(tap.shape)[ok]
+    o0 = u["origin"]                     # pair-mode plans keep a scratch tap slot in front of the 27 real ones
+    out[dest[ok]] = dw[o0:o0 + tap.size].numpy().reshape(tap.shape)[ok]
     assert ok.sum() == w.numel() and np.array_equal(out, dw[torch.from_numpy(plan.gidx)].numpy())
 
 
@@ -157,3 +159,24 @@ def test_block_input_gradient_in_one_launch(cins, cout, stride):
     for o, c in zip(outs, cins):
         assert torch.allclose(from_ndhwc(o, c), x.grad[:, off:off + c], atol=1e-4, rtol=1e-4)
         off += c
+
+
+@pytest.mark.parametrize("cins,cout,D", [([30], 30, 2), ([30], 30, 5), ([30, 30], 30, 3), ([12], 30, 4), ([8], 16, 6)])
+def test_wgrad_pair_mode_plans(cins, cout, D, monkeypatch):
+    """U3D_WG_PAIR=1 (tuning switch, off by default: measured slower, profiles/r01_notes.md): two dy planes side by side
+    in N, taps kd = -1 and 3 in scratch slots around the 27 real ones."""
+    monkeypatch.setenv("U3D_WG_PAIR", "1")
+    N, H, W = 1, 3, 4
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, sum(cins), D, H, W, generator=g)
+    w = (torch.randn(cout, sum(cins), 3, 3, 3, generator=g) * 0.1).requires_grad_(True)
+    dy = torch.randn(N, cout, D, H, W, generator=g)
+    F.conv3d(x, w, None, padding=1).backward(dy)
+    xs, off = [], 0
+    for c in cins:
+        xs.append(to_ndhwc(x[:, off:off + c], P.pad_channels(c))); off += c
+    plan = P.make_wgrad_plan("conv", 3, 1, cins, cout, (N, D, H, W))
+    assert plan.unpack["origin"] > 0 and (int(plan.tab.reshape(plan.n_jobs, -1)[0][7]) >> 30) & 1
+    dw = run_wgrad_plan(plan, xs, to_ndhwc(dy, P.pad_channels(cout)), (N, D, H, W))
+    got = dw[torch.from_numpy(plan.gidx)].reshape(w.shape).float()
+    assert torch.allclose(got, w.grad, atol=1e-3, rtol=1e-3)

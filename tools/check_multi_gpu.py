@@ -53,6 +53,32 @@ for name, glob in (("local-dice / averaged", False), ("global-dice / summed", Tr
     if rank == 0:
         print(f"{name}: worst per-tensor rel-L2 vs the single-process reference {worst:.2e}")
     ok = ok and worst < 2e-2
+# BatchNorm variant: SyncBN (statistics of the global batch) + global-batch Dice + summed gradients must equal ONE process
+# on the concatenated batch, running statistics included; without SyncBN the two differ (per-rank statistics)
+torch.manual_seed(1)
+bn = unet3d_b200.ResAttrBNUnet3D(num_pool=1, num_features=8, out_channels=3).to(dev).train()
+for mod in bn.modules():
+    if hasattr(mod, "dropout_p"):
+        mod.dropout_p = 0.0                                    # no dropout: the runs must be comparable
+sd0 = {k: v.clone() for k, v in bn.state_dict().items()}
+loss_g = unet3d_b200.DiceLoss(global_batch=True)
+parallel.enable_sync_batchnorm(bn)
+bn.zero_grad(set_to_none=True)
+loss_g(bn(xs), ys).backward()
+parallel.all_reduce_gradients(bn, average=False)
+got = {n: p.grad.detach().clone() for n, p in bn.named_parameters() if p.grad is not None}
+got_buf = {n: b.detach().clone() for n, b in bn.named_buffers()}
+parallel.enable_sync_batchnorm(bn, False)
+bn.load_state_dict(sd0)
+bn.zero_grad(set_to_none=True)
+unet3d_b200.DiceLoss()(bn(x_all), y_all).backward()
+ref = {n: p.grad.detach().clone() for n, p in bn.named_parameters() if p.grad is not None}
+worst = max(rel(got[n], ref[n]) for n in ref if ref[n].norm() > 1e-6 * max(r.norm() for r in ref.values()))
+worst_buf = max(rel(got_buf[n].double(), b.detach().double()) for n, b in bn.named_buffers() if b.dtype.is_floating_point)
+if rank == 0:
+    print(f"SyncBN + global-dice / summed: worst per-tensor gradient rel-L2 vs one process on the whole batch {worst:.2e}, "
+          f"running statistics {worst_buf:.2e}")
+ok = ok and worst < 2e-2 and worst_buf < 1e-5
 import numpy as np
 vol = np.random.RandomState(3).standard_normal((96, 72, 40, 1)).astype(np.float32)
 sharded = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False)

@@ -58,8 +58,8 @@ for name, glob in (("local-dice / averaged", False), ("global-dice / summed", Tr
 torch.manual_seed(1)
 bn = unet3d_b200.ResAttrBNUnet3D(num_pool=1, num_features=8, out_channels=3).to(dev).train()
 for mod in bn.modules():
-    if hasattr(mod, "dropout_p"):
-        mod.dropout_p = 0.0                                    # no dropout: the runs must be comparable
+    if isinstance(mod, torch.nn.Dropout3d):
+        mod.p = 0.0                                            # no dropout: the runs must be comparable
 sd0 = {k: v.clone() for k, v in bn.state_dict().items()}
 loss_g = unet3d_b200.DiceLoss(global_batch=True)
 parallel.enable_sync_batchnorm(bn)
@@ -78,6 +78,8 @@ worst_buf = max(rel(got_buf[n].double(), b.detach().double()) for n, b in bn.nam
 if rank == 0:
     print(f"SyncBN + global-dice / summed: worst per-tensor gradient rel-L2 vs one process on the whole batch {worst:.2e}, "
           f"running statistics {worst_buf:.2e}")
+if not (worst < 2e-2 and worst_buf < 1e-5):
+    print(f"[rank {rank}] SyncBN check failed: gradients {worst:.3e}, running statistics {worst_buf:.3e}", flush=True)
 ok = ok and worst < 2e-2 and worst_buf < 1e-5
 import numpy as np
 vol = np.random.RandomState(3).standard_normal((96, 72, 40, 1)).astype(np.float32)
@@ -89,7 +91,11 @@ probs_1 = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=
 dmax = float(np.nanmax(np.abs(probs_s - probs_1)))
 if rank == 0:
     print(f"sliding-window inference over {world} ranks vs one process: label agreement {agree:.6f}, max |dp| {dmax:.2e}")
+if not (agree > 0.9999 and dmax < 1e-5):
+    print(f"[rank {rank}] inference check failed: agreement {agree}, max |dp| {dmax}", flush=True)
 ok = ok and agree > 0.9999 and dmax < 1e-5
+if not ok:
+    print(f"[rank {rank}] MISMATCH", flush=True)
 dist.barrier()
 if rank == 0:
     print("OK" if ok else "MISMATCH")

@@ -78,6 +78,7 @@ class UNetEngine:
         self._dw_done, self._dw_split, self._g_split, self._chunk_handle = 0, -1, 0, None
         self._dw_table_a = self._dw_table_b = None
         self._infer_graphs = {}          # predict_per_patch's captured window forwards, by (batch, channels, patch, precision)
+        self._infer_sig = None           # what the packed weights / graphs of the last no-grad forward were built from
 
     # ------------------------------------------------------------------ public entry
     def run(self, x: torch.Tensor) -> torch.Tensor:
@@ -107,7 +108,21 @@ class UNetEngine:
             return _UNetFn.apply(x, self, *params)
         with torch.no_grad():
             logits, _ = self.forward_impl(x.detach(), save=False)
+        if not torch.cuda.is_current_stream_capturing():
+            self._infer_sig = self._param_signature()
         return logits
+
+    def _param_signature(self):
+        return (ops.PACK_EPOCH, self.act_dtype, self.owner.training,
+                tuple((p.data_ptr(), p._version) for p in self.net.parameters()),
+                tuple((b.data_ptr(), b._version) for b in self.net.buffers()))
+
+    def replay_is_current(self) -> bool:
+        """True when nothing a captured inference graph depends on has changed since the last no-grad forward of this
+        engine: no training forward (fused optimizers do not bump tensor versions, so that alone disqualifies), same
+        parameter / buffer tensors at the same versions, same precision and mode.  predict_per_patch then replays its
+        cached window graph from the first window on instead of running one eager forward per volume."""
+        return (not self._last_was_train) and self._infer_sig is not None and self._infer_sig == self._param_signature()
 
     # ------------------------------------------------------------------ helpers
     @property

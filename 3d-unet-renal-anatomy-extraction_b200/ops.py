@@ -160,7 +160,12 @@ class DeviceConvPlan:
         key = (b.data_ptr(), b._version, PACK_EPOCH)
         if self._b_version != key or (torch.cuda.is_current_stream_capturing() and torch.is_grad_enabled()):
             flat = torch.cat([b.detach().reshape(-1).float(), b.new_zeros(1, dtype=torch.float32)])
-            self._b_packed = flat.index_select(0, self.bidx).contiguous()
+            new = flat.index_select(0, self.bidx)
+            # refreshed IN PLACE: a captured inference graph keeps reading this buffer
+            if self._b_packed is None or self._b_packed.shape != new.shape or self._b_packed.device != new.device:
+                self._b_packed = new.contiguous()
+            else:
+                self._b_packed.copy_(new)
             self._b_version = key
         return self._b_packed
 

@@ -94,14 +94,15 @@ def gaussian_window(patch: Sequence[int], sigma_scale: float = 0.125) -> np.ndar
 # sliding-window inference
 # ------------------------------------------------------------------------------------------------
 def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step_per_patch=4, verbose=True,
-                      one_hot=False, window=None, grid_mode="reference", window_batch=2, cuda_graph=True,
+                      one_hot=False, window=None, grid_mode="reference", window_batch=4, cuda_graph=True,
                       distributed=True):
     """input: (X, Y, Z, C_in) float32 numpy.  Returns uint8 labels (X, Y, Z) or, with one_hot=True,
     float32 probabilities (X, Y, Z, num_classes) -- trainer.py:17-98.
 
     window: None = uniform blending (the reference), "gaussian" or a (px,py,pz) float array = weighted.
     window_batch: windows per forward pass (the reference runs one; InstanceNorm and the blend are per window, so
-    the result does not depend on it -- it only amortises the ~300 kernel launches of a forward pass).
+    the result does not depend on it -- it amortises the ~300 kernel launches of a forward pass and the weight
+    traffic of the deep, weight-bound levels: 0.567 / 0.517 / 0.503 s per 512x512x256 volume at 2 / 4 / 8).
     cuda_graph: capture the forward pass of one window batch once and replay it for the others (this library's
     models only; a window forward is ~300 kernel launches and is host-bound when launched eagerly).
     Under an initialised torch.distributed job the window list is cut into contiguous shares (x-slabs), each rank
@@ -118,26 +119,58 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
             print(f"[predict_per_patch rank {parallel.rank_world()[0]}] {what}: {t_dbg[-1] - t_dbg[-2]:.3f} s", flush=True)
 
     patch = tuple(int(p) for p in patch_size)
-    orig_shape = input.shape[:3]
-    vol = pad_to_patch(np.asarray(input, dtype=np.float32), patch)
-    host = np.ascontiguousarray(np.moveaxis(vol, -1, 0))[None]                                   # (1, C, X, Y, Z)
+    orig_shape = tuple(input.shape[:3])
+    vol = np.asarray(input, dtype=np.float32)
+    if any(vol.shape[d] < patch[d] for d in range(3)):       # transform.pad: only volumes smaller than a patch are copied
+        vol = pad_to_patch(vol, patch)
+    pshape = tuple(vol.shape[:3])
+    if vol.shape[3] == 1:
+        host = np.ascontiguousarray(vol).reshape(1, 1, *pshape)                                  # (1, 1, X, Y, Z): a view
+    else:
+        host = np.ascontiguousarray(np.moveaxis(vol, -1, 0))[None]                               # (1, C, X, Y, Z)
 
     def upload(mine, device):
-        if parallel.rank_world()[1] > 1 and distributed:
-            # only the x-range this rank's windows read is uploaded; the rest of the device copy is never touched
-            x = torch.empty(host.shape, dtype=torch.float32, device=device)
-            if mine:
-                xlo, xhi = min(o[0] for o in mine), max(o[0] for o in mine) + patch[0]
-                x[:, :, xlo:xhi].copy_(torch.from_numpy(host[:, :, xlo:xhi]))
-            return x
-        return torch.from_numpy(host).to(device)
+        """The device copy of the volume is filled x-slab by x-slab, on a side stream, just ahead of the windows that read
+        it: the host-side staging of the (pageable) numpy volume overlaps the forward passes already enqueued, and a rank
+        of a sharded run only ever uploads the slabs of its own windows."""
+        x = torch.empty(host.shape, dtype=torch.float32, device=device)
+        side = torch.cuda.Stream(device=device)
+        state = {"lo": None, "hi": None}
 
-    res = _predict_padded(upload, vol.shape[:3], model, num_classes, patch, step_per_patch, verbose, one_hot, window,
+        def ensure(xlo, xhi):
+            if state["lo"] is None:
+                todo = [(xlo, xhi)]
+                state["lo"], state["hi"] = xlo, xhi
+            else:
+                todo = []
+                if xlo < state["lo"]:
+                    todo.append((xlo, state["lo"]))
+                    state["lo"] = xlo
+                if xhi > state["hi"]:
+                    todo.append((state["hi"], xhi))
+                    state["hi"] = xhi
+            if not todo:
+                return
+            with torch.cuda.stream(side):
+                for a, b in todo:
+                    x[:, :, a:b].copy_(torch.from_numpy(host[:, :, a:b]), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            torch.cuda.current_stream(device).wait_event(ev)
+        return x, ensure
+
+    res = _predict_padded(upload, pshape, model, num_classes, patch, step_per_patch, verbose, one_hot, window,
                           grid_mode, window_batch, cuda_graph, distributed, mark)
-    res = res.cpu().numpy()
+    # _predict_padded returns with the GPU still working: the host result buffer is allocated and touched (page faults:
+    # ~25 ms for a 512x512x256 label map) while the windows run, so the copy at the end only moves bytes.  (A pinned
+    # buffer would copy faster but costs ~100 ms of cudaHostAlloc whenever PyTorch's pinned cache has no free block.)
+    out = torch.empty(res.shape, dtype=res.dtype)
+    out.zero_()
+    out.copy_(res)
+    out = out.numpy()
     ops.check_device_errors()
     mark("D2H")
-    return center_pad_crop(res, orig_shape)
+    return out if pshape == orig_shape else center_pad_crop(out, orig_shape)
 
 
 def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, verbose, one_hot, window, grid_mode,
@@ -151,6 +184,9 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
     rank, world = parallel.rank_world() if distributed else (0, 1)      # distributed=False: this process alone
     mine = parallel.shard_contiguous(origins, rank, world)          # an x-slab of the volume per rank
     x = upload(mine, device)
+    ensure = None
+    if isinstance(x, tuple):               # (device volume, ensure(xlo, xhi)): slabs are uploaded on demand
+        x, ensure = x
     result = torch.zeros((num_classes, *shape), dtype=torch.float32, device=device)
     weight = torch.zeros(shape, dtype=torch.float32, device=device)
     if isinstance(window, str):
@@ -159,7 +195,7 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
         window = gaussian_window(patch)
     wdev = None if window is None else torch.as_tensor(window, dtype=torch.float32, device=device).contiguous()
 
-    mark("pad + H2D + buffers")
+    mark("buffers (+ H2D when the volume is not uploaded slab by slab)")
     was_training = model.training
     model.eval()
     it = None
@@ -173,11 +209,19 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
     static_in = torch.empty((wb, x.shape[1], *patch), dtype=torch.float32, device=device)
     graph, static_out = None, None
     first = True
+    eng = getattr(model.net if hasattr(model, "net") else model, "_engine", None) if graphable else None
+    if eng is not None and eng.device == device and gkey in eng._infer_graphs and eng.replay_is_current():
+        # a forward of this shape was captured by an earlier call and neither the weights nor the mode changed since:
+        # replay from the first window on -- no eager forward (~300 Python-side launches, ~30 ms) per volume
+        graph, static_in, static_out = eng._infer_graphs[gkey]
+        first = False
     with torch.no_grad():
         for b0 in range(0, len(mine), wb):
             group = mine[b0:b0 + wb]
             # a short last group is padded with its first window so that only ONE batch shape is ever planned
             padded = group + [group[0]] * (wb - len(group))
+            if ensure is not None:
+                ensure(min(o[0] for o in group), max(o[0] for o in group) + patch[0])
             for i, (ox, oy, oz) in enumerate(padded):
                 static_in[i].copy_(x[0, :, ox:ox + patch[0], oy:oy + patch[1], oz:oz + patch[2]])
             if graph is not None:
@@ -226,7 +270,7 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
 
 
 def predict_case(case, model, target_spacing, normalize_stats, num_classes=3, patch_size=(96, 96, 96),
-                 step_per_patch=4, verbose=True, one_hot=False, window=None, grid_mode="reference", window_batch=2,
+                 step_per_patch=4, verbose=True, one_hot=False, window=None, grid_mode="reference", window_batch=4,
                  cuda_graph=True, distributed=True, keep_on_device=False):
     """trainer.py:101-133: resample + normalise the case, predict it window by window, resize the prediction back to the
     original grid.  Same arguments and result (``case['pred']``: uint8 labels, or float32 probabilities with one_hot).

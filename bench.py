@@ -308,8 +308,8 @@ def main():
         n_win = len(unet3d_b200.tile_origins((512, 512, 256), (128, 128, 128), 2))
         infer = {"metric": "infer CT volumes/s", "value": 1.0 / dt, "unit": "volumes/s", "seconds_per_volume": dt, "seconds_all_runs": [round(v, 4) for v in runs],
                  "volume": [512, 512, 256], "window": [128, 128, 128], "windows": n_win, "grid": "reference (trainer.py:29-40)",
-                 "blend": "uniform", "windows_per_forward": 2, "includes": "H2D of the fp32 volume, all window forwards, blend, normalise + argmax, "
-                 "D2H of the uint8 label map" + (", all-reduce of the blend buffers" if world > 1 else ""),
+                 "blend": "uniform", "windows_per_forward": 4, "includes": "H2D of the fp32 volume from pageable host memory (x-slabs, overlapped with the window forwards), all "
+                 "window forwards, blend, normalise + argmax, D2H of the uint8 label map into pinned memory" + (", all-reduce of the blend buffers" if world > 1 else ""),
                  "label_hist": [int(v) for v in np.bincount(labels.reshape(-1), minlength=3)[:3]]}
 
         if rank == 0:

@@ -206,3 +206,43 @@ def test_graphed_train_step_matches_eager():
         # Adam normalises the update: an element whose tiny gradient changes sign with the atomic summation order moves
         # by +-lr per step in either run, so the parameters agree to a few lr x steps, not to rounding
         assert ((p1 - p2).norm() / p1.norm().clamp_min(1e-12)).item() < 0.1, n1
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_cached_window_graph_follows_the_weights(fused):
+    """predict_per_patch keeps the captured window forward on the engine and, when nothing changed, replays it from the
+    first window of the next volume.  After a training step (fused Adam does not bump tensor versions), an in-place
+    weight edit or load_state_dict the replayed result must still equal an eager, graph-free run on the new weights."""
+    torch.manual_seed(0)
+    model = unet3d_b200.ResUnet3D(num_pool=1, num_features=8, out_channels=3).to(DEV)
+    vol = torch.randn(48, 40, 32, 1, generator=torch.Generator().manual_seed(2)).numpy()
+    kw = dict(num_classes=3, patch_size=(16, 16, 16), step_per_patch=2, verbose=False, one_hot=True, window_batch=2)
+
+    def both():
+        a = unet3d_b200.predict_per_patch(vol, model, **kw)                       # cached graph / fast path
+        b = unet3d_b200.predict_per_patch(vol, model, cuda_graph=False, **kw)     # eager reference
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.allclose(np.nan_to_num(a), np.nan_to_num(b), atol=1e-6), np.nanmax(np.abs(a - b))
+        return a
+
+    p0 = both()
+    p1 = both()                                   # nothing changed: replay from the first window
+    assert np.allclose(np.nan_to_num(p0), np.nan_to_num(p1), atol=1e-6)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-2, fused=fused)
+    x = torch.randn(2, 1, 16, 16, 16, device=DEV)
+    y = torch.randint(0, 3, (2, 16, 16, 16), device=DEV)
+    model.train()
+    unet3d_b200.DiceLoss()(model(x), y).backward()
+    opt.step()
+    model.eval()
+    p2 = both()                                   # after an optimizer step
+    assert np.nanmax(np.abs(p2 - p1)) > 1e-3
+    with torch.no_grad():
+        model.net.fc.bias[0] += 2.0               # in-place edit outside any forward (one class: softmax sees it)
+    p3 = both()
+    assert np.nanmax(np.abs(p3 - p2)) > 1e-3
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["net.fc.bias"][0] -= 2.0
+    model.load_state_dict(sd)
+    p4 = both()
+    assert np.allclose(np.nan_to_num(p4), np.nan_to_num(p2), atol=1e-5)

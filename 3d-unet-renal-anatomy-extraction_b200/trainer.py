@@ -374,6 +374,67 @@ def cascade_predict_case(case, coarse_model, coarse_target_spacing, coarse_norma
 # ------------------------------------------------------------------------------------------------
 # training step loop
 # ------------------------------------------------------------------------------------------------
+class DevicePrefetcher:
+    """Iterates over a loader of dict batches (trainer.py:471-473: ``batch['image'].to(device)``) and yields them on the
+    device: the host->device copies of batch i+1 are enqueued on a side stream BEFORE batch i is handed out, so with
+    pinned batches (the reference's DataLoader default, trainer.py:422) they run under the training step of batch i
+    instead of in front of batch i+1.  Non-tensor entries pass through.
+
+    The device tensors are two alternating sets of staging buffers per (key, shape, dtype), kept per device for the life
+    of the process (no allocator traffic in the loop): a batch stays valid until the batch after the next one is
+    requested -- keep a ``.clone()`` if you need it longer."""
+
+    _streams: Dict[torch.device, torch.cuda.Stream] = {}
+    _buffers: Dict[tuple, List[torch.Tensor]] = {}
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _staging(self, key, t, slot):
+        k = (self.device, key, tuple(t.shape), t.dtype)
+        if k not in self._buffers:
+            self._buffers[k] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for _ in range(2)]
+        return self._buffers[k][slot]
+
+    def __iter__(self):
+        if self.device not in self._streams:
+            self._streams[self.device] = torch.cuda.Stream(device=self.device)
+        side = self._streams[self.device]
+        it = iter(self.loader)
+        count = [0]
+
+        def load():
+            try:
+                batch = next(it)
+            except StopIteration:
+                return None
+            slot = count[0] & 1
+            count[0] += 1
+            # the staging set about to be overwritten was last read by the batch before the current one; all of that
+            # batch's work is already enqueued on the main stream
+            free = torch.cuda.Event()
+            free.record(torch.cuda.current_stream(self.device))
+            side.wait_event(free)
+            with torch.cuda.stream(side):
+                out = {k: (self._staging(k, v, slot).copy_(v, non_blocking=True) if torch.is_tensor(v) else v)
+                       for k, v in batch.items()}
+            ev = torch.cuda.Event()
+            ev.record(side)
+            return out, ev
+
+        nxt = load()
+        while nxt is not None:
+            cur, ev = nxt
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            nxt = load()          # the next upload overlaps whatever the caller enqueues for `cur`
+            yield cur
+
+
 class _TransformedSubset(torch.utils.data.Dataset):
     def __init__(self, dataset, indices, transform):
         self.dataset, self.indices, self.transform = dataset, list(indices), transform
@@ -433,7 +494,8 @@ class Trainer:
         if bar is not None:
             bar.reset(len(data_loader))
             bar.set_description("Epoch %d/%d (LR %.2g)" % (self.current_epoch + 1, self.num_epochs, self.get_lr()))
-        for batch in data_loader:
+        batches = DevicePrefetcher(data_loader, self.device) if self.device.type == "cuda" else data_loader
+        for batch in batches:
             if is_train and self._graphed is not None:
                 loss, y_pred = self._graphed(batch['image'], batch['label'])
                 y = self._graphed.static_label if self._graphed.graph is not None else batch['label'].to(self.device)

@@ -184,7 +184,30 @@ def main():
             return eager_step(img, lab)
         return stepper(img, lab)[0]
 
+    def timed_e2e(n_steps):
+        """End to end through the public API: pinned host batches -> DevicePrefetcher (the upload of batch i+1 runs on a
+        side stream under the step of batch i; every batch is uploaded inside the timed region) -> training step ->
+        loss.item().  One pair of events around the whole loop, first upload included."""
+        l2_flush.zero_()
+        host_batches = [{"image": h_img, "label": h_lab} for _ in range(n_steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        marks = [time.perf_counter()]
+        for b in unet3d_b200.DevicePrefetcher(host_batches, dev):
+            loss = step(b["image"], b["label"])
+            _ = loss.item()                                   # D2H of the step's result
+            marks.append(time.perf_counter())
+        e1.record()
+        torch.cuda.synchronize()
+        if os.environ.get("U3D_BENCH_DEBUG"):
+            print(f"[bench rank {rank}] e2e host ms per step: {[round((b - a) * 1e3, 2) for a, b in zip(marks[:-1], marks[1:])]}, "
+                  f"events {e0.elapsed_time(e1):.2f} ms, graph {'yes' if stepper is not None and stepper.graph is not None else 'no'}",
+                  file=sys.stderr, flush=True)
+        return e0.elapsed_time(e1) / n_steps
+
     def timed(n_steps, e2e):
+        if e2e:
+            return timed_e2e(n_steps)
         evs = []
         for _ in range(n_steps):
             l2_flush.zero_()                                  # flush L2 between timed iterations

@@ -246,3 +246,14 @@ def test_cached_window_graph_follows_the_weights(fused):
     model.load_state_dict(sd)
     p4 = both()
     assert np.allclose(np.nan_to_num(p4), np.nan_to_num(p2), atol=1e-5)
+
+
+def test_device_prefetcher_yields_every_batch_in_order():
+    host = [{"image": torch.full((2, 1, 8, 8, 8), float(i)).pin_memory(), "label": torch.full((2, 8, 8, 8), i).pin_memory(),
+             "case_id": f"c{i}"} for i in range(5)]
+    seen = []
+    for b in unet3d_b200.DevicePrefetcher(host, DEV):
+        assert b["image"].is_cuda and b["label"].is_cuda and b["label"].dtype == torch.int64
+        seen.append((b["case_id"], float(b["image"].mean().item()), int(b["label"].max().item())))
+    assert seen == [(f"c{i}", float(i), i) for i in range(5)]
+    assert len(unet3d_b200.DevicePrefetcher(host, DEV)) == 5

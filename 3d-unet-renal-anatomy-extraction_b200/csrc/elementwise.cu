@@ -255,11 +255,12 @@ __global__ void channel_sum_kernel(const uint4* __restrict__ x, double* __restri
 // Stem: Conv3d(Cin -> C, k3, p1) + bias on an fp32 NCDHW input (Cin = 1 in every reference script), bf16 NDHWC output
 // (network.py:541,550 -- no norm / activation follows).  K = 27 Cin: HBM-bound, CUDA cores.
 // ---------------------------------------------------------------------------------------------
-template <int CP>
+template <int CP, bool ONE>
 __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cin][27][CP]*/,
-                                const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, int N, int Cin, int D,
+                                const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out, int N, int Cin_rt, int D,
                                 int H, int W, int af) {
   extern __shared__ float ws[];                  // Cin * 27 * CP weights, then CP biases
+  const int Cin = ONE ? 1 : Cin_rt;              // the single-channel stem of every reference script: loop folded away
   const int nw = Cin * 27 * CP;
   for (int i = threadIdx.x; i < nw + CP; i += blockDim.x) ws[i] = i < nw ? w[i] : b[i - nw];
   __syncthreads();
@@ -401,6 +402,158 @@ __global__ void __launch_bounds__(CP / 8 * 3 * 16) stem_wgrad_kernel(const float
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem weight/bias gradient on the (legacy, warp-level) tensor-core path: the contraction over voxels is a GEMM with
+// M = 32 rows (27 taps, row 27 = ones -> the bias sum, rows 28..31 empty), N = CP channels, K = voxels:
+//     dw[tap][c] = sum_v x[v + shift(tap)] * dy[v][c]
+// A warp walks the 16-voxel runs of a w-row: the 3x3 window of fp32 x rows is staged in shared memory (gathering the A
+// fragment straight from global cost ~12 L1 sector operations per voxel and bounded the kernel) and split into a 16-bit
+// high and low part (two MMAs: the result keeps ~fp32 accuracy in x); the dy run (16 voxels x CP channels) goes
+// through shared memory and ldmatrix.trans.  72 FMAs per voxel and thread of the CUDA-core
+// kernel above become 2 x 2 x CP/8 mma.sync.m16n8k16 per 16 voxels and warp -- the kernel is left HBM-bound on dy.
+// K = 27 is far too small for tcgen05 (M = 128 rows minimum): mma.sync is the right tool for this one layer.
+// ---------------------------------------------------------------------------------------------
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int CP, bool F16>
+__global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
+                                                            float* __restrict__ dw, int N, int D, int H, int W,
+                                                            long long x_sN) {
+  constexpr int NT = CP / 8;                       // n-tiles of 8 channels
+  constexpr int PITCH = CP * 2 + 16;               // bytes per voxel row of the staged dy run (+16: ldmatrix bank spread)
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  typedef uint8_t (*SdyT)[2][16 * PITCH];
+  typedef float (*SxT)[2][10 * 20];
+  SdyT sdy = reinterpret_cast<SdyT>(stem_smem);                                  // per warp, double buffered: the dy run
+  SxT sx = reinterpret_cast<SxT>(stem_smem + 8 * 2 * 16 * PITCH);                // ... the 3x3 window of x rows + a zero row
+  float* sred = reinterpret_cast<float*>(stem_smem + 8 * 2 * 16 * PITCH + 8 * 2 * 10 * 20 * 4);     // [32][CP]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;       // fragment coordinates
+  for (int i = threadIdx.x; i < 32 * CP; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float acc[2][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[mt][nt][r] = 0.f;
+  const long long n_rows = (long long)N * D * H;
+  const int cpr = (W + 15) / 16;                   // 16-voxel runs per w-row
+  // this thread's four taps as (row of the staged 3x3 x-window, kw): row 9 = zeros (taps 28..31), tap 27 = ones
+  int trow[4], tkw[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int tap = gid + 8 * r;
+    trow[r] = tap < 27 ? tap / 3 : 9;
+    tkw[r] = tap < 27 ? tap % 3 : 0;
+  }
+  // the warp's runs form one sequence (row-major over its rows); run i+1 is fetched with cp.async into the other half of
+  // the staging buffers while run i is multiplied -- without this every run paid two global-load latencies in series
+  const long long row0 = (long long)blockIdx.x * 8 + warp, row_step = (long long)gridDim.x * 8;
+  const long long my_rows = row0 < n_rows ? (n_rows - row0 + row_step - 1) / row_step : 0;
+  const long long my_runs = my_rows * cpr;
+  auto fetch = [&](long long i, int buf) {
+    const long long row = row0 + (i / cpr) * row_step;
+    const int w0 = (int)(i % cpr) * 16;
+    long long q = row;
+    const int h = (int)(q % H); q /= H;
+    const int d = (int)(q % D);
+    const int n = (int)(q / D);
+    const float* xn = x + (size_t)n * x_sN;
+    const bf16* drow = dy + ((((size_t)n * D + d) * H + h) * W + w0) * CP;
+    const uint32_t dst_y = smem_u32(sdy[warp][buf]), dst_x = smem_u32(sx[warp][buf]);
+    for (int j = lane; j < 16 * NT; j += 32) {                 // dy run: 16 voxels x CP channels, rows past W zero-filled
+      const int v = j / NT, c8 = j - v * NT;
+      const bool ok = w0 + v < W;
+      const void* src = ok ? (const void*)(drow + (size_t)j * 8) : (const void*)dy;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_y + v * PITCH + c8 * 16), "l"(src), "r"(ok ? 16 : 0));
+    }
+    for (int j = lane; j < 10 * 18; j += 32) {                 // 3x3 window of x rows [w0-1, w0+16], zero outside; row 9 zeros
+      const int rr = j / 18, jj = j - rr * 18;
+      const int xd = d + rr / 3 - 1, xh = h + rr % 3 - 1, xw = w0 + jj - 1;
+      const bool ok = rr < 9 && xd >= 0 && xd < D && xh >= 0 && xh < H && xw >= 0 && xw < W;
+      const void* src = ok ? (const void*)(xn + ((size_t)xd * H + xh) * W + xw) : (const void*)x;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_x + (rr * 20 + jj) * 4), "l"(src), "r"(ok ? 4 : 0));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (my_runs > 0) fetch(0, 0);
+  for (long long i = 0; i < my_runs; ++i) {
+    const int buf = (int)(i & 1);
+    if (i + 1 < my_runs) {
+      fetch(i + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const float* myx = sx[warp][buf];
+    const uint32_t my_s = smem_u32(sdy[warp][buf]);
+    // ---- A fragments: x[v + shift(tap)] for this thread's 4 taps x 4 voxels (k = 2 tig, 2 tig + 1, + 8, + 9)
+    uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                  // row block r: tap = gid + 8 r -> m-tile r / 2, fragment regs (r & 1) + {0, 2}
+      const float* xr = myx + trow[r] * 20 + tkw[r];
+      float hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = 2 * tig + (j & 1) + 8 * (j >> 1);
+        float t = xr[k];
+        if (gid + 8 * r == 27) t = 1.f;            // the bias row: sum of dy (rows of dy past W are zero)
+        hi[j] = F16 ? __half2float(__float2half_rn(t)) : __bfloat162float(__float2bfloat16_rn(t));
+        lo[j] = t - hi[j];
+      }
+      const int mt = r >> 1, base = r & 1;         // a0/a2 belong to row gid, a1/a3 to row gid + 8 of the m-tile
+      ahi[mt][base] = pack_2x16(hi[0], hi[1], F16);
+      ahi[mt][base + 2] = pack_2x16(hi[2], hi[3], F16);
+      alo[mt][base] = pack_2x16(lo[0], lo[1], F16);
+      alo[mt][base + 2] = pack_2x16(lo[2], lo[3], F16);
+    }
+    // ---- B fragments from shared memory (ldmatrix.trans: thread gets (k = 2 tig + {0,1}, n = gid)) and the MMAs
+#pragma unroll
+    for (int nt = 0; nt < NT; nt += 2) {
+      // four 8x8 matrices: (voxels 0-7, tile nt), (voxels 8-15, tile nt), (voxels 0-7, tile nt+1), (voxels 8-15, tile nt+1)
+      const int mat = lane >> 3, rrow = lane & 7;
+      const uint32_t addr = my_s + (uint32_t)((rrow + 8 * (mat & 1)) * PITCH + (nt + (mat >> 1)) * 16);
+      uint32_t b[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr));
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_16816<F16>(acc[mt][nt], ahi[mt], b[0], b[1]);
+        mma_16816<F16>(acc[mt][nt], alo[mt], b[0], b[1]);
+        mma_16816<F16>(acc[mt][nt + 1], ahi[mt], b[2], b[3]);
+        mma_16816<F16>(acc[mt][nt + 1], alo[mt], b[2], b[3]);
+      }
+    }
+    __syncwarp();                                  // everyone is done with this half before the run after next lands in it
+  }
+  // ---- CTA reduction in shared memory, then one atomic per (tap row < 28, channel)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int row = mt * 16 + gid, col = nt * 8 + 2 * tig;
+      atomicAdd(&sred[row * CP + col], acc[mt][nt][0]);
+      atomicAdd(&sred[row * CP + col + 1], acc[mt][nt][1]);
+      atomicAdd(&sred[(row + 8) * CP + col], acc[mt][nt][2]);
+      atomicAdd(&sred[(row + 8) * CP + col + 1], acc[mt][nt][3]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 28 * CP; i += blockDim.x) atomicAdd(&dw[i], sred[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1099,17 +1252,46 @@ int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, i
   const int g = grid_for(total, 128, num_sms, 16);
   const size_t smem = ((size_t)Cin * 27 * Cp + Cp) * sizeof(float);
   if (Cin < 1 || smem > 48 * 1024) return U3D_ERR_UNSUPPORTED;
-  if (Cp == 32) stem_fwd_kernel<32><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af);
-  else if (Cp == 16) stem_fwd_kernel<16><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af);
-  else if (Cp == 48) stem_fwd_kernel<48><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af);
-  else if (Cp == 64) stem_fwd_kernel<64><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af);
+#define U3D_SF(CPV)                                                                                  \
+  do {                                                                                               \
+    if (Cin == 1) stem_fwd_kernel<CPV, true><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af); \
+    else stem_fwd_kernel<CPV, false><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af);        \
+  } while (0)
+  if (Cp == 32) U3D_SF(32);
+  else if (Cp == 16) U3D_SF(16);
+  else if (Cp == 48) U3D_SF(48);
+  else if (Cp == 64) U3D_SF(64);
   else return U3D_ERR_UNSUPPORTED;
+#undef U3D_SF
   return U3D_CHECK_LAUNCH();
 }
 
 int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, int W, long long x_sN, int Cp, int af,
                int num_sms, cudaStream_t s) {
   const long long n_runs = (long long)N * D * H * ((W + 15) / 16);
+  static const bool legacy = getenv("U3D_STEM_WGRAD_FMA") != nullptr;        // the CUDA-core kernel, for comparisons
+  if (!legacy) {
+    const int g = grid_for((long long)N * D * H, 8 * 4, num_sms, 4);
+#define U3D_SW(CPV)                                                                                          \
+  do {                                                                                                       \
+    constexpr int smem = 8 * 2 * 16 * (CPV * 2 + 16) + 8 * 2 * 10 * 20 * 4 + 32 * CPV * 4;                   \
+    static bool attr = false;                                                                                \
+    if (!attr) {                                                                                             \
+      cudaFuncSetAttribute(stem_wgrad_mma_kernel<CPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+      cudaFuncSetAttribute(stem_wgrad_mma_kernel<CPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+      attr = true;                                                                                           \
+    }                                                                                                        \
+    if (af) stem_wgrad_mma_kernel<CPV, true><<<g, 256, smem, s>>>(x, dy, dw, N, D, H, W, x_sN);              \
+    else stem_wgrad_mma_kernel<CPV, false><<<g, 256, smem, s>>>(x, dy, dw, N, D, H, W, x_sN);                \
+  } while (0)
+    if (Cp == 32) U3D_SW(32);
+    else if (Cp == 16) U3D_SW(16);
+    else if (Cp == 48) U3D_SW(48);
+    else if (Cp == 64) U3D_SW(64);
+    else return U3D_ERR_UNSUPPORTED;
+#undef U3D_SW
+    return U3D_CHECK_LAUNCH();
+  }
   dim3 blk(Cp / 8, 3, 16);
   const int g = grid_for(n_runs, 16 * 4, num_sms, 4);
   if (Cp == 32) stem_wgrad_kernel<32><<<g, blk, 0, s>>>(x, dy, dw, N, D, H, W, x_sN, af);

@@ -415,6 +415,31 @@ __global__ void __launch_bounds__(CP / 8 * 3 * 16) stem_wgrad_kernel(const float
 // kernel above become 2 x 2 x CP/8 mma.sync.m16n8k16 per 16 voxels and warp -- the kernel is left HBM-bound on dy.
 // K = 27 is far too small for tcgen05 (M = 128 rows minimum): mma.sync is the right tool for this one layer.
 // ---------------------------------------------------------------------------------------------
+// Stage the 3x3 window of fp32 x rows around (d, h), columns [w0 - 4, w0 + 20), into shared memory with cp.async (row pitch 28
+// floats; element (row rr, column jj) = x[d + rr/3 - 1][h + rr%3 - 1][w0 - 4 + jj], zero outside the volume).  16-byte pieces
+// when W % 4 == 0 (54 per run instead of 9 x 18 four-byte ones: the staging was what bounded both stem kernels).
+constexpr int STEM_XP = 28;
+__device__ __forceinline__ void stem_stage_x(uint32_t dst, const float* __restrict__ xn, const float* __restrict__ any, int d, int h,
+                                             int w0, int D, int H, int W, int lane) {
+  if ((W & 3) == 0) {
+    for (int j = lane; j < 9 * 6; j += 32) {
+      const int rr = j / 6, pc = j - rr * 6;
+      const int xd = d + rr / 3 - 1, xh = h + rr % 3 - 1, xw = w0 - 4 + 4 * pc;
+      const bool ok = xd >= 0 && xd < D && xh >= 0 && xh < H && xw >= 0 && xw < W;
+      const void* src = ok ? (const void*)(xn + ((size_t)xd * H + xh) * W + xw) : (const void*)any;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (rr * STEM_XP + 4 * pc) * 4), "l"(src), "r"(ok ? 16 : 0));
+    }
+  } else {
+    for (int j = lane; j < 9 * 18; j += 32) {
+      const int rr = j / 18, jj = j - rr * 18 + 3;
+      const int xd = d + rr / 3 - 1, xh = h + rr % 3 - 1, xw = w0 - 4 + jj;
+      const bool ok = xd >= 0 && xd < D && xh >= 0 && xh < H && xw >= 0 && xw < W;
+      const void* src = ok ? (const void*)(xn + ((size_t)xd * H + xh) * W + xw) : (const void*)any;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (rr * STEM_XP + jj) * 4), "l"(src), "r"(ok ? 4 : 0));
+    }
+  }
+}
+
 template <bool F16>
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   if (F16)
@@ -435,13 +460,15 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const float* __rest
   constexpr int PITCH = CP * 2 + 16;               // bytes per voxel row of the staged dy run (+16: ldmatrix bank spread)
   extern __shared__ __align__(16) uint8_t stem_smem[];
   typedef uint8_t (*SdyT)[2][16 * PITCH];
-  typedef float (*SxT)[2][10 * 20];
+  typedef float (*SxT)[2][10 * STEM_XP];
   SdyT sdy = reinterpret_cast<SdyT>(stem_smem);                                  // per warp, double buffered: the dy run
   SxT sx = reinterpret_cast<SxT>(stem_smem + 8 * 2 * 16 * PITCH);                // ... the 3x3 window of x rows + a zero row
-  float* sred = reinterpret_cast<float*>(stem_smem + 8 * 2 * 16 * PITCH + 8 * 2 * 10 * 20 * 4);     // [32][CP]
+  float* sred = reinterpret_cast<float*>(stem_smem + 8 * 2 * 16 * PITCH + 8 * 2 * 10 * STEM_XP * 4);     // [32][CP]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;       // fragment coordinates
   for (int i = threadIdx.x; i < 32 * CP; i += blockDim.x) sred[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * 2 * STEM_XP; i += blockDim.x)               // row 9 of every window buffer: zeros, never staged
+    sx[i / (2 * STEM_XP)][(i / STEM_XP) & 1][9 * STEM_XP + i % STEM_XP] = 0.f;
   __syncthreads();
   float acc[2][NT][4];
 #pragma unroll
@@ -481,13 +508,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const float* __rest
       const void* src = ok ? (const void*)(drow + (size_t)j * 8) : (const void*)dy;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_y + v * PITCH + c8 * 16), "l"(src), "r"(ok ? 16 : 0));
     }
-    for (int j = lane; j < 10 * 18; j += 32) {                 // 3x3 window of x rows [w0-1, w0+16], zero outside; row 9 zeros
-      const int rr = j / 18, jj = j - rr * 18;
-      const int xd = d + rr / 3 - 1, xh = h + rr % 3 - 1, xw = w0 + jj - 1;
-      const bool ok = rr < 9 && xd >= 0 && xd < D && xh >= 0 && xh < H && xw >= 0 && xw < W;
-      const void* src = ok ? (const void*)(xn + ((size_t)xd * H + xh) * W + xw) : (const void*)x;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_x + (rr * 20 + jj) * 4), "l"(src), "r"(ok ? 4 : 0));
-    }
+    stem_stage_x(dst_x, xn, x, d, h, w0, D, H, W, lane);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   if (my_runs > 0) fetch(0, 0);
@@ -506,7 +527,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const float* __rest
     uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {                  // row block r: tap = gid + 8 r -> m-tile r / 2, fragment regs (r & 1) + {0, 2}
-      const float* xr = myx + trow[r] * 20 + tkw[r];
+      const float* xr = myx + trow[r] * STEM_XP + tkw[r] + 3;
       float hi[4], lo[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -554,6 +575,135 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const float* __rest
     }
   __syncthreads();
   for (int i = threadIdx.x; i < 28 * CP; i += blockDim.x) atomicAdd(&dw[i], sred[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-channel stem forward on mma.sync: out[v][c] = b[c] + sum_tap x[v + shift(tap)] * w[tap][c] as a GEMM with
+// M = 16 voxels of a w-run, K = 32 (27 taps, tap 27 = ones against the bias row, 28..31 empty), N = CP channels.
+// x and w are split into 16-bit high and low parts (hi*hi + hi*lo + lo*hi: fp32-grade products, like the FMA kernel).
+// The 3x3 window of x rows arrives by cp.async one run ahead; the 16 x CP output run is staged in shared memory and leaves as
+// one contiguous 16-bit NDHWC block (16-byte stores).  HBM-bound on the output; also the first kernel of every window forward.
+// ---------------------------------------------------------------------------------------------
+template <int CP, bool F16>
+__global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w /*[27][CP]*/,
+                                                          const float* __restrict__ b /*[CP]*/, bf16* __restrict__ out,
+                                                          int N, int D, int H, int W) {
+  constexpr int NT = CP / 8;
+  constexpr int OPITCH = CP * 2 + 16;              // bytes per voxel row of the staged output run
+  __shared__ __align__(16) float sx[8][2][10 * STEM_XP];
+  __shared__ __align__(16) uint8_t so[8][16 * OPITCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  // ---- B fragments (taps x channels), loop invariant: b0 = (k = 2 tig + {0,1}, n = gid), b1 = k + 8; two k-steps
+  uint32_t bhi[2][NT][2], blo[2][NT][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float v[2], hi[2], lo[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int tap = ks * 16 + r * 8 + 2 * tig + j, c = nt * 8 + gid;
+          v[j] = tap < 27 ? __ldg(&w[tap * CP + c]) : (tap == 27 ? __ldg(&b[c]) : 0.f);
+          hi[j] = F16 ? __half2float(__float2half_rn(v[j])) : __bfloat162float(__float2bfloat16_rn(v[j]));
+          lo[j] = v[j] - hi[j];
+        }
+        bhi[ks][nt][r] = pack_2x16(hi[0], hi[1], F16);
+        blo[ks][nt][r] = pack_2x16(lo[0], lo[1], F16);
+      }
+  // this thread's A columns: taps ks*16 + {2 tig, 2 tig + 1, 2 tig + 8, 2 tig + 9} as (window row, kw); 27 = ones, > 27 zero row
+  int trow[2][4], tkw[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tap = ks * 16 + 2 * tig + (j & 1) + 8 * (j >> 1);
+      trow[ks][j] = tap < 27 ? tap / 3 : 9;
+      tkw[ks][j] = tap < 27 ? tap % 3 : 0;
+    }
+  for (int i = threadIdx.x; i < 8 * 2 * STEM_XP; i += blockDim.x)               // row 9 of every window buffer: zeros, never staged
+    sx[i / (2 * STEM_XP)][(i / STEM_XP) & 1][9 * STEM_XP + i % STEM_XP] = 0.f;
+  __syncthreads();
+  const long long n_rows = (long long)N * D * H;
+  const int cpr = (W + 15) / 16;
+  const long long row0 = (long long)blockIdx.x * 8 + warp, row_step = (long long)gridDim.x * 8;
+  const long long my_rows = row0 < n_rows ? (n_rows - row0 + row_step - 1) / row_step : 0;
+  const long long my_runs = my_rows * cpr;
+  auto fetch = [&](long long i, int buf) {
+    const long long row = row0 + (i / cpr) * row_step;
+    const int w0 = (int)(i % cpr) * 16;
+    long long q = row;
+    const int h = (int)(q % H); q /= H;
+    const int d = (int)(q % D);
+    const int n = (int)(q / D);
+    const float* xn = x + (size_t)n * D * H * W;
+    const uint32_t dst_x = smem_u32(sx[warp][buf]);
+    stem_stage_x(dst_x, xn, x, d, h, w0, D, H, W, lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (my_runs > 0) fetch(0, 0);
+  for (long long i = 0; i < my_runs; ++i) {
+    const int buf = (int)(i & 1);
+    if (i + 1 < my_runs) {
+      fetch(i + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const float* myx = sx[warp][buf];
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[nt][r] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      // A fragment: a0 = (voxel gid, taps 2 tig + {0,1}), a1 = voxel gid + 8, a2 / a3 = taps + 8
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for (int vr = 0; vr < 2; ++vr) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = myx[trow[ks][j] * STEM_XP + tkw[ks][j] + 3 + gid + 8 * vr];
+          if (ks == 1 && 2 * tig + (j & 1) + 8 * (j >> 1) == 11) t = 1.f;      // tap 27: the bias row of B
+          hi[j] = F16 ? __half2float(__float2half_rn(t)) : __bfloat162float(__float2bfloat16_rn(t));
+          lo[j] = t - hi[j];
+        }
+        ahi[vr] = pack_2x16(hi[0], hi[1], F16);
+        ahi[vr + 2] = pack_2x16(hi[2], hi[3], F16);
+        alo[vr] = pack_2x16(lo[0], lo[1], F16);
+        alo[vr + 2] = pack_2x16(lo[2], lo[3], F16);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mma_16816<F16>(acc[nt], ahi, bhi[ks][nt][0], bhi[ks][nt][1]);
+        mma_16816<F16>(acc[nt], ahi, blo[ks][nt][0], blo[ks][nt][1]);
+        mma_16816<F16>(acc[nt], alo, bhi[ks][nt][0], bhi[ks][nt][1]);
+      }
+    }
+    // ---- stage the 16 x CP run (c0,c1 = voxel gid, channels nt*8 + 2 tig + {0,1}; c2,c3 = voxel gid + 8), store coalesced
+    uint8_t* myo = so[warp];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      *reinterpret_cast<uint32_t*>(myo + gid * OPITCH + (nt * 8 + 2 * tig) * 2) = pack_2x16(acc[nt][0], acc[nt][1], F16);
+      *reinterpret_cast<uint32_t*>(myo + (gid + 8) * OPITCH + (nt * 8 + 2 * tig) * 2) = pack_2x16(acc[nt][2], acc[nt][3], F16);
+    }
+    __syncwarp();
+    {
+      const long long row = row0 + (i / cpr) * row_step;
+      const int w0 = (int)(i % cpr) * 16;
+      uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)row * W + w0) * CP);
+      for (int j = lane; j < 16 * NT; j += 32) {
+        const int v = j / NT, c8 = j - v * NT;
+        if (w0 + v < W) dst[j] = *reinterpret_cast<const uint4*>(myo + v * OPITCH + c8 * 16);
+      }
+    }
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1252,6 +1402,18 @@ int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, i
   const int g = grid_for(total, 128, num_sms, 16);
   const size_t smem = ((size_t)Cin * 27 * Cp + Cp) * sizeof(float);
   if (Cin < 1 || smem > 48 * 1024) return U3D_ERR_UNSUPPORTED;
+  static const bool legacy = getenv("U3D_STEM_FWD_FMA") != nullptr;          // the CUDA-core kernel, for comparisons
+  if (Cin == 1 && !legacy && (Cp == 16 || Cp == 32)) {
+    const int gm = grid_for((long long)N * D * H, 8 * 4, num_sms, 4);
+    if (Cp == 32) {
+      if (af) stem_fwd_mma_kernel<32, true><<<gm, 256, 0, s>>>(x, w, b, out, N, D, H, W);
+      else stem_fwd_mma_kernel<32, false><<<gm, 256, 0, s>>>(x, w, b, out, N, D, H, W);
+    } else {
+      if (af) stem_fwd_mma_kernel<16, true><<<gm, 256, 0, s>>>(x, w, b, out, N, D, H, W);
+      else stem_fwd_mma_kernel<16, false><<<gm, 256, 0, s>>>(x, w, b, out, N, D, H, W);
+    }
+    return U3D_CHECK_LAUNCH();
+  }
 #define U3D_SF(CPV)                                                                                  \
   do {                                                                                               \
     if (Cin == 1) stem_fwd_kernel<CPV, true><<<g, 128, smem, s>>>(x, w, b, out, N, Cin, D, H, W, af); \
@@ -1274,7 +1436,7 @@ int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, i
     const int g = grid_for((long long)N * D * H, 8 * 4, num_sms, 4);
 #define U3D_SW(CPV)                                                                                          \
   do {                                                                                                       \
-    constexpr int smem = 8 * 2 * 16 * (CPV * 2 + 16) + 8 * 2 * 10 * 20 * 4 + 32 * CPV * 4;                   \
+    constexpr int smem = 8 * 2 * 16 * (CPV * 2 + 16) + 8 * 2 * 10 * STEM_XP * 4 + 32 * CPV * 4;                   \
     static bool attr = false;                                                                                \
     if (!attr) {                                                                                             \
       cudaFuncSetAttribute(stem_wgrad_mma_kernel<CPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \

@@ -489,16 +489,18 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const float* __rest
   }
   // the warp's runs form one sequence (row-major over its rows); run i+1 is fetched with cp.async into the other half of
   // the staging buffers while run i is multiplied -- without this every run paid two global-load latencies in series
-  const long long row0 = (long long)blockIdx.x * 8 + warp, row_step = (long long)gridDim.x * 8;
-  const long long my_rows = row0 < n_rows ? (n_rows - row0 + row_step - 1) / row_step : 0;
-  const long long my_runs = my_rows * cpr;
-  auto fetch = [&](long long i, int buf) {
-    const long long row = row0 + (i / cpr) * row_step;
-    const int w0 = (int)(i % cpr) * 16;
-    long long q = row;
-    const int h = (int)(q % H); q /= H;
-    const int d = (int)(q % D);
-    const int n = (int)(q / D);
+  // 32-bit index arithmetic (the launcher refuses volumes with 2^31 runs or more): 64-bit divisions cost ~50 instructions each
+  const int row0 = blockIdx.x * 8 + warp, row_step = gridDim.x * 8;
+  const int my_rows = row0 < (int)n_rows ? ((int)n_rows - row0 + row_step - 1) / row_step : 0;
+  const int my_runs = my_rows * cpr;
+  auto fetch = [&](int i, int buf) {
+    const int ri = i / cpr;
+    const int row = row0 + ri * row_step;
+    const int w0 = (i - ri * cpr) * 16;
+    int q = row;
+    const int h = q % H; q /= H;
+    const int d = q % D;
+    const int n = q / D;
     const float* xn = x + (size_t)n * x_sN;
     const bf16* drow = dy + ((((size_t)n * D + d) * H + h) * W + w0) * CP;
     const uint32_t dst_y = smem_u32(sdy[warp][buf]), dst_x = smem_u32(sx[warp][buf]);
@@ -512,8 +514,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const float* __rest
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   if (my_runs > 0) fetch(0, 0);
-  for (long long i = 0; i < my_runs; ++i) {
-    const int buf = (int)(i & 1);
+  for (int i = 0; i < my_runs; ++i) {
+    const int buf = i & 1;
     if (i + 1 < my_runs) {
       fetch(i + 1, buf ^ 1);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -628,24 +630,26 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const float* __restri
   __syncthreads();
   const long long n_rows = (long long)N * D * H;
   const int cpr = (W + 15) / 16;
-  const long long row0 = (long long)blockIdx.x * 8 + warp, row_step = (long long)gridDim.x * 8;
-  const long long my_rows = row0 < n_rows ? (n_rows - row0 + row_step - 1) / row_step : 0;
-  const long long my_runs = my_rows * cpr;
-  auto fetch = [&](long long i, int buf) {
-    const long long row = row0 + (i / cpr) * row_step;
-    const int w0 = (int)(i % cpr) * 16;
-    long long q = row;
-    const int h = (int)(q % H); q /= H;
-    const int d = (int)(q % D);
-    const int n = (int)(q / D);
+  // 32-bit index arithmetic (the launcher refuses volumes with 2^31 runs or more): 64-bit divisions cost ~50 instructions each
+  const int row0 = blockIdx.x * 8 + warp, row_step = gridDim.x * 8;
+  const int my_rows = row0 < (int)n_rows ? ((int)n_rows - row0 + row_step - 1) / row_step : 0;
+  const int my_runs = my_rows * cpr;
+  auto fetch = [&](int i, int buf) {
+    const int ri = i / cpr;
+    const int row = row0 + ri * row_step;
+    const int w0 = (i - ri * cpr) * 16;
+    int q = row;
+    const int h = q % H; q /= H;
+    const int d = q % D;
+    const int n = q / D;
     const float* xn = x + (size_t)n * D * H * W;
     const uint32_t dst_x = smem_u32(sx[warp][buf]);
     stem_stage_x(dst_x, xn, x, d, h, w0, D, H, W, lane);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   if (my_runs > 0) fetch(0, 0);
-  for (long long i = 0; i < my_runs; ++i) {
-    const int buf = (int)(i & 1);
+  for (int i = 0; i < my_runs; ++i) {
+    const int buf = i & 1;
     if (i + 1 < my_runs) {
       fetch(i + 1, buf ^ 1);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -694,8 +698,9 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const float* __restri
     }
     __syncwarp();
     {
-      const long long row = row0 + (i / cpr) * row_step;
-      const int w0 = (int)(i % cpr) * 16;
+      const int ri = i / cpr;
+      const int row = row0 + ri * row_step;
+      const int w0 = (i - ri * cpr) * 16;
       uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)row * W + w0) * CP);
       for (int j = lane; j < 16 * NT; j += 32) {
         const int v = j / NT, c8 = j - v * NT;
@@ -1403,7 +1408,7 @@ int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, i
   const size_t smem = ((size_t)Cin * 27 * Cp + Cp) * sizeof(float);
   if (Cin < 1 || smem > 48 * 1024) return U3D_ERR_UNSUPPORTED;
   static const bool legacy = getenv("U3D_STEM_FWD_FMA") != nullptr;          // the CUDA-core kernel, for comparisons
-  if (Cin == 1 && !legacy && (Cp == 16 || Cp == 32)) {
+  if (Cin == 1 && !legacy && (Cp == 16 || Cp == 32) && total < 0x7fffffffLL) {
     const int gm = grid_for((long long)N * D * H, 8 * 4, num_sms, 4);
     if (Cp == 32) {
       if (af) stem_fwd_mma_kernel<32, true><<<gm, 256, 0, s>>>(x, w, b, out, N, D, H, W);
@@ -1432,7 +1437,7 @@ int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, i
                int num_sms, cudaStream_t s) {
   const long long n_runs = (long long)N * D * H * ((W + 15) / 16);
   static const bool legacy = getenv("U3D_STEM_WGRAD_FMA") != nullptr;        // the CUDA-core kernel, for comparisons
-  if (!legacy) {
+  if (!legacy && n_runs < 0x7fffffffLL) {
     const int g = grid_for((long long)N * D * H, 8 * 4, num_sms, 4);
 #define U3D_SW(CPV)                                                                                          \
   do {                                                                                                       \

@@ -1407,8 +1407,11 @@ int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, i
   const int g = grid_for(total, 128, num_sms, 16);
   const size_t smem = ((size_t)Cin * 27 * Cp + Cp) * sizeof(float);
   if (Cin < 1 || smem > 48 * 1024) return U3D_ERR_UNSUPPORTED;
-  static const bool legacy = getenv("U3D_STEM_FWD_FMA") != nullptr;          // the CUDA-core kernel, for comparisons
-  if (Cin == 1 && !legacy && (Cp == 16 || Cp == 32) && total < 0x7fffffffLL) {
+  // The mma.sync forward is opt-in (U3D_STEM_FWD_MMA=1): it is faster (0.21 vs 0.32 ms at 2 x 128^3) and passes every
+  // single-process parity test, but with it the 2-GPU check (tools/check_multi_gpu.py) shows bf16-level noise (4e-3) between
+  // the two-rank and the one-process gradients that the CUDA-core kernel does not show (1e-7) -- not understood yet.
+  static const bool use_mma = getenv("U3D_STEM_FWD_MMA") != nullptr;
+  if (Cin == 1 && use_mma && (Cp == 16 || Cp == 32) && total < 0x7fffffffLL) {
     const int gm = grid_for((long long)N * D * H, 8 * 4, num_sms, 4);
     if (Cp == 32) {
       if (af) stem_fwd_mma_kernel<32, true><<<gm, 256, 0, s>>>(x, w, b, out, N, D, H, W);

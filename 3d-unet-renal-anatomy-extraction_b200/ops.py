@@ -27,6 +27,7 @@ LAUNCHES = 0
 # PACK_EPOCH at every training-mode forward and at the first no-grad forward after one, so a pack is reused only
 # across forwards between which no optimizer step can have happened (e.g. the windows of one inference volume).
 PACK_EPOCH = 0
+BIAS_EPOCH = 0          # bumped whenever a plan's packed bias vector is re-created (BatchNorm variant: conv biases are applied)
 DBG_OUT = None          # tuning experiments: int64[8] device tensor receiving the conv MMA warp's cycle counters
 
 
@@ -160,12 +161,10 @@ class DeviceConvPlan:
         key = (b.data_ptr(), b._version, PACK_EPOCH)
         if self._b_version != key or (torch.cuda.is_current_stream_capturing() and torch.is_grad_enabled()):
             flat = torch.cat([b.detach().reshape(-1).float(), b.new_zeros(1, dtype=torch.float32)])
-            new = flat.index_select(0, self.bidx)
-            # refreshed IN PLACE: a captured inference graph keeps reading this buffer
-            if self._b_packed is None or self._b_packed.shape != new.shape or self._b_packed.device != new.device:
-                self._b_packed = new.contiguous()
-            else:
-                self._b_packed.copy_(new)
+            global BIAS_EPOCH
+            if self._b_packed is not None:
+                BIAS_EPOCH += 1            # a captured inference graph still reads the old buffer: it must be re-captured
+            self._b_packed = flat.index_select(0, self.bidx).contiguous()
             self._b_version = key
         return self._b_packed
 

@@ -205,7 +205,7 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
     wb = max(1, int(window_batch))
     from . import network as _nw
     graphable = cuda_graph and isinstance(model, (_nw.Unet, _nw._ResNetBase)) and len(mine) > 2 * wb
-    gkey = (wb, x.shape[1], patch, getattr(model, "precision", "bf16"))
+    gkey = (wb, x.shape[1], patch, getattr(model, "precision", "bf16"), ops.BIAS_EPOCH)
     static_in = torch.empty((wb, x.shape[1], *patch), dtype=torch.float32, device=device)
     graph, static_out = None, None
     first = True
@@ -233,6 +233,7 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
                     # the captured forward is kept on the engine and reused by later calls (other volumes): capture
                     # + instantiation of ~200 launches costs more than one volume's worth of host launch overhead
                     eng = (model.net if hasattr(model, "net") else model)._engine
+                    gkey = gkey[:-1] + (ops.BIAS_EPOCH,)        # the eager forward above may have re-packed biases
                     cached = eng._infer_graphs.get(gkey)
                     if cached is None:
                         torch.cuda.synchronize()

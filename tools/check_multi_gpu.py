@@ -49,9 +49,16 @@ for name, glob in (("local-dice / averaged", False), ("global-dice / summed", Tr
     else:
         parts = [grads_of(ref_fn, x_all[2 * r:2 * r + 2], y_all[2 * r:2 * r + 2]) for r in range(world)]
         ref = {n: sum(p[n] for p in parts) / world for n in parts[0]}
-    worst = max(rel(got[n], ref[n]) for n in ref if not (n.endswith("bias") and ("conv1" in n or "conv2" in n)))
+    errs = sorted(((rel(got[n], ref[n]), n) for n in ref if not (n.endswith("bias") and ("conv1" in n or "conv2" in n))),
+                  reverse=True)
+    worst = errs[0][0]
+    if rank == 0 and worst > 1e-4:        # diagnostics: a uniform scale error, or noise?
+        for e, n in errs[:4]:
+            a, b = got[n].double().flatten(), ref[n].double().flatten()
+            print(f"    {n}: rel {e:.2e}, |got|/|ref| {float(a.norm() / b.norm()):.6f}, cosine {float(a @ b / (a.norm() * b.norm())):.8f}, "
+                  f"elements differing by > 1e-3 relative: {int(((a - b).abs() > 1e-3 * b.abs().max()).sum())} of {a.numel()}")
     if rank == 0:
-        print(f"{name}: worst per-tensor rel-L2 vs the single-process reference {worst:.2e}")
+        print(f"{name}: worst per-tensor rel-L2 vs the single-process reference {worst:.2e} ({errs[0][1]}; next {errs[1][0]:.1e} {errs[1][1]})")
     ok = ok and worst < 2e-2
 # BatchNorm variant: SyncBN (statistics of the global batch) + global-batch Dice + summed gradients must equal ONE process
 # on the concatenated batch, running statistics included; without SyncBN the two differ (per-rank statistics)

@@ -80,7 +80,16 @@ bn.load_state_dict(sd0)
 bn.zero_grad(set_to_none=True)
 unet3d_b200.DiceLoss()(bn(x_all), y_all).backward()
 ref = {n: p.grad.detach().clone() for n, p in bn.named_parameters() if p.grad is not None}
-worst = max(rel(got[n], ref[n]) for n in ref if ref[n].norm() > 1e-6 * max(r.norm() for r in ref.values()))
+# conv biases in front of a training-mode BatchNorm have a mathematically zero gradient (the batch mean absorbs them): what
+# is computed is the rounding noise of a sum of 16-bit values, ~1e-3 of the real gradients, with a relative error of ~1
+# between any two runs (tools/det_probe_bn.py shows it for ONE process computing the same batch twice).  They are the
+# conv1 / conv2 biases of the residual blocks (the transposed conv's bias is NOT cancelled: the zero pad planes inserted
+# between it and the norm do not carry it); checked for smallness only.
+import re
+big = max(r.norm() for r in ref.values())
+zero_grad = [n for n in ref if re.search(r"(conv1|conv2)\.bias$", n)]
+assert all(got[n].norm() < 1e-2 * big and ref[n].norm() < 1e-2 * big for n in zero_grad), "BatchNorm-cancelled bias gradients are not small"
+worst = max(rel(got[n], ref[n]) for n in ref if n not in zero_grad)
 worst_buf = max(rel(got_buf[n].double(), b.detach().double()) for n, b in bn.named_buffers() if b.dtype.is_floating_point)
 if rank == 0:
     print(f"SyncBN + global-dice / summed: worst per-tensor gradient rel-L2 vs one process on the whole batch {worst:.2e}, "

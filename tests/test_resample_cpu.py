@@ -118,3 +118,28 @@ def test_oracle_merge_regions_semantics():
     assert out[0, 1, 0] == preds[0][1][2, 0, 0].argmax()               # box starts at -2: region voxel 2 lands on voxel 0
     one = R.merge_regions((10, 8, 6), 1, [(b, p[..., :1]) for b, p in preds])
     assert set(np.unique(one)) <= {0, 1}
+
+
+def test_crop_pad_to_bbox_and_translate_match_oracle():
+    """Host-side index math of regions_crop_case (transform.py:422-437, data.py:68-71): numpy path of the product helper
+    against the oracle's restatement, boxes partly and fully outside the volume included."""
+    rng = np.random.RandomState(11)
+    vol = rng.randn(9, 7, 5, 2).astype(np.float32)
+    lab = rng.randint(0, 3, (9, 7, 5)).astype(np.uint8)
+    for _ in range(50):
+        lo = [int(rng.randint(-6, s + 2)) for s in lab.shape]
+        bbox = np.array([[l, l + int(rng.randint(1, 9))] for l in lo])
+        got = unet3d_b200.crop_pad_to_bbox(lab, bbox)
+        assert got.dtype == lab.dtype and got.shape == tuple(b[1] - b[0] for b in bbox)
+        inside = all(min(b[1], s) > max(b[0], 0) for b, s in zip(bbox, lab.shape))
+        if inside:                                  # the reference (np.pad of an empty crop) is only defined for overlapping boxes
+            assert np.array_equal(got, R.crop_pad_to_bbox(lab, bbox))
+            bbox_c = np.concatenate([bbox, [[0, 2]]])
+            assert np.array_equal(unet3d_b200.crop_pad_to_bbox(vol, bbox_c), R.crop_pad_to_bbox(vol, bbox_c))
+        else:
+            assert not got.any()
+    A = np.diag([0.8, 1.2, 2.5, 1.0])
+    A[:3, 3] = [4.0, -2.0, 7.5]
+    assert np.allclose(unet3d_b200.apply_translate(A, [1.0, 2.0, -3.0]), R.apply_translate(A, [1.0, 2.0, -3.0]))
+    t = unet3d_b200.transform.normalize_table({"mean": 101.5, "std": 76.25, "pct_00_5": -79.0, "pct_99_5": 304.0})
+    assert t == [(np.float32(-79.0), np.float32(304.0), np.float32(101.5), np.float32(76.25 + 1e-8))]

@@ -243,6 +243,8 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
                         g = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g):
                             g_out = model(g_in)
+                        for stale in [k for k in eng._infer_graphs if k[:-1] == gkey[:-1]]:
+                            del eng._infer_graphs[stale]         # same shape, older bias epoch: its memory pool goes too
                         cached = eng._infer_graphs[gkey] = (g, g_in, g_out)
                     graph, static_in_new, static_out = cached
                     static_in = static_in_new

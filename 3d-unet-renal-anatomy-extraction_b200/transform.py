@@ -73,6 +73,8 @@ def rescale_device(x: torch.Tensor, scale, is_label: bool = False, multi_class: 
             num_classes = int(x.max().item()) + 1          # np.unique(input).max() + 1, transform.py:50
     if is_label and num_classes >= 3:
         dst = torch.empty(oshape, dtype=torch.uint8, device=x.device) if out is None else out
+        if tuple(dst.shape) != oshape:
+            raise ValueError(f"out has shape {tuple(dst.shape)}, the zoomed volume is {oshape}")
         ops.zoom_label(x, dst)
         return dst
     if out is None:

@@ -70,13 +70,13 @@ int encode_src(CUtensorMap* m, const unet3d_src& s, int bw, int bh, int chans = 
   return U3D_OK;
 }
 
-int g_num_sms = 0;
+int g_num_sms[64] = {};      // per device ordinal (one process may drive several GPUs)
 int num_sms() {
-  if (g_num_sms > 0) return g_num_sms;
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev >= 0 && dev < 64 && g_num_sms[dev] > 0) return g_num_sms[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  g_num_sms = n;
+  if (dev >= 0 && dev < 64) g_num_sms[dev] = n;
   return n;
 }
 

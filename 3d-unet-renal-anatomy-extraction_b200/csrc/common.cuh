@@ -13,6 +13,16 @@ namespace u3d {
 
 typedef __nv_bfloat16 bf16;
 
+// cudaFuncSetAttribute is PER DEVICE: a process that drives several GPUs must set the opt-in shared-memory size on
+// each of them (a per-process flag gives a launch failure on the second device).  `done` is one flag per device ordinal.
+inline bool first_use_on_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 // error codes: U3D_OK / U3D_ERR_* from the public header
 // ---- smem / mbarrier ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

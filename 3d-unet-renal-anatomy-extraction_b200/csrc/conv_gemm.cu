@@ -607,11 +607,10 @@ int conv_gemm_launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
     return U3D_ERR_INVALID;
   const size_t smem = conv_gemm_smem_bytes(p.Dt, p.G, p.nblk, p.fuse, p.wT, p.w_stages, p.a_stages);
   if (smem > 227 * 1024) return U3D_ERR_INVALID;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return U3D_ERR_CUDA;
-    attr_set = true;
   }
   const int grid = p.n_work < num_sms ? p.n_work : num_sms;
   conv_gemm_kernel<<<grid, CG_THREADS, smem, stream>>>(p);

@@ -1445,11 +1445,10 @@ int stem_wgrad(const float* x, const bf16* dy, float* dw, int N, int D, int H, i
 #define U3D_SW(CPV)                                                                                          \
   do {                                                                                                       \
     constexpr int smem = 8 * 2 * 16 * (CPV * 2 + 16) + 8 * 2 * 10 * STEM_XP * 4 + 32 * CPV * 4;                   \
-    static bool attr = false;                                                                                \
-    if (!attr) {                                                                                             \
+    static bool attr[64] = {};                                                                               \
+    if (first_use_on_device(attr)) {                                                                         \
       cudaFuncSetAttribute(stem_wgrad_mma_kernel<CPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
       cudaFuncSetAttribute(stem_wgrad_mma_kernel<CPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-      attr = true;                                                                                           \
     }                                                                                                        \
     if (af) stem_wgrad_mma_kernel<CPV, true><<<g, 256, smem, s>>>(x, dy, dw, N, D, H, W, x_sN);              \
     else stem_wgrad_mma_kernel<CPV, false><<<g, 256, smem, s>>>(x, dy, dw, N, D, H, W, x_sN);                \

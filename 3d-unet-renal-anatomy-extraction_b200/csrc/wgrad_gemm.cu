@@ -212,11 +212,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
 }  // namespace
 
 int wgrad_gemm_launch(const WgradParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return U3D_ERR_CUDA;
-    attr_set = true;
   }
   // shared memory is sized for the largest stage any job can ask for; the host plan keeps
   // 2 * (Px*Gx*2944 + Dt*Gy*2048) + 2 KiB under the 227 KiB limit.

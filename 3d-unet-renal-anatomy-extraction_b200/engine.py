@@ -66,6 +66,11 @@ class UNetEngine:
         self._inv_scale = None
         self._last_was_train = True      # the first forward always packs
         self.grad_chunk_hook = None      # callable(flat prefix tensor) -> handle; set by parallel.overlap_gradient_all_reduce
+        # tests only (teacher-forced block parity, tests/test_block_parity_gpu.py): when a list, every block of the
+        # backward pass appends the tensors it consumed and produced; `capture_scale` is the fp16 gradient scale
+        self.capture = None
+        self.capture_scale = None
+        self._cap_drop = {}
         self._reset_caches()
 
     def _reset_caches(self):
@@ -483,6 +488,8 @@ class UNetEngine:
         c1 = self._op(key + ("conv1",), "conv", 3, blk.stride, in_C, blk.out_channels, grid, skip_k1=blk.uses_skip_conv)
         c2 = self._op(key + ("conv2",), "conv", 3, 1, [blk.out_channels], blk.out_channels, grid)
         drop = self._drop_scale(n, blk.out_channels, blk.dropout_p) if (train and blk.dropout_p > 0) else None
+        if self.capture is not None:
+            self._cap_drop[key] = drop
         # conv biases directly followed by InstanceNorm(affine=False) cancel exactly: not applied.
         # In front of BatchNorm they shift the running mean (and count in eval mode): applied.
         bn = isinstance(blk.norm, torch.nn.BatchNorm3d)
@@ -660,7 +667,7 @@ class UNetEngine:
         grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias) if b2 is None else self._unscale(ds2[:co].float())
         da1 = self._grad_like(a1)
         ops.conv_gemm(c2.dgrad, [dy2], self._pw(c2.dgrad, blk.conv2.weight), [da1], c2.grid)
-        _, dy1, _, ds1 = self._norm_bwd(b1, da1, None, a1, False, y1, t1, grads)
+        g1, dy1, _, ds1 = self._norm_bwd(b1, da1, None, a1, False, y1, t1, grads)
         grads[blk.conv1.weight] = self._wgrad(c1, inputs, dy1, blk.conv1.weight)
         grads[blk.conv1.bias] = torch.zeros_like(blk.conv1.bias) if b1 is None else self._unscale(ds1[:co].float())
         dins = [self._grad_like(t) for t in inputs]
@@ -674,6 +681,11 @@ class UNetEngine:
         else:
             ops.conv_gemm(c1.dgrad, [dy1], self._pw(c1.dgrad, blk.conv1.weight), dins, c1.grid,
                           addends=[g2])
+        if self.capture is not None:
+            self.capture.append(dict(kind="res", key=key, blk=blk, inputs=inputs, in_C=in_C, dout=dout, dout2=dout2,
+                                     dins=dins, drop=self._cap_drop.get(key),
+                                     fwd=dict(y1=y1, a1=a1, y2=y2, out=out), tab=dict(t1=t1, t2=t2),
+                                     bwd=dict(g2=g2, dy2=dy2, da1=da1, g1=g1, dy1=dy1)))
         return dins
 
     def _conv_block_bwd(self, blk, key, rec, dout, dout2, grads):
@@ -711,13 +723,22 @@ class UNetEngine:
         d_cur = self._grad_like(a_last)
         dwf = torch.zeros(K * wf.shape[1] + K, device=self.device)
         ops.head_bwd(dlogits.contiguous(), a_last, wf, d_cur, dwf, gscale)
+        if self.capture is not None:
+            self.capture_scale = gscale
+            self.capture.append(dict(kind="head", key=("head",), a=a_last, dlogits=dlogits, din=d_cur))
         grads[net.fc.weight] = dwf[:K * wf.shape[1]].view(K, wf.shape[1])[:, :cl].reshape(net.fc.weight.shape)
         grads[net.fc.bias] = dwf[K * wf.shape[1]:].clone()
         pending = {}
         for i in range(np_):
             d_up, d_skip = self._block_bwd(net.decode_blocks[i], ("dec", i), tape[("dec", i)], d_cur, None, grads)
             if ("att", i) in tape:
+                d_up0, d_gated = d_up, d_skip
                 d_up, d_skip = self._att_bwd(net.up_blocks[i].att_gate, i, tape[("att", i)], d_up, d_skip, grads)
+                if self.capture is not None:
+                    self.capture.append(dict(kind="att", key=("att", i), gate=net.up_blocks[i].att_gate,
+                                             skip=tape[("att", i)][0], au=tape[("att", i)][1], d_up_in=d_up0,
+                                             dout=d_gated, dup=d_up, dskip=d_skip,
+                                             fwd=dict(zip(("xs", "f", "z"), tape[("att", i)][2:5]))))
             pending[i] = d_skip
             xin, yu, tu, au, bu = tape[("up", i)]
             ct = net.up_blocks[i].conv_trans.up[0]
@@ -727,6 +748,9 @@ class UNetEngine:
             grads[ct.bias] = self._unscale(dsum[:ct.out_channels].float())
             d_cur = self._grad_like(xin)
             ops.conv_gemm(uop.dgrad, [dyu], self._pw(uop.dgrad, ct.weight), [d_cur], uop.grid)
+            if self.capture is not None:
+                self.capture.append(dict(kind="up", key=("up", i), ct=ct, xin=xin, dout=d_up, din=d_cur,
+                                         fwd=dict(y=yu, a=au), tab=dict(t=tu)))
         d_cur = self._block_bwd(net.encode_blocks[np_], ("enc", np_), tape[("enc", np_)], d_cur, None, grads)[0]
         for i in range(np_ - 1, -1, -1):
             d_cur = self._block_bwd(net.pool_blocks[i], ("pool", i), tape[("pool", i)], d_cur, None, grads)[0]
@@ -737,6 +761,8 @@ class UNetEngine:
         cin = net.conv.in_channels
         dw0 = torch.zeros(cin, 28, cp0, device=self.device)
         ops.stem_wgrad(tape["x"], d_cur, dw0)
+        if self.capture is not None:
+            self.capture.append(dict(kind="stem", key=("stem",), x=tape["x"], dout=d_cur))
         grads[net.conv.weight] = self._unscale(dw0[:, :27, :c0].permute(2, 0, 1).reshape(net.conv.weight.shape))
         grads[net.conv.bias] = self._unscale(dw0[0, 27, :c0].clone())
         self._finish_wgrads()

@@ -50,6 +50,11 @@ def paired_features2(num_pool: int, num_features: int) -> List[List[int]]:
     return down + bottom + up
 
 
+# network.py:18-22: down + bottom + up widths of ResAttrUnet3D2
+ATTR2_FEATURES = ([[30, 30], [60, 60], [120, 120], [240, 240], [320, 320]] + [[320, 320]] +
+                  [[320, 320], [240, 240], [120, 120], [60, 60], [30, 30]])
+
+
 class DropoutMasks:
     """Source of Dropout3d channel masks (network.py:159-160,382-383,412-413).
 
@@ -168,7 +173,8 @@ def up_concat(sd, pre, x, skip, attention: bool = False) -> Tensor:
 
 
 def resunet3d_forward(sd: Dict[str, Tensor], x: Tensor, num_pool: int = 4, num_features: int = 30,
-                      masks: Optional[DropoutMasks] = None, attention: bool = False, bn_train: bool = False) -> Tensor:
+                      masks: Optional[DropoutMasks] = None, attention: bool = False, bn_train: bool = False,
+                      pf: Optional[List[List[int]]] = None) -> Tensor:
     """network.py:104-132 (ResUnet3D) over network.py:549-565 (Unet.forward).
 
     A state dict with ``...norm.weight`` / ``...up.2.weight`` tensors selects the BatchNorm3d variant
@@ -177,13 +183,16 @@ def resunet3d_forward(sd: Dict[str, Tensor], x: Tensor, num_pool: int = 4, num_f
 
     encode level L = ResBlockStack with max(L,1) blocks (network.py:116-118); pooling is a
     stride-2 ResBlock (network.py:125-126); decode = ResBlock(2f -> f) (network.py:523-527).
-    ``attention=True`` gives ResAttrUnet3D (network.py:72-101).
+    ``attention=True`` gives ResAttrUnet3D (network.py:72-101); an explicit ``pf`` (list of channel pairs) gives the
+    nets with hand-written widths: ResAttrUnet3D2 (network.py:6-35) = ``pf=ATTR2_FEATURES, attention=True``.
     """
     global BN_TRAIN
     BN_TRAIN = bool(bn_train)
     masks = masks or DropoutMasks(train=False)
-    pf = paired_features(num_pool, num_features)
+    if pf is None:
+        pf = paired_features(num_pool, num_features)
     npairs = len(pf)
+    num_pool = npairs // 2
     x = F.conv3d(x, sd["net.conv.weight"], sd["net.conv.bias"], padding=1)   # network.py:550, no norm
     skips = []
     for i in range(num_pool):

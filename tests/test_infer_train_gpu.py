@@ -35,7 +35,10 @@ def test_predict_per_patch_matches_reference_golden(golden_dir):
     net = _ToyNet(torch.from_numpy(z["w"]), torch.from_numpy(z["b"])).to(DEV)
     lab = unet3d_b200.predict_per_patch(z["vol"], net, 3, (16, 24, 16), 2, verbose=False)
     assert lab.dtype == np.uint8 and lab.shape == z["labels"].shape
-    assert (lab != z["labels"]).mean() < 1e-4          # argmax of fp32 sums: ties aside, bit-exact
+    # BIT-EXACT label map (north_star: "label maps bit-exact").  The toy conv runs in fp32 on cuDNN here and on the CPU in
+    # the reference; the smallest class margin of the fixture's blended probabilities is 2.8e-6, ~30x the fp32 rounding
+    # of a 27-tap conv + softmax, so no voxel is allowed to differ
+    assert np.array_equal(lab, z["labels"]), int((lab != z["labels"]).sum())
     prob = unet3d_b200.predict_per_patch(z["vol"], net, 3, (16, 24, 16), 2, verbose=False, one_hot=True)
     assert np.array_equal(np.isnan(prob), np.isnan(z["probs"]))
     assert np.allclose(np.nan_to_num(prob), np.nan_to_num(z["probs"]), atol=2e-6)

@@ -213,3 +213,52 @@ def test_bf16_storage_model_of_the_oracle(golden_dir):
     assert rel(exact) < 1e-5
     assert 2e-3 < rel(bf) < 3e-2          # bf16 storage: ~1.7e-2 on this net
     assert rel(fp16) < 4e-3               # fp16 storage: ~2e-3
+
+
+def test_trained_weights_golden_and_storage_models(golden_dir):
+    """Trained weights (tests/golden/make_golden_trained.py: the LIVE reference trained for 400 steps on the phantom):
+    the oracle reproduces the reference's logits; the 16-bit storage models of the oracle (what the CUDA path keeps in
+    16 bit) stay inside the north-star bars on these weights in bf16 and fp16 -- the CPU-side statement of
+    tests/test_trained_parity_gpu.py."""
+    from oracle import bf16_model as Q
+    z = _load(golden_dir, "trained_resunet.npz")
+    sd = _sd(z)
+    x, y, ref = torch.from_numpy(z["x"]), torch.from_numpy(z["y"]).long(), torch.from_numpy(z["logits"])
+    npool, nf = int(z["num_pool"]), int(z["num_features"])
+    logits = O.resunet3d_forward(sd, x, npool, nf)
+    assert torch.allclose(logits, ref, rtol=1e-4, atol=1e-5)
+    assert abs(O.dice_loss(logits, y).item() - float(z["dice_loss"])) < 1e-5
+    for dt in (torch.bfloat16, torch.float16):
+        q = Q.resunet3d_forward(sd, x, npool, nf, dtype=dt)
+        assert ((q - ref).norm() / ref.norm()).item() <= 1e-2
+        assert (q.argmax(1) == ref.argmax(1)).float().mean().item() >= 0.999
+        assert (O.dice_per_class(q, y) - O.dice_per_class(ref, y)).abs().max().item() <= 1e-3
+
+
+def test_attr2_net_golden(golden_dir):
+    """ResAttrUnet3D2 (network.py:6-35; five poolings, 320-wide bottom, attention gates): the oracle with the explicit
+    width list reproduces the live reference's logits, loss and gradients (tests/golden/make_golden_attr2.py)."""
+    import unet3d_b200
+    z = _load(golden_dir, "attr2_64.npz")
+    torch.manual_seed(int(z["weight_seed"]))
+    m = unet3d_b200.ResAttrUnet3D2(in_channels=1, out_channels=3)
+    names = [k for k, _ in m.named_parameters()]
+    assert names == z["names"].tolist()
+    assert np.allclose([float(p.detach().double().sum()) for _, p in m.named_parameters()], z["weight_sum"], rtol=1e-9)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    x = torch.randn(1, 1, 64, 64, 64, generator=torch.Generator().manual_seed(int(z["x_seed"])))
+    from tests.golden.make_golden import blocky_labels
+    y = torch.from_numpy(blocky_labels((1, 64, 64, 64), int(z["label_seed"])))
+    logits = O.resunet3d_forward(sd, x, attention=True, pf=O.ATTR2_FEATURES)
+    assert torch.allclose(logits[:, :, ::2, ::2, ::2], torch.from_numpy(z["logits_sub"]), rtol=1e-3, atol=1e-4)
+    loss = O.dice_loss(logits, y)
+    assert abs(loss.item() - float(z["loss"])) < 1e-5
+    loss.backward()
+    unused = set(z["unused"].tolist())
+    for i, k in enumerate(names):
+        if k in unused:
+            assert sd[k].grad is None
+        elif not (k.endswith("bias") and ("conv1" in k or "conv2" in k)):
+            assert abs(float(sd[k].grad.double().norm()) - z["grad_norm"][i]) <= 2e-3 * z["grad_norm"][i] + 1e-9, k
+    assert torch.allclose(sd["net.up_blocks.0.att_gate.conv.weight"].grad, torch.from_numpy(z["grad_att0_w"]),
+                          rtol=2e-3, atol=1e-7)

@@ -181,3 +181,58 @@ def test_batchnorm_variant_vs_reference(golden_dir, precision):
                     got = model.state_dict()[k[6:]].float().cpu()
                     ref = torch.from_numpy(z[k]).float()
                     assert torch.allclose(got, ref, rtol=2e-2, atol=2e-3), k
+
+
+def test_attr2_net_vs_reference(golden_dir):
+    """ResAttrUnet3D2 (network.py:6-35): five poolings, widths 30/60/120/240/320/320 (a 320 -> 320 stride-2 pooling block
+    with its skip conv, a 640 -> 320 decoder), attention gates on every level.  Weights by seed (the parameter order is
+    the reference's), one 1 x 64^3 patch, fp16 storage.
+
+    This randomly initialised net is ill-conditioned at 64^3 (InstanceNorm over the 8 voxels of its 2^3 bottom grid, six
+    levels deep, gates on top): the oracle's own 16-bit storage model moves the logits by 4.4e-2 in fp16 and 2.5e-1 in
+    bf16 (tests/test_oracle_golden.py pins the oracle to the live reference's fixture), and two 16-bit realisations of
+    it differ from each other by as much (3.5e-2 measured between the CUDA path and that storage model).  So here the
+    logits are held to the live reference at the bar the storage model predicts (6e-2), the loss to 5e-3 and the
+    decoder-level gradients to the fixture; the tight statement for this net is block-wise:
+    tests/test_block_parity_gpu.py::test_attr2_net_every_block (every forward stage 4e-3, every gradient 1e-2)."""
+    from oracle import unet3d_oracle as O
+    from oracle import bf16_model as Q
+    z = np.load(os.path.join(golden_dir, "attr2_64.npz"))
+    torch.manual_seed(int(z["weight_seed"]))
+    model = unet3d_b200.ResAttrUnet3D2(in_channels=1, out_channels=3)
+    assert np.allclose([float(p.detach().double().sum()) for _, p in model.named_parameters()], z["weight_sum"], rtol=1e-9)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    model.precision = "fp16"
+    from tests.golden.make_golden import blocky_labels
+    xc = torch.randn(1, 1, 64, 64, 64, generator=torch.Generator().manual_seed(int(z["x_seed"])))
+    x = xc.to(DEV)
+    y = torch.from_numpy(blocky_labels((1, 64, 64, 64), int(z["label_seed"]))).to(DEV)
+    logits = model(x)
+    loss = unet3d_b200.DiceLoss()(logits, y)
+    loss.backward()
+    torch.cuda.synchronize()
+    ops.check_device_errors()
+    got_full = logits.detach().cpu()
+    with torch.no_grad():
+        emu = Q.resunet3d_forward(sd, xc, dtype=torch.float16, attention=True, pf=O.ATTR2_FEATURES)
+    r_emu = rel(got_full, emu)
+    ref = torch.from_numpy(z["logits_sub"])
+    got = got_full[:, :, ::2, ::2, ::2]
+    r = rel(got, ref)
+    agree = (got.argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"[ResAttrUnet3D2 fp16] logits rel-L2 {r_emu:.3e} vs the 16-bit-storage oracle, {r:.3e} vs the live reference "
+          f"(storage model: {rel(emu[:, :, ::2, ::2, ::2], ref):.3e}), argmax agreement {agree:.5f}, "
+          f"loss {loss.item():.6f} vs {float(z['loss']):.6f}")
+    assert r_emu < 6e-2 and r < 6e-2 and agree >= 0.98
+    assert abs(loss.item() - float(z["loss"])) < 5e-3
+    unused = set(z["unused"].tolist())
+    names = z["names"].tolist()
+    params = dict(model.named_parameters())
+    for k in names:
+        assert (params[k].grad is None) == (k in unused), k
+    for key, name in (("grad_fc_w", "net.fc.weight"), ("grad_att0_w", "net.up_blocks.0.att_gate.conv.weight"),
+                      ("grad_att0_b", "net.up_blocks.0.att_gate.conv.bias")):
+        rr = rel(params[name].grad.detach().cpu(), torch.from_numpy(z[key]))
+        print(f"   grad rel-L2 {rr:.3e}  {name}")
+        assert rr < 0.15, (name, rr)         # decoder-level-0 tensors behind the ill-conditioned forward (see above)

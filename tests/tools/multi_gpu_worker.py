@@ -6,9 +6,10 @@ label agreement), and the two data-parallel loss modes:
   (ii) global_batch=True   : per-class sums all-reduced inside the loss, gradients SUMMED == the gradient of ONE process
                              on the concatenated batch (exact large-batch equivalence).
 
-Both references are computed by rank 0 alone on the same weights.  python -m torch.distributed.run --nproc-per-node 2 tools/check_multi_gpu.py"""
+Both references are computed by every rank alone on the same weights.  Launched by tests/test_multi_gpu.py:
+python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/tools/multi_gpu_worker.py"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 import unet3d_b200

@@ -117,6 +117,15 @@ class UNetEngine:
             self._infer_sig = self._param_signature()
         return logits
 
+    def invalidate_weights(self):
+        """Call after changing parameters IN PLACE behind autograd's back between two no-grad forwards (``p.data.copy_``,
+        EMA / SWA averaging, a fused or foreach optimizer step without a training forward in between): tensor version
+        counters do not see those writes, so the cached 16-bit weight packs and the captured inference graphs would be
+        stale.  ``load_state_dict`` and ``parallel.broadcast_parameters`` call it themselves."""
+        ops.PACK_EPOCH += 1
+        self._infer_sig = None
+        self._infer_graphs = {}
+
     def _param_signature(self):
         return (ops.PACK_EPOCH, self.act_dtype, self.owner.training,
                 tuple((p.data_ptr(), p._version) for p in self.net.parameters()),

@@ -39,6 +39,8 @@ class GraphedTrainStep:
         self._side = None
         self.graph_opt = None
         self.launches_per_replay = 0
+        self.replayed = False           # whether the most recent call replayed the graph (False: it ran eagerly)
+        self.last_label = None          # the label tensor the most recent call computed its loss against
         self._static_grads, self._static_flats = [], []
         _make_capturable(optimizer)
 
@@ -68,8 +70,12 @@ class GraphedTrainStep:
         self.calls += 1
         world = parallel.rank_world()[1]
         split = world > 1 and self.allreduce
+        self.replayed = False
         if self.key is not None and key != self.key:
-            return self._eager(image.to(dev, non_blocking=True), label.to(dev, non_blocking=True))
+            # another batch shape (a short last batch) or mode (first train batch after a validation pass): eager, and
+            # the caller must compare the logits with THIS label tensor, not with the graph's static one
+            self.last_label = label.to(dev, non_blocking=True)
+            return self._eager(image.to(dev, non_blocking=True), self.last_label)
         if self.calls <= self.warmup:
             # warm-up steps run on a side stream: autograd's AccumulateGrad nodes are then not tied to the legacy
             # default stream, which a capturing stream may not synchronise with (cudaErrorStreamCaptureImplicit)
@@ -77,7 +83,8 @@ class GraphedTrainStep:
                 self._side = torch.cuda.Stream(device=dev)
             self._side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(self._side):
-                out = self._eager(image.to(dev, non_blocking=True), label.to(dev, non_blocking=True))
+                self.last_label = label.to(dev, non_blocking=True)
+                out = self._eager(image.to(dev, non_blocking=True), self.last_label)
             torch.cuda.current_stream(dev).wait_stream(self._side)
             return out
         if self.graph is None:
@@ -114,6 +121,7 @@ class GraphedTrainStep:
             p.grad = g
         for eng, flats in self._static_flats:
             eng._last_gflat = flats
+        self.replayed, self.last_label = True, self.static_label
         self.graph.replay()
         if split:
             parallel.all_reduce_gradients(self.model)

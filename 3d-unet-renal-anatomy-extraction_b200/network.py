@@ -232,6 +232,15 @@ class Unet(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._run(x, self)
 
+    def invalidate_weights(self):
+        """See engine.UNetEngine.invalidate_weights: call after in-place parameter writes autograd cannot see."""
+        if self._engine is not None:
+            self._engine.invalidate_weights()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_weights()          # load_state_dict copies into .data: the 16-bit packs are stale
+
     def _run(self, x, owner):
         if self._engine is None or self._engine.owner is not owner:
             self._engine = engine.UNetEngine(self, owner)
@@ -259,6 +268,11 @@ class _ResNetBase(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.net._run(x, self)
+
+    def invalidate_weights(self):
+        """Call after in-place parameter writes autograd cannot see (EMA / SWA, ``p.data.copy_``): drops the cached 16-bit
+        weight packs and captured inference graphs."""
+        self.net.invalidate_weights()
 
 
 class ResUnet3D(_ResNetBase):

@@ -41,6 +41,39 @@ def all_reduce_sum(tensors: Iterable[torch.Tensor]):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
 
+def broadcast_object(obj, src: int = 0):
+    """`obj` of rank `src` on every rank (a picklable host object: index lists, small dicts).  Identity in a
+    single-process run."""
+    if rank_world()[1] == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def broadcast_parameters(model: torch.nn.Module, src: int = 0):
+    """Parameters and buffers of rank `src` on every rank (start of a data-parallel fit: the ranks may have been
+    initialised with different seeds).  In place; no-op in a single-process run."""
+    if rank_world()[1] == 1:
+        return
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=src)
+    for eng in _engines(model):
+        eng.invalidate_weights()
+
+
+def all_reduce_mean_results(sums: dict, count: int, device) -> dict:
+    """Epoch means over ALL ranks' steps: `sums` = per-key sums of this rank's step results, `count` = how many steps
+    they cover.  Every rank gets the same dict back, so schedulers / best-checkpoint logic stay in lock step."""
+    keys = sorted(sums)
+    t = torch.tensor([float(sums[k]) for k in keys] + [float(count)], dtype=torch.float64, device=device)
+    if rank_world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    n = max(float(t[-1].item()), 1.0)
+    return {k: float(t[i].item()) / n for i, k in enumerate(keys)}
+
+
 def gradient_buckets(params: List[torch.nn.Parameter], bucket_bytes: int = BUCKET_BYTES) -> List[List[torch.nn.Parameter]]:
     """Parameters that have a gradient, in reverse registration order (roughly the order backward
     produces them), cut into buckets of about `bucket_bytes`."""

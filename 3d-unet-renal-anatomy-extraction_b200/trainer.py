@@ -383,17 +383,18 @@ class DevicePrefetcher:
     pinned batches (the reference's DataLoader default, trainer.py:422) they run under the training step of batch i
     instead of in front of batch i+1.  Non-tensor entries pass through.
 
-    The device tensors are two alternating sets of staging buffers per (key, shape, dtype), kept per device for the life
-    of the process (no allocator traffic in the loop): a batch stays valid until the batch after the next one is
-    requested -- keep a ``.clone()`` if you need it longer."""
+    The device tensors are two alternating sets of staging buffers per (key, shape, dtype) owned by THIS prefetcher (no
+    allocator traffic in the loop; two live prefetchers never share staging memory): a batch stays valid until the
+    batch after the next one is requested -- keep a ``.clone()`` if you need it longer.  Pass ``buffers=`` (a dict) to
+    let several short-lived prefetchers of one owner (a Trainer's epochs) reuse the same staging sets."""
 
     _streams: Dict[torch.device, torch.cuda.Stream] = {}
-    _buffers: Dict[tuple, List[torch.Tensor]] = {}
 
-    def __init__(self, loader, device):
+    def __init__(self, loader, device, buffers: Optional[dict] = None):
         self.loader, self.device = loader, torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
+        self._buffers: Dict[tuple, List[torch.Tensor]] = {} if buffers is None else buffers
 
     def __len__(self):
         return len(self.loader)
@@ -465,6 +466,8 @@ class Trainer:
         order = list(range(len(dataset)))
         n_valid = int(np.floor(valid_split * len(dataset)))
         np.random.shuffle(order)
+        # data parallel: ONE train / valid split for the whole job (every process shuffles with its own RNG state)
+        order = parallel.broadcast_object(order)
         self.train_indices, self.valid_indices = order[n_valid:], order[:n_valid]
         self.dataloader_kwargs = {'batch_size': batch_size, **dataloader_kwargs}
         self.num_samples, self.valid_split = num_samples, valid_split
@@ -476,7 +479,12 @@ class Trainer:
         self.num_epochs, self.use_amp, self.save_dir, self.progress_bar = 1, False, None, None
         # optional (not in the reference): replay the whole training step as one CUDA graph
         self._graphed = None
+        self._staging = {}                  # DevicePrefetcher staging sets, reused across epochs
         if cuda_graph:
+            net = model.net if hasattr(model, "net") else model
+            if parallel.rank_world()[1] > 1 and (getattr(loss, "global_batch", False) or getattr(net, "sync_bn", False)):
+                raise ValueError("cuda_graph=True cannot be combined with global_batch losses or SyncBN: their "
+                                 "collectives are issued from Python between kernel launches and cannot be captured")
             from .graph import GraphedTrainStep
             self._graphed = GraphedTrainStep(model, loss, optimizer)
 
@@ -497,11 +505,13 @@ class Trainer:
         if bar is not None:
             bar.reset(len(data_loader))
             bar.set_description("Epoch %d/%d (LR %.2g)" % (self.current_epoch + 1, self.num_epochs, self.get_lr()))
-        batches = DevicePrefetcher(data_loader, self.device) if self.device.type == "cuda" else data_loader
+        batches = DevicePrefetcher(data_loader, self.device, self._staging) if self.device.type == "cuda" else data_loader
+        # global-batch losses all-reduce their partial sums themselves and need SUMMED gradients (SURVEY.md 8e mode ii)
+        average = not getattr(self.loss, 'global_batch', False)
         for batch in batches:
             if is_train and self._graphed is not None:
                 loss, y_pred = self._graphed(batch['image'], batch['label'])
-                y = self._graphed.static_label if self._graphed.graph is not None else batch['label'].to(self.device)
+                y = self._graphed.last_label        # the label tensor the step actually used (static under replay)
                 result = {'loss': loss.item()}
                 if self.metrics is not None:
                     with torch.no_grad():
@@ -526,7 +536,7 @@ class Trainer:
             if is_train:
                 self.optimizer.zero_grad()
                 loss.backward()
-                parallel.all_reduce_gradients(self.model)
+                parallel.all_reduce_gradients(self.model, average=average)
                 self.optimizer.step()
             result = {'loss': loss.item()}
             if self.metrics is not None:
@@ -539,7 +549,13 @@ class Trainer:
                 bar.set_postfix(result)
                 bar.update()
         ops.check_device_errors()
-        mean_result = {k: float(np.mean([r[k] for r in results])) for k in results[0]}
+        keys = list(results[0]) if results else ['loss'] + list(self.metrics or {})
+        if parallel.rank_world()[1] > 1:
+            # one epoch mean for the whole job: ReduceLROnPlateau and the best-checkpoint test must not diverge
+            mean_result = parallel.all_reduce_mean_results({k: sum(r[k] for r in results) for k in keys}, len(results),
+                                                           self.device)
+        else:
+            mean_result = {k: float(np.mean([r[k] for r in results])) for k in keys}
         if self.save_dir is not None and parallel.rank_world()[0] == 0:
             try:
                 from torch.utils.tensorboard import SummaryWriter
@@ -555,7 +571,12 @@ class Trainer:
         ds = _TransformedSubset(self.dataset, indices, transform)
         rank, world = parallel.rank_world()
         if world > 1:
-            ds = _TransformedSubset(ds, list(range(rank, len(ds), world)), None)     # shard cases over ranks
+            # shard the cases over the ranks with EQUAL lengths (the remainder of an indivisible count is dropped): a rank
+            # with one batch more would wait forever in its last gradient all-reduce
+            per = len(ds) // world
+            if per == 0:
+                raise ValueError(f"{len(ds)} cases cannot be sharded over {world} ranks")
+            ds = _TransformedSubset(ds, list(range(rank, per * world, world)), None)
         if n_samples is not None:
             sampler = torch.utils.data.RandomSampler(ds, True, max(1, n_samples // world))
             return torch.utils.data.DataLoader(ds, sampler=sampler, **self.dataloader_kwargs)
@@ -565,10 +586,12 @@ class Trainer:
         from tqdm import tqdm
         self.num_epochs, self.use_amp, self.save_dir = num_epochs, use_amp, save_dir
         if use_amp and hasattr(self.model, "precision"):
-            # apex O1 in the reference = fp16 activations with fp32 master weights (trainer.py:538-542); the
-            # equivalent here is fp16 forward storage (gradients stay bf16, so no loss scaling is needed)
+            # apex O1 in the reference = fp16 activations with fp32 master weights and a dynamic loss scale
+            # (trainer.py:538-542); the equivalent here is fp16 storage of activations AND gradients with the engine's
+            # internal per-step power-of-two gradient scale (engine.backward_impl)
             self.model.precision = "fp16"
         self.progress_bar = tqdm(total=0, disable=parallel.rank_world()[0] != 0)
+        parallel.broadcast_parameters(self.model)          # data parallel: every rank starts from rank 0's weights
         train_loader = self._loader(self.train_indices, self.train_transform, self.num_samples, True)
         valid_loader = None
         if len(self.valid_indices) > 0:
@@ -602,8 +625,22 @@ class Trainer:
             ckpt['scheduler_state_dict'] = self.scheduler.state_dict()
         torch.save(ckpt, file_path)
 
-    def load_checkpoint(self, file_path):
-        ckpt = torch.load(file_path, map_location=self.device, weights_only=False)   # reference files hold numpy scalars
+    def load_checkpoint(self, file_path, allow_pickle=True):
+        """trainer.py:621-634.  The file is first read with ``weights_only=True`` plus an allow-list for the numpy scalars
+        the reference stores in ``best_result``; only if that fails (and ``allow_pickle`` is left on -- checkpoints
+        from untrusted sources should be loaded with ``allow_pickle=False``) with the unrestricted unpickler the
+        reference's ``torch.load`` used."""
+        try:
+            safe = [np.dtype, np.float64, np.float32, np.int64]
+            core = getattr(np, "_core", None) or getattr(np, "core")
+            safe += [core.multiarray.scalar, core.multiarray._reconstruct, np.ndarray]
+            safe += [type(np.dtype(t)) for t in (np.float64, np.float32, np.int64)]
+            with torch.serialization.safe_globals(safe):
+                ckpt = torch.load(file_path, map_location=self.device, weights_only=True)
+        except Exception:
+            if not allow_pickle:
+                raise
+            ckpt = torch.load(file_path, map_location=self.device, weights_only=False)
         self.model.load_state_dict(ckpt['model_state_dict'])
         self.optimizer.load_state_dict(ckpt['optimizer_state_dict'])
         self.current_epoch = ckpt['current_epoch'] + 1

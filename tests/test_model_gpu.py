@@ -4,12 +4,18 @@ oracle with identical weights and inputs, in both precision modes.
 precision="fp16" (fp16 forward activations / weights, what apex O1 gave the reference; gradients bf16):
     the north-star tolerances -- logits rel-L2 <= 1e-2, argmax agreement >= 99.9 %, Dice within 1e-3.
 precision="bf16" (default; BASELINE.json's configs name bf16):
-    logits rel-L2 <= 3e-2, argmax >= 99.5 %, Dice within 2e-3.  The 1e-2 bar is NOT met with bf16 operands and
+    logits rel-L2 <= 3e-2, argmax >= 98.5 %, Dice within 2e-3 ON RANDOMLY INITIALISED NETS.  There the 1e-2 bar is NOT met with bf16 operands and
     cannot be: rounding only the weights to bf16 already costs 1.2e-2 on this randomly initialised network
     (oracle/bf16_model.py; DESIGN.md "Numerics").  The bf16-storage model of the oracle is printed alongside; it is
     not a tight reference either, because 1-ulp bf16 rounding flips decorrelate two implementations.
-Per-layer gradients vs the fp32 oracle: rel-L2 <= 8e-2 (bf16 gradient tensors through ~40 layers), absolute
-tolerance for the InstanceNorm-cancelled conv biases, grad None for the unused skip_conv tensors (S5)."""
+On TRAINED weights bf16 meets the north-star bars too (tests/test_trained_parity_gpu.py: 2.1e-3 / 99.997 % / 2e-5).
+
+Gradients: the per-layer statement with a tight tolerance is tests/test_block_parity_gpu.py (every block's backward
+against the oracle block on the CUDA run's own tensors, rel-L2 <= 1e-2).  A whole-net comparison against the fp32
+oracle cannot be tight on a 16-bit path (rounding flips LeakyReLU masks of near-zero units; ~40 layers of that
+decorrelate the encoder gradients), so here it is a sanity bound only: cosine of the full parameter gradient, every
+weight tensor's own cosine, exact zeros for the InstanceNorm-cancelled conv biases, grad None for the
+unused skip_conv tensors (S5)."""
 import pytest
 import torch
 
@@ -67,7 +73,7 @@ def _run(num_pool, nf, shape, seed=0, train=False, loss_kind="hybrid", precision
     return model, logits.detach().cpu(), loss.item(), sdr, ref_logits.detach(), ref_loss.item(), y, q_logits, precision
 
 
-def _check(model, logits, loss, sdr, ref_logits, ref_loss, y, q_logits, precision, grad_tol=8e-2, agree_floor=None):
+def _check(model, logits, loss, sdr, ref_logits, ref_loss, y, q_logits, precision, agree_floor=None):
     small = sum(p.numel() for p in model.parameters()) < 1e6      # tiny random nets have tiny logit margins
     tol, agree_min, dice_tol = (1e-2, 0.998 if small else 0.999, 1e-3) if precision == "fp16" else (3e-2, 0.985, 2e-3)
     if agree_floor is not None:
@@ -85,7 +91,8 @@ def _check(model, logits, loss, sdr, ref_logits, ref_loss, y, q_logits, precisio
     d2 = O.dice_per_class(ref_logits, y)
     assert (d1 - d2).abs().max().item() < dice_tol
     assert abs(loss - ref_loss) < 5e-3 * max(1.0, abs(ref_loss))
-    worst = []
+    dot = na = nb = 0.0
+    per_tensor = []
     for name, p in model.named_parameters():
         rg = sdr[name].grad
         if rg is None:
@@ -93,28 +100,30 @@ def _check(model, logits, loss, sdr, ref_logits, ref_loss, y, q_logits, precisio
             continue
         assert p.grad is not None, name
         gpu = p.grad.detach().cpu()
+        assert torch.isfinite(gpu).all(), name
         if name.endswith("bias") and ("conv1" in name or "conv2" in name):
             assert gpu.abs().max().item() < 1e-5 + 10 * rg.abs().max().item(), name     # S1: ~0 in the reference
             continue
-        r = rel(gpu, rg)
-        worst.append((r, name))
-    for r, name in worst:
-        print(f"   grad rel-L2 {r:.3e}  {name}")
-    # Deep nets: 16-bit forward rounding flips the LeakyReLU mask of near-zero units, and every flipped unit changes
-    # the gradient that flows through it; ~40 layers of that decorrelate the encoder gradients from the fp32 run
-    # (PyTorch's own autocast shows the same: tests/tools/amp_reference.py, DESIGN.md 'Numerics').  Shallow nets are tight.
-    n_layers = sum(1 for n, _ in model.named_parameters() if n.endswith("conv1.weight"))
-    if n_layers <= 3:
-        grad_tol = 0.06 if precision == "fp16" else 0.35
-    elif n_layers <= 8:
-        grad_tol = 0.15 if precision == "fp16" else 0.5
-    else:
-        grad_tol = 0.4 if precision == "fp16" else 0.9        # run-to-run spread (atomic order) seen: 0.27-0.30 fp16
-    bad = [(n, r) for r, n in worst if not r < grad_tol]
-    assert not bad, bad
-    return sorted(worst)[-3:]
+        a, b = gpu.double().reshape(-1), rg.double().reshape(-1)
+        dot, na, nb = dot + float(a @ b), na + float(a @ a), nb + float(b @ b)
+        if name.endswith("weight"):
+            per_tensor.append((float(a @ b) / max(float(a.norm() * b.norm()), 1e-300), rel(gpu, rg), name))
+    cos = dot / max((na * nb) ** 0.5, 1e-300)
+    per_tensor.sort()
+    for c, r, name in per_tensor[:4]:
+        print(f"   grad cosine {c:.4f} (rel-L2 {r:.3e})  {name}")
+    print(f"[{precision}] whole-net gradient cosine vs the fp32 oracle {cos:.5f}, |grad| ratio {(na / nb) ** 0.5:.4f}")
+    # sanity bounds.  Measured on a B200 over the nets of this file: whole-net cosine fp16 0.961 (6-level cfg-5 net) ..
+    # 0.9997, bf16 0.909 (default net) .. 0.997; worst single tensor 0.92 fp16 / 0.75 bf16.  The tight per-block
+    # statement is tests/test_block_parity_gpu.py
+    cos_min, tensor_min = COS_BARS[precision]
+    assert cos >= cos_min, cos
+    assert per_tensor[0][0] >= tensor_min, per_tensor[0]
+    assert 0.8 < (na / nb) ** 0.5 < 1.25
+    return per_tensor[:3]
 
 
+COS_BARS = {"fp16": (0.95, 0.85), "bf16": (0.85, 0.60)}
 PRECISIONS = ["bf16", "fp16"]
 
 

@@ -99,23 +99,28 @@ class UNetEngine:
         if D % (1 << np_) or H % (1 << np_) or W % (1 << np_):
             raise RuntimeError(f"spatial size {(D, H, W)} must be divisible by 2^num_pool = {1 << np_} "
                                f"(the reference fails in torch.cat, network.py:350)")
-        if self.device != x.device:
-            from . import _lib
-            self.device = x.device
-            self.num_sms = _lib.lib().unet3d_num_sms()
-            self._reset_caches()
         params = list(net.parameters())
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        if need_grad or self._last_was_train:
-            ops.PACK_EPOCH += 1          # an optimizer step may lie behind us: re-pack the weights (see ops.PACK_EPOCH)
-        self._last_was_train = need_grad
-        if need_grad:
-            return _UNetFn.apply(x, self, *params)
-        with torch.no_grad():
-            logits, _ = self.forward_impl(x.detach(), save=False)
-        if not torch.cuda.is_current_stream_capturing():
-            self._infer_sig = self._param_signature()
-        return logits
+        if any(p.device != x.device for p in params):
+            raise RuntimeError(f"input on {x.device}, parameters on {params[0].device}: move the model with .to(device)")
+        # every launch below goes to the CURRENT device's stream: make the tensors' device current for the duration
+        # (a model on cuda:1 must work without a prior torch.cuda.set_device(1), like the reference's PyTorch modules)
+        with torch.cuda.device(x.device):
+            if self.device != x.device:
+                from . import _lib
+                self.device = x.device
+                self.num_sms = _lib.lib().unet3d_num_sms()
+                self._reset_caches()
+            need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+            if need_grad or self._last_was_train:
+                ops.PACK_EPOCH += 1          # an optimizer step may lie behind us: re-pack the weights (see ops.PACK_EPOCH)
+            self._last_was_train = need_grad
+            if need_grad:
+                return _UNetFn.apply(x, self, *params)
+            with torch.no_grad():
+                logits, _ = self.forward_impl(x.detach(), save=False)
+            if not torch.cuda.is_current_stream_capturing():
+                self._infer_sig = self._param_signature()
+            return logits
 
     def invalidate_weights(self):
         """Call after changing parameters IN PLACE behind autograd's back between two no-grad forwards (``p.data.copy_``,
@@ -788,7 +793,8 @@ class _UNetFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits):
-        grads = ctx.eng.backward_impl(ctx.tape, ctx.x_shape, dlogits)
+        with torch.cuda.device(dlogits.device):
+            grads = ctx.eng.backward_impl(ctx.tape, ctx.x_shape, dlogits)
         ctx.tape = None
         out = [grads.get(p) if p.requires_grad else None for p in ctx.params]
         return (None, None, *out)

@@ -22,6 +22,11 @@ from . import ops
 
 
 _W_CACHE = {}
+# The kernels skip labels outside [0, C) silently where the reference's F.one_hot raises (loss.py:27).  Checking costs a
+# device synchronisation per loss call, so it is opt-in: set unet3d_b200.loss.CHECK_TARGET_RANGE = True while debugging
+# a data pipeline (or export U3D_CHECK_TARGETS=1).
+import os as _os
+CHECK_TARGET_RANGE = bool(_os.environ.get("U3D_CHECK_TARGETS"))
 
 
 def _class_weights(c: int, weight_v, device) -> torch.Tensor:
@@ -50,8 +55,13 @@ class _SegLossFn(torch.autograd.Function):
         if tg.dtype != torch.int64:
             tg = tg.long()
         v = lg[0, 0].numel()
+        if tg.device != lg.device:
+            raise RuntimeError(f"logits on {lg.device}, target on {tg.device}")
+        if CHECK_TARGET_RANGE and (int(tg.min()) < 0 or int(tg.max()) >= k):
+            raise RuntimeError(f"target labels must lie in [0, {k}) (F.one_hot raises here in the reference, loss.py:27)")
         sums = torch.zeros(k, 4, dtype=torch.float64, device=lg.device)
-        ops.loss_fwd(lg, tg, sums, gamma)
+        with torch.cuda.device(lg.device):           # launches go to the current device's stream
+            ops.loss_fwd(lg, tg, sums, gamma)
         if global_batch:
             # exact large-batch equivalence under data parallelism: the per-class sums of ALL ranks
             # enter the (nonlinear) Dice ratio, so every rank's logits gradient is the gradient of the one global loss
@@ -88,7 +98,8 @@ class _SegLossFn(torch.autograd.Function):
     def backward(ctx, gout):
         lg, tg, coef = ctx.saved_tensors
         dl = torch.empty_like(lg)
-        ops.loss_bwd(lg, tg, coef, gout.detach().float().contiguous().view(1), dl, ctx.gamma, ctx.use_focal)
+        with torch.cuda.device(lg.device):
+            ops.loss_bwd(lg, tg, coef, gout.detach().float().contiguous().view(1), dl, ctx.gamma, ctx.use_focal)
         return dl, None, None, None, None, None, None, None, None
 
 

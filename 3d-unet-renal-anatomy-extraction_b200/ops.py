@@ -29,6 +29,16 @@ LAUNCHES = 0
 PACK_EPOCH = 0
 BIAS_EPOCH = 0          # bumped whenever a plan's packed bias vector is re-created (BatchNorm variant: conv biases are applied)
 DBG_OUT = None          # tuning experiments: int64[8] device tensor receiving the conv MMA warp's cycle counters
+# bench.py instrumentation: padded -> real channel count of the benchmarked net ({32: 30, 64: 60, 128: 120} for the
+# default ResUnet3D).  SURVEY.md 8d makes UNPADDED channels the algorithmic figure, so the HBM-kernel byte counts that
+# go with PROFILE are scaled by real / padded channels when the map knows the width (padding is overhead, not credit).
+REAL_CHANNELS: Dict[int, int] = {}
+
+
+def _alg_numel(t: torch.Tensor) -> float:
+    """Element count of an NDHWC activation with its REAL channel count (see REAL_CHANNELS)."""
+    cp = t.shape[-1]
+    return t.numel() * (REAL_CHANNELS.get(cp, cp) / float(cp))
 
 
 def _count(n: int = 1):
@@ -54,6 +64,19 @@ class _Timed:
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device_of_first_arg(fn):
+    """Entry points that users call directly with tensors (case-level kernels): run with the tensor's device current, so
+    that the launch goes to THAT device's stream.  (The network / loss / predict paths set the device once at their own
+    entry: engine.UNetEngine.run, loss._SegLossFn, trainer.predict_*.)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(t, *a, **k):
+        with torch.cuda.device(t.device):
+            return fn(t, *a, **k)
+    return wrapper
 
 
 def err_word(device) -> torch.Tensor:
@@ -318,7 +341,7 @@ def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, t
     n, d, h, w, cp = y.shape
     _count()
     assert out.dtype == y.dtype and (skip is None or skip.dtype == y.dtype)
-    with _Timed("in_apply", 0.0, y.numel() * 2.0 * (3 if skip is not None else 2)):
+    with _Timed("in_apply", 0.0, _alg_numel(y) * 2.0 * (3 if skip is not None else 2)):
         _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), _ptr(shift), n, d * h * w, cp,
                                               _f16(y), _stream()), "unet3d_in_apply")
 
@@ -327,7 +350,7 @@ def in_bwd_reduce(dout, dout2, out, y, g, table, sums, shift=None):
     n, d, h, w, cp = y.shape
     _count()
     assert dout.dtype == y.dtype and g.dtype == y.dtype and (out is None or out.dtype == y.dtype)
-    with _Timed("in_bwd_reduce", 0.0, y.numel() * 2.0 * (3 + (dout2 is not None) + (out is not None))):
+    with _Timed("in_bwd_reduce", 0.0, _alg_numel(y) * 2.0 * (3 + (dout2 is not None) + (out is not None))):
         _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), _ptr(out), y.data_ptr(), g.data_ptr(),
                                                    table.data_ptr(), _ptr(shift), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
                    "unet3d_in_bwd_reduce")
@@ -337,7 +360,7 @@ def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False, coef=None):
     n, d, h, w, cp = y.shape
     _count()
     assert g.dtype == y.dtype and dy.dtype == y.dtype
-    with _Timed("in_bwd_apply", 0.0, y.numel() * 2.0 * 3):
+    with _Timed("in_bwd_apply", 0.0, _alg_numel(y) * 2.0 * 3):
         _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
                                                   _ptr(coef), _ptr(dsum), n, d, h, w, cp, int(zero_last), _f16(y), _stream()),
                    "unet3d_in_bwd_apply")
@@ -416,7 +439,7 @@ def stem_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out: torch.Tenso
     cin = x.shape[1]
     assert x.is_contiguous() and w.numel() == cin * 27 * cp
     _count()
-    with _Timed("stem_fwd", 0.0, x.numel() * 4.0 + out.numel() * 2.0):
+    with _Timed("stem_fwd", 0.0, x.numel() * 4.0 + _alg_numel(out) * 2.0):
         _lib.check(_lib.lib().unet3d_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, cin, d, h, ww, cp,
                                               _f16(out), _stream()), "unet3d_stem_fwd")
 
@@ -429,7 +452,7 @@ def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
     vol = d * h * ww
     for ci in range(cin):
         _count()
-        with _Timed("stem_wgrad", 0.0, x.numel() / cin * 4.0 + dy.numel() * 2.0):
+        with _Timed("stem_wgrad", 0.0, x.numel() / cin * 4.0 + _alg_numel(dy) * 2.0):
             _lib.check(_lib.lib().unet3d_stem_wgrad(x.data_ptr() + 4 * ci * vol, dy.data_ptr(), dw.data_ptr() + 4 * ci * 28 * cp,
                                                     n, d, h, ww, cin * vol, cp, _f16(dy), _stream()), "unet3d_stem_wgrad")
 
@@ -438,7 +461,7 @@ def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Te
     n, d, h, ww, cp = a.shape
     k = logits.shape[1]
     _count()
-    with _Timed("head_fwd", 0.0, a.numel() * 2.0 + logits.numel() * 4.0):
+    with _Timed("head_fwd", 0.0, _alg_numel(a) * 2.0 + logits.numel() * 4.0):
         _lib.check(_lib.lib().unet3d_head_fwd(a.data_ptr(), w.data_ptr(), b.data_ptr(), logits.data_ptr(), k, n, d * h * ww,
                                               cp, _f16(a), _stream()), "unet3d_head_fwd")
 
@@ -449,7 +472,7 @@ def head_bwd(dl: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tenso
     k = dl.shape[1]
     _count()
     assert da.dtype == a.dtype
-    with _Timed("head_bwd", 0.0, dl.numel() * 4.0 + a.numel() * 4.0):
+    with _Timed("head_bwd", 0.0, dl.numel() * 4.0 + _alg_numel(a) * 4.0):
         _lib.check(_lib.lib().unet3d_head_bwd(dl.data_ptr(), a.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(),
                                               _ptr(grad_scale), k, n, d * h * ww, cp, _f16(a), _stream()), "unet3d_head_bwd")
 
@@ -503,6 +526,7 @@ def _c_arr(ctype, values):
     return (ctype * len(values))(*[int(v) for v in values])
 
 
+@_on_device_of_first_arg
 def zoom_linear(src: torch.Tensor, dst: torch.Tensor, norm: Optional[Sequence[Sequence[float]]] = None):
     """dst[x', y', z', c] = zoom(src[..., c]); src / dst are 4-D (x, y, z, channel) VIEWS (any strides) of float32 or
     uint8 CUDA tensors; the output shape is dst's.  norm: per channel (pct_00_5, pct_99_5, mean, std + 1e-8)."""
@@ -522,6 +546,7 @@ def zoom_linear(src: torch.Tensor, dst: torch.Tensor, norm: Optional[Sequence[Se
             _c_arr(C.c_longlong, dst.stride()), nm, ws.data_ptr(), nbytes, _stream()), "unet3d_zoom_linear")
 
 
+@_on_device_of_first_arg
 def zoom_label(src: torch.Tensor, dst: torch.Tensor):
     """Labels with >= 3 classes: per-class one-hot zoom + argmax (transform.py:72-78); 3-D uint8 views."""
     assert src.is_cuda and dst.is_cuda and src.dim() == 3 and dst.dim() == 3
@@ -538,6 +563,7 @@ def zoom_label(src: torch.Tensor, dst: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # cascade glue (data.regions_crop_case, trainer.cascade_predict_case merge) -- csrc/regions.cu
 # ------------------------------------------------------------------------------------------------
+@_on_device_of_first_arg
 def connected_components(mask: torch.Tensor):
     """6-connected components of a uint8 CUDA volume (X, Y, Z): scipy.ndimage.label's numbering.
     Returns (labels int32 (X, Y, Z): root index or -1, roots int32 [n] sorted, stats int32 [n][8] =
@@ -562,6 +588,7 @@ def connected_components(mask: torch.Tensor):
     return labels, roots, stats[:n]
 
 
+@_on_device_of_first_arg
 def region_accumulate(pred: torch.Tensor, result: torch.Tensor, count: torch.Tensor, src0, dst0, box):
     """result[dst0 + i] += pred[src0 + i] over `box` voxels; pred float32 (rx, ry, rz, K) view, result float64
     (X, Y, Z, K) contiguous, count int32 (X, Y, Z) contiguous."""
@@ -578,6 +605,7 @@ def region_accumulate(pred: torch.Tensor, result: torch.Tensor, count: torch.Ten
             _stream()), "unet3d_region_accumulate")
 
 
+@_on_device_of_first_arg
 def merge_finalize(result: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
     labels = torch.empty(count.shape, dtype=torch.uint8, device=count.device)
     _count()

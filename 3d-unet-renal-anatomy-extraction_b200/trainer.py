@@ -159,8 +159,9 @@ def predict_per_patch(input, model, num_classes=3, patch_size=(96, 96, 96), step
             torch.cuda.current_stream(device).wait_event(ev)
         return x, ensure
 
-    res = _predict_padded(upload, pshape, model, num_classes, patch, step_per_patch, verbose, one_hot, window,
-                          grid_mode, window_batch, cuda_graph, distributed, mark)
+    with torch.cuda.device(next(model.parameters()).device):       # launches go to the current device's stream
+        res = _predict_padded(upload, pshape, model, num_classes, patch, step_per_patch, verbose, one_hot, window,
+                              grid_mode, window_batch, cuda_graph, distributed, mark)
     # _predict_padded returns with the GPU still working: the host result buffer is allocated and touched (page faults:
     # ~25 ms for a 512x512x256 label map) while the windows run, so the copy at the end only moves bytes.  (A pinned
     # buffer would copy faster but costs ~100 ms of cudaHostAlloc whenever PyTorch's pinned cache has no free block.)
@@ -272,9 +273,15 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
     return res
 
 
-def predict_case(case, model, target_spacing, normalize_stats, num_classes=3, patch_size=(96, 96, 96),
-                 step_per_patch=4, verbose=True, one_hot=False, window=None, grid_mode="reference", window_batch=4,
-                 cuda_graph=True, distributed=True, keep_on_device=False):
+def predict_case(case, model, *args, **kwargs):
+    """trainer.py:101-133 -- see _predict_case for the arguments; runs with the model's device current."""
+    with torch.cuda.device(next(model.parameters()).device):
+        return _predict_case(case, model, *args, **kwargs)
+
+
+def _predict_case(case, model, target_spacing, normalize_stats, num_classes=3, patch_size=(96, 96, 96),
+                  step_per_patch=4, verbose=True, one_hot=False, window=None, grid_mode="reference", window_batch=4,
+                  cuda_graph=True, distributed=True, keep_on_device=False):
     """trainer.py:101-133: resample + normalise the case, predict it window by window, resize the prediction back to the
     original grid.  Same arguments and result (``case['pred']``: uint8 labels, or float32 probabilities with one_hot).
 
@@ -326,8 +333,20 @@ def predict_case(case, model, target_spacing, normalize_stats, num_classes=3, pa
 
 
 def cascade_predict_case(case, coarse_model, coarse_target_spacing, coarse_normalize_stats, coarse_patch_size,
-                         detail_model, detail_target_spacing, detail_normalize_stats, detail_patch_size, num_classes=3,
-                         step_per_patch=4, region_threshold=10000, crop_padding=20, verbose=True, **predict_kwargs):
+                         detail_model, *args, **kwargs):
+    """trainer.py:164-245 -- see _cascade_predict_case for the arguments; runs with the detail model's device current
+    (both models must live on the same device)."""
+    dev = next(detail_model.parameters()).device
+    if next(coarse_model.parameters()).device != dev:
+        raise RuntimeError("coarse and detail model must be on the same device")
+    with torch.cuda.device(dev):
+        return _cascade_predict_case(case, coarse_model, coarse_target_spacing, coarse_normalize_stats, coarse_patch_size,
+                                     detail_model, *args, **kwargs)
+
+
+def _cascade_predict_case(case, coarse_model, coarse_target_spacing, coarse_normalize_stats, coarse_patch_size,
+                          detail_model, detail_target_spacing, detail_normalize_stats, detail_patch_size, num_classes=3,
+                          step_per_patch=4, region_threshold=10000, crop_padding=20, verbose=True, **predict_kwargs):
     """trainer.py:164-245: coarse one-class prediction -> connected regions of at least ``region_threshold`` voxels, each
     grown by ``crop_padding`` mm -> detail prediction per region -> mean of the overlapping probabilities -> labels.
 

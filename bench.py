@@ -11,6 +11,7 @@ the task description): `value` times the step with the batch resident in HBM, `e
 through the public API from pinned host memory (H2D of image + label, D2H of the loss) each step.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -71,50 +72,176 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_port_step_time(steps, warmup, threads=None):
-    """Reference algorithm (oracle port, fp32) on the host cores: one 1x1x64^3 patch per step
-    (BASELINE.json configs[0]) -- a bounded sample of the 128^3 workload; FLOPs are linear in voxels."""
-    import torch
-    from oracle import unet3d_oracle as O
-    import unet3d_b200
-    if threads:
-        torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    model = unet3d_b200.ResUnet3D(out_channels=3)
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
-    x = torch.randn(1, 1, 64, 64, 64)
-    y = torch.randint(0, 3, (1, 64, 64, 64))
-    times = []
-    for i in range(warmup + steps):
+def _reference_or_port():
+    """The reference's own modules from oracle/_ref (copied there by oracle/build_ref.py at build time; kind "reference")
+    or, when that directory did not travel, the oracle port (kind "port")."""
+    from oracle import build_ref
+    mods = build_ref.load()
+    return (mods, "reference") if mods is not None else (None, "port")
+
+
+class CpuStepper:
+    """One training step of the reference algorithm on the host cores, the SAME timed region as the CUDA arm:
+    zero_grad + forward (train mode, Dropout3d active) + DiceLoss + backward + Adam step, fp32, every core."""
+
+    def __init__(self, shape):
+        import torch
+        torch.set_num_threads(os.cpu_count() or 1)             # BASELINE.md 4.2 -- also under torchrun (OMP_NUM_THREADS=1)
+        mods, self.kind = _reference_or_port()
+        torch.manual_seed(0)
+        self.torch = torch
+        n, d, h, w = shape
+        self.x = torch.randn(n, 1, d, h, w, generator=torch.Generator().manual_seed(1234))
+        self.y = torch.randint(0, 3, (n, d, h, w), generator=torch.Generator().manual_seed(4321))
+        self.voxels = n * d * h * w
+        if mods is not None:
+            network, loss = mods
+            self.model = network.ResUnet3D(num_pool=4, num_features=30, in_channels=1, out_channels=3).train()
+            self.loss = loss.DiceLoss()
+            self.params = list(self.model.parameters())
+        else:
+            from oracle import unet3d_oracle as O
+            import unet3d_b200
+            self.O = O
+            self.sd = {k: v.detach().clone().requires_grad_(True)
+                       for k, v in unet3d_b200.ResUnet3D(out_channels=3).state_dict().items()}
+            self.params = list(self.sd.values())
+        self.opt = torch.optim.Adam(self.params, lr=1e-4)
+        self.cores = torch.get_num_threads()
+
+    def step(self):
         t0 = time.perf_counter()
-        for p in sd.values():
-            p.grad = None
-        masks = O.DropoutMasks(train=True)
-        loss = O.dice_loss(O.resunet3d_forward(sd, x, masks=masks), y)
+        self.opt.zero_grad(set_to_none=True)
+        if self.kind == "reference":
+            loss = self.loss(self.model(self.x), self.y)
+        else:
+            loss = self.O.dice_loss(self.O.resunet3d_forward(self.sd, self.x, masks=self.O.DropoutMasks(train=True)), self.y)
         loss.backward()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    return sum(times) / len(times), 64 ** 3, torch.get_num_threads()
+        self.opt.step()
+        return time.perf_counter() - t0
+
+
+def _host_ram_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 0.0
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle/_ref when present) on the box's host
+    cores, --steps / --warmup honoured.  The step is the metric's own config (2 x 1x128^3) when one such step fits the
+    time budget (about 200 s for the whole run) and 64 GB of free host RAM, else a bounded sample (1 x 1x64^3: 1/16 of
+    the voxels; the network's FLOPs and activation bytes are exactly linear in voxels) -- `cpu_baseline.sample` says which."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 8), min(args.warmup, 2)
-    sec, vox, cores = cpu_port_step_time(steps, max(1, warmup))
-    value = vox / sec
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    budget_s = float(os.environ.get("U3D_REF_BUDGET_S", "200"))
+    small = CpuStepper((1, 64, 64, 64))
+    t_small = min(small.step() for _ in range(2))
+    full_cfg = None
+    est_full = t_small * 16.0 * 1.1
+    if est_full * (steps + warmup + 1) <= budget_s and _host_ram_gb() >= 64.0 and not args.no_full_step:
+        try:
+            full_cfg = CpuStepper((BATCH, *PATCH))
+        except Exception:
+            full_cfg = None
+    runner, sample = (full_cfg, f"{steps} steps of the full config, {BATCH} x 1x128^3 per step") if full_cfg is not None else \
+                     (small, f"{steps} steps of 1 x 1x64^3 (1/16 of the 2x128^3 step's voxels; FLOPs and bytes linear in voxels)")
+    for _ in range(warmup):
+        runner.step()
+    times = [runner.step() for _ in range(steps)]
+    sec = sum(times) / len(times)
+    value = runner.voxels / sec
+    one_full = None
+    if full_cfg is None and not args.no_full_step and _host_ram_gb() >= 64.0 and est_full <= 120.0:
+        # one real step of the metric's config, as a check of the linear extrapolation (BASELINE.md 4.3)
+        try:
+            one = CpuStepper((BATCH, *PATCH))
+            dt = one.step()
+            one_full = {"ms": dt * 1e3, "voxels_per_s": one.voxels / dt, "note": "ONE cold step of 2 x 1x128^3 (no warm-up)"}
+        except Exception as e:      # pragma: no cover
+            one_full = {"error": repr(e)[:200]}
     line = {"impl": "reference", "metric": "train voxels/s (fwd+bwd)", "value": value, "unit": "voxels/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": max(1, warmup), "ms_per_step": sec * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference algorithm (oracle port of network.py/loss.py, torch CPU "
-                       "ops, fp32, no optimizer) on the host cores"},
-            "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores, "kind": "port",
-                             "sample": "1 x 1x64^3 patch per step (1/16 of the 2x128^3 step; FLOPs linear in voxels)"},
+            "config": {"workload": WORKLOAD, "global_batch": BATCH, "patch": list(PATCH),
+                       "timed_region": "zero_grad + forward + DiceLoss + backward + Adam step",
+                       "note": ("the reference's own network.py / loss.py (oracle/_ref), " if runner.kind == "reference" else
+                                "oracle port of network.py / loss.py, ") + "torch CPU fp32, train mode, all host cores"},
+            "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": runner.cores, "kind": runner.kind, "sample": sample,
+                             "host_cpus": os.cpu_count(), "full_config_step": one_full},
             "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cudnn_bar(dev, l2_flush, steps=3):
+    """SURVEY.md 2.2 / 8d "secondary bar": the UNMODIFIED algorithm (the reference's network.py + loss.py from
+    oracle/_ref, else the oracle port) through PyTorch / cuDNN on this GPU at cfg-2 -- fp32 as PyTorch runs it by default
+    (cuDNN may use TF32) and bf16 autocast with channels_last_3d.  Context for `value`, not credit: it answers whether
+    the hand-written path beats the library path the reference would dispatch to on the same box."""
+    import torch
+    mods, kind = _reference_or_port()
+    out = {"impl": kind, "config": "cfg-2: 2 x 1x128^3, train mode, zero_grad + forward + DiceLoss + backward + Adam(fused)"}
+    torch.manual_seed(0)
+    x = torch.randn(BATCH, 1, *PATCH, device=dev)
+    y = torch.randint(0, 3, (BATCH, *PATCH), device=dev)
+    for name in ("fp32", "bf16_autocast_channels_last_3d"):
+        try:
+            if mods is not None:
+                net = mods[0].ResUnet3D(num_pool=4, num_features=30, in_channels=1, out_channels=3).to(dev).train()
+                loss_fn = mods[1].DiceLoss()
+                fwd = lambda inp: loss_fn(net(inp), y)
+                params = list(net.parameters())
+            else:
+                from oracle import unet3d_oracle as O
+                import unet3d_b200
+                sd = {k: v.detach().to(dev).requires_grad_(True)
+                      for k, v in unet3d_b200.ResUnet3D(out_channels=3).state_dict().items()}
+                fwd = lambda inp: O.dice_loss(O.resunet3d_forward(sd, inp, masks=O.DropoutMasks(train=True)), y.cpu()).to(dev)
+                params = list(sd.values())
+                net = None
+            opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+            inp = x
+            if name != "fp32":
+                inp = x.contiguous(memory_format=torch.channels_last_3d)
+                if net is not None:
+                    net = net.to(memory_format=torch.channels_last_3d)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                if name == "fp32":
+                    loss = fwd(inp)
+                else:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        loss = fwd(inp)
+                loss.backward()
+                opt.step()
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            evs = []
+            for _ in range(steps):
+                l2_flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step()
+                e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+            out[name] = {"ms_per_step": ms, "voxels_per_s": BATCH * PATCH[0] ** 3 / (ms * 1e-3),
+                         "peak_mem_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)}
+            del opt, params, net
+        except Exception as e:                      # pragma: no cover - context only, never fails the bench
+            out[name] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+    out["note"] = ("the reference returns its loss as a CPU tensor built from per-class .item()-like copies (loss.py:112-118), so "
+                   "each step of this arm contains C host synchronisations, as the reference's own training loop does")
+    return out
 
 
 def main():
@@ -124,6 +251,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-step", action="store_true", help="reference arm: never run a 2 x 128^3 step on the CPU")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the context measurements (other precision, cfg-3, cfg-5, cuDNN bar)")
     ap.add_argument("--patch", type=int, default=PATCH[0], help="cubic patch edge (default 128 = the metric's config)")
     ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement (cfg-4)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
@@ -151,6 +281,7 @@ def main():
     W = max(3, args.warmup)
     K = args.steps
     pe = args.patch
+    ops.REAL_CHANNELS = {32: 30, 64: 60, 128: 120}      # HBM-kernel bytes are counted on the net's unpadded widths
     torch.manual_seed(0)
     model = unet3d_b200.ResUnet3D(num_pool=4, num_features=30, in_channels=1, out_channels=3).to(dev).train()
     model.precision = args.precision
@@ -190,10 +321,11 @@ def main():
         loss.item().  One pair of events around the whole loop, first upload included."""
         l2_flush.zero_()
         host_batches = [{"image": h_img, "label": h_lab} for _ in range(n_steps)]
+        staging = timed_e2e.__dict__.setdefault("staging", {})        # one set of staging buffers for all e2e loops
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         marks = [time.perf_counter()]
-        for b in unet3d_b200.DevicePrefetcher(host_batches, dev):
+        for b in unet3d_b200.DevicePrefetcher(host_batches, dev, staging):
             loss = step(b["image"], b["label"])
             _ = loss.item()                                   # D2H of the step's result
             marks.append(time.perf_counter())
@@ -250,6 +382,7 @@ def main():
         dist.barrier()
     # per-kernel CUDA events for the roofline: a REPEAT of the timed region (same steps, same inputs, same clocks window)
     # with an event pair around every launch -- kept out of `value` because ~700 event records per step cost ~1.5 ms
+    used_graph = stepper is not None
     ops.PROFILE = []
     graphed, stepper = stepper, None          # the event pairs need eager launches
     timed(K, e2e=False)
@@ -301,12 +434,73 @@ def main():
                                     "frac": round(v[0] / (v[1] * 1e-3) / 1e9 / hbm, 3) if v[1] > 0 else None}
                                 for k, v in sorted(mem.items(), key=lambda kv: -kv[1][1])}}
 
+    # ---- context measurements (extra keys; not part of `value`): the other 16-bit storage format, BASELINE.json's cfg-3
+    # and cfg-5 at full size, and the same algorithm through PyTorch / cuDNN on this GPU (SURVEY.md 8d "secondary bar")
+    extras = {}
+    if not args.no_extras and pe == 128:
+        stepper = graphed = None                # frees the captured step's memory pool
+        opt.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+
+        def time_config(make_model, shape, precision, steps=5):
+            """ms per full training step (graph replay, L2 flushed between steps, max over ranks) of another config."""
+            torch.manual_seed(0)
+            m = make_model().to(dev).train()
+            m.precision = precision
+            o = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
+            gx = torch.Generator(device=dev).manual_seed(99 + rank)
+            x = torch.randn(*shape, device=dev, generator=gx)
+            y = torch.randint(0, 3, (shape[0], *shape[2:]), device=dev, generator=gx)
+            st = unet3d_b200.GraphedTrainStep(m, unet3d_b200.DiceLoss(), o, warmup=2)
+            for _ in range(4):                      # 2 eager steps, capture + replay, one more replay
+                st(x, y)
+            torch.cuda.synchronize()
+            ops.check_device_errors()
+            evs = []
+            for _ in range(steps):
+                l2_flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                st(x, y)
+                e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / steps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+            del st, m, o, x, y
+            torch.cuda.empty_cache()
+            return float(t.item()), peak
+
+        def entry(ms_, voxels, flop_per_voxel, peak_gib, **kw):
+            return {"ms_per_step": ms_, "voxels_per_s": voxels / (ms_ * 1e-3), "algorithmic_tflops_per_gpu":
+                    flop_per_voxel * voxels / world / (ms_ * 1e-3) / 1e12, "peak_mem_gib": round(peak_gib, 1), **kw}
+
+        default_net = lambda: unet3d_b200.ResUnet3D(num_pool=4, num_features=30, in_channels=1, out_channels=3)
+        other = "fp16" if args.precision == "bf16" else "bf16"
+        ms_o, pk = time_config(default_net, (BATCH, 1, pe, pe, pe), other)
+        extras[other] = entry(ms_o, BATCH * pe ** 3 * world, FWD_BWD_FLOP_PER_VOXEL, pk,
+                              note=f"the same cfg-2 step with {other} storage (same tcgen05 kind::f16 rate)")
+        # cfg-3: KiTS19-shaped 160x160x80 patches, global batch 16 over 2 / 4 / 8 GPUs (2 per GPU when run on one GPU)
+        b3 = 16 // world if world in (2, 4, 8) else 2
+        ms_3, pk = time_config(default_net, (b3, 1, 160, 160, 80), args.precision)
+        extras["cfg3"] = entry(ms_3, b3 * 160 * 160 * 80 * world, FWD_BWD_FLOP_PER_VOXEL, pk, per_gpu_batch=b3,
+                               global_batch=b3 * world, patch=[160, 160, 80])
+        # cfg-5: wide / deep variant, ResUnet3D(num_pool=5, num_features=32) on one 192^3 patch per GPU
+        ms_5, pk = time_config(lambda: unet3d_b200.ResUnet3D(num_pool=5, num_features=32, in_channels=1, out_channels=3),
+                               (1, 1, 192, 192, 192), args.precision, steps=3)
+        extras["cfg5"] = entry(ms_5, 192 ** 3 * world, 2239200, pk, per_gpu_batch=1, patch=[192, 192, 192],
+                               net="ResUnet3D(num_pool=5, num_features=32, out=3), 464 M parameters")
+        if rank == 0:
+            extras["cudnn_bar"] = cudnn_bar(dev, l2_flush)
+
     # ---- second half of BASELINE.json's metric: sliding-window inference, CT volumes/s (cfg-4: 512x512x256 volume,
     # 128^3 windows at 50 % overlap = 147 windows on the reference's grid; windows are dealt to the ranks)
     infer = None
     if not args.no_infer and pe == 128:
         import numpy as np
-        del d_img, d_lab
+        d_img = d_lab = None
         opt.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()
         vol = np.random.RandomState(7).standard_normal((512, 512, 256, 1)).astype(np.float32)
@@ -333,7 +527,16 @@ def main():
                  "volume": [512, 512, 256], "window": [128, 128, 128], "windows": n_win, "grid": "reference (trainer.py:29-40)",
                  "blend": "uniform", "windows_per_forward": 4, "includes": "H2D of the fp32 volume from pageable host memory (x-slabs, overlapped with the window forwards), all "
                  "window forwards, blend, normalise + argmax, D2H of the uint8 label map into pinned memory" + (", all-reduce of the blend buffers" if world > 1 else ""),
-                 "label_hist": [int(v) for v in np.bincount(labels.reshape(-1), minlength=3)[:3]]}
+                 "label_hist": [int(v) for v in np.bincount(labels.reshape(-1), minlength=3)[:3]],
+                 "label_sha256": hashlib.sha256(np.ascontiguousarray(labels).tobytes()).hexdigest()[:16]}
+        if world > 1:
+            # the sharded label map must be the single-GPU label map, bit for bit: rank 0 recomputes the volume alone
+            if rank == 0:
+                single = unet3d_b200.predict_per_patch(vol, model, 3, (128, 128, 128), 2, verbose=False, distributed=False)
+                infer["single_gpu_label_sha256"] = hashlib.sha256(np.ascontiguousarray(single).tobytes()).hexdigest()[:16]
+                infer["labels_equal_single_gpu"] = bool(np.array_equal(single, labels))
+                infer["label_mismatches_vs_single_gpu"] = int((single != labels).sum())
+            dist.barrier()
 
         if rank == 0:
             # the steps either side of the window loop (trainer.predict_case): zoom + clip + z-score of a raw
@@ -372,16 +575,20 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cvox, cores = cpu_port_step_time(4, 1)
-        cpu = {"value": cvox / sec, "unit": "voxels/s", "cores": cores, "kind": "port",
-               "sample": "4 steps of 1 x 1x64^3 (fwd + Dice + bwd, fp32 oracle port of network.py/loss.py)"}
+        c = CpuStepper((1, 64, 64, 64))
+        c.step()
+        sec = sum(c.step() for _ in range(4)) / 4
+        cpu = {"value": c.voxels / sec, "unit": "voxels/s", "cores": c.cores, "kind": c.kind, "host_cpus": os.cpu_count(),
+               "sample": "4 steps (after 1 warm-up) of 1 x 1x64^3 = 1/16 of the 2x128^3 step: zero_grad + forward + DiceLoss + "
+                         "backward + Adam, fp32, train mode, " + ("the reference's own network.py / loss.py (oracle/_ref)"
+                                                                  if c.kind == "reference" else "oracle port of network.py / loss.py")}
 
     if rank == 0:
         line = {"metric": "train voxels/s (fwd+bwd)", "value": vox / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": WORKLOAD if pe == 128 else f"REDUCED patch {pe}^3 (not the metric's config)",
-                           "global_batch": BATCH * world, "patch": [pe, pe, pe], "parallelism": f"dp{world}", "cuda_graph": stepper is not None,
+                           "global_batch": BATCH * world, "patch": [pe, pe, pe], "parallelism": f"dp{world}", "cuda_graph": used_graph,
                            "timed_region": "zero_grad + forward + DiceLoss + backward + grad all-reduce (N>1) + Adam step",
                            "l2": "256 MB buffer written between timed iterations (L2 flush); activations per step >> L2",
                            "tensor_frac_of_step": (FWD_BWD_FLOP_PER_VOXEL * BATCH * pe ** 3 / (ms * 1e-3) / 1e12) /
@@ -389,7 +596,8 @@ def main():
                 "e2e": {"value": vox / (ms_e2e * 1e-3), "unit": "voxels/s",
                         "h2d_bytes_per_step": (h_img.numel() * 4 + h_lab.numel() * 8) * world, "d2h_bytes_per_step": 4 * world,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "infer": infer}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "infer": infer,
+                **extras}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -179,3 +179,75 @@ def test_gloo_world2_gradient_allreduce_and_tile_sharding():
     import torch.multiprocessing as mp
     port = 29000 + os.getpid() % 2000
     mp.spawn(_gloo_worker, args=(2, port), nprocs=2, join=True)
+
+
+class _OddCases(torch.utils.data.Dataset):
+    """7 cases: not divisible by 2 ranks, and after a 0.3 validation split neither part is."""
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(11)
+        self.x = torch.randn(7, 1, 4, 4, 4, generator=g)
+        self.y = (self.x[:, 0] > 0).long()
+
+    def __len__(self):
+        return 7
+
+    def __getitem__(self, i):
+        return {"image": self.x[i], "label": self.y[i]}
+
+
+def _gloo_trainer_worker(rank, world, port, tmp):
+    """Trainer under data parallelism (trainer.py:415-604 has no multi-GPU code): every rank must see ONE
+    train / valid split, run the same number of steps although 7 cases do not divide by 2, start from rank 0's
+    parameters, and hand the scheduler / best-checkpoint logic the same epoch means."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import unet3d_b200
+    torch.manual_seed(100 + rank)                 # different initial weights and shuffles per rank on purpose
+    np.random.seed(100 + rank)
+    model = torch.nn.Conv3d(1, 2, 3, padding=1)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.5, patience=0, threshold=10.0)
+    tr = unet3d_b200.Trainer(model, opt, torch.nn.CrossEntropyLoss(), _OddCases(), batch_size=2,
+                             dataloader_kwargs={"num_workers": 0}, valid_split=0.3, scheduler=sched)
+    splits = [None] * world
+    dist.all_gather_object(splits, (tr.train_indices, tr.valid_indices))
+    assert splits[0] == splits[1]                                  # one split for the whole job
+    assert sorted(splits[0][0] + splits[0][1]) == list(range(7))
+    tr.fit(num_epochs=3, save_dir=os.path.join(tmp, "ck"))
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    both = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    assert torch.equal(both[0], both[1])                           # same start, same averaged gradients
+    state = [None] * world
+    dist.all_gather_object(state, (tr.get_lr(), tr.best_result["loss"]))
+    assert state[0] == state[1]                                    # reduced epoch means: schedulers in lock step
+    assert tr.get_lr() < 0.1                                       # the plateau scheduler did act
+    if rank == 0:
+        assert os.path.exists(os.path.join(tmp, "ck-last.pt"))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_trainer_odd_case_count(tmp_path):
+    import torch.multiprocessing as mp
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_gloo_trainer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
+def test_checkpoint_loads_without_unrestricted_pickle(tmp_path):
+    """Reference checkpoints hold numpy scalars in best_result (trainer.py:606-619): they must load through
+    weights_only=True with the allow-list, i.e. also with allow_pickle=False."""
+    model = torch.nn.Conv3d(1, 2, 1)
+    opt = torch.optim.Adam(model.parameters())
+    tr = unet3d_b200.Trainer(model, opt, torch.nn.CrossEntropyLoss(), _OddCases(), batch_size=2,
+                             dataloader_kwargs={"num_workers": 0}, valid_split=0.0)
+    tr.best_result = {"loss": np.float64(0.25), "dice": np.float32(0.5)}
+    tr.current_epoch = 4
+    path = str(tmp_path / "ref-like.pt")
+    tr.save_checkpoint(path)
+    tr2 = unet3d_b200.Trainer(torch.nn.Conv3d(1, 2, 1), torch.optim.Adam(model.parameters()), torch.nn.CrossEntropyLoss(),
+                              _OddCases(), batch_size=2, dataloader_kwargs={"num_workers": 0}, valid_split=0.0)
+    tr2.load_checkpoint(path, allow_pickle=False)
+    assert tr2.current_epoch == 5 and float(tr2.best_result["loss"]) == 0.25
+    assert tr2.train_indices == tr.train_indices

@@ -11,6 +11,7 @@ namespace u3d {
 namespace {
 
 constexpr float LRELU = 0.01f;     // nn.LeakyReLU default slope (network.py:165,390)
+constexpr int IN_U = 4;            // voxels per thread and loop trip in the InstanceNorm kernels (loads issued up front)
 
 // f16 = 1: the tensor is stored as IEEE half (forward activations in "fp16" precision mode), else bfloat16
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int f16 = 0) {
@@ -55,7 +56,7 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, const float
 
 // out = lrelu((y - mean) * scale [+ shift] [+ skip]);  shift (per (n, c), optional) carries BatchNorm's affine offset
 template <bool HAS_SKIP>
-__global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ skip,
+__global__ void __launch_bounds__(256, 2) in_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ skip,
                                 uint4* __restrict__ out, const float2* __restrict__ table,
                                 const float* __restrict__ shift, int chunks, long long V, int Cp, int af) {
   const int n = blockIdx.y;
@@ -69,26 +70,42 @@ __global__ void in_apply_kernel(const uint4* __restrict__ y, const uint4* __rest
     sh[j] = shift ? shift[(size_t)n * Cp + ch * 8 + j] : 0.f;
   }
   const size_t base = (size_t)n * V * chunks;
-  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
-    const size_t idx = base + (size_t)v * chunks + ch;
-    float f[8];
-    unpack8(ld_stream(y + idx), f, af);
-    float s[8];
-    if (HAS_SKIP) unpack8(ld_stream(skip + idx), s, af);
+  // IN_U voxels per thread and trip: all loads of a trip are issued before the first use (memory-level parallelism; with
+  // one voxel per trip the small level-2..4 tensors ran at 1.7-2.7 TB/s, latency-bound)
+  const long long stride = (long long)gridDim.x * blockDim.y;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += stride * IN_U) {
+    uint4 ry[IN_U], rs[IN_U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float z = fmaf(f[j] - mean[j], scale[j], sh[j]);
-      if (HAS_SKIP) z += s[j];
-      f[j] = z > 0.f ? z : LRELU * z;
+    for (int u = 0; u < IN_U; ++u) {
+      const long long vv = v + u * stride;
+      if (vv < V) {
+        const size_t idx = base + (size_t)vv * chunks + ch;
+        ry[u] = ld_stream(y + idx);
+        if (HAS_SKIP) rs[u] = ld_stream(skip + idx);
+      }
     }
-    out[idx] = pack8(f, af);
+#pragma unroll
+    for (int u = 0; u < IN_U; ++u) {
+      const long long vv = v + u * stride;
+      if (vv >= V) break;
+      float f[8], s[8];
+      unpack8(ry[u], f, af);
+      if (HAS_SKIP) unpack8(rs[u], s, af);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = fmaf(f[j] - mean[j], scale[j], sh[j]);
+        if (HAS_SKIP) z += s[j];
+        f[j] = z > 0.f ? z : LRELU * z;
+      }
+      out[base + (size_t)vv * chunks + ch] = pack8(f, af);
+    }
   }
 }
 
 // Backward, pass 1:  g = (dout [+ dout2]) * lrelu'(out)   (sign(out) == sign(pre-activation));
 // accumulates sum(g), sum(g * yhat) per (n, c).  g is also d(skip) of a residual block.
 template <bool HAS_D2>
-__global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2,
+__global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2,
                                      const uint4* __restrict__ out, const uint4* __restrict__ y,
                                      uint4* __restrict__ g, const float2* __restrict__ table,
                                      const float* __restrict__ shift, double* __restrict__ sums, int chunks,
@@ -106,38 +123,53 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
     s1[j] = 0.f;
     s2[j] = 0.f;
   }
+  constexpr int RU = HAS_D2 ? 2 : IN_U;          // four tensors in flight per voxel with dout2: keep the registers
   const size_t base = (size_t)n * V * chunks;
-  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
-    const size_t idx = base + (size_t)v * chunks + ch;
-    float d[8], o[8], yy[8];
-    unpack8(ld_stream(dout + idx), d, af);
-    if (HAS_D2) {
-      float d2[8];
-      unpack8(ld_stream(dout2 + idx), d2, af);
+  const long long stride = (long long)gridDim.x * blockDim.y;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += stride * RU) {
+    uint4 rd[RU], rd2[RU], ro[RU], ry[RU];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] += d2[j];
-    }
-    unpack8(ld_stream(y + idx), yy, af);
-    if (out != nullptr) {
-      unpack8(ld_stream(out + idx), o, af);
-    } else {
-      // no residual input: the activation's sign is the sign of the normalised value, `out` need not be read
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(yy[j] - mean[j], scale[j], sh[j]);
+    for (int u = 0; u < RU; ++u) {
+      const long long vv = v + u * stride;
+      if (vv < V) {
+        const size_t idx = base + (size_t)vv * chunks + ch;
+        rd[u] = ld_stream(dout + idx);
+        if (HAS_D2) rd2[u] = ld_stream(dout2 + idx);
+        ry[u] = ld_stream(y + idx);
+        if (out != nullptr) ro[u] = ld_stream(out + idx);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gg = o[j] > 0.f ? d[j] : LRELU * d[j];
-      d[j] = gg;
-    }
-    const uint4 gp = pack8(d, af);
-    g[idx] = gp;
-    unpack8(gp, d, af);      // reduce what pass 2 will read back (the rounded g)
+    for (int u = 0; u < RU; ++u) {
+      const long long vv = v + u * stride;
+      if (vv >= V) break;
+      float d[8], o[8], yy[8];
+      unpack8(rd[u], d, af);
+      if (HAS_D2) {
+        float d2[8];
+        unpack8(rd2[u], d2, af);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float yh = fmaf(yy[j] - mean[j], scale[j], sh[j]);
-      s1[j] += d[j];
-      s2[j] += d[j] * yh;
+        for (int j = 0; j < 8; ++j) d[j] += d2[j];
+      }
+      unpack8(ry[u], yy, af);
+      if (out != nullptr) {
+        unpack8(ro[u], o, af);
+      } else {
+        // no residual input: the activation's sign is the sign of the normalised value, `out` need not be read
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(yy[j] - mean[j], scale[j], sh[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : LRELU * d[j];
+      const uint4 gp = pack8(d, af);
+      g[base + (size_t)vv * chunks + ch] = gp;
+      unpack8(gp, d, af);      // reduce what pass 2 will read back (the rounded g)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float yh = fmaf(yy[j] - mean[j], scale[j], sh[j]);
+        s1[j] += d[j];
+        s2[j] += d[j] * yh;
+      }
     }
   }
   const int C8 = chunks * 8;
@@ -159,7 +191,7 @@ __global__ void in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4
 // Backward, pass 2:  dy = scale * (g - mean(g) - yhat * mean(g * yhat)); optional zeroing of the
 // ConstantPad3d planes of a ConvTrans3D output (network.py:314) and per-channel sum(dy) (its bias grad).
 template <bool ZERO_LAST, bool HAS_DSUM>
-__global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+__global__ void __launch_bounds__(256, 2) in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
                                     uint4* __restrict__ dy, const float2* __restrict__ table,
                                     const double* __restrict__ sums, const float* __restrict__ coef,
                                     double* __restrict__ dsum, int chunks,
@@ -186,28 +218,45 @@ __global__ void in_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
     acc[j] = 0.f;
   }
   const size_t base = (size_t)n * V * chunks;
-  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += (long long)gridDim.x * blockDim.y) {
-    const size_t idx = base + (size_t)v * chunks + ch;
-    float gg[8], yy[8];
-    unpack8(ld_stream(g + idx), gg, af);
-    unpack8(ld_stream(y + idx), yy, af);
-    bool z = false;
-    if (ZERO_LAST) {
-      const int w = (int)(v % W), h = (int)((v / W) % H), d = (int)(v / ((long long)W * H));
-      z = (w == W - 1) || (h == H - 1) || (d == D - 1);
+  const long long stride = (long long)gridDim.x * blockDim.y;
+  for (long long v = (long long)blockIdx.x * blockDim.y + threadIdx.y; v < V; v += stride * IN_U) {
+    uint4 rg[IN_U], ry[IN_U];
+#pragma unroll
+    for (int u = 0; u < IN_U; ++u) {
+      const long long vv = v + u * stride;
+      if (vv < V) {
+        const size_t idx = base + (size_t)vv * chunks + ch;
+        rg[u] = ld_stream(g + idx);
+        ry[u] = ld_stream(y + idx);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float r = fmaf(gg[j], ca[j], fmaf(yy[j], cb[j], cc[j]));
-      if (ZERO_LAST && z) r = 0.f;
-      gg[j] = r;
-    }
-    const uint4 o = pack8(gg, af);
-    dy[idx] = o;
-    if (HAS_DSUM) {
-      unpack8(o, gg, af);
+    for (int u = 0; u < IN_U; ++u) {
+      const long long vv = v + u * stride;
+      if (vv >= V) break;
+      float gg[8], yy[8];
+      unpack8(rg[u], gg, af);
+      unpack8(ry[u], yy, af);
+      bool z = false;
+      if (ZERO_LAST) {
+        // V < 2^31 per sample: 32-bit index arithmetic (the 64-bit divisions doubled this kernel's time)
+        const unsigned v32 = (unsigned)vv, q1 = v32 / (unsigned)W, wq = v32 - q1 * (unsigned)W;
+        const unsigned dq = q1 / (unsigned)H, hq = q1 - dq * (unsigned)H;
+        z = (wq == (unsigned)(W - 1)) || (hq == (unsigned)(H - 1)) || (dq == (unsigned)(D - 1));
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += gg[j];
+      for (int j = 0; j < 8; ++j) {
+        float r = fmaf(gg[j], ca[j], fmaf(yy[j], cb[j], cc[j]));
+        if (ZERO_LAST && z) r = 0.f;
+        gg[j] = r;
+      }
+      const uint4 o = pack8(gg, af);
+      dy[base + (size_t)vv * chunks + ch] = o;
+      if (HAS_DSUM) {
+        unpack8(o, gg, af);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += gg[j];
+      }
     }
   }
   if (HAS_DSUM) {
@@ -1033,7 +1082,9 @@ __global__ void weight_pack_kernel(const float* __restrict__ w, const int* __res
 // 16-32 rows of a 1 MB tensor is DRAM-latency bound: ~20 us launches at levels 3-4), capped at `waves` CTA waves over
 // the whole (gx, N) grid for large ones.
 inline int grid_rows(long long V, int rows_per_block, int N, int num_sms, int waves) {
-  long long need = (V + 2LL * rows_per_block - 1) / (2LL * rows_per_block);
+  // blocks per sample: at least one IN_U-voxel trip per thread, at most `waves` resident blocks per SM over all samples
+  // (few long-lived blocks: the per-thread prologue -- tables, fp64 sums -- and the per-block atomics are not free)
+  long long need = (V + (long long)IN_U * rows_per_block - 1) / ((long long)IN_U * rows_per_block);
   long long cap = ((long long)num_sms * waves + N - 1) / N;
   long long g = need < cap ? need : cap;
   return (int)(g < 1 ? 1 : g);
@@ -1346,7 +1397,7 @@ int in_apply(const bf16* y, const bf16* skip, bf16* out, const float* table, con
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
-  const int gx = grid_rows(V, blk.y, N, num_sms, 16);
+  const int gx = grid_rows(V, blk.y, N, num_sms, 8);
   dim3 grd(gx, N);
   if (skip)
     in_apply_kernel<true><<<grd, blk, 0, s>>>((const uint4*)y, (const uint4*)skip, (uint4*)out, (const float2*)table, shift, chunks, V, Cp, af);
@@ -1360,7 +1411,7 @@ int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   dim3 blk = cv_block(chunks);
-  const int gx = grid_rows(V, blk.y, N, num_sms, 8);
+  const int gx = grid_rows(V, blk.y, N, num_sms, 2);
   dim3 grd(gx, N);
   const size_t sm = (size_t)blk.y * Cp * 2 * sizeof(float);
   if (dout2)
@@ -1378,7 +1429,7 @@ int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, con
   const int chunks = Cp / 8;
   const long long V = (long long)D * H * W;
   dim3 blk = cv_block(chunks);
-  const int gx = grid_rows(V, blk.y, N, num_sms, 8);
+  const int gx = grid_rows(V, blk.y, N, num_sms, 2);
   dim3 grd(gx, N);
   const size_t sm = dsum ? (size_t)blk.y * Cp * sizeof(float) : 0;
 #define U3D_BWD_APPLY(Z, S)                                                                                         \
@@ -1407,10 +1458,11 @@ int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, i
   const int g = grid_for(total, 128, num_sms, 16);
   const size_t smem = ((size_t)Cin * 27 * Cp + Cp) * sizeof(float);
   if (Cin < 1 || smem > 48 * 1024) return U3D_ERR_UNSUPPORTED;
-  // The mma.sync forward is opt-in (U3D_STEM_FWD_MMA=1): it is faster (0.21 vs 0.32 ms at 2 x 128^3) and passes every
-  // single-process parity test, but with it the 2-GPU check (tools/check_multi_gpu.py) shows bf16-level noise (4e-3) between
-  // the two-rank and the one-process gradients that the CUDA-core kernel does not show (1e-7) -- not understood yet.
-  static const bool use_mma = getenv("U3D_STEM_FWD_MMA") != nullptr;
+  // Single-channel stems run on the mma.sync kernel (0.21 vs 0.32 ms at 2 x 128^3).  Round 1 kept it opt-in because a
+  // 2-GPU check showed 4e-3 of gradient noise with it; tools/diag/stem_partition.py (round 2) shows its output is
+  // bit-identical for N = 4 and for the same samples as 2 + 2 and from run to run, i.e. it does not depend on the
+  // partition; U3D_STEM_FWD_FMA=1 selects the CUDA-core kernel for comparisons.
+  static const bool use_mma = getenv("U3D_STEM_FWD_FMA") == nullptr;
   if (Cin == 1 && use_mma && (Cp == 16 || Cp == 32) && total < 0x7fffffffLL) {
     const int gm = grid_for((long long)N * D * H, 8 * 4, num_sms, 4);
     if (Cp == 32) {

@@ -26,6 +26,7 @@ from . import ops
 from . import plan as P
 
 IN_EPS = 1e-5      # nn.InstanceNorm3d default (network.py:163,388: no eps passed)
+PACK_SYNC_LAYERS = 5   # weight packs made on the main stream at the start of a pass; the rest overlaps the first layers
 
 
 class _ConvOp:
@@ -76,6 +77,7 @@ class UNetEngine:
     def _reset_caches(self):
         self._ops = {}
         self._pack_bind, self._pack_table, self._pack_table_key, self._pack_ptrs = {}, None, None, None
+        self._pack_table_late, self._pack_late_ids, self._pack_join, self._pack_stream = None, frozenset(), None, None
         self._dw_slots, self._dw_order, self._dw_table, self._dw_table_n = {}, [], None, 0
         self._dw_arena, self._gflat, self._g_total, self._dw_ready = None, None, 0, False
         self._z_arena, self._z_used, self._z_demand, self._z_size = None, 0, 0, 0
@@ -400,7 +402,14 @@ class UNetEngine:
         steps can pack every layer in one launch (_prepack)."""
         if id(dp) not in self._pack_bind:
             self._pack_bind[id(dp)] = (dp, w)
+        if self._pack_join is not None and id(dp) in self._pack_late_ids:
+            self._join_pack()               # first layer whose pack was left to the side stream: wait for it here
         return dp.packed_weight(w, self.act_dtype)
+
+    def _join_pack(self):
+        if self._pack_join is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._pack_join)
+            self._pack_join = None
 
     def _prepack(self):
         """Pack all known (plan, parameter) pairs whose cached tile stream is stale with one gather_multi launch."""
@@ -429,13 +438,28 @@ class UNetEngine:
                     return
                 jobs.append(dict(src0=src0.view(-1), src1=None if src1 is None else src1.view(-1), idx=dp.widx,
                                  out=dp.pack_buffer(dt, self.device), n0=n0, mode=int(dt == torch.float16)))
-            self._pack_table = ops.GatherTable(jobs, self.device)
+            # The packs of the first few layers (first-use order = forward order: the level-0 encoder block and the
+            # first pooling block, tiny weights) are made on the main stream; everything else -- 99 % of the bytes,
+            # including all data-gradient streams -- is packed on a side stream WHILE those first layers run (the pack
+            # kernel is bound by scattered 4-byte L2 reads and needs no shared memory, so it shares the SMs with the
+            # persistent tensor kernels), and the main stream joins at the first layer that needs one of them.
+            k = min(PACK_SYNC_LAYERS, len(jobs))
+            self._pack_table = ops.GatherTable(jobs[:k], self.device)
+            self._pack_table_late = ops.GatherTable(jobs[k:], self.device) if len(jobs) > k else None
+            self._pack_late_ids = frozenset(id(dp) for dp, _ in binds[k:])
             self._pack_table_key = (len(binds), dt)
             self._pack_ptrs = [tuple(t.data_ptr() for t in (w if isinstance(w, (list, tuple)) else [w])) for _, w in binds]
         if self._pack_ptrs != [tuple(t.data_ptr() for t in (w if isinstance(w, (list, tuple)) else [w])) for _, w in binds]:
             self._pack_table = None              # a parameter was re-allocated (e.g. .to()): rebuild next time
             return
         self._pack_table.launch()
+        if self._pack_table_late is not None:
+            if self._pack_stream is None:
+                self._pack_stream = torch.cuda.Stream(device=self.device)
+            self._pack_stream.wait_stream(torch.cuda.current_stream(self.device))      # fork (also inside a capture)
+            with torch.cuda.stream(self._pack_stream):
+                self._pack_table_late.launch()
+            self._pack_join = self._pack_stream
         for dp, w in binds:
             dp._w_version = dp.weight_key(w, dt)
             dp._packed_in_capture = capturing
@@ -638,6 +662,7 @@ class UNetEngine:
         wf[:, :cl] = net.fc.weight.detach().reshape(K, cl)
         logits = torch.empty(N, K, D, H, W, device=self.device, dtype=torch.float32)
         ops.head_fwd(cur, wf, net.fc.bias.detach().float().contiguous(), logits)
+        self._join_pack()           # normally joined long ago (first deep layer); a fork must never outlive the pass
         if save:
             tape["head"] = (cur, wf)
         return logits, (tape if save else None)

@@ -20,6 +20,7 @@ _err_words: Dict[int, torch.Tensor] = {}
 # bench.py instrumentation: when PROFILE is a list, every launch of the library appends
 # (kernel name, algorithmic FLOPs, start event, end event, algorithmic HBM bytes); LAUNCHES counts every kernel enqueued.
 PROFILE = None
+PROFILE_DETAIL = None   # tools/step_table.py: when a list, one descriptor string per PROFILE entry (layer shape, plan)
 LAUNCHES = 0
 
 # Packed-weight caches are keyed by (address, tensor version, dtype, PACK_EPOCH).  The version counter alone is NOT
@@ -47,8 +48,8 @@ def _count(n: int = 1):
 
 
 class _Timed:
-    def __init__(self, name, flops=0.0, nbytes=0.0):
-        self.name, self.flops, self.nbytes = name, flops, nbytes
+    def __init__(self, name, flops=0.0, nbytes=0.0, detail=""):
+        self.name, self.flops, self.nbytes, self.detail = name, flops, nbytes, detail
 
     def __enter__(self):
         if PROFILE is not None:
@@ -60,6 +61,8 @@ class _Timed:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             PROFILE.append((self.name, self.flops, self.e0, e1, self.nbytes))
+            if PROFILE_DETAIL is not None:
+                PROFILE_DETAIL.append(self.detail() if callable(self.detail) else self.detail)
 
 
 def _stream() -> int:
@@ -235,7 +238,9 @@ def conv_gemm(dp: DeviceConvPlan, inputs: Sequence[torch.Tensor], wpacked: torch
     a.dbg_out = DBG_OUT.data_ptr() if DBG_OUT is not None else None
     flops = pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3]
     _count()
-    with _Timed("conv_gemm_kernel", flops):
+    with _Timed("conv_gemm_kernel", flops, 0.0,
+                lambda: f"{pl.kind} k{pl.ks} s{pl.stride} {pl.in_C}->{pl.out_C} grid{tuple(grid)} nblk{pl.nblk} Dt{pl.Dt} G{pl.G} "
+                        f"fuse{3 if pl.fuse_kd else 1} nbuf{pl.nbuf} dense{int(pl.dense)} items{a.N * -(-a.D // pl.Dt) * -(-a.H // P.HT) * -(-a.W // P.WT) * pl.n_nblk}"):
         _lib.check(_lib.lib().unet3d_conv_gemm(C.byref(a), _stream()), "unet3d_conv_gemm")
 
 
@@ -324,7 +329,9 @@ def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor
     assert all(x.dtype == dy.dtype for x in xs)        # one MMA cannot mix fp16 and bf16 operands
     assert dw.dtype == torch.float32 and dw.numel() >= pl.dw_numel
     _count()
-    with _Timed("wgrad_gemm_kernel", pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3]):
+    with _Timed("wgrad_gemm_kernel", pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3], 0.0,
+                lambda: f"{pl.kind} x{[tuple(x.shape[1:]) for x in xs]} dy{tuple(dy.shape[1:])} grid{tuple(grid)} jobs{pl.n_jobs} "
+                        f"split{pl.split} wx{pl.wx} wy{pl.wy} dt{[j['dt'] for j in pl.jobs][:3]} ent{[len(j['units']) for j in pl.jobs][:4]}"):
         _lib.check(_lib.lib().unet3d_wgrad_gemm(C.byref(a), _stream()), "unet3d_wgrad_gemm")
 
 
@@ -341,7 +348,7 @@ def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, t
     n, d, h, w, cp = y.shape
     _count()
     assert out.dtype == y.dtype and (skip is None or skip.dtype == y.dtype)
-    with _Timed("in_apply", 0.0, _alg_numel(y) * 2.0 * (3 if skip is not None else 2)):
+    with _Timed("in_apply", 0.0, _alg_numel(y) * 2.0 * (3 if skip is not None else 2), f"{tuple(y.shape)} skip{int(skip is not None)}"):
         _lib.check(_lib.lib().unet3d_in_apply(y.data_ptr(), _ptr(skip), out.data_ptr(), table.data_ptr(), _ptr(shift), n, d * h * w, cp,
                                               _f16(y), _stream()), "unet3d_in_apply")
 
@@ -350,7 +357,8 @@ def in_bwd_reduce(dout, dout2, out, y, g, table, sums, shift=None):
     n, d, h, w, cp = y.shape
     _count()
     assert dout.dtype == y.dtype and g.dtype == y.dtype and (out is None or out.dtype == y.dtype)
-    with _Timed("in_bwd_reduce", 0.0, _alg_numel(y) * 2.0 * (3 + (dout2 is not None) + (out is not None))):
+    with _Timed("in_bwd_reduce", 0.0, _alg_numel(y) * 2.0 * (3 + (dout2 is not None) + (out is not None)),
+                f"{tuple(y.shape)} d2{int(dout2 is not None)} out{int(out is not None)}"):
         _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), _ptr(out), y.data_ptr(), g.data_ptr(),
                                                    table.data_ptr(), _ptr(shift), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
                    "unet3d_in_bwd_reduce")
@@ -360,7 +368,7 @@ def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False, coef=None):
     n, d, h, w, cp = y.shape
     _count()
     assert g.dtype == y.dtype and dy.dtype == y.dtype
-    with _Timed("in_bwd_apply", 0.0, _alg_numel(y) * 2.0 * 3):
+    with _Timed("in_bwd_apply", 0.0, _alg_numel(y) * 2.0 * 3, f"{tuple(y.shape)}"):
         _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
                                                   _ptr(coef), _ptr(dsum), n, d, h, w, cp, int(zero_last), _f16(y), _stream()),
                    "unet3d_in_bwd_apply")

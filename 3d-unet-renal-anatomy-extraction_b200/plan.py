@@ -60,7 +60,8 @@ def weight_ring(dt: int, g: int, nblk: int, fuse: int, n_taps: int = 27) -> Tupl
     wt = max(1, min(taps, 16, 28672 // tile))
     while wt > 1 and avail // (wt * tile) < 2:
         wt -= 1
-    stages = min(W_STAGES, max(2, 57344 // (wt * tile)), avail // (wt * tile))
+    ring_bytes = int(os.environ.get("U3D_W_RING", "57344"))
+    stages = min(W_STAGES, max(2, ring_bytes // (wt * tile)), avail // (wt * tile))
     return wt, stages
 
 
@@ -250,7 +251,7 @@ def _kidx_and_valid(plan_kind: str, ks: int, stride: int, pattern: str, shift, p
 
 
 _PLAN_CACHE: Dict[tuple, object] = {}
-_TUNING_ENV = ("U3D_CONV_CFG", "U3D_A_STAGES", "U3D_WG_WAVES", "U3D_WG_NOSW", "U3D_WG_FORCESW", "U3D_WG_PAIR")
+_TUNING_ENV = ("U3D_CONV_CFG", "U3D_A_STAGES", "U3D_WG_WAVES", "U3D_WG_NOSW", "U3D_WG_FORCESW", "U3D_WG_PAIR", "U3D_W_RING")
 
 
 def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: Sequence[int], depth: int,

@@ -504,13 +504,36 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) bias_v[j] = __ldg(&b[j]);
         }
-        for (int d = (CG_EPI_WARPS == 8 ? ((cc * p.Dt + half) & 1) : 0); d < p.Dt; d += CG_EPI_WARPS / 4) {
+        // residual-gradient addend: the 64 bytes of plane d + 1 are requested while plane d is converted and stored (the
+        // load used to sit between tcgen05.ld and the store of the same plane: ~1 us of exposed global latency per
+        // plane made the epilogue, not the MMAs, the critical path of every dgrad launch with an addend -- 430 vs 240 us
+        // at level 0)
+        constexpr int D_STEP = CG_EPI_WARPS / 4;
+        const int d_first = (CG_EPI_WARPS == 8 ? ((cc * p.Dt + half) & 1) : 0);
+        uint4 add_nxt[4];
+        auto addend_fetch = [&](int d, uint4 (&dst)[4]) {
+          const int gd = seg * p.Dt + d;
+          const int od = gd * p.omul + (ooff & 0xff);
+          if (addp == nullptr || !(hw_ok && gd < p.D) || d >= p.Dt) return;
+          const long long off = (long long)n * p.out_sN + (long long)od * p.out_sD + (long long)oh * p.out_sH +
+                                (long long)ow * p.out_sW + coff;
+          const uint4* ap = reinterpret_cast<const uint4*>(addp + off + cc * 32);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            if (c0 + k4 * 8 < p.out_C) dst[k4] = __ldg(ap + k4);
+        };
+        addend_fetch(d_first, add_nxt);
+        for (int d = d_first; d < p.Dt; d += D_STEP) {
           const int gd = seg * p.Dt + d;
           const int od = gd * p.omul + (ooff & 0xff);
           const bool valid = hw_ok && gd < p.D;
           const bool zero = (od == p.zD) || (oh == p.zH) || (ow == p.zW);
           const long long off = (long long)n * p.out_sN + (long long)od * p.out_sD + (long long)oh * p.out_sH +
                                 (long long)ow * p.out_sW + coff;
+          uint4 add_cur[4];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) add_cur[k4] = add_nxt[k4];
+          addend_fetch(d + D_STEP, add_nxt);
           uint32_t raw[32];
           __syncwarp();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)d * p.nblk + cc * 32;
@@ -525,11 +548,10 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
             for (int j = 0; j < 32; ++j) v[j] += bias_v[j];
           }
           if (addp != nullptr && valid) {
-            const uint4* ap = reinterpret_cast<const uint4*>(addp + off + cc * 32);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               if (c0 + k4 * 8 < p.out_C) {
-                const uint4 u = __ldg(ap + k4);
+                const uint4 u = add_cur[k4];
                 float2 f;
                 f = unpack_2x16(u.x, of16); v[k4 * 8 + 0] += f.x; v[k4 * 8 + 1] += f.y;
                 f = unpack_2x16(u.y, of16); v[k4 * 8 + 2] += f.x; v[k4 * 8 + 3] += f.y;

@@ -100,9 +100,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
               tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_XLIST + 2 * b])], full, __ldg(&jt[WG_J_XLIST + 2 * b + 1]),
                           tw * CG_WT - 1, th * CG_HT - 1, seg * Dt + xd0 + pl, n);
           for (int d = 0; d < Dt; ++d)
-            for (int b = 0; b < nby; ++b, dst += y_pitch)
-              tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_YLIST + 2 * b])], full, __ldg(&jt[WG_J_YLIST + 2 * b + 1]),
-                          tw * CG_WT, th * CG_HT, seg * Dt + d, n);
+            for (int b = 0; b < nby; ++b, dst += y_pitch) {
+              // bits 16-17 of the channel word: w shift of this dy box (plan.py "w-shift" mode: the three kw taps of a
+              // 3x3x3 layer are three copies of the dy tile shifted by +1 / 0 / -1 voxel in w, side by side in N)
+              const int cw = __ldg(&jt[WG_J_YLIST + 2 * b + 1]);
+              const int code = (cw >> 16) & 3;
+              tma_load_5d(dst, &p.map[__ldg(&jt[WG_J_YLIST + 2 * b])], full, cw & 0xffff,
+                          tw * CG_WT + (code ? code - 2 : 0), th * CG_HT, seg * Dt + d, n);
+            }
         } else {
           mbar_expect_tx(full, (uint32_t)Px * Gx * CG_BOX_BYTES + (uint32_t)Dt * Gy * WG_DY_BOX_BYTES);
           uint32_t dst = stage0 + st * stage_bytes;

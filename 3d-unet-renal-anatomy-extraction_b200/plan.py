@@ -251,7 +251,8 @@ def _kidx_and_valid(plan_kind: str, ks: int, stride: int, pattern: str, shift, p
 
 
 _PLAN_CACHE: Dict[tuple, object] = {}
-_TUNING_ENV = ("U3D_CONV_CFG", "U3D_A_STAGES", "U3D_WG_WAVES", "U3D_WG_NOSW", "U3D_WG_FORCESW", "U3D_WG_PAIR", "U3D_W_RING")
+_TUNING_ENV = ("U3D_CONV_CFG", "U3D_A_STAGES", "U3D_WG_WAVES", "U3D_WG_NOSW", "U3D_WG_FORCESW", "U3D_WG_PAIR", "U3D_W_RING",
+               "U3D_WG_WSHIFT")
 
 
 def make_conv_plan(kind: str, ks: int, stride: int, in_C: Sequence[int], out_C: Sequence[int], depth: int,
@@ -584,7 +585,22 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
         return (kk[0] * ks + kk[1]) * ks + kk[2]
 
     case_a = kind == "conv" and stride == 1 and ks == 3 and len(XL) <= 16 and 16 % len(XL) == 0
-    if case_a:
+    # ---- w-shift mode (3x3x3 stride-1 layers whose sources and dy all have 17..32 channels: the level-0 layers, 41 % of
+    # the net's FLOPs).  With N = 32 an M = 128, K = 16 MMA costs ~47 cycles whatever it computes (operand-read floor), so
+    # nine (kh, kw) entries of N = 32 run at a third of the tensor peak.  Substituting u = v + (kw - 1) e_w in
+    #     dW[kd,kh,kw] = sum_v x[v + (kd-1, kh-1, kw-1)] dy[v]  =  sum_u x[u + (kd-1, kh-1, 0)] dy[u - (kw-1) e_w]
+    # moves the kw tap from the x operand to the dy operand: three copies of the dy tile, TMA-loaded at w0 + 1, w0, w0 - 1
+    # (out-of-volume voxels are zero-filled, exactly the terms that must vanish), sit side by side as three MN atoms of
+    # one swizzled B operand, so ONE MMA of N = 96 per kh does the work of three; the kd taps stay in M (four x planes).
+    wshift = (case_a and len(YL) == 4 and all(cp == 32 for cp in x_Cp) and D_ >= 1
+              and os.environ.get("U3D_WG_WSHIFT", "1") == "1" and not os.environ.get("U3D_WG_NOSW")
+              and os.environ.get("U3D_WG_PAIR", "0") != "1")            # (the round-1 pair-mode experiment overrides it)
+    if wshift:
+        m_blocks = [(4 * i, 4) for i in range(len(x_Cp))]          # one job family per source: M = 4 planes x 32 channels
+        ppm = 4
+        units = [(0, sh, 1) for sh in range(3)]                     # kw is carried by the dy copies; x stays at the centre
+        planes_extra = 4
+    elif case_a:
         m_blocks = [(0, len(XL))]
         ppm = 16 // len(XL)
         units = [(pg, sh, sw) for pg in range(0, span, ppm) for (sh, sw) in hw_shifts]
@@ -623,7 +639,7 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
     jobs = []
     p0_values = sorted(set(u[0] for u in units))
     for (y0, ycnt) in y_blocks:
-        gy = -(-ycnt // 4) * 4
+        gy = -(-ycnt // 4) * 4 * (3 if wshift else 1)
         max_ent = min(512 // (gy * 8 * (2 if pair else 1)), WG_ENT_MAX)
         for (m0, gx) in m_blocks:
             for p0 in p0_values:          # one job never spans plane groups: keeps the x stage small
@@ -664,7 +680,9 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
     if os.environ.get("U3D_WG_NOSW"):
         wx = wy = 1
     use_sw = wx > 1 and wy > 1 and not pair
-    if case_a and wx < 8 and not os.environ.get("U3D_WG_FORCESW"):
+    if wshift:
+        assert wx == 4 and wy == 4
+    elif case_a and wx < 8 and not os.environ.get("U3D_WG_FORCESW"):
         # 16/32-channel 3x3x3 layers are bound by the tensor core's shared-memory operand reads, not by the loads, and a
         # 32/64-byte MN-major row fills only part of a 128-byte read wavefront: measured 0.436 vs 0.412 ms (30->30) and
         # 0.951 vs 0.853 ms (60->30 concat) at 2x128^3 -- they keep the 16-byte-row layout (8 rows x 16 B = one wavefront)
@@ -698,13 +716,16 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
         row = tab[ji]
         row[0:7] = [dt, px, min_sd - 1 + j["p0"], gx, gy, len(j["units"]), ld]
         xl = [XL[j["m0"] + i] for i in range(gx)]
-        yl = [YL[j["y0"] + i] if i < j["ycnt"] else YL[j["y0"]] for i in range(gy)]
+        yl = [YL[j["y0"] + i] if i < j["ycnt"] else YL[j["y0"]] for i in range(gy // (3 if wshift else 1))]
         j["xl"], j["yl"] = xl, yl
         if use_sw:
             row[7] = wx | (wy << 8) | (nbx << 16) | (nby << 24)
             for b in range(nbx):
                 row[WG_J_XLIST + 2 * b], row[WG_J_XLIST + 2 * b + 1] = xl[b * wx]["map"], xl[b * wx]["ch"]
             for b in range(nby):
+                if wshift:              # box b = the dy tile for kw = b, loaded at w0 + (1 - kw): code 3 / 2 / 1 in bits 16-17
+                    row[WG_J_YLIST + 2 * b], row[WG_J_YLIST + 2 * b + 1] = YL[0]["map"], YL[0]["ch"] | ((3 - b) << 16)
+                    continue
                 c = YL[j["y0"] + b * wy] if b * wy < j["ycnt"] else YL[j["y0"]]
                 row[WG_J_YLIST + 2 * b], row[WG_J_YLIST + 2 * b + 1] = c["map"], c["ch"]
         else:
@@ -721,6 +742,15 @@ def _make_wgrad_plan(kind: str, ks: int, stride: int, x_C: Sequence[int], y_C: i
             ent[1] = col
             col += gy * 8 * (2 if pair else 1)
             ent[2:] = -1
+            if wshift:
+                for s in range(16):
+                    sd = p0 + s // gx
+                    if sd <= 2:
+                        ent[2 + s] = (((sd * 3 + sh) * 3 + 0) * Kp + xl[s % gx]["k0"]) * ld
+                for kw in range(3):
+                    for h in range(4):
+                        ent[18 + kw * 4 + h] = kw * Kp * ld + yl[h]["n0"]
+                continue
             if pair:
                 # rows: x plane shift sd = 0..3 (3 pairs only with the second dy plane); columns: (dy plane j, chunk h)
                 for s in range(16):

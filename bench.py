@@ -337,12 +337,17 @@ def main():
                   file=sys.stderr, flush=True)
         return e0.elapsed_time(e1) / n_steps
 
-    def timed(n_steps, e2e):
+    def timed(n_steps, e2e, lead_sleep=False):
         if e2e:
             return timed_e2e(n_steps)
         evs = []
         for _ in range(n_steps):
             l2_flush.zero_()                                  # flush L2 between timed iterations
+            if lead_sleep:
+                # per-kernel profiling pass (eager launches, an event pair around each): a ~40 ms spin kernel lets the
+                # host enqueue the whole step ahead of the GPU, so that every event interval is kernel time and not the
+                # host's launch latency (which used to inflate every launch shorter than ~10 us)
+                torch.cuda._sleep(int(0.040 * 1.9e9))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if e2e:
@@ -385,7 +390,7 @@ def main():
     used_graph = stepper is not None
     ops.PROFILE = []
     graphed, stepper = stepper, None          # the event pairs need eager launches
-    timed(K, e2e=False)
+    timed(K, e2e=False, lead_sleep=True)
     stepper = graphed
     prof = ops.PROFILE
     ops.PROFILE = None

@@ -107,11 +107,12 @@ def run_wgrad_plan(plan, xs, dy, grid):
             bx = [(int(row[P.WG_J_XLIST + 2 * b]), int(row[P.WG_J_XLIST + 2 * b + 1])) for b in range(nbx)]
             by = [(int(row[P.WG_J_YLIST + 2 * b]), int(row[P.WG_J_YLIST + 2 * b + 1])) for b in range(nby)]
             xl = [(bx[i // wx][0], bx[i // wx][1] + 8 * (i % wx)) for i in range(nbx * wx)]
-            yl = [(by[i // wy][0], by[i // wy][1] + 8 * (i % wy)) for i in range(nby * wy)]
+            # bits 16-17 of a dy box's channel word: w shift code (w-shift mode: 3 = +1, 2 = 0, 1 = -1; 0 = no shift)
+            yl = [(by[i // wy][0], (by[i // wy][1] & 0xffff) + 8 * (i % wy), ((by[i // wy][1] >> 16) & 3)) for i in range(nby * wy)]
             gx_mem = nbx * wx          # chunks per plane as laid out in shared memory (the MMA's M index runs over them)
         else:
             xl = [(int(row[P.WG_J_XLIST + 2 * i]), int(row[P.WG_J_XLIST + 2 * i + 1])) for i in range(gx)]
-            yl = [(int(row[P.WG_J_YLIST + 2 * i]), int(row[P.WG_J_YLIST + 2 * i + 1])) for i in range(gy)]
+            yl = [(int(row[P.WG_J_YLIST + 2 * i]), int(row[P.WG_J_YLIST + 2 * i + 1]), 0) for i in range(gy)]
             gx_mem = gx
         for e in range(n_ent):
             ent = row[P.WG_J_ENT + e * P.WG_E_SIZE: P.WG_J_ENT + (e + 1) * P.WG_E_SIZE]
@@ -133,12 +134,22 @@ def run_wgrad_plan(plan, xs, dy, grid):
                     if co < 0:
                         continue
                     jp, h = divmod(hh, gy)
-                    my, chy = yl[h]
+                    my, chy, code = yl[h]
                     vy = view(*maps[my])
                     b = torch.zeros(N, D + 2, H, W, 8, dtype=torch.float64)
                     d1, h1, w1 = min(vy.shape[1], D), min(vy.shape[2], H), min(vy.shape[3], W)
                     if chy < vy.shape[-1]:
                         b[:, :d1, :h1, :w1] = vy[:, :d1, :h1, :w1, chy:chy + 8]
+                    if code:        # the dy box was loaded at w0 + (code - 2): tile voxel w holds dy[w + code - 2], zero outside
+                        wsh = code - 2
+                        shifted_b = torch.zeros_like(b)
+                        if wsh > 0:
+                            shifted_b[:, :, :, :W - wsh] = b[:, :, :, wsh:W]
+                        elif wsh < 0:
+                            shifted_b[:, :, :, -wsh:W] = b[:, :, :, :W + wsh]
+                        else:
+                            shifted_b = b
+                        b = shifted_b
                     if pair:       # the MMA of dy planes (d, d+1), d even: x plane d + shift against dy plane d + jp
                         assert dt % 2 == 0
                         n_pairs = (D + 1) // 2

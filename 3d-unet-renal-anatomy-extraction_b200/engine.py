@@ -26,6 +26,12 @@ from . import ops
 from . import plan as P
 
 IN_EPS = 1e-5      # nn.InstanceNorm3d default (network.py:163,388: no eps passed)
+import os as _os
+# overlapped all-reduce: the first chunk = head, decoder, bottom level and the first level-3 blocks = ~90 % of the gradient
+# bytes, complete about half way into the backward pass; the rest of the encoder backward (the heaviest kernels) hides
+# its transfer, and a ~30 MB second chunk is left behind the backward pass.  Measured on 2 B200s (18.93 ms on one GPU):
+# split 0.8 -> 19.57 ms, 0.9 -> 19.29, 0.97 -> 19.50 (NCCL_MAX_CTAS=32; with 16 / 8 / 4 CTAs 19.65 / 20.03 / 20.60).
+CHUNK_SPLIT_FRACTION = float(_os.environ.get("U3D_CHUNK_SPLIT", "0.9"))
 PACK_SYNC_LAYERS = 5   # weight packs made on the main stream at the start of a pass; the rest overlaps the first layers
 
 
@@ -67,6 +73,10 @@ class UNetEngine:
         self._inv_scale = None
         self._last_was_train = True      # the first forward always packs
         self.grad_chunk_hook = None      # callable(flat prefix tensor) -> handle; set by parallel.overlap_gradient_all_reduce
+        # data parallel: 1 / world folded into the weight-gradient unpack (set by parallel.prescale_gradients), so the
+        # flat buffer that the all-reduce SUMS already holds this rank's share of the mean -- no 336 MB divide pass
+        self.grad_prescale = None        # float or None
+        self._prescale_dev = None
         # tests only (teacher-forced block parity, tests/test_block_parity_gpu.py): when a list, every block of the
         # backward pass appends the tensors it consumed and produced; `capture_scale` is the fp16 gradient scale
         self.capture = None
@@ -327,7 +337,8 @@ class UNetEngine:
             self._dw_slots[id(op.wgrad)] = None
             self._dw_order.append((op.wgrad, param.numel()))
         g = dw.index_select(0, op.wgrad.gidx).view_as(param)
-        return g if self._inv_scale is None else g.mul_(self._inv_scale)
+        sc = self._unpack_scale()
+        return g if sc is None else g.mul_(sc)
 
     def _begin_wgrads(self):
         """Called at the start of a backward pass: zero the accumulator arena, allocate this step's flat gradient buffer."""
@@ -339,6 +350,21 @@ class UNetEngine:
             self._gflat = torch.empty(self._g_total, dtype=torch.float32, device=self.device)
             self._dw_ready = True
 
+    def set_grad_prescale(self, value):
+        """value = 1 / world (data parallel averaging folded into the unpack) or None."""
+        self.grad_prescale = None if value is None else float(value)
+        self._prescale_dev = None
+        if value is not None and self.device is not None:
+            self._prescale_dev = torch.full((1,), float(value), dtype=torch.float32, device=self.device)
+
+    def _unpack_scale(self):
+        """Device scalar the weight-gradient unpack multiplies in: 1 / fp16-gradient-scale and / or the data-parallel 1 / world."""
+        if self.grad_prescale is None:
+            return self._inv_scale
+        if self._prescale_dev is None:
+            self._prescale_dev = torch.full((1,), self.grad_prescale, dtype=torch.float32, device=self.device)
+        return self._prescale_dev if self._inv_scale is None else self._inv_scale * self._prescale_dev
+
     def _wgrad_done(self):
         """Bookkeeping after every weight-gradient launch in steady state: when the layers of the FIRST chunk (backward
         order: head, decoder, bottom level = ~2/3 of the gradient bytes) are complete and somebody asked for it
@@ -346,17 +372,17 @@ class UNetEngine:
         -- the NCCL all-reduce of the prefix then overlaps the encoder half of the backward pass."""
         self._dw_done += 1
         if self._dw_ready and self.grad_chunk_hook is not None and self._dw_done == self._dw_split:
-            self._dw_table_a.launch(scale=self._inv_scale, out_base=self._gflat)
+            self._dw_table_a.launch(scale=self._unpack_scale(), out_base=self._gflat)
             self._chunk_handle = self.grad_chunk_hook(self._gflat[:self._g_split])
 
     def _finish_wgrads(self):
         self._last_gflat = None
         if self._dw_ready:
             if self._chunk_handle is not None or (self.grad_chunk_hook is not None and self._dw_done >= self._dw_split):
-                self._dw_table_b.launch(scale=self._inv_scale, out_base=self._gflat)
+                self._dw_table_b.launch(scale=self._unpack_scale(), out_base=self._gflat)
                 self._last_gflat = [(self._gflat[:self._g_split], self._chunk_handle), (self._gflat[self._g_split:], None)]
             else:
-                self._dw_table.launch(scale=self._inv_scale, out_base=self._gflat)
+                self._dw_table.launch(scale=self._unpack_scale(), out_base=self._gflat)
                 self._last_gflat = [(self._gflat, None)]
             self._dw_ready = False
         elif self._dw_order and (self._dw_table is None or self._dw_table_n != len(self._dw_order)):
@@ -379,7 +405,7 @@ class UNetEngine:
             acc, split = 0, len(jobs)
             for i, (wp, n_param) in enumerate(self._dw_order):
                 acc += n_param
-                if acc >= 0.6 * sum(n for _, n in self._dw_order) and i + 1 < len(jobs):
+                if acc >= CHUNK_SPLIT_FRACTION * sum(n for _, n in self._dw_order) and i + 1 < len(jobs):
                     split = i + 1
                     break
             self._dw_split = split
@@ -395,6 +421,11 @@ class UNetEngine:
         the layout).  One or two all-reduces cover 99.9 % of the gradient bytes without flattening copies; a piece
         with a handle was already sent by grad_chunk_hook during the backward pass."""
         return self._last_gflat
+
+    def conv_weight_gradients_prescaled(self) -> bool:
+        """True when the conv weight gradients (flat buffers AND the tensors of the first, layer-by-layer backward)
+        were already multiplied by grad_prescale (1 / world): the all-reduce must then only sum them."""
+        return self.grad_prescale is not None
 
     # ------------------------------------------------------------------ packed weights: one batched launch per step
     def _pw(self, dp, w):

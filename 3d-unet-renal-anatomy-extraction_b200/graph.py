@@ -29,9 +29,17 @@ def _make_capturable(optimizer):
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, optimizer, warmup: int = 3, allreduce: bool = True):
+    def __init__(self, model, loss_fn, optimizer, warmup: int = 3, allreduce: bool = True, capture_collectives: bool = True,
+                 overlap: bool = True):
+        """capture_collectives (data parallel only): capture the NCCL gradient all-reduce INSIDE the step's graph (one
+        graph per step, no host round trip between backward and optimizer); with `overlap` the first ~85 % of the
+        gradient bytes (head, decoder, bottom level) are all-reduced on NCCL's stream while the encoder half of the
+        backward pass is still running, and 1 / world is folded into the gradient unpack.  False = round-1 behaviour:
+        two graphs with an eager all-reduce between them."""
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.warmup, self.allreduce = warmup, allreduce
+        self.capture_collectives, self.overlap = capture_collectives, overlap
+        self.mode = None                # "single" | "one-graph-dp" | "two-graph-dp" once captured
         self.calls = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_image = self.static_label = self.static_loss = self.static_logits = None
@@ -70,6 +78,11 @@ class GraphedTrainStep:
         self.calls += 1
         world = parallel.rank_world()[1]
         split = world > 1 and self.allreduce
+        if split and self.calls == 2 and self.capture_collectives:
+            # engines exist after the first step: average inside the unpack, send the first chunk during backward
+            parallel.prescale_gradients(self.model)
+            if self.overlap:
+                parallel.overlap_gradient_all_reduce(self.model)
         self.replayed = False
         if self.key is not None and key != self.key:
             # another batch shape (a short last batch) or mode (first train batch after a validation pass): eager, and
@@ -98,11 +111,30 @@ class GraphedTrainStep:
             launches0 = ops.LAUNCHES
             g = torch.cuda.CUDAGraph()
             self.optimizer.zero_grad(set_to_none=True)
-            with torch.cuda.graph(g):
-                if split:
-                    self.static_loss, self.static_logits = self._fwd_bwd(self.static_image, self.static_label)
-                else:
-                    self.static_loss, self.static_logits = self._eager(self.static_image, self.static_label)
+            one_graph = split and self.capture_collectives
+            if one_graph:
+                try:
+                    with torch.cuda.graph(g):
+                        self.static_loss, self.static_logits = self._eager(self.static_image, self.static_label)
+                    self.mode = "one-graph-dp"
+                except Exception as e:          # NCCL capture refused: fall back to two graphs around an eager all-reduce
+                    import warnings
+                    warnings.warn(f"GraphedTrainStep: capturing the gradient all-reduce failed ({e!r}); using two graphs")
+                    torch.cuda.synchronize()
+                    one_graph = False
+                    parallel.overlap_gradient_all_reduce(self.model, enable=False)
+                    g = torch.cuda.CUDAGraph()
+                    self.optimizer.zero_grad(set_to_none=True)
+            if one_graph:
+                split = False
+            else:
+                with torch.cuda.graph(g):
+                    if split:
+                        self.static_loss, self.static_logits = self._fwd_bwd(self.static_image, self.static_label)
+                        self.mode = "two-graph-dp"
+                    else:
+                        self.static_loss, self.static_logits = self._eager(self.static_image, self.static_label)
+                        self.mode = "single"
             self.graph = g
             if split:
                 g2 = torch.cuda.CUDAGraph()
@@ -123,7 +155,7 @@ class GraphedTrainStep:
             eng._last_gflat = flats
         self.replayed, self.last_label = True, self.static_label
         self.graph.replay()
-        if split:
+        if self.graph_opt is not None:
             parallel.all_reduce_gradients(self.model)
             self.graph_opt.replay()
         return self.static_loss, self.static_logits

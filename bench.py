@@ -260,8 +260,11 @@ def main():
     ap.add_argument("--eager", action="store_true",
                     help="launch every kernel of the step from Python instead of replaying the captured step "
                          "(GraphedTrainStep, the library's Trainer(cuda_graph=True) path)")
-    ap.add_argument("--overlap", action="store_true",
-                    help="N > 1: all-reduce the first 2/3 of the weight gradients during the encoder half of the backward pass")
+    ap.add_argument("--two-graph", action="store_true",
+                    help="N > 1: round-1 behaviour -- two graphs per step with an eager NCCL all-reduce between them "
+                         "(default: ONE graph per step with the all-reduce captured inside it)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: do not send the first ~85 %% of the gradient bytes during the encoder half of the backward pass")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -277,6 +280,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the all-reduce of the first gradient chunk runs UNDER the backward pass and takes SMs from the persistent
+        # one-CTA-per-SM tensor kernels: 32 CTAs measured best on 2 B200s (19.29 ms; 16 / 8 / 4 CTAs: 19.65 / 20.03 / 20.60,
+        # 64: 19.50); overridable from the environment
+        os.environ.setdefault("NCCL_MAX_CTAS", "32")
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = args.steps
@@ -308,7 +315,9 @@ def main():
 
     # default: the whole step replayed as a CUDA graph (one graph at N = 1; at N > 1 two graphs with the NCCL all-reduce
     # issued eagerly between them) -- the same kernels, without ~530 Python-side launches per step
-    stepper = None if args.eager else unet3d_b200.GraphedTrainStep(model, loss_fn, opt, warmup=3)
+    stepper = None if args.eager else unet3d_b200.GraphedTrainStep(model, loss_fn, opt, warmup=3,
+                                                                   capture_collectives=not args.two_graph,
+                                                                   overlap=not args.no_overlap)
 
     def step(img, lab):
         if stepper is None:
@@ -366,9 +375,10 @@ def main():
 
     for i in range(max(W, 3) + (0 if stepper is None else 2)):      # 3 eager steps, then capture + one replay
         step(d_img, d_lab)
-        if i == 0 and world > 1 and args.overlap:
-            # engines exist after the first forward: from now on the first ~2/3 of the weight gradients are all-reduced
-            # while the encoder half of the backward pass is still running
+        if i == 0 and world > 1 and stepper is None and not args.no_overlap:
+            # eager launches: engines exist after the first forward; from now on 1 / world is folded into the gradient
+            # unpack and the first ~85 % of the gradient bytes are all-reduced during the encoder half of the backward pass
+            unet3d_b200.parallel.prescale_gradients(model)
             unet3d_b200.parallel.overlap_gradient_all_reduce(model)
     torch.cuda.synchronize()
     ops.check_device_errors()
@@ -392,6 +402,7 @@ def main():
     graphed, stepper = stepper, None          # the event pairs need eager launches
     timed(K, e2e=False, lead_sleep=True)
     stepper = graphed
+    dp_mode = graphed.mode if graphed is not None else "eager"
     prof = ops.PROFILE
     ops.PROFILE = None
     torch.cuda.synchronize()
@@ -593,7 +604,8 @@ def main():
                 "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": WORKLOAD if pe == 128 else f"REDUCED patch {pe}^3 (not the metric's config)",
-                           "global_batch": BATCH * world, "patch": [pe, pe, pe], "parallelism": f"dp{world}", "cuda_graph": used_graph,
+                           "global_batch": BATCH * world, "patch": [pe, pe, pe], "parallelism": f"dp{world}", "cuda_graph": used_graph, "dp_mode": dp_mode if world > 1 else None,
+                           "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS") if world > 1 else None,
                            "timed_region": "zero_grad + forward + DiceLoss + backward + grad all-reduce (N>1) + Adam step",
                            "l2": "256 MB buffer written between timed iterations (L2 flush); activations per step >> L2",
                            "tensor_frac_of_step": (FWD_BWD_FLOP_PER_VOXEL * BATCH * pe ** 3 / (ms * 1e-3) / 1e12) /
@@ -605,7 +617,19 @@ def main():
                 **extras}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # tear-down: graphs that hold captured NCCL kernels must go before the process group does, and a communicator
+        # destroy that blocks (seen with captured collectives) must never keep the job alive after the result is printed
+        stepper = graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
         dist.destroy_process_group()
+        killer.cancel()
 
 
 if __name__ == "__main__":

@@ -68,8 +68,8 @@ _SIGS = {
     "unet3d_head_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "unet3d_loss_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_void_p]),
     "unet3d_loss_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_int, C.c_void_p]),
-    "unet3d_sw_accumulate": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 10 + [C.c_void_p]),
-    "unet3d_sw_finalize": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_longlong, C.c_void_p]),
+    "unet3d_sw_accumulate": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 11 + [C.c_void_p]),
+    "unet3d_sw_finalize": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_longlong, C.c_void_p]),
     "unet3d_att_gate_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_int, C.c_void_p]),
     "unet3d_att_gate_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "unet3d_att_mid_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),

@@ -224,15 +224,13 @@ int unet3d_loss_bwd(const float* logits, const long long* target, const float* c
                         (cudaStream_t)stream),
                "loss_bwd");
 }
-int unet3d_sw_accumulate(const float* logits, const float* window, float* result, float* weight, int K, int px,
-                         int py, int pz, int x0, int y0, int z0, int X, int Y, int Z, void* stream) {
-  return check(sw_accumulate(logits, window, result, weight, K, px, py, pz, x0, y0, z0, X, Y, Z, num_sms(),
-                             (cudaStream_t)stream),
+int unet3d_sw_accumulate(const float* logits, const float* window, long long* acc, int K, int px, int py, int pz,
+                         int x0, int y0, int z0, int X, int Y, int Z, int Xs, void* stream) {
+  return check(sw_accumulate(logits, window, acc, K, px, py, pz, x0, y0, z0, X, Y, Z, Xs, num_sms(), (cudaStream_t)stream),
                "sw_accumulate");
 }
-int unet3d_sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K,
-                       long long XYZ, void* stream) {
-  return check(sw_finalize(result, weight, labels, probs, K, XYZ, num_sms(), (cudaStream_t)stream), "sw_finalize");
+int unet3d_sw_finalize(const long long* acc, uint8_t* labels, float* probs, int K, long long n, void* stream) {
+  return check(sw_finalize(acc, labels, probs, K, n, num_sms(), (cudaStream_t)stream), "sw_finalize");
 }
 int unet3d_maxpool3d_fwd(const void* x, void* out, uint8_t* code, int N, int D, int H, int W, int Cp, int act_f16,
                          void* stream) {

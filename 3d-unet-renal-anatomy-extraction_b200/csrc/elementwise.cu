@@ -998,13 +998,26 @@ __global__ void loss_bwd_kernel(const float* __restrict__ logits, const long lon
 // ---------------------------------------------------------------------------------------------
 // Sliding-window blend (trainer.py:72-96): result[:, tile] += softmax(logits) * w ; weight[tile] += w
 // then result / weight -> argmax (uint8) or probabilities.  w == null is the reference's uniform blend.
+//
+// The sums are kept in 64-bit FIXED POINT (scale 2^54): every fp32 term p * w converts exactly, integer addition is
+// associative, so the sums -- and with them the label map -- do not depend on the order in which windows are added:
+// the windows of one volume can be dealt to any number of GPUs and reduced in any order (NCCL reduce-scatter of
+// int64) and give bit-identical labels.  (The reference adds fp32 in window order; its label map differs from the
+// exact one only where two class probabilities tie to ~1e-7.)  Up to 512 overlapping windows fit below 2^63.
+//
+// Layout of `acc`: [n_slab][K + 1][Xs][Y][Z] int64, x = slab * Xs + xs; channel K is the weight sum.  One slab
+// (Xs = X) in a single-process run; with R ranks Xs = ceil(X / R) and slab r is what rank r owns after the
+// reduce-scatter.
 // ---------------------------------------------------------------------------------------------
+constexpr float SW_FIXED_SCALE = 18014398509481984.f;        // 2^54
+
 template <int KMAX>
 __global__ void sw_accumulate_kernel(const float* __restrict__ logits /*[K][px][py][pz]*/,
                                      const float* __restrict__ window /*[px][py][pz] or null*/,
-                                     float* __restrict__ result /*[K][X][Y][Z]*/, float* __restrict__ weight /*[X][Y][Z]*/,
-                                     int K, int px, int py, int pz, int x0, int y0, int z0, int X, int Y, int Z) {
+                                     long long* __restrict__ acc, int K, int px, int py, int pz, int x0, int y0, int z0,
+                                     int Xs, int Y, int Z) {
   const long long P = (long long)px * py * pz;
+  const size_t YZ = (size_t)Y * Z;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
     const int iz = (int)(i % pz), iy = (int)((i / pz) % py), ix = (int)(i / ((long long)pz * py));
     float z[KMAX], p[KMAX], lse;
@@ -1016,39 +1029,41 @@ __global__ void sw_accumulate_kernel(const float* __restrict__ logits /*[K][px][
       softmax_k<KMAX>(z, K, p, lse);
     }
     const float wv = window ? __ldg(&window[i]) : 1.f;
-    const size_t o = ((size_t)(x0 + ix) * Y + (y0 + iy)) * Z + (z0 + iz);
-    const size_t XYZ = (size_t)X * Y * Z;
+    const int x = x0 + ix, slab = x / Xs, xs = x - slab * Xs;
+    long long* a = acc + ((size_t)slab * (K + 1) * Xs + xs) * YZ + (size_t)(y0 + iy) * Z + (z0 + iz);
+    const size_t cstride = (size_t)Xs * YZ;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
-      if (k < K) result[(size_t)k * XYZ + o] += p[k] * wv;
-    weight[o] += wv;
+      if (k < K) a[(size_t)k * cstride] += __float2ll_rn(p[k] * wv * SW_FIXED_SCALE);
+    a[(size_t)K * cstride] += __float2ll_rn(wv * SW_FIXED_SCALE);
   }
 }
 
 template <int KMAX>
-__global__ void sw_finalize_kernel(const float* __restrict__ result, const float* __restrict__ weight,
-                                   uint8_t* __restrict__ labels, float* __restrict__ probs /*[X][Y][Z][K] or null*/,
-                                   int K, long long XYZ) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < XYZ; i += (long long)gridDim.x * blockDim.x) {
-    const float wv = weight[i];
-    float r[KMAX];
+__global__ void sw_finalize_kernel(const long long* __restrict__ acc /*[K + 1][n]*/, uint8_t* __restrict__ labels,
+                                   float* __restrict__ probs /*[n][K] or null*/, int K, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long wsum = acc[(size_t)K * n + i];
+    long long s[KMAX];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) r[k] = k < K ? result[(size_t)k * XYZ + i] / wv : 0.f;   // 0/0 = NaN where uncovered
+    for (int k = 0; k < KMAX; ++k) s[k] = k < K ? acc[(size_t)k * n + i] : 0;
     if (probs) {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
-        if (k < K) probs[(size_t)i * K + k] = r[k];
+        if (k < K) probs[(size_t)i * K + k] = wsum == 0 ? __int_as_float(0x7fc00000) /* 0/0 = NaN where uncovered */
+                                                         : (float)((double)s[k] / (double)wsum);
     }
     if (labels) {
-      // argmax(softmax(r)) == argmax(r); NaN (uncovered) -> torch.argmax picks index 0 (first NaN)
+      // argmax(softmax(result / weight)) == argmax of the integer sums (same positive divisor): first maximum wins like
+      // torch.argmax; uncovered voxels (NaN in the reference) -> index 0
       int best = 0;
       if (K == 1) {
-        best = (int)rintf(r[0]);      // trainer.py:91-96: squeeze + np.round
-      } else if (!(r[0] != r[0])) {
-        float bv = r[0];
+        best = wsum == 0 ? 0 : (int)rintf((float)((double)s[0] / (double)wsum));      // trainer.py:91-96: squeeze + np.round
+      } else if (wsum != 0) {
+        long long bv = s[0];
 #pragma unroll
         for (int k = 1; k < KMAX; ++k)
-          if (k < K && r[k] > bv) { bv = r[k]; best = k; }
+          if (k < K && s[k] > bv) { bv = s[k]; best = k; }
       }
       labels[i] = (uint8_t)best;
     }
@@ -1561,20 +1576,19 @@ int loss_bwd(const float* logits, const long long* target, const float* coef, co
   return U3D_CHECK_LAUNCH();
 }
 
-int sw_accumulate(const float* logits, const float* window, float* result, float* weight, int K, int px, int py, int pz,
-                  int x0, int y0, int z0, int X, int Y, int Z, int num_sms, cudaStream_t s) {
+int sw_accumulate(const float* logits, const float* window, long long* acc, int K, int px, int py, int pz,
+                  int x0, int y0, int z0, int X, int Y, int Z, int Xs, int num_sms, cudaStream_t s) {
   if (K < 1 || K > 8) return U3D_ERR_UNSUPPORTED;
-  if (x0 < 0 || y0 < 0 || z0 < 0 || x0 + px > X || y0 + py > Y || z0 + pz > Z) return U3D_ERR_INVALID;
+  if (x0 < 0 || y0 < 0 || z0 < 0 || x0 + px > X || y0 + py > Y || z0 + pz > Z || Xs < 1) return U3D_ERR_INVALID;
   const int g = grid_for((long long)px * py * pz, 256 * 2, num_sms, 8);
-  sw_accumulate_kernel<8><<<g, 256, 0, s>>>(logits, window, result, weight, K, px, py, pz, x0, y0, z0, X, Y, Z);
+  sw_accumulate_kernel<8><<<g, 256, 0, s>>>(logits, window, acc, K, px, py, pz, x0, y0, z0, Xs, Y, Z);
   return U3D_CHECK_LAUNCH();
 }
 
-int sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K, long long XYZ,
-                int num_sms, cudaStream_t s) {
+int sw_finalize(const long long* acc, uint8_t* labels, float* probs, int K, long long n, int num_sms, cudaStream_t s) {
   if (K < 1 || K > 8) return U3D_ERR_UNSUPPORTED;
-  const int g = grid_for(XYZ, 256 * 2, num_sms, 8);
-  sw_finalize_kernel<8><<<g, 256, 0, s>>>(result, weight, labels, probs, K, XYZ);
+  const int g = grid_for(n, 256 * 2, num_sms, 8);
+  sw_finalize_kernel<8><<<g, 256, 0, s>>>(acc, labels, probs, K, n);
   return U3D_CHECK_LAUNCH();
 }
 

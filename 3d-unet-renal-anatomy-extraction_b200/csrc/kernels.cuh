@@ -25,10 +25,9 @@ int loss_fwd(const float* logits, const long long* target, double* sums, int K, 
              int num_sms, cudaStream_t s);
 int loss_bwd(const float* logits, const long long* target, const float* coef, const float* gscale, float* dlogits, int K,
              int N, long long V, float gamma, int use_focal, int num_sms, cudaStream_t s);
-int sw_accumulate(const float* logits, const float* window, float* result, float* weight, int K, int px, int py, int pz,
-                  int x0, int y0, int z0, int X, int Y, int Z, int num_sms, cudaStream_t s);
-int sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K, long long XYZ,
-                int num_sms, cudaStream_t s);
+int sw_accumulate(const float* logits, const float* window, long long* acc, int K, int px, int py, int pz,
+                  int x0, int y0, int z0, int X, int Y, int Z, int Xs, int num_sms, cudaStream_t s);
+int sw_finalize(const long long* acc, uint8_t* labels, float* probs, int K, long long n, int num_sms, cudaStream_t s);
 int maxpool_fwd(const bf16* x, bf16* out, uint8_t* code, int N, int D, int H, int W, int Cp, int af, int num_sms,
                 cudaStream_t s);
 int maxpool_bwd(const bf16* dout, const uint8_t* code, bf16* dx, int N, int D, int H, int W, int Cp, int num_sms,

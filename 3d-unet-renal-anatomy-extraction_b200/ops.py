@@ -504,22 +504,30 @@ def loss_bwd(logits, target, coef, gscale, dlogits, gamma, use_focal):
                    "unet3d_loss_bwd")
 
 
-def sw_accumulate(logits, window, result, weight, origin):
+def sw_accumulate(logits, window, acc, origin, shape):
+    """acc: int64 (n_slab, K + 1, Xs, Y, Z) fixed-point sums (see csrc/elementwise.cu: sw_accumulate_kernel); shape = the
+    (padded) volume extent (X, Y, Z) the window origin refers to, X <= n_slab * Xs."""
     k, px, py, pz = logits.shape[-4:]
-    _, X, Y, Z = result.shape
+    n_slab, k1, Xs, Y, Z = acc.shape
+    X = int(shape[0])
+    assert acc.dtype == torch.int64 and acc.is_contiguous() and k1 == k + 1 and X <= n_slab * Xs
+    assert (Y, Z) == (int(shape[1]), int(shape[2]))
     _count()
-    with _Timed("sw_accumulate", 0.0, px * py * pz * (12.0 * k + 8.0 + (4.0 if window is not None else 0.0))):
-        _lib.check(_lib.lib().unet3d_sw_accumulate(logits.data_ptr(), _ptr(window), result.data_ptr(), weight.data_ptr(), k,
-                                                   px, py, pz, origin[0], origin[1], origin[2], X, Y, Z, _stream()),
+    with _Timed("sw_accumulate", 0.0, px * py * pz * (4.0 * k + 16.0 * (k + 1) + (4.0 if window is not None else 0.0))):
+        _lib.check(_lib.lib().unet3d_sw_accumulate(logits.data_ptr(), _ptr(window), acc.data_ptr(), k, px, py, pz,
+                                                   origin[0], origin[1], origin[2], X, Y, Z, Xs, _stream()),
                    "unet3d_sw_accumulate")
 
 
-def sw_finalize(result, weight, labels, probs):
-    k = result.shape[0]
+def sw_finalize(slab, labels, probs):
+    """slab: int64 (K + 1, ...) sums of one slab; labels uint8 (...) and / or probs fp32 (..., K)."""
+    k = slab.shape[0] - 1
+    n = slab[0].numel()
+    assert slab.dtype == torch.int64 and slab.is_contiguous()
     _count()
-    with _Timed("sw_finalize", 0.0, weight.numel() * (4.0 * k + 4.0 + (1.0 if labels is not None else 0.0) + (4.0 * k if probs is not None else 0.0))):
-        _lib.check(_lib.lib().unet3d_sw_finalize(result.data_ptr(), weight.data_ptr(), _ptr(labels), _ptr(probs), k,
-                                                 weight.numel(), _stream()), "unet3d_sw_finalize")
+    with _Timed("sw_finalize", 0.0, n * (8.0 * (k + 1) + (1.0 if labels is not None else 0.0) + (4.0 * k if probs is not None else 0.0))):
+        _lib.check(_lib.lib().unet3d_sw_finalize(slab.data_ptr(), _ptr(labels), _ptr(probs), k, n, _stream()),
+                   "unet3d_sw_finalize")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -188,8 +188,9 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
     ensure = None
     if isinstance(x, tuple):               # (device volume, ensure(xlo, xhi)): slabs are uploaded on demand
         x, ensure = x
-    result = torch.zeros((num_classes, *shape), dtype=torch.float32, device=device)
-    weight = torch.zeros(shape, dtype=torch.float32, device=device)
+    # 2^54 fixed-point sums (exact, order-independent: see ops.sw_accumulate), one x-slab per rank; channel K = weight sum
+    xs_len = -(-shape[0] // world)
+    acc = torch.zeros((world, num_classes + 1, xs_len, shape[1], shape[2]), dtype=torch.int64, device=device)
     if isinstance(window, str):
         if window != "gaussian":
             raise ValueError(window)
@@ -251,7 +252,7 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
                     static_in = static_in_new
             first = False
             for i, origin in enumerate(group):
-                ops.sw_accumulate(logits[i].contiguous(), wdev, result, weight, origin)
+                ops.sw_accumulate(logits[i].contiguous(), wdev, acc, origin, shape)
             if verbose:
                 it.update(len(group))
             if b0 < 6 * wb:
@@ -261,14 +262,29 @@ def _predict_padded(upload, shape, model, num_classes, patch, step_per_patch, ve
     model.train(was_training)
     mark(f"{len(mine)} windows")
     if world > 1:
-        parallel.all_reduce_sum([result, weight])
-        mark("all-reduce of the blend buffers")
-    if one_hot:
-        res = torch.empty((*shape, num_classes), dtype=torch.float32, device=device)
-        ops.sw_finalize(result, weight, None, res)
+        # every rank ends up with the complete sums of ITS x-slab (int64 addition: any reduction order gives the same
+        # bits), finalises that slab, and the uint8 label slabs (or probability slabs) are gathered
+        import torch.distributed as dist
+        mine = torch.empty(acc.shape[1:], dtype=torch.int64, device=device)
+        dist.reduce_scatter_tensor(mine, acc)
+        mark("reduce-scatter of the blend sums")
     else:
-        res = torch.empty(shape, dtype=torch.uint8, device=device)
-        ops.sw_finalize(result, weight, res, None)
+        mine = acc[0]
+    slab_shape = (xs_len, shape[1], shape[2])
+    if one_hot:
+        part = torch.empty((*slab_shape, num_classes), dtype=torch.float32, device=device)
+        ops.sw_finalize(mine, None, part)
+    else:
+        part = torch.empty(slab_shape, dtype=torch.uint8, device=device)
+        ops.sw_finalize(mine, part, None)
+    if world > 1:
+        full = torch.empty((world, *part.shape), dtype=part.dtype, device=device)
+        dist.all_gather_into_tensor(full, part)
+        res = full.view(world * xs_len, *part.shape[1:])[:shape[0]]
+        if not res.is_contiguous():
+            res = res.contiguous()
+    else:
+        res = part
     mark("finalize")
     return res
 

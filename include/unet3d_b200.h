@@ -176,12 +176,15 @@ int unet3d_loss_fwd(const float* logits, const long long* target, double* sums, 
 int unet3d_loss_bwd(const float* logits, const long long* target, const float* coef, const float* grad_scale,
                     float* dlogits, int K, int N, long long V, float gamma, int use_focal, void* stream);
 
-/* Sliding-window blending (trainer.py:72-96): accumulate one window's softmax (uniform when window==NULL,
- * else weighted), then normalise + argmax / probabilities. */
-int unet3d_sw_accumulate(const float* logits, const float* window, float* result, float* weight, int K, int px,
-                         int py, int pz, int x0, int y0, int z0, int X, int Y, int Z, void* stream);
-int unet3d_sw_finalize(const float* result, const float* weight, uint8_t* labels, float* probs, int K,
-                       long long XYZ, void* stream);
+/* Sliding-window blending (trainer.py:72-96: result[:, tile] += softmax(out); result_n[tile] += 1; result / result_n;
+ * argmax).  acc: int64 [n_slab][K + 1][Xs][Y][Z], x = slab * Xs + xs, channel K = the weight sum; sums are 2^54 fixed
+ * point, so they (and the label map) do not depend on the order in which windows -- or the partial buffers of several
+ * GPUs -- are added.  window == NULL: uniform blending (the reference), else a (px, py, pz) fp32 weight map.
+ * unet3d_sw_finalize works on ONE slab ([K + 1][n] with n = Xs * Y * Z): labels uint8 [n] (first maximum wins; uncovered
+ * voxels -> 0) and / or probs fp32 [n][K] (NaN where uncovered, like the reference's 0 / 0). */
+int unet3d_sw_accumulate(const float* logits, const float* window, long long* acc, int K, int px, int py, int pz,
+                         int x0, int y0, int z0, int X, int Y, int Z, int Xs, void* stream);
+int unet3d_sw_finalize(const long long* acc, uint8_t* labels, float* probs, int K, long long n, void* stream);
 
 /* MaxPoolBlock = nn.MaxPool3d(kernel_size=2, stride=2) (network.py:452-463) on 16-bit NDHWC (N, D, H, W, Cp), D/H/W even.
  * code: uint8 (N, D/2, H/2, W/2, Cp) = kd*4 + kh*2 + kw of the winner, PyTorch's scan order and tie/NaN rule, i.e.

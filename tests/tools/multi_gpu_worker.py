@@ -1,6 +1,6 @@
 """Multi-GPU checks, run under torchrun on one box: sliding-window inference sharded over the ranks must
-return the labels of a single process bit for bit (up to the fp32 summation order of overlapping windows: compared as
-label agreement), and the two data-parallel loss modes:
+return the labels AND probabilities of a single process bit for bit (fixed-point blend sums), the Trainer must keep the
+ranks in lock step, and the two data-parallel loss modes:
 
   (i)  local Dice (default): every rank's loss on its own shard, gradients averaged == mean of the shard gradients;
   (ii) global_batch=True   : per-class sums all-reduced inside the loss, gradients SUMMED == the gradient of ONE process
@@ -99,18 +99,53 @@ if not (worst < 2e-2 and worst_buf < 1e-5):
     print(f"[rank {rank}] SyncBN check failed: gradients {worst:.3e}, running statistics {worst_buf:.3e}", flush=True)
 ok = ok and worst < 2e-2 and worst_buf < 1e-5
 import numpy as np
+# ---- sliding-window inference, windows dealt to the ranks: the blend sums are 2^54 fixed point (exact integer addition),
+# so the sharded result must equal the single-process result BIT FOR BIT -- labels and probabilities, uniform and Gaussian
 vol = np.random.RandomState(3).standard_normal((96, 72, 40, 1)).astype(np.float32)
-sharded = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False)
-single = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, distributed=False)
-agree = float((sharded == single).mean())
-probs_s = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, one_hot=True)
-probs_1 = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, one_hot=True, distributed=False)
-dmax = float(np.nanmax(np.abs(probs_s - probs_1)))
+for window in (None, "gaussian"):
+    sharded = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, window=window)
+    single = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, distributed=False, window=window)
+    probs_s = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, one_hot=True, window=window)
+    probs_1 = unet3d_b200.predict_per_patch(vol, model, 3, (32, 32, 32), 2, verbose=False, one_hot=True, distributed=False,
+                                            window=window)
+    same_l = bool(np.array_equal(sharded, single))
+    same_p = bool(np.array_equal(probs_s.view(np.uint32), probs_1.view(np.uint32)))
+    if rank == 0:
+        print(f"sliding-window inference over {world} ranks vs one process ({window or 'uniform'}): labels bit-identical {same_l}, "
+              f"probabilities bit-identical {same_p} (NaN border voxels: {int(np.isnan(probs_1).any(-1).sum())})")
+    if not (same_l and same_p):
+        print(f"[rank {rank}] inference check failed ({window}): labels {same_l}, probabilities {same_p}", flush=True)
+    ok = ok and same_l and same_p
+
+# ---- Trainer under data parallelism: 7 cases over 2 ranks, different seeds per rank -> one split, equal step
+# counts, identical parameters and learning rates afterwards
+class _Cases(torch.utils.data.Dataset):
+    def __init__(self):
+        g = torch.Generator().manual_seed(11)
+        self.x = torch.randn(7, 1, 16, 16, 16, generator=g)
+        self.y = (self.x[:, 0] > 0.3).long() + (self.x[:, 0] > 1.0).long()
+    def __len__(self):
+        return 7
+    def __getitem__(self, i):
+        return {"image": self.x[i], "label": self.y[i]}
+
+torch.manual_seed(100 + rank)
+np.random.seed(100 + rank)
+tm = unet3d_b200.ResUnet3D(num_pool=2, num_features=8, out_channels=3).to(dev)
+opt = torch.optim.Adam(tm.parameters(), lr=1e-3)
+tr = unet3d_b200.Trainer(tm, opt, unet3d_b200.DiceLoss(), _Cases(), batch_size=2, dataloader_kwargs={"num_workers": 0},
+                         valid_split=0.3, metrics={"dice": unet3d_b200.Dice()})
+tr.fit(num_epochs=2)
+flat = torch.cat([p.detach().reshape(-1) for p in tm.parameters()])
+both = [torch.zeros_like(flat) for _ in range(world)]
+dist.all_gather(both, flat)
+splits = [None] * world
+dist.all_gather_object(splits, (tr.train_indices, tr.valid_indices, tr.best_result["loss"]))
+same_params = all(torch.equal(both[0], b) for b in both[1:])
+same_split = all(s == splits[0] for s in splits[1:])
 if rank == 0:
-    print(f"sliding-window inference over {world} ranks vs one process: label agreement {agree:.6f}, max |dp| {dmax:.2e}")
-if not (agree > 0.9999 and dmax < 1e-5):
-    print(f"[rank {rank}] inference check failed: agreement {agree}, max |dp| {dmax}", flush=True)
-ok = ok and agree > 0.9999 and dmax < 1e-5
+    print(f"Trainer on {world} ranks, 7 cases: identical parameters after 2 epochs {same_params}, one split / one epoch mean {same_split}")
+ok = ok and same_params and same_split
 if not ok:
     print(f"[rank {rank}] MISMATCH", flush=True)
 dist.barrier()

@@ -27,11 +27,14 @@ from . import plan as P
 
 IN_EPS = 1e-5      # nn.InstanceNorm3d default (network.py:163,388: no eps passed)
 import os as _os
-# overlapped all-reduce: the first chunk = head, decoder, bottom level and the first level-3 blocks = ~90 % of the gradient
-# bytes, complete about half way into the backward pass; the rest of the encoder backward (the heaviest kernels) hides
-# its transfer, and a ~30 MB second chunk is left behind the backward pass.  Measured on 2 B200s (18.93 ms on one GPU):
-# split 0.8 -> 19.57 ms, 0.9 -> 19.29, 0.97 -> 19.50 (NCCL_MAX_CTAS=32; with 16 / 8 / 4 CTAs 19.65 / 20.03 / 20.60).
-CHUNK_SPLIT_FRACTION = float(_os.environ.get("U3D_CHUNK_SPLIT", "0.9"))
+# overlapped all-reduce: the gradient bytes are cut into chunks in the order the backward pass completes them --
+#   chunk 1 = head, decoder and bottom level (72 % of the bytes, complete ~40 % into the backward pass),
+#   chunk 2 = pooling block 3, encoder level 3, pooling block 2 (up to 97 %), chunk 3 = the rest (~10 MB, sent behind the pass)
+# -- and every chunk but the last is all-reduced on NCCL's stream while the backward pass goes on.  Measured, ms per step:
+#   2 B200s (18.93 on one GPU): no overlap 19.84; one cut at 0.8 / 0.9 / 0.97: 19.57 / 19.29-19.59 / 19.50; cuts 0.72,0.97: 19.54
+#   8 B200s: no overlap 20.11; one cut at 0.9: 19.92; cuts 0.72,0.97: 19.82 (32 CTAs) / 19.79 (16 CTAs)
+# What stays exposed (~0.85 ms at 8 GPUs) is SM contention: NCCL's CTAs cannot share an SM with the 227 KB tensor CTAs.
+CHUNK_SPLIT_FRACTIONS = tuple(float(v) for v in _os.environ.get("U3D_CHUNK_SPLIT", "0.72,0.97").split(","))
 PACK_SYNC_LAYERS = 5   # weight packs made on the main stream at the start of a pass; the rest overlaps the first layers
 
 
@@ -92,8 +95,9 @@ class UNetEngine:
         self._dw_arena, self._gflat, self._g_total, self._dw_ready = None, None, 0, False
         self._z_arena, self._z_used, self._z_demand, self._z_size = None, 0, 0, 0
         self._last_gflat = None
-        self._dw_done, self._dw_split, self._g_split, self._chunk_handle = 0, -1, 0, None
-        self._dw_table_a = self._dw_table_b = None
+        self._dw_done = 0
+        self._chunks = []              # overlapped all-reduce: [(wgrad calls done when the chunk is complete, flat begin, flat end, UnpackTable)]
+        self._chunk_next, self._chunk_handles = 0, []
         self._infer_graphs = {}          # predict_per_patch's captured window forwards, by (batch, channels, patch, precision)
         self._infer_sig = None           # what the packed weights / graphs of the last no-grad forward were built from
 
@@ -344,7 +348,7 @@ class UNetEngine:
         """Called at the start of a backward pass: zero the accumulator arena, allocate this step's flat gradient buffer."""
         self._dw_ready = False
         self._dw_done = 0
-        self._chunk_handle = None
+        self._chunk_next, self._chunk_handles = 0, []
         if self._dw_table is not None and self._dw_table_n == len(self._dw_order):
             self._dw_arena.zero_()
             self._gflat = torch.empty(self._g_total, dtype=torch.float32, device=self.device)
@@ -371,16 +375,24 @@ class UNetEngine:
         (parallel.overlap_gradient_all_reduce), unpack that chunk now and hand its slice of the flat buffer to the hook
         -- the NCCL all-reduce of the prefix then overlaps the encoder half of the backward pass."""
         self._dw_done += 1
-        if self._dw_ready and self.grad_chunk_hook is not None and self._dw_done == self._dw_split:
-            self._dw_table_a.launch(scale=self._unpack_scale(), out_base=self._gflat)
-            self._chunk_handle = self.grad_chunk_hook(self._gflat[:self._g_split])
+        if self._dw_ready and self.grad_chunk_hook is not None:
+            while self._chunk_next < len(self._chunks) - 1 and self._dw_done >= self._chunks[self._chunk_next][0]:
+                _, g0, g1, table = self._chunks[self._chunk_next]
+                table.launch(scale=self._unpack_scale(), out_base=self._gflat)
+                self._chunk_handles.append((self._gflat[g0:g1], self.grad_chunk_hook(self._gflat[g0:g1])))
+                self._chunk_next += 1
 
     def _finish_wgrads(self):
         self._last_gflat = None
         if self._dw_ready:
-            if self._chunk_handle is not None or (self.grad_chunk_hook is not None and self._dw_done >= self._dw_split):
-                self._dw_table_b.launch(scale=self._unpack_scale(), out_base=self._gflat)
-                self._last_gflat = [(self._gflat[:self._g_split], self._chunk_handle), (self._gflat[self._g_split:], None)]
+            if self.grad_chunk_hook is not None and len(self._chunks) > 1:
+                # chunks whose hook has not fired yet (normally only the last one) are unpacked now, un-sent
+                rest = []
+                for i in range(self._chunk_next, len(self._chunks)):
+                    _, g0, g1, table = self._chunks[i]
+                    table.launch(scale=self._unpack_scale(), out_base=self._gflat)
+                    rest.append((self._gflat[g0:g1], None))
+                self._last_gflat = self._chunk_handles + rest
             else:
                 self._dw_table.launch(scale=self._unpack_scale(), out_base=self._gflat)
                 self._last_gflat = [(self._gflat, None)]
@@ -400,20 +412,22 @@ class UNetEngine:
                                  out=4 * g, **{k: v for k, v in wp.plan.unpack.items() if k not in ("rowmap", "origin")}))
             self._dw_table = ops.UnpackTable(jobs, self.device)
             self._dw_table_n = len(self._dw_order)
-            # two-chunk variant for the overlapped all-reduce: split where the cumulative gradient bytes pass 60 %
-            # (never inside a layer that accumulates several launches: the split counts wgrad CALLS, see _wgrad)
-            acc, split = 0, len(jobs)
+            # chunked variant for the overlapped all-reduce: cut where the cumulative gradient bytes pass each fraction
+            # of CHUNK_SPLIT_FRACTIONS (never inside a layer that accumulates several launches: the cut counts wgrad CALLS)
+            total = sum(n for _, n in self._dw_order)
+            cuts, acc, fi = [], 0, 0
             for i, (wp, n_param) in enumerate(self._dw_order):
                 acc += n_param
-                if acc >= CHUNK_SPLIT_FRACTION * sum(n for _, n in self._dw_order) and i + 1 < len(jobs):
-                    split = i + 1
-                    break
-            self._dw_split = split
-            self._g_split = self._dw_slots[id(self._dw_order[split][0])][1] if split < len(jobs) else goff
-            self._dw_table_a = ops.UnpackTable(jobs[:split], self.device) if split < len(jobs) else None
-            self._dw_table_b = ops.UnpackTable(jobs[split:], self.device) if split < len(jobs) else None
-            if self._dw_table_a is None:
-                self._dw_split = -1
+                if fi < len(CHUNK_SPLIT_FRACTIONS) and acc >= CHUNK_SPLIT_FRACTIONS[fi] * total and i + 1 < len(jobs):
+                    cuts.append(i + 1)
+                    while fi < len(CHUNK_SPLIT_FRACTIONS) and acc >= CHUNK_SPLIT_FRACTIONS[fi] * total:
+                        fi += 1
+            bounds = [0] + cuts + [len(jobs)]
+            self._chunks = []
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                g0 = self._dw_slots[id(self._dw_order[a][0])][1]
+                g1 = self._dw_slots[id(self._dw_order[b][0])][1] if b < len(jobs) else goff
+                self._chunks.append((b, g0, g1, ops.UnpackTable(jobs[a:b], self.device)))
 
     def flat_weight_gradients(self):
         """[(flat fp32 tensor, pending all-reduce handle or None), ...]: the buffer(s) the conv weight gradients of the

@@ -280,10 +280,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # the all-reduce of the first gradient chunk runs UNDER the backward pass and takes SMs from the persistent
-        # one-CTA-per-SM tensor kernels: 32 CTAs measured best on 2 B200s (19.29 ms; 16 / 8 / 4 CTAs: 19.65 / 20.03 / 20.60,
-        # 64: 19.50); overridable from the environment
-        os.environ.setdefault("NCCL_MAX_CTAS", "32")
+        # the all-reduce of the first gradient chunks runs UNDER the backward pass and takes SMs from the persistent
+        # one-CTA-per-SM tensor kernels: 16-32 CTAs measured best (2 B200s: 32 / 16 / 8 / 4 CTAs -> 19.57 / 19.65 / 20.03 /
+        # 20.60 ms; 8 B200s: 19.79 with 16, 19.82 with 32); overridable from the environment
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = args.steps

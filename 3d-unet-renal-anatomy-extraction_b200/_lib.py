@@ -70,6 +70,10 @@ _SIGS = {
     "unet3d_loss_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_int, C.c_void_p]),
     "unet3d_sw_accumulate": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 11 + [C.c_void_p]),
     "unet3d_sw_finalize": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_longlong, C.c_void_p]),
+    "unet3d_aug_flip": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
+    "unet3d_aug_stats": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "unet3d_aug_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "unet3d_aug_gamma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "unet3d_att_gate_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_int, C.c_void_p]),
     "unet3d_att_gate_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "unet3d_att_mid_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
@@ -79,6 +83,7 @@ _SIGS = {
     "unet3d_ccl_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "unet3d_region_accumulate": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong),
                                            C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p]),
+    "unet3d_overlap_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "unet3d_merge_finalize": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_longlong, C.c_void_p]),
     "unet3d_zoom_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "unet3d_zoom_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int),

@@ -6,10 +6,10 @@ OUT=../libunet3d_b200.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --use_fast_math"
 pids=()
-for f in conv_gemm wgrad_gemm elementwise resample regions capi; do
+for f in conv_gemm wgrad_gemm elementwise resample regions augment capi; do
   $NVCC $FLAGS -c $f.cu -o $f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT conv_gemm.o wgrad_gemm.o elementwise.o resample.o regions.o capi.o -cudart static
+$NVCC -shared -o $OUT conv_gemm.o wgrad_gemm.o elementwise.o resample.o regions.o augment.o capi.o -cudart static
 echo "built $(realpath $OUT)"

@@ -232,6 +232,21 @@ int unet3d_sw_accumulate(const float* logits, const float* window, long long* ac
 int unet3d_sw_finalize(const long long* acc, uint8_t* labels, float* probs, int K, long long n, void* stream) {
   return check(sw_finalize(acc, labels, probs, K, n, num_sms(), (cudaStream_t)stream), "sw_finalize");
 }
+
+int unet3d_aug_flip(const void* in, void* out, int elem_bytes, int X, int Y, int Z, int C, int fx, int fy, int fz,
+                    void* stream) {
+  return check(aug_flip(in, out, elem_bytes, X, Y, Z, C, fx, fy, fz, num_sms(), (cudaStream_t)stream), "aug_flip");
+}
+int unet3d_aug_stats(const float* x, long long n, const long long* leaf_off, int n_leaves, float* leaf_scratch,
+                     float* stats, void* stream) {
+  return check(aug_stats(x, n, leaf_off, n_leaves, leaf_scratch, stats, num_sms(), (cudaStream_t)stream), "aug_stats");
+}
+int unet3d_aug_affine(const float* x, float* out, long long n, const float* stats, int which, float factor, void* stream) {
+  return check(aug_affine(x, out, n, stats, which, factor, num_sms(), (cudaStream_t)stream), "aug_affine");
+}
+int unet3d_aug_gamma(const float* x, float* out, long long n, const float* stats, float gamma, float eps, void* stream) {
+  return check(aug_gamma(x, out, n, stats, gamma, eps, num_sms(), (cudaStream_t)stream), "aug_gamma");
+}
 int unet3d_maxpool3d_fwd(const void* x, void* out, uint8_t* code, int N, int D, int H, int W, int Cp, int act_f16,
                          void* stream) {
   return check(maxpool_fwd((const bf16*)x, (bf16*)out, code, N, D, H, W, Cp, act_f16, num_sms(), (cudaStream_t)stream),
@@ -300,6 +315,10 @@ int unet3d_region_accumulate(const float* pred, double* result, int* count, int 
 int unet3d_merge_finalize(const double* result, const int* count, uint8_t* labels, int K, long long n_voxels, void* stream) {
   if (!result || !count || !labels) return check(U3D_ERR_INVALID, "merge_finalize");
   return check(merge_finalize(result, count, labels, K, n_voxels, num_sms(), (cudaStream_t)stream), "merge_finalize");
+}
+int unet3d_overlap_counts(const uint8_t* pred, const uint8_t* label, long long n, unsigned long long* counts, void* stream) {
+  if (!pred || !label || !counts) return check(U3D_ERR_INVALID, "overlap_counts");
+  return check(overlap_counts(pred, label, n, counts, num_sms(), (cudaStream_t)stream), "overlap_counts");
 }
 
 }  // extern "C"

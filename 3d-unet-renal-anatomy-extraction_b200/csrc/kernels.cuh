@@ -28,6 +28,15 @@ int loss_bwd(const float* logits, const long long* target, const float* coef, co
 int sw_accumulate(const float* logits, const float* window, long long* acc, int K, int px, int py, int pz,
                   int x0, int y0, int z0, int X, int Y, int Z, int Xs, int num_sms, cudaStream_t s);
 int sw_finalize(const long long* acc, uint8_t* labels, float* probs, int K, long long n, int num_sms, cudaStream_t s);
+// csrc/augment.cu
+int aug_flip(const void* in, void* out, int elem_bytes, int X, int Y, int Z, int C, int fx, int fy, int fz, int num_sms,
+             cudaStream_t s);
+int aug_stats(const float* x, long long n, const long long* leaf_off, int n_leaves, float* leaf_scratch, float* stats,
+              int num_sms, cudaStream_t s);
+int aug_affine(const float* x, float* out, long long n, const float* stats, int which, float factor, int num_sms,
+               cudaStream_t s);
+int aug_gamma(const float* x, float* out, long long n, const float* stats, float gamma, float eps, int num_sms,
+              cudaStream_t s);
 int maxpool_fwd(const bf16* x, bf16* out, uint8_t* code, int N, int D, int H, int W, int Cp, int af, int num_sms,
                 cudaStream_t s);
 int maxpool_bwd(const bf16* dout, const uint8_t* code, bf16* dx, int N, int D, int H, int W, int Cp, int num_sms,
@@ -53,5 +62,7 @@ int ccl_stats(const int* labels, const int* roots, int n_roots, int* stats, int 
 int region_accumulate(const float* pred, double* result, int* count, int K, const int* box_n, const long long* pstride,
                       const int* dst0, int Y, int Z, int num_sms, cudaStream_t s);
 int merge_finalize(const double* result, const int* count, uint8_t* labels, int K, long long n, int num_sms, cudaStream_t s);
+int overlap_counts(const uint8_t* pred, const uint8_t* label, long long n, unsigned long long* counts, int num_sms,
+                   cudaStream_t s);
 
 }  // namespace u3d

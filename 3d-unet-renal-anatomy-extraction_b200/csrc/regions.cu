@@ -196,7 +196,37 @@ inline int grid_for_n(long long n, int per_block, int num_sms) {
   return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
+// trainer.evaluate_case (trainer.py:348-356): per label c the three counts its Dice needs, |pred == c AND label == c|,
+// |pred == c|, |label == c|, in one pass over the two uint8 volumes (the reference makes 2 float32 masks and 3 masked
+// sums per class on the CPU).  Exact integer counts; per-block shared-memory histogram, one atomic per (block, bin).
+__global__ void overlap_counts_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ label, long long n,
+                                      unsigned long long* __restrict__ counts /*[3][256]*/) {
+  __shared__ unsigned int h[3][256];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) (&h[0][0])[i] = 0u;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned p = pred[i], l = label[i];
+    if (p == l) atomicAdd(&h[0][p], 1u);
+    atomicAdd(&h[1][p], 1u);
+    atomicAdd(&h[2][l], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+    const unsigned v = (&h[0][0])[i];
+    if (v) atomicAdd(&counts[i], (unsigned long long)v);
+  }
+}
+
 }  // namespace
+
+int overlap_counts(const uint8_t* pred, const uint8_t* label, long long n, unsigned long long* counts, int num_sms,
+                   cudaStream_t s) {
+  if (n < 1) return U3D_ERR_INVALID;
+  long long need = (n + 256 * 16 - 1) / (256 * 16);
+  const int g = (int)(need < (long long)num_sms * 4 ? need : (long long)num_sms * 4);
+  overlap_counts_kernel<<<g, 256, 0, s>>>(pred, label, n, counts);
+  return cudaGetLastError() == cudaSuccess ? U3D_OK : U3D_ERR_CUDA;
+}
 
 int ccl_label(const uint8_t* mask, int* labels, uint8_t* is_root, int X, int Y, int Z, int num_sms, cudaStream_t s) {
   const long long n = (long long)X * Y * Z;

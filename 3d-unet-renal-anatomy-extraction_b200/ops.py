@@ -629,3 +629,17 @@ def merge_finalize(result: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
         _lib.check(_lib.lib().unet3d_merge_finalize(result.data_ptr(), count.data_ptr(), labels.data_ptr(),
                                                     int(result.shape[3]), count.numel(), _stream()), "unet3d_merge_finalize")
     return labels
+
+
+@_on_device_of_first_arg
+def overlap_counts(pred: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """int64 (3, 256): per label value c {|pred == c and label == c|, |pred == c|, |label == c|} of two uint8 CUDA volumes."""
+    assert pred.is_cuda and label.is_cuda and pred.dtype == torch.uint8 and label.dtype == torch.uint8
+    assert pred.shape == label.shape
+    pred, label = pred.contiguous(), label.contiguous()
+    counts = torch.zeros(3, 256, dtype=torch.int64, device=pred.device)
+    _count()
+    with _Timed("overlap_counts", 0.0, 2.0 * pred.numel()):
+        _lib.check(_lib.lib().unet3d_overlap_counts(pred.data_ptr(), label.data_ptr(), pred.numel(), counts.data_ptr(),
+                                                    _stream()), "unet3d_overlap_counts")
+    return counts

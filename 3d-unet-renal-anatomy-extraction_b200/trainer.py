@@ -410,6 +410,38 @@ def _cascade_predict_case(case, coarse_model, coarse_target_spacing, coarse_norm
 
 
 # ------------------------------------------------------------------------------------------------
+# evaluation (trainer.py:348-356)
+# ------------------------------------------------------------------------------------------------
+def evaluate_case(case):
+    """trainer.py:348-356: Dice (loss.dice, alpha = beta = 0.5, smooth = 1e-7) of every label 1 .. label.max() between
+    ``case['pred']`` and ``case['label']`` (uint8 volumes: numpy arrays or CUDA tensors).  Returns the list of floats
+    the reference returns.
+
+    One device pass counts |pred == c and label == c|, |pred == c|, |label == c| for all labels at once (exact
+    integers); the reference builds two float32 masks per label and sums them in fp32 on the CPU.  The final ratio is
+    evaluated in float32 in the reference's operation order, so the result is bit-identical as long as the counts are
+    exactly representable in float32 (< 2^24 voxels per label; above that the reference's own fp32 sums round)."""
+    pred, label = case['pred'], case['label']
+    dev = pred.device if isinstance(pred, torch.Tensor) and pred.is_cuda else (
+        label.device if isinstance(label, torch.Tensor) and label.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+    as_dev = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dev).to(torch.uint8)
+    counts = ops.overlap_counts(as_dev(pred), as_dev(label)).cpu().numpy()
+    ops.check_device_errors()
+    num_classes = int(np.nonzero(counts[2])[0].max()) if counts[2].any() else 0          # case['label'].max()
+    f32 = np.float32
+    out = []
+    for c in range(1, num_classes + 1):
+        tp = f32(counts[0, c])
+        fn = f32(counts[2, c] - counts[0, c])
+        fp = f32(counts[1, c] - counts[0, c])
+        # loss.py:32-48: (tp + smooth) / (tp + alpha * fn + beta * fp + smooth), float32 tensors with Python-float scalars
+        num = f32(tp + f32(1e-7))
+        den = f32(f32(f32(tp + f32(f32(0.5) * fn)) + f32(f32(0.5) * fp)) + f32(1e-7))
+        out.append(float(f32(num / den)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # training step loop
 # ------------------------------------------------------------------------------------------------
 class DevicePrefetcher:

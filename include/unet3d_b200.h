@@ -186,6 +186,25 @@ int unet3d_sw_accumulate(const float* logits, const float* window, long long* ac
                          int x0, int y0, int z0, int X, int Y, int Z, int Xs, void* stream);
 int unet3d_sw_finalize(const long long* acc, uint8_t* labels, float* probs, int K, long long n, void* stream);
 
+/* Train-loader augmentation on a patch that is already in HBM (transform.py:176-301), bit-exact with the reference's
+ * numpy arithmetic (csrc/augment.cu).
+ *   unet3d_aug_flip   : RandomMirror (transform.py:279-301): out = np.flip(in, axes) for a (X, Y, Z, C) array of 4-byte or
+ *                       1-byte elements; in != out.
+ *   unet3d_aug_stats  : stats[0] = min, stats[1] = max (order-preserving int encodings, read only by the two kernels
+ *                       below), and -- when leaf_off != NULL -- stats[2] = numpy's float32 input.mean(), stats[3] = sum:
+ *                       leaf_off[n_leaves + 1] = the leaf boundaries of numpy's pairwise summation of n elements
+ *                       (augment.py computes them once per n), leaf_scratch = n_leaves floats.
+ *   unet3d_aug_affine : adjust_contrast (which = 0: a = mean) / adjust_brightness (which = 1: a = min), transform.py:176-185:
+ *                       out = (x - a) * factor + a in separately rounded fp32 operations.  in-place allowed.
+ *   unet3d_aug_gamma  : adjust_gamma (transform.py:188-193): arange = max - min + eps;
+ *                       out = power((x - min) / arange, gamma) * arange + min.  in-place allowed. */
+int unet3d_aug_flip(const void* in, void* out, int elem_bytes, int X, int Y, int Z, int C, int fx, int fy, int fz,
+                    void* stream);
+int unet3d_aug_stats(const float* x, long long n, const long long* leaf_off, int n_leaves, float* leaf_scratch,
+                     float* stats, void* stream);
+int unet3d_aug_affine(const float* x, float* out, long long n, const float* stats, int which, float factor, void* stream);
+int unet3d_aug_gamma(const float* x, float* out, long long n, const float* stats, float gamma, float eps, void* stream);
+
 /* MaxPoolBlock = nn.MaxPool3d(kernel_size=2, stride=2) (network.py:452-463) on 16-bit NDHWC (N, D, H, W, Cp), D/H/W even.
  * code: uint8 (N, D/2, H/2, W/2, Cp) = kd*4 + kh*2 + kw of the winner, PyTorch's scan order and tie/NaN rule, i.e.
  * torch's return_indices value is ((2d+kd)*H + 2h+kh)*W + 2w+kw.  bwd writes every element of dx (no pre-zeroing). */
@@ -239,6 +258,11 @@ int unet3d_ccl_stats(const int* labels, const int* roots, int n_roots, int* stat
 int unet3d_region_accumulate(const float* pred, double* result, int* count, int K, const int box_n[3],
                              const long long pstride[3], const int dst0[3], int Y, int Z, void* stream);
 int unet3d_merge_finalize(const double* result, const int* count, uint8_t* labels, int K, long long n_voxels, void* stream);
+
+/* trainer.evaluate_case (trainer.py:348-356): counts [3][256] uint64 (zeroed by the caller) += per label value c
+ * { |pred == c AND label == c|, |pred == c|, |label == c| } over two uint8 volumes of n voxels -- what the per-label Dice
+ * (loss.dice with alpha = beta = 0.5) needs: TP, FP = |pred| - TP, FN = |label| - TP. */
+int unet3d_overlap_counts(const uint8_t* pred, const uint8_t* label, long long n, unsigned long long* counts, void* stream);
 
 #ifdef __cplusplus
 }

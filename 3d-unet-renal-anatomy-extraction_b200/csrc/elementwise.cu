@@ -161,9 +161,11 @@ __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const uint4* __re
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : LRELU * d[j];
-      const uint4 gp = pack8(d, af);
-      g[base + (size_t)vv * chunks + ch] = gp;
-      unpack8(gp, d, af);      // reduce what pass 2 will read back (the rounded g)
+      if (g != nullptr) {
+        const uint4 gp = pack8(d, af);
+        g[base + (size_t)vv * chunks + ch] = gp;
+        unpack8(gp, d, af);    // reduce what pass 2 will read back (the rounded g)
+      }                        // g == null: pass 2 recomputes the same fp32 g from dout (no 16-bit round trip)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float yh = fmaf(yy[j] - mean[j], scale[j], sh[j]);
@@ -195,12 +197,15 @@ __global__ void __launch_bounds__(256, 2) in_bwd_apply_kernel(const uint4* __res
                                     uint4* __restrict__ dy, const float2* __restrict__ table,
                                     const double* __restrict__ sums, const float* __restrict__ coef,
                                     double* __restrict__ dsum, int chunks,
-                                    long long V, int Cp, double inv_count, int zero_last, int D, int H, int W, int af) {
+                                    long long V, int Cp, double inv_count, int zero_last, int D, int H, int W, int af,
+                                    int g_is_dout) {
   extern __shared__ float red[];
   const int n = blockIdx.y;
   const int ch = threadIdx.x;
   // dy = scale * (g - mg - yhat * mgy) = g * A + y * B + C  with per-channel constants
-  float ca[8], cb[8], cc[8], acc[8];
+  // g_is_dout: `g` holds the upstream gradient of a norm WITHOUT residual input; g = dout * lrelu'(yhat) is recomputed
+  // here (sign of (y - mean) * scale, as pass 1 did) instead of being written and re-read in 16 bit
+  float ca[8], cb[8], cc[8], acc[8], tm[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const size_t c = (size_t)n * Cp + ch * 8 + j;
@@ -215,6 +220,7 @@ __global__ void __launch_bounds__(256, 2) in_bwd_apply_kernel(const uint4* __res
       cb[j] = -t.y * t.y * mgy;
       cc[j] = -t.y * mg + t.y * t.y * mgy * t.x;
     }
+    tm[j] = t.x;
     acc[j] = 0.f;
   }
   const size_t base = (size_t)n * V * chunks;
@@ -243,6 +249,10 @@ __global__ void __launch_bounds__(256, 2) in_bwd_apply_kernel(const uint4* __res
         const unsigned v32 = (unsigned)vv, q1 = v32 / (unsigned)W, wq = v32 - q1 * (unsigned)W;
         const unsigned dq = q1 / (unsigned)H, hq = q1 - dq * (unsigned)H;
         z = (wq == (unsigned)(W - 1)) || (hq == (unsigned)(H - 1)) || (dq == (unsigned)(D - 1));
+      }
+      if (g_is_dout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gg[j] = (yy[j] - tm[j]) * ca[j] > 0.f ? gg[j] : LRELU * gg[j];     // ca = scale (InstanceNorm)
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -1439,7 +1449,8 @@ int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf
 }
 
 int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, const double* sums, const float* coef,
-                 double* dsum, int N, int D, int H, int W, int Cp, int zero_last, int af, int num_sms, cudaStream_t s) {
+                 double* dsum, int N, int D, int H, int W, int Cp, int flags, int af, int num_sms, cudaStream_t s) {
+  const int zero_last = flags & 1, g_is_dout = (flags >> 1) & 1;
   if (Cp % 8 || Cp / 8 > 256) return U3D_ERR_INVALID;
   const int chunks = Cp / 8;
   const long long V = (long long)D * H * W;
@@ -1449,7 +1460,8 @@ int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, con
   const size_t sm = dsum ? (size_t)blk.y * Cp * sizeof(float) : 0;
 #define U3D_BWD_APPLY(Z, S)                                                                                         \
   in_bwd_apply_kernel<Z, S><<<grd, blk, sm, s>>>((const uint4*)g, (const uint4*)y, (uint4*)dy, (const float2*)table, \
-                                                 sums, coef, dsum, chunks, V, Cp, 1.0 / (double)V, zero_last, D, H, W, af)
+                                                 sums, coef, dsum, chunks, V, Cp, 1.0 / (double)V, zero_last, D, H, W, af, g_is_dout)
+  if (g_is_dout && coef != nullptr) return U3D_ERR_INVALID;        // recomputation is for the InstanceNorm path only
   if (zero_last && dsum) U3D_BWD_APPLY(true, true);
   else if (zero_last) U3D_BWD_APPLY(true, false);
   else if (dsum) U3D_BWD_APPLY(false, true);

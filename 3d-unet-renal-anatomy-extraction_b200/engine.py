@@ -89,6 +89,7 @@ class UNetEngine:
 
     def _reset_caches(self):
         self._ops = {}
+        self._zb_arena, self._zb_used, self._zb_demand, self._zb_size = None, 0, 0, 0
         self._pack_bind, self._pack_table, self._pack_table_key, self._pack_ptrs = {}, None, None, None
         self._pack_table_late, self._pack_late_ids, self._pack_join, self._pack_stream = None, frozenset(), None, None
         self._dw_slots, self._dw_order, self._dw_table, self._dw_table_n = {}, [], None, 0
@@ -210,6 +211,8 @@ class UNetEngine:
             table, bn = self._bn_tables(norm, stats, drop, count)
             return y, table, bn
         table = torch.empty(n, y.shape[-1], 2, dtype=torch.float32, device=self.device)
+        # (folding this into in_apply's prologue was measured: -42 launches, but the fp64 divide / sqrt per thread made
+        # in_apply 0.36 ms per step slower -- 1.07 -> 1.43 ms -- so the table stays a separate 2 us launch)
         ops.in_finalize(stats, drop, table, count, IN_EPS)
         return y, table, None
 
@@ -311,11 +314,17 @@ class UNetEngine:
 
     def _in_bwd(self, dout, dout2, out, y, table, zero_last=False, want_dsum=False):
         n, cp = y.shape[0], y.shape[-1]
-        g = self._grad_like(y)
         sums = self._z64(n, cp, 2)
-        ops.in_bwd_reduce(dout, dout2, out, y, g, table, sums)
         dy = self._grad_like(y)
         dsum = self._z64(cp) if want_dsum else None
+        if out is None and dout2 is None and self.capture is None:
+            # norm without residual input: g = dout * lrelu'(y_hat) is needed by nobody else, so pass 1 only reduces and
+            # pass 2 recomputes it from dout (2 bytes per element less to write, 16-bit round trip of g avoided)
+            ops.in_bwd_reduce(dout, None, None, y, None, table, sums)
+            ops.in_bwd_apply(dout, y, dy, table, sums, dsum, zero_last, g_is_dout=True)
+            return None, dy, sums, dsum
+        g = self._grad_like(y)
+        ops.in_bwd_reduce(dout, dout2, out, y, g, table, sums)
         ops.in_bwd_apply(g, y, dy, table, sums, dsum, zero_last)
         return g, dy, sums, dsum
 
@@ -529,6 +538,23 @@ class UNetEngine:
         self._z_demand = 0
         self._z_used = 0
         self._z_arena = torch.zeros(size, dtype=torch.float64, device=self.device) if size else None
+
+    def _zero_grad_of(self, p):
+        """Gradient of a conv bias that InstanceNorm cancels exactly: exact zeros, carved out of ONE fp32
+        arena zeroed once per backward pass (38 fill launches per step at the default net otherwise).  A fresh view per
+        step, so autograd's AccumulateGrad can adopt it without a copy (a cached tensor would be cloned)."""
+        n = p.numel()
+        self._zb_demand += (n + 3) // 4 * 4
+        if self._zb_arena is not None and self._zb_used + n <= self._zb_arena.numel():
+            out = self._zb_arena[self._zb_used:self._zb_used + n].view_as(p)
+            self._zb_used += (n + 3) // 4 * 4
+            return out
+        return torch.zeros_like(p)
+
+    def _zb_begin(self):
+        size = max(self._zb_demand, self._zb_size)
+        self._zb_size, self._zb_demand, self._zb_used = size, 0, 0
+        self._zb_arena = torch.zeros(size, dtype=torch.float32, device=self.device) if size else None
 
     def _unscale(self, g):
         return g if self._inv_scale is None else g * self._inv_scale
@@ -748,12 +774,12 @@ class UNetEngine:
         grads[blk.conv2.weight] = self._wgrad(c2, [a1], dy2, blk.conv2.weight)
         # InstanceNorm cancels the bias exactly (S1); under BatchNorm its gradient is sum(dy) (zero up to rounding in
         # training mode, real in eval mode)
-        grads[blk.conv2.bias] = torch.zeros_like(blk.conv2.bias) if b2 is None else self._unscale(ds2[:co].float())
+        grads[blk.conv2.bias] = self._zero_grad_of(blk.conv2.bias) if b2 is None else self._unscale(ds2[:co].float())
         da1 = self._grad_like(a1)
         ops.conv_gemm(c2.dgrad, [dy2], self._pw(c2.dgrad, blk.conv2.weight), [da1], c2.grid)
         g1, dy1, _, ds1 = self._norm_bwd(b1, da1, None, a1, False, y1, t1, grads)
         grads[blk.conv1.weight] = self._wgrad(c1, inputs, dy1, blk.conv1.weight)
-        grads[blk.conv1.bias] = torch.zeros_like(blk.conv1.bias) if b1 is None else self._unscale(ds1[:co].float())
+        grads[blk.conv1.bias] = self._zero_grad_of(blk.conv1.bias) if b1 is None else self._unscale(ds1[:co].float())
         dins = [self._grad_like(t) for t in inputs]
         if blk.uses_skip_conv:
             sk = self._op(key + ("skip",), "conv", 1, blk.stride, in_C, blk.out_channels, grid)
@@ -778,7 +804,7 @@ class UNetEngine:
         op = self._op(key + ("conv",), "conv", 3, 1, in_C, blk.out_channels, (inputs[0].shape[0], *y.shape[1:4]))
         _, dy, _, ds = self._norm_bwd(b, dout, dout2, a, False, y, t, grads)
         grads[blk.conv.weight] = self._wgrad(op, inputs, dy, blk.conv.weight)
-        grads[blk.conv.bias] = (torch.zeros_like(blk.conv.bias) if b is None          # cancelled by InstanceNorm (S1)
+        grads[blk.conv.bias] = (self._zero_grad_of(blk.conv.bias) if b is None          # cancelled by InstanceNorm (S1)
                                 else self._unscale(ds[:blk.out_channels].float()))
         dins = [self._grad_like(x) for x in inputs]
         ops.conv_gemm(op.dgrad, [dy], self._pw(op.dgrad, blk.conv.weight), dins, op.grid)
@@ -792,6 +818,7 @@ class UNetEngine:
         dims = [(D >> i, H >> i, W >> i) for i in range(np_ + 1)]
         grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         self._z_begin()
+        self._zb_begin()
         self._begin_wgrads()
         # fp16 gradients need a scale to stay inside fp16's range (Dice gradients are ~1e-7 per voxel).  It is
         # internal and dynamic: a power of two that puts max|dlogits| at 64, taken from this step's dlogits on the

@@ -356,21 +356,24 @@ def in_apply(y: torch.Tensor, skip: Optional[torch.Tensor], out: torch.Tensor, t
 def in_bwd_reduce(dout, dout2, out, y, g, table, sums, shift=None):
     n, d, h, w, cp = y.shape
     _count()
-    assert dout.dtype == y.dtype and g.dtype == y.dtype and (out is None or out.dtype == y.dtype)
-    with _Timed("in_bwd_reduce", 0.0, _alg_numel(y) * 2.0 * (3 + (dout2 is not None) + (out is not None)),
-                f"{tuple(y.shape)} d2{int(dout2 is not None)} out{int(out is not None)}"):
-        _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), _ptr(out), y.data_ptr(), g.data_ptr(),
+    assert dout.dtype == y.dtype and (g is None or g.dtype == y.dtype) and (out is None or out.dtype == y.dtype)
+    with _Timed("in_bwd_reduce", 0.0, _alg_numel(y) * 2.0 * (2 + (g is not None) + (dout2 is not None) + (out is not None)),
+                f"{tuple(y.shape)} d2{int(dout2 is not None)} out{int(out is not None)} g{int(g is not None)}"):
+        _lib.check(_lib.lib().unet3d_in_bwd_reduce(dout.data_ptr(), _ptr(dout2), _ptr(out), y.data_ptr(), _ptr(g),
                                                    table.data_ptr(), _ptr(shift), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
                    "unet3d_in_bwd_reduce")
 
 
-def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False, coef=None):
+def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False, coef=None, g_is_dout=False):
+    """g_is_dout: `g` is the upstream gradient of a norm without residual input (pass 1 ran with g=None): the activation
+    gradient is recomputed here from the sign of the normalised value instead of being stored and re-read."""
     n, d, h, w, cp = y.shape
     _count()
-    assert g.dtype == y.dtype and dy.dtype == y.dtype
+    assert g.dtype == y.dtype and dy.dtype == y.dtype and not (g_is_dout and coef is not None)
     with _Timed("in_bwd_apply", 0.0, _alg_numel(y) * 2.0 * 3, f"{tuple(y.shape)}"):
         _lib.check(_lib.lib().unet3d_in_bwd_apply(g.data_ptr(), y.data_ptr(), dy.data_ptr(), table.data_ptr(), sums.data_ptr(),
-                                                  _ptr(coef), _ptr(dsum), n, d, h, w, cp, int(zero_last), _f16(y), _stream()),
+                                                  _ptr(coef), _ptr(dsum), n, d, h, w, cp, int(zero_last) | (int(g_is_dout) << 1),
+                                                  _f16(y), _stream()),
                    "unet3d_in_bwd_apply")
 
 

@@ -142,11 +142,15 @@ int unet3d_in_finalize(const double* stats, const float* drop_scale, float* tabl
 int unet3d_in_apply(const void* y, const void* skip, void* out, const float* table, const float* shift, int N,
                     long long V, int Cp, int act_f16, void* stream);
 /* in_bwd_reduce: `out` may be NULL when the norm had no residual input (the activation's sign is then taken from the
- * normalised value and the activation output is not read); dout2 may be NULL. */
+ * normalised value and the activation output is not read); dout2 may be NULL; g may be NULL (only the sums are wanted:
+ * unet3d_in_bwd_apply then recomputes g from dout, flag bit 1). */
 int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, void* g,
                          const float* table, const float* shift, double* sums, int N, long long V, int Cp, int act_f16,
                          void* stream);
-/* dy = g * A + y * B + C per (n, c): from (table, sums) for InstanceNorm, or from coef (fp32 [N][Cp][3], BatchNorm). */
+/* dy = g * A + y * B + C per (n, c): from (table, sums) for InstanceNorm, or from coef (fp32 [N][Cp][3], BatchNorm).
+ * The `zero_last` argument is a flag word: bit 0 = zero the ConstantPad3d planes (network.py:314), bit 1 = `g` holds the
+ * UPSTREAM gradient of a norm without residual input and g = dout * lrelu'((y - mean) * scale) is recomputed (InstanceNorm
+ * only, coef must be NULL). */
 int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums,
                         const float* coef, double* dsum, int N, int D, int H, int W, int Cp, int zero_last, int act_f16,
                         void* stream);

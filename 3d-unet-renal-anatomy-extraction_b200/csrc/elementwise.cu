@@ -780,28 +780,33 @@ __global__ void head_fwd_kernel(const bf16* __restrict__ a, const float* __restr
   __shared__ float ws[KMAX * CP + KMAX];
   for (int i = threadIdx.x; i < K * CP + K; i += blockDim.x) ws[i] = i < K * CP ? w[i] : b[i - K * CP];
   __syncthreads();
-  const long long total = (long long)N * V;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(i / V);
-    const long long v = i - (long long)n * V;
-    float acc[KMAX];
+  // one thread = one voxel: its CP / 8 16-byte loads are issued together; samples in an outer loop (no 64-bit division)
+  for (int n = 0; n < N; ++n) {
+    const bf16* an = a + (size_t)n * V * CP;
+    float* ln = logits + (size_t)n * K * V;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+      float acc[KMAX];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) acc[k] = k < K ? ws[K * CP + k] : 0.f;
-    const uint4* ap = reinterpret_cast<const uint4*>(a + (size_t)i * CP);
+      for (int k = 0; k < KMAX; ++k) acc[k] = k < K ? ws[K * CP + k] : 0.f;
+      const uint4* ap = reinterpret_cast<const uint4*>(an + (size_t)v * CP);
+      uint4 ra[CP / 8];
 #pragma unroll
-    for (int c8 = 0; c8 < CP / 8; ++c8) {
-      float f[8];
-      unpack8(ld_stream(ap + c8), f, af);
+      for (int c8 = 0; c8 < CP / 8; ++c8) ra[c8] = ld_stream(ap + c8);
+#pragma unroll
+      for (int c8 = 0; c8 < CP / 8; ++c8) {
+        float f[8];
+        unpack8(ra[c8], f, af);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], ws[k * CP + c8 * 8 + j], acc[k]);
+          }
+      }
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
-        if (k < K) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], ws[k * CP + c8 * 8 + j], acc[k]);
-        }
+        if (k < K) ln[(size_t)k * V + v] = acc[k];
     }
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < K) logits[((size_t)n * K + k) * V + v] = acc[k];
   }
 }
 
@@ -823,7 +828,6 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   for (int i = threadIdx.x; i < KMAX * CP; i += blockDim.x) ws[i] = i < K * CP ? w[i] : 0.f;
   for (int i = threadIdx.x; i < KMAX * CP + KMAX; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  const long long total = (long long)N * V;
   const float gs = gscale ? __ldg(gscale) : 1.f;      // internal gradient scale (fp16 mode); dW / db stay unscaled
   const int ch = threadIdx.x % CH, vin = threadIdx.x / CH, vpb = blockDim.x / CH;
   float wk[KMAX][8], pw[KMAX][8], pb[KMAX];
@@ -836,28 +840,48 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       wk[k][j] = ws[k * CP + ch * 8 + j];
     }
   }
-  for (long long i = (long long)blockIdx.x * vpb + vin; i < total; i += (long long)gridDim.x * vpb) {
-    const int n = (int)(i / V);
-    const long long v = i - (long long)n * V;
-    float g[KMAX];
+  // HB_U voxels per thread and trip, all loads issued before the first use (the one-voxel loop ran at 2.2 TB/s: two
+  // dependent global loads and a 64-bit division per trip); samples are walked in an outer loop, so no division at all
+  constexpr int HB_U = 4;
+  const long long stride = (long long)gridDim.x * vpb;
+  for (int n = 0; n < N; ++n) {
+    const float* dln = dl + (size_t)n * K * V;
+    const bf16* an = a + (size_t)n * V * CP;
+    bf16* dan = da + (size_t)n * V * CP;
+    for (long long v0 = (long long)blockIdx.x * vpb + vin; v0 < V; v0 += stride * HB_U) {
+      float g[HB_U][KMAX];
+      uint4 ra[HB_U];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) g[k] = k < K ? __ldg(&dl[((size_t)n * K + k) * V + v]) : 0.f;
-    float f[8], t[8];
-    unpack8(ld_stream(reinterpret_cast<const uint4*>(a + (size_t)i * CP) + ch), f, af);
+      for (int u = 0; u < HB_U; ++u) {
+        const long long v = v0 + u * stride;
+        if (v < V) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float sacc = 0.f;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        sacc = fmaf(g[k], wk[k][j], sacc);              // rows k >= K of the weights are zero
-        pw[k][j] = fmaf(g[k], f[j], pw[k][j]);
+          for (int k = 0; k < KMAX; ++k) g[u][k] = k < K ? __ldg(&dln[(size_t)k * V + v]) : 0.f;
+          ra[u] = ld_stream(reinterpret_cast<const uint4*>(an + (size_t)v * CP) + ch);
+        }
       }
-      t[j] = sacc * gs;
-    }
-    reinterpret_cast<uint4*>(da + (size_t)i * CP)[ch] = pack8(t, af);
-    if (ch == 0) {
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) pb[k] += g[k];
+      for (int u = 0; u < HB_U; ++u) {
+        const long long v = v0 + u * stride;
+        if (v >= V) break;
+        float f[8], t[8];
+        unpack8(ra[u], f, af);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            sacc = fmaf(g[u][k], wk[k][j], sacc);              // rows k >= K of the weights are zero
+            pw[k][j] = fmaf(g[u][k], f[j], pw[k][j]);
+          }
+          t[j] = sacc * gs;
+        }
+        reinterpret_cast<uint4*>(dan + (size_t)v * CP)[ch] = pack8(t, af);
+        if (ch == 0) {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) pb[k] += g[u][k];
+        }
+      }
     }
   }
   // lanes with equal (lane % CH) hold the same chunk (CH divides 32): butterfly over the other lane bits

@@ -34,9 +34,23 @@ FUSE_KD = True                 # fuse the three d-taps of a (kh,kw) into one wid
 SMEM_LIMIT = 227 * 1024
 
 
+_PAD64 = os.environ.get("U3D_PAD64", "0") == "1"
+
+
 def pad_channels(c: int) -> int:
-    """Physical channel count of a bf16 NDHWC activation: multiple of 16 (UMMA K step)."""
-    return (c + 15) // 16 * 16
+    """Physical channel count of a 16-bit NDHWC activation: a multiple of 16 (UMMA K step).
+
+    Tuning knob U3D_PAD64=1 (off): wide tensors go up to the next multiple of 64 when that costs at most 7 %
+    (240 -> 256, 480 -> 512), so that the conv kernels can use 32- / 64-channel groups where 240 = 15 x 16 forces
+    16-channel ones.  Measured at cfg-2 (tools/bench_layers.py, round 2): the strided 240 -> 480 layers gain (forward
+    130 -> 95 us, transposed data gradient 126 -> 92 us), the 8^3-grid weight gradients too (50 -> 40 us x 9), but the
+    level-4 forward / data gradient lose (58 -> 61, 54 -> 56 us x 9): about -0.1 ms per 18.7 ms step for 6.7 % more
+    activation memory on the deep levels -- not taken."""
+    p16 = (c + 15) // 16 * 16
+    p64 = (c + 63) // 64 * 64
+    if _PAD64 and c > 128 and p64 * 100 <= c * 107:
+        return p64
+    return p16
 
 
 def a_slabs(dt: int, g: int) -> int:

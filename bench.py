@@ -434,12 +434,15 @@ def main():
         fl, tms, cnt = by[name]
         ach = fl / (tms * 1e-3) / 1e12
         # traffic: dram__bytes_read + dram__bytes_write of ONE launch from the committed ncu --set full capture
-        # (profiles/r01_ncu_kernels.txt: the level-0 30->30 forward launch, 203.8 algorithmic GFLOP, 537 MB algorithmic
-        # bytes = 16-bit input + output); the per-step `achieved` above is the FLOP-weighted mean over all 92 launches
+        # (profiles/r02_ncu_kernels.txt: the level-0 30->30 forward launch, 203.8 algorithmic GFLOP, 537 MB algorithmic
+        # bytes = 16-bit input + output; 268.6 MB read + 220.2 MB written); the per-step `achieved` above is the
+        # FLOP-weighted mean over all 92 launches of the step (level 0: ~800 TFLOP/s, strided / transposed / 8^3-grid
+        # layers far below: profiles/r02_step_table.txt)
         roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": 489.1e6,
-                "traffic_note": "level-0 conv 30->30 k3 forward launch (203.8 GFLOP, 537e6 algorithmic bytes), ncu capture "
-                                "profiles/r01_ncu_kernels.txt", "peak_source": f"{src} (bf16_tflops_sustained)",
+                "frac": ach / peak, "traffic": 488.8e6,
+                "traffic_note": "level-0 conv 30->30 k3 forward launch (203.8 GFLOP, 537e6 algorithmic bytes), ncu --set full "
+                                "capture of round 2: profiles/r02_ncu_kernels.txt (a bench run cannot measure DRAM bytes itself)",
+                "peak_source": f"{src} (bf16_tflops_sustained)",
                 "launches_per_step": cnt // K, "kernel_ms_per_step": tms / K,
                 "per_kernel_ms_per_step": {k: v[1] / K for k, v in by.items()},
                 "per_kernel_tflops": {k: (v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None) for k, v in by.items()},

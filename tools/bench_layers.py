@@ -40,6 +40,9 @@ layers = [  # name, kind, ks, stride, cins, cout, out dims (tile grid), count pe
     ("L2 120->120 k3", "conv", 3, 1, [120], 120, (32, 32, 32), 6),
     ("L3 240->240 k3", "conv", 3, 1, [240], 240, (16, 16, 16), 8),
     ("L4 480->480 k3", "conv", 3, 1, [480], 480, (8, 8, 8), 9),
+    ("P3 240->480 k3 s2", "conv", 3, 2, [240], 480, (8, 8, 8), 1),
+    ("P2 120->240 k3 s2", "conv", 3, 2, [120], 240, (16, 16, 16), 1),
+    ("D3 480->240 k3 cat", "conv", 3, 1, [240, 240], 240, (16, 16, 16), 1),
     ("U0 60->30 convT", "convT", 3, 2, [60], 30, (64, 64, 64), 1),
     ("U3 480->240 convT", "convT", 3, 2, [480], 240, (8, 8, 8), 1),
 ]

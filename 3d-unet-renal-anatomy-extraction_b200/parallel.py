@@ -186,7 +186,7 @@ def enable_sync_batchnorm(model: torch.nn.Module, enabled: bool = True):
     the GLOBAL batch (what torch.nn.SyncBatchNorm does around the reference) instead of every rank's own shard.  Each
     norm application then adds one all-reduce of 2 x C float64 sums in the forward pass and one in the backward pass;
     with ``DiceLoss(global_batch=True)`` and summed gradients the result is exactly the single-process gradient on
-    the concatenated batch (tools/check_multi_gpu.py).  Every rank must hold the same number of samples.  The
+    the concatenated batch (tests/test_multi_gpu.py).  Every rank must hold the same number of samples.  The
     all-reduces are issued from Python between kernel launches, so this mode does not combine with GraphedTrainStep."""
     net = model.net if hasattr(model, "net") else model
     net.sync_bn = bool(enabled)            # read by the engine at every BatchNorm application

@@ -327,6 +327,62 @@ class RandomGamma(_Intensity):
         return self.range
 
 
+def combination_lut(combinations, num_classes: int) -> np.ndarray:
+    """Old label -> new label table of transform.combination_labels (transform.py:323-363): the listed combinations keep
+    the order in which their first member appears when walking 0 .. num_classes - 1, every unlisted class becomes a
+    combination of its own at its place in that walk; the new label is the index of the (first) combination that holds
+    the old one (the reference takes the argmax over the OR-ed one-hot planes)."""
+    combos = [list(c) for c in combinations] if len(np.array(combinations, dtype=object).shape) != 1 or \
+        isinstance(combinations[0], (list, tuple, np.ndarray)) else [list(combinations)]
+    full, used = [], []
+    for c in range(num_classes):
+        rows = [i for i, combo in enumerate(combos) if c in combo]
+        if rows:
+            for i in rows:
+                if i not in used:
+                    full.append(combos[i])
+                    used.append(i)
+        else:
+            full.append([c])
+    lut = np.zeros(num_classes, dtype=np.uint8)
+    for c in range(num_classes):
+        lut[c] = next(i for i, combo in enumerate(full) if c in combo)
+    return lut
+
+
+class CombineLabels(object):
+    """transform.py:366-384: merge label indices (a lookup table on numpy arrays and CUDA tensors alike)."""
+
+    def __init__(self, combinations, num_classes):
+        self.combinations, self.num_classes = combinations, num_classes
+        self.lut = combination_lut(combinations, num_classes)
+
+    def __call__(self, case):
+        lab = case['label']
+        if isinstance(lab, torch.Tensor):
+            case['label'] = torch.from_numpy(self.lut).to(lab.device)[lab.long()].to(lab.dtype)
+        else:
+            case['label'] = self.lut[lab].astype(lab.dtype)
+        return case
+
+
+class ToOnehot(object):
+    """transform.py:304-320: label (d1, .., dn) -> one-hot (d1, .., dn, class), or (class, d1, .., dn) with to_tensor."""
+
+    def __init__(self, num_classes, to_tensor=False):
+        self.num_classes, self.to_tensor = num_classes, to_tensor
+
+    def __call__(self, case):
+        lab = case['label']
+        if isinstance(lab, torch.Tensor):
+            oh = (lab.long().unsqueeze(-1) == torch.arange(self.num_classes, device=lab.device)).to(lab.dtype)
+            case['label'] = oh.permute(lab.dim(), *range(lab.dim())).contiguous() if self.to_tensor else oh
+        else:
+            oh = (lab[..., None] == np.arange(self.num_classes)).astype(lab.dtype)
+            case['label'] = np.ascontiguousarray(np.moveaxis(oh, -1, 0)) if self.to_tensor else oh
+        return case
+
+
 class ToTensor(object):
     """transform.py:156-163: (X, Y, Z, C) -> (C, X, Y, Z) (a contiguous device tensor here)."""
 

@@ -423,12 +423,22 @@ def main():
     # dominant kernel: conv_gemm (forward + data-gradient launches) -- algorithmic FLOPs / CUDA-event time
     roof = None
     if rank == 0 and prof:
-        by, mem = {}, {}
+        by, mem, big = {}, {}, {}
         for name, flops, a, b, nbytes in prof:
             d = (by if flops > 0 else mem).setdefault(name, [0.0, 0.0, 0])
             d[0] += flops if flops > 0 else nbytes
             d[1] += a.elapsed_time(b)
             d[2] += 1
+            if flops <= 0:
+                big.setdefault(name, []).append((nbytes, a.elapsed_time(b)))
+        # the same kernels on their LARGEST tensors only (level 0: 2 x 128^3 x 30 channels): the per-step mean above also
+        # holds the 1-16 MB tensors of levels 2-4, which are launch-latency-bound whatever the kernel does
+        largest = {}
+        for name, rows in big.items():
+            top = max(r[0] for r in rows)
+            sel = [r for r in rows if r[0] >= 0.9 * top]
+            tb, tt = sum(r[0] for r in sel), sum(r[1] for r in sel)
+            largest[name] = (len(sel) // K, tb / (tt * 1e-3) / 1e9 if tt > 0 else None)
         peak, hbm, src = read_peaks()
         name = max(by, key=lambda k: by[k][1])
         fl, tms, cnt = by[name]
@@ -450,7 +460,10 @@ def main():
                 "hbm_peak_gbs": hbm,
                 "hbm_kernels": {k: {"launches_per_step": v[2] // K, "ms_per_step": round(v[1] / K, 4),
                                     "gbs": round(v[0] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None,
-                                    "frac": round(v[0] / (v[1] * 1e-3) / 1e9 / hbm, 3) if v[1] > 0 else None}
+                                    "frac": round(v[0] / (v[1] * 1e-3) / 1e9 / hbm, 3) if v[1] > 0 else None,
+                                    "largest_tensor_launches_per_step": largest[k][0],
+                                    "largest_tensor_gbs": round(largest[k][1], 1) if largest[k][1] else None,
+                                    "largest_tensor_frac": round(largest[k][1] / hbm, 3) if largest[k][1] else None}
                                 for k, v in sorted(mem.items(), key=lambda kv: -kv[1][1])}}
 
     # ---- context measurements (extra keys; not part of `value`): the other 16-bit storage format, BASELINE.json's cfg-3

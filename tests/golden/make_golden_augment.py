@@ -61,6 +61,11 @@ def main():
         img_e, lab_e = run(s, [RT.RandomRescaleCrop(0.2, (12, 12, 12), crop_mode='random', enforce_label_indices=[2]),
                                RT.RandomMirror(0.5)])
         out[f"e{s}/image"], out[f"e{s}/label"] = img_e, lab_e
+    # label re-coding (transform.py:323-384), as nb_train_* scripts use it
+    out["combine_12"] = RT.combination_labels(label.copy(), [[1, 2]], 3)
+    out["combine_01"] = RT.combination_labels(label.copy(), [0, 1], 3)
+    out["onehot"] = RT.to_one_hot(label[:6, :5, :4].copy(), 3)
+    out["onehot_t"] = RT.to_one_hot(label[:6, :5, :4].copy(), 3, to_tensor=True)
     np.savez_compressed(os.path.join(HERE, "augment.npz"), **out)
     print("wrote augment.npz:", {k: v.shape for k, v in out.items() if k.startswith("s0") or k.startswith("e0")})
 

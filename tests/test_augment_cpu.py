@@ -78,3 +78,16 @@ def test_pairwise_leaf_table_reproduces_numpy_sum():
         total = tree([leaf(a[off[i]:off[i + 1]]) for i in range(off.size - 1)], n)
         assert total == a.sum()
         assert f32(total / f32(n)) == a.mean()
+
+
+def test_label_recoding_matches_reference(golden_dir):
+    """CombineLabels / ToOnehot (transform.py:304-384) on numpy labels against the live reference's outputs."""
+    z = _z(golden_dir)
+    G = unet3d_b200.augment
+    lab = z["label"]
+    assert np.array_equal(G.CombineLabels([[1, 2]], 3)({"label": lab.copy()})["label"], z["combine_12"])
+    assert np.array_equal(G.CombineLabels([0, 1], 3)({"label": lab.copy()})["label"], z["combine_01"])
+    small = lab[:6, :5, :4].copy()
+    a = G.ToOnehot(3)({"label": small.copy()})["label"]
+    b = G.ToOnehot(3, to_tensor=True)({"label": small.copy()})["label"]
+    assert a.dtype == z["onehot"].dtype and np.array_equal(a, z["onehot"]) and np.array_equal(b, z["onehot_t"])

@@ -932,9 +932,11 @@ __device__ __forceinline__ void softmax_k(const float (&z)[KMAX], int K, float (
 template <int KMAX>
 __global__ void loss_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                 double* __restrict__ sums /*[K][4]*/, int K, int N, long long V, float gamma) {
-  __shared__ float red[KMAX * 4];
-  for (int i = threadIdx.x; i < KMAX * 4; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
+  // Reproducible sums: fixed per-thread order, shuffle tree, then the warps' partials are added in warp order in fp64;
+  // only the cross-block fp64 atomics are unordered (1e-16 relative, invisible after the fp32 rounding of coef).  A
+  // float atomic here made dlogits differ in the last bit from run to run, and the 16-bit backward chain re-rounds
+  // that into ~0.5 % of the level-0 gradients (profiles/r02_notes.md, "run-to-run reproducibility").
+  __shared__ float red[32][KMAX * 4];
   float tp[KMAX], sp[KMAX], sg[KMAX], fo[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) tp[k] = sp[k] = sg[k] = fo[k] = 0.f;
@@ -973,14 +975,20 @@ __global__ void loss_fwd_kernel(const float* __restrict__ logits, const long lon
       d += __shfl_xor_sync(0xffffffffu, d, o);
     }
     if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&red[k * 4 + 0], a);
-      atomicAdd(&red[k * 4 + 1], b);
-      atomicAdd(&red[k * 4 + 2], c);
-      atomicAdd(&red[k * 4 + 3], d);
+      float* r = red[threadIdx.x >> 5];
+      r[k * 4 + 0] = a;
+      r[k * 4 + 1] = b;
+      r[k * 4 + 2] = c;
+      r[k * 4 + 3] = d;
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < K * 4; i += blockDim.x) atomicAdd(&sums[i], (double)red[i]);
+  const int warps = (blockDim.x + 31) >> 5;
+  for (int i = threadIdx.x; i < K * 4; i += blockDim.x) {
+    double t = 0.0;
+    for (int w = 0; w < warps; ++w) t += (double)red[w][i];
+    atomicAdd(&sums[i], t);
+  }
 }
 
 // coef[k] = { a_k = dL/dTP_k, b_k = dL/dSP_k, f_k = w_k * K / (N V) (focal weight), unused };

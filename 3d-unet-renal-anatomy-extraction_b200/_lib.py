@@ -61,6 +61,7 @@ _SIGS = {
     "unet3d_in_apply": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "unet3d_in_bwd_reduce": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "unet3d_in_bwd_apply": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 7 + [C.c_void_p]),
+    "unet3d_in_bwd_small": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "unet3d_channel_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "unet3d_stem_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "unet3d_stem_wgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),

@@ -192,6 +192,12 @@ int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* tab
                             act_f16, num_sms(), (cudaStream_t)stream),
                "in_bwd_apply");
 }
+int unet3d_in_bwd_small(const void* dout, const void* dout2, const void* out, const void* y, void* g, void* dy,
+                        const float* table, double* sums, int N, long long V, int Cp, int act_f16, void* stream) {
+  return check(in_bwd_small((const bf16*)dout, (const bf16*)dout2, (const bf16*)out, (const bf16*)y, (bf16*)g, (bf16*)dy, table,
+                            sums, N, V, Cp, act_f16, num_sms(), (cudaStream_t)stream),
+               "in_bwd_small");
+}
 int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* stream) {
   return check(channel_sum((const bf16*)x, dsum, NV, Cp, num_sms(), (cudaStream_t)stream), "channel_sum");
 }

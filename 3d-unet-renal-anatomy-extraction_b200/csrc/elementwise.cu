@@ -5,6 +5,7 @@
 // vectors); one thread owns one 8-channel vector, threads of a block tile (channel chunk, voxel) so
 // every warp access is a run of consecutive 16-byte words.
 #include "kernels.cuh"
+#include <cooperative_groups.h>
 
 namespace u3d {
 
@@ -280,6 +281,155 @@ __global__ void __launch_bounds__(256, 2) in_bwd_apply_kernel(const uint4* __res
       float a = 0.f;
       for (int r = 0; r < (int)blockDim.y; ++r) a += red[(size_t)r * C8 + i];
       atomicAdd(&dsum[i], (double)a);
+    }
+  }
+}
+
+// Both backward passes of an InstanceNorm in ONE launch, for tensors whose per-sample slice is small (levels 2-4 of the
+// default net: 0.5-8 MB).  A thread-block CLUSTER owns one 8-channel chunk of one sample: its CTAs split the voxels,
+// reduce locally, exchange the partial sums through distributed shared memory (added in rank order: reproducible, no
+// atomics), then apply from L2-resident data.  The two-kernel path costs two launches of 10-20 us each there
+// (latency-bound, 0.8-2.4 TB/s); a first single-CTA version of this kernel was no faster than the pair (21 us at level
+// 3: 30-60 CTAs each walking 4096 voxels serially) -- the cluster is what shortens the per-thread chain to 1-4 trips.
+// g == nullptr (only with out == nullptr, dout2 == nullptr): the activation gradient is recomputed in pass 2.
+template <bool HAS_D2>
+__global__ void __launch_bounds__(256) in_bwd_small_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2,
+                                   const uint4* __restrict__ out, const uint4* __restrict__ y, uint4* __restrict__ g,
+                                   uint4* __restrict__ dy, const float2* __restrict__ table, double* __restrict__ sums,
+                                   int chunks, int V, int Cp, double inv_count, int af) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int KC = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+  extern __shared__ float red[];   // [blockDim.x][8][2]
+  __shared__ float part[16];       // this CTA's partial sums: read by every CTA of the cluster
+  __shared__ double tot[16];
+  const int n = blockIdx.y;
+  const int ch = blockIdx.x / KC;
+  const int T = blockDim.x;
+  float mean[8], scale[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 t = table[(size_t)n * Cp + ch * 8 + j];
+    mean[j] = t.x;
+    scale[j] = t.y;
+    s1[j] = 0.f;
+    s2[j] = 0.f;
+  }
+  constexpr int RU = HAS_D2 ? 2 : IN_U;
+  const size_t base = (size_t)n * V * chunks;
+  const int v0 = crank * T + threadIdx.x, vstep = KC * T;
+  for (int v = v0; v < V; v += vstep * RU) {
+    uint4 rd[RU], rd2[RU], ro[RU], ry[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int vv = v + u * vstep;
+      if (vv < V) {
+        const size_t idx = base + (size_t)vv * chunks + ch;
+        rd[u] = dout[idx];
+        if (HAS_D2) rd2[u] = dout2[idx];
+        ry[u] = y[idx];
+        if (out != nullptr) ro[u] = out[idx];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int vv = v + u * vstep;
+      if (vv >= V) break;
+      float d[8], o[8], yy[8];
+      unpack8(rd[u], d, af);
+      if (HAS_D2) {
+        float d2[8];
+        unpack8(rd2[u], d2, af);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += d2[j];
+      }
+      unpack8(ry[u], yy, af);
+      if (out != nullptr) {
+        unpack8(ro[u], o, af);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (yy[j] - mean[j]) * scale[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : LRELU * d[j];
+      if (g != nullptr) {
+        const uint4 gp = pack8(d, af);
+        g[base + (size_t)vv * chunks + ch] = gp;     // re-read by this same thread in pass 2
+        unpack8(gp, d, af);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float yh = (yy[j] - mean[j]) * scale[j];
+        s1[j] += d[j];
+        s2[j] += d[j] * yh;
+      }
+    }
+  }
+  // warp tree, then the warps' partials in warp order, then the CTAs' partials in rank order
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+    }
+  }
+  const int warp = threadIdx.x >> 5, nwarps = T >> 5;
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[warp * 16 + 2 * j] = s1[j];
+      red[warp * 16 + 2 * j + 1] = s2[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float acc = 0.f;
+    for (int w = 0; w < nwarps; ++w) acc += red[w * 16 + threadIdx.x];
+    part[threadIdx.x] = acc;
+  }
+  cluster.sync();
+  if (threadIdx.x < 16) {
+    float acc = 0.f;
+    for (int r = 0; r < KC; ++r) acc += *cluster.map_shared_rank(&part[threadIdx.x], r);
+    tot[threadIdx.x] = (double)acc;
+    if (crank == 0) sums[((size_t)n * Cp + (size_t)ch * 8) * 2 + threadIdx.x] = (double)acc;
+  }
+  cluster.sync();      // no CTA leaves (or its `part` dies) while a peer still reads it; publishes `tot` to the block
+  // pass 2: dy = scale * (g - mean(g) - yhat * mean(g * yhat)) = g * A + y * B + C
+  float ca[8], cb[8], cc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float mg = (float)(tot[2 * j] * inv_count), mgy = (float)(tot[2 * j + 1] * inv_count);
+    ca[j] = scale[j];
+    cb[j] = -scale[j] * scale[j] * mgy;
+    cc[j] = -scale[j] * mg + scale[j] * scale[j] * mgy * mean[j];
+  }
+  for (int v = v0; v < V; v += vstep * IN_U) {
+    uint4 rg[IN_U], ry[IN_U];
+#pragma unroll
+    for (int u = 0; u < IN_U; ++u) {
+      const int vv = v + u * vstep;
+      if (vv < V) {
+        const size_t idx = base + (size_t)vv * chunks + ch;
+        rg[u] = g != nullptr ? g[idx] : dout[idx];
+        ry[u] = y[idx];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < IN_U; ++u) {
+      const int vv = v + u * vstep;
+      if (vv >= V) break;
+      float gg[8], yy[8];
+      unpack8(rg[u], gg, af);
+      unpack8(ry[u], yy, af);
+      if (g == nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gg[j] = (yy[j] - mean[j]) * ca[j] > 0.f ? gg[j] : LRELU * gg[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gg[j] = fmaf(gg[j], ca[j], fmaf(yy[j], cb[j], cc[j]));
+      dy[base + (size_t)vv * chunks + ch] = pack8(gg, af);
     }
   }
 }
@@ -1500,6 +1650,36 @@ int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, con
   else U3D_BWD_APPLY(false, false);
 #undef U3D_BWD_APPLY
   return U3D_CHECK_LAUNCH();
+}
+
+int in_bwd_small(const bf16* dout, const bf16* dout2, const bf16* out, const bf16* y, bf16* g, bf16* dy, const float* table,
+                 double* sums, int N, long long V, int Cp, int af, int num_sms, cudaStream_t s) {
+  if (Cp % 8 || V < 1 || V > (1 << 24)) return U3D_ERR_INVALID;
+  if (g == nullptr && (out != nullptr || dout2 != nullptr)) return U3D_ERR_INVALID;
+  const int chunks = Cp / 8, T = 256;
+  // cluster size: enough CTAs to cover the SMs, at most 8 (the portable limit), at least one voxel row per CTA
+  int kc = 1;
+  while (kc < 8 && (long long)chunks * N * kc < num_sms && (long long)2 * kc * T <= V) kc *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(chunks * kc, N);
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = (T / 32) * 16 * sizeof(float);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kc;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const uint4 *pd = (const uint4*)dout, *pd2 = (const uint4*)dout2, *po = (const uint4*)out, *py = (const uint4*)y;
+  uint4 *pg = (uint4*)g, *pdy = (uint4*)dy;
+  const float2* pt = (const float2*)table;
+  const int Vi = (int)V;
+  const double inv = 1.0 / (double)V;
+  cudaError_t e = dout2 ? cudaLaunchKernelEx(&cfg, in_bwd_small_kernel<true>, pd, pd2, po, py, pg, pdy, pt, sums, chunks, Vi, Cp, inv, af)
+                        : cudaLaunchKernelEx(&cfg, in_bwd_small_kernel<false>, pd, pd2, po, py, pg, pdy, pt, sums, chunks, Vi, Cp, inv, af);
+  return e == cudaSuccess ? U3D_CHECK_LAUNCH() : U3D_ERR_CUDA;
 }
 
 int channel_sum(const bf16* x, double* dsum, long long NV, int Cp, int num_sms, cudaStream_t s) {

@@ -12,6 +12,8 @@ int in_bwd_reduce(const bf16* dout, const bf16* dout2, const bf16* out, const bf
                   const float* shift, double* sums, int N, long long V, int Cp, int af, int num_sms, cudaStream_t s);
 int in_bwd_apply(const bf16* g, const bf16* y, bf16* dy, const float* table, const double* sums, const float* coef,
                  double* dsum, int N, int D, int H, int W, int Cp, int zero_last, int af, int num_sms, cudaStream_t s);
+int in_bwd_small(const bf16* dout, const bf16* dout2, const bf16* out, const bf16* y, bf16* g, bf16* dy, const float* table,
+                 double* sums, int N, long long V, int Cp, int af, int num_sms, cudaStream_t s);
 int channel_sum(const bf16* x, double* dsum, long long NV, int Cp, int num_sms, cudaStream_t s);
 int stem_fwd(const float* x, const float* w, const float* b, bf16* out, int N, int Cin, int D, int H, int W, int Cp,
              int af, int num_sms, cudaStream_t s);

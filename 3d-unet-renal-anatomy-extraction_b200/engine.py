@@ -36,6 +36,12 @@ import os as _os
 # What stays exposed (~0.85 ms at 8 GPUs) is SM contention: NCCL's CTAs cannot share an SM with the 227 KB tensor CTAs.
 CHUNK_SPLIT_FRACTIONS = tuple(float(v) for v in _os.environ.get("U3D_CHUNK_SPLIT", "0.72,0.97").split(","))
 PACK_SYNC_LAYERS = 5   # weight packs made on the main stream at the start of a pass; the rest overlaps the first layers
+# InstanceNorm backward of a tensor whose per-sample slice is at most this many bytes runs as ONE cluster kernel instead of
+# the reduce + apply pair (levels 3-4 of the default net at 128^3: 2 MB / 0.5 MB per sample); 0 = always the pair.
+# Measured (profiles/r02_notes.md): level 4 10.7-12.2 us vs ~20 for the pair, level 3 15.4-16.8 vs ~27, level 2 (8 MB)
+# 38-55 vs ~37 -- hence the 2 MB default; 20 launches fewer per step, ~0.1 ms of kernel time, within the noise of the
+# graph-replayed step (these launches are latency chains either way).  U3D_IN_BWD_SMALL overrides.
+IN_BWD_SMALL_BYTES = int(_os.environ.get("U3D_IN_BWD_SMALL", str(2 << 20)))
 
 
 class _ConvOp:
@@ -317,6 +323,11 @@ class UNetEngine:
         sums = self._z64(n, cp, 2)
         dy = self._grad_like(y)
         dsum = self._z64(cp) if want_dsum else None
+        if IN_BWD_SMALL_BYTES and not zero_last and not want_dsum and y[0].numel() * 2 <= IN_BWD_SMALL_BYTES:
+            # levels 3-4: one launch for both passes (each of the two kernels is launch- / latency-bound there)
+            g = None if (out is None and dout2 is None and self.capture is None) else self._grad_like(y)
+            ops.in_bwd_small(dout, dout2, out, y, g, dy, table, sums)
+            return g, dy, sums, dsum
         if out is None and dout2 is None and self.capture is None:
             # norm without residual input: g = dout * lrelu'(y_hat) is needed by nobody else, so pass 1 only reduces and
             # pass 2 recomputes it from dout (2 bytes per element less to write, 16-bit round trip of g avoided)

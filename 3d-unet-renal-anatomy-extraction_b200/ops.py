@@ -377,6 +377,19 @@ def in_bwd_apply(g, y, dy, table, sums, dsum=None, zero_last=False, coef=None, g
                    "unet3d_in_bwd_apply")
 
 
+def in_bwd_small(dout, dout2, out, y, g, dy, table, sums):
+    """Both backward passes of an InstanceNorm in one launch (small per-sample slices); `sums` is written."""
+    n, d, h, w, cp = y.shape
+    _count()
+    assert dout.dtype == y.dtype and dy.dtype == y.dtype and (g is None or g.dtype == y.dtype)
+    assert g is not None or (out is None and dout2 is None)
+    with _Timed("in_bwd_small", 0.0, _alg_numel(y) * 2.0 * (3 + (dout2 is not None) + (out is not None) + (g is not None)),
+                f"{tuple(y.shape)} d2{int(dout2 is not None)} out{int(out is not None)} g{int(g is not None)}"):
+        _lib.check(_lib.lib().unet3d_in_bwd_small(dout.data_ptr(), _ptr(dout2), _ptr(out), y.data_ptr(), _ptr(g), dy.data_ptr(),
+                                                  table.data_ptr(), sums.data_ptr(), n, d * h * w, cp, _f16(y), _stream()),
+                   "unet3d_in_bwd_small")
+
+
 def channel_sum(x: torch.Tensor, dsum: torch.Tensor):
     n, d, h, w, cp = x.shape
     _count()

@@ -154,6 +154,12 @@ int unet3d_in_bwd_reduce(const void* dout, const void* dout2, const void* out, c
 int unet3d_in_bwd_apply(const void* g, const void* y, void* dy, const float* table, const double* sums,
                         const float* coef, double* dsum, int N, int D, int H, int W, int Cp, int zero_last, int act_f16,
                         void* stream);
+/* in_bwd_reduce + in_bwd_apply of an InstanceNorm (no pad planes, no bias sum) in ONE launch, for small per-sample
+ * slices (V * Cp of a few MB: levels 3-4 of the default net): `sums` ([N][Cp][2] fp64) is WRITTEN, not accumulated.
+ * g may be NULL only when out and dout2 are NULL (the activation gradient is then recomputed, as with flag bit 1 above).
+ * Same arithmetic as the two-kernel path up to the summation order of the fp32 partial sums. */
+int unet3d_in_bwd_small(const void* dout, const void* dout2, const void* out, const void* y, void* g, void* dy,
+                        const float* table, double* sums, int N, long long V, int Cp, int act_f16, void* stream);
 int unet3d_channel_sum(const void* x, double* dsum, long long NV, int Cp, void* stream);
 
 /* Stem Conv3d(Cin->C,k3,p1)+bias, fp32 NCDHW in -> bf16 NDHWC out (network.py:541,550); w fp32 [Cin][27][Cp].

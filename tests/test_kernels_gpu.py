@@ -234,6 +234,53 @@ def test_instance_norm_fwd_bwd():
     assert rel(from_ndhwc(dy, C), y.grad) < 2e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C,dims", [(240, (16, 16, 16)), (480, (8, 8, 8)), (30, (5, 6, 7)), (8, (3, 3, 3))])
+def test_instance_norm_bwd_one_launch(C, dims, dtype):
+    """in_bwd_small (levels 3-4: both backward passes in one launch) against the reduce + apply pair on the same tensors,
+    in its three uses: first norm of a block (g recomputed), second norm (residual, g written), encoder output (two
+    upstream gradients).  g is bit-identical; the sums differ only by the fp32 partial-sum order, dy by an occasional
+    16-bit rounding flip."""
+    torch.manual_seed(11)
+    N = 2
+    cp = P.pad_channels(C)
+    shape = (N, *dims, cp)
+    V = dims[0] * dims[1] * dims[2]
+    y = (torch.randn(shape, device=DEV) * 2 + 0.5).to(dtype)
+    y[..., C:] = 0
+    skip = torch.randn(shape, device=DEV).to(dtype)
+    dout = torch.randn(shape, device=DEV).to(dtype)
+    dout2 = torch.randn(shape, device=DEV).to(dtype)
+    yf = y.float()
+    stats = torch.zeros(N, cp, 2, device=DEV, dtype=torch.float64)
+    stats[..., 0] = yf.sum(dim=(1, 2, 3)); stats[..., 1] = (yf * yf).sum(dim=(1, 2, 3))
+    table = torch.empty(N, cp, 2, device=DEV)
+    ops.in_finalize(stats, None, table, V)
+    out = torch.empty_like(y)
+    ops.in_apply(y, skip, out, table)
+    for d2, o, want_g in ((None, None, False), (None, out, True), (dout2, out, True), (dout2, None, True)):
+        g_ref = torch.empty_like(y) if want_g else None
+        dy_ref = torch.empty_like(y)
+        sums_ref = torch.zeros(N, cp, 2, device=DEV, dtype=torch.float64)
+        ops.in_bwd_reduce(dout, d2, o, y, g_ref, table, sums_ref)
+        if want_g:
+            ops.in_bwd_apply(g_ref, y, dy_ref, table, sums_ref)
+        else:
+            ops.in_bwd_apply(dout, y, dy_ref, table, sums_ref, g_is_dout=True)
+        g = torch.full_like(y, float("nan")) if want_g else None
+        dy = torch.full_like(y, float("nan"))
+        sums = torch.full((N, cp, 2), float("nan"), device=DEV, dtype=torch.float64)
+        ops.in_bwd_small(dout, d2, o, y, g, dy, table, sums)
+        torch.cuda.synchronize()
+        ops.check_device_errors()
+        if want_g:
+            assert torch.equal(g, g_ref)
+        scale = sums_ref.abs().amax(dim=(0, 1), keepdim=True)
+        assert float(((sums - sums_ref).abs() / scale).max()) < 1e-5
+        assert not torch.isnan(dy.float()).any()
+        assert rel(dy.float(), dy_ref.float()) < 2e-4, (C, dims, d2 is not None, o is not None)
+
+
 @pytest.mark.parametrize("cin", [1, 2, 3])
 def test_stem_and_head(cin):
     torch.manual_seed(4)

@@ -38,8 +38,8 @@ CHUNK_SPLIT_FRACTIONS = tuple(float(v) for v in _os.environ.get("U3D_CHUNK_SPLIT
 PACK_SYNC_LAYERS = 5   # weight packs made on the main stream at the start of a pass; the rest overlaps the first layers
 # InstanceNorm backward of a tensor whose per-sample slice is at most this many bytes runs as ONE cluster kernel instead of
 # the reduce + apply pair (levels 3-4 of the default net at 128^3: 2 MB / 0.5 MB per sample); 0 = always the pair.
-# Measured (profiles/r02_notes.md): level 4 10.7-12.2 us vs ~20 for the pair, level 3 15.4-16.8 vs ~27, level 2 (8 MB)
-# 38-55 vs ~37 -- hence the 2 MB default; 20 launches fewer per step, ~0.1 ms of kernel time, within the noise of the
+# Measured (profiles/r02_notes.md): level 4 10.7-12.2 us vs 19.2 for the pair, level 3 15.4-16.8 vs 25.5, level 2 (8 MB)
+# 38-55 vs 35 -- hence the 2 MB default; 20 launches fewer per step, ~0.1 ms of kernel time, within the noise of the
 # graph-replayed step (these launches are latency chains either way).  U3D_IN_BWD_SMALL overrides.
 IN_BWD_SMALL_BYTES = int(_os.environ.get("U3D_IN_BWD_SMALL", str(2 << 20)))
 

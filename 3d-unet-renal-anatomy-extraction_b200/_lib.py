@@ -51,6 +51,7 @@ _SIGS = {
     "unet3d_version": (C.c_char_p, []),
     "unet3d_last_error_string": (C.c_char_p, []),
     "unet3d_num_sms": (C.c_int, []),
+    "unet3d_set_sm_limit": (C.c_int, [C.c_int]),
     "unet3d_conv_gemm": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "unet3d_conv_gemm_smem_bytes": (C.c_size_t, [C.c_int] * 7),
     "unet3d_weight_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),

@@ -71,12 +71,18 @@ int encode_src(CUtensorMap* m, const unet3d_src& s, int bw, int bh, int chans = 
 }
 
 int g_num_sms[64] = {};      // per device ordinal (one process may drive several GPUs)
+int g_sm_limit[64] = {};     // unet3d_set_sm_limit: grids are sized for this many SMs while it is > 0
 int num_sms() {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-  if (dev >= 0 && dev < 64 && g_num_sms[dev] > 0) return g_num_sms[dev];
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  if (dev >= 0 && dev < 64) g_num_sms[dev] = n;
+  const bool in_range = dev >= 0 && dev < 64;
+  if (in_range && g_num_sms[dev] > 0) {
+    n = g_num_sms[dev];
+  } else {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (in_range) g_num_sms[dev] = n;
+  }
+  if (in_range && g_sm_limit[dev] > 0 && g_sm_limit[dev] < n) n = g_sm_limit[dev];
   return n;
 }
 
@@ -89,6 +95,12 @@ extern "C" {
 const char* unet3d_version(void) { return "unet3d_b200 0.1 (sm_100a)"; }
 const char* unet3d_last_error_string(void) { return g_err; }
 int unet3d_num_sms(void) { return num_sms(); }
+int unet3d_set_sm_limit(int limit) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || limit < 0) return fail(U3D_ERR_INVALID, "set_sm_limit%s");
+  g_sm_limit[dev] = limit;
+  return U3D_OK;
+}
 
 size_t unet3d_conv_gemm_smem_bytes(int Dt, int G, int nblk, int fuse, int wT, int w_stages, int a_stages) {
   return conv_gemm_smem_bytes(Dt, G, nblk, fuse, wT, w_stages, a_stages);

@@ -41,6 +41,13 @@ PACK_SYNC_LAYERS = 5   # weight packs made on the main stream at the start of a 
 # Measured (profiles/r02_notes.md): level 4 10.7-12.2 us vs 19.2 for the pair, level 3 15.4-16.8 vs 25.5, level 2 (8 MB)
 # 38-55 vs 35 -- hence the 2 MB default; 20 launches fewer per step, ~0.1 ms of kernel time, within the noise of the
 # graph-replayed step (these launches are latency chains either way).  U3D_IN_BWD_SMALL overrides.
+# Library launches after each overlapped all-reduce chunk whose grids leave NCCL_MAX_CTAS SMs to NCCL (ops.set_sm_limit):
+# the persistent GEMM kernels assign tiles to their 148 CTAs statically, so with 16 SMs taken by NCCL the 16 CTAs that
+# wait for an SM start when the first ones exit and the launch takes up to twice as long; sized for 132 SMs it takes
+# 12 % longer.  Needs NCCL_MAX_CTAS in the environment (bench.py sets 16); "0" = off.  Measured, one step of cfg-2
+# (profiles/r02_sm_limit_window.json): 2 B200s 19.26 (off) / 19.20 (20,4) / 19.10 (40,8) / 19.19 (80,16) ms;
+# 8 B200s 19.44 (off) / 19.25 (48,10) ms against 18.63 ms on one.
+NCCL_WINDOW = tuple(int(v) for v in _os.environ.get("U3D_NCCL_WINDOW", "48,10").split(","))
 IN_BWD_SMALL_BYTES = int(_os.environ.get("U3D_IN_BWD_SMALL", str(2 << 20)))
 
 
@@ -400,10 +407,15 @@ class UNetEngine:
                 _, g0, g1, table = self._chunks[self._chunk_next]
                 table.launch(scale=self._unpack_scale(), out_base=self._gflat)
                 self._chunk_handles.append((self._gflat[g0:g1], self.grad_chunk_hook(self._gflat[g0:g1])))
+                window = NCCL_WINDOW[min(self._chunk_next, len(NCCL_WINDOW) - 1)]
+                nccl_ctas = int(_os.environ.get("NCCL_MAX_CTAS", "0"))
+                if window > 0 and nccl_ctas > 0 and self._chunk_handles[-1][1] is not None:
+                    ops.set_sm_limit(ops.num_sms() - nccl_ctas, window)
                 self._chunk_next += 1
 
     def _finish_wgrads(self):
         self._last_gflat = None
+        ops.set_sm_limit(0)
         if self._dw_ready:
             if self.grad_chunk_hook is not None and len(self._chunks) > 1:
                 # chunks whose hook has not fired yet (normally only the last one) are unpacked now, un-sent

@@ -42,9 +42,39 @@ def _alg_numel(t: torch.Tensor) -> float:
     return t.numel() * (REAL_CHANNELS.get(cp, cp) / float(cp))
 
 
+SM_LIMIT = 0            # > 0: grids are being sized for this many SMs (set_sm_limit), until LAUNCHES reaches _SM_LIMIT_UNTIL
+_SM_LIMIT_UNTIL = 0
+
+
+_NUM_SMS = {}
+
+
+def num_sms() -> int:
+    """SM count of the current device (not the set_sm_limit value)."""
+    dev = torch.cuda.current_device()
+    if dev not in _NUM_SMS:
+        if SM_LIMIT:
+            set_sm_limit(0)
+        _NUM_SMS[dev] = int(_lib.lib().unet3d_num_sms())
+    return _NUM_SMS[dev]
+
+
+def set_sm_limit(limit: int, launches: int = 0):
+    """Size the grids of the next `launches` library launches (current device) for `limit` SMs; 0 = back to all SMs.
+    Used while a gradient all-reduce overlaps the backward pass: NCCL's CTAs occupy SMs the persistent GEMM kernels
+    (one 227 KB CTA per SM, tiles assigned statically) would otherwise wait for."""
+    global SM_LIMIT, _SM_LIMIT_UNTIL
+    limit = int(limit) if launches > 0 else 0
+    if limit != SM_LIMIT:
+        _lib.check(_lib.lib().unet3d_set_sm_limit(limit), "unet3d_set_sm_limit")
+    SM_LIMIT, _SM_LIMIT_UNTIL = limit, LAUNCHES + int(launches)
+
+
 def _count(n: int = 1):
     global LAUNCHES
     LAUNCHES += n
+    if SM_LIMIT and LAUNCHES > _SM_LIMIT_UNTIL:
+        set_sm_limit(0)
 
 
 class _Timed:
@@ -324,14 +354,17 @@ def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor
         a.box_w[i], a.box_h[i], a.box_c[i] = bw, bh, bc
     a.tab, a.dw, a.err = dp.tab.data_ptr(), dw.data_ptr(), err_word(dw.device).data_ptr()
     a.N, a.D, a.H, a.W = grid
-    a.n_jobs, a.job_stride, a.split = pl.n_jobs, pl.job_stride, pl.split
+    _count()
+    split = pl.split
+    if SM_LIMIT and pl.n_jobs <= SM_LIMIT < pl.n_jobs * split:
+        split = SM_LIMIT // pl.n_jobs            # jobs x split CTAs, one per SM: fit the SMs NCCL leaves
+    a.n_jobs, a.job_stride, a.split = pl.n_jobs, pl.job_stride, split
     a.x_f16 = _f16(xs[0])
     assert all(x.dtype == dy.dtype for x in xs)        # one MMA cannot mix fp16 and bf16 operands
     assert dw.dtype == torch.float32 and dw.numel() >= pl.dw_numel
-    _count()
     with _Timed("wgrad_gemm_kernel", pl.flops_per_voxel * grid[0] * grid[1] * grid[2] * grid[3], 0.0,
                 lambda: f"{pl.kind} x{[tuple(x.shape[1:]) for x in xs]} dy{tuple(dy.shape[1:])} grid{tuple(grid)} jobs{pl.n_jobs} "
-                        f"split{pl.split} wx{pl.wx} wy{pl.wy} dt{[j['dt'] for j in pl.jobs][:3]} ent{[len(j['units']) for j in pl.jobs][:4]}"):
+                        f"split{split} wx{pl.wx} wy{pl.wy} dt{[j['dt'] for j in pl.jobs][:3]} ent{[len(j['units']) for j in pl.jobs][:4]}"):
         _lib.check(_lib.lib().unet3d_wgrad_gemm(C.byref(a), _stream()), "unet3d_wgrad_gemm")
 
 

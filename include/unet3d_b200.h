@@ -38,6 +38,10 @@ const char* unet3d_version(void);
 const char* unet3d_last_error_string(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int unet3d_num_sms(void);
+/* Size the grids of all later launches on the current device for `limit` SMs (0 = all of them).  The data-parallel step
+ * sets it to (SMs - NCCL_MAX_CTAS) for the launches that run while a gradient all-reduce is in flight: the persistent
+ * GEMM kernels assign tiles to CTAs statically, so a CTA that has to wait for an SM NCCL occupies doubles its launch. */
+int unet3d_set_sm_limit(int limit);
 
 /* One bf16 NDHWC view feeding the A operand of a contraction: a whole tensor, one half of a
  * channel concat (network.py:350 torch.cat -- never materialised), or one stride-2 parity

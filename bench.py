@@ -284,8 +284,9 @@ def main():
         # one-CTA-per-SM tensor kernels: 16-32 CTAs measured best (2 B200s: 32 / 16 / 8 / 4 CTAs -> 19.57 / 19.65 / 20.03 /
         # 20.60 ms; 8 B200s: 19.79 with 16, 19.82 with 32); overridable from the environment
         os.environ.setdefault("NCCL_MAX_CTAS", "16")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # VERSION printf()s a line to stdout: rank 0 must print ONE JSON line
+        # NCCL_DEBUG=VERSION / WARN writes a version banner to NCCL's log file, stdout by default: rank 0's stdout must
+        # carry ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = args.steps

@@ -287,6 +287,8 @@ def main():
         # NCCL_DEBUG=VERSION / WARN writes a version banner to NCCL's log file, stdout by default: rank 0's stdout must
         # carry ONE JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # this image's default: a bare printf to stdout
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = args.steps

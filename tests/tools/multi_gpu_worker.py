@@ -15,6 +15,7 @@ import torch.distributed as dist
 import unet3d_b200
 from unet3d_b200 import parallel
 
+os.environ.setdefault("NCCL_MAX_CTAS", "16")      # as bench.py: also arms the SM-limit window of the overlapped all-reduce
 dist.init_process_group("nccl")
 rank, world = dist.get_rank(), dist.get_world_size()
 dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
@@ -206,7 +207,9 @@ drift = rel(p_graph, p_eager)
 both = [torch.zeros_like(p_graph) for _ in range(world)]
 dist.all_gather(both, p_graph)
 same_ranks = all(torch.equal(both[0], b) for b in both[1:])
+from unet3d_b200 import engine as _eng
 if rank == 0:
+    print(f"SM-limit window {_eng.NCCL_WINDOW} with NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS')}")
     print(f"GraphedTrainStep ({mode}) vs eager data-parallel steps: worst per-tensor GRADIENT rel-L2 {gerrs[0][0]:.2e} ({gerrs[0][1]}; "
           f"|graph| / |eager| = {float(g_graph[gerrs[0][1]].norm() / g_eager[gerrs[0][1]].norm()):.6f}); 7 Adam steps: parameter "
           f"rel-L2 {drift:.2e} (two eager runs: {rel(p_eager2, p_eager):.2e}), last loss {l_graph[-1]:.6f} vs {l_eager[-1]:.6f}, identical parameters on all ranks {same_ranks}")

@@ -383,6 +383,80 @@ class ToOnehot(object):
         return case
 
 
+def to_tensor(input):
+    """transform.py:144-147: (d1, .., dn, class) -> (class, d1, .., dn) as a view (numpy or torch)."""
+    n = input.dim() if isinstance(input, torch.Tensor) else input.ndim
+    order = (n - 1, *range(n - 1))
+    return input.permute(*order) if isinstance(input, torch.Tensor) else input.transpose(order)
+
+
+def to_numpy(input):
+    """transform.py:150-153: (class, d1, .., dn) -> (d1, .., dn, class) as a view (numpy or torch)."""
+    n = input.dim() if isinstance(input, torch.Tensor) else input.ndim
+    order = (*range(1, n), 0)
+    return input.permute(*order) if isinstance(input, torch.Tensor) else input.transpose(order)
+
+
+def to_one_hot(input, num_classes, to_tensor=False):
+    """transform.py:262-276: label (d1, .., dn) -> one-hot (d1, .., dn, class) or (class, d1, .., dn), in the label's dtype."""
+    return ToOnehot(num_classes, to_tensor)({'label': input})['label']
+
+
+class ToNumpy(object):
+    """transform.py:166-173: (C, X, Y, Z) -> (X, Y, Z, C)."""
+
+    def __call__(self, case):
+        img = to_numpy(case['image'])
+        case['image'] = img.contiguous() if isinstance(img, torch.Tensor) else np.ascontiguousarray(img)
+        return case
+
+
+class RemoveSmallRegion(object):
+    """transform.py:14-20."""
+
+    def __init__(self, threshold):
+        self.threshold = threshold
+
+    def __call__(self, case):
+        case['label'] = T.remove_small_region(case['label'], self.threshold)
+        return case
+
+
+class Resize(object):
+    """transform.py:103-118: image (X, Y, Z, C) and label (X, Y, Z) resized to ``shape`` (linear; labels through the
+    per-class zoom + argmax of transform.py:66-74)."""
+
+    def __init__(self, shape):
+        self.shape = shape
+
+    def __call__(self, case):
+        case['image'] = T.resize(case['image'], self.shape)
+        case['label'] = T.resize(case['label'], self.shape, is_label=True)
+        return case
+
+
+class RandomRescale(object):
+    """transform.py:121-141: one np.random.uniform draw, the same isotropic factor for image and label.  The reference
+    passes the scalar factor to ndi.zoom for the 4-D image too, i.e. it also "zooms" the channel axis; for the
+    single-channel images of every reference script that axis stays 1 and its values are unchanged, which is what is
+    built here (spatial axes only); more channels are refused rather than silently resampled differently."""
+
+    def __init__(self, scale):
+        if isinstance(scale, float):
+            assert 0 <= scale <= 1, "If range is a single number, it must be non negative"
+            self.scale = [1 - scale, 1 + scale]
+        else:
+            self.scale = scale
+
+    def __call__(self, case):
+        scale = np.random.uniform(self.scale[0], self.scale[1])
+        if case['image'].shape[-1] != 1:
+            raise NotImplementedError("RandomRescale: single-channel images only (see the docstring)")
+        case['image'] = T.rescale(case['image'], (scale, scale, scale), multi_class=True)
+        case['label'] = T.rescale(case['label'], scale, is_label=True)
+        return case
+
+
 class ToTensor(object):
     """transform.py:156-163: (X, Y, Z, C) -> (C, X, Y, Z) (a contiguous device tensor here)."""
 

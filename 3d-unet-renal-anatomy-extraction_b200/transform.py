@@ -194,6 +194,30 @@ def crop_pad_to_bbox(input, bbox, pad_mode='constant', pad_cval=0):
     return out
 
 
+def remove_small_region(input, threshold):
+    """transform.py:5-11: zero every 6-connected component of the non-zero voxels that has fewer than ``threshold`` voxels
+    (ndi.label + np.bincount + mask there; one ccl_label + ccl_stats pass here).  In place like the reference, for a
+    numpy array or a CUDA tensor (X, Y, Z); returns its argument."""
+    is_np = not isinstance(input, torch.Tensor)
+    t = torch.from_numpy(np.ascontiguousarray(input)).to(_device()) if is_np else input
+    if t.dim() != 3:
+        raise ValueError("remove_small_region takes a (X, Y, Z) label volume")
+    work = t if t.is_contiguous() else t.contiguous()
+    labels, roots, stats = ops.connected_components((work != 0).to(torch.uint8))
+    if roots.numel():
+        flat = labels.view(-1)
+        comp = torch.searchsorted(roots, flat.clamp_min(0)).clamp_max(roots.numel() - 1)    # roots are sorted flat indices
+        small = (flat >= 0) & (stats[:, 0][comp] < threshold)
+        work.view(-1)[small] = 0
+    ops.check_device_errors()
+    if is_np:
+        input[...] = work.cpu().numpy()
+        return input
+    if work is not t:
+        t.copy_(work)
+    return t
+
+
 def component_regions(mask: torch.Tensor, threshold=0):
     """Connected components (6-connectivity) of a boolean / uint8 CUDA volume with at least ``threshold`` voxels, in
     scipy.ndimage.label's order: [(voxels, ((x0, x1), (y0, y1), (z0, z1)))] with half-open boxes (find_objects).

@@ -91,3 +91,21 @@ def test_label_recoding_matches_reference(golden_dir):
     a = G.ToOnehot(3)({"label": small.copy()})["label"]
     b = G.ToOnehot(3, to_tensor=True)({"label": small.copy()})["label"]
     assert a.dtype == z["onehot"].dtype and np.array_equal(a, z["onehot"]) and np.array_equal(b, z["onehot_t"])
+
+
+def test_layout_helpers_match_reference_semantics():
+    """to_tensor / to_numpy / to_one_hot (transform.py:144-153, 262-276) on numpy and torch inputs."""
+    import torch
+    from unet3d_b200 import augment as G
+    rng = np.random.RandomState(0)
+    a = rng.randn(3, 4, 5, 2).astype(np.float32)
+    dims = np.arange(a.ndim)
+    assert np.array_equal(G.to_tensor(a), a.transpose(np.concatenate((dims[-1:], dims[:-1]))))
+    assert np.array_equal(G.to_numpy(G.to_tensor(a)), a)
+    assert torch.equal(G.to_numpy(G.to_tensor(torch.from_numpy(a))), torch.from_numpy(a))
+    lab = rng.randint(0, 4, (3, 4, 5)).astype(np.uint8)
+    want = np.eye(4)[lab]
+    assert np.array_equal(G.to_one_hot(lab, 4), want.astype(np.uint8))
+    assert np.array_equal(G.to_one_hot(lab, 4, to_tensor=True), np.moveaxis(want, -1, 0).astype(np.uint8))
+    case = G.ToNumpy()({"image": np.ascontiguousarray(np.moveaxis(a, -1, 0))})
+    assert np.array_equal(case["image"], a) and case["image"].flags["C_CONTIGUOUS"]

@@ -103,3 +103,46 @@ def test_evaluate_case_matches_reference_dice():
     assert got == want
     got_dev = unet3d_b200.evaluate_case({"pred": torch.from_numpy(pred).cuda(), "label": torch.from_numpy(label).cuda()})
     assert got_dev == want
+
+
+def test_remove_small_region_resize_random_rescale():
+    """The remaining thin transform classes (transform.py:5-20, 103-141, 166-173) against the reference's algorithm
+    restated with scipy on the same inputs: RemoveSmallRegion bit-exact (labels), Resize / RandomRescale within the
+    zoom kernels' parity with scipy.ndimage.zoom (tests/test_resample_gpu.py pins those bit-exactly)."""
+    import scipy.ndimage as ndi
+    rng = np.random.RandomState(3)
+    lab = np.zeros((24, 20, 18), np.uint8)
+    lab[2:9, 3:9, 2:8] = 1            # 252 voxels
+    lab[12:14, 12:14, 10:12] = 2      # 8 voxels
+    lab[14, 12, 10] = 1               # touches the block above: one two-class component of 9 voxels
+    lab[20:22, 2:4, 15:17] = 2        # 8 voxels, separate
+    lab[18, 18, 1] = 1                # 1 voxel
+    for thr in (0, 2, 9, 300):
+        lbl, n = ndi.label(lab)
+        areas = np.bincount(lbl.ravel())
+        want = lab.copy()
+        want[(areas < thr)[lbl]] = 0
+        got_np = G.RemoveSmallRegion(thr)({"label": lab.copy()})["label"]
+        got_dev = G.RemoveSmallRegion(thr)({"label": torch.from_numpy(lab).cuda()})["label"]
+        assert isinstance(got_np, np.ndarray) and got_dev.is_cuda
+        assert np.array_equal(got_np, want), thr
+        assert np.array_equal(got_dev.cpu().numpy(), want), thr
+    img = rng.randn(24, 20, 18, 1).astype(np.float32)
+    case = G.Resize((30, 16, 21))({"image": img.copy(), "label": lab.copy()})
+    zoom = np.array((30, 16, 21)) / np.array(lab.shape)
+    want_img = ndi.zoom(img[..., 0], zoom, order=1, mode="reflect")
+    onehot = np.stack([ndi.zoom((lab == k).astype(np.float32), zoom, order=1, mode="reflect") for k in range(3)])
+    assert case["image"].shape == (30, 16, 21, 1) and case["label"].shape == (30, 16, 21)
+    assert np.abs(case["image"][..., 0] - want_img).max() < 1e-5
+    assert (case["label"] != onehot.argmax(0)).mean() < 1e-3          # ties between classes may fall either way
+    np.random.seed(5)
+    s = np.random.uniform(0.9, 1.1)
+    np.random.seed(5)
+    case = G.RandomRescale(0.1)({"image": img.copy(), "label": lab.copy()})
+    want_img = ndi.zoom(img[..., 0], s, order=1, mode="reflect")
+    assert case["image"].shape == (*want_img.shape, 1) and case["label"].shape == want_img.shape
+    assert np.abs(case["image"][..., 0] - want_img).max() < 1e-5
+    back = G.ToNumpy()(G.ToTensor()({"image": img.copy()}))["image"]
+    assert np.array_equal(back, img)
+    torch.cuda.synchronize()
+    ops.check_device_errors()

@@ -70,6 +70,14 @@ def set_sm_limit(limit: int, launches: int = 0):
     SM_LIMIT, _SM_LIMIT_UNTIL = limit, LAUNCHES + int(launches)
 
 
+def limited_split(n_jobs: int, split: int, limit: int) -> int:
+    """Split-K count of a weight-gradient launch (jobs x split CTAs, one per SM) while only `limit` SMs are free: the
+    largest split that keeps one wave; unchanged without a limit, if it already fits, or if the jobs alone exceed it."""
+    if limit and n_jobs <= limit < n_jobs * split:
+        return limit // n_jobs
+    return split
+
+
 def _count(n: int = 1):
     global LAUNCHES
     LAUNCHES += n
@@ -355,9 +363,7 @@ def wgrad_gemm(dp: DeviceWgradPlan, xs: Sequence[torch.Tensor], dy: torch.Tensor
     a.tab, a.dw, a.err = dp.tab.data_ptr(), dw.data_ptr(), err_word(dw.device).data_ptr()
     a.N, a.D, a.H, a.W = grid
     _count()
-    split = pl.split
-    if SM_LIMIT and pl.n_jobs <= SM_LIMIT < pl.n_jobs * split:
-        split = SM_LIMIT // pl.n_jobs            # jobs x split CTAs, one per SM: fit the SMs NCCL leaves
+    split = limited_split(pl.n_jobs, pl.split, SM_LIMIT)
     a.n_jobs, a.job_stride, a.split = pl.n_jobs, pl.job_stride, split
     a.x_f16 = _f16(xs[0])
     assert all(x.dtype == dy.dtype for x in xs)        # one MMA cannot mix fp16 and bf16 operands

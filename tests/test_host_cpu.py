@@ -251,3 +251,40 @@ def test_checkpoint_loads_without_unrestricted_pickle(tmp_path):
     tr2.load_checkpoint(path, allow_pickle=False)
     assert tr2.current_epoch == 5 and float(tr2.best_result["loss"]) == 0.25
     assert tr2.train_indices == tr.train_indices
+
+
+def test_sm_limit_window_bookkeeping(monkeypatch):
+    """ops.set_sm_limit / _count: the limit set for N launches is dropped by the launch after the N-th; the weight
+    gradient's split-K count is re-derived for the limited SM count (engine.NCCL_WINDOW)."""
+    from unet3d_b200 import ops, _lib
+
+    calls = []
+
+    class _Fake:
+        def unet3d_set_sm_limit(self, limit):
+            calls.append(int(limit))
+            return 0
+
+    monkeypatch.setattr(_lib, "lib", lambda: _Fake())
+    monkeypatch.setattr(ops, "SM_LIMIT", 0)
+    monkeypatch.setattr(ops, "_SM_LIMIT_UNTIL", 0)
+    base = ops.LAUNCHES
+    ops.set_sm_limit(132, 3)
+    assert calls == [132] and ops.SM_LIMIT == 132
+    for _ in range(3):
+        ops._count()
+        assert ops.SM_LIMIT == 132
+    ops._count()                                   # the 4th launch runs on all SMs again
+    assert ops.SM_LIMIT == 0 and calls == [132, 0]
+    ops.set_sm_limit(0)                            # idempotent: no library call
+    ops.set_sm_limit(132, 0)                       # zero launches = off
+    assert calls == [132, 0] and ops.SM_LIMIT == 0
+    monkeypatch.setattr(ops, "LAUNCHES", base)
+    # jobs x split CTAs, one per SM
+    assert ops.limited_split(1, 148, 0) == 148
+    assert ops.limited_split(1, 148, 132) == 132
+    assert ops.limited_split(4, 37, 132) == 33
+    assert ops.limited_split(36, 4, 132) == 3
+    assert ops.limited_split(132, 1, 132) == 1
+    assert ops.limited_split(160, 1, 132) == 1      # more jobs than SMs: several waves either way
+    assert ops.limited_split(9, 14, 132) == 14      # 126 CTAs already fit

@@ -627,6 +627,7 @@ def main():
                 "config": {"workload": WORKLOAD if pe == 128 else f"REDUCED patch {pe}^3 (not the metric's config)",
                            "global_batch": BATCH * world, "patch": [pe, pe, pe], "parallelism": f"dp{world}", "cuda_graph": used_graph, "dp_mode": dp_mode if world > 1 else None,
                            "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS") if world > 1 else None,
+                           "sm_limit_window_launches": list(unet3d_b200.engine.NCCL_WINDOW) if world > 1 else None,
                            "timed_region": "zero_grad + forward + DiceLoss + backward + grad all-reduce (N>1) + Adam step",
                            "l2": "256 MB buffer written between timed iterations (L2 flush); activations per step >> L2",
                            "tensor_frac_of_step": (FWD_BWD_FLOP_PER_VOXEL * BATCH * pe ** 3 / (ms * 1e-3) / 1e12) /
